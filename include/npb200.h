@@ -1,0 +1,164 @@
+/*
+ * npb200.h -- C ABI of libnpb200.so: the B200 (sm_100a) Gibbs-reassignment path for
+ * Dirichlet-process mixtures, drop-in behind the sampler seam of mrquincle/noparama.
+ *
+ * The reference has no FFI: its "operator API" is constructor injection of three C++
+ * interfaces (citations relative to the reference tree):
+ *     UpdateClusterPopulation::update(membertrix&, const data_ids_t&)   include/np_update_cluster_population.h:35-43
+ *     distribution_t::{init, probability, logprobability, operator()}    include/statistics/distribution.h:47-87
+ *     membertrix::{assign, retract, addCluster, getClusterId, count ...} include/membertrix.h:106-290
+ * driven by MCMC::run (src/np_mcmc.cpp:48-175).  Each entry point below names the reference
+ * function(s) it replaces.  Conventions: plain pointers and sizes, no C++/torch types; every
+ * function returns npb_status (0 = OK, negative = error) and never aborts; host buffers are caller
+ * owned and are copied during the call; every *_create pairs with a *_destroy; one context = one
+ * CUDA device and one stream; a context is thread-compatible (one caller at a time).
+ *
+ * There is NO CPU fallback: without a CUDA device npb_ctx_create fails with NPB_E_CUDA.
+ */
+#ifndef NPB200_H
+#define NPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int npb_status;
+enum {
+	NPB_OK = 0,
+	NPB_E_BAD_ARG = -1,
+	NPB_E_CUDA = -2,
+	NPB_E_KMAX_OVERFLOW = -3,     /* a chain needed more than Kmax cluster slots */
+	NPB_E_NOT_POSITIVE = -4,      /* covariance not invertible / precision not positive definite */
+	NPB_E_UNSUPPORTED = -5,
+	NPB_E_REPLAY_MISMATCH = -6,   /* replay picked a different candidate than the recorded trace */
+	NPB_E_NOMEM = -7,
+	/* mirrors of np_error_t (include/membertrix.h:16-23) for the single-item seam */
+	NPB_E_ALREADY_ASSIGNED = -16,
+	NPB_E_ASSIGNMENT_REMAINING = -17,
+	NPB_E_ASSIGNMENT_ABSENT = -18
+};
+
+/* samplers selectable by -a (src/np_main.cpp:212-236, 424-459) */
+enum { NPB_ALG8 = 8, NPB_ALG2 = 2, NPB_JAIN_NEAL = 20, NPB_TRIADIC = 30 };
+
+/* behaviour switches of npb_prior_set_niw; the default (all bug-compatible flags set) reproduces the
+ * reference, quirk numbers refer to SURVEY.md 7.4 */
+enum {
+	NPB_BUGCOMPAT_DEGENERATE_IW = 1 << 0, /* Q2: Sigma = v^2 L^T L with scalar v ~ N(D, nu^2) (invwishart.h:34-46) */
+	NPB_BUGCOMPAT_UNDERFLOW     = 1 << 1, /* Q6: linear-domain double weights underflow to 0; all-zero => first candidate */
+	NPB_BUGCOMPAT_DEFAULT       = NPB_BUGCOMPAT_DEGENERATE_IW
+};
+
+typedef struct npb_ctx npb_ctx;
+typedef struct npb_dataset npb_dataset;
+typedef struct npb_chains npb_chains;
+
+typedef struct npb_sweep_stats {
+	int64_t reassignments;      /* item updates performed = chains * N * sweeps (Alg. 8) */
+	int64_t candidates;         /* sum over updates of (K_i + m): density evaluations that enter a pick */
+	int64_t moved;              /* updates that changed the item's cluster */
+	int64_t new_clusters;       /* updates that picked an auxiliary draw (np_neal_algorithm8.cpp:136-145) */
+	int64_t sm_attempts[4];     /* split/merge samplers: merge 2->1, split 1->2, merge 3->2, split 2->3 */
+	int64_t sm_accepts[4];
+	int64_t sams_allocations;   /* items allocated by restricted (SAMS) scans over all proposals */
+	double  mean_K;             /* mean occupied clusters over chains after the last sweep */
+	int32_t max_K;              /* largest occupied-cluster count over chains after the last sweep */
+	int32_t overflow_chains;    /* chains that hit Kmax (their results are invalid) */
+	float   kernel_ms;          /* device time of the sweep kernel(s), CUDA events on the context stream */
+} npb_sweep_stats;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+npb_status npb_ctx_create(int device, npb_ctx **out);
+npb_status npb_ctx_destroy(npb_ctx *ctx);
+/* the cudaStream_t all work of this context is enqueued on (for event timing by the caller) */
+void *npb_ctx_stream(npb_ctx *ctx);
+npb_status npb_ctx_synchronize(npb_ctx *ctx);
+const char *npb_status_str(npb_status s);
+/* last CUDA error text seen by this context ("" if none) */
+const char *npb_ctx_last_error(npb_ctx *ctx);
+
+/* ---- data: replaces membertrix::addData / dataset_t (membertrix.cpp:124-138, np_data.h:9-15) ------------ */
+/* X row-major [N,D] doubles; stored on the device as fp32 (sweeps) and fp64 (replay / precision=64) */
+npb_status npb_dataset_upload(npb_ctx *ctx, const double *X, int64_t N, int D, npb_dataset **out);
+/* re-upload new values into an existing dataset of the same shape (end-to-end timing path) */
+npb_status npb_dataset_update(npb_dataset *ds, const double *X);
+npb_status npb_dataset_destroy(npb_dataset *ds);
+
+/* ---- prior: replaces dirichlet_process(alpha, normal_inverse_wishart_distribution) ----------------------
+ * (dirichlet.h:20-93, normalinvwishart.h:27-64, constants np_main.cpp:164,367-371) */
+npb_status npb_prior_set_niw(npb_ctx *ctx, int D, const double *mu0, double kappa, double nu, const double *Lambda,
+		double alpha, int flags);
+
+/* ---- density: replaces multivariate_normal_distribution::{init, probability, logprobability} -----------
+ * (multivariatenormal.cpp:16-35, 64-146).  out[r*K+k] = log N(X[rows[r]] | mu[k], Sigma[k]); rows == NULL
+ * means rows 0..n_rows-1.  Sigma[k] is a general D x D matrix (row-major; the reference's known-answer test
+ * uses a non-symmetric one).  precision = 64 evaluates in double, 32 in float with double parameters prepared
+ * on the host. */
+npb_status npb_logdensity_batch(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows, int64_t n_rows, const double *mu,
+		const double *Sigma, int K, int precision, double *out);
+/* sum over a member list, multivariatenormal.cpp:138-146: out[k] = sum_r log N(X[rows[r]] | theta_k) */
+npb_status npb_logdensity_sum(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows, int64_t n_rows, const double *mu,
+		const double *Sigma, int K, double *out);
+
+/* ---- chains: replaces MCMC::run's state (np_mcmc.cpp:48-91: K0 prior clusters, uniform assignment,
+ * cleanup) for n_chains independent chains run in lockstep ------------------------------------------------ */
+npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, int Kmax, int m_aux, int K0,
+		uint64_t seed, npb_chains **out);
+npb_status npb_chains_destroy(npb_chains *ch);
+/* overwrite the state of one chain (used by parity tests and by the single-item seam):
+ * z [N] slot ids, K clusters with slot ids, means [K,D], covariances [K,D,D] */
+npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z, int K, const int32_t *slots,
+		const double *mu, const double *Sigma);
+
+/* n_sweeps sweeps of the chosen sampler over all chains: replaces the doubly nested loop of
+ * np_mcmc.cpp:109-163 with NealAlgorithm8::update (np_neal_algorithm8.cpp:49-167),
+ * JainNealAlgorithm::update (np_jain_neal_algorithm.cpp:424-502) or TriadicAlgorithm::update
+ * (np_triadic_algorithm.cpp:633-795) inside. */
+npb_status npb_chains_sweep(npb_chains *ch, int sampler, int n_sweeps, npb_sweep_stats *stats);
+/* end-to-end form with host buffers: upload X (as npb_dataset_update), sweep, download the assignments of
+ * all chains; z_out [N, n_chains] uint16 slot ids (item-major), may be NULL */
+npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,
+		npb_sweep_stats *stats);
+
+/* one NealAlgorithm8::update(membertrix&, {item}) on one chain (the reference's single-item seam) */
+npb_status npb_chain_update_alg8(npb_chains *ch, int64_t chain, int64_t item);
+
+/* parity level 2: replay a recorded fp64 trace on one chain starting from the state set
+ * with npb_chains_set_state.  steps = n_steps; per step: item, K candidates `order` (slot ids, ragged via
+ * order_off [n_steps+1]), m_aux auxiliary thetas, the uniform u, the slot a picked auxiliary is born into.
+ * picked_out [n_steps] receives the candidate index chosen by the device; z_after_out (may be NULL) receives
+ * z after every `z_every` steps ([n_steps / z_every, N]). */
+npb_status npb_chain_replay_alg8(npb_chains *ch, int64_t chain, int64_t n_steps, const int32_t *item,
+		const int64_t *order_off, const int32_t *order, const double *aux_mu, const double *aux_Sigma,
+		const double *u, const int32_t *new_slot, int32_t *picked_out, int64_t z_every, int32_t *z_after_out);
+
+/* state readback: replaces membertrix::getClusterId / getClusters / count (membertrix.cpp:235-257,328-330) */
+npb_status npb_chains_get_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out /* [n,N] slot ids */);
+npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts,
+		double *mu /* [cap,D] */, double *Sigma /* [cap,D,D] */);
+
+/* metrics for every chain: replaces clustering_performance::{calculateContingencyMatrix, calculateSimilarity}
+ * (clustering_performance.cpp:14-82) and MCMC::considerMaxLikelihood's joint log-likelihood
+ * (np_mcmc.cpp:187-203).  truth [N] labels >= 0; outputs [n_chains] each, any may be NULL. */
+npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *purity, double *rand_index,
+		double *adjusted_rand, double *joint_loglik, int32_t *K);
+
+/* posterior co-clustering counts over this context's chains for an anchor subset: S[a,b] = #chains with
+ * z[anchors[a]] == z[anchors[b]].  S_dev is a DEVICE pointer to n_anchor*n_anchor floats (so that the caller can
+ * all-reduce it over NCCL without a host round trip); accumulate != 0 adds to S_dev. */
+npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, float *S_dev, int accumulate);
+
+/* The scan order of sweep number `sweep` (replaces the per-sweep std::shuffle of np_mcmc.cpp:120-125): a keyed
+ * permutation of 0..N-1 shared by all chains of a run; order_out[s] = item visited at step s.  Pure host
+ * function (no device needed); the kernels evaluate the same function point-wise. */
+npb_status npb_scan_order_host(uint64_t seed, uint32_t sweep, int64_t N, int32_t *order_out);
+
+int64_t npb_chains_count(npb_chains *ch);
+int npb_chains_kmax(npb_chains *ch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPB200_H */

@@ -1,0 +1,12 @@
+"""noparama_b200 -- B200-native (sm_100a) Gibbs reassignment for Dirichlet-process mixtures.
+
+One hot path of mrquincle/noparama (Neal Algorithm 8 and the machinery it shares with the split-merge samplers),
+behind the reference's sampler seam.  All compute is in libnpb200.so (CUDA); there is no CPU path.
+"""
+from .api import (ALG8, ALG2, JAIN_NEAL, TRIADIC, BUGCOMPAT_DEFAULT, BUGCOMPAT_DEGENERATE_IW, BUGCOMPAT_UNDERFLOW,
+                  Chains, Context, Dataset, MCMC, MultivariateNormal, NealAlgorithm8, NormalInverseWishart, NpbError,
+                  SweepStats, load_library, scan_order, LIB_PATH, EXPORTS)
+from . import synthetic
+
+__all__ = ["ALG8", "ALG2", "JAIN_NEAL", "TRIADIC", "Chains", "Context", "Dataset", "MCMC", "MultivariateNormal",
+           "NealAlgorithm8", "NormalInverseWishart", "NpbError", "SweepStats", "load_library", "synthetic"]

@@ -1,0 +1,325 @@
+"""Host-side mirror (Python) of the reference's sampler seam on top of the C ABI of libnpb200.so.
+
+The reference wires `MCMC(generator, InitClusters, UpdateClusters, UpdateClusterPopulation, subset_count, likelihood)`
+and calls `run(dataset, T)` (include/np_mcmc.h:71-95, src/np_main.cpp:391-471).  The classes below keep those names
+and argument meanings; all arithmetic happens in the CUDA library.  There is no CPU fallback: importing works
+without a GPU (so that CPU-only checks can load the library and inspect its symbols), creating a Context does not.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnpb200.so")
+
+ALG8, ALG2, JAIN_NEAL, TRIADIC = 8, 2, 20, 30
+BUGCOMPAT_DEGENERATE_IW, BUGCOMPAT_UNDERFLOW = 1, 2
+BUGCOMPAT_DEFAULT = BUGCOMPAT_DEGENERATE_IW
+
+OK = 0
+E_KMAX_OVERFLOW = -3
+E_UNSUPPORTED = -5
+
+EXPORTS = [
+    "npb_ctx_create", "npb_ctx_destroy", "npb_ctx_stream", "npb_ctx_synchronize", "npb_status_str",
+    "npb_ctx_last_error", "npb_dataset_upload", "npb_dataset_update", "npb_dataset_destroy", "npb_prior_set_niw",
+    "npb_logdensity_batch", "npb_logdensity_sum", "npb_chains_create", "npb_chains_destroy", "npb_chains_set_state",
+    "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_chain_replay_alg8",
+    "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
+    "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host",
+]
+
+
+class NpbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("npb200: %s (status %d)" % (msg, status))
+        self.status = status
+
+
+class SweepStats(C.Structure):
+    _fields_ = [("reassignments", C.c_int64), ("candidates", C.c_int64), ("moved", C.c_int64),
+                ("new_clusters", C.c_int64), ("sm_attempts", C.c_int64 * 4), ("sm_accepts", C.c_int64 * 4),
+                ("sams_allocations", C.c_int64), ("mean_K", C.c_double), ("max_K", C.c_int32),
+                ("overflow_chains", C.c_int32), ("kernel_ms", C.c_float)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libnpb200.so; raises if the CUDA extension has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libnpb200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(noparama_b200 has no CPU path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, dp = C.c_void_p, C.c_int64, C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int32)
+    L.npb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.npb_ctx_destroy.argtypes = [vp]
+    L.npb_ctx_stream.restype = vp
+    L.npb_ctx_stream.argtypes = [vp]
+    L.npb_ctx_synchronize.argtypes = [vp]
+    L.npb_status_str.restype = C.c_char_p
+    L.npb_status_str.argtypes = [C.c_int]
+    L.npb_ctx_last_error.restype = C.c_char_p
+    L.npb_ctx_last_error.argtypes = [vp]
+    L.npb_dataset_upload.argtypes = [vp, dp, i64, C.c_int, C.POINTER(vp)]
+    L.npb_dataset_update.argtypes = [vp, dp]
+    L.npb_dataset_destroy.argtypes = [vp]
+    L.npb_prior_set_niw.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp, C.c_double, C.c_int]
+    L.npb_logdensity_batch.argtypes = [vp, vp, C.POINTER(i64), i64, dp, dp, C.c_int, C.c_int, dp]
+    L.npb_logdensity_sum.argtypes = [vp, vp, C.POINTER(i64), i64, dp, dp, C.c_int, dp]
+    L.npb_chains_create.argtypes = [vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(vp)]
+    L.npb_chains_destroy.argtypes = [vp]
+    L.npb_chains_set_state.argtypes = [vp, i64, ip, C.c_int, ip, dp, dp]
+    L.npb_chains_sweep.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SweepStats)]
+    L.npb_chains_sweep_host.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(SweepStats)]
+    L.npb_chain_update_alg8.argtypes = [vp, i64, i64]
+    L.npb_chain_replay_alg8.argtypes = [vp, i64, i64, ip, C.POINTER(i64), ip, dp, dp, dp, ip, ip, i64, ip]
+    L.npb_chains_get_assignments.argtypes = [vp, i64, i64, ip]
+    L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
+    L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
+    L.npb_cocluster.argtypes = [vp, C.POINTER(i64), i64, vp, C.c_int]
+    L.npb_chains_count.restype = i64
+    L.npb_chains_count.argtypes = [vp]
+    L.npb_chains_kmax.argtypes = [vp]
+    L.npb_scan_order_host.argtypes = [C.c_uint64, C.c_uint32, i64, ip]
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def scan_order(seed, sweep, N):
+    """Item visited at each step of sweep `sweep` (host evaluation of the kernels' keyed permutation)."""
+    out = np.empty(N, dtype=np.int32)
+    st = load_library().npb_scan_order_host(seed, sweep, N, _ip(out))
+    if st != OK:
+        raise NpbError(st, "bad argument")
+    return out
+
+
+class Context:
+    """One CUDA device + stream (npb_ctx)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        st = self._lib.npb_ctx_create(device, C.byref(h))
+        if st != OK:
+            raise NpbError(st, "cannot create a context on CUDA device %d (no GPU? there is no CPU path)" % device)
+        self._h = h
+        self.device = device
+
+    def check(self, st):
+        if st != OK:
+            detail = self._lib.npb_ctx_last_error(self._h).decode()
+            raise NpbError(st, self._lib.npb_status_str(st).decode() + (": " + detail if detail else ""))
+
+    @property
+    def stream(self):
+        return self._lib.npb_ctx_stream(self._h)
+
+    def synchronize(self):
+        self.check(self._lib.npb_ctx_synchronize(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.npb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Dataset:
+    """dataset_t (include/np_data.h:9-15) resident in HBM."""
+
+    def __init__(self, ctx, X):
+        X = _f64(X)
+        assert X.ndim == 2
+        self.ctx, self.N, self.D = ctx, X.shape[0], X.shape[1]
+        h = C.c_void_p()
+        ctx.check(ctx._lib.npb_dataset_upload(ctx._h, _dp(X), self.N, self.D, C.byref(h)))
+        self._h = h
+
+    def update(self, X):
+        X = _f64(X)
+        assert X.shape == (self.N, self.D)
+        self.ctx.check(self.ctx._lib.npb_dataset_update(self._h, _dp(X)))
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.npb_dataset_destroy(self._h)
+            self._h = None
+
+
+class NormalInverseWishart:
+    """Suffies_NormalInvWishart + Suffies_Dirichlet (np_suffies.h:80-95; constants np_main.cpp:164,367-371)."""
+
+    def __init__(self, mu0, kappa, nu, Lambda, alpha=1.0, flags=BUGCOMPAT_DEFAULT):
+        self.mu0, self.Lambda = _f64(mu0), _f64(Lambda)
+        self.kappa, self.nu, self.alpha, self.flags = float(kappa), float(nu), float(alpha), int(flags)
+        self.D = len(self.mu0)
+
+    def bind(self, ctx):
+        ctx.check(ctx._lib.npb_prior_set_niw(ctx._h, self.D, _dp(self.mu0), self.kappa, self.nu, _dp(self.Lambda),
+                                             self.alpha, self.flags))
+
+
+class MultivariateNormal:
+    """multivariate_normal_distribution (statistics/multivariatenormal.h): batched log-densities on the device."""
+
+    def __init__(self, ctx, dataset):
+        self.ctx, self.ds = ctx, dataset
+
+    def logprobability(self, mu, Sigma, rows=None, precision=64):
+        """log N(X[rows] | mu[k], Sigma[k]) -> [n_rows, K]  (multivariatenormal.cpp:106-136)"""
+        mu, Sigma = _f64(mu), _f64(Sigma)
+        K, D = mu.shape
+        assert D == self.ds.D and Sigma.shape == (K, D, D)
+        if rows is None:
+            n, rp = self.ds.N, None
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.int64)
+            n, rp = len(rows), rows.ctypes.data_as(C.POINTER(C.c_int64))
+        out = np.empty((n, K), dtype=np.float64)
+        self.ctx.check(self.ctx._lib.npb_logdensity_batch(self.ctx._h, self.ds._h, rp, n, _dp(mu), _dp(Sigma), K,
+                                                          precision, _dp(out)))
+        return out
+
+    def probability(self, mu, Sigma, rows=None, precision=64):
+        """multivariatenormal.cpp:64-94"""
+        return np.exp(self.logprobability(mu, Sigma, rows, precision))
+
+    def logprobability_dataset(self, mu, Sigma, rows=None):
+        """sum over a member list (multivariatenormal.cpp:138-146) -> [K]"""
+        mu, Sigma = _f64(mu), _f64(Sigma)
+        K, D = mu.shape
+        if rows is None:
+            n, rp = self.ds.N, None
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.int64)
+            n, rp = len(rows), rows.ctypes.data_as(C.POINTER(C.c_int64))
+        out = np.empty(K, dtype=np.float64)
+        self.ctx.check(self.ctx._lib.npb_logdensity_sum(self.ctx._h, self.ds._h, rp, n, _dp(mu), _dp(Sigma), K, _dp(out)))
+        return out
+
+
+class Chains:
+    """The membertrix state (include/membertrix.h) of n_chains independent chains, device resident."""
+
+    def __init__(self, ctx, dataset, n_chains, Kmax=256, m_aux=3, K0=20, seed=20261018):
+        self.ctx, self.ds = ctx, dataset
+        self.C, self.Kmax, self.m_aux, self.K0 = int(n_chains), int(Kmax), int(m_aux), int(K0)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.npb_chains_create(ctx._h, dataset._h, self.C, self.Kmax, self.m_aux, self.K0, seed, C.byref(h)))
+        self._h = h
+
+    def sweep(self, sampler=ALG8, n_sweeps=1, want_stats=True):
+        st = SweepStats()
+        self.ctx.check(self.ctx._lib.npb_chains_sweep(self._h, sampler, n_sweeps, C.byref(st) if want_stats else None))
+        return st
+
+    def sweep_host(self, X, sampler=ALG8, n_sweeps=1, z_out=None, want_stats=False):
+        """end-to-end step with host buffers: H2D of X, sweep, D2H of all assignments [N, C] uint16"""
+        st = SweepStats()
+        zp = z_out.ctypes.data_as(C.POINTER(C.c_uint16)) if z_out is not None else None
+        self.ctx.check(self.ctx._lib.npb_chains_sweep_host(self._h, _dp(X), sampler, n_sweeps, zp,
+                                                           C.byref(st) if want_stats else None))
+        return st
+
+    def set_state(self, chain, z, slots, mu, Sigma):
+        z = np.ascontiguousarray(z, dtype=np.int32)
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        mu, Sigma = _f64(mu), _f64(Sigma)
+        self.ctx.check(self.ctx._lib.npb_chains_set_state(self._h, chain, _ip(z), len(slots), _ip(slots), _dp(mu), _dp(Sigma)))
+
+    def assignments(self, chain0=0, n=None):
+        n = self.C - chain0 if n is None else n
+        out = np.empty((n, self.ds.N), dtype=np.int32)
+        self.ctx.check(self.ctx._lib.npb_chains_get_assignments(self._h, chain0, n, _ip(out)))
+        return out
+
+    def params(self, chain):
+        cap, D = self.Kmax, self.ds.D
+        K = C.c_int()
+        slots = np.empty(cap, np.int32)
+        counts = np.empty(cap, np.int64)
+        mu = np.empty((cap, D))
+        Sigma = np.empty((cap, D, D))
+        self.ctx.check(self.ctx._lib.npb_chains_get_params(self._h, chain, cap, C.byref(K), _ip(slots),
+                                                           counts.ctypes.data_as(C.POINTER(C.c_int64)), _dp(mu), _dp(Sigma)))
+        k = K.value
+        return slots[:k].copy(), counts[:k].copy(), mu[:k].copy(), Sigma[:k].copy()
+
+    def metrics(self, truth=None, joint_loglik=True):
+        """purity / Rand / adjusted Rand per chain (clustering_performance.cpp:38-82), joint log-likelihood
+        (np_mcmc.cpp:187-203) and occupied cluster count."""
+        Cn = self.C
+        pur, ri, ari, jll = (np.zeros(Cn) for _ in range(4))
+        K = np.zeros(Cn, np.int32)
+        tp = None
+        if truth is not None:
+            truth = np.ascontiguousarray(truth, dtype=np.int32)
+            tp = _ip(truth)
+        self.ctx.check(self.ctx._lib.npb_chains_metrics(self._h, tp, _dp(pur), _dp(ri), _dp(ari),
+                                                        _dp(jll) if joint_loglik else None, _ip(K)))
+        return dict(purity=pur, rand_index=ri, adjusted_rand=ari, joint_loglik=jll, K=K)
+
+    def cocluster_into(self, anchors, S_dev_ptr, accumulate=False):
+        anchors = np.ascontiguousarray(anchors, dtype=np.int64)
+        self.ctx.check(self.ctx._lib.npb_cocluster(self._h, anchors.ctypes.data_as(C.POINTER(C.c_int64)), len(anchors),
+                                                   C.c_void_p(S_dev_ptr), int(accumulate)))
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.npb_chains_destroy(self._h)
+            self._h = None
+
+
+class NealAlgorithm8:
+    """UpdateClusterPopulation implementation selected by `-a algorithm8` (np_main.cpp:433-439)."""
+    sampler = ALG8
+    subset_count = 1
+
+
+class MCMC:
+    """MCMC::run (np_mcmc.cpp:48-175) for `chains` lockstep chains on one device.
+
+    run(T) performs T sweeps; getMembershipMatrix() mirrors MCMC::getMembershipMatrix (np_mcmc.h:88)."""
+
+    def __init__(self, ctx, dataset, prior, update_cluster_population=NealAlgorithm8, chains=1, Kmax=256, K0=20,
+                 m_aux=3, seed=20261018):
+        prior.bind(ctx)
+        self.algorithm = update_cluster_population
+        self.chains = Chains(ctx, dataset, chains, Kmax=Kmax, m_aux=m_aux, K0=K0, seed=seed)
+
+    def run(self, T, sweeps_per_launch=None):
+        stats = []
+        step = T if not sweeps_per_launch else sweeps_per_launch
+        done = 0
+        while done < T:
+            n = min(step, T - done)
+            stats.append(self.chains.sweep(self.algorithm.sampler, n))
+            done += n
+        return stats
+
+    def getMembershipMatrix(self, chain0=0, n=None):
+        return self.chains.assignments(chain0, n)

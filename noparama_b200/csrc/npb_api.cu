@@ -1,0 +1,577 @@
+// npb_api.cu -- the C ABI of include/npb200.h: handle management, host<->device staging, launch order.
+#include "npb_internal.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+npb_status npb_launch_logdensity(npb_ctx *, npb_dataset *, const int64_t *, int64_t, int, const double *, const double *,
+		const double *, const float *, const float *, const float *, int, double *);
+npb_status npb_launch_logdensity_sum(npb_ctx *, npb_dataset *, const int64_t *, int64_t, int, const double *, const double *,
+		const double *, double *);
+npb_status npb_launch_metrics(npb_chains *, const int32_t *, int, double *, double *, double *, double *, int32_t *);
+npb_status npb_launch_cocluster(npb_chains *, const int64_t *, int, float *, int);
+npb_status npb_launch_replay_alg8(npb_chains *ch, int64_t chain, int64_t n_steps, const int32_t *d_item,
+		const int64_t *d_order_off, const int32_t *d_order, const double *d_aux_mu, const double *d_aux_T,
+		const double *d_aux_c, const double *d_u, const int32_t *d_new_slot, int32_t *d_picked, int64_t z_every,
+		int32_t *d_z_after, const double *d_mu, const double *d_T, const double *d_c, const int32_t *d_z0,
+		const int32_t *d_cnt0, int nslots, int *d_status);
+
+npb_status npb_fail_cuda(npb_ctx *ctx, cudaError_t e, const char *expr, const char *file, int line) {
+	if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s (%s:%d)", cudaGetErrorString(e), expr, file, line);
+	return e == cudaErrorMemoryAllocation ? NPB_E_NOMEM : NPB_E_CUDA;
+}
+npb_status npb_fail(npb_ctx *ctx, npb_status s, const char *msg) {
+	if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+	return s;
+}
+
+// small RAII device buffer for call-scoped staging
+template <typename T>
+struct DevBuf {
+	T *p = nullptr;
+	cudaError_t alloc(size_t n) { return cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T)); }
+	~DevBuf() { if (p) cudaFree(p); }
+};
+
+extern "C" {
+
+const char *npb_status_str(npb_status s) {
+	switch (s) {
+	case NPB_OK: return "ok";
+	case NPB_E_BAD_ARG: return "bad argument";
+	case NPB_E_CUDA: return "CUDA error";
+	case NPB_E_KMAX_OVERFLOW: return "a chain needed more than Kmax clusters";
+	case NPB_E_NOT_POSITIVE: return "covariance not invertible / precision not positive definite";
+	case NPB_E_UNSUPPORTED: return "unsupported configuration";
+	case NPB_E_REPLAY_MISMATCH: return "replay diverged from the recorded trace";
+	case NPB_E_NOMEM: return "out of device memory";
+	case NPB_E_ALREADY_ASSIGNED: return "already assigned";
+	case NPB_E_ASSIGNMENT_REMAINING: return "assignment remaining";
+	case NPB_E_ASSIGNMENT_ABSENT: return "assignment absent";
+	default: return "unknown status";
+	}
+}
+
+npb_status npb_ctx_create(int device, npb_ctx **out) {
+	if (!out) return NPB_E_BAD_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return NPB_E_CUDA; // no CPU fallback
+	if (device < 0 || device >= ndev) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = new (std::nothrow) npb_ctx();
+	if (!ctx) return NPB_E_NOMEM;
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+			cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+		delete ctx;
+		return NPB_E_CUDA;
+	}
+	*out = ctx;
+	return NPB_OK;
+}
+
+npb_status npb_ctx_destroy(npb_ctx *ctx) {
+	if (!ctx) return NPB_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->d_CT2) cudaFree(ctx->d_CT2);
+	if (ctx->d_S) cudaFree(ctx->d_S);
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return NPB_OK;
+}
+
+void *npb_ctx_stream(npb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+const char *npb_ctx_last_error(npb_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+npb_status npb_ctx_synchronize(npb_ctx *ctx) {
+	if (!ctx) return NPB_E_BAD_ARG;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+// ---- dataset ------------------------------------------------------------------------------------------------
+__global__ void k_to_float(const double *in, float *out, int64_t n) {
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = (float)in[i];
+}
+
+static npb_status dataset_push(npb_dataset *ds, const double *X) {
+	npb_ctx *ctx = ds->ctx;
+	const int64_t n = ds->N * ds->D;
+	memcpy(ds->h_stage, X, sizeof(double) * n);
+	NPB_CUDA_OK(cudaMemcpyAsync(ds->X64, ds->h_stage, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+	k_to_float<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ds->X64, ds->X32, n);
+	NPB_CUDA_OK(cudaGetLastError());
+	ds->whitened_epoch = 0;
+	return NPB_OK;
+}
+
+npb_status npb_dataset_upload(npb_ctx *ctx, const double *X, int64_t N, int D, npb_dataset **out) {
+	if (!ctx || !X || !out || N <= 0 || D <= 0 || D > NPB_MAX_D || N > 0x7fffffff) return NPB_E_BAD_ARG;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	npb_dataset *ds = new (std::nothrow) npb_dataset();
+	if (!ds) return NPB_E_NOMEM;
+	ds->ctx = ctx;
+	ds->N = N;
+	ds->D = D;
+	const size_t n = (size_t)N * D;
+	cudaError_t e;
+	if ((e = cudaMalloc((void **)&ds->X64, n * sizeof(double))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ds->X32, n * sizeof(float))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ds->Xw, n * sizeof(float))) != cudaSuccess ||
+			(e = cudaMallocHost((void **)&ds->h_stage, n * sizeof(double))) != cudaSuccess) {
+		npb_dataset_destroy(ds);
+		return npb_fail_cuda(ctx, e, "dataset allocation", __FILE__, __LINE__);
+	}
+	npb_status s = dataset_push(ds, X);
+	if (s != NPB_OK) { npb_dataset_destroy(ds); return s; }
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	*out = ds;
+	return NPB_OK;
+}
+
+npb_status npb_dataset_update(npb_dataset *ds, const double *X) {
+	if (!ds || !X) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ds->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream)); // the staging buffer may still be in flight
+	return dataset_push(ds, X);
+}
+
+npb_status npb_dataset_destroy(npb_dataset *ds) {
+	if (!ds) return NPB_OK;
+	cudaSetDevice(ds->ctx->device);
+	cudaStreamSynchronize(ds->ctx->stream);
+	if (ds->X64) cudaFree(ds->X64);
+	if (ds->X32) cudaFree(ds->X32);
+	if (ds->Xw) cudaFree(ds->Xw);
+	if (ds->h_stage) cudaFreeHost(ds->h_stage);
+	delete ds;
+	return NPB_OK;
+}
+
+// ---- prior --------------------------------------------------------------------------------------------------
+npb_status npb_prior_set_niw(npb_ctx *ctx, int D, const double *mu0, double kappa, double nu, const double *Lambda,
+		double alpha, int flags) {
+	if (!ctx || !mu0 || !Lambda || D <= 0 || D > NPB_MAX_D || !(kappa > 0) || !(alpha > 0)) return NPB_E_BAD_ARG;
+	if (!(flags & NPB_BUGCOMPAT_DEGENERATE_IW))
+		return npb_fail(ctx, NPB_E_UNSUPPORTED, "only the reference's degenerate inverse-Wishart draw (Q2) is implemented");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	PriorHost p;
+	p.D = D;
+	p.flags = flags;
+	p.kappa = kappa;
+	p.nu = nu;
+	p.alpha = alpha;
+	p.mu0.assign(mu0, mu0 + D);
+	p.Lambda.assign(Lambda, Lambda + (size_t)D * D);
+	if (!npb_prepare_prior(p)) return npb_fail(ctx, NPB_E_NOT_POSITIVE, "Lambda is not positive definite");
+	p.set = true;
+	const int TRI = npb_tri(D);
+	std::vector<float> ct2(TRI), s(TRI);
+	for (int t = 0; t < TRI; ++t) {
+		ct2[t] = (float)(p.CT[t] * NPB_HALF_LOG2E_SQRT);
+		s[t] = (float)p.S[t];
+	}
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if (ctx->d_CT2) cudaFree(ctx->d_CT2);
+	if (ctx->d_S) cudaFree(ctx->d_S);
+	ctx->d_CT2 = ctx->d_S = nullptr;
+	NPB_CUDA_OK(cudaMalloc((void **)&ctx->d_CT2, TRI * sizeof(float)));
+	NPB_CUDA_OK(cudaMalloc((void **)&ctx->d_S, TRI * sizeof(float)));
+	NPB_CUDA_OK(cudaMemcpy(ctx->d_CT2, ct2.data(), TRI * sizeof(float), cudaMemcpyHostToDevice));
+	NPB_CUDA_OK(cudaMemcpy(ctx->d_S, s.data(), TRI * sizeof(float), cudaMemcpyHostToDevice));
+	ctx->prior = p;
+	ctx->prior_epoch++;
+	return NPB_OK;
+}
+
+// ---- density ------------------------------------------------------------------------------------------------
+struct ThetaStaging {
+	std::vector<double> T, c;
+};
+static npb_status stage_thetas(npb_ctx *ctx, int D, int K, const double *mu, const double *Sigma, ThetaStaging &st) {
+	const int TRI = npb_tri(D);
+	st.T.resize((size_t)K * TRI);
+	st.c.resize(K);
+	for (int k = 0; k < K; ++k) {
+		double logdet;
+		if (!npb_prepare_theta(D, mu + (size_t)k * D, Sigma + (size_t)k * D * D, st.T.data() + (size_t)k * TRI, &logdet))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "Sigma is not invertible with a positive definite symmetric precision");
+		// -log sqrt((2 pi)^D det Sigma), multivariatenormal.cpp:131-133
+		st.c[k] = -0.5 * (D * std::log(2.0 * M_PI) + logdet);
+	}
+	return NPB_OK;
+}
+
+static npb_status logdensity_common(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows, int64_t n_rows, const double *mu,
+		const double *Sigma, int K, int precision, bool sum, double *out) {
+	if (!ctx || !ds || !mu || !Sigma || !out || K <= 0 || n_rows < 0 || (precision != 32 && precision != 64)) return NPB_E_BAD_ARG;
+	if (ds->ctx != ctx) return NPB_E_BAD_ARG;
+	if (n_rows == 0) {
+		if (sum) for (int k = 0; k < K; ++k) out[k] = 0.0;
+		return NPB_OK;
+	}
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ds->D, TRI = npb_tri(D);
+	if (rows)
+		for (int64_t r = 0; r < n_rows; ++r)
+			if (rows[r] < 0 || rows[r] >= ds->N) return NPB_E_BAD_ARG;
+	ThetaStaging st;
+	npb_status s = stage_thetas(ctx, D, K, mu, Sigma, st);
+	if (s != NPB_OK) return s;
+	DevBuf<double> d_mu, d_T, d_c, d_out;
+	DevBuf<float> f_mu, f_T, f_c;
+	DevBuf<int64_t> d_rows;
+	const size_t n_out = sum ? (size_t)K : (size_t)n_rows * K;
+	NPB_CUDA_OK(d_mu.alloc((size_t)K * D));
+	NPB_CUDA_OK(d_T.alloc((size_t)K * TRI));
+	NPB_CUDA_OK(d_c.alloc(K));
+	NPB_CUDA_OK(d_out.alloc(n_out));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_mu.p, mu, sizeof(double) * K * D, cudaMemcpyHostToDevice, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_T.p, st.T.data(), sizeof(double) * K * TRI, cudaMemcpyHostToDevice, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_c.p, st.c.data(), sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+	std::vector<float> hmu, hT, hc;
+	if (precision == 32) {
+		hmu.resize((size_t)K * D); hT.resize((size_t)K * TRI); hc.resize(K);
+		for (size_t i = 0; i < hmu.size(); ++i) hmu[i] = (float)mu[i];
+		for (size_t i = 0; i < hT.size(); ++i) hT[i] = (float)st.T[i];
+		for (int k = 0; k < K; ++k) hc[k] = (float)st.c[k];
+		NPB_CUDA_OK(f_mu.alloc(hmu.size()));
+		NPB_CUDA_OK(f_T.alloc(hT.size()));
+		NPB_CUDA_OK(f_c.alloc(K));
+		NPB_CUDA_OK(cudaMemcpyAsync(f_mu.p, hmu.data(), sizeof(float) * hmu.size(), cudaMemcpyHostToDevice, ctx->stream));
+		NPB_CUDA_OK(cudaMemcpyAsync(f_T.p, hT.data(), sizeof(float) * hT.size(), cudaMemcpyHostToDevice, ctx->stream));
+		NPB_CUDA_OK(cudaMemcpyAsync(f_c.p, hc.data(), sizeof(float) * K, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if (rows) {
+		NPB_CUDA_OK(d_rows.alloc(n_rows));
+		NPB_CUDA_OK(cudaMemcpyAsync(d_rows.p, rows, sizeof(int64_t) * n_rows, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if (sum) s = npb_launch_logdensity_sum(ctx, ds, rows ? d_rows.p : nullptr, n_rows, K, d_mu.p, d_T.p, d_c.p, d_out.p);
+	else s = npb_launch_logdensity(ctx, ds, rows ? d_rows.p : nullptr, n_rows, K, d_mu.p, d_T.p, d_c.p, f_mu.p, f_T.p, f_c.p, precision, d_out.p);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaMemcpyAsync(out, d_out.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+npb_status npb_logdensity_batch(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows, int64_t n_rows, const double *mu,
+		const double *Sigma, int K, int precision, double *out) {
+	return logdensity_common(ctx, ds, rows, n_rows, mu, Sigma, K, precision, false, out);
+}
+npb_status npb_logdensity_sum(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows, int64_t n_rows, const double *mu,
+		const double *Sigma, int K, double *out) {
+	return logdensity_common(ctx, ds, rows, n_rows, mu, Sigma, K, 64, true, out);
+}
+
+// ---- chains -------------------------------------------------------------------------------------------------
+static npb_status ensure_whitened(npb_dataset *ds) {
+	if (ds->whitened_epoch == ds->ctx->prior_epoch) return NPB_OK;
+	return npb_launch_whiten(ds);
+}
+
+npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, int Kmax, int m_aux, int K0, uint64_t seed,
+		npb_chains **out) {
+	if (!ctx || !ds || !out || ds->ctx != ctx || n_chains <= 0 || n_chains > 0x7fffffff || Kmax <= 0 || Kmax > 65535 ||
+			m_aux <= 0 || m_aux > NPB_MAX_AUX || K0 <= 0 || K0 > Kmax)
+		return NPB_E_BAD_ARG;
+	if (!ctx->prior.set || ctx->prior.D != ds->D) return npb_fail(ctx, NPB_E_BAD_ARG, "set a prior of the dataset's dimension first");
+	if (Kmax % 32) return npb_fail(ctx, NPB_E_BAD_ARG, "Kmax must be a multiple of 32");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	npb_chains *ch = new (std::nothrow) npb_chains();
+	if (!ch) return NPB_E_NOMEM;
+	ch->ctx = ctx;
+	ch->ds = ds;
+	ch->C = n_chains;
+	ch->Kmax = Kmax;
+	ch->m_aux = m_aux;
+	ch->K0 = K0;
+	ch->D = ds->D;
+	ch->seed = seed;
+	const size_t PS = npb_ps(ds->D);
+	cudaError_t e;
+	if ((e = cudaMalloc((void **)&ch->z, (size_t)ds->N * n_chains * sizeof(npb_z_t))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ch->theta, (size_t)n_chains * Kmax * PS * sizeof(float))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ch->counts, (size_t)n_chains * Kmax * sizeof(int))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ch->st, (size_t)n_chains * 4 * sizeof(unsigned long long))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ch->kocc, (size_t)n_chains * sizeof(int))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ch->overflow, (size_t)n_chains * sizeof(int))) != cudaSuccess) {
+		npb_chains_destroy(ch);
+		return npb_fail_cuda(ctx, e, "chain state allocation", __FILE__, __LINE__);
+	}
+	npb_status s = ensure_whitened(ds);
+	if (s == NPB_OK) s = npb_launch_chains_init(ch);
+	if (s != NPB_OK) { npb_chains_destroy(ch); return s; }
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	*out = ch;
+	return NPB_OK;
+}
+
+npb_status npb_chains_destroy(npb_chains *ch) {
+	if (!ch) return NPB_OK;
+	cudaSetDevice(ch->ctx->device);
+	cudaStreamSynchronize(ch->ctx->stream);
+	if (ch->z) cudaFree(ch->z);
+	if (ch->theta) cudaFree(ch->theta);
+	if (ch->counts) cudaFree(ch->counts);
+	if (ch->st) cudaFree(ch->st);
+	if (ch->kocc) cudaFree(ch->kocc);
+	if (ch->overflow) cudaFree(ch->overflow);
+	if (ch->h_z) cudaFreeHost(ch->h_z);
+	delete ch;
+	return NPB_OK;
+}
+
+int64_t npb_chains_count(npb_chains *ch) { return ch ? ch->C : 0; }
+int npb_chains_kmax(npb_chains *ch) { return ch ? ch->Kmax : 0; }
+
+__global__ void k_scatter_chain_z(npb_z_t *z, const int32_t *zin, int N, int C, int chain) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) z[(size_t)i * C + chain] = (npb_z_t)zin[i];
+}
+__global__ void k_gather_chain_z(const npb_z_t *z, int32_t *zout, int N, int C, int chain0, int n) {
+	int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (int64_t)N * n) return;
+	int c = (int)(idx % n), i = (int)(idx / n); // consecutive threads read consecutive chains (coalesced)
+	zout[(size_t)c * N + i] = (int32_t)z[(size_t)i * C + chain0 + c];
+}
+
+npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z, int K, const int32_t *slots,
+		const double *mu, const double *Sigma) {
+	if (!ch || !z || !slots || !mu || !Sigma || chain < 0 || chain >= ch->C || K <= 0 || K > ch->Kmax) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ch->D, TRI = npb_tri(D), PS = npb_ps(D), N = (int)ch->ds->N;
+	std::vector<float> th((size_t)ch->Kmax * PS, 0.0f);
+	std::vector<int> cnt(ch->Kmax, 0);
+	std::vector<char> used(ch->Kmax, 0);
+	std::vector<double> T(TRI);
+	for (int k = 0; k < K; ++k) {
+		const int s = slots[k];
+		if (s < 0 || s >= ch->Kmax || used[s]) return NPB_E_BAD_ARG;
+		used[s] = 1;
+		double logdet;
+		if (!npb_prepare_theta(D, mu + (size_t)k * D, Sigma + (size_t)k * D * D, T.data(), &logdet))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "Sigma is not invertible with a positive definite symmetric precision");
+		float *o = th.data() + (size_t)s * PS;
+		for (int d = 0; d < D; ++d) o[d] = (float)mu[(size_t)k * D + d];
+		for (int t = 0; t < TRI; ++t) o[D + t] = (float)(T[t] * NPB_HALF_LOG2E_SQRT);
+		o[D + TRI] = (float)(-0.5 * (D * std::log2(2.0 * M_PI) + logdet / std::log(2.0)));
+	}
+	for (int i = 0; i < N; ++i) {
+		if (z[i] < 0 || z[i] >= ch->Kmax || !used[z[i]]) return NPB_E_BAD_ARG;
+		cnt[z[i]]++;
+	}
+	int occ = 0;
+	for (int s = 0; s < ch->Kmax; ++s) occ += cnt[s] > 0;
+	DevBuf<int32_t> d_z;
+	NPB_CUDA_OK(d_z.alloc(N));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_z.p, z, sizeof(int32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+	k_scatter_chain_z<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ch->z, d_z.p, N, (int)ch->C, (int)chain);
+	NPB_CUDA_OK(cudaGetLastError());
+	NPB_CUDA_OK(cudaMemcpyAsync(ch->theta + (size_t)chain * ch->Kmax * PS, th.data(), sizeof(float) * th.size(), cudaMemcpyHostToDevice, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(ch->counts + (size_t)chain * ch->Kmax, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(ch->kocc + chain, &occ, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+static npb_status collect_stats(npb_chains *ch, const std::vector<unsigned long long> &before, int n_sweeps, float ms,
+		npb_sweep_stats *stats) {
+	npb_ctx *ctx = ch->ctx;
+	const size_t C = (size_t)ch->C;
+	std::vector<unsigned long long> st(C * 4);
+	std::vector<int> kocc(C), ovf(C);
+	NPB_CUDA_OK(cudaMemcpyAsync(st.data(), ch->st, sizeof(unsigned long long) * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(kocc.data(), ch->kocc, sizeof(int) * C, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(ovf.data(), ch->overflow, sizeof(int) * C, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	memset(stats, 0, sizeof(*stats));
+	stats->reassignments = (int64_t)C * ch->ds->N * n_sweeps;
+	double sumK = 0;
+	for (size_t c = 0; c < C; ++c) {
+		stats->candidates += (int64_t)(st[c * 4 + 0] - before[c * 4 + 0]);
+		stats->moved += (int64_t)(st[c * 4 + 1] - before[c * 4 + 1]);
+		stats->new_clusters += (int64_t)(st[c * 4 + 2] - before[c * 4 + 2]);
+		sumK += kocc[c];
+		if (kocc[c] > stats->max_K) stats->max_K = kocc[c];
+		stats->overflow_chains += ovf[c] != 0;
+	}
+	stats->mean_K = sumK / (double)C;
+	stats->kernel_ms = ms;
+	return NPB_OK;
+}
+
+static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, npb_sweep_stats *stats, const double *X, uint16_t *z_out) {
+	if (!ch || n_sweeps < 0) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	if (sampler != NPB_ALG8) return npb_fail(ctx, NPB_E_UNSUPPORTED, "sampler not implemented on the device yet");
+	std::vector<unsigned long long> before;
+	if (stats) {
+		before.resize((size_t)ch->C * 4);
+		NPB_CUDA_OK(cudaMemcpyAsync(before.data(), ch->st, sizeof(unsigned long long) * before.size(), cudaMemcpyDeviceToHost, ctx->stream));
+		NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	}
+	npb_status s;
+	if (X) {
+		s = npb_dataset_update(ch->ds, X);
+		if (s != NPB_OK) return s;
+	}
+	s = ensure_whitened(ch->ds);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (n_sweeps > 0) {
+		s = npb_launch_alg8_sweep(ch, n_sweeps);
+		if (s != NPB_OK) return s;
+	}
+	NPB_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+	if (z_out) {
+		const size_t bytes = (size_t)ch->ds->N * ch->C * sizeof(npb_z_t);
+		if (!ch->h_z) NPB_CUDA_OK(cudaMallocHost((void **)&ch->h_z, bytes));
+		NPB_CUDA_OK(cudaMemcpyAsync(ch->h_z, ch->z, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if (z_out) memcpy(z_out, ch->h_z, (size_t)ch->ds->N * ch->C * sizeof(npb_z_t));
+	float ms = 0.0f;
+	NPB_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	if (stats) {
+		s = collect_stats(ch, before, n_sweeps, ms, stats);
+		if (s != NPB_OK) return s;
+		if (stats->overflow_chains) return npb_fail(ctx, NPB_E_KMAX_OVERFLOW, "at least one chain ran out of cluster slots");
+	}
+	return NPB_OK;
+}
+
+npb_status npb_chains_sweep(npb_chains *ch, int sampler, int n_sweeps, npb_sweep_stats *stats) {
+	return sweep_common(ch, sampler, n_sweeps, stats, nullptr, nullptr);
+}
+npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,
+		npb_sweep_stats *stats) {
+	if (!X) return NPB_E_BAD_ARG;
+	return sweep_common(ch, sampler, n_sweeps, stats, X, z_out);
+}
+
+npb_status npb_chains_get_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out) {
+	if (!ch || !z_out || chain0 < 0 || n <= 0 || chain0 + n > ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int N = (int)ch->ds->N;
+	DevBuf<int32_t> d;
+	NPB_CUDA_OK(d.alloc((size_t)N * n));
+	int64_t total = (int64_t)N * n;
+	k_gather_chain_z<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ch->z, d.p, N, (int)ch->C, (int)chain0, (int)n);
+	NPB_CUDA_OK(cudaGetLastError());
+	NPB_CUDA_OK(cudaMemcpyAsync(z_out, d.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts, double *mu,
+		double *Sigma) {
+	if (!ch || !K || chain < 0 || chain >= ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ch->D, TRI = npb_tri(D), PS = npb_ps(D);
+	std::vector<float> th((size_t)ch->Kmax * PS);
+	std::vector<int> cnt(ch->Kmax);
+	NPB_CUDA_OK(cudaMemcpyAsync(th.data(), ch->theta + (size_t)chain * ch->Kmax * PS, sizeof(float) * th.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(cnt.data(), ch->counts + (size_t)chain * ch->Kmax, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	int k = 0;
+	std::vector<double> T(TRI);
+	for (int s = 0; s < ch->Kmax; ++s) {
+		if (cnt[s] <= 0) continue;
+		if (k < cap) {
+			if (slots) slots[k] = s;
+			if (counts) counts[k] = cnt[s];
+			const float *o = th.data() + (size_t)s * PS;
+			if (mu) for (int d = 0; d < D; ++d) mu[(size_t)k * D + d] = o[d];
+			if (Sigma) {
+				for (int t = 0; t < TRI; ++t) T[t] = (double)o[D + t] / NPB_HALF_LOG2E_SQRT;
+				npb_theta_to_sigma(D, T.data(), Sigma + (size_t)k * D * D);
+			}
+		}
+		k++;
+	}
+	*K = k;
+	return k <= cap ? NPB_OK : NPB_E_BAD_ARG;
+}
+
+npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *purity, double *rand_index, double *adjusted_rand,
+		double *joint_loglik, int32_t *K) {
+	if (!ch) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int N = (int)ch->ds->N;
+	const size_t C = (size_t)ch->C;
+	int Ktrue = 1;
+	DevBuf<int32_t> d_truth, d_K;
+	DevBuf<double> d_out; // purity, ri, ari, jll
+	if (truth) {
+		for (int i = 0; i < N; ++i) {
+			if (truth[i] < 0) return NPB_E_BAD_ARG;
+			if (truth[i] + 1 > Ktrue) Ktrue = truth[i] + 1;
+		}
+		NPB_CUDA_OK(d_truth.alloc(N));
+		NPB_CUDA_OK(cudaMemcpyAsync(d_truth.p, truth, sizeof(int32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	NPB_CUDA_OK(d_out.alloc(C * 4));
+	NPB_CUDA_OK(d_K.alloc(C));
+	npb_status s = npb_launch_metrics(ch, truth ? d_truth.p : nullptr, Ktrue, d_out.p, d_out.p + C, d_out.p + 2 * C,
+			joint_loglik ? d_out.p + 3 * C : nullptr, d_K.p);
+	if (s != NPB_OK) return s;
+	std::vector<double> h(C * 4);
+	std::vector<int32_t> hK(C);
+	NPB_CUDA_OK(cudaMemcpyAsync(h.data(), d_out.p, sizeof(double) * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(hK.data(), d_K.p, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if (truth) {
+		if (purity) memcpy(purity, h.data(), sizeof(double) * C);
+		if (rand_index) memcpy(rand_index, h.data() + C, sizeof(double) * C);
+		if (adjusted_rand) memcpy(adjusted_rand, h.data() + 2 * C, sizeof(double) * C);
+	}
+	if (joint_loglik) memcpy(joint_loglik, h.data() + 3 * C, sizeof(double) * C);
+	if (K) memcpy(K, hK.data(), sizeof(int32_t) * C);
+	return NPB_OK;
+}
+
+npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, float *S_dev, int accumulate) {
+	if (!ch || !anchors || !S_dev || n_anchor <= 0 || n_anchor > 65535) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	for (int64_t a = 0; a < n_anchor; ++a)
+		if (anchors[a] < 0 || anchors[a] >= ch->ds->N) return NPB_E_BAD_ARG;
+	DevBuf<int64_t> d_a;
+	NPB_CUDA_OK(d_a.alloc(n_anchor));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_a.p, anchors, sizeof(int64_t) * n_anchor, cudaMemcpyHostToDevice, ctx->stream));
+	npb_status s = npb_launch_cocluster(ch, d_a.p, (int)n_anchor, S_dev, accumulate);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+npb_status npb_scan_order_host(uint64_t seed, uint32_t sweep, int64_t N, int32_t *order_out) {
+	if (!order_out || N <= 0 || N > 0x7fffffff) return NPB_E_BAD_ARG;
+	const ScanOrder so = npb_scan_order(seed, sweep, (uint32_t)N);
+	for (int64_t s = 0; s < N; ++s) order_out[s] = (int32_t)npb_scan_item(so, (uint32_t)s);
+	return NPB_OK;
+}
+
+npb_status npb_chain_update_alg8(npb_chains *ch, int64_t, int64_t) {
+	return npb_fail(ch ? ch->ctx : nullptr, NPB_E_UNSUPPORTED, "single-item seam not built yet");
+}
+
+npb_status npb_chain_replay_alg8(npb_chains *ch, int64_t, int64_t, const int32_t *, const int64_t *, const int32_t *,
+		const double *, const double *, const double *, const int32_t *, int32_t *, int64_t, int32_t *) {
+	return npb_fail(ch ? ch->ctx : nullptr, NPB_E_UNSUPPORTED, "replay not built yet");
+}
+
+} // extern "C"

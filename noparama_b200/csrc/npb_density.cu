@@ -1,0 +1,190 @@
+// npb_density.cu -- batched multivariate-normal log-densities and per-chain diagnostics (sm_100a).
+//
+// k_logdensity<T>: replaces multivariate_normal_distribution::logprobability
+//   (src/statistics/multivariatenormal.cpp:106-136): log N(x | mu_k, Sigma_k) = -q/2 - log sqrt((2 pi)^D det Sigma),
+//   q = |T_k (x - mu_k)|^2 with the triangular factor prepared once per theta (npb_linalg.cpp) instead of an LU
+//   inverse + determinant per call.
+// k_chain_metrics: replaces clustering_performance::{calculateContingencyMatrix, calculateSimilarity}
+//   (src/clustering_performance.cpp:14-82, int64 instead of int: Q12) and the joint log-likelihood of
+//   MCMC::considerMaxLikelihood (src/np_mcmc.cpp:187-203), one CTA per chain.
+#include "npb_internal.h"
+
+template <typename T>
+__global__ void k_logdensity(const T *X, const int64_t *rows, int64_t n_rows, int D, const T *mu, const T *Tf,
+		const T *cst, int K, double *out) {
+	const int TRI = npb_tri(D);
+	int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n_rows * K) return;
+	const int64_t r = idx / K;
+	const int k = (int)(idx - r * K);
+	const int64_t i = rows ? rows[r] : r;
+	const T *x = X + i * D;
+	const T *m = mu + (size_t)k * D;
+	const T *t = Tf + (size_t)k * TRI;
+	T q = 0;
+	for (int a = 0; a < D; ++a) {
+		T y = 0;
+		for (int b = a; b < D; ++b) y += t[npb_tri_off(D, a, b)] * (x[b] - m[b]);
+		q += y * y;
+	}
+	out[idx] = (double)(cst[k] - (T)0.5 * q);
+}
+
+// out[k] = sum_r log N(X[rows[r]] | theta_k): one CTA per k, fp64, fixed-order tree reduction (deterministic)
+__global__ void k_logdensity_sum(const double *X, const int64_t *rows, int64_t n_rows, int D, const double *mu,
+		const double *Tf, const double *cst, double *out) {
+	__shared__ double red[256];
+	const int TRI = npb_tri(D);
+	const int k = blockIdx.x;
+	const double *m = mu + (size_t)k * D;
+	const double *t = Tf + (size_t)k * TRI;
+	double acc = 0.0;
+	for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+		const int64_t i = rows ? rows[r] : r;
+		const double *x = X + i * D;
+		double q = 0;
+		for (int a = 0; a < D; ++a) {
+			double y = 0;
+			for (int b = a; b < D; ++b) y += t[npb_tri_off(D, a, b)] * (x[b] - m[b]);
+			q += y * y;
+		}
+		acc += cst[k] - 0.5 * q;
+	}
+	red[threadIdx.x] = acc;
+	__syncthreads();
+	for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[k] = red[0];
+}
+
+// One CTA per chain.  Contingency n[a][b] (a = truth label, b = slot) in shared memory, then purity / RI / ARI,
+// joint log-likelihood from the chain's own slot table (log2 domain, float factors) and the occupied count.
+__global__ void k_chain_metrics(const npb_z_t *z, const float *X, const float *theta, const int *counts, const int32_t *truth,
+		int N, int C, int Kmax, int D, int Ktrue, double *purity, double *ri, double *ari, double *jll, int32_t *Kout) {
+	extern __shared__ unsigned char smem_raw[];
+	int *cont = (int *)smem_raw;                             // [Ktrue][Kmax]
+	double *red = (double *)(cont + (size_t)Ktrue * Kmax);   // [blockDim.x]
+	const int chain = blockIdx.x;
+	const int PS = npb_ps(D), TRI = npb_tri(D);
+	const float *th = theta + (size_t)chain * Kmax * PS;
+	for (int t = threadIdx.x; t < Ktrue * Kmax; t += blockDim.x) cont[t] = 0;
+	__syncthreads();
+	double acc = 0.0;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) {
+		const int s = (int)z[(size_t)i * C + chain];
+		if (truth) atomicAdd(&cont[truth[i] * Kmax + s], 1);
+		if (jll) {
+			const float *p = th + (size_t)s * PS;
+			const float *x = X + (size_t)i * D;
+			float q = 0.0f;
+			for (int a = 0; a < D; ++a) {
+				float y = 0.0f;
+				for (int b = a; b < D; ++b) y = fmaf(p[D + npb_tri_off(D, a, b)], x[b] - p[b], y);
+				q = fmaf(y, y, q);
+			}
+			acc += (double)(p[D + TRI] - q);
+		}
+	}
+	red[threadIdx.x] = acc;
+	__syncthreads();
+	for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		if (jll) jll[chain] = red[0] * (double)NPB_LN2;
+		if (Kout) {
+			int k = 0;
+			for (int s = 0; s < Kmax; ++s) k += counts[(size_t)chain * Kmax + s] > 0;
+			Kout[chain] = k;
+		}
+		if (truth && (purity || ri || ari)) {
+			// clustering_performance.cpp:38-82 in int64 / double
+			long long a = 0, b = 0, c = 0, colmax = 0, n = 0;
+			for (int s = 0; s < Kmax; ++s) {
+				long long col = 0, mx = 0;
+				for (int t = 0; t < Ktrue; ++t) {
+					long long v = cont[t * Kmax + s];
+					col += v;
+					mx = v > mx ? v : mx;
+					a += (v * v - v) / 2;
+				}
+				colmax += mx;
+				c += (col * col - col) / 2;
+				n += col;
+			}
+			for (int t = 0; t < Ktrue; ++t) {
+				long long row = 0;
+				for (int s = 0; s < Kmax; ++s) row += cont[t * Kmax + s];
+				b += (row * row - row) / 2;
+			}
+			double S = ((double)n * (double)n - (double)n) / 2.0;
+			double pu = n ? (double)colmax / (double)n : 0.0, r = 0.0, ar = 0.0;
+			if (S != 0.0) {
+				r = (2.0 * (double)a - (double)b - (double)c) / S + 1.0;
+				double bc = (double)b * (double)c / S, bpc = ((double)b + (double)c) / 2.0;
+				if (bc != bpc) ar = ((double)a - bc) / (bpc - bc);
+			}
+			if (purity) purity[chain] = pu;
+			if (ri) ri[chain] = r;
+			if (ari) ari[chain] = ar;
+		}
+	}
+}
+
+// co-clustering counts over an anchor subset: S[a][b] += #chains with z[anchor a] == z[anchor b]
+// (plain CUDA-core version; the tensor-core one-hot GEMM is a later row of SURVEY 8)
+__global__ void k_cocluster(const npb_z_t *z, const int64_t *anchors, int n_anchor, int C, float *S, int accumulate) {
+	const int a = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_anchor) return;
+	const npb_z_t *za = z + (size_t)anchors[a] * C, *zb = z + (size_t)anchors[b] * C;
+	int cnt = 0;
+	for (int c = 0; c < C; ++c) cnt += za[c] == zb[c];
+	float *o = S + (size_t)a * n_anchor + b;
+	*o = (accumulate ? *o : 0.0f) + (float)cnt;
+}
+
+// ---- launchers used by npb_api.cu -------------------------------------------------------------------------
+npb_status npb_launch_logdensity(npb_ctx *ctx, npb_dataset *ds, const int64_t *d_rows, int64_t n_rows, int K,
+		const double *d_mu, const double *d_T, const double *d_c, const float *f_mu, const float *f_T, const float *f_c,
+		int precision, double *d_out) {
+	int64_t total = n_rows * K;
+	int threads = 256;
+	int64_t blocks = (total + threads - 1) / threads;
+	if (precision == 64)
+		k_logdensity<double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X64, d_rows, n_rows, ds->D, d_mu, d_T, d_c, K, d_out);
+	else
+		k_logdensity<float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X32, d_rows, n_rows, ds->D, f_mu, f_T, f_c, K, d_out);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+npb_status npb_launch_logdensity_sum(npb_ctx *ctx, npb_dataset *ds, const int64_t *d_rows, int64_t n_rows, int K,
+		const double *d_mu, const double *d_T, const double *d_c, double *d_out) {
+	k_logdensity_sum<<<K, 256, 0, ctx->stream>>>(ds->X64, d_rows, n_rows, ds->D, d_mu, d_T, d_c, d_out);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+npb_status npb_launch_metrics(npb_chains *ch, const int32_t *d_truth, int Ktrue, double *d_purity, double *d_ri,
+		double *d_ari, double *d_jll, int32_t *d_K) {
+	npb_ctx *ctx = ch->ctx;
+	const int threads = 256;
+	size_t shmem = (size_t)Ktrue * ch->Kmax * sizeof(int) + threads * sizeof(double);
+	if (shmem > 200 * 1024) return npb_fail(ctx, NPB_E_UNSUPPORTED, "contingency table does not fit shared memory");
+	NPB_CUDA_OK(cudaFuncSetAttribute(k_chain_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+	k_chain_metrics<<<(unsigned)ch->C, threads, shmem, ctx->stream>>>(ch->z, ch->ds->X32, ch->theta, ch->counts, d_truth,
+			(int)ch->ds->N, (int)ch->C, ch->Kmax, ch->D, Ktrue, d_purity, d_ri, d_ari, d_jll, d_K);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+npb_status npb_launch_cocluster(npb_chains *ch, const int64_t *d_anchors, int n_anchor, float *S_dev, int accumulate) {
+	npb_ctx *ctx = ch->ctx;
+	dim3 grid((n_anchor + 127) / 128, n_anchor);
+	k_cocluster<<<grid, 128, 0, ctx->stream>>>(ch->z, d_anchors, n_anchor, (int)ch->C, S_dev, accumulate);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}

@@ -1,0 +1,82 @@
+// npb_internal.h -- host-side structs behind the opaque handles of include/npb200.h
+#pragma once
+#include "../../include/npb200.h"
+#include "npb_common.cuh"
+#include <vector>
+
+typedef uint16_t npb_z_t; // slot id of an item; Kmax <= 65535
+
+struct PriorHost {
+	bool set = false;
+	int D = 0, flags = 0;
+	double kappa = 0, nu = 0, alpha = 0;
+	std::vector<double> mu0, Lambda;
+	std::vector<double> CT;  // C^T packed upper (A^-1 = C C^T)
+	std::vector<double> S;   // C^-T packed upper
+	double logdetA = 0;
+};
+
+struct npb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	char err[512] = {0};
+	PriorHost prior;
+	float *d_CT2 = nullptr, *d_S = nullptr; // device copies of the packed prior factors
+	uint64_t prior_epoch = 0;               // bumped by npb_prior_set_niw; datasets re-whiten lazily
+};
+
+struct npb_dataset {
+	npb_ctx *ctx = nullptr;
+	int64_t N = 0;
+	int D = 0;
+	double *X64 = nullptr;  // [N,D]
+	float *X32 = nullptr;   // [N,D]
+	float *Xw = nullptr;    // [N,D] whitened against the prior: C^T (x - mu0) * sqrt(log2e/2)
+	uint64_t whitened_epoch = 0;
+	double *h_stage = nullptr; // pinned staging for uploads
+};
+
+struct npb_chains {
+	npb_ctx *ctx = nullptr;
+	npb_dataset *ds = nullptr;
+	int64_t C = 0;
+	int Kmax = 0, m_aux = 0, K0 = 0, D = 0;
+	uint64_t seed = 0;
+	uint32_t sweep = 0;         // sweeps done so far (Philox counter / scan-order key)
+	npb_z_t *z = nullptr;       // [N, C] item-major
+	float *theta = nullptr;     // [C, Kmax, PS]
+	int *counts = nullptr;      // [C, Kmax]
+	unsigned long long *st = nullptr; // [C, 4]: candidates, moved, births, reserved
+	int *kocc = nullptr;        // [C]
+	int *overflow = nullptr;    // [C]
+	npb_z_t *h_z = nullptr;     // pinned staging for npb_chains_sweep_host
+};
+
+struct SweepArgs {
+	const float *X, *Xw;
+	npb_z_t *z;
+	float *theta;
+	int *counts;
+	unsigned long long *st;
+	int *kocc, *overflow;
+	int N, C, Kmax;
+	uint32_t sweep0;
+	int n_sweeps;
+	uint64_t seed;
+	PriorDev prior;
+};
+
+npb_status npb_fail_cuda(npb_ctx *ctx, cudaError_t e, const char *expr, const char *file, int line);
+npb_status npb_fail(npb_ctx *ctx, npb_status s, const char *msg);
+
+// host linear algebra (double), npb_linalg.cpp
+bool npb_prepare_theta(int D, const double *mu, const double *Sigma, double *T_packed_upper, double *logdet);
+bool npb_prepare_prior(PriorHost &p);
+void npb_theta_to_sigma(int D, const double *T_packed_upper, double *Sigma);
+
+// launchers (npb_alg8.cu / npb_density.cu / npb_metrics.cu)
+npb_status npb_launch_whiten(npb_dataset *ds);
+npb_status npb_launch_chains_init(npb_chains *ch);
+npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps);
+PriorDev npb_prior_dev(const npb_ctx *ctx, int m_aux);

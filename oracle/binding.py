@@ -1,0 +1,234 @@
+"""ctypes binding of the CPU oracle (oracle/np_oracle.h).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (noparama_b200/) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ALG8, JAIN_NEAL, TRIADIC = 8, 2, 3
+DENSE_MATRIX, PER_CALL_LU, UPDATE_CLUSTERS, MAX_LIKELIHOOD, RECORD_TRACE, LOG_DOMAIN = (1 << i for i in range(6))
+FAITHFUL = DENSE_MATRIX | PER_CALL_LU | UPDATE_CLUSTERS | MAX_LIKELIHOOD
+
+
+class Prior(C.Structure):
+    _fields_ = [("D", C.c_int), ("mu0", C.POINTER(C.c_double)), ("kappa", C.c_double), ("nu", C.c_double),
+                ("Lambda", C.POINTER(C.c_double)), ("alpha", C.c_double)]
+
+
+class Options(C.Structure):
+    _fields_ = [("algorithm", C.c_int), ("T", C.c_int), ("K0", C.c_int), ("M_aux", C.c_int), ("mh_steps", C.c_int),
+                ("seed_main", C.c_uint32), ("seed_shuffle", C.c_uint32), ("flags", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("seconds_total", C.c_double), ("seconds_reassign", C.c_double), ("updates", C.c_int64),
+                ("density_evals", C.c_int64), ("candidates", C.c_int64), ("new_cluster_events", C.c_int64),
+                ("moved", C.c_int64), ("sm_attempts", C.c_int64 * 4), ("sm_accepts", C.c_int64 * 4),
+                ("sams_allocations", C.c_int64), ("mean_K", C.c_double), ("K_final", C.c_int),
+                ("max_loglik", C.c_double)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libnp_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("np_oracle.cpp", "np_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):
+        subprocess.check_call(["make", "-C", _HERE, "libnp_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        for name in ("npo_mvn_pdf", "npo_mvn_logpdf"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
+        for name in ("npo_mvn_pdf_dataset", "npo_mvn_logpdf_dataset"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.c_int]
+        L.npo_mvn_logpdf_batch.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                           C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        L.npo_weighted_pick_u.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double]
+        L.npo_weighted_pick_freq.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int64)]
+        L.npo_sample_base.argtypes = [C.POINTER(Prior), C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.npo_lu_determinant.restype = C.c_double
+        L.npo_lu_determinant.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.npo_lu_inverse.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.npo_metrics.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
+        L.npo_membertrix_selftest.argtypes = [C.c_uint32, C.c_int]
+        L.npo_mcmc_run.restype = C.c_void_p
+        L.npo_mcmc_run.argtypes = [C.POINTER(Prior), C.POINTER(Options), C.POINTER(C.c_double), C.c_int]
+        L.npo_run_free.argtypes = [C.c_void_p]
+        L.npo_run_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.npo_run_assignments.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.npo_run_params.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_int64), C.c_int]
+        L.npo_run_init_K.argtypes = [C.c_void_p]
+        L.npo_run_init_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]
+        L.npo_trace_steps.restype = C.c_int64
+        L.npo_trace_steps.argtypes = [C.c_void_p]
+        L.npo_trace_order_len.restype = C.c_int64
+        L.npo_trace_order_len.argtypes = [C.c_void_p]
+        L.npo_trace_max_slot.argtypes = [C.c_void_p]
+        L.npo_trace_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+        _LIB = L
+    return _LIB
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def mvn_pdf(mu, Sigma, x):
+    mu, Sigma, x = _f64(mu), _f64(Sigma), _f64(x)
+    return lib().npo_mvn_pdf(len(mu), _dp(mu), _dp(Sigma), _dp(x))
+
+
+def mvn_logpdf(mu, Sigma, x):
+    mu, Sigma, x = _f64(mu), _f64(Sigma), _f64(x)
+    return lib().npo_mvn_logpdf(len(mu), _dp(mu), _dp(Sigma), _dp(x))
+
+
+def mvn_pdf_dataset(mu, Sigma, X):
+    mu, Sigma, X = _f64(mu), _f64(Sigma), _f64(X)
+    return lib().npo_mvn_pdf_dataset(len(mu), _dp(mu), _dp(Sigma), _dp(X), X.shape[0])
+
+
+def mvn_logpdf_dataset(mu, Sigma, X):
+    mu, Sigma, X = _f64(mu), _f64(Sigma), _f64(X)
+    return lib().npo_mvn_logpdf_dataset(len(mu), _dp(mu), _dp(Sigma), _dp(X), X.shape[0])
+
+
+def mvn_logpdf_batch(mu, Sigma, X):
+    """mu [K,D], Sigma [K,D,D], X [n,D] -> [n,K]"""
+    mu, Sigma, X = _f64(mu), _f64(Sigma), _f64(X)
+    K, D = mu.shape
+    out = np.empty((X.shape[0], K), dtype=np.float64)
+    lib().npo_mvn_logpdf_batch(D, _dp(mu), _dp(Sigma), K, _dp(X), X.shape[0], _dp(out))
+    return out
+
+
+def weighted_pick_u(w, u):
+    w = _f64(w)
+    return lib().npo_weighted_pick_u(_dp(w), len(w), float(u))
+
+
+def weighted_pick_freq(w, draws, seed):
+    w = _f64(w)
+    freq = np.zeros(len(w), dtype=np.int64)
+    lib().npo_weighted_pick_freq(_dp(w), len(w), draws, seed, freq.ctypes.data_as(C.POINTER(C.c_int64)))
+    return freq
+
+
+def make_prior(mu0, kappa, nu, Lambda, alpha):
+    mu0, Lambda = _f64(mu0), _f64(Lambda)
+    p = Prior(len(mu0), _dp(mu0), kappa, nu, _dp(Lambda), alpha)
+    p._keep = (mu0, Lambda)
+    return p
+
+
+def sample_base(prior, seed, count):
+    D = prior.D
+    mu = np.empty((count, D))
+    Sigma = np.empty((count, D, D))
+    lib().npo_sample_base(C.byref(prior), seed, count, _dp(mu), _dp(Sigma))
+    return mu, Sigma
+
+
+def lu_determinant(A):
+    A = _f64(A)
+    return lib().npo_lu_determinant(A.shape[0], _dp(A))
+
+
+def lu_inverse(A):
+    A = _f64(A)
+    out = np.empty_like(A)
+    lib().npo_lu_inverse(A.shape[0], _dp(A), _dp(out))
+    return out
+
+
+def metrics(truth, result):
+    truth = np.ascontiguousarray(truth, dtype=np.int32)
+    result = np.ascontiguousarray(result, dtype=np.int32)
+    out = np.zeros(3)
+    lib().npo_metrics(_ip(truth), _ip(result), len(truth), _dp(out))
+    return tuple(out)
+
+
+def membertrix_selftest(seed, dense=True):
+    return lib().npo_membertrix_selftest(seed, int(dense))
+
+
+class Run:
+    """One oracle run of MCMC::run (np_mcmc.cpp:48-175)."""
+
+    def __init__(self, prior, X, algorithm=ALG8, T=1000, K0=20, M_aux=3, mh_steps=20, seed_main=1, seed_shuffle=2,
+                 flags=FAITHFUL):
+        X = _f64(X)
+        self.N, self.D = X.shape
+        self.M_aux = M_aux
+        self.T = T
+        opt = Options(algorithm, T, K0, M_aux, mh_steps, seed_main, seed_shuffle, flags)
+        self._h = lib().npo_mcmc_run(C.byref(prior), C.byref(opt), _dp(X), self.N)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().npo_run_free(self._h)
+            self._h = None
+
+    def stats(self):
+        s = Stats()
+        lib().npo_run_stats(self._h, C.byref(s))
+        return s
+
+    def assignments(self, which=0):
+        z = np.empty(self.N, dtype=np.int32)
+        lib().npo_run_assignments(self._h, which, _ip(z))
+        return z
+
+    def params(self, cap=4096):
+        K = C.c_int()
+        mu = np.empty((cap, self.D))
+        Sigma = np.empty((cap, self.D, self.D))
+        counts = np.empty(cap, dtype=np.int64)
+        rc = lib().npo_run_params(self._h, C.byref(K), _dp(mu), _dp(Sigma), counts.ctypes.data_as(C.POINTER(C.c_int64)), cap)
+        assert rc == 0
+        return mu[:K.value].copy(), Sigma[:K.value].copy(), counts[:K.value].copy()
+
+    def init_state(self):
+        K = lib().npo_run_init_K(self._h)
+        z0 = np.empty(self.N, dtype=np.int32)
+        slots = np.empty(K, dtype=np.int32)
+        mu = np.empty((K, self.D))
+        Sigma = np.empty((K, self.D, self.D))
+        lib().npo_run_init_state(self._h, _ip(z0), _ip(slots), _dp(mu), _dp(Sigma))
+        return z0, slots, mu, Sigma
+
+    def trace(self):
+        S = lib().npo_trace_steps(self._h)
+        OL = lib().npo_trace_order_len(self._h)
+        M, D = self.M_aux, self.D
+        t = dict(item=np.empty(S, np.int32), K=np.empty(S, np.int32), order_off=np.empty(S + 1, np.int64),
+                 order=np.empty(OL, np.int32), aux_mu=np.empty((S, M, D)), aux_Sigma=np.empty((S, M, D, D)),
+                 u=np.empty(S), picked=np.empty(S, np.int32), new_slot=np.empty(S, np.int32),
+                 z_after=np.empty((self.T, self.N), np.int32))
+        lib().npo_trace_copy(self._h, *[t[k].ctypes.data for k in
+                                        ("item", "K", "order_off", "order", "aux_mu", "aux_Sigma", "u", "picked",
+                                         "new_slot", "z_after")])
+        t["max_slot"] = lib().npo_trace_max_slot(self._h)
+        return t
