@@ -125,12 +125,15 @@ npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, i
 /* one NealAlgorithm8::update(membertrix&, {item}) on one chain (the reference's single-item seam) */
 npb_status npb_chain_update_alg8(npb_chains *ch, int64_t chain, int64_t item);
 
-/* parity level 2: replay a recorded fp64 trace on one chain starting from the state set
- * with npb_chains_set_state.  steps = n_steps; per step: item, K candidates `order` (slot ids, ragged via
- * order_off [n_steps+1]), m_aux auxiliary thetas, the uniform u, the slot a picked auxiliary is born into.
- * picked_out [n_steps] receives the candidate index chosen by the device; z_after_out (may be NULL) receives
- * z after every `z_every` steps ([n_steps / z_every, N]). */
-npb_status npb_chain_replay_alg8(npb_chains *ch, int64_t chain, int64_t n_steps, const int32_t *item,
+/* parity level 2: replay a recorded trace of NealAlgorithm8::update in double precision with
+ * the reference's linear-domain weights, for one chain over `ds`, using the bound prior's alpha.
+ * Initial state: z0 [N] slot ids, K0 clusters (slots0, mu0 [K0,D], Sigma0 [K0,D,D]); nslots = slot capacity.
+ * Per step s < n_steps: item[s]; the K candidates order[order_off[s] .. order_off[s+1]) as slot ids in the order
+ * the reference iterated them; m_aux auxiliary thetas aux_mu [S,m,D], aux_Sigma [S,m,D,D]; the uniform u[s]; the
+ * slot new_slot[s] a picked auxiliary is born into.  picked_out [n_steps] receives the candidate index chosen on
+ * the device; z_after_out (may be NULL) receives z after every `z_every` steps ([n_steps / z_every, N]). */
+npb_status npb_replay_alg8(npb_ctx *ctx, npb_dataset *ds, int m_aux, int nslots, const int32_t *z0, int K0,
+		const int32_t *slots0, const double *mu0, const double *Sigma0, int64_t n_steps, const int32_t *item,
 		const int64_t *order_off, const int32_t *order, const double *aux_mu, const double *aux_Sigma,
 		const double *u, const int32_t *new_slot, int32_t *picked_out, int64_t z_every, int32_t *z_after_out);
 
@@ -154,6 +157,10 @@ npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_ancho
  * permutation of 0..N-1 shared by all chains of a run; order_out[s] = item visited at step s.  Pure host
  * function (no device needed); the kernels evaluate the same function point-wise. */
 npb_status npb_scan_order_host(uint64_t seed, uint32_t sweep, int64_t N, int32_t *order_out);
+
+/* measured FP32 FFMA peak of the context's device in TFLOP/s (register-resident FMA loop, best of 10): the
+ * roofline denominator of the sweep kernels, which are bound by the FP32 pipe */
+npb_status npb_fp32_peak(npb_ctx *ctx, double *tflops);
 
 int64_t npb_chains_count(npb_chains *ch);
 int npb_chains_kmax(npb_chains *ch);

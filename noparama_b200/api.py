@@ -24,9 +24,9 @@ EXPORTS = [
     "npb_ctx_create", "npb_ctx_destroy", "npb_ctx_stream", "npb_ctx_synchronize", "npb_status_str",
     "npb_ctx_last_error", "npb_dataset_upload", "npb_dataset_update", "npb_dataset_destroy", "npb_prior_set_niw",
     "npb_logdensity_batch", "npb_logdensity_sum", "npb_chains_create", "npb_chains_destroy", "npb_chains_set_state",
-    "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_chain_replay_alg8",
+    "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
-    "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host",
+    "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak",
 ]
 
 
@@ -78,7 +78,8 @@ def load_library():
     L.npb_chains_sweep.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SweepStats)]
     L.npb_chains_sweep_host.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(SweepStats)]
     L.npb_chain_update_alg8.argtypes = [vp, i64, i64]
-    L.npb_chain_replay_alg8.argtypes = [vp, i64, i64, ip, C.POINTER(i64), ip, dp, dp, dp, ip, ip, i64, ip]
+    L.npb_replay_alg8.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp, i64, ip, C.POINTER(i64), ip, dp, dp,
+                                  dp, ip, ip, i64, ip]
     L.npb_chains_get_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -220,6 +221,33 @@ class MultivariateNormal:
         out = np.empty(K, dtype=np.float64)
         self.ctx.check(self.ctx._lib.npb_logdensity_sum(self.ctx._h, self.ds._h, rp, n, _dp(mu), _dp(Sigma), K, _dp(out)))
         return out
+
+
+def replay_alg8(ctx, dataset, trace, init_state, m_aux=3, z_every=None):
+    """Parity level 2: replay a recorded NealAlgorithm8 trace in double precision (npb_replay_alg8).
+
+    trace: dict with item, order_off, order, aux_mu, aux_Sigma, u, new_slot, max_slot (oracle/binding.py Run.trace());
+    init_state: (z0, slots, mu, Sigma).  Returns (picked [S], z_after [S // z_every, N])."""
+    z0, slots, mu, Sigma = init_state
+    z0 = np.ascontiguousarray(z0, dtype=np.int32)
+    slots = np.ascontiguousarray(slots, dtype=np.int32)
+    mu, Sigma = _f64(mu), _f64(Sigma)
+    S = len(trace["item"])
+    N = dataset.N
+    z_every = N if z_every is None else z_every
+    item = np.ascontiguousarray(trace["item"], dtype=np.int32)
+    off = np.ascontiguousarray(trace["order_off"], dtype=np.int64)
+    order = np.ascontiguousarray(trace["order"], dtype=np.int32)
+    aux_mu, aux_Sigma, u = _f64(trace["aux_mu"]), _f64(trace["aux_Sigma"]), _f64(trace["u"])
+    new_slot = np.ascontiguousarray(trace["new_slot"], dtype=np.int32)
+    picked = np.empty(S, dtype=np.int32)
+    z_after = np.empty((S // z_every, N), dtype=np.int32)
+    nslots = int(max(trace.get("max_slot", 0), slots.max() + 1, new_slot.max() + 1))
+    ctx.check(ctx._lib.npb_replay_alg8(ctx._h, dataset._h, m_aux, nslots, _ip(z0), len(slots), _ip(slots), _dp(mu),
+                                       _dp(Sigma), S, _ip(item), off.ctypes.data_as(C.POINTER(C.c_int64)), _ip(order),
+                                       _dp(aux_mu), _dp(aux_Sigma), _dp(u), _ip(new_slot), _ip(picked), z_every,
+                                       _ip(z_after)))
+    return picked, z_after
 
 
 class Chains:

@@ -12,11 +12,11 @@ npb_status npb_launch_logdensity_sum(npb_ctx *, npb_dataset *, const int64_t *, 
 		const double *, double *);
 npb_status npb_launch_metrics(npb_chains *, const int32_t *, int, double *, double *, double *, double *, int32_t *);
 npb_status npb_launch_cocluster(npb_chains *, const int64_t *, int, float *, int);
-npb_status npb_launch_replay_alg8(npb_chains *ch, int64_t chain, int64_t n_steps, const int32_t *d_item,
-		const int64_t *d_order_off, const int32_t *d_order, const double *d_aux_mu, const double *d_aux_T,
-		const double *d_aux_c, const double *d_u, const int32_t *d_new_slot, int32_t *d_picked, int64_t z_every,
-		int32_t *d_z_after, const double *d_mu, const double *d_T, const double *d_c, const int32_t *d_z0,
-		const int32_t *d_cnt0, int nslots, int *d_status);
+npb_status npb_launch_fma_peak(npb_ctx *ctx, double *tflops);
+npb_status npb_launch_replay(npb_ctx *ctx, const double *X, int N, int D, int M, double alpha, int nslots, double *theta,
+		int *counts, int32_t *z, int64_t n_steps, const int32_t *item, const int64_t *order_off, const int32_t *order,
+		const double *aux_theta, const double *u, const int32_t *new_slot, int32_t *picked, int64_t z_every,
+		int32_t *z_after, int *status);
 
 npb_status npb_fail_cuda(npb_ctx *ctx, cudaError_t e, const char *expr, const char *file, int line) {
 	if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s (%s:%d)", cudaGetErrorString(e), expr, file, line);
@@ -565,13 +565,93 @@ npb_status npb_scan_order_host(uint64_t seed, uint32_t sweep, int64_t N, int32_t
 	return NPB_OK;
 }
 
+npb_status npb_fp32_peak(npb_ctx *ctx, double *tflops) {
+	if (!ctx || !tflops) return NPB_E_BAD_ARG;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	return npb_launch_fma_peak(ctx, tflops);
+}
+
 npb_status npb_chain_update_alg8(npb_chains *ch, int64_t, int64_t) {
 	return npb_fail(ch ? ch->ctx : nullptr, NPB_E_UNSUPPORTED, "single-item seam not built yet");
 }
 
-npb_status npb_chain_replay_alg8(npb_chains *ch, int64_t, int64_t, const int32_t *, const int64_t *, const int32_t *,
-		const double *, const double *, const double *, const int32_t *, int32_t *, int64_t, int32_t *) {
-	return npb_fail(ch ? ch->ctx : nullptr, NPB_E_UNSUPPORTED, "replay not built yet");
+// theta in the replay kernel's double layout: mu[D], T upper packed, c = -0.5 (D log 2pi + log det Sigma)
+static bool pack_theta64(int D, const double *mu, const double *Sigma, double *out) {
+	const int TRI = npb_tri(D);
+	double logdet;
+	if (!npb_prepare_theta(D, mu, Sigma, out + D, &logdet)) return false;
+	for (int d = 0; d < D; ++d) out[d] = mu[d];
+	out[D + TRI] = -0.5 * (D * std::log(2.0 * M_PI) + logdet);
+	return true;
+}
+
+npb_status npb_replay_alg8(npb_ctx *ctx, npb_dataset *ds, int m_aux, int nslots, const int32_t *z0, int K0,
+		const int32_t *slots0, const double *mu0, const double *Sigma0, int64_t n_steps, const int32_t *item,
+		const int64_t *order_off, const int32_t *order, const double *aux_mu, const double *aux_Sigma,
+		const double *u, const int32_t *new_slot, int32_t *picked_out, int64_t z_every, int32_t *z_after_out) {
+	if (!ctx || !ds || ds->ctx != ctx || !z0 || !slots0 || !mu0 || !Sigma0 || !item || !order_off || !order || !aux_mu ||
+			!aux_Sigma || !u || !new_slot || !picked_out || m_aux <= 0 || nslots <= 0 || K0 <= 0 || K0 > nslots || n_steps <= 0)
+		return NPB_E_BAD_ARG;
+	if (!ctx->prior.set || ctx->prior.D != ds->D) return npb_fail(ctx, NPB_E_BAD_ARG, "set a prior of the dataset's dimension first");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ds->D, PS = npb_ps(D), N = (int)ds->N;
+	std::vector<double> theta((size_t)nslots * PS, 0.0);
+	std::vector<int> counts(nslots, 0);
+	for (int k = 0; k < K0; ++k) {
+		if (slots0[k] < 0 || slots0[k] >= nslots) return NPB_E_BAD_ARG;
+		if (!pack_theta64(D, mu0 + (size_t)k * D, Sigma0 + (size_t)k * D * D, theta.data() + (size_t)slots0[k] * PS))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "initial Sigma not invertible");
+	}
+	for (int i = 0; i < N; ++i) {
+		if (z0[i] < 0 || z0[i] >= nslots) return NPB_E_BAD_ARG;
+		counts[z0[i]]++;
+	}
+	for (int64_t s = 0; s < n_steps; ++s)
+		if (item[s] < 0 || item[s] >= N || order_off[s + 1] < order_off[s]) return NPB_E_BAD_ARG;
+	std::vector<double> aux((size_t)n_steps * m_aux * PS);
+	for (int64_t t = 0; t < n_steps * m_aux; ++t)
+		if (!pack_theta64(D, aux_mu + (size_t)t * D, aux_Sigma + (size_t)t * D * D, aux.data() + (size_t)t * PS))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "auxiliary Sigma not invertible");
+	const int64_t n_order = order_off[n_steps];
+	const int64_t n_snap = (z_after_out && z_every > 0) ? n_steps / z_every : 0;
+	DevBuf<double> d_theta, d_aux, d_u;
+	DevBuf<int> d_counts, d_status;
+	DevBuf<int32_t> d_z, d_item, d_order, d_new, d_picked, d_zafter;
+	DevBuf<int64_t> d_off;
+	NPB_CUDA_OK(d_theta.alloc(theta.size()));
+	NPB_CUDA_OK(d_aux.alloc(aux.size()));
+	NPB_CUDA_OK(d_u.alloc(n_steps));
+	NPB_CUDA_OK(d_counts.alloc(nslots));
+	NPB_CUDA_OK(d_status.alloc(1));
+	NPB_CUDA_OK(d_z.alloc(N));
+	NPB_CUDA_OK(d_item.alloc(n_steps));
+	NPB_CUDA_OK(d_order.alloc(n_order));
+	NPB_CUDA_OK(d_new.alloc(n_steps));
+	NPB_CUDA_OK(d_picked.alloc(n_steps));
+	NPB_CUDA_OK(d_zafter.alloc((size_t)n_snap * N));
+	NPB_CUDA_OK(d_off.alloc(n_steps + 1));
+	cudaStream_t st = ctx->stream;
+	int zero = 0;
+	NPB_CUDA_OK(cudaMemcpyAsync(d_theta.p, theta.data(), sizeof(double) * theta.size(), cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_aux.p, aux.data(), sizeof(double) * aux.size(), cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_u.p, u, sizeof(double) * n_steps, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_counts.p, counts.data(), sizeof(int) * nslots, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_status.p, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_z.p, z0, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_item.p, item, sizeof(int32_t) * n_steps, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_order.p, order, sizeof(int32_t) * n_order, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_new.p, new_slot, sizeof(int32_t) * n_steps, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_off.p, order_off, sizeof(int64_t) * (n_steps + 1), cudaMemcpyHostToDevice, st));
+	npb_status s = npb_launch_replay(ctx, ds->X64, N, D, m_aux, ctx->prior.alpha, nslots, d_theta.p, d_counts.p, d_z.p, n_steps,
+			d_item.p, d_off.p, d_order.p, d_aux.p, d_u.p, d_new.p, d_picked.p, z_every, n_snap ? d_zafter.p : nullptr, d_status.p);
+	if (s != NPB_OK) return s;
+	int status = 0;
+	NPB_CUDA_OK(cudaMemcpyAsync(picked_out, d_picked.p, sizeof(int32_t) * n_steps, cudaMemcpyDeviceToHost, st));
+	if (n_snap) NPB_CUDA_OK(cudaMemcpyAsync(z_after_out, d_zafter.p, sizeof(int32_t) * n_snap * N, cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaStreamSynchronize(st));
+	if (status != 0) return npb_fail(ctx, status, "replay stopped: candidate index past the end or slot out of range");
+	return NPB_OK;
 }
 
 } // extern "C"

@@ -9,8 +9,11 @@
 //   MCMC::considerMaxLikelihood (src/np_mcmc.cpp:187-203), one CTA per chain.
 #include "npb_internal.h"
 
+// T = double: everything in double.  T = float: the quadratic form in float, but the difference x - mu is formed
+// in double first (float coordinates would lose |x| * 6e-8, which is 1e-5 of a tight cluster's scale and breaks the
+// 1e-5 relative bar on the log-density).
 template <typename T>
-__global__ void k_logdensity(const T *X, const int64_t *rows, int64_t n_rows, int D, const T *mu, const T *Tf,
+__global__ void k_logdensity(const double *X, const int64_t *rows, int64_t n_rows, int D, const double *mu, const T *Tf,
 		const T *cst, int K, double *out) {
 	const int TRI = npb_tri(D);
 	int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -18,13 +21,13 @@ __global__ void k_logdensity(const T *X, const int64_t *rows, int64_t n_rows, in
 	const int64_t r = idx / K;
 	const int k = (int)(idx - r * K);
 	const int64_t i = rows ? rows[r] : r;
-	const T *x = X + i * D;
-	const T *m = mu + (size_t)k * D;
+	const double *x = X + i * D;
+	const double *m = mu + (size_t)k * D;
 	const T *t = Tf + (size_t)k * TRI;
 	T q = 0;
 	for (int a = 0; a < D; ++a) {
 		T y = 0;
-		for (int b = a; b < D; ++b) y += t[npb_tri_off(D, a, b)] * (x[b] - m[b]);
+		for (int b = a; b < D; ++b) y += t[npb_tri_off(D, a, b)] * (T)(x[b] - m[b]);
 		q += y * y;
 	}
 	out[idx] = (double)(cst[k] - (T)0.5 * q);
@@ -156,7 +159,7 @@ npb_status npb_launch_logdensity(npb_ctx *ctx, npb_dataset *ds, const int64_t *d
 	if (precision == 64)
 		k_logdensity<double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X64, d_rows, n_rows, ds->D, d_mu, d_T, d_c, K, d_out);
 	else
-		k_logdensity<float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X32, d_rows, n_rows, ds->D, f_mu, f_T, f_c, K, d_out);
+		k_logdensity<float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X64, d_rows, n_rows, ds->D, d_mu, f_T, f_c, K, d_out);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
@@ -186,5 +189,44 @@ npb_status npb_launch_cocluster(npb_chains *ch, const int64_t *d_anchors, int n_
 	dim3 grid((n_anchor + 127) / 128, n_anchor);
 	k_cocluster<<<grid, 128, 0, ctx->stream>>>(ch->z, d_anchors, n_anchor, (int)ch->C, S_dev, accumulate);
 	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+// ---- FP32 FFMA peak of the device (roofline denominator for the sweep kernels; SURVEY 8d asks the builder to
+// measure it because MEASURED_PEAKS.json holds only HBM and bf16 tensor figures) -------------------------------
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b) {
+	float r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int u = 0; u < 16; ++u) {
+			r0 = fmaf(r0, a, b); r1 = fmaf(r1, a, b); r2 = fmaf(r2, a, b); r3 = fmaf(r3, a, b);
+			r4 = fmaf(r4, a, b); r5 = fmaf(r5, a, b); r6 = fmaf(r6, a, b); r7 = fmaf(r7, a, b);
+		}
+	}
+	float s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+	if (s == 123.456f) out[0] = s;
+}
+
+npb_status npb_launch_fma_peak(npb_ctx *ctx, double *tflops) {
+	float *d = nullptr;
+	NPB_CUDA_OK(cudaMalloc((void **)&d, sizeof(float)));
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const int blocks = sms * 8, threads = 256, iters = 4096;
+	double best = 0.0;
+	for (int rep = 0; rep < 12; ++rep) {
+		cudaEventRecord(ctx->ev0, ctx->stream);
+		k_fma_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999f, 0.001f);
+		cudaEventRecord(ctx->ev1, ctx->stream);
+		cudaError_t e = cudaStreamSynchronize(ctx->stream);
+		if (e != cudaSuccess) { cudaFree(d); return npb_fail_cuda(ctx, e, "k_fma_peak", __FILE__, __LINE__); }
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+		double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+		double tf = fl / (ms * 1e-3) / 1e12;
+		if (rep >= 2 && tf > best) best = tf;
+	}
+	cudaFree(d);
+	*tflops = best;
 	return NPB_OK;
 }

@@ -77,6 +77,7 @@ def lib():
         L.npo_run_assignments.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.npo_run_params.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_int64), C.c_int]
+        L.npo_run_sweep_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.npo_run_init_K.argtypes = [C.c_void_p]
         L.npo_run_init_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
@@ -195,6 +196,11 @@ class Run:
         s = Stats()
         lib().npo_run_stats(self._h, C.byref(s))
         return s
+
+    def sweep_seconds(self):
+        a, b = np.empty(self.T), np.empty(self.T)
+        lib().npo_run_sweep_seconds(self._h, _dp(a), _dp(b))
+        return a, b
 
     def assignments(self, which=0):
         z = np.empty(self.N, dtype=np.int32)

@@ -526,6 +526,7 @@ struct npo_run {
 	std::vector<int> tr_item, tr_K, tr_order, tr_picked, tr_new_slot, tr_z_after;
 	std::vector<int64_t> tr_order_off;
 	std::vector<double> tr_aux_mu, tr_aux_sigma, tr_u;
+	std::vector<double> sweep_reassign_seconds, sweep_total_seconds;
 	/* slot allocator */
 	std::vector<char> slot_used;
 	int alloc_slot() {
@@ -759,10 +760,15 @@ struct Sampler {
 					sm_update(subset);
 				st.updates++;
 			}
-			reassign_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			{
+				double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+				reassign_seconds += dt;
+				run.sweep_reassign_seconds.push_back(dt);
+			}
 			if (record) record_z_after();
 			if (run.opt.flags & NPO_UPDATE_CLUSTERS) update_clusters(run.opt.mh_steps); /* :170 */
 			if ((run.opt.flags & NPO_MAX_LIKELIHOOD) && t % 5 == 0) consider_max_likelihood(); /* :172-174 */
+			run.sweep_total_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 		}
 		st.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
 		st.seconds_reassign = reassign_seconds;
@@ -949,6 +955,10 @@ void npo_run_init_state(const npo_run *r, int *z0, int *slots, double *mu, doubl
 	std::memcpy(slots, r->init_slots.data(), sizeof(int) * r->init_slots.size());
 	std::memcpy(mu, r->init_mu.data(), sizeof(double) * r->init_mu.size());
 	std::memcpy(Sigma, r->init_sigma.data(), sizeof(double) * r->init_sigma.size());
+}
+void npo_run_sweep_seconds(const npo_run *r, double *reassign, double *total) {
+	std::memcpy(reassign, r->sweep_reassign_seconds.data(), sizeof(double) * r->sweep_reassign_seconds.size());
+	std::memcpy(total, r->sweep_total_seconds.data(), sizeof(double) * r->sweep_total_seconds.size());
 }
 int64_t npo_trace_steps(const npo_run *r) { return (int64_t)r->tr_item.size(); }
 int64_t npo_trace_order_len(const npo_run *r) { return (int64_t)r->tr_order.size(); }

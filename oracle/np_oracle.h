@@ -109,6 +109,8 @@ npo_run *npo_mcmc_run(const npo_prior *prior, const npo_options *opt, const doub
 void npo_run_free(npo_run *r);
 void npo_run_stats(const npo_run *r, npo_stats *out);
 void npo_run_assignments(const npo_run *r, int which /*0 final, 1 max-likelihood*/, int *z_out /*[N], compact labels*/);
+/* per-sweep wall time: the update() loop only (np_mcmc.cpp:146-163) and the whole sweep body; [T] each */
+void npo_run_sweep_seconds(const npo_run *r, double *reassign, double *total);
 int npo_run_params(const npo_run *r, int *K, double *mu /*[K,D]*/, double *Sigma /*[K,D,D]*/, int64_t *counts, int cap);
 
 /* initial state (after np_mcmc.cpp:49-91), in SLOT numbering: for GPU replay */
