@@ -109,6 +109,7 @@ static SweepArgs make_args(npb_chains *ch, int n_sweeps) {
 	a.sweep0 = ch->sweep;
 	a.n_sweeps = n_sweeps;
 	a.seed = ch->seed;
+	a.scan_order = ch->scan_order;
 	a.prior = npb_prior_dev(ch->ctx, ch->m_aux);
 	return a;
 }
@@ -141,7 +142,21 @@ NPB_DECL(2, 1) NPB_DECL(2, 2) NPB_DECL(2, 4) NPB_DECL(2, 8) NPB_DECL(2, 16)
 NPB_DECL(3, 1) NPB_DECL(3, 2) NPB_DECL(3, 4) NPB_DECL(3, 8)
 #undef NPB_DECL
 
-npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
+// scan order of sweeps sweep0 .. sweep0+n_sweeps-1 into order[n_sweeps][N] (npb_common.cuh: keyed permutation with
+// cycle walking; evaluated once per sweep here instead of per chain inside the sweep kernel)
+__global__ void k_scan_order(int32_t *order, int N, uint64_t seed, uint32_t sweep0) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	const ScanOrder so = npb_scan_order(seed, sweep0 + blockIdx.y, (uint32_t)N);
+	order[(size_t)blockIdx.y * N + s] = (int32_t)npb_scan_item(so, (uint32_t)s);
+}
+
+static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
+	npb_ctx *ctx = ch->ctx;
+	const int N = (int)ch->ds->N;
+	dim3 grid((N + 255) / 256, n_sweeps);
+	k_scan_order<<<grid, 256, 0, ctx->stream>>>(ch->scan_order, N, ch->seed, ch->sweep);
+	NPB_CUDA_OK(cudaGetLastError());
 	SweepArgs a = make_args(ch, n_sweeps);
 	npb_status s = NPB_E_UNSUPPORTED;
 	const int key = ch->D * 1000 + ch->Kmax / 32;
@@ -156,9 +171,27 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 	case 3004: s = npb_launch_alg8_reg<3, 4>(ch, a); break;
 	case 3008: s = npb_launch_alg8_reg<3, 8>(ch, a); break;
 	default:
-		return npb_fail(ch->ctx, NPB_E_UNSUPPORTED,
+		return npb_fail(ctx, NPB_E_UNSUPPORTED,
 				"Alg. 8 sweep kernels cover D = 2 (Kmax 32/64/128/256/512) and D = 3 (Kmax 32/64/128/256)");
 	}
 	if (s == NPB_OK) ch->sweep += (uint32_t)n_sweeps;
 	return s;
+}
+
+npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
+	npb_ctx *ctx = ch->ctx;
+	if (!ch->scan_order) {
+		// as many sweeps per launch as fit 64 MB of scan orders
+		const size_t per_sweep = (size_t)ch->ds->N * sizeof(int32_t);
+		size_t cap = (64u << 20) / per_sweep;
+		ch->scan_cap = (int)(cap < 1 ? 1 : (cap > 1024 ? 1024 : cap));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->scan_order, per_sweep * ch->scan_cap));
+	}
+	for (int done = 0; done < n_sweeps;) {
+		const int n = (n_sweeps - done < ch->scan_cap) ? n_sweeps - done : ch->scan_cap;
+		npb_status s = launch_chunk(ch, n);
+		if (s != NPB_OK) return s;
+		done += n;
+	}
+	return NPB_OK;
 }

@@ -5,26 +5,6 @@
 
 #define NPB_SWEEP_WARPS 2
 
-__device__ __forceinline__ float warp_max(float v) {
-	int i = __float_as_int(v);
-	i ^= (i >> 31) & 0x7fffffff; // order-preserving map float -> signed int
-	i = __reduce_max_sync(0xffffffffu, i);
-	i ^= (i >> 31) & 0x7fffffff;
-	return __int_as_float(i);
-}
-__device__ __forceinline__ float warp_inclusive_sum(float v, int lane) {
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		float t = __shfl_up_sync(0xffffffffu, v, o);
-		if (lane >= o) v += t;
-	}
-	return v;
-}
-__device__ __forceinline__ float fast_ex2(float x) {
-	float y;
-	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-	return y;
-}
 __device__ __forceinline__ float fast_lg2(float x) {
 	float y;
 	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -70,12 +50,14 @@ __device__ inline void npb_draw_theta(const PriorDev &pr, const Philox &ph, uint
 // cumulative-sum rule for bit-exact parity with recorded draws.)
 //
 // A step is split in two stages so that consecutive steps overlap inside one warp:
-//   stage A(j)  -- independent of the chain state step j-1 changes: broadcast item j, log2-densities of the
-//                  occupied slots (empty slots carry c2 = -inf), Exp(1) noise from Philox, base_s = l_s - log2 E_s;
-//   stage B(j)  -- the sequential part: key_s = base_s + log2(n_s - own), warp arg-max, count update.
-// The loop issues A(j+1) together with B(j); a birth (which changes theta) re-issues A(j+1).
-// The number of register levels in use (NL = ceil(highest occupied slot / 32)) is a compile-time parameter of the
-// step loop, re-dispatched whenever a birth opens a new level, so the per-level code is straight-line.
+//   stage A(j)  -- independent of the chain state step j-1 changes: broadcast item j, log2-densities of every
+//                  slot, Exp(1) noise, base_s = l_s - log2 E_s;
+//   stage B(j)  -- the sequential part: key_s = base_s + log2(n_s - own)  (-inf for an empty slot), warp arg-max,
+//                  count update.
+// The step loop issues A(j+1) together with B(j) and only ever writes the counts: a step won by an auxiliary
+// draw (a birth, ~3e-5 of the steps) leaves the loop and is finished by generic code at tile level, which then
+// re-enters the loop.  The number of register levels in use (NL = ceil(highest occupied slot / 32)) is a
+// compile-time parameter of the step loop, so the per-level code is straight-line.
 // ---------------------------------------------------------------------------------------------------------
 template <int D, int SPL, int M>
 struct SweepState {
@@ -86,20 +68,20 @@ struct SweepState {
 	unsigned long long st_cand, st_moved, st_births;
 };
 
-template <int D, int M, int NC>
+template <int D, int M, int NG>
 struct TileRegs {          // what lane j holds for step s0 + j of the current tile
 	int zold_aux;          // old slot | (winning auxiliary index << 16)
 	int znew;
 	float x[D];
 	float auxkey;          // max_m [ log2 p(x|theta'_m) alpha/M - log2 E_m ]
 	float av[M];
-	float g[NC * 4];
+	float g[NG];
 	uint32_t rs[4];        // xoshiro128++ state of this lane for the tile's race noise (seeded from Philox per tile)
 };
 
 template <int NL>
 struct StageA {
-	float base[NL], ownf[NL];
+	float base[NL];
 	float auxkey;
 	int zo_aux;
 };
@@ -132,16 +114,13 @@ __device__ __forceinline__ float neg_lg2_exp1(uint32_t r) {
 	return -fast_lg2(e);
 }
 
-template <int D, int SPL, int M, int NC, int NL>
-__device__ __forceinline__ void stage_a(const SweepState<D, SPL, M> &S, TileRegs<D, M, NC> &t, int lane, int j, StageA<NL> &o) {
+template <int D, int SPL, int M, int NG, int NL>
+__device__ __forceinline__ void stage_a(const SweepState<D, SPL, M> &S, TileRegs<D, M, NG> &t, int j, StageA<NL> &o) {
 	float xs[D];
 #pragma unroll
 	for (int d = 0; d < D; ++d) xs[d] = __shfl_sync(0xffffffffu, t.x[d], j);
 	o.auxkey = __shfl_sync(0xffffffffu, t.auxkey, j);
 	o.zo_aux = __shfl_sync(0xffffffffu, t.zold_aux, j);
-	const int zo = o.zo_aux & 0xffff;
-	const int osub = zo >> 5;
-	const bool is_olane = lane == (zo & 31);
 #pragma unroll
 	for (int s = 0; s < NL; ++s) {
 		float dd[D];
@@ -156,150 +135,168 @@ __device__ __forceinline__ void stage_a(const SweepState<D, SPL, M> &S, TileRegs
 			q = fmaf(y, y, q);
 		}
 		o.base[s] = (S.c2[s] - q) + neg_lg2_exp1(xoshiro_next(t.rs));
-		o.ownf[s] = (is_olane && osub == s) ? 1.0f : 0.0f;
 	}
 }
 
-// runs steps j0 .. cnt-1 of the current tile with NL register levels; returns the next step to run (== cnt unless a
-// birth opened level NL, in which case the caller re-dispatches with more levels)
-template <int D, int SPL, int M, int NC, int NL>
-__device__ __forceinline__ int run_steps(SweepState<D, SPL, M> &S, TileRegs<D, M, NC> &t, const SweepArgs &a, int lane, int j0, int cnt) {
-	constexpr int TRI = npb_tri(D);
-	StageA<NL> cur, nxt;
-	stage_a<D, SPL, M, NC, NL>(S, t, lane, j0, cur);
-	int j = j0;
-	while (j < cnt) {
-		// -------- stage A of the next step: independent of everything below --------
-		stage_a<D, SPL, M, NC, NL>(S, t, lane, (j + 1) & 31, nxt);
+#define NPB_STEP_BIRTH 0x100
 
-		// -------- stage B of this step --------
+// Runs steps j0 .. cnt-1 of the current tile with NL register levels.  Returns cnt when the tile is done, or
+// (j | NPB_STEP_BIRTH) when step j was won by an auxiliary draw: nothing of step j has been applied yet and the caller
+// finishes it.  Only S.n and the counters are written here.
+template <int D, int SPL, int M, int NG, int NL>
+__device__ __forceinline__ int run_steps(SweepState<D, SPL, M> &S, TileRegs<D, M, NG> &t, int lane, int j0, int cnt) {
+	StageA<NL> bufA, bufB;
+	int myslot[NL];
+#pragma unroll
+	for (int s = 0; s < NL; ++s) myslot[s] = s * 32 + lane;
+	int j = j0;
+	int ret = cnt;
+	stage_a<D, SPL, M, NG, NL>(S, t, j0, bufA);
+
+	// one step: stage A of step j+1 into `nxt`, stage B of step j from `cur`; returns false to leave the loop
+	auto step = [&](const StageA<NL> &cur, StageA<NL> &nxt) -> bool {
+		stage_a<D, SPL, M, NG, NL>(S, t, (j + 1) & 31, nxt);
 		const int zo = cur.zo_aux & 0xffff;
 		float key[NL];
 		float kmax = -INFINITY;
 #pragma unroll
 		for (int s = 0; s < NL; ++s) {
-			key[s] = cur.base[s] + fast_lg2(S.n[s] - cur.ownf[s]);
+			const float ne = (zo == myslot[s]) ? S.n[s] - 1.0f : S.n[s];
+			key[s] = cur.base[s] + fast_lg2(ne);
 			kmax = fmaxf(kmax, key[s]);
 		}
 		const int my_enc = float_order_key(kmax);
-		const int aux_enc = float_order_key(cur.auxkey);
-		const int top = max(__reduce_max_sync(0xffffffffu, my_enc), aux_enc);
+		const int top = max(__reduce_max_sync(0xffffffffu, my_enc), float_order_key(cur.auxkey));
 		const unsigned b = __ballot_sync(0xffffffffu, my_enc == top && kmax > -INFINITY);
-		int sub = 0;
-#pragma unroll
-		for (int s = NL - 1; s >= 0; --s)
-			if (key[s] == kmax) sub = s;
-		int new_slot = __shfl_sync(0xffffffffu, sub * 32 + lane, (__ffs(b) - 1) & 31);
-		const bool birth = (b == 0u); // an auxiliary draw won (or nothing had weight: open a cluster as well)
-
-		S.cand_tile += (unsigned)(S.kocc + M);
-		bool redo_next = false, level_opened = false;
-		if (birth || new_slot != zo) {
-			// retract (membertrix.cpp:175-233): the emptied cluster disappears (its theta is not recycled, Q6)
-			bool dead = false;
-			float c2dead = 0.0f;
-#pragma unroll
-			for (int s = 0; s < NL; ++s)
-				if (cur.ownf[s] != 0.0f) {
-					S.n[s] -= 1.0f;
-					if (S.n[s] <= 0.0f) { dead = true; c2dead = S.c2[s]; S.c2[s] = -INFINITY; }
-				}
-			const bool died = __any_sync(0xffffffffu, dead);
-			if (died) { S.kocc--; S.cand_tile--; }
-			if (birth) {
-				// np_neal_algorithm8.cpp:136-145: the lowest free slot takes theta' of the winning auxiliary draw
-				int fsub = -1, fl = 0;
-#pragma unroll
-				for (int s = 0; s < SPL; ++s) {
-					const unsigned fb = __ballot_sync(0xffffffffu, S.n[s] <= 0.0f);
-					if (fsub < 0 && fb) { fsub = s; fl = __ffs(fb) - 1; }
-				}
-				if (fsub < 0) {
-					// no room: flag the chain and put the item back where it was
-					S.overflow = 1;
-					new_slot = zo;
-					if (died) S.kocc++;
-#pragma unroll
-					for (int s = 0; s < NL; ++s)
-						if (cur.ownf[s] != 0.0f && dead) S.c2[s] = c2dead;
-				} else {
-					new_slot = fsub * 32 + fl;
-					const int aux_pick = (cur.zo_aux >> 16) & 0xff;
-					// the lane that owns this step holds the auxiliary draws: re-derive theta' of the winner
-					float avp = 1.0f, gz[D];
-#pragma unroll
-					for (int m = 0; m < M; ++m)
-						if (m == aux_pick) {
-							avp = t.av[m];
-#pragma unroll
-							for (int d = 0; d < D; ++d) gz[d] = t.g[m * (D + 1) + 1 + d];
-						}
-					avp = __shfl_sync(0xffffffffu, avp, j);
-					float munew[D];
-#pragma unroll
-					for (int d = 0; d < D; ++d) munew[d] = a.prior.mu0[d];
-					const float sc = avp * a.prior.inv_sqrt_kappa;
-#pragma unroll
-					for (int c = 0; c < D; ++c) {
-						const float gc = __shfl_sync(0xffffffffu, gz[c], j) * sc;
-#pragma unroll
-						for (int r = 0; r <= c; ++r) munew[r] = fmaf(a.prior.S[npb_tri_off(D, r, c)], gc, munew[r]);
-					}
-					const float inv = 1.0f / avp;
-					const float c2new = a.prior.c0_2 - (float)D * log2f(avp);
-#pragma unroll
-					for (int s = 0; s < SPL; ++s)
-						if (s == fsub && lane == fl) {
-#pragma unroll
-							for (int d = 0; d < D; ++d) S.mu[s][d] = munew[d];
-#pragma unroll
-							for (int q = 0; q < TRI; ++q) S.T[s][q] = a.prior.CT2[q] * inv;
-							S.c2[s] = c2new;
-						}
-					S.kocc++;
-					S.st_births++;
-					redo_next = true;
-					if (fsub + 1 > S.nlev) { S.nlev = fsub + 1; level_opened = fsub + 1 > NL; }
-				}
-			}
-			{
-				const int nsub = new_slot >> 5;
-				const bool is_nlane = lane == (new_slot & 31);
-#pragma unroll
-				for (int s = 0; s < SPL; ++s)
-					if (is_nlane && nsub == s) S.n[s] += 1.0f;
-			}
-			S.st_moved++;
+		if (b == 0u) { // an auxiliary draw won (or nothing had weight at all): a cluster is born
+			ret = j | NPB_STEP_BIRTH;
+			return false;
 		}
-		if (lane == j) t.znew = new_slot;
+		int code = myslot[NL - 1];
+#pragma unroll
+		for (int s = NL - 2; s >= 0; --s)
+			if (key[s] == kmax) code = myslot[s];
+		const int new_slot = __shfl_sync(0xffffffffu, code, __ffs(b) - 1);
+		S.cand_tile += (unsigned)(S.kocc + M);
+		if (new_slot != zo) {
+			// retract + assign (membertrix.cpp:175-233, 147-164); an emptied cluster disappears (Q6)
+			bool dead = false;
+#pragma unroll
+			for (int s = 0; s < NL; ++s) {
+				if (zo == myslot[s]) {
+					S.n[s] -= 1.0f;
+					dead = S.n[s] <= 0.0f;
+				}
+				if (new_slot == myslot[s]) S.n[s] += 1.0f;
+			}
+			if (__any_sync(0xffffffffu, dead)) { S.kocc--; S.cand_tile--; }
+			S.st_moved++;
+			if (lane == j) t.znew = new_slot;
+		}
 		++j;
-		if (level_opened) return j;
-		if (redo_next) stage_a<D, SPL, M, NC, NL>(S, t, lane, j & 31, cur);
-		else cur = nxt;
+		return j < cnt;
+	};
+	for (;;) {
+		if (!step(bufA, bufB)) break;
+		if (!step(bufB, bufA)) break;
 	}
-	return j;
+	return ret;
 }
 
-template <int D, int SPL, int M, int NC, int NL>
+template <int D, int SPL, int M, int NG, int NL>
 struct Dispatch {
-	static __device__ __forceinline__ int run(SweepState<D, SPL, M> &S, TileRegs<D, M, NC> &t, const SweepArgs &a, int lane, int j, int cnt) {
-		if (S.nlev <= NL) return run_steps<D, SPL, M, NC, NL>(S, t, a, lane, j, cnt);
-		return Dispatch<D, SPL, M, NC, (NL < SPL ? NL + 1 : SPL)>::run(S, t, a, lane, j, cnt);
+	static __device__ __forceinline__ int run(SweepState<D, SPL, M> &S, TileRegs<D, M, NG> &t, int lane, int j, int cnt) {
+		if (S.nlev <= NL) return run_steps<D, SPL, M, NG, NL>(S, t, lane, j, cnt);
+		return Dispatch<D, SPL, M, NG, (NL < SPL ? NL + 1 : SPL)>::run(S, t, lane, j, cnt);
 	}
 };
-template <int D, int SPL, int M, int NC>
-struct Dispatch<D, SPL, M, NC, SPL> {
-	static __device__ __forceinline__ int run(SweepState<D, SPL, M> &S, TileRegs<D, M, NC> &t, const SweepArgs &a, int lane, int j, int cnt) {
-		return run_steps<D, SPL, M, NC, SPL>(S, t, a, lane, j, cnt);
+template <int D, int SPL, int M, int NG>
+struct Dispatch<D, SPL, M, NG, SPL> {
+	static __device__ __forceinline__ int run(SweepState<D, SPL, M> &S, TileRegs<D, M, NG> &t, int lane, int j, int cnt) {
+		return run_steps<D, SPL, M, NG, SPL>(S, t, lane, j, cnt);
 	}
 };
+
+// Finishes step j of the tile, which an auxiliary draw won (np_neal_algorithm8.cpp:136-145): retract the item, give
+// the lowest free slot theta' of the winning draw, assign.  Generic over the levels (rare path, kept out of the
+// NL-specialised loops).
+template <int D, int SPL, int M, int NG>
+__device__ __forceinline__ void finish_birth(SweepState<D, SPL, M> &S, TileRegs<D, M, NG> &t, const SweepArgs &a, int lane, int j) {
+	constexpr int TRI = npb_tri(D);
+	const int zo_aux = __shfl_sync(0xffffffffu, t.zold_aux, j);
+	const int zo = zo_aux & 0xffff;
+	const int aux_pick = (zo_aux >> 16) & 0xff;
+	S.cand_tile += (unsigned)(S.kocc + M);
+	bool dead = false;
+#pragma unroll
+	for (int s = 0; s < SPL; ++s)
+		if (zo == s * 32 + lane) {
+			S.n[s] -= 1.0f;
+			dead = S.n[s] <= 0.0f;
+		}
+	const bool died = __any_sync(0xffffffffu, dead);
+	if (died) { S.kocc--; S.cand_tile--; }
+	int fsub = -1, fl = 0;
+#pragma unroll
+	for (int s = 0; s < SPL; ++s) {
+		const unsigned fb = __ballot_sync(0xffffffffu, S.n[s] <= 0.0f);
+		if (fsub < 0 && fb) { fsub = s; fl = __ffs(fb) - 1; }
+	}
+	int new_slot;
+	if (fsub < 0) {
+		// no room: flag the chain and put the item back where it was
+		S.overflow = 1;
+		new_slot = zo;
+		if (died) S.kocc++;
+	} else {
+		new_slot = fsub * 32 + fl;
+		// the lane that owns this step holds the auxiliary draws: re-derive theta' of the winner
+		float avp = 1.0f, gz[D];
+#pragma unroll
+		for (int m = 0; m < M; ++m)
+			if (m == aux_pick) {
+				avp = t.av[m];
+#pragma unroll
+				for (int d = 0; d < D; ++d) gz[d] = t.g[m * (D + 1) + 1 + d];
+			}
+		avp = __shfl_sync(0xffffffffu, avp, j);
+		float munew[D];
+#pragma unroll
+		for (int d = 0; d < D; ++d) munew[d] = a.prior.mu0[d];
+		const float sc = avp * a.prior.inv_sqrt_kappa;
+#pragma unroll
+		for (int c = 0; c < D; ++c) {
+			const float gc = __shfl_sync(0xffffffffu, gz[c], j) * sc;
+#pragma unroll
+			for (int r = 0; r <= c; ++r) munew[r] = fmaf(a.prior.S[npb_tri_off(D, r, c)], gc, munew[r]);
+		}
+		const float inv = 1.0f / avp;
+		const float c2new = a.prior.c0_2 - (float)D * log2f(avp);
+#pragma unroll
+		for (int s = 0; s < SPL; ++s)
+			if (s == fsub && lane == fl) {
+#pragma unroll
+				for (int d = 0; d < D; ++d) S.mu[s][d] = munew[d];
+#pragma unroll
+				for (int q = 0; q < TRI; ++q) S.T[s][q] = a.prior.CT2[q] * inv;
+				S.c2[s] = c2new;
+			}
+		S.kocc++;
+		S.st_births++;
+		if (fsub + 1 > S.nlev) S.nlev = fsub + 1;
+	}
+#pragma unroll
+	for (int s = 0; s < SPL; ++s)
+		if (new_slot == s * 32 + lane) S.n[s] += 1.0f;
+	S.st_moved++;
+	if (lane == j) t.znew = new_slot;
+}
 
 template <int D, int SPL, int M>
 __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const SweepArgs a) {
 	constexpr int TRI = npb_tri(D), PS = npb_ps(D);
 	constexpr int NPAIR = (M * (D + 1) + 1) / 2;  // Box-Muller pairs for the M (D+1) normals of a step
-	constexpr int NN = 2 * NPAIR + M;             // + M words for the auxiliaries' race noise
-	constexpr int NC = (NN + 3) / 4;              // Philox calls per step in the tile prologue
+	constexpr int NC = (2 * NPAIR + M + 3) / 4;   // Philox calls per step: the normals + M words of race noise
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int chain = blockIdx.x * NPB_SWEEP_WARPS + warp;
 	if (chain >= a.C) return;
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 			for (int d = 0; d < D; ++d) S.mu[s][d] = th[(size_t)slot * PS + d];
 #pragma unroll
 			for (int q = 0; q < TRI; ++q) S.T[s][q] = th[(size_t)slot * PS + D + q];
-			S.c2[s] = (S.n[s] > 0.0f) ? th[(size_t)slot * PS + D + TRI] : -INFINITY;
+			S.c2[s] = th[(size_t)slot * PS + D + TRI];
 		}
 	}
 	S.kocc = 0;
@@ -327,11 +324,7 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 	S.cand_tile = 0u;
 	S.st_cand = S.st_moved = S.st_births = 0ull;
 #pragma unroll
-	for (int s = 0; s < SPL; ++s) {
-		const unsigned b = __ballot_sync(0xffffffffu, S.n[s] > 0.0f);
-		S.kocc += __popc(b);
-		if (b) S.nlev = s + 1;
-	}
+	for (int s = 0; s < SPL; ++s) S.kocc += __popc(__ballot_sync(0xffffffffu, S.n[s] > 0.0f));
 
 	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 	const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
@@ -339,7 +332,7 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
 		const uint32_t sweep = a.sweep0 + (uint32_t)sw;
-		const ScanOrder so = npb_scan_order(a.seed, sweep, (uint32_t)N);
+		const int32_t *order = a.scan_order + (size_t)sw * N;
 		// levels only grow inside a sweep; shrink them here when the top ones have emptied
 		{
 			int nl = 1;
@@ -350,10 +343,10 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 		}
 		for (int s0 = 0; s0 < N; s0 += 32) {
 			// ---------------- tile prologue: lane j owns step s0 + j ----------------
-			TileRegs<D, M, NC> t;
+			TileRegs<D, M, 2 * NPAIR> t;
 			const int sj = s0 + lane;
 			const bool valid = sj < N;
-			const uint32_t item = valid ? npb_scan_item(so, (uint32_t)sj) : 0u;
+			const int item = valid ? order[sj] : 0;
 			const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
 			t.znew = zold;
 			float xw[D];
@@ -365,8 +358,7 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 			uint32_t rw[NC * 4];
 #pragma unroll
 			for (int c = 0; c < NC; ++c) ph((uint32_t)sj, (uint32_t)c, sweep, NPB_RNG_AUX, rw + 4 * c);
-			// words 0 .. 2*ceil(M(D+1)/2)-1 make the normals (Box-Muller pairs), the last M words the race noise
-			static_assert(2 * NPAIR + M <= NC * 4, "not enough Philox words per step");
+			// words 0 .. 2 NPAIR - 1 make the normals (Box-Muller pairs), the next M words the auxiliaries' race noise
 #pragma unroll
 			for (int p = 0; p < NPAIR; ++p) npb_normal2(rw[2 * p], rw[2 * p + 1], t.g[2 * p], t.g[2 * p + 1]);
 			t.auxkey = -INFINITY;
@@ -392,10 +384,17 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 
 			// ---------------- the steps of the tile ----------------
 			int j = 0;
-			while (j < cnt) j = Dispatch<D, SPL, M, NC, 1>::run(S, t, a, lane, j, cnt);
+			while (j < cnt) {
+				const int r = Dispatch<D, SPL, M, 2 * NPAIR, 1>::run(S, t, lane, j, cnt);
+				j = r & 0xff;
+				if (r & NPB_STEP_BIRTH) {
+					finish_birth<D, SPL, M, 2 * NPAIR>(S, t, a, lane, j);
+					++j;
+				}
+			}
 
 			// ---------------- tile epilogue ----------------
-			if (valid) a.z[(size_t)item * C + chain] = (npb_z_t)t.znew;
+			if (valid && t.znew != zold) a.z[(size_t)item * C + chain] = (npb_z_t)t.znew;
 			S.st_cand += S.cand_tile;
 			S.cand_tile = 0u;
 		}
@@ -427,7 +426,6 @@ __global__ void __launch_bounds__(NPB_SWEEP_WARPS * 32) k_alg8_sweep_reg(const S
 		}
 	}
 }
-
 
 template <int D, int SPL>
 npb_status npb_launch_alg8_reg(npb_chains *ch, const SweepArgs &a) {

@@ -325,6 +325,7 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->kocc) cudaFree(ch->kocc);
 	if (ch->overflow) cudaFree(ch->overflow);
 	if (ch->h_z) cudaFreeHost(ch->h_z);
+	if (ch->scan_order) cudaFree(ch->scan_order);
 	delete ch;
 	return NPB_OK;
 }

@@ -51,10 +51,13 @@ struct npb_chains {
 	int *kocc = nullptr;        // [C]
 	int *overflow = nullptr;    // [C]
 	npb_z_t *h_z = nullptr;     // pinned staging for npb_chains_sweep_host
+	int32_t *scan_order = nullptr; // [scan_cap, N] item visited at each step of the sweeps of one launch
+	int scan_cap = 0;              // sweeps per launch the buffer holds
 };
 
 struct SweepArgs {
 	const float *X, *Xw;
+	const int32_t *scan_order; // [n_sweeps, N]
 	npb_z_t *z;
 	float *theta;
 	int *counts;
