@@ -103,10 +103,11 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------------------------
 def oracle_chain_worker(args):
     """one independent reference chain on one host core (the reference is single threaded)"""
-    seed, sweeps, faithful = args
+    seed, sweeps, faithful, n_items = args
     from oracle import binding as orc
     from noparama_b200 import synthetic as syn
     X, _ = syn.config(2)
+    X = X[:n_items]
     pr = orc.make_prior(**syn.reference_prior(DIM))
     flags = orc.FAITHFUL if faithful else 0
     r = orc.Run(pr, X, T=sweeps, K0=K0, M_aux=M_AUX, seed_main=1000 + seed, seed_shuffle=2000 + seed, flags=flags)
@@ -115,10 +116,10 @@ def oracle_chain_worker(args):
     return re.tolist(), tot.tolist(), s.candidates / max(1, s.updates), s.mean_K
 
 
-def run_oracle(cores, sweeps, faithful=True):
+def run_oracle(cores, sweeps, faithful=True, n_items=N_ITEMS):
     import multiprocessing as mp
     with mp.get_context("spawn").Pool(cores) as pool:
-        return pool.map(oracle_chain_worker, [(c, sweeps, faithful) for c in range(cores)])
+        return pool.map(oracle_chain_worker, [(c, sweeps, faithful, n_items) for c in range(cores)])
 
 
 def cpu_baseline_sample(cores):
@@ -143,20 +144,24 @@ def reference_arm(args, rank, world):
         return
     cores = os.cpu_count() or 1
     sweeps = args.warmup + args.steps
+    # bounded sample: a faithful sweep of N = 100k costs ~3 s per chain; keep the whole run within a few minutes by
+    # sweeping a prefix of the (shuffled) items when many steps are asked for
+    n_items = N_ITEMS if sweeps <= 40 else max(2000, N_ITEMS * 40 // sweeps)
     t0 = time.time()
-    res = run_oracle(cores, sweeps, True)
+    res = run_oracle(cores, sweeps, True, n_items)
     wall = time.time() - t0
     t = max(sum(r[0][args.warmup:]) for r in res)
     t_full = max(sum(r[1][args.warmup:]) for r in res)
-    n = cores * N_ITEMS * args.steps
+    n = cores * n_items * args.steps
     val = n / t
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "chains": cores, "note": "one reference chain per host core; a step = one "
-                       "sweep of every chain"},
+            "config": {"workload": WORKLOAD, "chains": cores, "items_per_sweep": n_items,
+                       "note": "one reference chain per host core; a step = one sweep of every chain over "
+                               "items_per_sweep items of the config (a prefix when W+K > 40)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d chains x %d sweeps x N=%d, update() loop only" % (cores, args.steps, N_ITEMS),
+                             "sample": "%d chains x %d sweeps x N=%d, update() loop only" % (cores, args.steps, n_items),
                              "full_sweep_value": n / t_full},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
@@ -197,7 +202,7 @@ def main():
     ctx = npb.Context(local_rank)
     ds = npb.Dataset(ctx, X)
     prior = npb.NormalInverseWishart(**syn.reference_prior(DIM))
-    mc = npb.MCMC(ctx, ds, prior, chains=args.chains, Kmax=args.kmax, K0=K0, m_aux=M_AUX, seed=SEED + 7919 * rank)
+    mc = npb.MCMC(ctx, ds, prior, chains=args.chains, Kmax=args.kmax, K0=K0, m_aux=M_AUX, seed=__import__('noparama_b200').diagnostics.rank_seed(SEED, rank))
     chains = mc.chains
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
@@ -241,25 +246,26 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    # ---- diagnostics exchange (outside the timed region): co-clustering counts + metric sums over all ranks ----
+    # ---- diagnostics exchange (outside the timed region): a short traced phase for R-hat, then one all-reduce of
+    # the co-clustering counts, the score sums and the R-hat partials over all ranks (NCCL when world > 1) ----
+    from noparama_b200 import diagnostics as dg
+    k_trace, jll_trace = [], []
+    for _ in range(8):
+        chains.sweep(npb.ALG8, 1, want_stats=False)
+        mm = chains.metrics(None)
+        k_trace.append(mm["K"].astype(np.float64))
+        jll_trace.append(mm["joint_loglik"])
     m = chains.metrics(y)
     anchors = np.arange(0, ds.N, ds.N // 256)[:256]
     S = torch.zeros((len(anchors), len(anchors)), dtype=torch.float32, device="cuda")
     chains.cocluster_into(anchors, S.data_ptr())
-    diag = torch.tensor([m["purity"].sum(), m["rand_index"].sum(), m["adjusted_rand"].sum(), float(m["K"].sum()),
-                         float(args.chains)], dtype=torch.float64, device="cuda")
+    diag = dg.combine(dg.score_partial(m), {"K": dg.rhat_partial(np.stack(k_trace, 1)),
+                                            "joint_loglik": dg.rhat_partial(np.stack(jll_trace, 1))},
+                      cocluster=S, device="cuda")
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(S)
-        dist.all_reduce(diag)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([float(cand), float(moved), float(births)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tot)
-        cand_all, moved_all, births_all = tot.tolist()
-    else:
-        cand_all, moved_all, births_all = float(cand), float(moved), float(births)
     elapsed_ms, e2e_s = t.tolist()
-    diag = diag.tolist()
 
     if rank == 0:
         n_step = args.chains * ds.N  # reassignments per step per GPU
@@ -294,8 +300,9 @@ def main():
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                              "peak_source": hbm_src},
-            "diagnostics": {"mean_purity": diag[0] / diag[4], "mean_rand": diag[1] / diag[4], "mean_ari": diag[2] / diag[4],
-                            "mean_K": diag[3] / diag[4], "cocluster_anchor_diag_mean": float(S.diag().mean().item()),
+            "diagnostics": {"mean_purity": diag["mean_purity"], "mean_rand": diag["mean_rand"], "mean_ari": diag["mean_ari"],
+                            "mean_K": diag["mean_K"], "chains": diag["chains"], "rhat": diag["rhat"],
+                            "cocluster_anchor_diag_mean": float(S.diag().mean().item()),
                             "allreduce": "nccl" if world > 1 else "none (1 rank)"},
         }
         if not args.no_cpu_baseline and world == 1:
