@@ -112,6 +112,10 @@ npb_status npb_chains_destroy(npb_chains *ch);
 npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z, int K, const int32_t *slots,
 		const double *mu, const double *Sigma);
 
+/* re-initialise EVERY chain with the same K given clusters (slots 0..K-1) and a fresh uniform assignment of the items
+ * to them: the InitClusters step (np_init_clusters.cpp:24-41) with caller-supplied instead of prior-drawn parameters */
+npb_status npb_chains_init_from_params(npb_chains *ch, int K, const double *mu /* [K,D] */, const double *Sigma /* [K,D,D] */);
+
 /* n_sweeps sweeps of the chosen sampler over all chains: replaces the doubly nested loop of
  * np_mcmc.cpp:109-163 with NealAlgorithm8::update (np_neal_algorithm8.cpp:49-167),
  * JainNealAlgorithm::update (np_jain_neal_algorithm.cpp:424-502) or TriadicAlgorithm::update

@@ -26,7 +26,7 @@ EXPORTS = [
     "npb_logdensity_batch", "npb_logdensity_sum", "npb_chains_create", "npb_chains_destroy", "npb_chains_set_state",
     "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
-    "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak",
+    "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
 ]
 
 
@@ -75,6 +75,7 @@ def load_library():
     L.npb_chains_create.argtypes = [vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(vp)]
     L.npb_chains_destroy.argtypes = [vp]
     L.npb_chains_set_state.argtypes = [vp, i64, ip, C.c_int, ip, dp, dp]
+    L.npb_chains_init_from_params.argtypes = [vp, C.c_int, dp, dp]
     L.npb_chains_sweep.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SweepStats)]
     L.npb_chains_sweep_host.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(SweepStats)]
     L.npb_chain_update_alg8.argtypes = [vp, i64, i64]
@@ -278,6 +279,11 @@ class Chains:
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         mu, Sigma = _f64(mu), _f64(Sigma)
         self.ctx.check(self.ctx._lib.npb_chains_set_state(self._h, chain, _ip(z), len(slots), _ip(slots), _dp(mu), _dp(Sigma)))
+
+    def init_from_params(self, mu, Sigma):
+        """every chain restarts from the same K clusters (given parameters) and a uniform random assignment"""
+        mu, Sigma = _f64(mu), _f64(Sigma)
+        self.ctx.check(self.ctx._lib.npb_chains_init_from_params(self._h, mu.shape[0], _dp(mu), _dp(Sigma)))
 
     def assignments(self, chain0=0, n=None):
         n = self.C - chain0 if n is None else n

@@ -13,14 +13,14 @@
 // lane j of the warp prefetches item, old assignment and coordinates of step s0+j and draws that step's
 // auxiliary parameters from Philox, so the sequential part of a step is: keys -> warp arg-max -> count update
 // (an exponential race, exact in distribution; see npb_alg8_kernel.cuh).  Weights stay in the log2 domain.
-#include "npb_alg8_kernel.cuh"
+#include "npb_alg8_tile.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // init: np_mcmc.cpp:49-91 -- K0 clusters from the base measure (np_init_clusters.cpp:24-41), every item to a
 // uniformly chosen cluster, clusters that got nothing dropped (cleanup, membertrix.cpp:343-364).
 // One warp per chain.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_chains_init(SweepArgs a, int K0) {
+__global__ void k_chains_init(SweepArgs a, int K0, const float *theta_given /* [K0, PS] or NULL */, uint32_t epoch) {
 	extern __shared__ int sh_counts[]; // [warps][Kmax]
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -33,12 +33,13 @@ __global__ void k_chains_init(SweepArgs a, int K0) {
 	float *th = a.theta + (size_t)chain * a.Kmax * PS;
 	for (int k = lane; k < a.Kmax; k += 32) {
 		float *o = th + (size_t)k * PS;
-		if (k < K0) npb_draw_theta(a.prior, ph, (uint32_t)k, 0u, NPB_RNG_INIT_THETA, 0, o);
+		if (k < K0 && theta_given) for (int t = 0; t < PS; ++t) o[t] = theta_given[(size_t)k * PS + t];
+		else if (k < K0) npb_draw_theta(a.prior, ph, (uint32_t)k, epoch, NPB_RNG_INIT_THETA, 0, o);
 		else for (int t = 0; t < PS; ++t) o[t] = 0.0f;
 	}
 	for (int i = lane; i < a.N; i += 32) {
 		uint32_t w[4];
-		ph((uint32_t)i, 0u, 0u, NPB_RNG_INIT_Z, w);
+		ph((uint32_t)i, 0u, epoch, NPB_RNG_INIT_Z, w);
 		int k = (int)__umulhi(w[0], (uint32_t)K0);
 		a.z[(size_t)i * a.C + chain] = (npb_z_t)k;
 		atomicAdd(&cnt[k], 1);
@@ -125,13 +126,14 @@ npb_status npb_launch_whiten(npb_dataset *ds) {
 	return NPB_OK;
 }
 
-npb_status npb_launch_chains_init(npb_chains *ch) {
+npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given) {
 	npb_ctx *ctx = ch->ctx;
 	SweepArgs a = make_args(ch, 0);
+	static uint32_t epoch = 0; // distinct initial assignments for repeated initialisations of a handle
 	const int warps = 4;
 	int64_t blocks = (ch->C + warps - 1) / warps;
 	size_t shmem = (size_t)warps * ch->Kmax * sizeof(int);
-	k_chains_init<<<(unsigned)blocks, warps * 32, shmem, ctx->stream>>>(a, ch->K0);
+	k_chains_init<<<(unsigned)blocks, warps * 32, shmem, ctx->stream>>>(a, K0, d_theta_given, d_theta_given ? ++epoch : 0u);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
@@ -141,6 +143,9 @@ npb_status npb_launch_chains_init(npb_chains *ch) {
 NPB_DECL(2, 1) NPB_DECL(2, 2) NPB_DECL(2, 4) NPB_DECL(2, 8) NPB_DECL(2, 16)
 NPB_DECL(3, 1) NPB_DECL(3, 2) NPB_DECL(3, 4) NPB_DECL(3, 8)
 #undef NPB_DECL
+#define NPB_TDECL(D, K) extern template npb_status npb_launch_alg8_tile<D, K>(npb_chains *, const SweepArgs &);
+NPB_TDECL(4, 32) NPB_TDECL(4, 64) NPB_TDECL(8, 32) NPB_TDECL(8, 64) NPB_TDECL(16, 32) NPB_TDECL(16, 64)
+#undef NPB_TDECL
 
 // scan order of sweeps sweep0 .. sweep0+n_sweeps-1 into order[n_sweeps][N] (npb_common.cuh: keyed permutation with
 // cycle walking; evaluated once per sweep here instead of per chain inside the sweep kernel)
@@ -170,9 +175,15 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	case 3002: s = npb_launch_alg8_reg<3, 2>(ch, a); break;
 	case 3004: s = npb_launch_alg8_reg<3, 4>(ch, a); break;
 	case 3008: s = npb_launch_alg8_reg<3, 8>(ch, a); break;
+	case 4001: s = npb_launch_alg8_tile<4, 32>(ch, a); break;
+	case 4002: s = npb_launch_alg8_tile<4, 64>(ch, a); break;
+	case 8001: s = npb_launch_alg8_tile<8, 32>(ch, a); break;
+	case 8002: s = npb_launch_alg8_tile<8, 64>(ch, a); break;
+	case 16001: s = npb_launch_alg8_tile<16, 32>(ch, a); break;
+	case 16002: s = npb_launch_alg8_tile<16, 64>(ch, a); break;
 	default:
 		return npb_fail(ctx, NPB_E_UNSUPPORTED,
-				"Alg. 8 sweep kernels cover D = 2 (Kmax 32/64/128/256/512) and D = 3 (Kmax 32/64/128/256)");
+				"Alg. 8 sweep kernels cover D = 2 (Kmax 32..512), D = 3 (Kmax 32..256) and D = 4, 8, 16 (Kmax 32/64)");
 	}
 	if (s == NPB_OK) ch->sweep += (uint32_t)n_sweeps;
 	return s;

@@ -307,7 +307,7 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 		return npb_fail_cuda(ctx, e, "chain state allocation", __FILE__, __LINE__);
 	}
 	npb_status s = ensure_whitened(ds);
-	if (s == NPB_OK) s = npb_launch_chains_init(ch);
+	if (s == NPB_OK) s = npb_launch_chains_init(ch, ch->K0, nullptr);
 	if (s != NPB_OK) { npb_chains_destroy(ch); return s; }
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	*out = ch;
@@ -327,6 +327,31 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->h_z) cudaFreeHost(ch->h_z);
 	if (ch->scan_order) cudaFree(ch->scan_order);
 	delete ch;
+	return NPB_OK;
+}
+
+npb_status npb_chains_init_from_params(npb_chains *ch, int K, const double *mu, const double *Sigma) {
+	if (!ch || !mu || !Sigma || K <= 0 || K > ch->Kmax) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ch->D, TRI = npb_tri(D), PS = npb_ps(D);
+	std::vector<float> th((size_t)K * PS);
+	std::vector<double> T(TRI);
+	for (int k = 0; k < K; ++k) {
+		double logdet;
+		if (!npb_prepare_theta(D, mu + (size_t)k * D, Sigma + (size_t)k * D * D, T.data(), &logdet))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "Sigma is not invertible with a positive definite symmetric precision");
+		float *o = th.data() + (size_t)k * PS;
+		for (int d = 0; d < D; ++d) o[d] = (float)mu[(size_t)k * D + d];
+		for (int t = 0; t < TRI; ++t) o[D + t] = (float)(T[t] * NPB_HALF_LOG2E_SQRT);
+		o[D + TRI] = (float)(-0.5 * (D * std::log2(2.0 * M_PI) + logdet / std::log(2.0)));
+	}
+	DevBuf<float> d_th;
+	NPB_CUDA_OK(d_th.alloc(th.size()));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_th.p, th.data(), sizeof(float) * th.size(), cudaMemcpyHostToDevice, ctx->stream));
+	npb_status s = npb_launch_chains_init(ch, K, d_th.p);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }
 

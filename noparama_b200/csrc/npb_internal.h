@@ -80,6 +80,6 @@ void npb_theta_to_sigma(int D, const double *T_packed_upper, double *Sigma);
 
 // launchers (npb_alg8.cu / npb_density.cu / npb_metrics.cu)
 npb_status npb_launch_whiten(npb_dataset *ds);
-npb_status npb_launch_chains_init(npb_chains *ch);
+npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given);
 npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps);
 PriorDev npb_prior_dev(const npb_ctx *ctx, int m_aux);

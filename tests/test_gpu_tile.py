@@ -1,0 +1,100 @@
+"""GPU (pytest -m gpu): the D = 4, 8, 16 sweep kernel (shared-memory slot table, producer/consumer warps)."""
+import numpy as np
+import pytest
+from scipy import stats as sps
+
+from noparama_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def invariants(chains, z, c, N):
+    slots, counts, mu, Sigma = chains.params(c)
+    assert counts.sum() == N
+    bc = np.bincount(z, minlength=chains.Kmax)
+    assert np.array_equal(np.nonzero(bc)[0], slots) and np.array_equal(bc[slots], counts)
+    assert np.all(np.isfinite(mu)) and np.all(np.isfinite(Sigma))
+    return len(slots)
+
+
+@pytest.mark.parametrize("D,kmax", [(4, 32), (4, 64), (8, 32), (16, 32), (16, 64)])
+def test_tile_kernel_invariants(npb, ctx, oracle, D, kmax):
+    N = (200 if kmax == 32 else 1000) + D  # not a multiple of the 32-step tile; small enough for 32 slots
+    X, y = syn.gmm(N, D, 4, 100 + D)
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=24, Kmax=kmax,
+                  K0=20 if kmax > 32 else 8, seed=D)
+    st = None
+    for _ in range(3):
+        st = mc.chains.sweep(npb.ALG8, 3)
+        assert st.overflow_chains == 0 and st.reassignments == 24 * N * 3
+        assert 4 * st.reassignments <= st.candidates <= (kmax + 3) * st.reassignments
+    z = mc.getMembershipMatrix()
+    m = mc.chains.metrics(y)
+    for c in range(0, 24, 5):
+        k = invariants(mc.chains, z[c], c, N)
+        assert k == m["K"][c]
+        want = oracle.metrics(y, z[c])
+        assert np.allclose([m["purity"][c], m["rand_index"][c], m["adjusted_rand"][c]], want, atol=1e-12)
+    assert abs(st.mean_K - m["K"].mean()) < 1e-9
+    # determinism and launch splitting
+    a = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=kmax, seed=77)
+    b = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=kmax, seed=77)
+    a.run(4)
+    b.run(4, sweeps_per_launch=1)
+    assert np.array_equal(a.getMembershipMatrix(), b.getMembershipMatrix())
+    ds.close()
+
+
+def test_tile_kernel_recovers_given_clusters_16d(npb, ctx):
+    """Config-5 regime: chains start from K_true known clusters (init_from_params) and a random assignment; a few
+    sweeps of Alg. 8 with frozen parameters must put (almost) every item into its own component."""
+    X, y = syn.gmm(4000, 16, 8, 5)
+    means = np.stack([X[y == k].mean(0) for k in range(8)])
+    Sigma = np.tile(np.eye(16), (8, 1, 1))
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(16)), chains=32, Kmax=32, seed=3)
+    mc.chains.init_from_params(means, Sigma)
+    m0 = mc.chains.metrics(y)
+    assert m0["purity"].mean() < 0.3 and np.all(m0["K"] == 8)
+    st = mc.run(3)[0]
+    assert st.overflow_chains == 0
+    m = mc.chains.metrics(y)
+    assert m["purity"].mean() > 0.99 and m["adjusted_rand"].mean() > 0.98
+    assert np.all(m["K"] >= 8)
+    z = mc.getMembershipMatrix(0, 2)
+    for c in range(2):
+        invariants(mc.chains, z[c], c, 4000)
+    ds.close()
+
+
+def test_tile_kernel_distribution_matches_log_domain_oracle_4d(npb, ctx, oracle):
+    """D = 4: 96 device chains against 96 oracle seeds (oracle in its log-domain mode: the same categorical without the
+    reference's double underflow), same prior, T = 150 sweeps: K, purity and adjusted Rand must agree in distribution."""
+    from multiprocessing import Pool
+    X, y = syn.gmm(240, 4, 3, 42, min_dist=5.0)
+    pr = syn.reference_prior(4)
+    T = 150
+    with Pool(8) as pool:
+        res = np.array(pool.map(_oracle_seed, [(s, T) for s in range(96)]))
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**pr), chains=96, Kmax=64, seed=11)
+    stats = mc.run(T, sweeps_per_launch=50)
+    assert all(s.overflow_chains == 0 for s in stats)
+    m = mc.chains.metrics(y)
+    for name, got, want in (("K", m["K"].astype(float), res[:, 0]), ("purity", m["purity"], res[:, 1]),
+                            ("ari", m["adjusted_rand"], res[:, 2])):
+        p = sps.ks_2samp(got, want).pvalue
+        assert p > 0.01, "%s: KS p=%.2e (gpu %.4f vs oracle %.4f)" % (name, p, got.mean(), want.mean())
+    ds.close()
+
+
+def _oracle_seed(args):
+    seed, T = args
+    from oracle import binding as orc
+    X, y = syn.gmm(240, 4, 3, 42, min_dist=5.0)
+    p = orc.make_prior(**syn.reference_prior(4))
+    r = orc.Run(p, X, T=T, seed_main=500 + seed, seed_shuffle=900 + seed, flags=orc.LOG_DOMAIN)
+    s = r.stats()
+    pur, ri, ari = orc.metrics(y, r.assignments(0))
+    return s.K_final, pur, ari
