@@ -1,0 +1,136 @@
+// npb_host.cpp -- see npb_host.h.  Everything here is plumbing above the C ABI; no arithmetic of the path lives on the host.
+#include "npb_host.h"
+
+#include <algorithm>
+#include <cassert>
+#include <iostream>
+
+namespace npb {
+
+device::device(int index) {
+	npb_status s = npb_ctx_create(index, &ctx_);
+	if (s != NPB_OK) throw npb_error(s, std::string("npb200: no usable CUDA device (") + npb_status_str(s) + "); there is no CPU path");
+}
+device::~device() { npb_ctx_destroy(ctx_); }
+void device::check(npb_status s) const {
+	if (s == NPB_OK) return;
+	std::string msg = npb_status_str(s);
+	const char *detail = npb_ctx_last_error(ctx_);
+	if (detail && *detail) msg += std::string(": ") + detail;
+	throw npb_error(s, msg);
+}
+
+membertrix::membertrix(device &dev, dataset_t &dataset, int D) : dev_(dev), dataset_(&dataset), N_((int)dataset.size()), D_(D) {
+	// addData for every item (membertrix.cpp:124-138): the rows go to the device once
+	std::vector<double> X((size_t)N_ * D_);
+	for (int i = 0; i < N_; ++i) {
+		assert((int)dataset[i]->size() >= D_);
+		std::copy(dataset[i]->begin(), dataset[i]->begin() + D_, X.begin() + (size_t)i * D_);
+	}
+	dev_.check(npb_dataset_upload(dev_.ctx(), X.data(), N_, D_, &ds_));
+}
+membertrix::~membertrix() { npb_dataset_destroy(ds_); }
+
+void membertrix::refresh() {
+	if (!dirty_ || !chains) return;
+	const int cap = npb_chains_kmax(chains);
+	z_.resize(N_);
+	slots_.resize(cap);
+	counts_.resize(cap);
+	mu_.resize((size_t)cap * D_);
+	sigma_.resize((size_t)cap * D_ * D_);
+	dev_.check(npb_chains_get_assignments(chains, chain_, 1, z_.data()));
+	int K = 0;
+	dev_.check(npb_chains_get_params(chains, chain_, cap, &K, slots_.data(), counts_.data(), mu_.data(), sigma_.data()));
+	slots_.resize(K);
+	counts_.resize(K);
+	dirty_ = false;
+}
+cluster_id_t membertrix::getClusterId(data_id_t i) {
+	refresh();
+	return (i >= 0 && i < N_) ? z_[i] : -1;
+}
+size_t membertrix::getClusterCount() {
+	refresh();
+	return slots_.size();
+}
+std::map<cluster_id_t, Suffies_MultivariateNormal> membertrix::getClusters() {
+	refresh();
+	std::map<cluster_id_t, Suffies_MultivariateNormal> out;
+	for (size_t k = 0; k < slots_.size(); ++k) {
+		Suffies_MultivariateNormal s(D_);
+		std::copy(mu_.begin() + k * D_, mu_.begin() + (k + 1) * D_, s.mu.begin());
+		std::copy(sigma_.begin() + k * D_ * D_, sigma_.begin() + (k + 1) * D_ * D_, s.sigma.begin());
+		out[slots_[k]] = s;
+	}
+	return out;
+}
+size_t membertrix::count(cluster_id_t k) {
+	refresh();
+	for (size_t j = 0; j < slots_.size(); ++j)
+		if (slots_[j] == k) return (size_t)counts_[j];
+	return 0;
+}
+void membertrix::getAssignments(cluster_id_t k, data_ids_t &ids) {
+	refresh();
+	for (int i = 0; i < N_; ++i)
+		if (z_[i] == k) ids.push_back(i);
+}
+
+void NealAlgorithm8::sweep(membertrix &cluster_matrix, int n_sweeps) {
+	dev_.check(npb_chains_sweep(cluster_matrix.chains, NPB_ALG8, n_sweeps, &last_));
+	accepted_ += last_.new_clusters;
+	rejected_ += last_.reassignments - last_.new_clusters;
+	cluster_matrix.invalidate();
+}
+void NealAlgorithm8::update(membertrix &cluster_matrix, const data_ids_t &data_ids) {
+	assert(data_ids.size() == 1); // np_neal_algorithm8.cpp:54
+	if (calls_++ % cluster_matrix.size() == 0) sweep(cluster_matrix, 1);
+}
+void NealAlgorithm8::printStatistics() { // np_neal_algorithm8.cpp:169-176
+	std::cout << "Statistics:" << std::endl;
+	std::cout << " # of new cluster events accepted: " << accepted_ << std::endl;
+	std::cout << " # of new cluster events rejected: " << rejected_ << std::endl;
+}
+
+MCMC::MCMC(device &dev, dirichlet_process &hyper, UpdateClusterPopulation &ucp, int64_t chains, int Kmax, int K0, int m_aux, uint64_t seed)
+	: dev_(dev), hyper_(hyper), ucp_(ucp), chains_(chains), Kmax_(Kmax), K0_(K0), m_aux_(m_aux), seed_(seed) {}
+MCMC::~MCMC() {
+	if (trix_) {
+		npb_chains_destroy(trix_->chains);
+		delete trix_;
+	}
+}
+
+void MCMC::run(dataset_t &dataset, int T, bool per_item_seam) {
+	const Suffies_NormalInvWishart &niw = hyper_.getSuffies();
+	if (!trix_) {
+		trix_ = new membertrix(dev_, dataset, niw.D);
+		dev_.check(npb_prior_set_niw(dev_.ctx(), niw.D, niw.mu.data(), niw.kappa, niw.nu, niw.Lambda.data(), hyper_.alpha(), NPB_BUGCOMPAT_DEFAULT));
+		// np_mcmc.cpp:49-91: K0 prior clusters, uniform assignment, empty clusters dropped
+		dev_.check(npb_chains_create(dev_.ctx(), trix_->dataset_handle(), chains_, Kmax_, m_aux_, K0_, seed_, &trix_->chains));
+	}
+	const int N = trix_->size();
+	if (per_item_seam) {
+		// the reference's own loop shape (np_mcmc.cpp:109-163): one update() per item
+		for (int t = 0; t < T; ++t)
+			for (int i = 0; i < N; ++i) {
+				data_ids_t subset(1, i);
+				ucp_.update(*trix_, subset);
+			}
+	} else {
+		ucp_.sweep(*trix_, T);
+	}
+}
+
+clustering_scores MCMC::scores(const std::vector<int> &ground_truth) {
+	clustering_scores s;
+	const size_t C = (size_t)chains_;
+	s.purity.resize(C); s.rand_index.resize(C); s.adjusted_rand.resize(C); s.joint_loglik.resize(C); s.K.resize(C);
+	std::vector<int32_t> gt(ground_truth.begin(), ground_truth.end());
+	dev_.check(npb_chains_metrics(trix_->chains, gt.empty() ? nullptr : gt.data(), s.purity.data(), s.rand_index.data(),
+			s.adjusted_rand.data(), s.joint_loglik.data(), s.K.data()));
+	return s;
+}
+
+} // namespace npb

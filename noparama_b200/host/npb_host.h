@@ -1,0 +1,166 @@
+// npb_host.h -- C++ host side above the C ABI (include/npb200.h): the reference's sampler seam, kept by name.
+//
+// The reference wires  MCMC(generator, InitClusters, UpdateClusters, UpdateClusterPopulation, subset_count, likelihood)
+// by hand in main (src/np_main.cpp:391-468) and drives  UpdateClusterPopulation::update(membertrix&, data_ids)  once
+// per item per sweep (src/np_mcmc.cpp:146-163).  These classes keep those names, argument meanings and error behaviour
+// (np_error_t), without Eigen, and delegate every computation to libnpb200.so.  One object graph drives `chains`
+// lockstep chains; chain 0 is what the single-chain accessors of the reference interface see.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/npb200.h"
+
+namespace npb {
+
+// ---- include/np_data.h:9-25, include/np_cluster.h:12-18 ----
+typedef std::vector<double> data_t;
+typedef std::vector<data_t *> dataset_t;
+typedef int data_id_t;
+typedef std::vector<data_id_t> data_ids_t;
+typedef int cluster_id_t;
+typedef std::vector<cluster_id_t> cluster_ids_t;
+
+// ---- include/membertrix.h:16-23 ----
+enum np_error_t { error_none, error_already_assigned, error_assignment_remaining, error_assignment_absent };
+
+// ---- include/np_suffies.h:80-95,187-200 and Suffies_Dirichlet ----
+struct Suffies_NormalInvWishart {
+	int D;
+	std::vector<double> mu;     // [D]
+	double kappa, nu;
+	std::vector<double> Lambda; // [D,D] row-major
+	explicit Suffies_NormalInvWishart(int d) : D(d), mu(d, 0.0), kappa(1.0), nu(d + 2.0), Lambda((size_t)d * d, 0.0) {}
+};
+struct Suffies_MultivariateNormal {
+	int D;
+	std::vector<double> mu, sigma;
+	explicit Suffies_MultivariateNormal(int d = 0) : D(d), mu(d, 0.0), sigma((size_t)d * d, 0.0) {}
+};
+struct Suffies_Dirichlet {
+	double alpha = 1.0;
+};
+
+struct npb_error : std::runtime_error {
+	npb_status status;
+	npb_error(npb_status s, const std::string &what) : std::runtime_error(what), status(s) {}
+};
+
+// One CUDA device + stream.  There is no CPU path: construction throws without a GPU.
+class device {
+public:
+	explicit device(int index = 0);
+	~device();
+	npb_ctx *ctx() const { return ctx_; }
+	void check(npb_status s) const;
+private:
+	npb_ctx *ctx_ = nullptr;
+	device(const device &) = delete;
+};
+
+// dirichlet_process(alpha, normal_inverse_wishart_distribution)  (include/statistics/dirichlet.h:20-93)
+class dirichlet_process {
+public:
+	dirichlet_process(const Suffies_Dirichlet &d, const Suffies_NormalInvWishart &niw) : alpha_(d.alpha), niw_(niw) {}
+	const Suffies_NormalInvWishart &getSuffies() const { return niw_; }
+	double alpha() const { return alpha_; }
+private:
+	double alpha_;
+	Suffies_NormalInvWishart niw_;
+};
+
+// The membership state (include/membertrix.h:52-314) of the device chains.  Cluster ids are device slot ids: stable,
+// so relabel() has nothing to do.  Reads refresh a host copy of one chain on demand.
+class membertrix {
+public:
+	membertrix(device &dev, dataset_t &dataset, int D);
+	~membertrix();
+	int size() const { return N_; }
+	int dim() const { return D_; }
+	data_t *getDatum(data_id_t i) { return (*dataset_)[i]; }                            // membertrix.cpp:140-144
+	cluster_id_t getClusterId(data_id_t i);                                              // :235-244
+	size_t getClusterCount();                                                            // :246-248
+	std::map<cluster_id_t, Suffies_MultivariateNormal> getClusters();                    // :250-257 (parameters by value)
+	size_t count(cluster_id_t k);                                                        // :328-330
+	void getAssignments(cluster_id_t k, data_ids_t &ids);                                // :315-322
+	bool assigned(data_id_t i) { return getClusterId(i) >= 0; }                          // :166-168
+	void relabel() {}                                                                    // :259-262
+	void select_chain(int64_t chain) { chain_ = chain; dirty_ = true; }
+	// device side
+	npb_dataset *dataset_handle() const { return ds_; }
+	npb_chains *chains = nullptr; // owned by MCMC
+	void invalidate() { dirty_ = true; }
+private:
+	void refresh();
+	device &dev_;
+	dataset_t *dataset_;
+	npb_dataset *ds_ = nullptr;
+	int N_, D_;
+	int64_t chain_ = 0;
+	bool dirty_ = true;
+	std::vector<int32_t> z_;
+	std::vector<int32_t> slots_;
+	std::vector<int64_t> counts_;
+	std::vector<double> mu_, sigma_;
+};
+
+// include/np_update_cluster_population.h:13-44
+class UpdateClusterPopulation {
+public:
+	virtual ~UpdateClusterPopulation() {}
+	virtual void update(membertrix &cluster_matrix, const data_ids_t &data_ids) = 0;
+	virtual void printStatistics() = 0;
+	virtual void sweep(membertrix &cluster_matrix, int n_sweeps) = 0; // batched form: n_sweeps sweeps of every chain
+	virtual int sampler() const = 0;
+	virtual int subset_count() const = 0;
+};
+
+// NealAlgorithm8 (include/np_neal_algorithm8.h:52-56, src/np_neal_algorithm8.cpp:49-176).  update() keeps the
+// per-item calling convention of MCMC::run: the first call of a sweep performs the whole sweep of every chain on the
+// device, the remaining N-1 calls of that sweep are absorbed.
+class NealAlgorithm8 : public UpdateClusterPopulation {
+public:
+	NealAlgorithm8(device &dev, dirichlet_process &nonparametrics) : dev_(dev), hyper_(nonparametrics) {}
+	void update(membertrix &cluster_matrix, const data_ids_t &data_ids) override;
+	void sweep(membertrix &cluster_matrix, int n_sweeps) override;
+	void printStatistics() override;
+	int sampler() const override { return NPB_ALG8; }
+	int subset_count() const override { return 1; }
+	const npb_sweep_stats &last() const { return last_; }
+private:
+	device &dev_;
+	dirichlet_process &hyper_;
+	int64_t calls_ = 0;
+	int64_t accepted_ = 0, rejected_ = 0;
+	npb_sweep_stats last_{};
+};
+
+struct clustering_scores { // src/clustering_performance.cpp:38-82
+	std::vector<double> purity, rand_index, adjusted_rand, joint_loglik;
+	std::vector<int32_t> K;
+};
+
+// MCMC (include/np_mcmc.h:71-95, src/np_mcmc.cpp:48-175) over `chains` lockstep chains.
+class MCMC {
+public:
+	MCMC(device &dev, dirichlet_process &hyper, UpdateClusterPopulation &update_cluster_population, int64_t chains = 1,
+			int Kmax = 256, int K0 = 20, int m_aux = 3, uint64_t seed = 20261018);
+	~MCMC();
+	void run(dataset_t &dataset, int T, bool per_item_seam = false);
+	membertrix &getMembershipMatrix() { return *trix_; }                  // np_mcmc.h:88
+	clustering_scores scores(const std::vector<int> &ground_truth);        // np_results.cpp:17-37 + clustering_performance
+	int64_t chains() const { return chains_; }
+private:
+	device &dev_;
+	dirichlet_process &hyper_;
+	UpdateClusterPopulation &ucp_;
+	int64_t chains_;
+	int Kmax_, K0_, m_aux_;
+	uint64_t seed_;
+	membertrix *trix_ = nullptr;
+};
+
+} // namespace npb

@@ -1,0 +1,107 @@
+// npb_main.cpp -- the reference's command line (src/np_main.cpp:187-267) on top of the device path:
+//   noparama_b200 -d <datafile> -a algorithm8 -T <sweeps> -c clustering [--chains C] [--seed S] [--kmax K] [--seam]
+// -d  text file, one item per line: D coordinates then the ground-truth label (the reference reads exactly 2 + 1
+//     columns, np_main.cpp:93-101; here D = columns - 1 <= 3 for the register kernel, 4/8/16 for the tile kernel)
+// -a  algorithm8 (jain_neal_split / triadic are not on the device yet and are refused, exit 107 like np_main.cpp:385)
+// -T  sweeps (default 2000, np_main.cpp:242)    -c  clustering only (regression/angular/points3d are out of scope)
+// Prior and constants as hard-wired in the reference: alpha = 1, NIW{mu = 6, kappa = 1/500, nu = D + 2, Lambda = 0.01 I}
+// (np_main.cpp:164,367-371), K0 = 20, M = 3.  No 200-row subsampling (np_main.cpp:166-167): every row is used.
+#include "npb_host.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <numeric>
+#include <sstream>
+
+using namespace npb;
+
+static void usage() {
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8 -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam]\n";
+}
+
+int main(int argc, char **argv) {
+	std::string datafile, algorithm = "algorithm8", config = "clustering";
+	int T = 2000, kmax = 256;
+	long long chains = 1;
+	unsigned long long seed = 20261018ull;
+	bool seam = false;
+	for (int i = 1; i < argc; ++i) {
+		std::string a = argv[i];
+		auto next = [&](const char *what) -> const char * {
+			if (i + 1 >= argc) { std::cerr << "missing value for " << what << std::endl; exit(1); }
+			return argv[++i];
+		};
+		if (a == "-d") datafile = next("-d");
+		else if (a == "-a") algorithm = next("-a");
+		else if (a == "-T") T = atoi(next("-T"));
+		else if (a == "-c") config = next("-c");
+		else if (a == "--chains") chains = atoll(next("--chains"));
+		else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
+		else if (a == "--kmax") kmax = atoi(next("--kmax"));
+		else if (a == "--seam") seam = true;
+		else if (a == "-h" || a == "-?") { usage(); return 0; }
+		else { std::cerr << "unknown option " << a << std::endl; usage(); return 1; }
+	}
+	if (datafile.empty()) { usage(); return 1; }
+	if (config != "clustering") { std::cerr << "Unknown likelihood (only -c clustering is on the device path)" << std::endl; return 107; }
+	if (algorithm != "algorithm8") { std::cerr << "Algorithm " << algorithm << " is not on the device path yet" << std::endl; return 107; }
+
+	// read_data (np_main.cpp:57-148), generalised to D columns + label
+	std::ifstream in(datafile);
+	if (!in) { std::cerr << "cannot open " << datafile << std::endl; return 7; }
+	dataset_t dataset;
+	std::vector<int> ground_truth;
+	std::string line;
+	int D = -1;
+	while (std::getline(in, line)) {
+		std::istringstream ss(line);
+		std::vector<double> row;
+		double v;
+		while (ss >> v) row.push_back(v);
+		if (row.empty()) continue;
+		if (D < 0) D = (int)row.size() - 1;
+		if ((int)row.size() != D + 1 || D < 1) { std::cerr << "ragged line in " << datafile << std::endl; return 7; }
+		ground_truth.push_back((int)row.back());
+		row.pop_back();
+		dataset.push_back(new data_t(row));
+	}
+	std::cout << "Read " << dataset.size() << " items of dimension " << D << std::endl;
+
+	try {
+		device dev(0);
+		Suffies_Dirichlet sd;
+		sd.alpha = 1.0; // np_main.cpp:164
+		Suffies_NormalInvWishart niw(D);
+		for (int d = 0; d < D; ++d) { niw.mu[d] = 6.0; niw.Lambda[(size_t)d * D + d] = 0.01; }
+		niw.kappa = 1.0 / 500;
+		niw.nu = D + 2.0;
+		dirichlet_process hyper(sd, niw);
+		NealAlgorithm8 alg8(dev, hyper);
+		MCMC mcmc(dev, hyper, alg8, chains, kmax, 20, 3, seed);
+		std::cout << "Run MCMC for " << T << " steps, " << chains << " chain(s)" << std::endl;
+		mcmc.run(dataset, T, seam);
+		alg8.printStatistics();
+		clustering_scores sc = mcmc.scores(ground_truth);
+		auto mean = [](const std::vector<double> &v) { return std::accumulate(v.begin(), v.end(), 0.0) / v.size(); };
+		// clustering_performance.cpp:77-79 prints the three scores; chain 0 first, then the mean over chains
+		std::cout << "Purity: " << sc.purity[0] << std::endl;
+		std::cout << "Rand Index: " << sc.rand_index[0] << std::endl;
+		std::cout << "Adjusted Rand Index: " << sc.adjusted_rand[0] << std::endl;
+		std::cout << "Clusters: " << sc.K[0] << "  Loglikelihood now: " << sc.joint_loglik[0] << std::endl;
+		if (chains > 1)
+			std::cout << "Mean over " << chains << " chains: purity " << mean(sc.purity) << " rand " << mean(sc.rand_index)
+				  << " adjusted rand " << mean(sc.adjusted_rand) << std::endl;
+		membertrix &trix = mcmc.getMembershipMatrix();
+		for (auto &kv : trix.getClusters())
+			std::cout << " cluster " << kv.first << " [#" << trix.count(kv.first) << "] mu " << kv.second.mu[0] << (D > 1 ? " " : "")
+				  << (D > 1 ? std::to_string(kv.second.mu[1]) : "") << std::endl;
+	} catch (const npb_error &e) {
+		std::cerr << "npb200: " << e.what() << std::endl;
+		return e.status == NPB_E_CUDA ? 2 : 1;
+	}
+	for (auto p : dataset) delete p;
+	return 0;
+}
