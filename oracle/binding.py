@@ -36,7 +36,7 @@ class Stats(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libnp_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("np_oracle.cpp", "np_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("np_oracle.cpp", "np_oracle.h", "np_oracle_sm.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "libnp_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -81,6 +81,9 @@ def lib():
         L.npo_run_init_K.argtypes = [C.c_void_p]
         L.npo_run_init_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
+        L.npo_run_K_after_len.restype = C.c_int64
+        L.npo_run_K_after_len.argtypes = [C.c_void_p]
+        L.npo_run_K_after.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.npo_trace_steps.restype = C.c_int64
         L.npo_trace_steps.argtypes = [C.c_void_p]
         L.npo_trace_order_len.restype = C.c_int64
@@ -201,6 +204,12 @@ class Run:
         a, b = np.empty(self.T), np.empty(self.T)
         lib().npo_run_sweep_seconds(self._h, _dp(a), _dp(b))
         return a, b
+
+    def K_after(self):
+        """cluster count after every sampler.update() call (RECORD_TRACE runs)"""
+        k = np.empty(lib().npo_run_K_after_len(self._h), dtype=np.int32)
+        lib().npo_run_K_after(self._h, _ip(k))
+        return k
 
     def assignments(self, which=0):
         z = np.empty(self.N, dtype=np.int32)

@@ -395,6 +395,16 @@ struct Membertrix {
 			if (matrix[(size_t)j * N + i]) return j;
 		return -1;
 	}
+	/* membertrix.cpp:315-322: column scan, ascending item id, APPENDS to the list it is given */
+	void getAssignments(int cluster_id, std::vector<int> &ids) const {
+		if (dense) {
+			for (int i = 0; i < N; ++i)
+				if (matrix[(size_t)cluster_id * N + i]) ids.push_back(i);
+		} else {
+			for (int i = 0; i < N; ++i)
+				if (z[i] == cluster_id) ids.push_back(i);
+		}
+	}
 	bool empty(int id) { return clusters_dataset.at(id)->size() == 0; }
 	size_t count(int id) const { return clusters_dataset.at(id)->size(); }
 	/* membertrix.cpp:213-228 */
@@ -527,6 +537,7 @@ struct npo_run {
 	std::vector<int64_t> tr_order_off;
 	std::vector<double> tr_aux_mu, tr_aux_sigma, tr_u;
 	std::vector<double> sweep_reassign_seconds, sweep_total_seconds;
+	std::vector<int> K_after_call; /* cluster count after every sampler.update() (RECORD_TRACE) */
 	/* slot allocator */
 	std::vector<char> slot_used;
 	int alloc_slot() {
@@ -701,7 +712,17 @@ struct Sampler {
 		for (int i = 0; i < N; ++i) run.tr_z_after.push_back(trix.cluster_objects.at(trix.z[i])->slot);
 	}
 
-	void sm_update(const std::vector<int> &subset); /* split/merge samplers, below */
+	/* split/merge samplers, np_oracle_sm.inc */
+	void sm_update(const std::vector<int> &subset);
+	double logprob_items(const Theta &th, const std::vector<int> &items);
+	bool jn_split(int data_i, int data_j, int cur_id);
+	bool jn_merge(int id0, int id1);
+	void jn_update(const std::vector<int> &ids);
+	void tri_allocate(std::vector<std::vector<int>> &pdata, const std::vector<int> &picks, int Q,
+			const std::vector<int> &source_ids, const std::vector<const Theta *> &target);
+	bool tri_split(const std::vector<int> &picks, std::vector<int> &cluster_ids);
+	bool tri_merge(const std::vector<int> &picks, std::vector<int> &cluster_ids);
+	void tri_update(const std::vector<int> &picks);
 
 	/* MCMC::run (np_mcmc.cpp:48-175) */
 	void mcmc_run() {
@@ -759,6 +780,7 @@ struct Sampler {
 				else
 					sm_update(subset);
 				st.updates++;
+				if (record) run.K_after_call.push_back((int)trix.cluster_objects.size());
 			}
 			{
 				double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -785,10 +807,7 @@ struct Sampler {
 	}
 };
 
-void Sampler::sm_update(const std::vector<int> &) {
-	/* split/merge samplers are added in oracle/np_oracle_sm.inc once the Alg. 8 path is green */
-	assert(false && "split-merge oracle not built in this translation unit");
-}
+#include "np_oracle_sm.inc"
 
 } // namespace
 
@@ -960,6 +979,8 @@ void npo_run_sweep_seconds(const npo_run *r, double *reassign, double *total) {
 	std::memcpy(reassign, r->sweep_reassign_seconds.data(), sizeof(double) * r->sweep_reassign_seconds.size());
 	std::memcpy(total, r->sweep_total_seconds.data(), sizeof(double) * r->sweep_total_seconds.size());
 }
+int64_t npo_run_K_after_len(const npo_run *r) { return (int64_t)r->K_after_call.size(); }
+void npo_run_K_after(const npo_run *r, int *out) { std::copy(r->K_after_call.begin(), r->K_after_call.end(), out); }
 int64_t npo_trace_steps(const npo_run *r) { return (int64_t)r->tr_item.size(); }
 int64_t npo_trace_order_len(const npo_run *r) { return (int64_t)r->tr_order.size(); }
 int npo_trace_max_slot(const npo_run *r) { return (int)r->slot_used.size(); }

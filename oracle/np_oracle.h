@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-enum { NPO_ALG8 = 8, NPO_JAIN_NEAL = 2, NPO_TRIADIC = 3 };
+enum { NPO_ALG8 = 8, NPO_JAIN_NEAL = 2, NPO_TRIADIC = 3 }; /* JN / triadic: np_oracle_sm.inc */
 
 /* option flags */
 enum {
@@ -112,6 +112,10 @@ void npo_run_assignments(const npo_run *r, int which /*0 final, 1 max-likelihood
 /* per-sweep wall time: the update() loop only (np_mcmc.cpp:146-163) and the whole sweep body; [T] each */
 void npo_run_sweep_seconds(const npo_run *r, double *reassign, double *total);
 int npo_run_params(const npo_run *r, int *K, double *mu /*[K,D]*/, double *Sigma /*[K,D,D]*/, int64_t *counts, int cap);
+
+/* cluster count after every sampler.update() call (needs NPO_RECORD_TRACE) */
+int64_t npo_run_K_after_len(const npo_run *r);
+void npo_run_K_after(const npo_run *r, int *out);
 
 /* initial state (after np_mcmc.cpp:49-91), in SLOT numbering: for GPU replay */
 int npo_run_init_K(const npo_run *r);

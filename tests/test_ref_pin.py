@@ -61,3 +61,23 @@ def test_alg8_trajectory_matches_reference_3d(oracle):
                      flags=oracle.FAITHFUL | oracle.RECORD_TRACE)
     assert np.array_equal(run.assignments(0), ref["z_final"])
     assert same_partition(run.assignments(1), ref["z_maxlik"])
+
+
+@pytest.mark.parametrize("alg,seed", [(2, 1), (2, 2), (3, 1), (3, 2), (3, 3)])
+def test_split_merge_trajectory_matches_reference(oracle, alg, seed):
+    """Jain-Neal (np_jain_neal_algorithm.cpp) and triadic (np_triadic_algorithm.cpp) restatements in
+    oracle/np_oracle_sm.inc: same number of proposals (Q11 collisions skipped alike), same cluster count after EVERY
+    proposal, same final and max-likelihood partitions as the reference's own code."""
+    X, _ = syn.twogaussians()
+    pr = syn.reference_prior(2)
+    T = 30
+    ref = refrun.run(X, pr, alg, T=T, seed_main=seed, seed_shuffle=500 + seed, record=True)
+    run = oracle.Run(oracle.make_prior(**pr), X, {2: oracle.JAIN_NEAL, 3: oracle.TRIADIC}[alg], T=T, seed_main=seed,
+                     seed_shuffle=500 + seed, flags=oracle.FAITHFUL | oracle.RECORD_TRACE)
+    st = run.stats()
+    assert ref["calls"] == st.updates and st.updates < T * len(X)  # some subsets collide (np_mcmc.cpp:155-158)
+    assert np.array_equal(run.K_after(), ref["K_after"])
+    assert sum(st.sm_accepts) > 0
+    assert same_partition(run.assignments(0), ref["z_final"])
+    assert same_partition(run.assignments(1), ref["z_maxlik"])
+    assert st.K_final == ref["K_final"]
