@@ -121,6 +121,15 @@ npb_status npb_chains_init_from_params(npb_chains *ch, int K, const double *mu /
  * JainNealAlgorithm::update (np_jain_neal_algorithm.cpp:424-502) or TriadicAlgorithm::update
  * (np_triadic_algorithm.cpp:633-795) inside. */
 npb_status npb_chains_sweep(npb_chains *ch, int sampler, int n_sweeps, npb_sweep_stats *stats);
+/* split-merge samplers only: the first n_proposals subsets of the next sweep(s) (np_mcmc.cpp:146-163; subsets with a
+ * repeated item are skipped like the reference does, :155-158).  n_proposals == N is one sweep.  Reports
+ * stats->reassignments = proposals actually made, sm_attempts/sm_accepts per move type, sams_allocations. */
+npb_status npb_chains_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, npb_sweep_stats *stats);
+/* detail of the LAST proposal of every chain, detail_out [n_chains,16] floats: move type (0 JN split, 1 JN merge,
+ * 2 triadic split, 3 triadic merge), statistics index, log acceptance ratio, accepted, part sizes |P_0..2|, pool size,
+ * new slot, removed slot, the uniform, Q.  For parity tests of the acceptance arithmetic
+ * (np_jain_neal_algorithm.cpp:243-296,339-392; np_triadic_algorithm.cpp:370-437,529-590). */
+npb_status npb_chains_last_proposal(npb_chains *ch, float *detail_out);
 /* end-to-end form with host buffers: upload X (as npb_dataset_update), sweep, download the assignments of
  * all chains; z_out [N, n_chains] uint16 slot ids (item-major), may be NULL */
 npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,

@@ -27,6 +27,7 @@ EXPORTS = [
     "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
+    "npb_chains_split_merge", "npb_chains_last_proposal",
 ]
 
 
@@ -77,6 +78,8 @@ def load_library():
     L.npb_chains_set_state.argtypes = [vp, i64, ip, C.c_int, ip, dp, dp]
     L.npb_chains_init_from_params.argtypes = [vp, C.c_int, dp, dp]
     L.npb_chains_sweep.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SweepStats)]
+    L.npb_chains_split_merge.argtypes = [vp, C.c_int, i64, C.POINTER(SweepStats)]
+    L.npb_chains_last_proposal.argtypes = [vp, C.POINTER(C.c_float)]
     L.npb_chains_sweep_host.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(SweepStats)]
     L.npb_chain_update_alg8.argtypes = [vp, i64, i64]
     L.npb_replay_alg8.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp, i64, ip, C.POINTER(i64), ip, dp, dp,
@@ -266,6 +269,20 @@ class Chains:
         self.ctx.check(self.ctx._lib.npb_chains_sweep(self._h, sampler, n_sweeps, C.byref(st) if want_stats else None))
         return st
 
+    def split_merge(self, sampler, n_proposals):
+        """the first n_proposals subsets of the next sweep of a split-merge sampler (np_mcmc.cpp:146-163)"""
+        st = SweepStats()
+        self.ctx.check(self.ctx._lib.npb_chains_split_merge(self._h, sampler, n_proposals, C.byref(st)))
+        return st
+
+    PROPOSAL_FIELDS = ("type", "stat", "logA", "accept", "n0", "n1", "n2", "pool", "new_slot", "dying", "u", "Q")
+
+    def last_proposal(self):
+        """detail of the last split-merge proposal of every chain -> dict of [C] arrays (npb_chains_last_proposal)"""
+        out = np.zeros((self.C, 16), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.npb_chains_last_proposal(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return {k: out[:, i].copy() for i, k in enumerate(self.PROPOSAL_FIELDS)}
+
     def sweep_host(self, X, sampler=ALG8, n_sweeps=1, z_out=None, want_stats=False):
         """end-to-end step with host buffers: H2D of X, sweep, D2H of all assignments [N, C] uint16"""
         st = SweepStats()
@@ -332,6 +349,18 @@ class NealAlgorithm8:
     """UpdateClusterPopulation implementation selected by `-a algorithm8` (np_main.cpp:433-439)."""
     sampler = ALG8
     subset_count = 1
+
+
+class JainNealAlgorithm:
+    """UpdateClusterPopulation implementation selected by `-a jain_neal_split` (np_main.cpp:440-446)."""
+    sampler = JAIN_NEAL
+    subset_count = 2
+
+
+class TriadicAlgorithm:
+    """UpdateClusterPopulation implementation selected by `-a triadic` (np_main.cpp:447-458)."""
+    sampler = TRIADIC
+    subset_count = 3
 
 
 class MCMC:

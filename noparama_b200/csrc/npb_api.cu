@@ -302,7 +302,9 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 			(e = cudaMalloc((void **)&ch->counts, (size_t)n_chains * Kmax * sizeof(int))) != cudaSuccess ||
 			(e = cudaMalloc((void **)&ch->st, (size_t)n_chains * 4 * sizeof(unsigned long long))) != cudaSuccess ||
 			(e = cudaMalloc((void **)&ch->kocc, (size_t)n_chains * sizeof(int))) != cudaSuccess ||
-			(e = cudaMalloc((void **)&ch->overflow, (size_t)n_chains * sizeof(int))) != cudaSuccess) {
+			(e = cudaMalloc((void **)&ch->overflow, (size_t)n_chains * sizeof(int))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ch->smst, (size_t)n_chains * 12 * sizeof(unsigned long long))) != cudaSuccess ||
+			(e = cudaMemsetAsync(ch->smst, 0, (size_t)n_chains * 12 * sizeof(unsigned long long), ctx->stream)) != cudaSuccess) {
 		npb_chains_destroy(ch);
 		return npb_fail_cuda(ctx, e, "chain state allocation", __FILE__, __LINE__);
 	}
@@ -326,6 +328,12 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->overflow) cudaFree(ch->overflow);
 	if (ch->h_z) cudaFreeHost(ch->h_z);
 	if (ch->scan_order) cudaFree(ch->scan_order);
+	if (ch->smst) cudaFree(ch->smst);
+	if (ch->sm_zt) cudaFree(ch->sm_zt);
+	if (ch->sm_pool) cudaFree(ch->sm_pool);
+	if (ch->sm_dec) cudaFree(ch->sm_dec);
+	if (ch->sm_order) cudaFree(ch->sm_order);
+	if (ch->sm_detail) cudaFree(ch->sm_detail);
 	delete ch;
 	return NPB_OK;
 }
@@ -409,20 +417,27 @@ npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z,
 	return NPB_OK;
 }
 
-static npb_status collect_stats(npb_chains *ch, const std::vector<unsigned long long> &before, int n_sweeps, float ms,
-		npb_sweep_stats *stats) {
+static npb_status collect_stats(npb_chains *ch, const std::vector<unsigned long long> &before,
+		const std::vector<unsigned long long> &sm_before, int sampler, int n_sweeps, float ms, npb_sweep_stats *stats) {
 	npb_ctx *ctx = ch->ctx;
 	const size_t C = (size_t)ch->C;
-	std::vector<unsigned long long> st(C * 4);
+	std::vector<unsigned long long> st(C * 4), sm(C * 12);
+	NPB_CUDA_OK(cudaMemcpyAsync(sm.data(), ch->smst, sizeof(unsigned long long) * C * 12, cudaMemcpyDeviceToHost, ctx->stream));
 	std::vector<int> kocc(C), ovf(C);
 	NPB_CUDA_OK(cudaMemcpyAsync(st.data(), ch->st, sizeof(unsigned long long) * C * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	NPB_CUDA_OK(cudaMemcpyAsync(kocc.data(), ch->kocc, sizeof(int) * C, cudaMemcpyDeviceToHost, ctx->stream));
 	NPB_CUDA_OK(cudaMemcpyAsync(ovf.data(), ch->overflow, sizeof(int) * C, cudaMemcpyDeviceToHost, ctx->stream));
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	memset(stats, 0, sizeof(*stats));
-	stats->reassignments = (int64_t)C * ch->ds->N * n_sweeps;
+	stats->reassignments = sampler == NPB_ALG8 ? (int64_t)C * ch->ds->N * n_sweeps : 0;
 	double sumK = 0;
 	for (size_t c = 0; c < C; ++c) {
+		for (int j = 0; j < 4; ++j) {
+			stats->sm_attempts[j] += (int64_t)(sm[c * 12 + j] - sm_before[c * 12 + j]);
+			stats->sm_accepts[j] += (int64_t)(sm[c * 12 + 4 + j] - sm_before[c * 12 + 4 + j]);
+		}
+		stats->sams_allocations += (int64_t)(sm[c * 12 + 8] - sm_before[c * 12 + 8]);
+		if (sampler != NPB_ALG8) stats->reassignments += (int64_t)(sm[c * 12 + 9] - sm_before[c * 12 + 9]); // proposals made
 		stats->candidates += (int64_t)(st[c * 4 + 0] - before[c * 4 + 0]);
 		stats->moved += (int64_t)(st[c * 4 + 1] - before[c * 4 + 1]);
 		stats->new_clusters += (int64_t)(st[c * 4 + 2] - before[c * 4 + 2]);
@@ -435,15 +450,21 @@ static npb_status collect_stats(npb_chains *ch, const std::vector<unsigned long 
 	return NPB_OK;
 }
 
-static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, npb_sweep_stats *stats, const double *X, uint16_t *z_out) {
-	if (!ch || n_sweeps < 0) return NPB_E_BAD_ARG;
+static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_t n_proposals, npb_sweep_stats *stats,
+		const double *X, uint16_t *z_out) {
+	if (!ch || n_sweeps < 0 || n_proposals < 0) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
-	if (sampler != NPB_ALG8) return npb_fail(ctx, NPB_E_UNSUPPORTED, "sampler not implemented on the device yet");
-	std::vector<unsigned long long> before;
+	if (sampler == NPB_ALG2)
+		return npb_fail(ctx, NPB_E_UNSUPPORTED, "Algorithm 2 is dead code in the reference (np_neal_algorithm2.cpp is not compiled); not built");
+	if (sampler != NPB_ALG8 && sampler != NPB_JAIN_NEAL && sampler != NPB_TRIADIC) return NPB_E_BAD_ARG;
+	if (sampler == NPB_ALG8 && n_proposals) return NPB_E_BAD_ARG;
+	std::vector<unsigned long long> before, sm_before;
 	if (stats) {
 		before.resize((size_t)ch->C * 4);
+		sm_before.resize((size_t)ch->C * 12);
 		NPB_CUDA_OK(cudaMemcpyAsync(before.data(), ch->st, sizeof(unsigned long long) * before.size(), cudaMemcpyDeviceToHost, ctx->stream));
+		NPB_CUDA_OK(cudaMemcpyAsync(sm_before.data(), ch->smst, sizeof(unsigned long long) * sm_before.size(), cudaMemcpyDeviceToHost, ctx->stream));
 		NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	}
 	npb_status s;
@@ -454,8 +475,15 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, npb_sw
 	s = ensure_whitened(ch->ds);
 	if (s != NPB_OK) return s;
 	NPB_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
-	if (n_sweeps > 0) {
+	if (sampler == NPB_ALG8 && n_sweeps > 0) {
 		s = npb_launch_alg8_sweep(ch, n_sweeps);
+		if (s != NPB_OK) return s;
+	} else if (sampler != NPB_ALG8 && (n_sweeps > 0 || n_proposals > 0)) {
+		if (!ch->sm_detail) {
+			NPB_CUDA_OK(cudaMalloc((void **)&ch->sm_detail, (size_t)ch->C * 16 * sizeof(float)));
+			NPB_CUDA_OK(cudaMemsetAsync(ch->sm_detail, 0, (size_t)ch->C * 16 * sizeof(float), ctx->stream));
+		}
+		s = npb_launch_split_merge(ch, sampler, n_proposals, n_sweeps, ch->sm_detail);
 		if (s != NPB_OK) return s;
 	}
 	NPB_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -469,7 +497,7 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, npb_sw
 	float ms = 0.0f;
 	NPB_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	if (stats) {
-		s = collect_stats(ch, before, n_sweeps, ms, stats);
+		s = collect_stats(ch, before, sm_before, sampler, n_sweeps, ms, stats);
 		if (s != NPB_OK) return s;
 		if (stats->overflow_chains) return npb_fail(ctx, NPB_E_KMAX_OVERFLOW, "at least one chain ran out of cluster slots");
 	}
@@ -477,12 +505,25 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, npb_sw
 }
 
 npb_status npb_chains_sweep(npb_chains *ch, int sampler, int n_sweeps, npb_sweep_stats *stats) {
-	return sweep_common(ch, sampler, n_sweeps, stats, nullptr, nullptr);
+	return sweep_common(ch, sampler, n_sweeps, 0, stats, nullptr, nullptr);
+}
+npb_status npb_chains_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, npb_sweep_stats *stats) {
+	if (sampler != NPB_JAIN_NEAL && sampler != NPB_TRIADIC) return NPB_E_BAD_ARG;
+	return sweep_common(ch, sampler, 0, n_proposals, stats, nullptr, nullptr);
+}
+npb_status npb_chains_last_proposal(npb_chains *ch, float *detail_out) {
+	if (!ch || !detail_out) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	if (!ch->sm_detail) return npb_fail(ctx, NPB_E_BAD_ARG, "no split-merge proposal has been made on this handle");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	NPB_CUDA_OK(cudaMemcpyAsync(detail_out, ch->sm_detail, (size_t)ch->C * 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
 }
 npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,
 		npb_sweep_stats *stats) {
 	if (!X) return NPB_E_BAD_ARG;
-	return sweep_common(ch, sampler, n_sweeps, stats, X, z_out);
+	return sweep_common(ch, sampler, n_sweeps, 0, stats, X, z_out);
 }
 
 npb_status npb_chains_get_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out) {

@@ -53,6 +53,13 @@ struct npb_chains {
 	npb_z_t *h_z = nullptr;     // pinned staging for npb_chains_sweep_host
 	int32_t *scan_order = nullptr; // [scan_cap, N] item visited at each step of the sweeps of one launch
 	int scan_cap = 0;              // sweeps per launch the buffer holds
+	// split-merge samplers (npb_splitmerge.cu)
+	unsigned long long *smst = nullptr; // [C, 12]: attempts[4], accepts[4], SAMS allocations, proposals, 2 reserved
+	npb_z_t *sm_zt = nullptr;      // [C, zstride] chain-major working copy of z
+	int32_t *sm_pool = nullptr;    // [C, N]
+	uint8_t *sm_dec = nullptr;     // [C, N]
+	int32_t *sm_order = nullptr;   // [3, N]
+	float *sm_detail = nullptr;    // [C, 16] detail of the last proposal of every chain (tests)
 };
 
 struct SweepArgs {
@@ -82,4 +89,5 @@ void npb_theta_to_sigma(int D, const double *T_packed_upper, double *Sigma);
 npb_status npb_launch_whiten(npb_dataset *ds);
 npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given);
 npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps);
+npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, int whole_sweeps, float *d_detail);
 PriorDev npb_prior_dev(const npb_ctx *ctx, int m_aux);

@@ -33,6 +33,22 @@ def cfg1_seed(seed):
     return fin + best + (s.K_final, s.mean_K, s.moved / s.updates, s.new_cluster_events / s.updates, s.max_loglik)
 
 
+T_SM = {orc.JAIN_NEAL: 100, orc.TRIADIC: 300}
+
+
+def cfg1_sm_seed(args):
+    """split-merge samplers on config 1 (oracle/np_oracle_sm.inc, pinned to the reference's own code by
+    tests/test_ref_pin.py)"""
+    alg, seed = args
+    X, y = syn.config(1)
+    pr = orc.make_prior(**syn.reference_prior(2))
+    r = orc.Run(pr, X, alg, T=T_SM[alg], seed_main=30_000 + seed, seed_shuffle=40_000 + seed,
+                flags=orc.UPDATE_CLUSTERS | orc.MAX_LIKELIHOOD)
+    s = r.stats()
+    return orc.metrics(y, r.assignments(0)) + (s.K_final, s.mean_K, s.updates, s.sams_allocations) + \
+        tuple(s.sm_attempts) + tuple(s.sm_accepts)
+
+
 def density_cases():
     out = {}
     for D in (2, 16, 64):
@@ -61,6 +77,14 @@ def main():
                         ari_maxlik=res[:, 5], K_final=res[:, 6], mean_K=res[:, 7], moved=res[:, 8], births=res[:, 9],
                         max_loglik=res[:, 10], T=T_CFG1)
     np.savez_compressed(os.path.join(HERE, "density_cases.npz"), **density_cases())
+    for alg, name in ((orc.JAIN_NEAL, "jain_neal"), (orc.TRIADIC, "triadic")):
+        with Pool(os.cpu_count()) as pool:
+            r = np.array(pool.map(cfg1_sm_seed, [(alg, s) for s in range(N_SEEDS)]), dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, "oracle_cfg1_%s_256seeds.npz" % name), purity=r[:, 0], rand=r[:, 1],
+                            ari=r[:, 2], K_final=r[:, 3], mean_K=r[:, 4], updates=r[:, 5], sams=r[:, 6],
+                            attempts=r[:, 7:11], accepts=r[:, 11:15], T=T_SM[alg])
+        print("%s: K %.2f purity %.4f ARI %.4f attempts %s accepts %s" % (name, r[:, 3].mean(), r[:, 0].mean(), r[:, 2].mean(),
+              r[:, 7:11].sum(0), r[:, 11:15].sum(0)))
     print("cfg1 over %d seeds: purity %.4f  RI %.4f  ARI %.4f  K %.2f  moved %.3f  births/step %.5f" %
           (N_SEEDS, res[:, 0].mean(), res[:, 1].mean(), res[:, 2].mean(), res[:, 6].mean(), res[:, 8].mean(), res[:, 9].mean()))
 
