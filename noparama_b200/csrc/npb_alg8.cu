@@ -13,7 +13,8 @@
 // lane j of the warp prefetches item, old assignment and coordinates of step s0+j and draws that step's
 // auxiliary parameters from Philox, so the sequential part of a step is: keys -> warp arg-max -> count update
 // (an exponential race, exact in distribution; see npb_alg8_kernel.cuh).  Weights stay in the log2 domain.
-#include "npb_alg8_tile.cuh"
+#include "npb_alg8_tile4.cuh"
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------------------
 // init: np_mcmc.cpp:49-91 -- K0 clusters from the base measure (np_init_clusters.cpp:24-41), every item to a
@@ -146,6 +147,9 @@ NPB_DECL(3, 1) NPB_DECL(3, 2) NPB_DECL(3, 4) NPB_DECL(3, 8)
 #define NPB_TDECL(D, K) extern template npb_status npb_launch_alg8_tile<D, K>(npb_chains *, const SweepArgs &);
 NPB_TDECL(4, 32) NPB_TDECL(4, 64) NPB_TDECL(8, 32) NPB_TDECL(8, 64) NPB_TDECL(16, 32) NPB_TDECL(16, 64)
 #undef NPB_TDECL
+#define NPB_T4DECL(D) extern template npb_status npb_launch_alg8_tile4<D>(npb_chains *, const SweepArgs &);
+NPB_T4DECL(4) NPB_T4DECL(8) NPB_T4DECL(16)
+#undef NPB_T4DECL
 
 // scan order of sweeps sweep0 .. sweep0+n_sweeps-1 into order[n_sweeps][N] (npb_common.cuh: keyed permutation with
 // cycle walking; evaluated once per sweep here instead of per chain inside the sweep kernel)
@@ -164,8 +168,15 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	NPB_CUDA_OK(cudaGetLastError());
 	SweepArgs a = make_args(ch, n_sweeps);
 	npb_status s = NPB_E_UNSUPPORTED;
-	const int key = ch->D * 1000 + ch->Kmax / 32;
+	int key = ch->D * 1000 + ch->Kmax / 32;
+	// Kmax = 32, D >= 4: four chains per CTA with setmaxnreg (npb_alg8_tile4.cuh); NPB_TILE_KERNEL=2warp selects the
+	// earlier one-chain-per-CTA kernel for A/B measurements
+	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
+	if (!two_warp && ch->Kmax == 32 && (ch->D == 4 || ch->D == 8 || ch->D == 16)) key = -ch->D;
 	switch (key) {
+	case -4: s = npb_launch_alg8_tile4<4>(ch, a); break;
+	case -8: s = npb_launch_alg8_tile4<8>(ch, a); break;
+	case -16: s = npb_launch_alg8_tile4<16>(ch, a); break;
 	case 2001: s = npb_launch_alg8_reg<2, 1>(ch, a); break;
 	case 2002: s = npb_launch_alg8_reg<2, 2>(ch, a); break;
 	case 2004: s = npb_launch_alg8_reg<2, 4>(ch, a); break;

@@ -1,0 +1,334 @@
+// npb_alg8_tile4.cuh -- Algorithm 8 sweeps for D = 4, 8, 16 and Kmax = 32: four chains per CTA, register budget moved
+// from the consumer warps to the producer warps with setmaxnreg.
+//
+// Same algorithm and the same random streams as k_alg8_sweep_tile (npb_alg8_tile.cuh), a different mapping.  ncu on the two-warp CTA showed the FP32 pipe 30 % busy with the schedulers issuing on 44 % of
+// the cycles: every thread of the kernel was allocated the ~200 registers the PRODUCER needs to keep one slot's
+// parameters resident, so only 8 warps fitted an SM (two per scheduler) and the dependent chain of the consumer's
+// sequential race could not be hidden.  Here
+//   * warps 0-3 (one warpgroup) are the CONSUMERS of chains 4b .. 4b+3, warps 4-7 their PRODUCERS;
+//   * the kernel is launched at 128 registers per thread, two CTAs per SM; the consumer warpgroup shrinks to 56
+//     registers (setmaxnreg.dec) and the producer warpgroup grows to 200 (setmaxnreg.inc): 16 resident warps per SM
+//     instead of 8 out of the same register file;
+//   * the master copy of the slot table stays in global memory (L2): producers read their slot once per launch and
+//     after a birth, so shared memory only holds the two [slot x step] tiles, the staged item rows and the versions
+//     (11 KB per chain);
+//   * one rendezvous barrier per (chain, buffer): the producer arrives after filling buffer b, the consumer before
+//     draining it; by the time the producer comes back to buffer b it has passed the other buffer's rendezvous, which
+//     the consumer reaches only after draining b.
+#pragma once
+#include "npb_alg8_tile.cuh"
+
+#define NPB_T4_CHAINS 4
+#define NPB_T4_CONSUMER_REGS 56
+#define NPB_T4_PRODUCER_REGS 200
+
+template <int D>
+struct Tile4Smem {
+	float tile[2][32 * 33];   // [buffer][slot * 33 + step]
+	float xs[NPB_TILE * D];   // item rows of the tile the producer is working on
+	int ver_tile[2][32];      // version of slot k the buffer's column was computed from, -1 = not computed
+	int ver_cur[32];          // current slot versions (bumped by a birth)
+	unsigned occ;             // occupancy bit mask, maintained by the consumer
+	unsigned pad[3];
+};
+
+// log2 N(x | theta) with theta streamed from global memory (consumer side, rare: a newborn slot's column)
+template <int D>
+__device__ __noinline__ float log2density_stream(const float *th, const float *xrow) {
+	constexpr int TRI = npb_tri(D);
+	float q = 0.0f;
+	for (int r = 0; r < D; ++r) {
+		float y = 0.0f;
+		for (int c = r; c < D; ++c) y = fmaf(__ldcg(th + D + npb_tri_off(D, r, c)), __ldg(xrow + c) - __ldcg(th + c), y);
+		q = fmaf(y, y, q);
+	}
+	return __ldcg(th + D + TRI) - q;
+}
+
+template <int D, int M>
+__global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) {
+	constexpr int TRI = npb_tri(D), PS = npb_ps(D), PSP = npb_psp(D), KMAX = 32;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int wid = threadIdx.x >> 5;
+	const bool producer = wid >= NPB_T4_CHAINS;
+	const int cl = wid & (NPB_T4_CHAINS - 1);
+	Tile4Smem<D> &sm = reinterpret_cast<Tile4Smem<D> *>(smem_raw)[cl];
+	const int chain = blockIdx.x * NPB_T4_CHAINS + cl;
+	const int N = a.N, C = a.C;
+	const int bar0 = 1 + cl * 2; // named barriers 1..8: rendezvous of (chain, buffer)
+	const int tiles_per_sweep = (N + NPB_TILE - 1) / NPB_TILE;
+
+	if (producer) {
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(NPB_T4_PRODUCER_REGS));
+		if (chain >= C) return;
+		// =========================== PRODUCER: lane = slot ===========================
+		const int k = lane;
+		const float *thg = a.theta + ((size_t)chain * KMAX + k) * PS;
+		float P[PSP];
+#pragma unroll
+		for (int e = 0; e < PSP; ++e) P[e] = e < PS ? __ldcg(thg + e) : 0.0f;
+		int myver = 0;
+		float *xs = sm.xs;
+		int t = 0;
+		// wait for the consumer's initial occupancy mask / versions
+		named_bar_sync(bar0, 64);
+		for (int sw = 0; sw < a.n_sweeps; ++sw) {
+			const int32_t *order = a.scan_order + (size_t)sw * N;
+			for (int ti = 0; ti < tiles_per_sweep; ++ti, ++t) {
+				const int b = t & 1;
+				const int s0 = ti * NPB_TILE;
+				const int cnt = min(NPB_TILE, N - s0);
+				{
+					const int item = (lane < cnt) ? order[s0 + lane] : 0;
+					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)item * D);
+					float4 *dst = reinterpret_cast<float4 *>(xs + lane * D);
+#pragma unroll
+					for (int c = 0; c < D / 4; ++c) dst[c] = __ldg(src + c);
+				}
+				__syncwarp();
+				const bool occupied = (*((volatile unsigned *)&sm.occ) >> lane) & 1u;
+				const int ver = ((volatile int *)sm.ver_cur)[k];
+				__threadfence_block(); // the version is read before the parameters
+				if (ver != myver) { // a birth re-used this slot: fetch the new parameters from the master copy
+#pragma unroll
+					for (int e = 0; e < PS; ++e) P[e] = __ldcg(thg + e);
+					myver = ver;
+				}
+				if (occupied) {
+					int j = 0;
+					for (; j + 1 < cnt; j += 2) {
+						float x0[D], x1[D];
+						load_row<D>(xs + j * D, x0);
+						load_row<D>(xs + (j + 1) * D, x1);
+						const float l0 = log2density_regs<D>(P, x0);
+						const float l1 = log2density_regs<D>(P, x1);
+						sm.tile[b][k * 33 + j] = l0;
+						sm.tile[b][k * 33 + j + 1] = l1;
+					}
+					if (j < cnt) {
+						float x0[D];
+						load_row<D>(xs + j * D, x0);
+						sm.tile[b][k * 33 + j] = log2density_regs<D>(P, x0);
+					}
+				}
+				sm.ver_tile[b][k] = occupied ? myver : -1;
+				__syncwarp();
+				__threadfence_block();
+				named_bar_sync(bar0 + b, 64); // hand buffer b over
+			}
+		}
+		return;
+	}
+
+	asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(NPB_T4_CONSUMER_REGS));
+	if (chain >= C) return;
+	// =========================== CONSUMER: lane = step (prologue) / lane = slot (steps) ===========================
+	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+	float *thc = a.theta + (size_t)chain * KMAX * PS;
+	float n = (float)a.counts[(size_t)chain * KMAX + lane];
+	int kocc = __popc(__ballot_sync(0xffffffffu, n > 0.0f));
+	sm.ver_cur[lane] = 0;
+	sm.ver_tile[0][lane] = -1;
+	sm.ver_tile[1][lane] = -1;
+	{
+		const unsigned b = __ballot_sync(0xffffffffu, n > 0.0f);
+		__syncwarp();
+		if (lane == 0) sm.occ = b;
+	}
+	__threadfence_block();
+	named_bar_sync(bar0, 64); // initial state published
+	unsigned long long st_cand = 0ull, st_moved = 0ull, st_births = 0ull;
+	int overflow = 0;
+	const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
+
+	// re-evaluates the tile column of `slot` for steps >= j_from of buffer b (lane = step) from the master copy
+	auto fix_column = [&](int slot, int b, int j_from, int item, bool valid) {
+		const float l = log2density_stream<D>(thc + (size_t)slot * PS, a.X + (size_t)item * D);
+		if (valid && lane >= j_from) sm.tile[b][slot * 33 + lane] = l;
+		__syncwarp();
+	};
+
+	int t = 0;
+	for (int sw = 0; sw < a.n_sweeps; ++sw) {
+		const uint32_t sweep = a.sweep0 + (uint32_t)sw;
+		const int32_t *order = a.scan_order + (size_t)sw * N;
+		for (int ti = 0; ti < tiles_per_sweep; ++ti, ++t) {
+			const int b = t & 1;
+			const int s0 = ti * NPB_TILE;
+			const int sj = s0 + lane;
+			const bool valid = sj < N;
+			const int item = valid ? order[sj] : 0;
+			const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
+			int znew = zold;
+			// ---- auxiliary draws of step sj (np_neal_algorithm8.cpp:79-84,119-126) and their race keys; the normals are
+			// consumed pair by pair in the order aux_normals() produces them (no per-draw arrays: 56 registers) ----
+			float auxkey_j = -INFINITY;
+			int auxm = 0;
+			{
+				const float *xw = a.Xw + (size_t)item * D;
+				uint32_t as[4];
+				ph((uint32_t)sj, 1u, sweep, NPB_RNG_AUX, as);
+				float lkey[M];
+#pragma unroll
+				for (int m = 0; m < M; ++m) {
+					float g0, g1;
+					{
+						const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+						npb_normal2(r0, r1, g0, g1);
+					}
+					const float v = a.prior.v_mean + a.prior.nu * g0;
+					const float av = fmaxf(fabsf(v), 1e-20f);
+					const float inv = __frcp_rn(av);
+					float q;
+					{
+						const float y = __ldg(xw) * inv - g1 * ik2; // coordinate 0 pairs with normal 1
+						q = y * y;
+					}
+#pragma unroll
+					for (int p = 1; p < (D + 2) / 2; ++p) {
+						const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+						npb_normal2(r0, r1, g0, g1);
+						// normals 2p and 2p+1 belong to coordinates 2p-1 and 2p
+						const float ya = __ldg(xw + 2 * p - 1) * inv - g0 * ik2;
+						q = fmaf(ya, ya, q);
+						if (2 * p < D) {
+							const float yb = __ldg(xw + 2 * p) * inv - g1 * ik2;
+							q = fmaf(yb, yb, q);
+						}
+					}
+					lkey[m] = a.prior.c0_2 - (float)D * fast_lg2(av) - q + a.prior.log2_alpha_m;
+				}
+#pragma unroll
+				for (int m = 0; m < M; ++m) {
+					const float key = lkey[m] + neg_lg2_exp1(xoshiro_next(as));
+					if (key > auxkey_j) { auxkey_j = key; auxm = m; }
+				}
+			}
+			const int zold_aux_j = zold | (auxm << 16);
+			uint32_t rs[4];
+			ph((uint32_t)sj, 0u, sweep, NPB_RNG_PICK, rs);
+			const int cnt = min(NPB_TILE, N - s0);
+
+			named_bar_sync(bar0 + b, 64); // the producer has filled buffer b
+			{
+				unsigned stale = __ballot_sync(0xffffffffu, n > 0.0f && sm.ver_tile[b][lane] != sm.ver_cur[lane]);
+				while (stale) {
+					const int k = __ffs(stale) - 1;
+					stale &= stale - 1;
+					fix_column(k, b, 0, item, valid);
+				}
+			}
+			unsigned cand_tile = 0u;
+
+			for (int j = 0; j < cnt; ++j) {
+				const int zo_aux = __shfl_sync(0xffffffffu, zold_aux_j, j);
+				const float ak = __shfl_sync(0xffffffffu, auxkey_j, j);
+				const int zo = zo_aux & 0xffff;
+				const float base = sm.tile[b][lane * 33 + j] + neg_lg2_exp1(xoshiro_next(rs));
+				const float ne = (zo == lane) ? n - 1.0f : n;
+				const float key = ne > 0.0f ? base + fast_lg2(ne) : -INFINITY;
+				const int my_enc = float_order_key(key);
+				const int top = max(__reduce_max_sync(0xffffffffu, my_enc), float_order_key(ak));
+				const unsigned bal = __ballot_sync(0xffffffffu, my_enc == top && key > -INFINITY);
+				cand_tile += (unsigned)(kocc + M);
+				int new_slot;
+				bool born = false;
+				if (bal != 0u) {
+					new_slot = __ffs(bal) - 1;
+				} else {
+					born = true;
+					new_slot = zo;
+				}
+				if (born || new_slot != zo) {
+					// retract (membertrix.cpp:175-233)
+					bool dead = false;
+					if (zo == lane) {
+						n -= 1.0f;
+						dead = n <= 0.0f;
+					}
+					const bool died = __any_sync(0xffffffffu, dead);
+					if (died) {
+						kocc--;
+						cand_tile--;
+						if (lane == 0) sm.occ &= ~(1u << zo);
+					}
+					if (born) {
+						// np_neal_algorithm8.cpp:136-145: the lowest free slot takes theta' of the winning auxiliary draw
+						const unsigned fb = __ballot_sync(0xffffffffu, n <= 0.0f);
+						const int fs = fb ? __ffs(fb) - 1 : -1;
+						if (fs < 0) {
+							overflow = 1; // no room: the item goes back where it was
+							if (died) { kocc++; if (lane == 0) sm.occ |= 1u << zo; }
+						} else {
+							new_slot = fs;
+							const int m = (zo_aux >> 16) & 0xff;
+							const uint32_t step = (uint32_t)(s0 + j);
+							// re-derive theta' of draw m of this step from the step's stream: lane d takes normal 1+d
+							uint32_t as[4];
+							ph(step, 1u, sweep, NPB_RNG_AUX, as);
+							float gg[2 * ((D + 2) / 2)];
+							for (int mm = 0; mm <= m; ++mm) aux_normals<D>(as, gg);
+							const float v = a.prior.v_mean + a.prior.nu * gg[0];
+							const float av = fmaxf(fabsf(v), 1e-20f);
+							float g = 0.0f;
+#pragma unroll
+							for (int c = 0; c < D; ++c)
+								if (lane == c) g = gg[1 + c] * (av * a.prior.inv_sqrt_kappa);
+							float mu_r = lane < D ? a.prior.mu0[lane] : 0.0f;
+							for (int c = 0; c < D; ++c) {
+								const float gc = __shfl_sync(0xffffffffu, g, c);
+								if (lane <= c && lane < D) mu_r = fmaf(a.prior.S[npb_tri_off(D, lane, c)], gc, mu_r);
+							}
+							float *th = thc + (size_t)fs * PS;
+							if (lane < D) th[lane] = mu_r;
+							const float inv = 1.0f / av;
+							for (int q = lane; q < TRI; q += 32) th[D + q] = a.prior.CT2[q] * inv;
+							if (lane == 0) th[D + TRI] = a.prior.c0_2 - (float)D * log2f(av);
+							__threadfence();
+							__syncwarp();
+							if (lane == 0) { // publish only once theta is complete
+								sm.ver_cur[fs] += 1;
+								__threadfence_block();
+								sm.occ |= 1u << fs;
+							}
+							__syncwarp();
+							kocc++;
+							st_births++;
+							fix_column(fs, b, j + 1, item, valid);
+						}
+					}
+					if (new_slot == lane) n += 1.0f;
+					st_moved++;
+					if (lane == j) znew = new_slot;
+				}
+			}
+			if (valid && znew != zold) a.z[(size_t)item * C + chain] = (npb_z_t)znew;
+			__syncwarp();
+			st_cand += cand_tile;
+			__threadfence_block();
+		}
+	}
+
+	// ---- chain state back to memory (theta already lives there) ----
+	a.counts[(size_t)chain * KMAX + lane] = (int)n;
+	if (lane == 0) {
+		a.kocc[chain] = kocc;
+		if (overflow) a.overflow[chain] = 1;
+		a.st[(size_t)chain * 4 + 0] += st_cand;
+		a.st[(size_t)chain * 4 + 1] += st_moved;
+		a.st[(size_t)chain * 4 + 2] += st_births;
+	}
+}
+
+template <int D>
+npb_status npb_launch_alg8_tile4(npb_chains *ch, const SweepArgs &a) {
+	npb_ctx *ctx = ch->ctx;
+	if (ch->m_aux != 3) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 3 for the D >= 4 sweep kernel");
+	const size_t shmem = sizeof(Tile4Smem<D>) * NPB_T4_CHAINS;
+	NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_tile4<D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+	const unsigned blocks = (unsigned)((ch->C + NPB_T4_CHAINS - 1) / NPB_T4_CHAINS);
+	k_alg8_sweep_tile4<D, 3><<<blocks, 256, shmem, ctx->stream>>>(a);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
