@@ -25,12 +25,83 @@
 template <int D>
 struct Tile4Smem {
 	float tile[2][32 * 33];   // [buffer][slot * 33 + step]
-	float xs[NPB_TILE * D];   // item rows of the tile the producer is working on
+	float xs[NPB_TILE * D];   // item rows of the tile the producer is working on, pair-interleaved:
+	                          // xs[(p * D + c) * 2 + h] = coordinate c of item 2p + h
 	int ver_tile[2][32];      // version of slot k the buffer's column was computed from, -1 = not computed
 	int ver_cur[32];          // current slot versions (bumped by a birth)
 	unsigned occ;             // occupancy bit mask, maintained by the consumer
 	unsigned pad[3];
 };
+
+// Packed FP32 (sm_100a FFMA2): one instruction does two FMAs, on a 64-bit register pair; an operand written as
+// {t, t} is encoded as a broadcast of the 32-bit register t (SASS "R.F32"), so the slot's parameters are not duplicated.
+// The producer evaluates TWO items per instruction stream: pair = (item 2p, item 2p+1).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_bcast(float t) {
+	f32x2_t r;
+	// volatile: keeps the pack next to its use, where ptxas folds it into the FFMA2 operand (hoisted out of the item
+	// loop it would be materialised as a register PAIR per parameter, i.e. twice the registers)
+	asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(t));
+	return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+	f32x2_t r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+	return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float &lo, float &hi) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// log2 N(x | theta) of the two items of a pair.  Q[]: nb[D] = -(T2 mu), T2 packed upper row-wise, c2 -- so that
+// y = T2 x - T2 mu needs no subtraction per item: row r starts from the broadcast -b[r] at its diagonal column.
+// Column-major accumulation: D independent chains; x2 = D packed coordinates {x_2p[c], x_2p+1[c]} in shared memory.
+template <int D>
+__device__ __forceinline__ void log2density_pair(const float (&Q)[npb_psp(D)], const f32x2_t *x2, float &l0, float &l1) {
+	constexpr int TRI = npb_tri(D);
+	f32x2_t y[D];
+#pragma unroll
+	for (int c = 0; c < D; c += 2) {
+		const ulonglong2 xx = *reinterpret_cast<const ulonglong2 *>(x2 + c); // coordinates c and c+1 of both items
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const int cc = c + h;
+			const f32x2_t xc = h ? xx.y : xx.x;
+#pragma unroll
+			for (int r = 0; r < cc; ++r) y[r] = f2_fma(f2_bcast(Q[D + npb_tri_off(D, r, cc)]), xc, y[r]);
+			y[cc] = f2_fma(f2_bcast(Q[D + npb_tri_off(D, cc, cc)]), xc, f2_bcast(Q[cc]));
+		}
+	}
+	f32x2_t q0 = f2_bcast(0.0f), q1 = f2_bcast(0.0f);
+#pragma unroll
+	for (int r = 0; r < D; r += 2) {
+		q0 = f2_fma(y[r], y[r], q0);
+		q1 = f2_fma(y[r + 1], y[r + 1], q1);
+	}
+	float a0, a1, b0, b1;
+	f2_unpack(q0, a0, a1);
+	f2_unpack(q1, b0, b1);
+	l0 = Q[D + TRI] - (a0 + b0);
+	l1 = Q[D + TRI] - (a1 + b1);
+}
+
+// slot parameters in the producer's form: mu replaced by nb = -(T2 mu)
+template <int D>
+__device__ __forceinline__ void load_theta_nb(const float *thg, float (&Q)[npb_psp(D)]) {
+	constexpr int PS = npb_ps(D);
+#pragma unroll
+	for (int e = 0; e < npb_psp(D); ++e) Q[e] = e < PS ? __ldcg(thg + e) : 0.0f;
+	float nb[D];
+#pragma unroll
+	for (int r = 0; r < D; ++r) {
+		float s = 0.0f;
+#pragma unroll
+		for (int c = r; c < D; ++c) s = fmaf(Q[D + npb_tri_off(D, r, c)], Q[c], s);
+		nb[r] = -s;
+	}
+#pragma unroll
+	for (int r = 0; r < D; ++r) Q[r] = nb[r];
+}
 
 // log2 N(x | theta) with theta streamed from global memory (consumer side, rare: a newborn slot's column)
 template <int D>
@@ -66,8 +137,7 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 		const int k = lane;
 		const float *thg = a.theta + ((size_t)chain * KMAX + k) * PS;
 		float P[PSP];
-#pragma unroll
-		for (int e = 0; e < PSP; ++e) P[e] = e < PS ? __ldcg(thg + e) : 0.0f;
+		load_theta_nb<D>(thg, P);
 		int myver = 0;
 		float *xs = sm.xs;
 		int t = 0;
@@ -82,34 +152,29 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 				{
 					const int item = (lane < cnt) ? order[s0 + lane] : 0;
 					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)item * D);
-					float4 *dst = reinterpret_cast<float4 *>(xs + lane * D);
+					float *dst = xs + (lane >> 1) * (2 * D) + (lane & 1);
 #pragma unroll
-					for (int c = 0; c < D / 4; ++c) dst[c] = __ldg(src + c);
+					for (int c = 0; c < D / 4; ++c) {
+						const float4 v = __ldg(src + c);
+						dst[(4 * c + 0) * 2] = v.x; dst[(4 * c + 1) * 2] = v.y;
+						dst[(4 * c + 2) * 2] = v.z; dst[(4 * c + 3) * 2] = v.w;
+					}
 				}
 				__syncwarp();
 				const bool occupied = (*((volatile unsigned *)&sm.occ) >> lane) & 1u;
 				const int ver = ((volatile int *)sm.ver_cur)[k];
 				__threadfence_block(); // the version is read before the parameters
 				if (ver != myver) { // a birth re-used this slot: fetch the new parameters from the master copy
-#pragma unroll
-					for (int e = 0; e < PS; ++e) P[e] = __ldcg(thg + e);
+					load_theta_nb<D>(thg, P);
 					myver = ver;
 				}
 				if (occupied) {
-					int j = 0;
-					for (; j + 1 < cnt; j += 2) {
-						float x0[D], x1[D];
-						load_row<D>(xs + j * D, x0);
-						load_row<D>(xs + (j + 1) * D, x1);
-						const float l0 = log2density_regs<D>(P, x0);
-						const float l1 = log2density_regs<D>(P, x1);
+					// item pairs (a ragged last pair evaluates one row of padding; its tile entry is never read)
+					for (int j = 0; j < cnt; j += 2) {
+						float l0, l1;
+						log2density_pair<D>(P, reinterpret_cast<const f32x2_t *>(xs + j * D), l0, l1);
 						sm.tile[b][k * 33 + j] = l0;
 						sm.tile[b][k * 33 + j + 1] = l1;
-					}
-					if (j < cnt) {
-						float x0[D];
-						load_row<D>(xs + j * D, x0);
-						sm.tile[b][k * 33 + j] = log2density_regs<D>(P, x0);
 					}
 				}
 				sm.ver_tile[b][k] = occupied ? myver : -1;

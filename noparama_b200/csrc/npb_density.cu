@@ -8,6 +8,8 @@
 //   (src/clustering_performance.cpp:14-82, int64 instead of int: Q12) and the joint log-likelihood of
 //   MCMC::considerMaxLikelihood (src/np_mcmc.cpp:187-203), one CTA per chain.
 #include "npb_internal.h"
+#include <cstdio>
+#include <cstdlib>
 
 // T = double: everything in double.  T = float: the quadratic form in float, but the difference x - mu is formed
 // in double first (float coordinates would lose |x| * 6e-8, which is 1e-5 of a tight cluster's scale and breaks the
@@ -207,6 +209,31 @@ __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a
 	if (s == 123.456f) out[0] = s;
 }
 
+// the same probe with the packed form (sm_100a FFMA2: two FMAs per instruction on a 64-bit register pair)
+__global__ void __launch_bounds__(256) k_fma2_peak(float *out, int iters, float a, float b) {
+	unsigned long long r[8], aa, bb;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+	for (int u = 0; u < 8; ++u) {
+		const float lo = threadIdx.x + u, hi = lo + 0.5f;
+		asm("mov.b64 %0, {%1, %2};" : "=l"(r[u]) : "f"(lo), "f"(hi));
+	}
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int u = 0; u < 16; ++u) {
+#pragma unroll
+			for (int k = 0; k < 8; ++k) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[k]) : "l"(aa), "l"(bb));
+		}
+	}
+	float s = 0.0f;
+	for (int u = 0; u < 8; ++u) {
+		float lo, hi;
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r[u]));
+		s += lo + hi;
+	}
+	if (s == 123.456f) out[0] = s;
+}
+
 npb_status npb_launch_fma_peak(npb_ctx *ctx, double *tflops) {
 	float *d = nullptr;
 	NPB_CUDA_OK(cudaMalloc((void **)&d, sizeof(float)));
@@ -224,6 +251,20 @@ npb_status npb_launch_fma_peak(npb_ctx *ctx, double *tflops) {
 		cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
 		double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
 		double tf = fl / (ms * 1e-3) / 1e12;
+		if (rep >= 2 && tf > best) best = tf;
+	}
+	// the roofline denominator is the better of the scalar and the packed instruction stream
+	for (int rep = 0; rep < 12; ++rep) {
+		cudaEventRecord(ctx->ev0, ctx->stream);
+		k_fma2_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999f, 0.001f);
+		cudaEventRecord(ctx->ev1, ctx->stream);
+		cudaError_t e = cudaStreamSynchronize(ctx->stream);
+		if (e != cudaSuccess) { cudaFree(d); return npb_fail_cuda(ctx, e, "k_fma2_peak", __FILE__, __LINE__); }
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+		double fl = 2.0 * 2 * 8 * 16 * (double)iters * blocks * threads;
+		double tf = fl / (ms * 1e-3) / 1e12;
+		if (getenv("NPB_PEAK_VERBOSE") && rep == 11) fprintf(stderr, "npb_fp32_peak: FFMA %.2f TFLOP/s, FFMA2 %.2f TFLOP/s\n", best, tf);
 		if (rep >= 2 && tf > best) best = tf;
 	}
 	cudaFree(d);
