@@ -29,6 +29,8 @@ struct Tile4Smem {
 	                          // xs[(p * D + c) * 2 + h] = coordinate c of item 2p + h
 	int ver_tile[2][32];      // version of slot k the buffer's column was computed from, -1 = not computed
 	int ver_cur[32];          // current slot versions (bumped by a birth)
+	float auxkey[2][32];      // [buffer][step]: race key of the best of the step's M auxiliary draws
+	int auxm[2][32];          // [buffer][step]: which draw that was
 	unsigned occ;             // occupancy bit mask, maintained by the consumer
 	unsigned pad[3];
 };
@@ -116,6 +118,54 @@ __device__ __noinline__ float log2density_stream(const float *th, const float *x
 	return __ldcg(th + D + TRI) - q;
 }
 
+// The M auxiliary draws of step sj for one item (np_neal_algorithm8.cpp:79-84,119-126) and the race among them: returns
+// the best key and which draw it was.  A draw's density needs only the prior-whitened item: log2 N(x | theta') =
+// c0_2 - D log2|v| - |xw/|v| - z/sqrt(kappa)|^2 (npb_common.cuh).  The normals are consumed pair by pair in the order
+// aux_normals() produces them, so a birth can re-derive theta' from the same stream.
+template <int D, int M>
+__device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, const float *xw, uint32_t sj, uint32_t sweep, float ik2,
+		float &auxkey_j, int &auxm) {
+	auxkey_j = -INFINITY;
+	auxm = 0;
+	uint32_t as[4];
+	ph(sj, 1u, sweep, NPB_RNG_AUX, as);
+	float lkey[M];
+#pragma unroll
+	for (int m = 0; m < M; ++m) {
+		float g0, g1;
+		{
+			const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+			npb_normal2(r0, r1, g0, g1);
+		}
+		const float v = pr.v_mean + pr.nu * g0;
+		const float av = fmaxf(fabsf(v), 1e-20f);
+		const float inv = __frcp_rn(av);
+		float q;
+		{
+			const float y = __ldg(xw) * inv - g1 * ik2; // coordinate 0 pairs with normal 1
+			q = y * y;
+		}
+#pragma unroll
+		for (int p = 1; p < (D + 2) / 2; ++p) {
+			const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+			npb_normal2(r0, r1, g0, g1);
+			// normals 2p and 2p+1 belong to coordinates 2p-1 and 2p
+			const float ya = __ldg(xw + 2 * p - 1) * inv - g0 * ik2;
+			q = fmaf(ya, ya, q);
+			if (2 * p < D) {
+				const float yb = __ldg(xw + 2 * p) * inv - g1 * ik2;
+				q = fmaf(yb, yb, q);
+			}
+		}
+		lkey[m] = pr.c0_2 - (float)D * fast_lg2(av) - q + pr.log2_alpha_m;
+	}
+#pragma unroll
+	for (int m = 0; m < M; ++m) {
+		const float key = lkey[m] + neg_lg2_exp1(xoshiro_next(as));
+		if (key > auxkey_j) { auxkey_j = key; auxm = m; }
+	}
+}
+
 template <int D, int M>
 __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) {
 	constexpr int TRI = npb_tri(D), PS = npb_ps(D), PSP = npb_psp(D), KMAX = 32;
@@ -139,6 +189,8 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 		float P[PSP];
 		load_theta_nb<D>(thg, P);
 		int myver = 0;
+		const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+		const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
 		float *xs = sm.xs;
 		int t = 0;
 		// wait for the consumer's initial occupancy mask / versions
@@ -151,6 +203,13 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 				const int cnt = min(NPB_TILE, N - s0);
 				{
 					const int item = (lane < cnt) ? order[s0 + lane] : 0;
+					// the step's auxiliary draws (lane = step): the producer has the idle issue slots, the consumer's
+					// sequential race is the critical path of a chain
+					float ak;
+					int am;
+					aux_race<D, M>(ph, a.prior, a.Xw + (size_t)item * D, (uint32_t)(s0 + lane), a.sweep0 + (uint32_t)sw, ik2, ak, am);
+					sm.auxkey[b][lane] = ak;
+					sm.auxm[b][lane] = am;
 					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)item * D);
 					float *dst = xs + (lane >> 1) * (2 * D) + (lane & 1);
 #pragma unroll
@@ -192,6 +251,7 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 	float *thc = a.theta + (size_t)chain * KMAX * PS;
 	float n = (float)a.counts[(size_t)chain * KMAX + lane];
+	float lgn = n > 0.0f ? fast_lg2(n) : -INFINITY, lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
 	int kocc = __popc(__ballot_sync(0xffffffffu, n > 0.0f));
 	sm.ver_cur[lane] = 0;
 	sm.ver_tile[0][lane] = -1;
@@ -226,56 +286,13 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 			const int item = valid ? order[sj] : 0;
 			const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
 			int znew = zold;
-			// ---- auxiliary draws of step sj (np_neal_algorithm8.cpp:79-84,119-126) and their race keys; the normals are
-			// consumed pair by pair in the order aux_normals() produces them (no per-draw arrays: 56 registers) ----
-			float auxkey_j = -INFINITY;
-			int auxm = 0;
-			{
-				const float *xw = a.Xw + (size_t)item * D;
-				uint32_t as[4];
-				ph((uint32_t)sj, 1u, sweep, NPB_RNG_AUX, as);
-				float lkey[M];
-#pragma unroll
-				for (int m = 0; m < M; ++m) {
-					float g0, g1;
-					{
-						const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-						npb_normal2(r0, r1, g0, g1);
-					}
-					const float v = a.prior.v_mean + a.prior.nu * g0;
-					const float av = fmaxf(fabsf(v), 1e-20f);
-					const float inv = __frcp_rn(av);
-					float q;
-					{
-						const float y = __ldg(xw) * inv - g1 * ik2; // coordinate 0 pairs with normal 1
-						q = y * y;
-					}
-#pragma unroll
-					for (int p = 1; p < (D + 2) / 2; ++p) {
-						const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-						npb_normal2(r0, r1, g0, g1);
-						// normals 2p and 2p+1 belong to coordinates 2p-1 and 2p
-						const float ya = __ldg(xw + 2 * p - 1) * inv - g0 * ik2;
-						q = fmaf(ya, ya, q);
-						if (2 * p < D) {
-							const float yb = __ldg(xw + 2 * p) * inv - g1 * ik2;
-							q = fmaf(yb, yb, q);
-						}
-					}
-					lkey[m] = a.prior.c0_2 - (float)D * fast_lg2(av) - q + a.prior.log2_alpha_m;
-				}
-#pragma unroll
-				for (int m = 0; m < M; ++m) {
-					const float key = lkey[m] + neg_lg2_exp1(xoshiro_next(as));
-					if (key > auxkey_j) { auxkey_j = key; auxm = m; }
-				}
-			}
-			const int zold_aux_j = zold | (auxm << 16);
 			uint32_t rs[4];
 			ph((uint32_t)sj, 0u, sweep, NPB_RNG_PICK, rs);
 			const int cnt = min(NPB_TILE, N - s0);
 
 			named_bar_sync(bar0 + b, 64); // the producer has filled buffer b
+			const float auxkey_j = sm.auxkey[b][lane];
+			const int zold_aux_j = zold | (sm.auxm[b][lane] << 16);
 			{
 				unsigned stale = __ballot_sync(0xffffffffu, n > 0.0f && sm.ver_tile[b][lane] != sm.ver_cur[lane]);
 				while (stale) {
@@ -286,13 +303,28 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 			}
 			unsigned cand_tile = 0u;
 
+			// The step loop is the critical path of a chain, so everything that does not depend on the previous step is
+			// taken off its dependent chain: the tile entry, the race noise and the broadcasts of step j+1 are fetched
+			// while step j is decided, and log2 of the member counts (n and n - 1) is kept in registers and refreshed
+			// only when a count changes.
+			float noise_next = neg_lg2_exp1(xoshiro_next(rs));
+			float base_next = sm.tile[b][lane * 33] + noise_next;
+			int zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, 0);
+			float ak_next = __shfl_sync(0xffffffffu, auxkey_j, 0);
 			for (int j = 0; j < cnt; ++j) {
-				const int zo_aux = __shfl_sync(0xffffffffu, zold_aux_j, j);
-				const float ak = __shfl_sync(0xffffffffu, auxkey_j, j);
+				const int zo_aux = zo_aux_next;
+				const float ak = ak_next;
+				const float base = base_next;
 				const int zo = zo_aux & 0xffff;
-				const float base = sm.tile[b][lane * 33 + j] + neg_lg2_exp1(xoshiro_next(rs));
-				const float ne = (zo == lane) ? n - 1.0f : n;
-				const float key = ne > 0.0f ? base + fast_lg2(ne) : -INFINITY;
+				{
+					const int jn = min(j + 1, NPB_TILE - 1);
+					noise_next = neg_lg2_exp1(xoshiro_next(rs));
+					base_next = sm.tile[b][lane * 33 + jn] + noise_next;
+					zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, jn);
+					ak_next = __shfl_sync(0xffffffffu, auxkey_j, jn);
+				}
+				const float lg = (zo == lane) ? lgn1 : lgn;
+				const float key = lg > -INFINITY ? base + lg : -INFINITY; // a slot without (other) members never wins
 				const int my_enc = float_order_key(key);
 				const int top = max(__reduce_max_sync(0xffffffffu, my_enc), float_order_key(ak));
 				const unsigned bal = __ballot_sync(0xffffffffu, my_enc == top && key > -INFINITY);
@@ -361,9 +393,13 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 							kocc++;
 							st_births++;
 							fix_column(fs, b, j + 1, item, valid);
+							// the prefetched entry of step j+1 was read before the newborn slot's column existed
+							if (lane == fs) base_next = sm.tile[b][fs * 33 + min(j + 1, NPB_TILE - 1)] + noise_next;
 						}
 					}
 					if (new_slot == lane) n += 1.0f;
+					lgn = n > 0.0f ? fast_lg2(n) : -INFINITY;
+					lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
 					st_moved++;
 					if (lane == j) znew = new_slot;
 				}
