@@ -1,24 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- item-reassignments/sec of the Gibbs reassignment path (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[1] -- 1024 lockstep Algorithm-8 chains per GPU over one synthetic
-10-component 2-D GMM with N = 100 000 items (noparama_b200/synthetic.py, seed 20261002), reference prior
-(np_main.cpp:164,367-371), m = 3 auxiliary draws, K0 = 20.  A "step" is one sweep: every chain reassigns every
-item once (np_mcmc.cpp:146-163) = chains * N item-reassignments, one kernel launch per GPU.
+Headline workload (config.workload): the per-GPU shard of BASELINE.json configs[4] -- the "16-D N=100k config" the
+metric and its target are quoted on: 8192 lockstep Algorithm-8 chains per GPU (65536 over 8 GPUs) over one synthetic
+32-component 16-D GMM with N = 100 000 items (noparama_b200/synthetic.py, seed 20261003), reference NIW prior
+generalised to 16-D (np_main.cpp:164,367-371), m = 3 auxiliary draws, Kmax = 32.  Regime (SURVEY 8d honesty rule): under
+the reference's bug-compatible prior a 16-D run collapses to one cluster and a reassignment becomes trivially cheap, so
+the chains start from K0 = K_true = 32 given clusters (class means, identity covariance) and every reassignment weighs
+32 occupied clusters + 3 auxiliary draws; cluster parameters stay frozen between births exactly as in the reference (Q1).
+A "step" is one sweep: every chain reassigns every item once (np_mcmc.cpp:146-163) = chains * N item-reassignments, one
+sweep-kernel launch per GPU.  `--config cfg2` measures BASELINE configs[1] (1024 chains, 2-D, reference prior and
+initialisation) instead; the default run also reports it, and the split-merge samplers at configs[2]'s shape, under "also".
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
-  python bench.py --impl reference [--gpus N] ...              the reference algorithm on the host cores (CPU oracle)
+  python bench.py --impl reference [--gpus N] ...              the reference's own CPU sampler on the host cores
 
-Under torchrun every rank owns one GPU and 1024 chains of its own (chains are independent: weak scaling, no
-collective on the data path); timing is barrier + synchronize on both sides, CUDA events on the library's stream,
-max over ranks.  After the timed region the ranks all-reduce (NCCL) the posterior co-clustering matrix of an anchor
-subset and the per-chain diagnostics, the only exchange the path has.
+Under torchrun every rank owns one GPU and its own chains (chains are independent: weak scaling, no collective on the
+data path); timing is barrier + synchronize on both sides, CUDA events on the library's stream, max over ranks.  After
+the timed region the ranks all-reduce (NCCL) the posterior co-clustering matrix of an anchor subset and the per-chain
+diagnostics, the only exchange the path has.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,19 +34,33 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-N_ITEMS, DIM, K_TRUE = 100_000, 2, 10
-CHAINS_PER_GPU = 1024
-KMAX, M_AUX, K0 = 256, 3, 20
+M_AUX, K0_REF = 3, 20
 SEED = 20261018
 METRIC = "item-reassignments/sec"
 UNIT = "reassignments/s"
-WORKLOAD = ("BASELINE configs[1]: %d lockstep Algorithm-8 chains per GPU, synthetic %d-component %d-D GMM, N=%d, "
-            "m=%d aux, K0=%d, reference NIW prior (bug-compatible)" % (CHAINS_PER_GPU, K_TRUE, DIM, N_ITEMS, M_AUX, K0))
+
+CONFIGS = {
+    # per-GPU shard of BASELINE configs[4] (also the data of configs[2]): the headline
+    "cfg5": dict(synthetic=5, N=100_000, D=16, K_true=32, chains=8192, kmax=32, given=True,
+                 workload="BASELINE configs[4] per-GPU shard (the 16-D N=100k config): 8192 lockstep Algorithm-8 chains per "
+                          "GPU (65536 over 8), synthetic 32-component 16-D GMM, N=100000, m=3 aux, Kmax=32, reference NIW "
+                          "prior generalised to 16-D; chains start from K0=K_true=32 given clusters (class means, identity "
+                          "covariance), parameters frozen between births as in the reference"),
+    # BASELINE configs[1]
+    "cfg2": dict(synthetic=2, N=100_000, D=2, K_true=10, chains=1024, kmax=256, given=False,
+                 workload="BASELINE configs[1]: 1024 lockstep Algorithm-8 chains per GPU, synthetic 10-component 2-D GMM, "
+                          "N=100000, m=3 aux, K0=20, reference NIW prior and initialisation (bug-compatible)"),
+}
 
 
 def f_eval(D):
     """algorithmic flops of one density evaluation, SURVEY 8d: D^2 + 4D + 3"""
     return D * D + 4 * D + 3
+
+
+def given_clusters(X, y):
+    K = int(y.max()) + 1
+    return np.stack([X[y == k].mean(0) for k in range(K)]), np.tile(np.eye(X.shape[1]), (K, 1, 1))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -101,84 +122,208 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def oracle_chain_worker(args):
-    """one independent reference chain on one host core (the reference is single threaded)"""
-    seed, sweeps, faithful, n_items = args
+# CPU side: the reference's own sampler (oracle/_ref/np_ref_run = its unmodified sources built against oracle/eigen_shim)
+# when that binary travelled with the snapshot, else the oracle port.  One independent chain per host core (the
+# reference is single threaded), on a bounded prefix of the workload's (already shuffled) items.
+# ---------------------------------------------------------------------------------------------------------------
+def ref_chains(cfg, cores, sweeps, n_items):
+    """`cores` concurrent runs of the reference binary -> list of per-sweep update()-loop seconds, K_final, seconds_run"""
+    from oracle import refrun
+    from noparama_b200 import synthetic as syn
+    X, _ = syn.config(cfg["synthetic"])
+    X = X[:n_items]
+    pr = syn.reference_prior(cfg["D"])
+    with tempfile.TemporaryDirectory() as d:
+        req = os.path.join(d, "req.bin")
+        refrun.write_request(req, X, pr)
+        procs = []
+        for c in range(cores):
+            res = os.path.join(d, "res%d.bin" % c)
+            procs.append((res, subprocess.Popen(refrun.command(8, sweeps, 1000 + c, 2000 + c, req, res),
+                                                stdout=subprocess.DEVNULL)))
+        out = []
+        for res, p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("np_ref_run failed")
+            r = refrun.read_result(res)
+            out.append((r["sweep_update_seconds"], r["K_final"], r["seconds_run"]))
+    return out
+
+
+def port_chain_worker(args):
+    cfgname, seed, sweeps, n_items, given = args
     from oracle import binding as orc
     from noparama_b200 import synthetic as syn
-    X, _ = syn.config(2)
+    cfg = CONFIGS[cfgname]
+    X, y = syn.config(cfg["synthetic"])
+    g = given_clusters(X, y) if given else None
     X = X[:n_items]
-    pr = orc.make_prior(**syn.reference_prior(DIM))
-    flags = orc.FAITHFUL if faithful else 0
-    r = orc.Run(pr, X, T=sweeps, K0=K0, M_aux=M_AUX, seed_main=1000 + seed, seed_shuffle=2000 + seed, flags=flags)
+    pr = orc.make_prior(**syn.reference_prior(cfg["D"]))
+    r = orc.Run(pr, X, T=sweeps, K0=K0_REF, M_aux=M_AUX, seed_main=1000 + seed, seed_shuffle=2000 + seed, flags=orc.FAITHFUL,
+                given=g)
     re, tot = r.sweep_seconds()
     s = r.stats()
-    return re.tolist(), tot.tolist(), s.candidates / max(1, s.updates), s.mean_K
+    return re.tolist(), tot.tolist(), s.candidates / max(1, s.updates), s.K_final
 
 
-def run_oracle(cores, sweeps, faithful=True, n_items=N_ITEMS):
+def port_chains(cfgname, cores, sweeps, n_items, given):
     import multiprocessing as mp
     with mp.get_context("spawn").Pool(cores) as pool:
-        return pool.map(oracle_chain_worker, [(c, sweeps, faithful, n_items) for c in range(cores)])
+        return pool.map(port_chain_worker, [(cfgname, c, sweeps, n_items, given) for c in range(cores)])
 
 
-def cpu_baseline_sample(cores):
-    """bounded sample of the same workload: `cores` independent chains, 1 warm-up + 2 timed sweeps each
-    (the first sweep starts from the random initial assignment and is not representative)"""
-    res = run_oracle(cores, 3, True)
-    t_reassign = max(sum(r[0][1:]) for r in res)
-    t_total = max(sum(r[1][1:]) for r in res)
-    n = cores * N_ITEMS * 2
-    return {"value": n / t_reassign, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d independent chains (one per host core), sweeps 2-3 of the same N=%d config, update() loop only "
-                      "(np_mcmc.cpp:146-163) with the reference cost profile (per-call LU inverse+determinant, density "
-                      "evaluated twice, dense bool matrix)" % (cores, N_ITEMS),
-            "full_sweep_value": n / t_total, "single_core_value": N_ITEMS * 2 / max(sum(r[0][1:]) for r in res[:1]),
-            "candidates_per_reassignment": float(np.mean([r[2] for r in res]))}
+def cpu_sample_items(cfg):
+    # about 10-30 s of CPU work per core: the reference spends ~0.3 ms (16-D, collapsed) .. 20 us (2-D) per reassignment
+    return 4000 if cfg["D"] >= 8 else 100_000
+
+
+def cpu_baseline_sample(cfgname, cores):
+    """bounded sample of the same workload on the host cores: 1 warm-up + 2 timed sweeps per chain"""
+    from oracle import refrun
+    cfg = CONFIGS[cfgname]
+    n_items = cpu_sample_items(cfg)
+    out = {"unit": UNIT, "cores": cores}
+    if refrun.available():
+        res = ref_chains(cfg, cores, 3, n_items)
+        t = max(float(np.sum(r[0][1:])) for r in res)
+        out.update(value=cores * n_items * 2 / t, kind="reference",
+                   sample="%d independent chains (one per host core) of the reference's own sampler (oracle/_ref: its unmodified "
+                          "sources built against the Eigen stand-in), sweeps 2-3 over the first %d items of the workload, "
+                          "update() loop only (np_mcmc.cpp:146-163); reference initialisation (K0=20 prior draws): final "
+                          "K = %.1f clusters" % (cores, n_items, float(np.mean([r[1] for r in res]))),
+                   single_core_value=n_items * 2 / float(np.sum(res[0][0][1:])))
+    # the oracle port with the reference cost profile, in the very regime the GPU number is taken in
+    n_port = 1000 if cfg["given"] else n_items
+    pres = port_chains(cfgname, cores, 3, n_port, cfg["given"])
+    tp = max(sum(r[0][1:]) for r in pres)
+    port = {"value": cores * n_port * 2 / tp, "full_sweep_value": cores * n_port * 2 / max(sum(r[1][1:]) for r in pres),
+            "candidates_per_reassignment": float(np.mean([r[2] for r in pres])), "items": n_port,
+            "regime": "same as the GPU run (%s)" % ("K0=K_true given clusters" if cfg["given"] else "reference initialisation")}
+    if "value" not in out:
+        out.update(value=port["value"], kind="port", sample="%d chains x sweeps 2-3 x %d items, oracle port, update() loop only"
+                   % (cores, n_port))
+    out["port_same_regime"] = port
+    return out
 
 
 def reference_arm(args, rank, world):
-    """--impl reference: the reference algorithm (CPU oracle port; the reference itself needs Eigen, which this image
-    lacks) on all host cores, one independent chain per core, same config / metric / unit."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, one independent chain per
+    core, same config / metric / unit; a step = one sweep of every chain over a bounded prefix of the items."""
     if rank != 0:
         return
+    from oracle import refrun
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     sweeps = args.warmup + args.steps
-    # bounded sample: a faithful sweep of N = 100k costs ~3 s per chain; keep the whole run within a few minutes by
-    # sweeping a prefix of the (shuffled) items when many steps are asked for
-    n_items = N_ITEMS if sweeps <= 40 else max(2000, N_ITEMS * 40 // sweeps)
+    n_items = cpu_sample_items(cfg)
+    if sweeps > 12:  # keep the whole run within a few minutes
+        n_items = max(500, n_items * 12 // sweeps)
     t0 = time.time()
-    res = run_oracle(cores, sweeps, True, n_items)
+    if refrun.available():
+        res = ref_chains(cfg, cores, sweeps, n_items)
+        t = max(float(np.sum(r[0][args.warmup:])) for r in res)
+        kind, how = "reference", "oracle/_ref/np_ref_run (the reference's unmodified sampler sources built against oracle/eigen_shim)"
+        extra = {"K_final_mean": float(np.mean([r[1] for r in res]))}
+    else:
+        res = port_chains(args.config, cores, sweeps, n_items, False)
+        t = max(sum(r[0][args.warmup:]) for r in res)
+        kind, how = "port", "oracle port (oracle/_ref was not built)"
+        extra = {"candidates_per_reassignment": float(np.mean([r[2] for r in res]))}
     wall = time.time() - t0
-    t = max(sum(r[0][args.warmup:]) for r in res)
-    t_full = max(sum(r[1][args.warmup:]) for r in res)
     n = cores * n_items * args.steps
     val = n / t
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "chains": cores, "items_per_sweep": n_items,
-                       "note": "one reference chain per host core; a step = one sweep of every chain over "
-                               "items_per_sweep items of the config (a prefix when W+K > 40)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d chains x %d sweeps x N=%d, update() loop only" % (cores, args.steps, n_items),
-                             "full_sweep_value": n / t_full},
+            "config": dict({"workload": cfg["workload"], "chains": cores, "items_per_sweep": n_items, "how": how,
+                            "note": "one reference chain per host core with the reference's own initialisation (K0=20 prior "
+                                    "draws); a step = one sweep of every chain over items_per_sweep items, update() loop only"},
+                           **extra),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d chains x %d sweeps x %d items" % (cores, args.steps, n_items)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def build_chains(npb, syn, ctx, cfg, chains, kmax, seed):
+    X, y = syn.config(cfg["synthetic"])
+    ds = npb.Dataset(ctx, X)
+    prior = npb.NormalInverseWishart(**syn.reference_prior(cfg["D"]))
+    mc = npb.MCMC(ctx, ds, prior, chains=chains, Kmax=kmax, K0=K0_REF, m_aux=M_AUX, seed=seed)
+    if cfg["given"]:
+        mc.chains.init_from_params(*given_clusters(X, y))
+    return X, y, ds, mc
+
+
+def timed_sweeps(npb, chains, steps):
+    ms, cand, moved, births, last = [], 0, 0, 0, None
+    for _ in range(steps):
+        st = chains.sweep(npb.ALG8, 1)
+        ms.append(st.kernel_ms)
+        cand += st.candidates
+        moved += st.moved
+        births += st.new_clusters
+        last = st
+    return ms, cand, moved, births, last
+
+
+def also_measure(npb, syn, ctx, fp32_peak, rank):
+    """secondary figures of the default run: BASELINE configs[1] (2-D) and the split-merge samplers at configs[2]'s shape"""
+    out = {}
+    cfg = CONFIGS["cfg2"]
+    X, y, ds, mc = build_chains(npb, syn, ctx, cfg, cfg["chains"], cfg["kmax"], SEED + 17 * rank)
+    for _ in range(5):
+        mc.chains.sweep(npb.ALG8, 1, want_stats=False)
+    ms, cand, moved, births, last = timed_sweeps(npb, mc.chains, 10)
+    k_ms = float(np.mean(ms))
+    n_step = cfg["chains"] * ds.N
+    fl = (cand / 10) * (f_eval(cfg["D"]) + 6)
+    out["cfg2"] = {"workload": cfg["workload"], "value": n_step / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": 10,
+                   "warmup": 5, "mean_K": last.mean_K, "candidates_per_reassignment": cand / (n_step * 10),
+                   "moved_fraction": moved / (n_step * 10),
+                   "roofline": {"bound": "fp32", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                "frac": fl / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                                "kernel": "k_alg8_sweep_reg<2,8>"}}
+    mc.chains.close()
+    ds.close()
+    # split-merge proposals (BASELINE configs[2] shape: 16-D, N = 100k, 4096 chains; SURVEY 8d: proposals/s and
+    # SAMS item-allocations/s)
+    cfg = CONFIGS["cfg5"]
+    X, y = syn.config(3)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(cfg["D"])).bind(ctx)
+    ch = npb.Chains(ctx, ds, 4096, Kmax=64, K0=K0_REF, seed=SEED + 31 * rank)
+    ch.init_from_params(*given_clusters(X, y))
+    ch.sweep(npb.ALG8, 1, want_stats=False)
+    sm = {}
+    for name, sampler in (("jain_neal", npb.JAIN_NEAL), ("triadic", npb.TRIADIC)):
+        ch.split_merge(sampler, 8)
+        st = ch.split_merge(sampler, 16)
+        sec = st.kernel_ms * 1e-3
+        sm[name] = {"proposals_per_s": st.reassignments / sec, "sams_allocations_per_s": st.sams_allocations / sec,
+                    "kernel_ms": st.kernel_ms, "proposals": int(st.reassignments), "attempts": list(st.sm_attempts),
+                    "accepts": list(st.sm_accepts)}
+    out["split_merge"] = dict(sm, workload="BASELINE configs[2] shape: 4096 chains, 16-D 32-component GMM, N=100000, K=32 given "
+                                           "clusters; 16 lockstep proposals per chain (np_mcmc.cpp:146-163)")
+    ch.close()
+    ds.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="npb200", choices=["npb200", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
-    ap.add_argument("--kmax", type=int, default=KMAX)
+    ap.add_argument("--config", default="cfg5", choices=sorted(CONFIGS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the config's)")
+    ap.add_argument("--kmax", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,21 +333,23 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    cfg = CONFIGS[args.config]
+    n_chains = args.chains or cfg["chains"]
+    kmax = args.kmax or cfg["kmax"]
+    DIM = cfg["D"]
 
     import torch
     import torch.distributed as dist
     import noparama_b200 as npb
     from noparama_b200 import synthetic as syn
+    from noparama_b200 import diagnostics as dg
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    X, y = syn.config(2)
     ctx = npb.Context(local_rank)
-    ds = npb.Dataset(ctx, X)
-    prior = npb.NormalInverseWishart(**syn.reference_prior(DIM))
-    mc = npb.MCMC(ctx, ds, prior, chains=args.chains, Kmax=args.kmax, K0=K0, m_aux=M_AUX, seed=__import__('noparama_b200').diagnostics.rank_seed(SEED, rank))
+    X, y, ds, mc = build_chains(npb, syn, ctx, cfg, n_chains, kmax, dg.rank_seed(SEED, rank))
     chains = mc.chains
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
@@ -212,7 +359,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    # ---- warm-up (also burns the chains in past the random initial assignment) ----
+    # ---- warm-up (also moves the items from the random initial assignment to their clusters) ----
     for _ in range(args.warmup):
         chains.sweep(npb.ALG8, 1, want_stats=False)
     # ---- timed region: exactly K sweeps, inputs resident in HBM ----
@@ -220,23 +367,17 @@ def main():
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, cand, moved, births = [], 0, 0, 0
     ev0.record(stream)
-    for _ in range(args.steps):
-        st = chains.sweep(npb.ALG8, 1)
-        kernel_ms.append(st.kernel_ms)
-        cand += st.candidates
-        moved += st.moved
-        births += st.new_clusters
+    kernel_ms, cand, moved, births, last = timed_sweeps(npb, chains, args.steps)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
-    last = st
 
-    # ---- end to end through the public call with host buffers (H2D of X, D2H of every assignment) ----
-    Xh = np.ascontiguousarray(X)
-    z_host = np.empty((ds.N, args.chains), dtype=np.uint16)
+    # ---- end to end through the public call with host buffers: every step uploads X from pinned host memory and
+    # reads the assignments of all chains back into page-locked host memory ----
+    Xh = torch.from_numpy(np.ascontiguousarray(X)).pin_memory().numpy()
+    z_host = torch.empty((ds.N, n_chains), dtype=torch.uint16, pin_memory=True).numpy()
     chains.sweep_host(Xh, npb.ALG8, 1, z_out=z_host)  # warm the staging buffers
     barrier()
     t0 = time.perf_counter()
@@ -248,9 +389,8 @@ def main():
 
     # ---- diagnostics exchange (outside the timed region): a short traced phase for R-hat, then one all-reduce of
     # the co-clustering counts, the score sums and the R-hat partials over all ranks (NCCL when world > 1) ----
-    from noparama_b200 import diagnostics as dg
     k_trace, jll_trace = [], []
-    for _ in range(8):
+    for _ in range(4):
         chains.sweep(npb.ALG8, 1, want_stats=False)
         mm = chains.metrics(None)
         k_trace.append(mm["K"].astype(np.float64))
@@ -266,37 +406,43 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_s = t.tolist()
+    n_items = ds.N
+    chains.close()
+    ds.close()
 
     if rank == 0:
-        n_step = args.chains * ds.N  # reassignments per step per GPU
+        n_step = n_chains * n_items  # reassignments per step per GPU
         total = world * n_step * args.steps
         value = total / (elapsed_ms * 1e-3)
         e2e_value = world * n_step * args.e2e_steps / e2e_s
-        # roofline of the dominant (only) kernel, per launch, from this rank's counters and CUDA-event times
+        # roofline of the dominant (only) kernel of a step, per launch, from this rank's counters and CUDA-event times
         flops_per_launch = (cand / args.steps) * (f_eval(DIM) + 6)
         k_ms = float(np.mean(kernel_ms))
         fp32_peak = mc_fp32_peak(ctx)
         hbm_peak, hbm_src = measured_peaks()
-        bytes_per_launch = n_step * (2 * 2 + 4 * DIM / 32.0)  # z read+write (u16) + x shared by the 32 lanes' prefetch
+        bytes_per_launch = n_step * (2 * 2 + 4 * DIM / 32.0)  # z read+write (u16) + x shared by a 32-step tile
+        kernel = "k_alg8_sweep_tile4<%d,3>" % DIM if (DIM >= 4 and kmax == 32) else ("k_alg8_sweep_tile" if DIM >= 4 else "k_alg8_sweep_reg")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "chains_per_gpu": args.chains, "N": ds.N, "D": DIM, "Kmax": args.kmax,
-                       "l2": "per-GPU assignment state %d MB + slot tables exceed the 126 MB L2; no flush needed"
-                             % (ds.N * args.chains * 2 // 2 ** 20),
+            "config": {"workload": cfg["workload"], "chains_per_gpu": n_chains, "N": n_items, "D": DIM, "Kmax": kmax,
+                       "l2": "per-GPU assignment state %d MB (+ %d MB of slot tables) exceeds the 126 MB L2; no flush needed"
+                             % (n_items * n_chains * 2 // 2 ** 20, n_chains * kmax * (DIM + DIM * (DIM + 1) // 2 + 1) * 4 // 2 ** 20),
                        "mean_K": last.mean_K, "max_K": last.max_K, "candidates_per_reassignment": cand / (n_step * args.steps),
                        "moved_fraction": moved / (n_step * args.steps), "new_clusters_per_step": births / args.steps},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ds.N * DIM * 8),
-                    "d2h_bytes_per_step": int(ds.N * args.chains * 2), "steps": args.e2e_steps,
-                    "call": "npb_chains_sweep_host (pinned staging; X up, all assignments down)"},
-            "gpu_launches": args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_items * DIM * 8),
+                    "d2h_bytes_per_step": int(n_items * n_chains * 2), "steps": args.e2e_steps,
+                    "call": "npb_chains_sweep_host (X up from pinned host memory, every chain's assignments down into "
+                            "page-locked host memory)"},
+            "gpu_launches": args.steps * 2,  # per step: k_scan_order + the sweep kernel
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": flops_per_launch / (k_ms * 1e-3) / 1e12, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": flops_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
-                         "traffic": None, "kernel": "k_alg8_sweep", "kernel_ms": k_ms,
-                         "peak_source": "FP32 FFMA peak measured in this run by npb_fp32_peak (MEASURED_PEAKS.json has no "
-                                        "FP32 figure); algorithmic flops = sum(K_i+m) * (D^2+4D+3+6), counter kept by the kernel"},
+                         "traffic": None, "kernel": kernel, "kernel_ms": k_ms,
+                         "peak_source": "FP32 FMA peak measured in this run by npb_fp32_peak (better of the scalar FFMA and the "
+                                        "packed FFMA2 instruction streams; MEASURED_PEAKS.json has no FP32 figure); algorithmic "
+                                        "flops = sum(K_i+m) * (D^2+4D+3+6), counter kept by the kernel"},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                              "peak_source": hbm_src},
@@ -305,9 +451,14 @@ def main():
                             "cocluster_anchor_diag_mean": float(S.diag().mean().item()),
                             "allreduce": "nccl" if world > 1 else "none (1 rank)"},
         }
+        if world == 1 and not args.no_also and args.config == "cfg5":
+            try:
+                line["also"] = also_measure(npb, syn, ctx, fp32_peak, rank)
+            except Exception as e:
+                line["also"] = {"failed": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             try:
-                line["cpu_baseline"] = cpu_baseline_sample(os.cpu_count() or 1)
+                line["cpu_baseline"] = cpu_baseline_sample(args.config, os.cpu_count() or 1)
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
@@ -316,7 +467,7 @@ def main():
 
 
 def mc_fp32_peak(ctx):
-    """FP32 FFMA peak of this GPU, TFLOP/s (register-resident FMA loop, best of 10, CUDA events)"""
+    """FP32 FMA peak of this GPU, TFLOP/s (register-resident FMA loops, scalar and packed, best of 10, CUDA events)"""
     import ctypes as C
     lib = ctx._lib
     if not hasattr(lib, "npb_fp32_peak"):

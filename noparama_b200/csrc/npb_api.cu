@@ -487,13 +487,19 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_
 		if (s != NPB_OK) return s;
 	}
 	NPB_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+	bool z_direct = false;
 	if (z_out) {
 		const size_t bytes = (size_t)ch->ds->N * ch->C * sizeof(npb_z_t);
-		if (!ch->h_z) NPB_CUDA_OK(cudaMallocHost((void **)&ch->h_z, bytes));
-		NPB_CUDA_OK(cudaMemcpyAsync(ch->h_z, ch->z, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		// a caller buffer that is already page-locked takes the DMA directly; pageable memory goes through the
+		// handle's own pinned staging buffer
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, z_out) == cudaSuccess && attr.type == cudaMemoryTypeHost) z_direct = true;
+		else cudaGetLastError();
+		if (!z_direct && !ch->h_z) NPB_CUDA_OK(cudaMallocHost((void **)&ch->h_z, bytes));
+		NPB_CUDA_OK(cudaMemcpyAsync(z_direct ? (void *)z_out : (void *)ch->h_z, ch->z, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-	if (z_out) memcpy(z_out, ch->h_z, (size_t)ch->ds->N * ch->C * sizeof(npb_z_t));
+	if (z_out && !z_direct) memcpy(z_out, ch->h_z, (size_t)ch->ds->N * ch->C * sizeof(npb_z_t));
 	float ms = 0.0f;
 	NPB_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	if (stats) {

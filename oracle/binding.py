@@ -72,6 +72,9 @@ def lib():
         L.npo_membertrix_selftest.argtypes = [C.c_uint32, C.c_int]
         L.npo_mcmc_run.restype = C.c_void_p
         L.npo_mcmc_run.argtypes = [C.POINTER(Prior), C.POINTER(Options), C.POINTER(C.c_double), C.c_int]
+        L.npo_mcmc_run_given.restype = C.c_void_p
+        L.npo_mcmc_run_given.argtypes = [C.POINTER(Prior), C.POINTER(Options), C.POINTER(C.c_double), C.c_int, C.c_int,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.npo_run_free.argtypes = [C.c_void_p]
         L.npo_run_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.npo_run_assignments.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -182,13 +185,17 @@ class Run:
     """One oracle run of MCMC::run (np_mcmc.cpp:48-175)."""
 
     def __init__(self, prior, X, algorithm=ALG8, T=1000, K0=20, M_aux=3, mh_steps=20, seed_main=1, seed_shuffle=2,
-                 flags=FAITHFUL):
+                 flags=FAITHFUL, given=None):
         X = _f64(X)
         self.N, self.D = X.shape
         self.M_aux = M_aux
         self.T = T
         opt = Options(algorithm, T, K0, M_aux, mh_steps, seed_main, seed_shuffle, flags)
-        self._h = lib().npo_mcmc_run(C.byref(prior), C.byref(opt), _dp(X), self.N)
+        if given is None:
+            self._h = lib().npo_mcmc_run(C.byref(prior), C.byref(opt), _dp(X), self.N)
+        else:  # NOT the reference: start from caller-supplied clusters (mu [K,D], Sigma [K,D,D])
+            mu, Sigma = _f64(given[0]), _f64(given[1])
+            self._h = lib().npo_mcmc_run_given(C.byref(prior), C.byref(opt), _dp(X), self.N, mu.shape[0], _dp(mu), _dp(Sigma))
 
     def __del__(self):
         if getattr(self, "_h", None):

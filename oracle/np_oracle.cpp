@@ -538,6 +538,8 @@ struct npo_run {
 	std::vector<double> tr_aux_mu, tr_aux_sigma, tr_u;
 	std::vector<double> sweep_reassign_seconds, sweep_total_seconds;
 	std::vector<int> K_after_call; /* cluster count after every sampler.update() (RECORD_TRACE) */
+	/* NOT the reference: initial clusters given by the caller instead of drawn from the prior (bench regime) */
+	std::vector<double> given_mu, given_sigma;
 	/* slot allocator */
 	std::vector<char> slot_used;
 	int alloc_slot() {
@@ -731,7 +733,14 @@ struct Sampler {
 		auto t_start = std::chrono::steady_clock::now();
 		for (int i = 0; i < N; ++i) trix.addData(); /* :58-63 */
 		for (int k = 0; k < K0; ++k) {              /* :66, np_init_clusters.cpp:24-41 */
-			Theta *th = sample_base(prior, proc, proc.gen_init);
+			Theta *th;
+			if (!run.given_mu.empty()) { /* caller-supplied parameters (npo_mcmc_run_given) */
+				th = new Theta();
+				th->mu.assign(run.given_mu.begin() + (size_t)k * D, run.given_mu.begin() + (size_t)(k + 1) * D);
+				th->sigma.assign(run.given_sigma.begin() + (size_t)k * D * D, run.given_sigma.begin() + (size_t)(k + 1) * D * D);
+			} else {
+				th = sample_base(prior, proc, proc.gen_init);
+			}
 			trix.addCluster(new Cluster{th, -1});
 		}
 		std::vector<double> weights(K0, 1 / (double)K0); /* :69-73 */
@@ -945,6 +954,25 @@ npo_run *npo_mcmc_run(const npo_prior *prior, const npo_options *opt, const doub
 	r->D = prior->D;
 	r->X.assign(X, X + (size_t)N * prior->D);
 	std::memset(&r->stats, 0, sizeof(r->stats));
+	r->stats.max_loglik = -std::numeric_limits<double>::infinity();
+	Sampler s(*r);
+	s.mcmc_run();
+	return r;
+}
+/* NOT the reference: the same run started from K0 = K caller-supplied clusters (mu [K,D], Sigma [K,D,D]) instead of K0
+ * prior draws -- the regime bench.py measures at D = 16, where the reference's own prior collapses to one cluster */
+npo_run *npo_mcmc_run_given(const npo_prior *prior, const npo_options *opt, const double *X, int N, int K, const double *mu,
+		const double *Sigma) {
+	npo_run *r = new npo_run();
+	r->prior = make_prior(prior);
+	r->opt = *opt;
+	r->opt.K0 = K;
+	r->N = N;
+	r->D = prior->D;
+	r->X.assign(X, X + (size_t)N * prior->D);
+	r->given_mu.assign(mu, mu + (size_t)K * prior->D);
+	r->given_sigma.assign(Sigma, Sigma + (size_t)K * prior->D * prior->D);
+	memset(&r->stats, 0, sizeof(r->stats));
 	r->stats.max_loglik = -std::numeric_limits<double>::infinity();
 	Sampler s(*r);
 	s.mcmc_run();

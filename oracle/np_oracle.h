@@ -106,6 +106,10 @@ int npo_membertrix_selftest(uint32_t seed, int dense);
 
 /* ---- the sampler (np_mcmc.cpp:48-175 with np_neal_algorithm8.cpp / np_jain_neal_algorithm.cpp / np_triadic_algorithm.cpp) ---- */
 npo_run *npo_mcmc_run(const npo_prior *prior, const npo_options *opt, const double *X /* [N,D] */, int N);
+/* NOT the reference: the same run started from K caller-supplied clusters (mu [K,D], Sigma [K,D,D]) instead of K0 prior
+ * draws; used by bench.py for the CPU figure in the D = 16 regime (the reference's own prior collapses to one cluster there) */
+npo_run *npo_mcmc_run_given(const npo_prior *prior, const npo_options *opt, const double *X, int N, int K, const double *mu,
+		const double *Sigma);
 void npo_run_free(npo_run *r);
 void npo_run_stats(const npo_run *r, npo_stats *out);
 void npo_run_assignments(const npo_run *r, int which /*0 final, 1 max-likelihood*/, int *z_out /*[N], compact labels*/);

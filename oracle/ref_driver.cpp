@@ -18,7 +18,8 @@
  *   request.bin : int32 N, int32 D, double kappa, nu, alpha, mu0[D], Lambda[D*D] (row-major), X[N*D] (row-major)
  *   result.bin  : int32 N, int32 T, int64 calls, double seconds_run, double seconds_update,
  *                 int32 K_final, int32 n_snap, int32 z_final[N], int32 z_maxlik[N],
- *                 int64 n_K, int32 K_after_call[n_K], int32 z_snap[n_snap][N]
+ *                 int64 n_K, int32 K_after_call[n_K], int32 z_snap[n_snap][N],
+ *                 int64 n_s, double cumulative_update_seconds_at_sweep_end[n_s]  (Alg. 8 only)
  */
 #include <chrono>
 #include <cstdint>
@@ -61,6 +62,7 @@ public:
 	double seconds = 0.0;
 	int64_t calls = 0;
 	std::vector<int32_t> K_after;
+	std::vector<double> sweep_seconds; /* Alg. 8: cumulative update() seconds at the end of every sweep */
 	std::vector<std::vector<int32_t>> snaps;
 	TimedSampler(UpdateClusterPopulation &s, int n, int subset_count, int rec) : inner(s), N(n), subset(subset_count), record(rec) {}
 	void update(membertrix &trix, const data_ids_t &ids) override {
@@ -68,6 +70,7 @@ public:
 		inner.update(trix, ids);
 		seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 		++calls;
+		if (subset == 1 && calls % N == 0) sweep_seconds.push_back(seconds);
 		if (record) {
 			K_after.push_back((int32_t)trix.getClusterCount());
 			/* Alg. 8 makes exactly N calls per sweep (np_mcmc.cpp:146-163); split-merge sweeps skip collisions (Q11) */
@@ -178,6 +181,9 @@ int main(int argc, char **argv) {
 	wr(fo, &nk, 1);
 	wr(fo, timed.K_after.data(), timed.K_after.size());
 	for (auto &z : timed.snaps) wr(fo, z.data(), z.size());
+	int64_t ns = (int64_t)timed.sweep_seconds.size();
+	wr(fo, &ns, 1);
+	wr(fo, timed.sweep_seconds.data(), timed.sweep_seconds.size());
 	std::fclose(fo);
 	std::printf("np_ref_run %s N=%d D=%d T=%d calls=%lld K_final=%d run %.3fs update %.3fs\n", alg.c_str(), N, D, T,
 			(long long)timed.calls, K_final, seconds_run, timed.seconds);

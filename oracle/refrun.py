@@ -49,7 +49,10 @@ def read_result(path):
     (nk,) = struct.unpack_from("<q", b, off); off += 8
     K_after = np.frombuffer(b, np.int32, nk, off); off += 4 * nk
     snaps = np.frombuffer(b, np.int32, n_snap * N, off).reshape(n_snap, N)
-    return dict(N=N, T=T, calls=calls, seconds_run=s_run, seconds_update=s_upd, K_final=K_final, z_final=z_final.copy(),
+    off += 4 * n_snap * N
+    (ns,) = struct.unpack_from("<q", b, off); off += 8
+    sweep_cum = np.frombuffer(b, np.float64, ns, off)
+    return dict(sweep_update_seconds=np.diff(np.concatenate([[0.0], sweep_cum])), N=N, T=T, calls=calls, seconds_run=s_run, seconds_update=s_upd, K_final=K_final, z_final=z_final.copy(),
                 z_maxlik=z_maxlik.copy(), K_after=K_after.copy(), z_snaps=snaps.copy())
 
 
