@@ -421,6 +421,13 @@ def main():
         fp32_peak = mc_fp32_peak(ctx)
         hbm_peak, hbm_src = measured_peaks()
         bytes_per_launch = n_step * (2 * 2 + 4 * DIM / 32.0)  # z read+write (u16) + x shared by a 32-step tile
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.config)
+            if tj and tj["chains"] == n_chains:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         kernel = "k_alg8_sweep_tile4<%d,3>" % DIM if (DIM >= 4 and kmax == 32) else ("k_alg8_sweep_tile" if DIM >= 4 else "k_alg8_sweep_reg")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -439,12 +446,13 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": flops_per_launch / (k_ms * 1e-3) / 1e12, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": flops_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
-                         "traffic": None, "kernel": kernel, "kernel_ms": k_ms,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read+write)",
+                         "algorithmic_bytes": bytes_per_launch, "kernel": kernel, "kernel_ms": k_ms,
                          "peak_source": "FP32 FMA peak measured in this run by npb_fp32_peak (better of the scalar FFMA and the "
                                         "packed FFMA2 instruction streams; MEASURED_PEAKS.json has no FP32 figure); algorithmic "
                                         "flops = sum(K_i+m) * (D^2+4D+3+6), counter kept by the kernel"},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                             "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                              "peak_source": hbm_src},
             "diagnostics": {"mean_purity": diag["mean_purity"], "mean_rand": diag["mean_rand"], "mean_ari": diag["mean_ari"],
                             "mean_K": diag["mean_K"], "chains": diag["chains"], "rhat": diag["rhat"],
