@@ -62,17 +62,20 @@ __global__ void k_chains_init(SweepArgs a, int K0, const float *theta_given /* [
 // ---------------------------------------------------------------------------------------------------------
 // whitening of the dataset against the prior: Xw = CT2 (x - mu0)  (CT2 upper triangular packed)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_whiten(const float *X, float *Xw, int64_t N, PriorDev pr) {
+__global__ void k_whiten(const float *X, float *Xw, float *Xwn, int64_t N, PriorDev pr) {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= N) return;
 	const int D = pr.D;
 	const float *x = X + i * D;
 	float *o = Xw + i * D;
+	float q = 0.0f;
 	for (int r = 0; r < D; ++r) {
 		float s = 0.0f;
 		for (int c = r; c < D; ++c) s += pr.CT2[npb_tri_off(D, r, c)] * (x[c] - pr.mu0[c]);
 		o[r] = s;
+		q += s * s;
 	}
+	Xwn[i] = sqrtf(q);
 }
 // ---------------------------------------------------------------------------------------------------------
 // launchers
@@ -99,6 +102,7 @@ static SweepArgs make_args(npb_chains *ch, int n_sweeps) {
 	SweepArgs a;
 	a.X = ch->ds->X32;
 	a.Xw = ch->ds->Xw;
+	a.Xwn = ch->ds->Xwn;
 	a.z = ch->z;
 	a.theta = ch->theta;
 	a.counts = ch->counts;
@@ -121,7 +125,7 @@ npb_status npb_launch_whiten(npb_dataset *ds) {
 	PriorDev pd = npb_prior_dev(ctx, 1);
 	int threads = 256;
 	int64_t blocks = (ds->N + threads - 1) / threads;
-	k_whiten<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X32, ds->Xw, ds->N, pd);
+	k_whiten<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ds->X32, ds->Xw, ds->Xwn, ds->N, pd);
 	NPB_CUDA_OK(cudaGetLastError());
 	ds->whitened_epoch = ctx->prior_epoch;
 	return NPB_OK;

@@ -118,12 +118,45 @@ __device__ __noinline__ float log2density_stream(const float *th, const float *x
 	return __ldcg(th + D + TRI) - q;
 }
 
-// The M auxiliary draws of step sj for one item (np_neal_algorithm8.cpp:79-84,119-126) and the race among them: returns
-// the best key and which draw it was.  A draw's density needs only the prior-whitened item: log2 N(x | theta') =
-// c0_2 - D log2|v| - |xw/|v| - z/sqrt(kappa)|^2 (npb_common.cuh).  The normals are consumed pair by pair in the order
-// aux_normals() produces them, so a birth can re-derive theta' from the same stream.
+// One auxiliary draw theta' ~ G0 in the form the race needs (np_neal_algorithm8.cpp:79-84; dirichlet.h:91-93 ->
+// normalinvwishart.h:44-64).  In prior-whitened coordinates theta' = (|v|, z), v ~ N(D, nu^2), z ~ N(0, I_D), and
+//     log2 N(x | theta') = c0_2 - D log2|v| - |xw/|v| - s z|^2,      s = ik2            (npb_common.cuh)
+// The density depends on z only through |a - s z|^2 with a = xw/|v|.  Split z along a: z = zpar a^ + zperp, then
+//     |a - s z|^2 = (|a| - s zpar)^2 + s^2 |zperp|^2,   zpar ~ N(0,1),  |zperp|^2 ~ chi^2_{D-1}, direction uniform,
+// all three independent.  So a draw's key needs THREE normals and (D-1)/2 uniforms instead of D+1 normals:
+// chi^2_{2k+1} = -2 ln(U_1 ... U_k) + z2^2.  Only when a draw wins the race (a birth, ~1e-5 of the steps) is the full
+// vector z materialised: zpar a^ + sqrt(R2) u^, u^ uniform on the unit sphere orthogonal to a^ (aux_birth_z below) --
+// the joint law of (key, theta') is the reference's.  Stream per draw: 4 words (two Box-Muller pairs: v, zpar, z2,
+// spare) + ceil((D-1)/4) words of 16-bit uniforms.
+template <int D>
+__device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &pr, float &av, float &zpar, float &R2) {
+	float g0, g1, g2, g3;
+	{
+		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+		npb_normal2(r0, r1, g0, g1);
+	}
+	{
+		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+		npb_normal2(r0, r1, g2, g3);
+	}
+	av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
+	zpar = g1;
+	constexpr int KU = (D - 1) / 2; // uniforms; D <= 16 keeps their product far above FLT_MIN
+	float prod = 1.0f;
+#pragma unroll
+	for (int i = 0; i < KU; i += 2) {
+		const uint32_t w = xoshiro_next(as);
+		prod *= __uint2float_rn((w & 0xffffu) + 1u) * (1.0f / 65536.0f);
+		if (i + 1 < KU) prod *= __uint2float_rn((w >> 16) + 1u) * (1.0f / 65536.0f);
+	}
+	R2 = -2.0f * NPB_LN2 * fast_lg2(prod);
+	if ((D - 1) & 1) R2 = fmaf(g2, g2, R2);
+}
+
+// The M auxiliary draws of step sj for one item and the race among them: best key and which draw it was.
+// rn = |xw| (k_whiten).
 template <int D, int M>
-__device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, const float *xw, uint32_t sj, uint32_t sweep, float ik2,
+__device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, float rn, uint32_t sj, uint32_t sweep, float ik2,
 		float &auxkey_j, int &auxm) {
 	auxkey_j = -INFINITY;
 	auxm = 0;
@@ -132,31 +165,10 @@ __device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, c
 	float lkey[M];
 #pragma unroll
 	for (int m = 0; m < M; ++m) {
-		float g0, g1;
-		{
-			const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-			npb_normal2(r0, r1, g0, g1);
-		}
-		const float v = pr.v_mean + pr.nu * g0;
-		const float av = fmaxf(fabsf(v), 1e-20f);
-		const float inv = __frcp_rn(av);
-		float q;
-		{
-			const float y = __ldg(xw) * inv - g1 * ik2; // coordinate 0 pairs with normal 1
-			q = y * y;
-		}
-#pragma unroll
-		for (int p = 1; p < (D + 2) / 2; ++p) {
-			const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-			npb_normal2(r0, r1, g0, g1);
-			// normals 2p and 2p+1 belong to coordinates 2p-1 and 2p
-			const float ya = __ldg(xw + 2 * p - 1) * inv - g0 * ik2;
-			q = fmaf(ya, ya, q);
-			if (2 * p < D) {
-				const float yb = __ldg(xw + 2 * p) * inv - g1 * ik2;
-				q = fmaf(yb, yb, q);
-			}
-		}
+		float av, zpar, R2;
+		aux_draw_chi<D>(as, pr, av, zpar, R2);
+		const float along = rn * __frcp_rn(av) - ik2 * zpar;
+		const float q = fmaf(along, along, ik2 * ik2 * R2);
 		lkey[m] = pr.c0_2 - (float)D * fast_lg2(av) - q + pr.log2_alpha_m;
 	}
 #pragma unroll
@@ -164,6 +176,35 @@ __device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, c
 		const float key = lkey[m] + neg_lg2_exp1(xoshiro_next(as));
 		if (key > auxkey_j) { auxkey_j = key; auxm = m; }
 	}
+}
+
+// Birth: coordinate `lane` (< D) of the full z of draw m of step `step`, consistent with the key that won the race.
+// All lanes of the warp call it; xw is the item's whitened row, rn its norm.
+template <int D>
+__device__ __forceinline__ float aux_birth_z(const Philox &ph, const PriorDev &pr, const float *xw, float rn, uint32_t step,
+		uint32_t sweep, int m, int lane, float &av_out) {
+	uint32_t as[4];
+	ph(step, 1u, sweep, NPB_RNG_AUX, as);
+	float av = 1.0f, zpar = 0.0f, R2 = 0.0f;
+	for (int mm = 0; mm <= m; ++mm) aux_draw_chi<D>(as, pr, av, zpar, R2);
+	av_out = av;
+	// unit vector along the item (any fixed direction if the item sits exactly on mu0)
+	const float ahat = lane < D ? (rn > 0.0f ? __ldg(xw + lane) / rn : (lane == 0 ? 1.0f : 0.0f)) : 0.0f;
+	// a standard normal vector from its own stream, made orthogonal to a^ and normalised
+	uint32_t w[4];
+	ph(step, 2u + (uint32_t)(lane >> 1), sweep, NPB_RNG_AUX, w);
+	float n0, n1;
+	npb_normal2(w[0], w[1], n0, n1);
+	float g = lane < D ? ((lane & 1) ? n1 : n0) : 0.0f;
+	float dot = g * ahat;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+	g -= dot * ahat;
+	float nn = g * g;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+	const float uhat = nn > 0.0f ? g * rsqrtf(nn) : 0.0f;
+	return zpar * ahat + sqrtf(R2) * uhat;
 }
 
 template <int D, int M>
@@ -207,7 +248,7 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 					// sequential race is the critical path of a chain
 					float ak;
 					int am;
-					aux_race<D, M>(ph, a.prior, a.Xw + (size_t)item * D, (uint32_t)(s0 + lane), a.sweep0 + (uint32_t)sw, ik2, ak, am);
+					aux_race<D, M>(ph, a.prior, __ldg(a.Xwn + item), (uint32_t)(s0 + lane), a.sweep0 + (uint32_t)sw, ik2, ak, am);
 					sm.auxkey[b][lane] = ak;
 					sm.auxm[b][lane] = am;
 					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)item * D);
@@ -265,7 +306,6 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 	named_bar_sync(bar0, 64); // initial state published
 	unsigned long long st_cand = 0ull, st_moved = 0ull, st_births = 0ull;
 	int overflow = 0;
-	const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
 
 	// re-evaluates the tile column of `slot` for steps >= j_from of buffer b (lane = step) from the master copy
 	auto fix_column = [&](int slot, int b, int j_from, int item, bool valid) {
@@ -361,17 +401,11 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 							new_slot = fs;
 							const int m = (zo_aux >> 16) & 0xff;
 							const uint32_t step = (uint32_t)(s0 + j);
-							// re-derive theta' of draw m of this step from the step's stream: lane d takes normal 1+d
-							uint32_t as[4];
-							ph(step, 1u, sweep, NPB_RNG_AUX, as);
-							float gg[2 * ((D + 2) / 2)];
-							for (int mm = 0; mm <= m; ++mm) aux_normals<D>(as, gg);
-							const float v = a.prior.v_mean + a.prior.nu * gg[0];
-							const float av = fmaxf(fabsf(v), 1e-20f);
-							float g = 0.0f;
-#pragma unroll
-							for (int c = 0; c < D; ++c)
-								if (lane == c) g = gg[1 + c] * (av * a.prior.inv_sqrt_kappa);
+							// materialise theta' of draw m of this step, consistent with the key that won (aux_birth_z)
+							const int bitem = order[step];
+							float av;
+							const float zc = aux_birth_z<D>(ph, a.prior, a.Xw + (size_t)bitem * D, __ldg(a.Xwn + bitem), step, sweep, m, lane, av);
+							const float g = zc * (av * a.prior.inv_sqrt_kappa);
 							float mu_r = lane < D ? a.prior.mu0[lane] : 0.0f;
 							for (int c = 0; c < D; ++c) {
 								const float gc = __shfl_sync(0xffffffffu, g, c);

@@ -125,6 +125,7 @@ npb_status npb_dataset_upload(npb_ctx *ctx, const double *X, int64_t N, int D, n
 	if ((e = cudaMalloc((void **)&ds->X64, n * sizeof(double))) != cudaSuccess ||
 			(e = cudaMalloc((void **)&ds->X32, n * sizeof(float))) != cudaSuccess ||
 			(e = cudaMalloc((void **)&ds->Xw, n * sizeof(float))) != cudaSuccess ||
+			(e = cudaMalloc((void **)&ds->Xwn, (size_t)N * sizeof(float))) != cudaSuccess ||
 			(e = cudaMallocHost((void **)&ds->h_stage, n * sizeof(double))) != cudaSuccess) {
 		npb_dataset_destroy(ds);
 		return npb_fail_cuda(ctx, e, "dataset allocation", __FILE__, __LINE__);
@@ -151,6 +152,7 @@ npb_status npb_dataset_destroy(npb_dataset *ds) {
 	if (ds->X64) cudaFree(ds->X64);
 	if (ds->X32) cudaFree(ds->X32);
 	if (ds->Xw) cudaFree(ds->Xw);
+	if (ds->Xwn) cudaFree(ds->Xwn);
 	if (ds->h_stage) cudaFreeHost(ds->h_stage);
 	delete ds;
 	return NPB_OK;

@@ -33,6 +33,7 @@ struct npb_dataset {
 	double *X64 = nullptr;  // [N,D]
 	float *X32 = nullptr;   // [N,D]
 	float *Xw = nullptr;    // [N,D] whitened against the prior: C^T (x - mu0) * sqrt(log2e/2)
+	float *Xwn = nullptr;   // [N] Euclidean norm of the whitened row
 	uint64_t whitened_epoch = 0;
 	double *h_stage = nullptr; // pinned staging for uploads
 };
@@ -63,7 +64,7 @@ struct npb_chains {
 };
 
 struct SweepArgs {
-	const float *X, *Xw;
+	const float *X, *Xw, *Xwn;
 	const int32_t *scan_order; // [n_sweeps, N]
 	npb_z_t *z;
 	float *theta;

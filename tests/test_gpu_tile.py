@@ -38,8 +38,9 @@ def test_tile_kernel_invariants(npb, ctx, oracle, D, kmax):
         assert np.allclose([m["purity"][c], m["rand_index"][c], m["adjusted_rand"][c]], want, atol=1e-12)
     assert abs(st.mean_K - m["K"].mean()) < 1e-9
     # determinism and launch splitting
-    a = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=kmax, seed=77)
-    b = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=kmax, seed=77)
+    k0 = 20 if kmax > 32 else 8  # 20 initial clusters plus the first sweeps' births can exceed 32 slots
+    a = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=kmax, K0=k0, seed=77)
+    b = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=kmax, K0=k0, seed=77)
     a.run(4)
     b.run(4, sweeps_per_launch=1)
     assert np.array_equal(a.getMembershipMatrix(), b.getMembershipMatrix())
@@ -98,3 +99,43 @@ def _oracle_seed(args):
     s = r.stats()
     pur, ri, ari = orc.metrics(y, r.assignments(0))
     return s.K_final, pur, ari
+
+
+def _oracle_seed_k0(args):
+    seed, T, K0 = args
+    from oracle import binding as orc
+    X, y = syn.gmm(240, 4, 3, 42, min_dist=5.0)
+    p = orc.make_prior(**syn.reference_prior(4))
+    r = orc.Run(p, X, T=T, K0=K0, seed_main=700 + seed, seed_shuffle=1900 + seed, flags=orc.LOG_DOMAIN)
+    s = r.stats()
+    pur, ri, ari = orc.metrics(y, r.assignments(0))
+    return s.K_final, pur, ari, s.new_cluster_events / s.updates, s.moved / s.updates
+
+
+def test_tile4_kernel_distribution_and_birth_rate_4d(npb, ctx, oracle):
+    """The four-chains-per-CTA kernel (Kmax = 32) draws an auxiliary candidate's race key from the non-central
+    chi-square form and materialises theta' only at a birth (npb_alg8_tile4.cuh).  128 device chains against 128 oracle
+    seeds (1024 device chains) from the same K0 = 8 start: K, purity, ARI in distribution, and the birth and move rates over the whole run --
+    a newborn cluster built inconsistently with its key would die at a different rate."""
+    from multiprocessing import Pool
+    X, y = syn.gmm(240, 4, 3, 42, min_dist=5.0)
+    pr = syn.reference_prior(4)
+    T, K0 = 150, 8
+    with Pool(8) as pool:
+        res = np.array(pool.map(_oracle_seed_k0, [(s, T, K0) for s in range(128)]))
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**pr), chains=1024, Kmax=32, K0=K0, seed=13)
+    stats = mc.run(T, sweeps_per_launch=50)
+    assert all(s.overflow_chains == 0 for s in stats)
+    m = mc.chains.metrics(y)
+    for name, got, want in (("K", m["K"].astype(float), res[:, 0]), ("purity", m["purity"], res[:, 1]),
+                            ("ari", m["adjusted_rand"], res[:, 2])):
+        p = sps.ks_2samp(got, want).pvalue
+        assert p > 0.01, "%s: KS p=%.2e (gpu %.4f vs oracle %.4f)" % (name, p, got.mean(), want.mean())
+    n = sum(s.reassignments for s in stats)
+    births = sum(s.new_clusters for s in stats) / n
+    moved = sum(s.moved for s in stats) / n
+    print("births/step gpu %.5f oracle %.5f; moved gpu %.4f oracle %.4f" % (births, res[:, 3].mean(), moved, res[:, 4].mean()))
+    assert abs(births - res[:, 3].mean()) < 0.05 * res[:, 3].mean() + 1e-5
+    assert abs(moved - res[:, 4].mean()) < 0.05 * res[:, 4].mean() + 1e-4
+    ds.close()
