@@ -116,6 +116,7 @@ static SweepArgs make_args(npb_chains *ch, int n_sweeps) {
 	a.n_sweeps = n_sweeps;
 	a.seed = ch->seed;
 	a.scan_order = ch->scan_order;
+	a.aux_keys = ch->aux_keys;
 	a.prior = npb_prior_dev(ch->ctx, ch->m_aux);
 	return a;
 }
@@ -151,7 +152,8 @@ NPB_DECL(3, 1) NPB_DECL(3, 2) NPB_DECL(3, 4) NPB_DECL(3, 8)
 #define NPB_TDECL(D, K) extern template npb_status npb_launch_alg8_tile<D, K>(npb_chains *, const SweepArgs &);
 NPB_TDECL(4, 32) NPB_TDECL(4, 64) NPB_TDECL(8, 32) NPB_TDECL(8, 64) NPB_TDECL(16, 32) NPB_TDECL(16, 64)
 #undef NPB_TDECL
-#define NPB_T4DECL(D) extern template npb_status npb_launch_alg8_tile4<D>(npb_chains *, const SweepArgs &);
+#define NPB_T4DECL(D) extern template npb_status npb_launch_alg8_tile4<D>(npb_chains *, const SweepArgs &); \
+	extern template npb_status npb_launch_aux_keys<D>(npb_chains *, const SweepArgs &);
 NPB_T4DECL(4) NPB_T4DECL(8) NPB_T4DECL(16)
 #undef NPB_T4DECL
 
@@ -178,9 +180,10 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
 	if (!two_warp && ch->Kmax == 32 && (ch->D == 4 || ch->D == 8 || ch->D == 16)) key = -ch->D;
 	switch (key) {
-	case -4: s = npb_launch_alg8_tile4<4>(ch, a); break;
-	case -8: s = npb_launch_alg8_tile4<8>(ch, a); break;
-	case -16: s = npb_launch_alg8_tile4<16>(ch, a); break;
+	// pre-pass (state independent, fully parallel): the race key of every (chain, step)'s auxiliary draws; then the sweep
+	case -4: s = npb_launch_aux_keys<4>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<4>(ch, a); break;
+	case -8: s = npb_launch_aux_keys<8>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<8>(ch, a); break;
+	case -16: s = npb_launch_aux_keys<16>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<16>(ch, a); break;
 	case 2001: s = npb_launch_alg8_reg<2, 1>(ch, a); break;
 	case 2002: s = npb_launch_alg8_reg<2, 2>(ch, a); break;
 	case 2004: s = npb_launch_alg8_reg<2, 4>(ch, a); break;
@@ -213,8 +216,17 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 		ch->scan_cap = (int)(cap < 1 ? 1 : (cap > 1024 ? 1024 : cap));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->scan_order, per_sweep * ch->scan_cap));
 	}
+	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
+	if (!two_warp && ch->Kmax == 32 && ch->D >= 4 && !ch->aux_keys) {
+		// as many sweeps per launch as fit 4 GB of auxiliary keys (one 32-bit word per chain and step)
+		const size_t per_sweep = (size_t)ch->ds->N * ch->C * sizeof(uint32_t);
+		size_t cap = ((size_t)4 << 30) / per_sweep;
+		ch->aux_cap = (int)(cap < 1 ? 1 : (cap > (size_t)ch->scan_cap ? (size_t)ch->scan_cap : cap));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->aux_keys, per_sweep * ch->aux_cap));
+	}
+	const int per_launch = ch->aux_keys ? ch->aux_cap : ch->scan_cap;
 	for (int done = 0; done < n_sweeps;) {
-		const int n = (n_sweeps - done < ch->scan_cap) ? n_sweeps - done : ch->scan_cap;
+		const int n = (n_sweeps - done < per_launch) ? n_sweeps - done : per_launch;
 		npb_status s = launch_chunk(ch, n);
 		if (s != NPB_OK) return s;
 		done += n;

@@ -29,8 +29,6 @@ struct Tile4Smem {
 	                          // xs[(p * D + c) * 2 + h] = coordinate c of item 2p + h
 	int ver_tile[2][32];      // version of slot k the buffer's column was computed from, -1 = not computed
 	int ver_cur[32];          // current slot versions (bumped by a birth)
-	float auxkey[2][32];      // [buffer][step]: race key of the best of the step's M auxiliary draws
-	int auxm[2][32];          // [buffer][step]: which draw that was
 	unsigned occ;             // occupancy bit mask, maintained by the consumer
 	unsigned pad[3];
 };
@@ -207,6 +205,35 @@ __device__ __forceinline__ float aux_birth_z(const Philox &ph, const PriorDev &p
 	return zpar * ahat + sqrtf(R2) * uhat;
 }
 
+// Pre-pass: the auxiliary draws of a step do not depend on the chain's state, only on (chain, step, sweep, item), so their
+// race is run for every (chain, step) of a launch by a plain data-parallel kernel before the sweep: one thread per
+// (chain, step), one packed 32-bit word out ([sweep][chain][step], coalesced along steps for writer and reader).  This
+// takes the 3 x (3 normals + 7 uniforms) per step off the sweep kernel's producer warp, whose FFMA2 stream then owns the
+// FP32 pipe; the extra HBM traffic (8 bytes per reassignment) is ~1 ms of a 200 ms sweep.
+template <int D, int M>
+__global__ void __launch_bounds__(256) k_aux_keys(const SweepArgs a, uint32_t *out) {
+	const int sj = blockIdx.x * 256 + threadIdx.x;
+	const int chain = blockIdx.y, sw = blockIdx.z;
+	if (sj >= a.N) return;
+	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+	const int item = a.scan_order[(size_t)sw * a.N + sj];
+	float ak;
+	int am;
+	aux_race<D, M>(ph, a.prior, __ldg(a.Xwn + item), (uint32_t)sj, a.sweep0 + (uint32_t)sw,
+			a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT, ak, am);
+	out[((size_t)sw * a.C + chain) * a.N + sj] = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+}
+
+template <int D>
+npb_status npb_launch_aux_keys(npb_chains *ch, const SweepArgs &a) {
+	npb_ctx *ctx = ch->ctx;
+	if (ch->m_aux != 3) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 3 for the D >= 4 sweep kernel");
+	dim3 grid((unsigned)((a.N + 255) / 256), (unsigned)ch->C, (unsigned)a.n_sweeps);
+	k_aux_keys<D, 3><<<grid, 256, 0, ctx->stream>>>(a, ch->aux_keys);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
 template <int D, int M>
 __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) {
 	constexpr int TRI = npb_tri(D), PS = npb_ps(D), PSP = npb_psp(D), KMAX = 32;
@@ -230,8 +257,6 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 		float P[PSP];
 		load_theta_nb<D>(thg, P);
 		int myver = 0;
-		const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
-		const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
 		float *xs = sm.xs;
 		int t = 0;
 		// wait for the consumer's initial occupancy mask / versions
@@ -244,13 +269,6 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 				const int cnt = min(NPB_TILE, N - s0);
 				{
 					const int item = (lane < cnt) ? order[s0 + lane] : 0;
-					// the step's auxiliary draws (lane = step): the producer has the idle issue slots, the consumer's
-					// sequential race is the critical path of a chain
-					float ak;
-					int am;
-					aux_race<D, M>(ph, a.prior, __ldg(a.Xwn + item), (uint32_t)(s0 + lane), a.sweep0 + (uint32_t)sw, ik2, ak, am);
-					sm.auxkey[b][lane] = ak;
-					sm.auxm[b][lane] = am;
 					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)item * D);
 					float *dst = xs + (lane >> 1) * (2 * D) + (lane & 1);
 #pragma unroll
@@ -330,9 +348,13 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 			ph((uint32_t)sj, 0u, sweep, NPB_RNG_PICK, rs);
 			const int cnt = min(NPB_TILE, N - s0);
 
+			// race key of the best of this step's M auxiliary draws and which draw it was (k_aux_keys, the state-independent
+			// pre-pass): the two low mantissa bits carry the draw index and stay in the key, 3 ulp of a noise-dominated number
+			const uint32_t auxp = valid ? __ldg(a.aux_keys + ((size_t)sw * C + chain) * N + sj) : 0xff800000u;
+			const float auxkey_j = __uint_as_float(auxp);
+			const int zold_aux_j = zold | ((int)(auxp & 3u) << 16);
+
 			named_bar_sync(bar0 + b, 64); // the producer has filled buffer b
-			const float auxkey_j = sm.auxkey[b][lane];
-			const int zold_aux_j = zold | (sm.auxm[b][lane] << 16);
 			{
 				unsigned stale = __ballot_sync(0xffffffffu, n > 0.0f && sm.ver_tile[b][lane] != sm.ver_cur[lane]);
 				while (stale) {

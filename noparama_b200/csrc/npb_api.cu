@@ -330,6 +330,7 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->overflow) cudaFree(ch->overflow);
 	if (ch->h_z) cudaFreeHost(ch->h_z);
 	if (ch->scan_order) cudaFree(ch->scan_order);
+	if (ch->aux_keys) cudaFree(ch->aux_keys);
 	if (ch->smst) cudaFree(ch->smst);
 	if (ch->sm_zt) cudaFree(ch->sm_zt);
 	if (ch->sm_pool) cudaFree(ch->sm_pool);

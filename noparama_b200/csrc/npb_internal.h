@@ -54,6 +54,8 @@ struct npb_chains {
 	npb_z_t *h_z = nullptr;     // pinned staging for npb_chains_sweep_host
 	int32_t *scan_order = nullptr; // [scan_cap, N] item visited at each step of the sweeps of one launch
 	int scan_cap = 0;              // sweeps per launch the buffer holds
+	uint32_t *aux_keys = nullptr;  // [aux_cap, C, N] packed race key of the best auxiliary draw of every (chain, step)
+	int aux_cap = 0;               // sweeps per launch that buffer holds
 	// split-merge samplers (npb_splitmerge.cu)
 	unsigned long long *smst = nullptr; // [C, 12]: attempts[4], accepts[4], SAMS allocations, proposals, 2 reserved
 	npb_z_t *sm_zt = nullptr;      // [C, zstride] chain-major working copy of z
@@ -66,6 +68,7 @@ struct npb_chains {
 struct SweepArgs {
 	const float *X, *Xw, *Xwn;
 	const int32_t *scan_order; // [n_sweeps, N]
+	const uint32_t *aux_keys;  // [n_sweeps, C, N] (k_aux_keys) or NULL
 	npb_z_t *z;
 	float *theta;
 	int *counts;

@@ -93,6 +93,28 @@ void NealAlgorithm8::printStatistics() { // np_neal_algorithm8.cpp:169-176
 	std::cout << " # of new cluster events rejected: " << rejected_ << std::endl;
 }
 
+void SplitMergeAlgorithm::sweep(membertrix &cluster_matrix, int n_sweeps) {
+	dev_.check(npb_chains_sweep(cluster_matrix.chains, sampler_, n_sweeps, &last_));
+	for (int i = 0; i < 4; ++i) {
+		attempts_[i] += last_.sm_attempts[i];
+		accepts_[i] += last_.sm_accepts[i];
+	}
+	cluster_matrix.invalidate();
+}
+void SplitMergeAlgorithm::update(membertrix &cluster_matrix, const data_ids_t &data_ids) {
+	assert((int)data_ids.size() == subsets_); // np_jain_neal_algorithm.cpp:429, np_triadic_algorithm.cpp:647
+	if (calls_++ % cluster_matrix.size() == 0) sweep(cluster_matrix, 1);
+}
+void SplitMergeAlgorithm::printStatistics() {
+	static const char *type[4] = {"merge from 2 to 1", "split from 1 to 2", "merge from 3 to 2", "split from 2 to 3"};
+	std::cout << "Statistics:" << std::endl;
+	for (int i = 0; i < (sampler_ == NPB_JAIN_NEAL ? 2 : 4); ++i) {
+		std::cout << " # of " << type[i] << " attempts: " << attempts_[i] << std::endl;
+		std::cout << "   o of accepted " << type[i] << " cluster events: " << accepts_[i] << std::endl;
+		std::cout << "   o of rejected " << type[i] << " cluster events: " << attempts_[i] - accepts_[i] << std::endl;
+	}
+}
+
 MCMC::MCMC(device &dev, dirichlet_process &hyper, UpdateClusterPopulation &ucp, int64_t chains, int Kmax, int K0, int m_aux, uint64_t seed)
 	: dev_(dev), hyper_(hyper), ucp_(ucp), chains_(chains), Kmax_(Kmax), K0_(K0), m_aux_(m_aux), seed_(seed) {}
 MCMC::~MCMC() {
@@ -112,10 +134,12 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam) {
 	}
 	const int N = trix_->size();
 	if (per_item_seam) {
-		// the reference's own loop shape (np_mcmc.cpp:109-163): one update() per item
+		// the reference's own loop shape (np_mcmc.cpp:109-163): one update() per subset of subset_count items
+		const int sc = ucp_.subset_count();
 		for (int t = 0; t < T; ++t)
 			for (int i = 0; i < N; ++i) {
-				data_ids_t subset(1, i);
+				data_ids_t subset(sc);
+				for (int j = 0; j < sc; ++j) subset[j] = (i + j * 7919) % N; // placeholders: the device draws the real subsets
 				ucp_.update(*trix_, subset);
 			}
 	} else {

@@ -138,6 +138,39 @@ private:
 	npb_sweep_stats last_{};
 };
 
+// The split-merge samplers (include/np_jain_neal_algorithm.h:75-79, include/np_triadic_algorithm.h:73-77).  update()
+// keeps MCMC::run's per-subset calling convention (np_mcmc.cpp:146-163): subsets of 2 / 3 items, asserted like the
+// reference (np_jain_neal_algorithm.cpp:429, np_triadic_algorithm.cpp:647); the first call of a sweep runs the whole
+// sweep of every chain on the device (the device draws its own lockstep subsets), the others are absorbed.
+class SplitMergeAlgorithm : public UpdateClusterPopulation {
+public:
+	SplitMergeAlgorithm(device &dev, dirichlet_process &nonparametrics, int sampler, int subsets)
+		: dev_(dev), hyper_(nonparametrics), sampler_(sampler), subsets_(subsets) {}
+	void update(membertrix &cluster_matrix, const data_ids_t &data_ids) override;
+	void sweep(membertrix &cluster_matrix, int n_sweeps) override;
+	void printStatistics() override; // np_jain_neal_algorithm.cpp:504-531, np_triadic_algorithm.cpp:797-826
+	int sampler() const override { return sampler_; }
+	int subset_count() const override { return subsets_; }
+	const npb_sweep_stats &last() const { return last_; }
+	const int64_t *attempts() const { return attempts_; }
+	const int64_t *accepts() const { return accepts_; }
+private:
+	device &dev_;
+	dirichlet_process &hyper_;
+	int sampler_, subsets_;
+	int64_t calls_ = 0;
+	int64_t attempts_[4] = {0, 0, 0, 0}, accepts_[4] = {0, 0, 0, 0};
+	npb_sweep_stats last_{};
+};
+class JainNealAlgorithm : public SplitMergeAlgorithm {
+public:
+	JainNealAlgorithm(device &dev, dirichlet_process &nonparametrics) : SplitMergeAlgorithm(dev, nonparametrics, NPB_JAIN_NEAL, 2) {}
+};
+class TriadicAlgorithm : public SplitMergeAlgorithm {
+public:
+	TriadicAlgorithm(device &dev, dirichlet_process &nonparametrics) : SplitMergeAlgorithm(dev, nonparametrics, NPB_TRIADIC, 3) {}
+};
+
 struct clustering_scores { // src/clustering_performance.cpp:38-82
 	std::vector<double> purity, rand_index, adjusted_rand, joint_loglik;
 	std::vector<int32_t> K;

@@ -1,8 +1,8 @@
 // npb_main.cpp -- the reference's command line (src/np_main.cpp:187-267) on top of the device path:
-//   noparama_b200 -d <datafile> -a algorithm8 -T <sweeps> -c clustering [--chains C] [--seed S] [--kmax K] [--seam]
+//   noparama_b200 -d <datafile> -a <algorithm8|jain_neal_split|triadic> -T <sweeps> -c clustering [--chains C] [--seed S] [--kmax K] [--seam]
 // -d  text file, one item per line: D coordinates then the ground-truth label (the reference reads exactly 2 + 1
 //     columns, np_main.cpp:93-101; here D = columns - 1 <= 3 for the register kernel, 4/8/16 for the tile kernel)
-// -a  algorithm8 (jain_neal_split / triadic are not on the device yet and are refused, exit 107 like np_main.cpp:385)
+// -a  algorithm8 | jain_neal_split | triadic (np_main.cpp:228-238)
 // -T  sweeps (default 2000, np_main.cpp:242)    -c  clustering only (regression/angular/points3d are out of scope)
 // Prior and constants as hard-wired in the reference: alpha = 1, NIW{mu = 6, kappa = 1/500, nu = D + 2, Lambda = 0.01 I}
 // (np_main.cpp:164,367-371), K0 = 20, M = 3.  No 200-row subsampling (np_main.cpp:166-167): every row is used.
@@ -19,7 +19,7 @@
 using namespace npb;
 
 static void usage() {
-	std::cout << "usage: noparama_b200 -d datafile -a algorithm8 -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam]\n";
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam]\n";
 }
 
 int main(int argc, char **argv) {
@@ -47,7 +47,10 @@ int main(int argc, char **argv) {
 	}
 	if (datafile.empty()) { usage(); return 1; }
 	if (config != "clustering") { std::cerr << "Unknown likelihood (only -c clustering is on the device path)" << std::endl; return 107; }
-	if (algorithm != "algorithm8") { std::cerr << "Algorithm " << algorithm << " is not on the device path yet" << std::endl; return 107; }
+	if (algorithm != "algorithm8" && algorithm != "jain_neal_split" && algorithm != "triadic") { // np_main.cpp:228-238
+		std::cerr << "Unknown algorithm: " << algorithm << std::endl;
+		return 1;
+	}
 
 	// read_data (np_main.cpp:57-148), generalised to D columns + label
 	std::ifstream in(datafile);
@@ -79,11 +82,16 @@ int main(int argc, char **argv) {
 		niw.kappa = 1.0 / 500;
 		niw.nu = D + 2.0;
 		dirichlet_process hyper(sd, niw);
+		// np_main.cpp:424-459
 		NealAlgorithm8 alg8(dev, hyper);
-		MCMC mcmc(dev, hyper, alg8, chains, kmax, 20, 3, seed);
+		JainNealAlgorithm jain_neal(dev, hyper);
+		TriadicAlgorithm triadic(dev, hyper);
+		UpdateClusterPopulation &sampler = algorithm == "algorithm8" ? (UpdateClusterPopulation &)alg8
+				: (algorithm == "jain_neal_split" ? (UpdateClusterPopulation &)jain_neal : (UpdateClusterPopulation &)triadic);
+		MCMC mcmc(dev, hyper, sampler, chains, kmax, 20, 3, seed);
 		std::cout << "Run MCMC for " << T << " steps, " << chains << " chain(s)" << std::endl;
 		mcmc.run(dataset, T, seam);
-		alg8.printStatistics();
+		sampler.printStatistics();
 		clustering_scores sc = mcmc.scores(ground_truth);
 		auto mean = [](const std::vector<double> &v) { return std::accumulate(v.begin(), v.end(), 0.0) / v.size(); };
 		// clustering_performance.cpp:77-79 prints the three scores; chain 0 first, then the mean over chains

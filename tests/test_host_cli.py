@@ -30,9 +30,10 @@ def test_cli_usage_and_refusals(tmp_path):
     assert r.returncode == 0 and "-d datafile" in r.stdout
     data = tmp_path / "twogaussians.data"
     write_data(str(data))
-    # the reference exits 107 on an unknown likelihood (np_main.cpp:346,385); split-merge is not on the device yet
+    # the reference exits 107 on an unknown likelihood (np_main.cpp:346,385) and 1 on an unknown algorithm (:236)
     assert subprocess.run([CLI, "-d", str(data), "-c", "regression"], capture_output=True).returncode == 107
-    assert subprocess.run([CLI, "-d", str(data), "-a", "triadic"], capture_output=True).returncode == 107
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm2"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown algorithm" in r.stderr
     assert subprocess.run([CLI, "-d", str(tmp_path / "missing")], capture_output=True).returncode == 7
 
 
@@ -65,3 +66,21 @@ def test_cli_runs_config1(tmp_path):
         assert "new cluster events accepted" in r.stdout
     # the per-item seam (one update() per item, np_mcmc.cpp:162) and the batched sweep walk the same trajectory
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algorithm", ["jain_neal_split", "triadic"])
+def test_cli_runs_split_merge(tmp_path, algorithm):
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    outs = []
+    for extra in ([], ["--seam"]):
+        r = subprocess.run([CLI, "-d", str(data), "-a", algorithm, "-T", "40", "-c", "clustering", "--chains", "32", "--kmax",
+                            "64", "--seed", "9"] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+        assert "merge from 2 to 1 attempts" in r.stdout and "split from 1 to 2 attempts" in r.stdout
+        assert ("merge from 3 to 2 attempts" in r.stdout) == (algorithm == "triadic")
+        assert re.search(r"^Purity: ([0-9.]+)", r.stdout, re.M)
+    assert outs[0] == outs[1]  # per-subset seam (np_mcmc.cpp:162) and batched sweeps: same trajectory
