@@ -33,6 +33,13 @@ struct Tile4Smem {
 	unsigned pad[3];
 };
 
+// -log2 E' as neg_lg2_exp1 (npb_alg8_kernel.cuh) without the clamp: E' = 0 (probability 2^-25) gives +inf, a certain
+// win, which is what an exponential that small means; 1 - v = 0 (probability 2^-32) gives -inf, a certain loss.
+__device__ __forceinline__ float neg_lg2_exp1_open(uint32_t r) {
+	const float omv = fmaf(__uint2float_rn(r), -2.3283064365386963e-10f, 1.0f - 2.3283064365386963e-10f);
+	return -fast_lg2(-fast_lg2(omv));
+}
+
 // Packed FP32 (sm_100a FFMA2): one instruction does two FMAs, on a 64-bit register pair; an operand written as
 // {t, t} is encoded as a broadcast of the 32-bit register t (SASS "R.F32"), so the slot's parameters are not duplicated.
 // The producer evaluates TWO items per instruction stream: pair = (item 2p, item 2p+1).
@@ -125,17 +132,20 @@ __device__ __noinline__ float log2density_stream(const float *th, const float *x
 // chi^2_{2k+1} = -2 ln(U_1 ... U_k) + z2^2.  Only when a draw wins the race (a birth, ~1e-5 of the steps) is the full
 // vector z materialised: zpar a^ + sqrt(R2) u^, u^ uniform on the unit sphere orthogonal to a^ (aux_birth_z below) --
 // the joint law of (key, theta') is the reference's.  Stream per draw: 4 words (two Box-Muller pairs: v, zpar, z2,
-// spare) + ceil((D-1)/4) words of 16-bit uniforms.
+// ) + ceil((D-1)/4) words of 16-bit uniforms.
 template <int D>
 __device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &pr, float &av, float &zpar, float &R2) {
-	float g0, g1, g2, g3;
+	float g0, g1;
 	{
 		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
 		npb_normal2(r0, r1, g0, g1);
 	}
+	// z2^2 alone: the square of one Box-Muller output, (-2 ln u) cos^2(2 pi v), needs no square root and no sine
+	float z2sq;
 	{
 		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-		npb_normal2(r0, r1, g2, g3);
+		const float c = __cosf(__uint2float_rn(r1) * (6.283185307179586f * 2.3283064365386963e-10f));
+		z2sq = -2.0f * NPB_LN2 * fast_lg2(npb_u01(r0)) * c * c;
 	}
 	av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
 	zpar = g1;
@@ -148,7 +158,19 @@ __device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &
 		if (i + 1 < KU) prod *= __uint2float_rn((w >> 16) + 1u) * (1.0f / 65536.0f);
 	}
 	R2 = -2.0f * NPB_LN2 * fast_lg2(prod);
-	if ((D - 1) & 1) R2 = fmaf(g2, g2, R2);
+	if ((D - 1) & 1) R2 += z2sq;
+}
+
+// xoshiro state of the auxiliary stream of (chain, step, sweep): four words of a multiply-xorshift hash (the murmur3
+// finaliser, full avalanche) of the chain's Philox key and the counters -- 36 instructions against Philox4x32-10's 70,
+// in a stream that only has to be distinct per (chain, step, sweep) and reproducible at a birth.
+__device__ __forceinline__ void aux_seed(const Philox &ph, uint32_t sj, uint32_t sweep, uint32_t (&as)[4]) {
+	uint32_t h = npb_mix32(ph.k0 ^ (sj * 0x9E3779B1u));
+	h = npb_mix32(h ^ ph.k1 ^ (sweep * 0x85EBCA77u));
+	as[0] = h;
+	as[1] = npb_mix32(h + 0x9E3779B9u);
+	as[2] = npb_mix32(h + 0x3C6EF372u);
+	as[3] = npb_mix32(h + 0xDAA66D2Bu) | 1u; // never the all-zero state
 }
 
 // The M auxiliary draws of step sj for one item and the race among them: best key and which draw it was.
@@ -159,7 +181,7 @@ __device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, f
 	auxkey_j = -INFINITY;
 	auxm = 0;
 	uint32_t as[4];
-	ph(sj, 1u, sweep, NPB_RNG_AUX, as);
+	aux_seed(ph, sj, sweep, as);
 	float lkey[M];
 #pragma unroll
 	for (int m = 0; m < M; ++m) {
@@ -182,7 +204,7 @@ template <int D>
 __device__ __forceinline__ float aux_birth_z(const Philox &ph, const PriorDev &pr, const float *xw, float rn, uint32_t step,
 		uint32_t sweep, int m, int lane, float &av_out) {
 	uint32_t as[4];
-	ph(step, 1u, sweep, NPB_RNG_AUX, as);
+	aux_seed(ph, step, sweep, as);
 	float av = 1.0f, zpar = 0.0f, R2 = 0.0f;
 	for (int mm = 0; mm <= m; ++mm) aux_draw_chi<D>(as, pr, av, zpar, R2);
 	av_out = av;
@@ -344,8 +366,16 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 			const int item = valid ? order[sj] : 0;
 			const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
 			int znew = zold;
-			uint32_t rs[4];
-			ph((uint32_t)sj, 0u, sweep, NPB_RNG_PICK, rs);
+			// race noise of the tile: one 32-bit LCG per lane (Knuth's multiplier; the top 24 bits of the state are what the
+			// float conversion keeps), re-seeded from a Philox block every tile, so a stream is 33 draws long.  The
+			// consumer's instruction count is what bounds a chain once the producers run packed FP32: xoshiro128++ was 9
+			// of its ~64 instructions per step, this is 1.
+			uint32_t rs;
+			{
+				uint32_t w[4];
+				ph((uint32_t)sj, 0u, sweep, NPB_RNG_PICK, w);
+				rs = w[0] ^ (w[1] << 1);
+			}
 			const int cnt = min(NPB_TILE, N - s0);
 
 			// race key of the best of this step's M auxiliary draws and which draw it was (k_aux_keys, the state-independent
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 			// taken off its dependent chain: the tile entry, the race noise and the broadcasts of step j+1 are fetched
 			// while step j is decided, and log2 of the member counts (n and n - 1) is kept in registers and refreshed
 			// only when a count changes.
-			float noise_next = neg_lg2_exp1(xoshiro_next(rs));
+			float noise_next = neg_lg2_exp1_open(rs = rs * 1664525u + 1013904223u);
 			float base_next = sm.tile[b][lane * 33] + noise_next;
 			int zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, 0);
 			float ak_next = __shfl_sync(0xffffffffu, auxkey_j, 0);
@@ -380,7 +410,7 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 				const int zo = zo_aux & 0xffff;
 				{
 					const int jn = min(j + 1, NPB_TILE - 1);
-					noise_next = neg_lg2_exp1(xoshiro_next(rs));
+					noise_next = neg_lg2_exp1_open(rs = rs * 1664525u + 1013904223u);
 					base_next = sm.tile[b][lane * 33 + jn] + noise_next;
 					zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, jn);
 					ak_next = __shfl_sync(0xffffffffu, auxkey_j, jn);
