@@ -442,7 +442,8 @@ def main():
                     "d2h_bytes_per_step": int(n_items * n_chains * 2), "steps": args.e2e_steps,
                     "call": "npb_chains_sweep_host (X up from pinned host memory, every chain's assignments down into "
                             "page-locked host memory)"},
-            "gpu_launches": args.steps * 2,  # per step: k_scan_order + the sweep kernel
+            # per step: k_scan_order, (D >= 4, Kmax 32: k_aux_keys, the state-independent auxiliary race,) the sweep kernel
+            "gpu_launches": args.steps * (3 if (DIM >= 4 and kmax == 32) else 2),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": flops_per_launch / (k_ms * 1e-3) / 1e12, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": flops_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,

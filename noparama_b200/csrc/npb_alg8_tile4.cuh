@@ -6,8 +6,8 @@
 // parameters resident, so only 8 warps fitted an SM (two per scheduler) and the dependent chain of the consumer's
 // sequential race could not be hidden.  Here
 //   * warps 0-3 (one warpgroup) are the CONSUMERS of chains 4b .. 4b+3, warps 4-7 their PRODUCERS;
-//   * the kernel is launched at 128 registers per thread, two CTAs per SM; the consumer warpgroup shrinks to 56
-//     registers (setmaxnreg.dec) and the producer warpgroup grows to 200 (setmaxnreg.inc): 16 resident warps per SM
+//   * the kernel is launched at 128 registers per thread, two CTAs per SM; the consumer warpgroup shrinks to 64
+//     registers (setmaxnreg.dec) and the producer warpgroup grows to 192 (setmaxnreg.inc): 16 resident warps per SM
 //     instead of 8 out of the same register file;
 //   * the master copy of the slot table stays in global memory (L2): producers read their slot once per launch and
 //     after a birth, so shared memory only holds the two [slot x step] tiles, the staged item rows and the versions
@@ -19,8 +19,8 @@
 #include "npb_alg8_tile.cuh"
 
 #define NPB_T4_CHAINS 4
-#define NPB_T4_CONSUMER_REGS 56
-#define NPB_T4_PRODUCER_REGS 200
+#define NPB_T4_CONSUMER_REGS 64
+#define NPB_T4_PRODUCER_REGS 192
 
 template <int D>
 struct Tile4Smem {
