@@ -1,20 +1,26 @@
 // npb_alg8_tile4.cuh -- Algorithm 8 sweeps for D = 4, 8, 16 and Kmax = 32: four chains per CTA, register budget moved
-// from the consumer warps to the producer warps with setmaxnreg.
+// from the consumer warps to the producer warps with setmaxnreg, packed FP32 in the producer, state-independent work
+// hoisted into a pre-pass kernel.
 //
-// Same algorithm and the same random streams as k_alg8_sweep_tile (npb_alg8_tile.cuh), a different mapping.  ncu on the two-warp CTA showed the FP32 pipe 30 % busy with the schedulers issuing on 44 % of
-// the cycles: every thread of the kernel was allocated the ~200 registers the PRODUCER needs to keep one slot's
-// parameters resident, so only 8 warps fitted an SM (two per scheduler) and the dependent chain of the consumer's
-// sequential race could not be hidden.  Here
+// Same algorithm as k_alg8_sweep_tile (npb_alg8_tile.cuh), a different mapping.  ncu on the two-warp CTA showed the FP32
+// pipe 30 % busy with the schedulers issuing on 44 % of the cycles: every thread of the kernel was allocated the ~200
+// registers the PRODUCER needs to keep one slot's parameters resident, so only 8 warps fitted an SM (two per scheduler)
+// and the dependent chain of the consumer's sequential race could not be hidden.  Here
 //   * warps 0-3 (one warpgroup) are the CONSUMERS of chains 4b .. 4b+3, warps 4-7 their PRODUCERS;
 //   * the kernel is launched at 128 registers per thread, two CTAs per SM; the consumer warpgroup shrinks to 64
 //     registers (setmaxnreg.dec) and the producer warpgroup grows to 192 (setmaxnreg.inc): 16 resident warps per SM
 //     instead of 8 out of the same register file;
+//   * the producer evaluates two items per instruction stream with fma.rn.f32x2 (FFMA2), the slot parameter being a
+//     broadcast operand: 88 instructions per (item, 32 slots) instead of 181;
+//   * the auxiliary draws of a step depend on (chain, step, sweep, item) only, so k_aux_keys computes the race key of
+//     their best for every (chain, step) before the sweep; the sweep kernel reads one packed word per step;
 //   * the master copy of the slot table stays in global memory (L2): producers read their slot once per launch and
 //     after a birth, so shared memory only holds the two [slot x step] tiles, the staged item rows and the versions
 //     (11 KB per chain);
 //   * one rendezvous barrier per (chain, buffer): the producer arrives after filling buffer b, the consumer before
 //     draining it; by the time the producer comes back to buffer b it has passed the other buffer's rendezvous, which
 //     the consumer reaches only after draining b.
+// Measured history and what bounds it now: profiles/README.md.
 #pragma once
 #include "npb_alg8_tile.cuh"
 
