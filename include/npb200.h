@@ -130,6 +130,14 @@ npb_status npb_chains_split_merge(npb_chains *ch, int sampler, int64_t n_proposa
  * new slot, removed slot, the uniform, Q.  For parity tests of the acceptance arithmetic
  * (np_jain_neal_algorithm.cpp:243-296,339-392; np_triadic_algorithm.cpp:370-437,529-590). */
 npb_status npb_chains_last_proposal(npb_chains *ch, float *detail_out);
+/* The parameter update of a sweep done right.  The reference calls UpdateClusters::update after every sweep
+ * (np_mcmc.cpp:170, np_update_clusters.cpp:71-141) but its result is sliced away (np_cluster.h:49-51), so parameters
+ * never change after birth; this opt-in call refreshes (mu, Sigma) of every occupied cluster of every chain from the
+ * conjugate normal-inverse-Wishart posterior of its members: a draw (NPB_UPDATE_POSTERIOR_DRAW) or the posterior mean
+ * (NPB_UPDATE_POSTERIOR_MEAN).  mu0 [D], Lambda0 [D,D] row-major; pass mu0 = Lambda0 = NULL to use the prior bound with
+ * npb_prior_set_niw (kappa0, nu0 are then ignored). */
+enum { NPB_UPDATE_POSTERIOR_DRAW = 1, NPB_UPDATE_POSTERIOR_MEAN = 2 };
+npb_status npb_chains_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);
 /* end-to-end form with host buffers: upload X (as npb_dataset_update), sweep, download the assignments of
  * all chains; z_out [N, n_chains] uint16 slot ids (item-major), may be NULL */
 npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnpb200.so")
 
 ALG8, ALG2, JAIN_NEAL, TRIADIC = 8, 2, 20, 30
+UPDATE_POSTERIOR_DRAW, UPDATE_POSTERIOR_MEAN = 1, 2
 BUGCOMPAT_DEGENERATE_IW, BUGCOMPAT_UNDERFLOW = 1, 2
 BUGCOMPAT_DEFAULT = BUGCOMPAT_DEGENERATE_IW
 
@@ -27,7 +28,7 @@ EXPORTS = [
     "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
-    "npb_chains_split_merge", "npb_chains_last_proposal",
+    "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params",
 ]
 
 
@@ -80,6 +81,7 @@ def load_library():
     L.npb_chains_sweep.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SweepStats)]
     L.npb_chains_split_merge.argtypes = [vp, C.c_int, i64, C.POINTER(SweepStats)]
     L.npb_chains_last_proposal.argtypes = [vp, C.POINTER(C.c_float)]
+    L.npb_chains_update_params.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, dp]
     L.npb_chains_sweep_host.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(SweepStats)]
     L.npb_chain_update_alg8.argtypes = [vp, i64, i64]
     L.npb_replay_alg8.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp, i64, ip, C.POINTER(i64), ip, dp, dp,
@@ -274,6 +276,16 @@ class Chains:
         st = SweepStats()
         self.ctx.check(self.ctx._lib.npb_chains_split_merge(self._h, sampler, n_proposals, C.byref(st)))
         return st
+
+    def update_params(self, mode=1, prior=None):
+        """refresh (mu, Sigma) of every occupied cluster from the conjugate NIW posterior of its members: mode 1 = draw,
+        2 = posterior mean; prior = dict(mu0, kappa, nu, Lambda) or None for the bound prior"""
+        if prior is None:
+            self.ctx.check(self.ctx._lib.npb_chains_update_params(self._h, mode, None, 0.0, 0.0, None))
+        else:
+            mu0, Lam = _f64(prior["mu0"]), _f64(prior["Lambda"])
+            self.ctx.check(self.ctx._lib.npb_chains_update_params(self._h, mode, _dp(mu0), float(prior["kappa"]),
+                                                                  float(prior["nu"]), _dp(Lam)))
 
     PROPOSAL_FIELDS = ("type", "stat", "logA", "accept", "n0", "n1", "n2", "pool", "new_slot", "dying", "u", "Q")
 

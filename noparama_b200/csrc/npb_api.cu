@@ -337,6 +337,9 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->sm_dec) cudaFree(ch->sm_dec);
 	if (ch->sm_order) cudaFree(ch->sm_order);
 	if (ch->sm_detail) cudaFree(ch->sm_detail);
+	if (ch->pstats) cudaFree(ch->pstats);
+	if (ch->pLambda0) cudaFree(ch->pLambda0);
+	if (ch->pfail) cudaFree(ch->pfail);
 	delete ch;
 	return NPB_OK;
 }
@@ -520,6 +523,18 @@ npb_status npb_chains_split_merge(npb_chains *ch, int sampler, int64_t n_proposa
 	if (sampler != NPB_JAIN_NEAL && sampler != NPB_TRIADIC) return NPB_E_BAD_ARG;
 	return sweep_common(ch, sampler, 0, n_proposals, stats, nullptr, nullptr);
 }
+npb_status npb_chains_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0) {
+	if (!ch || (mode != NPB_UPDATE_POSTERIOR_DRAW && mode != NPB_UPDATE_POSTERIOR_MEAN)) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const PriorHost &p = ctx->prior;
+	const bool own = mu0 && Lambda0;
+	if (!own && (mu0 || Lambda0)) return NPB_E_BAD_ARG;
+	if (own && !(kappa0 > 0.0 && nu0 > ch->D - 1.0)) return NPB_E_BAD_ARG;
+	return npb_launch_update_params(ch, mode, own ? mu0 : p.mu0.data(), own ? kappa0 : p.kappa, own ? nu0 : p.nu,
+			own ? Lambda0 : p.Lambda.data());
+}
+
 npb_status npb_chains_last_proposal(npb_chains *ch, float *detail_out) {
 	if (!ch || !detail_out) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;

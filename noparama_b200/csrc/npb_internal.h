@@ -63,6 +63,11 @@ struct npb_chains {
 	uint8_t *sm_dec = nullptr;     // [C, N]
 	int32_t *sm_order = nullptr;   // [3, N]
 	float *sm_detail = nullptr;    // [C, 16] detail of the last proposal of every chain (tests)
+	// parameter update (npb_params.cu)
+	double *pstats = nullptr;      // [C, Kmax, D + D(D+1)/2] sum x, upper triangle of sum x x^T
+	double *pLambda0 = nullptr;    // [D, D]
+	int *pfail = nullptr;
+	uint32_t param_epoch = 0;
 };
 
 struct SweepArgs {
@@ -93,5 +98,6 @@ void npb_theta_to_sigma(int D, const double *T_packed_upper, double *Sigma);
 npb_status npb_launch_whiten(npb_dataset *ds);
 npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given);
 npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps);
+npb_status npb_launch_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);
 npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, int whole_sweeps, float *d_detail);
 PriorDev npb_prior_dev(const npb_ctx *ctx, int m_aux);
