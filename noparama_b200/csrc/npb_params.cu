@@ -10,9 +10,10 @@
 // (mu_n, Lambda_n / (nu_n - D - 1)).  There is no reference arithmetic to match (parity unpinned by construction); the
 // tests check the sufficient statistics and the posterior-mean mode against numpy in double and the draw's moments.
 //
-// k_suffstats<D>   one CTA per chain, one warp per slot (mod 32): chunks of 256 items (assignment + row) are staged in
-//                  shared memory; a warp ballots the chunk for its slot's members and accumulates sum x and the upper
-//                  triangle of sum x x^T in fp64 registers, entries strided over the lanes -- no atomics.
+// k_member_lists  one warp per chain: the items of every slot, contiguous and in ascending order (deterministic).
+// k_suffstats<D>   one warp per (chain, slot): lanes stride over the slot's members, each keeping sum (x - c) and the upper
+//                  triangle of sum (x - c)(x - c)^T about the slot's current mean c in fp32 registers; lanes combined in
+//                  fp64 -- no atomics.
 // k_niw_update<D>  one thread per (chain, slot), fp64: UL-Cholesky  Lambda_n = G G^T  (G upper), L = G^-T (lower, so that
 //                  Lambda_n^-1 = L L^T), Bartlett factor B (lower; B_ii^2 ~ chi^2_{nu_n - i}, B_ij ~ N(0,1)), M = L B, and
 //                  Sigma^-1 = M M^T: the kernels' upper-triangular precision factor is M^T, no inverse is ever formed;
@@ -22,64 +23,108 @@
 
 enum { NPB_RNG_PARAMS = 6 };
 
-template <int D>
-__global__ void __launch_bounds__(1024) k_suffstats(const float *X, const npb_z_t *z, int N, int C, int Kmax, double *stats) {
-	constexpr int NE = D + npb_tri(D);        // sum x [D], sum x_r x_c (r <= c, packed row-wise)
-	constexpr int PER = (NE + 31) / 32;
-	constexpr int CH = 256;
-	__shared__ float xs[CH][D + 1];
-	__shared__ int zs[CH];
-	const int chain = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	// (r, c) of the entries this lane owns
-	int er[PER], ec[PER];
+// Member lists of every chain: perm[chain][off_k .. off_k + n_k) = the items of slot k in ascending item order, off_k the
+// prefix sum of the member counts.  One warp per chain, deterministic (no atomics): a batch of 32 items is grouped by slot
+// with match.any, the first lane of a group advances that slot's cursor (shared memory, one word per slot).
+__global__ void __launch_bounds__(128) k_member_lists(const npb_z_t *z, const int *counts, int N, int C, int Kmax, int32_t *perm) {
+	extern __shared__ int s_cursor[]; // [warps][Kmax]
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
+	if (chain >= C) return;
+	int *cur = s_cursor + warp * Kmax;
+	{
+		int run = 0; // exclusive prefix sum of the counts, 32 slots at a time
+		for (int k0 = 0; k0 < Kmax; k0 += 32) {
+			const int c = counts[(size_t)chain * Kmax + k0 + lane];
+			int incl = c;
 #pragma unroll
-	for (int p = 0; p < PER; ++p) {
-		const int e = lane + 32 * p;
-		er[p] = -1; ec[p] = 0;
-		if (e < D) { er[p] = e; ec[p] = -1; }
-		else if (e < NE) {
-			int t = e - D, r = 0;
-			while (t >= D - r) { t -= D - r; ++r; }
-			er[p] = r; ec[p] = r + t;
+			for (int o = 1; o < 32; o <<= 1) {
+				const int t = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += t;
+			}
+			cur[k0 + lane] = run + incl - c;
+			run += __shfl_sync(0xffffffffu, incl, 31);
 		}
 	}
-	for (int k0 = 0; k0 < Kmax; k0 += 32) {
-		const int slot = k0 + warp;
-		double acc[PER];
-#pragma unroll
-		for (int p = 0; p < PER; ++p) acc[p] = 0.0;
-		for (int i0 = 0; i0 < N; i0 += CH) {
-			__syncthreads();
-			for (int t = threadIdx.x; t < CH; t += blockDim.x) {
-				const int i = i0 + t;
-				zs[t] = i < N ? (int)z[(size_t)i * C + chain] : -1;
-			}
-			for (int t = threadIdx.x; t < CH * D; t += blockDim.x) {
-				const int j = t / D, c = t - j * D, i = i0 + j;
-				xs[j][c] = i < N ? X[(size_t)i * D + c] : 0.0f;
-			}
-			__syncthreads();
-			for (int s = 0; s < CH; s += 32) {
-				unsigned m = __ballot_sync(0xffffffffu, zs[s + lane] == slot);
-				while (m) {
-					const int j = s + __ffs(m) - 1;
-					m &= m - 1;
-#pragma unroll
-					for (int p = 0; p < PER; ++p) {
-						if (er[p] >= 0) {
-							const float a = xs[j][er[p]];
-							acc[p] += ec[p] < 0 ? (double)a : (double)a * (double)xs[j][ec[p]];
-						}
-					}
-				}
-			}
+	__syncwarp();
+	int32_t *out = perm + (size_t)chain * N;
+	int znext = lane < N ? (int)z[(size_t)lane * C + chain] : -1;
+	for (int i0 = 0; i0 < N; i0 += 32) {
+		const int i = i0 + lane;
+		const int zz = znext;
+		const int inx = i + 32;
+		znext = inx < N ? (int)z[(size_t)inx * C + chain] : -1; // next batch in flight while this one is placed
+		const unsigned active = __ballot_sync(0xffffffffu, i < N);
+		if (i < N) {
+			const unsigned grp = __match_any_sync(active, zz);
+			const int rank = __popc(grp & ((1u << lane) - 1u));
+			const int base = cur[zz];
+			out[base + rank] = i;
+			__syncwarp(active);
+			if (rank == 0) cur[zz] = base + __popc(grp);
 		}
-		if (slot < Kmax) {
-			double *o = stats + ((size_t)chain * Kmax + slot) * NE;
+		__syncwarp();
+	}
+}
+
+// Sufficient statistics of one (chain, slot) per warp from its member list: lanes stride over the members, each lane
+// keeps sum (x - c) and the upper triangle of sum (x - c)(x - c)^T about the slot's current mean c in fp32 registers
+// (D + D(D+1)/2 of them: the lane-private outer product costs D(D+1)/2 + 2D instructions per MEMBER AND LANE, i.e. 5 warp
+// instructions per member at D = 16 against ~65 for a version that spread one member's entries over the lanes), then the
+// lanes are combined in fp64.
+template <int D>
+__global__ void __launch_bounds__(128) k_suffstats(const float *X, const int32_t *perm, const int *counts, const float *theta, int N,
+		int C, int Kmax, double *stats) {
+	constexpr int NE = D + npb_tri(D);
+	const int lane = threadIdx.x & 31;
+	const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); // (chain, slot)
+	if (idx >= C * Kmax) return;
+	const int chain = idx / Kmax, slot = idx - chain * Kmax;
+	const int n = counts[idx];
+	double *o = stats + (size_t)idx * NE;
+	if (n <= 0) return;
+	int off = 0;
+	for (int k = lane; k < slot; k += 32) off += counts[(size_t)chain * Kmax + k];
 #pragma unroll
-			for (int p = 0; p < PER; ++p)
-				if (lane + 32 * p < NE) o[lane + 32 * p] = acc[p];
+	for (int s = 16; s > 0; s >>= 1) off += __shfl_xor_sync(0xffffffffu, off, s);
+	const int32_t *mem = perm + (size_t)chain * N + off;
+	float cen[D], acc[NE];
+	{
+		const float *th = theta + (size_t)idx * npb_ps(D);
+#pragma unroll
+		for (int r = 0; r < D; ++r) cen[r] = th[r];
+	}
+#pragma unroll
+	for (int e = 0; e < NE; ++e) acc[e] = 0.0f;
+	int item_next = lane < n ? mem[lane] : 0;
+	for (int t = lane; t < n; t += 32) {
+		const float *row = X + (size_t)item_next * D;
+		if (t + 32 < n) item_next = mem[t + 32]; // the next member's index is in flight while this row is used
+		float d[D];
+		if constexpr (D % 4 == 0) {
+#pragma unroll
+			for (int r = 0; r < D; r += 4) {
+				const float4 v = __ldg(reinterpret_cast<const float4 *>(row + r));
+				d[r] = v.x - cen[r]; d[r + 1] = v.y - cen[r + 1]; d[r + 2] = v.z - cen[r + 2]; d[r + 3] = v.w - cen[r + 3];
+			}
+		} else {
+#pragma unroll
+			for (int r = 0; r < D; ++r) d[r] = __ldg(row + r) - cen[r];
 		}
+		int e = D;
+#pragma unroll
+		for (int r = 0; r < D; ++r) {
+			acc[r] += d[r];
+#pragma unroll
+			for (int c = r; c < D; ++c, ++e) acc[e] = fmaf(d[r], d[c], acc[e]);
+		}
+	}
+#pragma unroll
+	for (int e = 0; e < NE; ++e) {
+		double v = (double)acc[e];
+#pragma unroll
+		for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+		if (lane == 0) o[e] = v;
 	}
 }
 
@@ -130,12 +175,19 @@ __global__ void k_niw_update(const double *stats, const int *counts, float *thet
 	const double *st = stats + (size_t)idx * NE;
 	double xbar[D], A[D][D];
 	const double dn = (double)n;
-	for (int r = 0; r < D; ++r) xbar[r] = st[r] / dn;
 	{
+		// the statistics were taken about the slot's current mean (k_suffstats): st[r] = sum (x_r - c_r),
+		// st[(r,c)] = sum (x_r - c_r)(x_c - c_c)
+		const float *cen = theta + (size_t)idx * PS;
+		double off[D];
+		for (int r = 0; r < D; ++r) {
+			off[r] = st[r] / dn;
+			xbar[r] = (double)cen[r] + off[r];
+		}
 		int e = D;
 		for (int r = 0; r < D; ++r)
 			for (int c = r; c < D; ++c, ++e) {
-				const double s = st[e] - dn * xbar[r] * xbar[c]; // scatter about the mean
+				const double s = st[e] - dn * off[r] * off[c]; // scatter about the members' mean
 				A[r][c] = s;
 				A[c][r] = s;
 			}
@@ -233,8 +285,17 @@ static npb_status update_params_d(npb_chains *ch, int mode, const ParamsPrior &p
 	if (!ch->pstats) NPB_CUDA_OK(cudaMalloc((void **)&ch->pstats, (size_t)C * Kmax * NE * sizeof(double)));
 	if (!ch->pfail) NPB_CUDA_OK(cudaMalloc((void **)&ch->pfail, sizeof(int)));
 	NPB_CUDA_OK(cudaMemsetAsync(ch->pfail, 0, sizeof(int), ctx->stream));
-	k_suffstats<D><<<C, 1024, 0, ctx->stream>>>(ch->ds->X32, ch->z, N, C, Kmax, ch->pstats);
-	NPB_CUDA_OK(cudaGetLastError());
+	if (!ch->sm_pool) NPB_CUDA_OK(cudaMalloc((void **)&ch->sm_pool, (size_t)N * C * sizeof(int32_t))); // shared with split-merge
+	{
+		const int warps = 4;
+		k_member_lists<<<(C + warps - 1) / warps, warps * 32, (size_t)warps * Kmax * sizeof(int), ctx->stream>>>(ch->z, ch->counts, N, C,
+				Kmax, ch->sm_pool);
+		NPB_CUDA_OK(cudaGetLastError());
+		const int total_w = C * Kmax;
+		k_suffstats<D><<<(total_w + warps - 1) / warps, warps * 32, 0, ctx->stream>>>(ch->ds->X32, ch->sm_pool, ch->counts, ch->theta, N,
+				C, Kmax, ch->pstats);
+		NPB_CUDA_OK(cudaGetLastError());
+	}
 	const int total = C * Kmax;
 	k_niw_update<D><<<(total + 63) / 64, 64, 0, ctx->stream>>>(ch->pstats, ch->counts, ch->theta, C, Kmax, pr, mode, ch->seed,
 			ch->param_epoch++, ch->pfail);
