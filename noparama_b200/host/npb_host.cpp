@@ -115,6 +115,12 @@ void SplitMergeAlgorithm::printStatistics() {
 	}
 }
 
+void UpdateClusters::update(membertrix &cluster_matrix, int) {
+	if (!fix_) return; // the reference's update changes no parameter
+	dev_.check(npb_chains_update_params(cluster_matrix.chains, NPB_UPDATE_POSTERIOR_DRAW, nullptr, 0.0, 0.0, nullptr));
+	cluster_matrix.invalidate();
+}
+
 MCMC::MCMC(device &dev, dirichlet_process &hyper, UpdateClusterPopulation &ucp, int64_t chains, int Kmax, int K0, int m_aux, uint64_t seed)
 	: dev_(dev), hyper_(hyper), ucp_(ucp), chains_(chains), Kmax_(Kmax), K0_(K0), m_aux_(m_aux), seed_(seed) {}
 MCMC::~MCMC() {
@@ -124,7 +130,7 @@ MCMC::~MCMC() {
 	}
 }
 
-void MCMC::run(dataset_t &dataset, int T, bool per_item_seam) {
+void MCMC::run(dataset_t &dataset, int T, bool per_item_seam, UpdateClusters *update_clusters) {
 	const Suffies_NormalInvWishart &niw = hyper_.getSuffies();
 	if (!trix_) {
 		trix_ = new membertrix(dev_, dataset, niw.D);
@@ -133,6 +139,14 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam) {
 		dev_.check(npb_chains_create(dev_.ctx(), trix_->dataset_handle(), chains_, Kmax_, m_aux_, K0_, seed_, &trix_->chains));
 	}
 	const int N = trix_->size();
+	const bool upd = update_clusters && update_clusters->fixes_q1();
+	if (upd && !per_item_seam) { // np_mcmc.cpp:109-175 with a working parameter update: sweep, then UpdateClusters::update
+		for (int t = 0; t < T; ++t) {
+			ucp_.sweep(*trix_, 1);
+			update_clusters->update(*trix_, 20);
+		}
+		return;
+	}
 	if (per_item_seam) {
 		// the reference's own loop shape (np_mcmc.cpp:109-163): one update() per subset of subset_count items
 		const int sc = ucp_.subset_count();
@@ -141,6 +155,7 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam) {
 				data_ids_t subset(sc);
 				for (int j = 0; j < sc; ++j) subset[j] = (i + j * 7919) % N; // placeholders: the device draws the real subsets
 				ucp_.update(*trix_, subset);
+				if (upd && i == N - 1) update_clusters->update(*trix_, 20); // np_mcmc.cpp:170
 			}
 	} else {
 		ucp_.sweep(*trix_, T);

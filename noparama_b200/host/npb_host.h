@@ -171,6 +171,21 @@ public:
 	TriadicAlgorithm(device &dev, dirichlet_process &nonparametrics) : SplitMergeAlgorithm(dev, nonparametrics, NPB_TRIADIC, 3) {}
 };
 
+// UpdateClusters (include/np_update_clusters.h, src/np_update_clusters.cpp:71-141), called after every sweep
+// (np_mcmc.cpp:170).  In the reference its result is sliced away (np_cluster.h:49-51): parameters never change,
+// so the default here is the same no-op; with fix_q1 the parameters of every cluster are redrawn from the conjugate
+// normal-inverse-Wishart posterior of its members on the device (npb_chains_update_params).
+class UpdateClusters {
+public:
+	UpdateClusters(device &dev, dirichlet_process &nonparametrics, bool fix_q1 = false) : dev_(dev), hyper_(nonparametrics), fix_(fix_q1) {}
+	void update(membertrix &cluster_matrix, int number_mh_steps);
+	bool fixes_q1() const { return fix_; }
+private:
+	device &dev_;
+	dirichlet_process &hyper_;
+	bool fix_;
+};
+
 struct clustering_scores { // src/clustering_performance.cpp:38-82
 	std::vector<double> purity, rand_index, adjusted_rand, joint_loglik;
 	std::vector<int32_t> K;
@@ -182,7 +197,7 @@ public:
 	MCMC(device &dev, dirichlet_process &hyper, UpdateClusterPopulation &update_cluster_population, int64_t chains = 1,
 			int Kmax = 256, int K0 = 20, int m_aux = 3, uint64_t seed = 20261018);
 	~MCMC();
-	void run(dataset_t &dataset, int T, bool per_item_seam = false);
+	void run(dataset_t &dataset, int T, bool per_item_seam = false, UpdateClusters *update_clusters = nullptr);
 	membertrix &getMembershipMatrix() { return *trix_; }                  // np_mcmc.h:88
 	clustering_scores scores(const std::vector<int> &ground_truth);        // np_results.cpp:17-37 + clustering_performance
 	int64_t chains() const { return chains_; }

@@ -1,5 +1,5 @@
 // npb_main.cpp -- the reference's command line (src/np_main.cpp:187-267) on top of the device path:
-//   noparama_b200 -d <datafile> -a <algorithm8|jain_neal_split|triadic> -T <sweeps> -c clustering [--chains C] [--seed S] [--kmax K] [--seam]
+//   noparama_b200 -d <datafile> -a <algorithm8|jain_neal_split|triadic> -T <sweeps> -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1]
 // -d  text file, one item per line: D coordinates then the ground-truth label (the reference reads exactly 2 + 1
 //     columns, np_main.cpp:93-101; here D = columns - 1 <= 3 for the register kernel, 4/8/16 for the tile kernel)
 // -a  algorithm8 | jain_neal_split | triadic (np_main.cpp:228-238)
@@ -19,7 +19,7 @@
 using namespace npb;
 
 static void usage() {
-	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam]\n";
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1]\n";
 }
 
 int main(int argc, char **argv) {
@@ -27,7 +27,7 @@ int main(int argc, char **argv) {
 	int T = 2000, kmax = 256;
 	long long chains = 1;
 	unsigned long long seed = 20261018ull;
-	bool seam = false;
+	bool seam = false, fix_q1 = false;
 	for (int i = 1; i < argc; ++i) {
 		std::string a = argv[i];
 		auto next = [&](const char *what) -> const char * {
@@ -42,6 +42,7 @@ int main(int argc, char **argv) {
 		else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
 		else if (a == "--kmax") kmax = atoi(next("--kmax"));
 		else if (a == "--seam") seam = true;
+		else if (a == "--fix-q1") fix_q1 = true;
 		else if (a == "-h" || a == "-?") { usage(); return 0; }
 		else { std::cerr << "unknown option " << a << std::endl; usage(); return 1; }
 	}
@@ -90,7 +91,8 @@ int main(int argc, char **argv) {
 				: (algorithm == "jain_neal_split" ? (UpdateClusterPopulation &)jain_neal : (UpdateClusterPopulation &)triadic);
 		MCMC mcmc(dev, hyper, sampler, chains, kmax, 20, 3, seed);
 		std::cout << "Run MCMC for " << T << " steps, " << chains << " chain(s)" << std::endl;
-		mcmc.run(dataset, T, seam);
+		UpdateClusters update_clusters(dev, hyper, fix_q1); // np_main.cpp:415
+		mcmc.run(dataset, T, seam, &update_clusters);
 		sampler.printStatistics();
 		clustering_scores sc = mcmc.scores(ground_truth);
 		auto mean = [](const std::vector<double> &v) { return std::accumulate(v.begin(), v.end(), 0.0) / v.size(); };

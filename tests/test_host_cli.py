@@ -84,3 +84,16 @@ def test_cli_runs_split_merge(tmp_path, algorithm):
         assert ("merge from 3 to 2 attempts" in r.stdout) == (algorithm == "triadic")
         assert re.search(r"^Purity: ([0-9.]+)", r.stdout, re.M)
     assert outs[0] == outs[1]  # per-subset seam (np_mcmc.cpp:162) and batched sweeps: same trajectory
+
+
+@pytest.mark.gpu
+def test_cli_fix_q1_refits_parameters(tmp_path):
+    """--fix-q1: UpdateClusters::update (np_mcmc.cpp:170) with a working parameter update (conjugate NIW posterior draw)."""
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "60", "-c", "clustering", "--chains", "32", "--kmax", "64",
+                        "--seed", "3", "--fix-q1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pur = float(re.search(r"chains: purity ([0-9.]+)", r.stdout).group(1))
+    assert pur > 0.95
