@@ -224,3 +224,34 @@ def test_split_merge_distribution_matches_oracle_256_seeds(npb, ctx, sampler_nam
         assert abs(m["purity"].mean() - g["purity"].mean()) < 0.01
     ch.close()
     ds.close()
+
+
+@pytest.mark.parametrize("sampler_name", ["jain_neal", "triadic"])
+def test_split_merge_full_size_properties_config3(npb, ctx, sampler_name):
+    """BASELINE configs[2] shape (16-D, 32 components, N = 100 000) at a reduced chain count: size-independent
+    properties of a prefix of a sweep -- bookkeeping invariants, conservation of the items, rejected proposals leave the
+    state untouched, idempotent readback."""
+    sampler = {"jain_neal": npb.JAIN_NEAL, "triadic": npb.TRIADIC}[sampler_name]
+    X, y = syn.config(3)
+    K = int(y.max()) + 1
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(16)).bind(ctx)
+    ch = npb.Chains(ctx, ds, 24, Kmax=64, seed=6)
+    means = np.stack([X[y == k].mean(0) for k in range(K)])
+    ch.init_from_params(means, np.tile(np.eye(16), (K, 1, 1)))
+    ch.sweep(npb.ALG8, 1)
+    zb = ch.assignments()
+    st = ch.split_merge(sampler, 12)
+    assert st.overflow_chains == 0 and 0 < st.reassignments <= 24 * 12
+    assert sum(st.sm_attempts) == st.reassignments
+    za = ch.assignments()
+    for c in range(24):
+        check_state(ch, za[c], c, ds.N)
+    if sum(st.sm_accepts) == 0:
+        # well separated unit-variance clusters: merging two of them or splitting one with a prior draw is rejected
+        assert np.array_equal(za, zb)
+    m = ch.metrics(y)
+    assert np.array_equal(m["K"], [len(np.unique(za[c])) for c in range(24)])
+    assert np.array_equal(ch.assignments(), za)
+    ch.close()
+    ds.close()

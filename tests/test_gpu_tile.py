@@ -139,3 +139,29 @@ def test_tile4_kernel_distribution_and_birth_rate_4d(npb, ctx, oracle):
     assert abs(births - res[:, 3].mean()) < 0.05 * res[:, 3].mean() + 1e-5
     assert abs(moved - res[:, 4].mean()) < 0.05 * res[:, 4].mean() + 1e-4
     ds.close()
+
+
+def test_full_size_properties_config5_shard(npb, ctx):
+    """BASELINE configs[4] per-GPU shard shape (16-D, N = 100 000, Kmax 32) at a reduced chain count: size-independent
+    properties -- every chain keeps its bookkeeping consistent, the given well-separated clusters are recovered exactly,
+    counters add up, readback and metrics are idempotent, a second sweep moves (almost) nothing."""
+    X, y = syn.config(5)
+    K = int(y.max()) + 1
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(16)), chains=44, Kmax=32, seed=12)
+    means = np.stack([X[y == k].mean(0) for k in range(K)])
+    mc.chains.init_from_params(means, np.tile(np.eye(16), (K, 1, 1)))
+    s1 = mc.chains.sweep(npb.ALG8, 1)
+    s2 = mc.chains.sweep(npb.ALG8, 1)
+    assert s1.overflow_chains == 0 and s1.reassignments == 44 * 100000 == s2.reassignments
+    assert s1.candidates == 35 * s1.reassignments == s2.candidates     # 32 occupied clusters + 3 auxiliary draws, every step
+    assert s1.moved > 0.9 * s1.reassignments and s2.moved < 1e-4 * s2.reassignments
+    z = mc.getMembershipMatrix(0, 3)
+    for c in range(3):
+        invariants(mc.chains, z[c], c, ds.N)
+    m = mc.chains.metrics(y)
+    assert np.all(m["K"] == K) and m["purity"].min() > 0.9999 and m["adjusted_rand"].min() > 0.9999
+    assert np.array_equal(mc.getMembershipMatrix(0, 3), z)
+    m2 = mc.chains.metrics(y)
+    assert np.array_equal(m["joint_loglik"], m2["joint_loglik"])
+    ds.close()
