@@ -27,8 +27,8 @@
 #include "npb_internal.h"
 #include "npb_alg8_kernel.cuh"
 
-#define SM_THREADS 256
-#define SM_MB 4                      // members per thread per chunk (register blocking of the theta reads)
+#define SM_THREADS 64
+#define SM_MB 2                      // members per thread per chunk (register blocking of the theta reads)
 #define SM_CHUNK (SM_THREADS * SM_MB) // pool members per chunk
 
 enum { SM_JN_SPLIT = 0, SM_JN_MERGE = 1, SM_TRI_SPLIT = 2, SM_TRI_MERGE = 3 };
@@ -119,7 +119,7 @@ __device__ __forceinline__ double sm_block_sum(double v, double *red /* [SM_THRE
 }
 
 template <int D>
-__global__ void __launch_bounds__(SM_THREADS) k_split_merge(SMArgs a) {
+__global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 	constexpr int PS = npb_ps(D);
 	__shared__ float s_th[3][PS + 3];
 	__shared__ float s_ld[3][SM_CHUNK];
@@ -384,22 +384,33 @@ __global__ void __launch_bounds__(SM_THREADS) k_split_merge(SMArgs a) {
 							npart[0] += d == 0; npart[1] += d == 1; npart[2] += d == 2;
 							sams++;
 						}
-						const float g0 = __shfl_sync(0xffffffffu, l0, j), g1 = __shfl_sync(0xffffffffu, l1, j);
-						const float g2 = __shfl_sync(0xffffffffu, l2, j);
-#pragma unroll
-						for (int q = 0; q < 3; ++q)
-							if (d == q) {
-								S[q][0] += (double)g0; S[q][1] += (double)g1;
-								if (p.nth > 2) S[q][2] += (double)g2;
-							}
 						if (lane == j) mydec = d;
 					}
-					if (ok) dec[t0 + my] = (uint8_t)mydec;
+					// the likelihood sums of the acceptance ratio: every lane adds ITS member's log-densities to the part
+					// that member went to (lane-private partial sums, combined after the last chunk) -- one step per 32
+					// members instead of one per member on the sequential path
+					if (ok) {
+#pragma unroll
+						for (int q = 0; q < 3; ++q)
+							if (mydec == q) {
+								S[q][0] += (double)l0; S[q][1] += (double)l1;
+								if (p.nth > 2) S[q][2] += (double)l2;
+							}
+						dec[t0 + my] = (uint8_t)mydec;
+					}
 				}
 			}
 			__syncthreads();
 		}
 		// ---------------- acceptance ----------------
+		if (warp == 0) { // lane-private partial sums of phase B -> every lane of warp 0 holds the totals
+#pragma unroll
+			for (int q = 0; q < 3; ++q)
+#pragma unroll
+				for (int k = 0; k < 3; ++k)
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) S[q][k] += __shfl_xor_sync(0xffffffffu, S[q][k], o);
+		}
 		double ownsum[3], q1sum[3];
 		for (int k = 0; k < 3; ++k) {
 			ownsum[k] = sm_block_sum(own[k], s_red);
