@@ -76,7 +76,7 @@ struct TileRegs {          // what lane j holds for step s0 + j of the current t
 	float auxkey;          // max_m [ log2 p(x|theta'_m) alpha/M - log2 E_m ]
 	float av[M];
 	float g[NG];
-	uint32_t rs[4];        // xoshiro128++ state of this lane for the tile's race noise (seeded from Philox per tile)
+	uint32_t rs[4];        // rs[0]: LCG state of this lane for the tile's race noise (seeded from a Philox block per tile)
 };
 
 template <int NL>
@@ -134,7 +134,15 @@ __device__ __forceinline__ void stage_a(const SweepState<D, SPL, M> &S, TileRegs
 			for (int c = r + 1; c < D; ++c) y = fmaf(S.T[s][npb_tri_off(D, r, c)], dd[c], y);
 			q = fmaf(y, y, q);
 		}
-		o.base[s] = (S.c2[s] - q) + neg_lg2_exp1(xoshiro_next(t.rs));
+		// race noise: one 32-bit LCG per lane (Numerical Recipes multiplier; the float conversion keeps the top 24 bits of
+		// the state), re-seeded from a Philox block every tile -- a stream is at most 32 * levels draws long.  xoshiro128++
+		// was 9 of the ~29 instructions a candidate level costs at D = 2; the clamp of neg_lg2_exp1 is dropped too
+		// (E' = 0, probability 2^-25, is a certain win, which is what an exponential that small means).
+		t.rs[0] = t.rs[0] * 1664525u + 1013904223u;
+		{
+			const float omv = fmaf(__uint2float_rn(t.rs[0]), -2.3283064365386963e-10f, 1.0f - 2.3283064365386963e-10f);
+			o.base[s] = (S.c2[s] - q) - fast_lg2(-fast_lg2(omv));
+		}
 	}
 }
 
