@@ -46,6 +46,12 @@ __device__ __forceinline__ float neg_lg2_exp1_open(uint32_t r) {
 	return -fast_lg2(-fast_lg2(omv));
 }
 
+__device__ __forceinline__ float redux_max_f32(float v) {
+	float r;
+	asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+	return r;
+}
+
 // Packed FP32 (sm_100a FFMA2): one instruction does two FMAs, on a 64-bit register pair; an operand written as
 // {t, t} is encoded as a broadcast of the 32-bit register t (SASS "R.F32"), so the slot's parameters are not duplicated.
 // The producer evaluates TWO items per instruction stream: pair = (item 2p, item 2p+1).
@@ -373,15 +379,11 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 			const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
 			int znew = zold;
 			// race noise of the tile: one 32-bit LCG per lane (Knuth's multiplier; the top 24 bits of the state are what the
-			// float conversion keeps), re-seeded from a Philox block every tile, so a stream is 33 draws long.  The
+			// float conversion keeps), re-seeded every tile from a hash of the chain's key and the counters, so a stream is 33
+			// draws long.  The
 			// consumer's instruction count is what bounds a chain once the producers run packed FP32: xoshiro128++ was 9
 			// of its ~64 instructions per step, this is 1.
-			uint32_t rs;
-			{
-				uint32_t w[4];
-				ph((uint32_t)sj, 0u, sweep, NPB_RNG_PICK, w);
-				rs = w[0] ^ (w[1] << 1);
-			}
+			uint32_t rs = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)sj * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
 			const int cnt = min(NPB_TILE, N - s0);
 
 			// race key of the best of this step's M auxiliary draws and which draw it was (k_aux_keys, the state-independent
@@ -423,9 +425,9 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 				}
 				const float lg = (zo == lane) ? lgn1 : lgn;
 				const float key = lg > -INFINITY ? base + lg : -INFINITY; // a slot without (other) members never wins
-				const int my_enc = float_order_key(key);
-				const int top = max(__reduce_max_sync(0xffffffffu, my_enc), float_order_key(ak));
-				const unsigned bal = __ballot_sync(0xffffffffu, my_enc == top && key > -INFINITY);
+				// warp arg-max with the floating-point warp reduction of sm_100a (redux.sync.max.f32 -> CREDUX.MAX.F32)
+				const float top = fmaxf(redux_max_f32(key), ak);
+				const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
 				cand_tile += (unsigned)(kocc + M);
 				int new_slot;
 				bool born = false;
