@@ -158,6 +158,21 @@ npb_status npb_replay_alg8(npb_ctx *ctx, npb_dataset *ds, int m_aux, int nslots,
 		const int64_t *order_off, const int32_t *order, const double *aux_mu, const double *aux_Sigma,
 		const double *u, const int32_t *new_slot, int32_t *picked_out, int64_t z_every, int32_t *z_after_out);
 
+/* parity level 2 for the split-merge samplers: replay a recorded run of JainNealAlgorithm::update
+ * (np_jain_neal_algorithm.cpp:424-502) or TriadicAlgorithm::update (np_triadic_algorithm.cpp:633-795) in double precision
+ * with the reference's own weights and picks.  Initial state as in npb_replay_alg8.  Per proposal p < n_prop: the subset
+ * picks [n_prop,3] (-1 pad) MCMC::run handed over, u0 (the triadic sampler's first uniform), the prior draw of a split
+ * (new_mu [n_prop,D], new_Sigma [n_prop,D,D]), the pool pool[pool_off[p] .. pool_off[p+1]) in the visiting order the
+ * reference shuffled it into with the uniform each allocation consumed (us, < 0 for a pick that seeded its part), the
+ * acceptance uniform uacc and the slot new_slot a cluster born by an accepted split takes.  Outputs: the move type the
+ * device derived (0 JN split, 1 JN merge, 2 triadic split, 3 triadic merge), the part every pool member was allocated to,
+ * accept, log acceptance ratio, and the assignments after the last proposal. */
+npb_status npb_replay_split_merge(npb_ctx *ctx, npb_dataset *ds, int sampler, int nslots, const int32_t *z0, int K0,
+		const int32_t *slots0, const double *mu0, const double *Sigma0, int64_t n_prop, const int32_t *picks, const double *u0,
+		const double *new_mu, const double *new_Sigma, const int64_t *pool_off, const int32_t *pool, const double *us,
+		const double *uacc, const int32_t *new_slot, int32_t *type_out, int32_t *dec_out, int32_t *accept_out, double *logA_out,
+		int32_t *z_final_out);
+
 /* state readback: replaces membertrix::getClusterId / getClusters / count (membertrix.cpp:235-257,328-330) */
 npb_status npb_chains_get_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out /* [n,N] slot ids */);
 npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts,

@@ -28,7 +28,7 @@ EXPORTS = [
     "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
-    "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params",
+    "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library():
     L.npb_chain_update_alg8.argtypes = [vp, i64, i64]
     L.npb_replay_alg8.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp, i64, ip, C.POINTER(i64), ip, dp, dp,
                                   dp, ip, ip, i64, ip]
+    L.npb_replay_split_merge.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp, i64, ip, dp, dp, dp,
+                                         C.POINTER(i64), ip, dp, dp, ip, ip, ip, ip, dp, ip]
     L.npb_chains_get_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -254,6 +256,31 @@ def replay_alg8(ctx, dataset, trace, init_state, m_aux=3, z_every=None):
                                        _dp(aux_mu), _dp(aux_Sigma), _dp(u), _ip(new_slot), _ip(picked), z_every,
                                        _ip(z_after)))
     return picked, z_after
+
+
+def replay_split_merge(ctx, dataset, sampler, trace, init_state):
+    """Parity level 2 for the split-merge samplers (npb_replay_split_merge): replay the oracle's recorded run
+    (oracle/binding.py Run.sm_trace()) in double precision.  Returns dict(type, dec, accept, logA, z_final)."""
+    z0, slots, mu, Sigma = init_state
+    z0 = np.ascontiguousarray(z0, dtype=np.int32)
+    slots = np.ascontiguousarray(slots, dtype=np.int32)
+    mu, Sigma = _f64(mu), _f64(Sigma)
+    n = len(trace["type"])
+    picks = np.ascontiguousarray(trace["picks"], dtype=np.int32)
+    u0, th_mu, th_sigma = _f64(trace["u0"]), _f64(trace["th_mu"]), _f64(trace["th_sigma"])
+    off = np.ascontiguousarray(trace["pool_off"], dtype=np.int64)
+    pool = np.ascontiguousarray(trace["pool"], dtype=np.int32)
+    us, uacc = _f64(trace["us"]), _f64(trace["uacc"])
+    new_slot = np.ascontiguousarray(trace["new_slot"], dtype=np.int32)
+    nslots = int(max(trace.get("max_slot", 0), slots.max() + 1, new_slot.max() + 1))
+    out = dict(type=np.empty(n, np.int32), dec=np.empty(len(pool), np.int32), accept=np.empty(n, np.int32),
+               logA=np.empty(n), z_final=np.empty(dataset.N, np.int32))
+    ctx.check(ctx._lib.npb_replay_split_merge(ctx._h, dataset._h, sampler, nslots, _ip(z0), len(slots), _ip(slots), _dp(mu),
+                                              _dp(Sigma), n, _ip(picks), _dp(u0), _dp(th_mu), _dp(th_sigma),
+                                              off.ctypes.data_as(C.POINTER(C.c_int64)), _ip(pool), _dp(us), _dp(uacc),
+                                              _ip(new_slot), _ip(out["type"]), _ip(out["dec"]), _ip(out["accept"]),
+                                              _dp(out["logA"]), _ip(out["z_final"])))
+    return out
 
 
 class Chains:

@@ -746,3 +746,108 @@ npb_status npb_replay_alg8(npb_ctx *ctx, npb_dataset *ds, int m_aux, int nslots,
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// split-merge replay (npb_replay_sm.cu)
+// ---------------------------------------------------------------------------------------------------------------------
+npb_status npb_launch_replay_sm(npb_ctx *ctx, const RsmArgs &a);
+
+// theta in the split-merge replay layout: mu[D], T upper packed, c, cst = sqrt((2 pi)^D det Sigma)
+static bool pack_theta64r(int D, const double *mu, const double *Sigma, double *out) {
+	const int TRI = npb_tri(D);
+	double logdet;
+	if (!npb_prepare_theta(D, mu, Sigma, out + D, &logdet)) return false;
+	for (int d = 0; d < D; ++d) out[d] = mu[d];
+	out[D + TRI] = -0.5 * (D * std::log(2.0 * M_PI) + logdet);
+	out[D + TRI + 1] = std::exp(0.5 * (D * std::log(2.0 * M_PI) + logdet));
+	return true;
+}
+
+npb_status npb_replay_split_merge(npb_ctx *ctx, npb_dataset *ds, int sampler, int nslots, const int32_t *z0, int K0,
+		const int32_t *slots0, const double *mu0, const double *Sigma0, int64_t n_prop, const int32_t *picks, const double *u0,
+		const double *new_mu, const double *new_Sigma, const int64_t *pool_off, const int32_t *pool, const double *us,
+		const double *uacc, const int32_t *new_slot, int32_t *type_out, int32_t *dec_out, int32_t *accept_out, double *logA_out,
+		int32_t *z_final_out) {
+	if (!ctx || !ds || ds->ctx != ctx || !z0 || !slots0 || !mu0 || !Sigma0 || !picks || !u0 || !new_mu || !new_Sigma || !pool_off ||
+			!pool || !us || !uacc || !new_slot || !type_out || !dec_out || !accept_out || !logA_out || nslots <= 0 || K0 <= 0 ||
+			K0 > nslots || n_prop <= 0 || (sampler != NPB_JAIN_NEAL && sampler != NPB_TRIADIC))
+		return NPB_E_BAD_ARG;
+	if (!ctx->prior.set || ctx->prior.D != ds->D) return npb_fail(ctx, NPB_E_BAD_ARG, "set a prior of the dataset's dimension first");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ds->D, PSR = npb_ps(D) + 1, N = (int)ds->N;
+	const int nsub = sampler == NPB_JAIN_NEAL ? 2 : 3;
+	std::vector<double> theta((size_t)nslots * PSR, 0.0);
+	std::vector<int> counts(nslots, 0);
+	for (int k = 0; k < K0; ++k) {
+		if (slots0[k] < 0 || slots0[k] >= nslots) return NPB_E_BAD_ARG;
+		if (!pack_theta64r(D, mu0 + (size_t)k * D, Sigma0 + (size_t)k * D * D, theta.data() + (size_t)slots0[k] * PSR))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "initial Sigma not invertible");
+	}
+	for (int i = 0; i < N; ++i) {
+		if (z0[i] < 0 || z0[i] >= nslots) return NPB_E_BAD_ARG;
+		counts[z0[i]]++;
+	}
+	const int64_t L = pool_off[n_prop];
+	for (int64_t p = 0; p < n_prop; ++p) {
+		if (pool_off[p + 1] < pool_off[p]) return NPB_E_BAD_ARG;
+		for (int j = 0; j < nsub; ++j)
+			if (picks[p * 3 + j] < 0 || picks[p * 3 + j] >= N) return NPB_E_BAD_ARG;
+	}
+	for (int64_t t = 0; t < L; ++t)
+		if (pool[t] < 0 || pool[t] >= N) return NPB_E_BAD_ARG;
+	std::vector<double> thn((size_t)n_prop * PSR);
+	for (int64_t p = 0; p < n_prop; ++p)
+		if (!pack_theta64r(D, new_mu + (size_t)p * D, new_Sigma + (size_t)p * D * D, thn.data() + (size_t)p * PSR))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "a recorded prior draw has a singular Sigma");
+	DevBuf<double> d_theta, d_thn, d_u0, d_us, d_uacc, d_logA;
+	DevBuf<int> d_counts, d_status;
+	DevBuf<int32_t> d_z, d_picks, d_pool, d_new, d_type, d_dec, d_acc;
+	DevBuf<int64_t> d_off;
+	NPB_CUDA_OK(d_theta.alloc(theta.size()));
+	NPB_CUDA_OK(d_thn.alloc(thn.size()));
+	NPB_CUDA_OK(d_u0.alloc(n_prop));
+	NPB_CUDA_OK(d_us.alloc(L));
+	NPB_CUDA_OK(d_uacc.alloc(n_prop));
+	NPB_CUDA_OK(d_logA.alloc(n_prop));
+	NPB_CUDA_OK(d_counts.alloc(nslots));
+	NPB_CUDA_OK(d_status.alloc(1));
+	NPB_CUDA_OK(d_z.alloc(N));
+	NPB_CUDA_OK(d_picks.alloc(n_prop * 3));
+	NPB_CUDA_OK(d_pool.alloc(L));
+	NPB_CUDA_OK(d_new.alloc(n_prop));
+	NPB_CUDA_OK(d_type.alloc(n_prop));
+	NPB_CUDA_OK(d_dec.alloc(L));
+	NPB_CUDA_OK(d_acc.alloc(n_prop));
+	NPB_CUDA_OK(d_off.alloc(n_prop + 1));
+	cudaStream_t st = ctx->stream;
+	int zero = 0;
+	NPB_CUDA_OK(cudaMemcpyAsync(d_theta.p, theta.data(), sizeof(double) * theta.size(), cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_thn.p, thn.data(), sizeof(double) * thn.size(), cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_u0.p, u0, sizeof(double) * n_prop, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_us.p, us, sizeof(double) * L, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_uacc.p, uacc, sizeof(double) * n_prop, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_counts.p, counts.data(), sizeof(int) * nslots, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_status.p, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_z.p, z0, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_picks.p, picks, sizeof(int32_t) * n_prop * 3, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_pool.p, pool, sizeof(int32_t) * L, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_new.p, new_slot, sizeof(int32_t) * n_prop, cudaMemcpyHostToDevice, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_off.p, pool_off, sizeof(int64_t) * (n_prop + 1), cudaMemcpyHostToDevice, st));
+	RsmArgs a;
+	a.X = ds->X64; a.N = N; a.D = D; a.sampler = sampler; a.nslots = nslots; a.alpha = ctx->prior.alpha;
+	a.theta = d_theta.p; a.counts = d_counts.p; a.z = d_z.p; a.n_prop = n_prop; a.picks = d_picks.p; a.u0 = d_u0.p;
+	a.th_new = d_thn.p; a.pool_off = d_off.p; a.pool = d_pool.p; a.us = d_us.p; a.uacc = d_uacc.p; a.new_slot = d_new.p;
+	a.type_out = d_type.p; a.dec_out = d_dec.p; a.accept_out = d_acc.p; a.logA_out = d_logA.p; a.status = d_status.p;
+	npb_status s = npb_launch_replay_sm(ctx, a);
+	if (s != NPB_OK) return s;
+	int status = 0;
+	NPB_CUDA_OK(cudaMemcpyAsync(type_out, d_type.p, sizeof(int32_t) * n_prop, cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(dec_out, d_dec.p, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(accept_out, d_acc.p, sizeof(int32_t) * n_prop, cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(logA_out, d_logA.p, sizeof(double) * n_prop, cudaMemcpyDeviceToHost, st));
+	if (z_final_out) NPB_CUDA_OK(cudaMemcpyAsync(z_final_out, d_z.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	NPB_CUDA_OK(cudaStreamSynchronize(st));
+	if (status != 0) return npb_fail(ctx, (npb_status)status, "split-merge replay left the recorded trajectory");
+	return NPB_OK;
+}

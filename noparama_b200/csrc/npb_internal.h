@@ -86,6 +86,29 @@ struct SweepArgs {
 	PriorDev prior;
 };
 
+// arguments of the split-merge replay kernel (npb_replay_sm.cu)
+struct RsmArgs {
+	const double *X;
+	int N, D, sampler, nslots;
+	double alpha;
+	double *theta;      // [nslots][PSR]
+	int *counts;        // [nslots]
+	int32_t *z;         // [N]
+	int64_t n_prop;
+	const int32_t *picks;   // [n,3]
+	const double *u0;       // [n]
+	const double *th_new;   // [n][PSR]
+	const int64_t *pool_off;
+	const int32_t *pool;
+	const double *us;
+	const double *uacc;
+	const int32_t *new_slot;
+	int32_t *type_out, *dec_out, *accept_out;
+	double *logA_out;
+	int *status;
+};
+
+
 npb_status npb_fail_cuda(npb_ctx *ctx, cudaError_t e, const char *expr, const char *file, int line);
 npb_status npb_fail(npb_ctx *ctx, npb_status s, const char *msg);
 

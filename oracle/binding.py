@@ -87,6 +87,11 @@ def lib():
         L.npo_run_K_after_len.restype = C.c_int64
         L.npo_run_K_after_len.argtypes = [C.c_void_p]
         L.npo_run_K_after.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.npo_sm_trace_proposals.restype = C.c_int64
+        L.npo_sm_trace_proposals.argtypes = [C.c_void_p]
+        L.npo_sm_trace_pool_len.restype = C.c_int64
+        L.npo_sm_trace_pool_len.argtypes = [C.c_void_p]
+        L.npo_sm_trace_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 13
         L.npo_trace_steps.restype = C.c_int64
         L.npo_trace_steps.argtypes = [C.c_void_p]
         L.npo_trace_order_len.restype = C.c_int64
@@ -240,6 +245,24 @@ class Run:
         Sigma = np.empty((K, self.D, self.D))
         lib().npo_run_init_state(self._h, _ip(z0), _ip(slots), _dp(mu), _dp(Sigma))
         return z0, slots, mu, Sigma
+
+    def sm_trace(self):
+        """split-merge replay trace (RECORD_TRACE runs of JAIN_NEAL / TRIADIC), see np_oracle.h"""
+        n = lib().npo_sm_trace_proposals(self._h)
+        L = lib().npo_sm_trace_pool_len(self._h)
+        D = self.D
+        t = dict(picks=np.empty((n, 3), np.int32), u0=np.empty(n), type=np.empty(n, np.int32), th_mu=np.empty((n, D)),
+                 th_sigma=np.empty((n, D, D)), pool_off=np.empty(n + 1, np.int64), pool=np.empty(L, np.int32),
+                 us=np.empty(L), dec=np.empty(L, np.int32), logA=np.empty(n), uacc=np.empty(n),
+                 accept=np.empty(n, np.int32), new_slot=np.empty(n, np.int32))
+        lib().npo_sm_trace_copy(self._h, *[t[k].ctypes.data for k in
+                                           ("picks", "u0", "type", "th_mu", "th_sigma", "pool_off", "pool", "us", "dec",
+                                            "logA", "uacc", "accept", "new_slot")])
+        z = np.empty((self.T, self.N), np.int32)
+        tr = self.trace()
+        t["z_after"] = tr["z_after"]
+        t["max_slot"] = tr["max_slot"]
+        return t
 
     def trace(self):
         S = lib().npo_trace_steps(self._h)

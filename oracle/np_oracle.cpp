@@ -538,6 +538,10 @@ struct npo_run {
 	std::vector<double> tr_aux_mu, tr_aux_sigma, tr_u;
 	std::vector<double> sweep_reassign_seconds, sweep_total_seconds;
 	std::vector<int> K_after_call; /* cluster count after every sampler.update() (RECORD_TRACE) */
+	/* split-merge replay trace (np_oracle_sm.inc: sm_record), one entry per proposal */
+	std::vector<int> sm_picks, sm_type, sm_pool, sm_dec, sm_accept, sm_new_slot;
+	std::vector<double> sm_u0, sm_th_mu, sm_th_sigma, sm_us, sm_logA, sm_uacc;
+	std::vector<int64_t> sm_pool_off{0};
 	/* NOT the reference: initial clusters given by the caller instead of drawn from the prior (bench regime) */
 	std::vector<double> given_mu, given_sigma;
 	/* slot allocator */
@@ -725,6 +729,10 @@ struct Sampler {
 	bool tri_split(const std::vector<int> &picks, std::vector<int> &cluster_ids);
 	bool tri_merge(const std::vector<int> &picks, std::vector<int> &cluster_ids);
 	void tri_update(const std::vector<int> &picks);
+	void sm_record(int type, const Theta *th_new, const std::vector<int> &pool, const std::vector<double> &us,
+			const std::vector<int> &dec, double logA, double u, bool accept, int new_slot);
+	std::vector<int> tri_pool, tri_dec;
+	std::vector<double> tri_us;
 
 	/* MCMC::run (np_mcmc.cpp:48-175) */
 	void mcmc_run() {
@@ -1009,6 +1017,24 @@ void npo_run_sweep_seconds(const npo_run *r, double *reassign, double *total) {
 }
 int64_t npo_run_K_after_len(const npo_run *r) { return (int64_t)r->K_after_call.size(); }
 void npo_run_K_after(const npo_run *r, int *out) { std::copy(r->K_after_call.begin(), r->K_after_call.end(), out); }
+int64_t npo_sm_trace_proposals(const npo_run *r) { return (int64_t)r->sm_type.size(); }
+int64_t npo_sm_trace_pool_len(const npo_run *r) { return (int64_t)r->sm_pool.size(); }
+void npo_sm_trace_copy(const npo_run *r, int *picks, double *u0, int *type, double *th_mu, double *th_sigma, int64_t *pool_off,
+		int *pool, double *us, int *dec, double *logA, double *uacc, int *accept, int *new_slot) {
+	std::copy(r->sm_picks.begin(), r->sm_picks.end(), picks);
+	std::copy(r->sm_u0.begin(), r->sm_u0.end(), u0);
+	std::copy(r->sm_type.begin(), r->sm_type.end(), type);
+	std::copy(r->sm_th_mu.begin(), r->sm_th_mu.end(), th_mu);
+	std::copy(r->sm_th_sigma.begin(), r->sm_th_sigma.end(), th_sigma);
+	std::copy(r->sm_pool_off.begin(), r->sm_pool_off.end(), pool_off);
+	std::copy(r->sm_pool.begin(), r->sm_pool.end(), pool);
+	std::copy(r->sm_us.begin(), r->sm_us.end(), us);
+	std::copy(r->sm_dec.begin(), r->sm_dec.end(), dec);
+	std::copy(r->sm_logA.begin(), r->sm_logA.end(), logA);
+	std::copy(r->sm_uacc.begin(), r->sm_uacc.end(), uacc);
+	std::copy(r->sm_accept.begin(), r->sm_accept.end(), accept);
+	std::copy(r->sm_new_slot.begin(), r->sm_new_slot.end(), new_slot);
+}
 int64_t npo_trace_steps(const npo_run *r) { return (int64_t)r->tr_item.size(); }
 int64_t npo_trace_order_len(const npo_run *r) { return (int64_t)r->tr_order.size(); }
 int npo_trace_max_slot(const npo_run *r) { return (int)r->slot_used.size(); }

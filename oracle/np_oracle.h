@@ -125,6 +125,16 @@ void npo_run_K_after(const npo_run *r, int *out);
 int npo_run_init_K(const npo_run *r);
 void npo_run_init_state(const npo_run *r, int *z0 /*[N] slot ids*/, int *slots /*[K]*/, double *mu /*[K,D]*/, double *Sigma /*[K,D,D]*/);
 
+/* Split-merge replay trace (needs NPO_RECORD_TRACE; Jain-Neal / triadic), one entry per proposal p < n:
+ * picks [n,3] the subset MCMC::run handed to update() (-1 pad), u0 [n] the triadic sampler's first uniform, type [n]
+ * (0 JN split, 1 JN merge, 2 triadic split, 3 triadic merge), th_mu [n,D] / th_sigma [n,D,D] the prior draw of a split,
+ * the pool pool[pool_off[p] .. pool_off[p+1]) in visiting order with us (the uniform an allocation consumed, -1 for a
+ * skipped pick) and dec (the part chosen), logA, the acceptance uniform uacc, accept, and the slot a new cluster got. */
+int64_t npo_sm_trace_proposals(const npo_run *r);
+int64_t npo_sm_trace_pool_len(const npo_run *r);
+void npo_sm_trace_copy(const npo_run *r, int *picks, double *u0, int *type, double *th_mu, double *th_sigma, int64_t *pool_off,
+		int *pool, double *us, int *dec, double *logA, double *uacc, int *accept, int *new_slot);
+
 /* Alg. 8 replay trace.  steps = T*N. All cluster references are SLOT ids. */
 int64_t npo_trace_steps(const npo_run *r);
 int64_t npo_trace_order_len(const npo_run *r);

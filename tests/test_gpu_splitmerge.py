@@ -255,3 +255,30 @@ def test_split_merge_full_size_properties_config3(npb, ctx, sampler_name):
     assert np.array_equal(ch.assignments(), za)
     ch.close()
     ds.close()
+
+
+@pytest.mark.parametrize("sampler_name,seed", [("jain_neal", 1), ("jain_neal", 2), ("triadic", 1), ("triadic", 2)])
+def test_split_merge_replay_bit_exact_config1(npb, ctx, oracle, sampler_name, seed):
+    """Parity level 2: config 1 with the oracle's recorded draws (subsets, prior draws, shuffled pools, every uniform)
+    replayed in double precision on the device.  The oracle run itself is pinned proposal by proposal to the reference's
+    own code (tests/test_ref_pin.py).  The device must derive the same move types, allocate every pool member to the same
+    part, accept and reject the same proposals and end with identical assignments."""
+    alg = {"jain_neal": oracle.JAIN_NEAL, "triadic": oracle.TRIADIC}[sampler_name]
+    sampler = {"jain_neal": npb.JAIN_NEAL, "triadic": npb.TRIADIC}[sampler_name]
+    X, _ = syn.config(1)
+    T = 60
+    run = oracle.Run(oracle.make_prior(**syn.reference_prior(2)), X, alg, T=T, seed_main=40 + seed, seed_shuffle=50 + seed,
+                     flags=oracle.RECORD_TRACE | oracle.UPDATE_CLUSTERS)
+    t = run.sm_trace()
+    n = len(t["type"])
+    assert n == run.stats().updates and t["accept"].sum() > 20
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(2)).bind(ctx)
+    out = npb.replay_split_merge(ctx, ds, sampler, t, run.init_state())
+    assert np.array_equal(out["type"], t["type"])
+    assert np.array_equal(out["dec"], t["dec"])
+    assert np.array_equal(out["accept"], t["accept"])
+    assert np.array_equal(out["z_final"], t["z_after"][-1])
+    fin = np.isfinite(t["logA"])
+    assert np.allclose(out["logA"][fin], t["logA"][fin], rtol=1e-9, atol=1e-7)
+    ds.close()
