@@ -184,6 +184,14 @@ npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K,
 npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *purity, double *rand_index,
 		double *adjusted_rand, double *joint_loglik, int32_t *K);
 
+/* MCMC::considerMaxLikelihood (np_mcmc.cpp:187-203) for every chain: the joint log-likelihood of the current state is
+ * compared with that of the state kept so far, and chains that improved copy their assignments, parameters and counts into
+ * the kept state (the reference deep-clones its membertrix).  joint_loglik_out / best_out [n_chains] may be NULL.
+ * npb_chains_get_best_assignments reads the kept assignments back like npb_chains_get_assignments
+ * (MCMC::getMaxLikelihoodMatrix, np_mcmc.h:90). */
+npb_status npb_chains_consider_max_likelihood(npb_chains *ch, double *joint_loglik_out, double *best_out);
+npb_status npb_chains_get_best_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out /* [n,N] slot ids */);
+
 /* posterior co-clustering counts over this context's chains for an anchor subset: S[a,b] = #chains with
  * z[anchors[a]] == z[anchors[b]].  S_dev is a DEVICE pointer to n_anchor*n_anchor floats (so that the caller can
  * all-reduce it over NCCL without a host round trip); accumulate != 0 adds to S_dev. */

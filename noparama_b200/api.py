@@ -28,7 +28,7 @@ EXPORTS = [
     "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
-    "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge",
+    "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
 ]
 
 
@@ -89,6 +89,8 @@ def load_library():
     L.npb_replay_split_merge.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, ip, dp, dp, i64, ip, dp, dp, dp,
                                          C.POINTER(i64), ip, dp, dp, ip, ip, ip, ip, dp, ip]
     L.npb_chains_get_assignments.argtypes = [vp, i64, i64, ip]
+    L.npb_chains_consider_max_likelihood.argtypes = [vp, dp, dp]
+    L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
     L.npb_cocluster.argtypes = [vp, C.POINTER(i64), i64, vp, C.c_int]
@@ -347,6 +349,19 @@ class Chains:
         self.ctx.check(self.ctx._lib.npb_chains_get_assignments(self._h, chain0, n, _ip(out)))
         return out
 
+    def consider_max_likelihood(self):
+        """MCMC::considerMaxLikelihood (np_mcmc.cpp:187-203) for every chain -> (joint log-lik now, best so far)"""
+        cur, best = np.empty(self.C), np.empty(self.C)
+        self.ctx.check(self.ctx._lib.npb_chains_consider_max_likelihood(self._h, _dp(cur), _dp(best)))
+        return cur, best
+
+    def best_assignments(self, chain0=0, n=None):
+        """assignments of the max-likelihood state kept by consider_max_likelihood (MCMC::getMaxLikelihoodMatrix)"""
+        n = self.C - chain0 if n is None else n
+        out = np.empty((n, self.ds.N), dtype=np.int32)
+        self.ctx.check(self.ctx._lib.npb_chains_get_best_assignments(self._h, chain0, n, _ip(out)))
+        return out
+
     def params(self, chain):
         cap, D = self.Kmax, self.ds.D
         K = C.c_int()
@@ -413,15 +428,23 @@ class MCMC:
         self.algorithm = update_cluster_population
         self.chains = Chains(ctx, dataset, chains, Kmax=Kmax, m_aux=m_aux, K0=K0, seed=seed)
 
-    def run(self, T, sweeps_per_launch=None):
+    def run(self, T, sweeps_per_launch=None, cycle_max_likelihood=0):
+        """T sweeps; cycle_max_likelihood = 5 keeps the max-likelihood state like np_mcmc.cpp:172-174 (every 5th sweep)"""
         stats = []
         step = T if not sweeps_per_launch else sweeps_per_launch
+        if cycle_max_likelihood:
+            step = cycle_max_likelihood
         done = 0
         while done < T:
             n = min(step, T - done)
             stats.append(self.chains.sweep(self.algorithm.sampler, n))
             done += n
+            if cycle_max_likelihood:
+                self.chains.consider_max_likelihood()
         return stats
+
+    def getMaxLikelihoodMatrix(self, chain0=0, n=None):
+        return self.chains.best_assignments(chain0, n)
 
     def getMembershipMatrix(self, chain0=0, n=None):
         return self.chains.assignments(chain0, n)

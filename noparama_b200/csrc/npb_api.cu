@@ -338,6 +338,11 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->sm_order) cudaFree(ch->sm_order);
 	if (ch->sm_detail) cudaFree(ch->sm_detail);
 	if (ch->pstats) cudaFree(ch->pstats);
+	if (ch->best_z) cudaFree(ch->best_z);
+	if (ch->best_theta) cudaFree(ch->best_theta);
+	if (ch->best_counts) cudaFree(ch->best_counts);
+	if (ch->best_jll) cudaFree(ch->best_jll);
+	if (ch->cur_jll) cudaFree(ch->cur_jll);
 	if (ch->pLambda0) cudaFree(ch->pLambda0);
 	if (ch->pfail) cudaFree(ch->pfail);
 	delete ch;
@@ -849,5 +854,75 @@ npb_status npb_replay_split_merge(npb_ctx *ctx, npb_dataset *ds, int sampler, in
 	NPB_CUDA_OK(cudaMemcpyAsync(&status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
 	NPB_CUDA_OK(cudaStreamSynchronize(st));
 	if (status != 0) return npb_fail(ctx, (npb_status)status, "split-merge replay left the recorded trajectory");
+	return NPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// max-likelihood snapshot: MCMC::considerMaxLikelihood (np_mcmc.cpp:187-203) for every chain at once
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_best_init(double *best, int C) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < C) best[c] = -INFINITY;
+}
+// chains whose current joint log-likelihood beats the kept one copy their column of z (item-major: a warp covers 32
+// neighbouring chains of one item, so the copy is coalesced where it happens)
+__global__ void k_best_copy_z(const npb_z_t *z, npb_z_t *best_z, const double *cur, const double *best, int N, int C) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= C || !(cur[c] > best[c])) return;
+	for (int i = blockIdx.y; i < N; i += gridDim.y) best_z[(size_t)i * C + c] = z[(size_t)i * C + c];
+}
+__global__ void k_best_copy_params(const float *theta, const int *counts, float *best_theta, int *best_counts, const double *cur,
+		double *best, int C, int Kmax, int PS) {
+	const int c = blockIdx.x;
+	if (!(cur[c] > best[c])) return;
+	for (int t = threadIdx.x; t < Kmax * PS; t += blockDim.x) best_theta[(size_t)c * Kmax * PS + t] = theta[(size_t)c * Kmax * PS + t];
+	for (int t = threadIdx.x; t < Kmax; t += blockDim.x) best_counts[(size_t)c * Kmax + t] = counts[(size_t)c * Kmax + t];
+	__syncthreads();
+	if (threadIdx.x == 0) best[c] = cur[c]; // last: the z copy (earlier launch) and this block read the old value
+}
+
+npb_status npb_chains_consider_max_likelihood(npb_chains *ch, double *joint_loglik_out, double *best_out) {
+	if (!ch) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int N = (int)ch->ds->N, C = (int)ch->C, PS = npb_ps(ch->D);
+	if (!ch->best_z) {
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->best_z, (size_t)N * C * sizeof(npb_z_t)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->best_theta, (size_t)C * ch->Kmax * PS * sizeof(float)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->best_counts, (size_t)C * ch->Kmax * sizeof(int)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->best_jll, (size_t)C * sizeof(double)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->cur_jll, (size_t)C * 4 * sizeof(double)));
+		k_best_init<<<(C + 255) / 256, 256, 0, ctx->stream>>>(ch->best_jll, C);
+		NPB_CUDA_OK(cudaGetLastError());
+	}
+	DevBuf<int32_t> d_K;
+	NPB_CUDA_OK(d_K.alloc(C));
+	// joint log-likelihood of the current state: sum_k sum_{i in k} log p(x_i | theta_k)
+	npb_status s = npb_launch_metrics(ch, nullptr, 1, ch->cur_jll + C, ch->cur_jll + 2 * (size_t)C, ch->cur_jll + 3 * (size_t)C, ch->cur_jll, d_K.p);
+	if (s != NPB_OK) return s;
+	dim3 gz((C + 127) / 128, 64);
+	k_best_copy_z<<<gz, 128, 0, ctx->stream>>>(ch->z, ch->best_z, ch->cur_jll, ch->best_jll, N, C);
+	NPB_CUDA_OK(cudaGetLastError());
+	k_best_copy_params<<<C, 128, 0, ctx->stream>>>(ch->theta, ch->counts, ch->best_theta, ch->best_counts, ch->cur_jll, ch->best_jll, C,
+			ch->Kmax, PS);
+	NPB_CUDA_OK(cudaGetLastError());
+	if (joint_loglik_out) NPB_CUDA_OK(cudaMemcpyAsync(joint_loglik_out, ch->cur_jll, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+	if (best_out) NPB_CUDA_OK(cudaMemcpyAsync(best_out, ch->best_jll, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+npb_status npb_chains_get_best_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out) {
+	if (!ch || !z_out || chain0 < 0 || n <= 0 || chain0 + n > ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	if (!ch->best_z) return npb_fail(ctx, NPB_E_BAD_ARG, "npb_chains_consider_max_likelihood has not been called on this handle");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int N = (int)ch->ds->N;
+	DevBuf<int32_t> d;
+	NPB_CUDA_OK(d.alloc((size_t)n * N));
+	k_gather_chain_z<<<(unsigned)(((size_t)n * N + 255) / 256), 256, 0, ctx->stream>>>(ch->best_z, d.p, N, (int)ch->C, (int)chain0, (int)n);
+	NPB_CUDA_OK(cudaGetLastError());
+	NPB_CUDA_OK(cudaMemcpyAsync(z_out, d.p, sizeof(int32_t) * n * N, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }

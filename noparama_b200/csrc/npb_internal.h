@@ -63,6 +63,12 @@ struct npb_chains {
 	uint8_t *sm_dec = nullptr;     // [C, N]
 	int32_t *sm_order = nullptr;   // [3, N]
 	float *sm_detail = nullptr;    // [C, 16] detail of the last proposal of every chain (tests)
+	// max-likelihood snapshot (MCMC::considerMaxLikelihood, np_mcmc.cpp:187-203)
+	npb_z_t *best_z = nullptr;     // [N, C]
+	float *best_theta = nullptr;   // [C, Kmax, PS]
+	int *best_counts = nullptr;    // [C, Kmax]
+	double *best_jll = nullptr;    // [C] device: joint log-likelihood of the kept state (-inf before the first call)
+	double *cur_jll = nullptr;     // [C] device scratch
 	// parameter update (npb_params.cu)
 	double *pstats = nullptr;      // [C, Kmax, D + D(D+1)/2] sum x, upper triangle of sum x x^T
 	double *pLambda0 = nullptr;    // [D, D]

@@ -1,6 +1,10 @@
 // npb_host.cpp -- see npb_host.h.  Everything here is plumbing above the C ABI; no arithmetic of the path lives on the host.
 #include "npb_host.h"
 
+#include <filesystem>
+#include <fstream>
+#include <map>
+
 #include <algorithm>
 #include <cassert>
 #include <iostream>
@@ -140,25 +144,109 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam, UpdateClusters *up
 	}
 	const int N = trix_->size();
 	const bool upd = update_clusters && update_clusters->fixes_q1();
-	if (upd && !per_item_seam) { // np_mcmc.cpp:109-175 with a working parameter update: sweep, then UpdateClusters::update
-		for (int t = 0; t < T; ++t) {
-			ucp_.sweep(*trix_, 1);
-			update_clusters->update(*trix_, 20);
+	// np_mcmc.cpp:109-175: per sweep t the population update (:146-163), UpdateClusters::update (:170) and, when
+	// t % 5 == 0, considerMaxLikelihood (:172-174)
+	if (!per_item_seam && !upd) {
+		// nothing happens between the sweeps t = 5j+1 .. 5j+4, so they share a launch with sweep 5(j+1)
+		for (int t = 0; t < T;) {
+			const int n = (t == 0) ? 1 : std::min(5, T - t);
+			ucp_.sweep(*trix_, n);
+			t += n;
+			if ((t - 1) % 5 == 0) considerMaxLikelihood();
 		}
 		return;
 	}
-	if (per_item_seam) {
-		// the reference's own loop shape (np_mcmc.cpp:109-163): one update() per subset of subset_count items
-		const int sc = ucp_.subset_count();
-		for (int t = 0; t < T; ++t)
+	const int sc = ucp_.subset_count();
+	for (int t = 0; t < T; ++t) {
+		if (per_item_seam) {
+			// the reference's own loop shape: one update() per subset of subset_count items
 			for (int i = 0; i < N; ++i) {
 				data_ids_t subset(sc);
 				for (int j = 0; j < sc; ++j) subset[j] = (i + j * 7919) % N; // placeholders: the device draws the real subsets
 				ucp_.update(*trix_, subset);
-				if (upd && i == N - 1) update_clusters->update(*trix_, 20); // np_mcmc.cpp:170
 			}
-	} else {
-		ucp_.sweep(*trix_, T);
+		} else {
+			ucp_.sweep(*trix_, 1);
+		}
+		if (upd) update_clusters->update(*trix_, 20);
+		if (t % 5 == 0) considerMaxLikelihood();
+	}
+}
+
+void MCMC::considerMaxLikelihood() {
+	dev_.check(npb_chains_consider_max_likelihood(trix_->chains, nullptr, nullptr));
+}
+std::vector<int32_t> MCMC::getMaxLikelihoodAssignments(int64_t chain) {
+	std::vector<int32_t> z(trix_->size());
+	dev_.check(npb_chains_get_best_assignments(trix_->chains, chain, 1, z.data()));
+	return z;
+}
+
+// clustering_performance::{calculateContingencyMatrix, calculateSimilarity} (clustering_performance.cpp:14-82) on the
+// host for ONE labelling, in 64-bit integers (the reference's int overflows for N > 46340)
+void Results::scores() {
+	const size_t N = z_.size();
+	if (truth_.size() != N || N < 2) return;
+	std::map<std::pair<int, int>, long long> nab;
+	std::map<int, long long> ra, cb;
+	for (size_t i = 0; i < N; ++i) { nab[{truth_[i], z_[i]}]++; ra[truth_[i]]++; cb[z_[i]]++; }
+	auto c2 = [](long long n) { return (double)n * (double)(n - 1) / 2.0; };
+	std::map<int, long long> colmax;
+	double a = 0, b = 0, c = 0;
+	for (auto &kv : nab) { a += c2(kv.second); colmax[kv.first.second] = std::max(colmax[kv.first.second], kv.second); }
+	for (auto &kv : ra) b += c2(kv.second);
+	for (auto &kv : cb) c += c2(kv.second);
+	double pm = 0;
+	for (auto &kv : colmax) pm += (double)kv.second;
+	const double S = c2((long long)N);
+	purity = pm / (double)N;
+	rand_index = (2 * a - b - c) / S + 1;
+	adjusted_rand = (a - b * c / S) / ((b + c) / 2 - b * c / S);
+}
+
+void Results::write(const std::string &workspace, const std::string &path, const std::string &basename) {
+	namespace fs = std::filesystem;
+	scores();
+	const std::string ws_path = workspace + path;
+	fs::create_directories(ws_path);
+	const std::string ws_latest = workspace + "LATEST";
+	std::error_code ec;
+	fs::remove(ws_latest, ec);
+	fs::create_symlink(path, ws_latest, ec);
+	int k = 0;
+	for (auto &kv : clusters_) { // np_results.cpp:71-97: one file per cluster with its items
+		std::ofstream of(ws_path + "/" + basename + std::to_string(k) + ".txt");
+		for (size_t i = 0; i < z_.size(); ++i)
+			if (z_[i] == kv.first) {
+				for (double d : *dataset_[i]) of << d << " ";
+				of << std::endl;
+			}
+		k++;
+	}
+	{ // writeOctave, np_results.cpp:112-196
+		std::ofstream of(ws_path + "/" + basename + ".txt");
+		const int K = (int)clusters_.size();
+		if (K > 0) {
+			const int D = (int)clusters_.begin()->second.mu.size();
+			of << "# name: mu" << std::endl << "# type: matrix" << std::endl << "# rows: " << K << std::endl << "# columns: " << D << std::endl;
+			for (auto &kv : clusters_) {
+				for (int d = 0; d < D; ++d) of << (d ? " " : "") << kv.second.mu[d];
+				of << std::endl;
+			}
+			of << std::endl << std::endl;
+			of << "# name: sigma" << std::endl << "# type: matrix" << std::endl << "# ndims: 3" << std::endl << " " << D << " " << D << " " << K << std::endl;
+			for (auto &kv : clusters_) { // column-major like Eigen's default storage printed with " \n" separators
+				for (int c = 0; c < D; ++c)
+					for (int r = 0; r < D; ++r) of << kv.second.sigma[(size_t)r * D + c] << " " << std::endl;
+				of << std::endl;
+			}
+		}
+	}
+	{ // clustering_performance::write, clustering_performance.cpp:84-93
+		std::ofstream of(ws_path + "/" + basename + ".score.txt");
+		of << "Purity: " << purity << std::endl;
+		of << "Rand Index: " << rand_index << std::endl;
+		of << "Adjusted Rand Index: " << adjusted_rand << std::endl;
 	}
 }
 

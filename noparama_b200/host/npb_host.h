@@ -199,6 +199,8 @@ public:
 	~MCMC();
 	void run(dataset_t &dataset, int T, bool per_item_seam = false, UpdateClusters *update_clusters = nullptr);
 	membertrix &getMembershipMatrix() { return *trix_; }                  // np_mcmc.h:88
+	std::vector<int32_t> getMaxLikelihoodAssignments(int64_t chain = 0);  // np_mcmc.h:90: the state kept by considerMaxLikelihood
+	void considerMaxLikelihood();                                         // np_mcmc.cpp:187-203, every chain at once
 	clustering_scores scores(const std::vector<int> &ground_truth);        // np_results.cpp:17-37 + clustering_performance
 	int64_t chains() const { return chains_; }
 private:
@@ -209,6 +211,25 @@ private:
 	int Kmax_, K0_, m_aux_;
 	uint64_t seed_;
 	membertrix *trix_ = nullptr;
+};
+
+// Results (include/np_results.h, src/np_results.cpp:39-196): writes one clustering of one chain the way the reference does --
+// <workspace>/<path>/<basename><k>.txt with the items of cluster k, <basename>.txt with the parameters as Octave
+// matrices "mu" and "sigma", <basename>.score.txt with purity / Rand / adjusted Rand (clustering_performance.cpp:84-93),
+// and the symlink <workspace>/LATEST -> <path>.
+class Results {
+public:
+	Results(dataset_t &dataset, const std::vector<int32_t> &assignments, const std::map<cluster_id_t, Suffies_MultivariateNormal> &clusters,
+			const std::vector<int> &ground_truth)
+		: dataset_(dataset), z_(assignments), clusters_(clusters), truth_(ground_truth) {}
+	void write(const std::string &workspace, const std::string &path, const std::string &basename);
+	double purity = 0, rand_index = 0, adjusted_rand = 0;
+private:
+	void scores();
+	dataset_t &dataset_;
+	std::vector<int32_t> z_;
+	std::map<cluster_id_t, Suffies_MultivariateNormal> clusters_;
+	std::vector<int> truth_;
 };
 
 } // namespace npb

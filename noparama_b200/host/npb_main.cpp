@@ -9,6 +9,7 @@
 #include "npb_host.h"
 
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -19,7 +20,7 @@
 using namespace npb;
 
 static void usage() {
-	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1]\n";
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR]\n";
 }
 
 int main(int argc, char **argv) {
@@ -28,6 +29,7 @@ int main(int argc, char **argv) {
 	long long chains = 1;
 	unsigned long long seed = 20261018ull;
 	bool seam = false, fix_q1 = false;
+	std::string output; // workspace root for the results files; empty = do not write (the reference always writes to output/)
 	for (int i = 1; i < argc; ++i) {
 		std::string a = argv[i];
 		auto next = [&](const char *what) -> const char * {
@@ -43,6 +45,7 @@ int main(int argc, char **argv) {
 		else if (a == "--kmax") kmax = atoi(next("--kmax"));
 		else if (a == "--seam") seam = true;
 		else if (a == "--fix-q1") fix_q1 = true;
+		else if (a == "--output") output = next("--output");
 		else if (a == "-h" || a == "-?") { usage(); return 0; }
 		else { std::cerr << "unknown option " << a << std::endl; usage(); return 1; }
 	}
@@ -105,6 +108,26 @@ int main(int argc, char **argv) {
 			std::cout << "Mean over " << chains << " chains: purity " << mean(sc.purity) << " rand " << mean(sc.rand_index)
 				  << " adjusted rand " << mean(sc.adjusted_rand) << std::endl;
 		membertrix &trix = mcmc.getMembershipMatrix();
+		if (!output.empty()) {
+			// np_main.cpp:476-497: the last state ("snapshot") and the max-likelihood state ("results") of chain 0, written
+			// to <output>/<algorithm>/<datafile name>/<timestamp>/ with the reference's file layout (np_results.cpp:39-196)
+			std::string base = datafile.substr(datafile.find_last_of('/') == std::string::npos ? 0 : datafile.find_last_of('/') + 1);
+			const std::string workspace = output + "/" + algorithm + "/" + base + "/";
+			char stamp[32];
+			std::time_t now = std::time(nullptr);
+			std::strftime(stamp, sizeof(stamp), "%Y%m%d_%H:%M", std::localtime(&now));
+			std::vector<int32_t> z_last(trix.size());
+			for (int i = 0; i < trix.size(); ++i) z_last[i] = trix.getClusterId(i);
+			Results snapshot(dataset, z_last, trix.getClusters(), ground_truth);
+			snapshot.write(workspace, stamp, "snapshot");
+			// parameters are frozen at birth (Q1) unless --fix-q1, and slot ids are stable: the clusters of the kept state
+			// are looked up in the current table; a slot that died since keeps its items but has no parameters to print
+			Results results(dataset, mcmc.getMaxLikelihoodAssignments(0), trix.getClusters(), ground_truth);
+			results.write(workspace, stamp, "results");
+			std::cout << "Wrote snapshot* and results* to " << workspace << stamp << std::endl;
+			std::cout << "Max-likelihood state: purity " << results.purity << " rand " << results.rand_index << " adjusted rand "
+				  << results.adjusted_rand << std::endl;
+		}
 		for (auto &kv : trix.getClusters())
 			std::cout << " cluster " << kv.first << " [#" << trix.count(kv.first) << "] mu " << kv.second.mu[0] << (D > 1 ? " " : "")
 				  << (D > 1 ? std::to_string(kv.second.mu[1]) : "") << std::endl;

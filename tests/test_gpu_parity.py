@@ -309,3 +309,26 @@ def test_alg8_replay_general_covariance_3d(npb, ctx, oracle):
     picked, z_after = npb.replay_alg8(ctx, ds, t, r.init_state(), m_aux=3, z_every=ds.N)
     assert np.array_equal(picked, t["picked"]) and np.array_equal(z_after, t["z_after"])
     ds.close()
+
+
+def test_max_likelihood_snapshot(npb, ctx, oracle):
+    """MCMC::considerMaxLikelihood (np_mcmc.cpp:187-203) on the device: the kept state of every chain is the one with
+    the highest joint log-likelihood among the states it was shown, chain by chain."""
+    X, y = syn.config(1)
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(2)), chains=48, Kmax=64, seed=21)
+    best_j = np.full(48, -np.inf)
+    best_z = np.zeros((48, ds.N), np.int32)
+    for it in range(12):
+        mc.chains.sweep(npb.ALG8, 5)
+        z = mc.getMembershipMatrix()
+        cur, best = mc.chains.consider_max_likelihood()
+        want = mc.chains.metrics(None)["joint_loglik"]
+        assert np.array_equal(cur, want)
+        better = cur > best_j
+        best_j = np.where(better, cur, best_j)
+        best_z[better] = z[better]
+        assert np.array_equal(best, best_j)
+        assert np.array_equal(mc.getMaxLikelihoodMatrix(), best_z)
+    assert (best_j >= cur).all() and not np.array_equal(best_z, z)   # some chain kept an earlier state
+    ds.close()

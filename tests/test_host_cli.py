@@ -97,3 +97,30 @@ def test_cli_fix_q1_refits_parameters(tmp_path):
     assert r.returncode == 0, r.stderr
     pur = float(re.search(r"chains: purity ([0-9.]+)", r.stdout).group(1))
     assert pur > 0.95
+
+
+@pytest.mark.gpu
+def test_cli_writes_results_like_the_reference(tmp_path):
+    """--output: snapshot* / results* files, Octave parameter file, score file and LATEST symlink (np_results.cpp:39-196,
+    np_main.cpp:476-497); the results are the max-likelihood state kept every 5 sweeps (np_mcmc.cpp:172-174,187-203)."""
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    out = tmp_path / "out"
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "100", "-c", "clustering", "--chains", "8", "--kmax", "64",
+                        "--seed", "5", "--output", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ws = out / "algorithm8" / "twogaussians.data"
+    latest = ws / "LATEST"
+    assert latest.is_symlink()
+    d = ws / os.readlink(str(latest))
+    for base in ("snapshot", "results"):
+        score = (d / (base + ".score.txt")).read_text()
+        assert score.startswith("Purity: ") and "Adjusted Rand Index: " in score
+        octave = (d / (base + ".txt")).read_text()
+        assert "# name: mu" in octave and "# name: sigma" in octave and "# ndims: 3" in octave
+        K = int(re.search(r"# rows: (\d+)", octave).group(1))
+        rows = sum(len((d / ("%s%d.txt" % (base, k))).read_text().splitlines()) for k in range(K))
+        assert rows <= 200 and rows > 150  # every item of a cluster that still has parameters is dumped once
+    pur = float(re.search(r"Purity: ([0-9.]+)", (d / "results.score.txt").read_text()).group(1))
+    assert pur > 0.95
