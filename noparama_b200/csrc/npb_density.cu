@@ -66,8 +66,11 @@ __global__ void k_logdensity_sum(const double *X, const int64_t *rows, int64_t n
 
 // One CTA per chain.  Contingency n[a][b] (a = truth label, b = slot) in shared memory, then purity / RI / ARI,
 // joint log-likelihood from the chain's own slot table (log2 domain, float factors) and the occupied count.
+// DT > 0: the dimension as a compile-time constant (straight-line quadratic form); DT = 0: generic (runtime D).
+template <int DT>
 __global__ void k_chain_metrics(const npb_z_t *z, const float *X, const float *theta, const int *counts, const int32_t *truth,
-		int N, int C, int Kmax, int D, int Ktrue, int stage_theta, double *purity, double *ri, double *ari, double *jll, int32_t *Kout) {
+		int N, int C, int Kmax, int Drt, int Ktrue, int stage_theta, double *purity, double *ri, double *ari, double *jll, int32_t *Kout) {
+	const int D = DT > 0 ? DT : Drt;
 	extern __shared__ unsigned char smem_raw[];
 	double *red = (double *)smem_raw;                        // [blockDim.x]
 	int *cont = (int *)(red + blockDim.x);                   // [Ktrue][Kmax]
@@ -91,10 +94,23 @@ __global__ void k_chain_metrics(const npb_z_t *z, const float *X, const float *t
 			const float *p = th + (size_t)s * PS;
 			const float *x = X + (size_t)i * D;
 			float q = 0.0f;
-			for (int a = 0; a < D; ++a) {
-				float y = 0.0f;
-				for (int b = a; b < D; ++b) y = fmaf(p[D + npb_tri_off(D, a, b)], x[b] - p[b], y);
-				q = fmaf(y, y, q);
+			if (DT > 0) {
+				float d[DT > 0 ? DT : 1];
+#pragma unroll
+				for (int b = 0; b < DT; ++b) d[b] = __ldg(x + b) - p[b];
+#pragma unroll
+				for (int a = 0; a < DT; ++a) {
+					float y = 0.0f;
+#pragma unroll
+					for (int b = a; b < DT; ++b) y = fmaf(p[DT + npb_tri_off(DT, a, b)], d[b], y);
+					q = fmaf(y, y, q);
+				}
+			} else {
+				for (int a = 0; a < D; ++a) {
+					float y = 0.0f;
+					for (int b = a; b < D; ++b) y = fmaf(p[D + npb_tri_off(D, a, b)], x[b] - p[b], y);
+					q = fmaf(y, y, q);
+				}
 			}
 			acc += (double)(p[D + TRI] - q);
 		}
@@ -189,9 +205,21 @@ npb_status npb_launch_metrics(npb_chains *ch, const int32_t *d_truth, int Ktrue,
 	const size_t table = (size_t)ch->Kmax * npb_ps(ch->D) * sizeof(float);
 	const int stage = (shmem + table <= 96 * 1024) ? 1 : 0;
 	if (stage) shmem += table;
-	NPB_CUDA_OK(cudaFuncSetAttribute(k_chain_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-	k_chain_metrics<<<(unsigned)ch->C, threads, shmem, ctx->stream>>>(ch->z, ch->ds->X32, ch->theta, ch->counts, d_truth,
-			(int)ch->ds->N, (int)ch->C, ch->Kmax, ch->D, Ktrue, stage, d_purity, d_ri, d_ari, d_jll, d_K);
+#define NPB_METRICS_LAUNCH(DT)                                                                                              \
+	do {                                                                                                               \
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_chain_metrics<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem)); \
+		k_chain_metrics<DT><<<(unsigned)ch->C, threads, shmem, ctx->stream>>>(ch->z, ch->ds->X32, ch->theta, ch->counts, \
+				d_truth, (int)ch->ds->N, (int)ch->C, ch->Kmax, ch->D, Ktrue, stage, d_purity, d_ri, d_ari, d_jll, d_K);      \
+	} while (0)
+	switch (ch->D) {
+	case 2: NPB_METRICS_LAUNCH(2); break;
+	case 3: NPB_METRICS_LAUNCH(3); break;
+	case 4: NPB_METRICS_LAUNCH(4); break;
+	case 8: NPB_METRICS_LAUNCH(8); break;
+	case 16: NPB_METRICS_LAUNCH(16); break;
+	default: NPB_METRICS_LAUNCH(0); break;
+	}
+#undef NPB_METRICS_LAUNCH
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
