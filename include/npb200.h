@@ -40,7 +40,9 @@ enum {
 	NPB_E_ASSIGNMENT_ABSENT = -18
 };
 
-/* samplers selectable by -a (src/np_main.cpp:212-236, 424-459) */
+/* samplers selectable by -a (src/np_main.cpp:212-236, 424-459).  NPB_ALG2 is the sampler src/np_neal_algorithm2.cpp:32-120
+ * describes (the reference does not compile it): K weights p(x|theta_k) n_k plus ONE prior draw weighted p(x|theta') alpha --
+ * the Algorithm 8 kernels with a single auxiliary draw; it needs chains created with m_aux = 1. */
 enum { NPB_ALG8 = 8, NPB_ALG2 = 2, NPB_JAIN_NEAL = 20, NPB_TRIADIC = 30 };
 
 /* behaviour switches of npb_prior_set_niw; the default (all bug-compatible flags set) reproduces the

@@ -405,6 +405,13 @@ class NealAlgorithm8:
     subset_count = 1
 
 
+class NealAlgorithm2:
+    """The sampler src/np_neal_algorithm2.cpp:32-120 describes (not compiled by the reference): one prior draw weighted
+    alpha beside the K occupied clusters.  Use with MCMC(..., m_aux=1)."""
+    sampler = ALG2
+    subset_count = 1
+
+
 class JainNealAlgorithm:
     """UpdateClusterPopulation implementation selected by `-a jain_neal_split` (np_main.cpp:440-446)."""
     sampler = JAIN_NEAL

@@ -261,9 +261,10 @@ __global__ void __launch_bounds__(256) k_aux_keys(const SweepArgs a, uint32_t *o
 template <int D>
 npb_status npb_launch_aux_keys(npb_chains *ch, const SweepArgs &a) {
 	npb_ctx *ctx = ch->ctx;
-	if (ch->m_aux != 3) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 3 for the D >= 4 sweep kernel");
+	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D >= 4 sweep kernel");
 	dim3 grid((unsigned)((a.N + 255) / 256), (unsigned)ch->C, (unsigned)a.n_sweeps);
-	k_aux_keys<D, 3><<<grid, 256, 0, ctx->stream>>>(a, ch->aux_keys);
+	if (ch->m_aux == 3) k_aux_keys<D, 3><<<grid, 256, 0, ctx->stream>>>(a, ch->aux_keys);
+	else k_aux_keys<D, 1><<<grid, 256, 0, ctx->stream>>>(a, ch->aux_keys);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
@@ -519,11 +520,16 @@ __global__ void __launch_bounds__(256, 2) k_alg8_sweep_tile4(const SweepArgs a) 
 template <int D>
 npb_status npb_launch_alg8_tile4(npb_chains *ch, const SweepArgs &a) {
 	npb_ctx *ctx = ch->ctx;
-	if (ch->m_aux != 3) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 3 for the D >= 4 sweep kernel");
+	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D >= 4 sweep kernel");
 	const size_t shmem = sizeof(Tile4Smem<D>) * NPB_T4_CHAINS;
-	NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_tile4<D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
 	const unsigned blocks = (unsigned)((ch->C + NPB_T4_CHAINS - 1) / NPB_T4_CHAINS);
-	k_alg8_sweep_tile4<D, 3><<<blocks, 256, shmem, ctx->stream>>>(a);
+	if (ch->m_aux == 3) {
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_tile4<D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+		k_alg8_sweep_tile4<D, 3><<<blocks, 256, shmem, ctx->stream>>>(a);
+	} else {
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_tile4<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+		k_alg8_sweep_tile4<D, 1><<<blocks, 256, shmem, ctx->stream>>>(a);
+	}
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }

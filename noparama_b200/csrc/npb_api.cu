@@ -466,8 +466,13 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_
 	if (!ch || n_sweeps < 0 || n_proposals < 0) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
-	if (sampler == NPB_ALG2)
-		return npb_fail(ctx, NPB_E_UNSUPPORTED, "Algorithm 2 is dead code in the reference (np_neal_algorithm2.cpp is not compiled); not built");
+	if (sampler == NPB_ALG2) {
+		// np_neal_algorithm2.cpp:32-120 (not compiled by the reference): K weights p(x|theta_k) n_k and ONE prior draw
+		// weighted p(x|theta') alpha, a Bernoulli for "new" and then a pick among the existing -- one categorical draw over
+		// K + 1 candidates, i.e. the Algorithm 8 kernels with a single auxiliary draw
+		if (ch->m_aux != 1) return npb_fail(ctx, NPB_E_BAD_ARG, "Algorithm 2 runs on chains created with m_aux = 1");
+		sampler = NPB_ALG8;
+	}
 	if (sampler != NPB_ALG8 && sampler != NPB_JAIN_NEAL && sampler != NPB_TRIADIC) return NPB_E_BAD_ARG;
 	if (sampler == NPB_ALG8 && n_proposals) return NPB_E_BAD_ARG;
 	std::vector<unsigned long long> before, sm_before;

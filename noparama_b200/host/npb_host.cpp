@@ -82,9 +82,15 @@ void membertrix::getAssignments(cluster_id_t k, data_ids_t &ids) {
 }
 
 void NealAlgorithm8::sweep(membertrix &cluster_matrix, int n_sweeps) {
-	dev_.check(npb_chains_sweep(cluster_matrix.chains, NPB_ALG8, n_sweeps, &last_));
-	accepted_ += last_.new_clusters;
-	rejected_ += last_.reassignments - last_.new_clusters;
+	npb_sweep_stats st{};
+	dev_.check(npb_chains_sweep(cluster_matrix.chains, NPB_ALG8, n_sweeps, &st));
+	record(st);
+	cluster_matrix.invalidate();
+}
+void NealAlgorithm2::sweep(membertrix &cluster_matrix, int n_sweeps) {
+	npb_sweep_stats st{};
+	dev().check(npb_chains_sweep(cluster_matrix.chains, NPB_ALG2, n_sweeps, &st));
+	record(st);
 	cluster_matrix.invalidate();
 }
 void NealAlgorithm8::update(membertrix &cluster_matrix, const data_ids_t &data_ids) {

@@ -130,12 +130,29 @@ public:
 	int sampler() const override { return NPB_ALG8; }
 	int subset_count() const override { return 1; }
 	const npb_sweep_stats &last() const { return last_; }
+protected:
+	device &dev() { return dev_; }
+	void record(const npb_sweep_stats &st) {
+		last_ = st;
+		accepted_ += st.new_clusters;
+		rejected_ += st.reassignments - st.new_clusters;
+	}
 private:
 	device &dev_;
 	dirichlet_process &hyper_;
 	int64_t calls_ = 0;
 	int64_t accepted_ = 0, rejected_ = 0;
 	npb_sweep_stats last_{};
+};
+
+// NealAlgorithm2 (include/np_neal_algorithm2.h, src/np_neal_algorithm2.cpp:32-120; not compiled by the reference): one prior
+// draw weighted alpha beside the K occupied clusters -- the same device sweep with m_aux = 1 (MCMC must be built with
+// m_aux = 1 for it).
+class NealAlgorithm2 : public NealAlgorithm8 {
+public:
+	NealAlgorithm2(device &dev, dirichlet_process &nonparametrics) : NealAlgorithm8(dev, nonparametrics) {}
+	int sampler() const override { return NPB_ALG2; }
+	void sweep(membertrix &cluster_matrix, int n_sweeps) override;
 };
 
 // The split-merge samplers (include/np_jain_neal_algorithm.h:75-79, include/np_triadic_algorithm.h:73-77).  update()

@@ -2,7 +2,7 @@
 //   noparama_b200 -d <datafile> -a <algorithm8|jain_neal_split|triadic> -T <sweeps> -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1]
 // -d  text file, one item per line: D coordinates then the ground-truth label (the reference reads exactly 2 + 1
 //     columns, np_main.cpp:93-101; here D = columns - 1 <= 3 for the register kernel, 4/8/16 for the tile kernel)
-// -a  algorithm8 | jain_neal_split | triadic (np_main.cpp:228-238)
+// -a  algorithm8 | jain_neal_split | triadic (np_main.cpp:228-238) | algorithm2 (commented out there, :222-227)
 // -T  sweeps (default 2000, np_main.cpp:242)    -c  clustering only (regression/angular/points3d are out of scope)
 // Prior and constants as hard-wired in the reference: alpha = 1, NIW{mu = 6, kappa = 1/500, nu = D + 2, Lambda = 0.01 I}
 // (np_main.cpp:164,367-371), K0 = 20, M = 3.  No 200-row subsampling (np_main.cpp:166-167): every row is used.
@@ -20,7 +20,7 @@
 using namespace npb;
 
 static void usage() {
-	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR]\n";
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|algorithm2|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR]\n";
 }
 
 int main(int argc, char **argv) {
@@ -51,7 +51,7 @@ int main(int argc, char **argv) {
 	}
 	if (datafile.empty()) { usage(); return 1; }
 	if (config != "clustering") { std::cerr << "Unknown likelihood (only -c clustering is on the device path)" << std::endl; return 107; }
-	if (algorithm != "algorithm8" && algorithm != "jain_neal_split" && algorithm != "triadic") { // np_main.cpp:228-238
+	if (algorithm != "algorithm8" && algorithm != "algorithm2" && algorithm != "jain_neal_split" && algorithm != "triadic") { // np_main.cpp:222-238
 		std::cerr << "Unknown algorithm: " << algorithm << std::endl;
 		return 1;
 	}
@@ -90,9 +90,11 @@ int main(int argc, char **argv) {
 		NealAlgorithm8 alg8(dev, hyper);
 		JainNealAlgorithm jain_neal(dev, hyper);
 		TriadicAlgorithm triadic(dev, hyper);
+		NealAlgorithm2 alg2(dev, hyper); // np_main.cpp:222-227,425-431 (commented out in the reference)
 		UpdateClusterPopulation &sampler = algorithm == "algorithm8" ? (UpdateClusterPopulation &)alg8
-				: (algorithm == "jain_neal_split" ? (UpdateClusterPopulation &)jain_neal : (UpdateClusterPopulation &)triadic);
-		MCMC mcmc(dev, hyper, sampler, chains, kmax, 20, 3, seed);
+				: (algorithm == "algorithm2" ? (UpdateClusterPopulation &)alg2
+				: (algorithm == "jain_neal_split" ? (UpdateClusterPopulation &)jain_neal : (UpdateClusterPopulation &)triadic));
+		MCMC mcmc(dev, hyper, sampler, chains, kmax, 20, algorithm == "algorithm2" ? 1 : 3, seed);
 		std::cout << "Run MCMC for " << T << " steps, " << chains << " chain(s)" << std::endl;
 		UpdateClusters update_clusters(dev, hyper, fix_q1); // np_main.cpp:415
 		mcmc.run(dataset, T, seam, &update_clusters);

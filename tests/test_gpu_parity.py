@@ -332,3 +332,44 @@ def test_max_likelihood_snapshot(npb, ctx, oracle):
         assert np.array_equal(mc.getMaxLikelihoodMatrix(), best_z)
     assert (best_j >= cur).all() and not np.array_equal(best_z, z)   # some chain kept an earlier state
     ds.close()
+
+
+def _oracle_alg2_seed(args):
+    seed, T = args
+    from oracle import binding as orc
+    X, y = syn.config(1)
+    r = orc.Run(orc.make_prior(**syn.reference_prior(2)), X, T=T, M_aux=1, seed_main=800 + seed, seed_shuffle=2800 + seed,
+                flags=orc.UPDATE_CLUSTERS)
+    s = r.stats()
+    pur, ri, ari = orc.metrics(y, r.assignments(0))
+    return s.K_final, pur, ri, ari, s.new_cluster_events / s.updates, s.moved / s.updates
+
+
+def test_algorithm2_distribution_matches_oracle(npb, ctx):
+    """NPB_ALG2 = the sampler np_neal_algorithm2.cpp:32-120 describes (dead code in the reference): K occupied clusters +
+    ONE prior draw weighted alpha.  The oracle runs NealAlgorithm8's code path with M = 1 (the same categorical); 512
+    device chains against 128 oracle seeds on config 1."""
+    from multiprocessing import Pool
+    T = 300
+    with Pool(8) as pool:
+        res = np.array(pool.map(_oracle_alg2_seed, [(s, T) for s in range(128)]))
+    X, y = syn.config(1)
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(2)), npb.NealAlgorithm2, chains=512, Kmax=64, m_aux=1,
+                  seed=31)
+    stats = mc.run(T, sweeps_per_launch=100)
+    assert all(s.overflow_chains == 0 for s in stats)
+    m = mc.chains.metrics(y)
+    for name, got, want in (("K", m["K"].astype(float), res[:, 0]), ("purity", m["purity"], res[:, 1]),
+                            ("rand", m["rand_index"], res[:, 2]), ("ari", m["adjusted_rand"], res[:, 3])):
+        p = sps.ks_2samp(got, want).pvalue
+        assert p > 0.01, "%s: KS p=%.2e (gpu %.4f vs oracle %.4f)" % (name, p, got.mean(), want.mean())
+    n = sum(s.reassignments for s in stats)
+    assert sum(s.candidates for s in stats) < sum(s.reassignments for s in stats) * (m["K"].max() + 40)
+    births = sum(s.new_clusters for s in stats) / n
+    assert abs(births - res[:, 4].mean()) < 0.08 * res[:, 4].mean() + 2e-5
+    # an ALG8 handle (m_aux = 3) refuses the Algorithm-2 sweep
+    mc3 = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(2)), chains=4, Kmax=64, seed=1)
+    with pytest.raises(npb.NpbError):
+        mc3.chains.sweep(npb.ALG2, 1)
+    ds.close()

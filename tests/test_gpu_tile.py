@@ -165,3 +165,22 @@ def test_full_size_properties_config5_shard(npb, ctx):
     m2 = mc.chains.metrics(y)
     assert np.array_equal(m["joint_loglik"], m2["joint_loglik"])
     ds.close()
+
+
+def test_tile4_algorithm2_single_auxiliary_draw(npb, ctx):
+    """m_aux = 1 (the sampler np_neal_algorithm2.cpp describes) through the D >= 4 kernels: bookkeeping invariants and the
+    candidate count of K + 1 per reassignment."""
+    X, y = syn.gmm(1000, 8, 4, 55)
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(8)), npb.NealAlgorithm2, chains=20, Kmax=32, K0=8,
+                  m_aux=1, seed=3)
+    means = np.stack([X[y == k].mean(0) for k in range(4)])
+    mc.chains.init_from_params(means, np.tile(np.eye(8), (4, 1, 1)))
+    st = mc.run(3)[0]
+    assert st.overflow_chains == 0 and st.reassignments == 20 * 1000 * 3
+    assert 4 * st.reassignments < st.candidates <= 6 * st.reassignments   # K = 4 (+ rare births) + 1 auxiliary draw
+    z = mc.getMembershipMatrix()
+    for c in (0, 19):
+        invariants(mc.chains, z[c], c, ds.N)
+    assert mc.chains.metrics(y)["purity"].mean() > 0.99
+    ds.close()

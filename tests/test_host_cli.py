@@ -32,7 +32,7 @@ def test_cli_usage_and_refusals(tmp_path):
     write_data(str(data))
     # the reference exits 107 on an unknown likelihood (np_main.cpp:346,385) and 1 on an unknown algorithm (:236)
     assert subprocess.run([CLI, "-d", str(data), "-c", "regression"], capture_output=True).returncode == 107
-    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm2"], capture_output=True, text=True)
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm9"], capture_output=True, text=True)
     assert r.returncode == 1 and "Unknown algorithm" in r.stderr
     assert subprocess.run([CLI, "-d", str(tmp_path / "missing")], capture_output=True).returncode == 7
 
@@ -66,6 +66,17 @@ def test_cli_runs_config1(tmp_path):
         assert "new cluster events accepted" in r.stdout
     # the per-item seam (one update() per item, np_mcmc.cpp:162) and the batched sweep walk the same trajectory
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_cli_runs_algorithm2(tmp_path):
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm2", "-T", "200", "-c", "clustering", "--chains", "32", "--kmax", "64",
+                        "--seed", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert float(re.search(r"chains: purity ([0-9.]+)", r.stdout).group(1)) > 0.97
 
 
 @pytest.mark.gpu
