@@ -145,7 +145,8 @@ npb_status npb_chains_update_params(npb_chains *ch, int mode, const double *mu0,
 npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,
 		npb_sweep_stats *stats);
 
-/* one NealAlgorithm8::update(membertrix&, {item}) on one chain (the reference's single-item seam) */
+/* one NealAlgorithm8::update(membertrix&, {item}) (np_neal_algorithm8.cpp:49-167) on one chain -- the reference's
+ * single-item seam (np_mcmc.cpp:162); chain < 0 applies it to every chain of the handle.  Any D and Kmax. */
 npb_status npb_chain_update_alg8(npb_chains *ch, int64_t chain, int64_t item);
 
 /* parity level 2: replay a recorded trace of NealAlgorithm8::update in double precision with

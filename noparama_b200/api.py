@@ -300,6 +300,10 @@ class Chains:
         self.ctx.check(self.ctx._lib.npb_chains_sweep(self._h, sampler, n_sweeps, C.byref(st) if want_stats else None))
         return st
 
+    def update_item(self, item, chain=-1):
+        """one NealAlgorithm8::update(membertrix&, {item}) on `chain` (every chain if negative): the single-item seam"""
+        self.ctx.check(self.ctx._lib.npb_chain_update_alg8(self._h, chain, item))
+
     def split_merge(self, sampler, n_proposals):
         """the first n_proposals subsets of the next sweep of a split-merge sampler (np_mcmc.cpp:146-163)"""
         st = SweepStats()

@@ -233,3 +233,101 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 	}
 	return NPB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// The single-item seam: one NealAlgorithm8::update(membertrix&, {item}) (np_neal_algorithm8.cpp:49-167) on chains
+// chain0 .. chain0+n-1, one warp per chain, any D <= NPB_MAX_D and any Kmax.  Not a throughput path: parameters are read
+// from the global slot table, the auxiliary draws are materialised in full (npb_draw_theta) into shared memory.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_update_item_alg8(SweepArgs a, int chain0, int item, uint32_t call) {
+	extern __shared__ float s_aux[]; // [M][PS]
+	const int lane = threadIdx.x, chain = chain0 + blockIdx.x;
+	const int D = a.prior.D, PS = npb_ps(D), TRI = npb_tri(D), M = a.prior.m_aux, Kmax = a.Kmax;
+	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+	float *theta = a.theta + (size_t)chain * Kmax * PS;
+	int *counts = a.counts + (size_t)chain * Kmax;
+	const float *x = a.X + (size_t)item * D;
+	const int zo = (int)a.z[(size_t)item * a.C + chain];
+	for (int m = lane; m < M; m += 32) npb_draw_theta(a.prior, ph, (uint32_t)item, 0x51A61E00u + call, NPB_RNG_AUX, m * (D + 1), s_aux + m * PS);
+	__syncwarp();
+	auto log2dens = [&](const float *p) {
+		float q = 0.0f;
+		for (int r = 0; r < D; ++r) {
+			float y = 0.0f;
+			for (int c = r; c < D; ++c) y = fmaf(p[D + npb_tri_off(D, r, c)], x[c] - p[c], y);
+			q = fmaf(y, y, q);
+		}
+		return p[D + TRI] - q;
+	};
+	// exponential race over the occupied slots (weights p n_k, the item itself retracted) and the M auxiliary draws
+	float best = -INFINITY;
+	int best_c = -1, cand = 0;
+	for (int c0 = 0; c0 < Kmax + M; c0 += 32) {
+		const int c = c0 + lane;
+		float key = -INFINITY;
+		if (c < Kmax + M) {
+			uint32_t w[4];
+			ph((uint32_t)item, (uint32_t)c, 0x51A61E00u + call, NPB_RNG_PICK, w);
+			const float noise = neg_lg2_exp1(w[0]);
+			if (c < Kmax) {
+				const int n = counts[c] - (c == zo ? 1 : 0);
+				if (n > 0) { key = log2dens(theta + (size_t)c * PS) + fast_lg2((float)n) + noise; cand++; }
+			} else {
+				key = log2dens(s_aux + (c - Kmax) * PS) + a.prior.log2_alpha_m + noise;
+				cand++;
+			}
+		}
+		if (key > best) { best = key; best_c = c; }
+	}
+	// warp arg-max (ties: lowest candidate index)
+	for (int o = 16; o > 0; o >>= 1) {
+		const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+		const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+		if (ob > best || (ob == best && oc >= 0 && (best_c < 0 || oc < best_c))) { best = ob; best_c = oc; }
+	}
+	cand = __reduce_add_sync(0xffffffffu, cand);
+	if (best_c < 0) return; // nothing had weight: the item stays (the reference would pick index 0, Q6)
+	int new_slot = best_c;
+	bool born = false;
+	if (best_c >= Kmax) { // np_neal_algorithm8.cpp:136-145: lowest free slot once the item is retracted
+		born = true;
+		int fs = -1;
+		for (int k0 = 0; k0 < Kmax && fs < 0; k0 += 32) {
+			const int k = k0 + lane;
+			const bool free_k = k < Kmax && (counts[k] - (k == zo ? 1 : 0)) <= 0;
+			const unsigned fb = __ballot_sync(0xffffffffu, free_k);
+			if (fb) fs = k0 + __ffs(fb) - 1;
+		}
+		if (fs < 0) { if (lane == 0) a.overflow[chain] = 1; return; }
+		new_slot = fs;
+		const float *src = s_aux + (best_c - Kmax) * PS;
+		for (int t = lane; t < PS; t += 32) theta[(size_t)fs * PS + t] = src[t];
+	}
+	__syncwarp();
+	if (lane == 0) {
+		const int before = counts[zo];
+		if (new_slot != zo || born) {
+			counts[zo] = before - 1;
+			counts[new_slot] += 1;
+			a.z[(size_t)item * a.C + chain] = (npb_z_t)new_slot;
+			int occ = a.kocc[chain];
+			if (before - 1 == 0 && new_slot != zo) occ--;
+			if (born && !(new_slot == zo)) occ++;
+			else if (born && new_slot == zo) occ += 0; // the emptied singleton's slot is re-used by the newborn
+			a.kocc[chain] = occ;
+			a.st[(size_t)chain * 4 + 1] += 1ull;
+			if (born) a.st[(size_t)chain * 4 + 2] += 1ull;
+		}
+		a.st[(size_t)chain * 4 + 0] += (unsigned long long)cand;
+	}
+}
+
+npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item) {
+	npb_ctx *ctx = ch->ctx;
+	SweepArgs a = make_args(ch, 0);
+	static uint32_t call = 0;
+	const size_t shmem = (size_t)ch->m_aux * npb_ps(ch->D) * sizeof(float);
+	k_update_item_alg8<<<(unsigned)n, 32, shmem, ctx->stream>>>(a, (int)chain0, (int)item, call++);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}

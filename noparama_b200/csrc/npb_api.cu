@@ -672,8 +672,18 @@ npb_status npb_fp32_peak(npb_ctx *ctx, double *tflops) {
 	return npb_launch_fma_peak(ctx, tflops);
 }
 
-npb_status npb_chain_update_alg8(npb_chains *ch, int64_t, int64_t) {
-	return npb_fail(ch ? ch->ctx : nullptr, NPB_E_UNSUPPORTED, "single-item seam not built yet");
+npb_status npb_chain_update_alg8(npb_chains *ch, int64_t chain, int64_t item) {
+	if (!ch) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	// chain < 0: the same item on every chain (what a lockstep driver of the reference's per-item loop does)
+	if (chain >= ch->C || item < 0 || item >= ch->ds->N) return NPB_E_BAD_ARG;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	npb_status s = ensure_whitened(ch->ds);
+	if (s != NPB_OK) return s;
+	s = chain < 0 ? npb_launch_update_item(ch, 0, ch->C, item) : npb_launch_update_item(ch, chain, 1, item);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
 }
 
 // theta in the replay kernel's double layout: mu[D], T upper packed, c = -0.5 (D log 2pi + log det Sigma)

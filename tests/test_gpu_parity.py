@@ -373,3 +373,41 @@ def test_algorithm2_distribution_matches_oracle(npb, ctx):
     with pytest.raises(npb.NpbError):
         mc3.chains.sweep(npb.ALG2, 1)
     ds.close()
+
+
+def test_single_item_seam_update(npb, ctx, oracle):
+    """npb_chain_update_alg8: one NealAlgorithm8::update(membertrix&, {item}) per call.  Every chain is put in the same
+    state; the empirical distribution of the cluster the item goes to must match the reference's categorical
+    p(x|theta_k) n_k / sum (np_neal_algorithm8.cpp:93-130, the item itself retracted) evaluated with the oracle's density."""
+    X, y = syn.config(1)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(2)).bind(ctx)
+    C = 4096
+    ch = npb.Chains(ctx, ds, C, Kmax=32, K0=8, seed=17)
+    # three overlapping clusters so that the item has a real choice
+    mu = np.array([[0.0, 0.0], [1.5, 1.0], [5.0, 5.0]])
+    Sigma = np.array([np.eye(2), [[1.5, 0.3], [0.3, 0.8]], np.eye(2)])
+    ch.init_from_params(mu, Sigma)
+    z0 = ch.assignments(0, 1)[0]
+    for c in range(1, C):
+        ch.set_state(c, z0, [0, 1, 2], mu, Sigma)
+    item = int(np.argmin(np.abs(X - np.array([0.9, 0.6])).sum(1)))
+    ch.update_item(item)
+    z = ch.assignments()
+    assert np.array_equal(np.delete(z, item, axis=1), np.tile(np.delete(z0, item), (C, 1)))   # only that item may move
+    for c in (0, 1, C - 1):
+        slots, counts, _, _ = ch.params(c)
+        assert counts.sum() == ds.N and np.array_equal(np.bincount(z[c], minlength=32)[slots], counts)
+    n = np.bincount(np.delete(z0, item), minlength=3).astype(float)
+    w = np.exp(oracle.mvn_logpdf_batch(mu, Sigma, X[item:item + 1])[0]) * n
+    p = w / w.sum()
+    chosen = z[:, item]
+    born = chosen > 2
+    assert born.mean() < 0.02            # the reference prior's auxiliary draws are far from the data
+    freq = np.bincount(chosen[~born], minlength=3) / (~born).sum()
+    assert p[:2].min() > 0.2 and np.all(np.abs(freq - p) < 4 * np.sqrt(p * (1 - p) / (~born).sum()) + 0.005), (freq, p)
+    # a second call draws afresh
+    ch.update_item(item)
+    assert not np.array_equal(ch.assignments()[:, item], chosen)
+    ch.close()
+    ds.close()
