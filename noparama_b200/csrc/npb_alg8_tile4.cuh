@@ -247,22 +247,24 @@ __device__ __forceinline__ float aux_birth_z(const Philox &ph, const PriorDev &p
 template <int D, int M>
 __global__ void __launch_bounds__(256) k_aux_keys(const SweepArgs a, uint32_t *out) {
 	const int sj = blockIdx.x * 256 + threadIdx.x;
-	const int chain = blockIdx.y, sw = blockIdx.z;
+	const int sw = blockIdx.z;
 	if (sj >= a.N) return;
-	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 	const int item = a.scan_order[(size_t)sw * a.N + sj];
-	float ak;
-	int am;
-	aux_race<D, M>(ph, a.prior, __ldg(a.Xwn + item), (uint32_t)sj, a.sweep0 + (uint32_t)sw,
-			a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT, ak, am);
-	out[((size_t)sw * a.C + chain) * a.N + sj] = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+	const float rn = __ldg(a.Xwn + item);
+	for (int chain = blockIdx.y; chain < a.C; chain += gridDim.y) { // grid.y is capped at 65535
+		const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+		float ak;
+		int am;
+		aux_race<D, M>(ph, a.prior, rn, (uint32_t)sj, a.sweep0 + (uint32_t)sw, a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT, ak, am);
+		out[((size_t)sw * a.C + chain) * a.N + sj] = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+	}
 }
 
 template <int D>
 npb_status npb_launch_aux_keys(npb_chains *ch, const SweepArgs &a) {
 	npb_ctx *ctx = ch->ctx;
 	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D >= 4 sweep kernel");
-	dim3 grid((unsigned)((a.N + 255) / 256), (unsigned)ch->C, (unsigned)a.n_sweeps);
+	dim3 grid((unsigned)((a.N + 255) / 256), (unsigned)(ch->C < 65535 ? ch->C : 65535), (unsigned)a.n_sweeps);
 	if (ch->m_aux == 3) k_aux_keys<D, 3><<<grid, 256, 0, ctx->stream>>>(a, ch->aux_keys);
 	else k_aux_keys<D, 1><<<grid, 256, 0, ctx->stream>>>(a, ch->aux_keys);
 	NPB_CUDA_OK(cudaGetLastError());
