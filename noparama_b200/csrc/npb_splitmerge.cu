@@ -8,9 +8,10 @@
 //
 // One CTA per chain.  A proposal is
 //   plan     thread 0 reads the slots of the picks and decides split / merge exactly like the reference's update();
-//   pool     the members of the source clusters, compacted from the chain's row of the (chain-major) assignment
-//            copy in ascending item order (membertrix::getAssignments, membertrix.cpp:315-322) and then visited in a
-//            keyed pseudo-random order (the reference shuffles the list, dim1algebra.hpp:2066-2073);
+//   pool     the member lists of the source clusters (membertrix::getAssignments, membertrix.cpp:315-322): the chain keeps
+//            every slot's items contiguous in a permutation array, rebuilt from its row of the (chain-major) assignment
+//            copy only after an accepted move; the pool is visited in a keyed pseudo-random order (the reference shuffles
+//            the list, dim1algebra.hpp:2066-2073);
 //   phase A  all threads: log2-densities of a chunk of pool members under the <= 3 parameter sets involved
 //            (sources + the fresh prior draw) -- the FP32 work, D(D+1)/2 + 2D FMAs per (member, theta) -- and the
 //            per-cluster sums  sum_{x in c} log p(x|theta_c)  of the acceptance ratio (fp64 accumulators);
@@ -126,11 +127,11 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 	__shared__ int s_id[SM_CHUNK];
 	__shared__ SMPlan s_plan;
 	__shared__ ScanOrder s_perm;
-	__shared__ int s_scan[SM_THREADS / 32 + 1];
 	__shared__ int s_npool, s_accept, s_newslot;
 	__shared__ int s_npart[3];
 	__shared__ double s_S[3][3];
 	__shared__ double s_red[SM_THREADS / 32];
+	extern __shared__ int s_off[]; // [Kmax + 1] start of every slot's member list in perm (rebuilt after an accepted move)
 
 	const int chain = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = a.N;
@@ -142,6 +143,44 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 	unsigned long long *st = a.smst + (size_t)chain * 12;
 	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 	const uint32_t c3 = NPB_RNG_SM | (a.sweep << 8);
+
+	// member lists of the chain: offsets from the counts, items in ascending order from the chain's row of z
+	// (deterministic: a batch of 32 items is grouped by slot with match.any, the group's first lane advances the cursor)
+	auto rebuild_lists = [&]() {
+		if (warp == 0) {
+			int run = 0;
+			for (int k0 = 0; k0 < a.Kmax; k0 += 32) {
+				const int c = counts[k0 + lane];
+				int incl = c;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const int t = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o) incl += t;
+				}
+				s_off[k0 + lane] = run + incl - c;
+				run += __shfl_sync(0xffffffffu, incl, 31);
+			}
+			__syncwarp();
+			for (int i0 = 0; i0 < N; i0 += 32) {
+				const int i = i0 + lane;
+				const unsigned active = __ballot_sync(0xffffffffu, i < N);
+				if (i < N) {
+					const int zz = zc[i];
+					const unsigned grp = __match_any_sync(active, zz);
+					const int rank = __popc(grp & ((1u << lane) - 1u));
+					const int b = s_off[zz];
+					pool[b + rank] = i;
+					__syncwarp(active);
+					if (rank == 0) s_off[zz] = b + __popc(grp);
+				}
+				__syncwarp();
+			}
+			// the cursors ran to the end of their segments: back to the starts
+			for (int k0 = 0; k0 < a.Kmax; k0 += 32) s_off[k0 + lane] -= counts[k0 + lane];
+		}
+		__syncthreads();
+	};
+	rebuild_lists();
 
 	for (int s = a.s0; s < a.s1; ++s) {
 		// ---------------- plan (np_jain_neal_algorithm.cpp:424-502 / np_triadic_algorithm.cpp:633-795) ----------------
@@ -228,52 +267,21 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 			s_perm = npb_scan_order(((uint64_t)w[1] << 32) | w[0], w[2], 2u);
 		}
 
-		// ---------------- pool: members of the source clusters, ascending item id ----------------
+		// ---------------- pool: the member lists of the source clusters, one after the other (membertrix::getAssignments
+		// per cluster, np_triadic_algorithm.cpp:230-238); perm[s_off[k] .. s_off[k] + counts[k]) holds slot k's items ----------------
+		int seg_start[3] = {0, 0, 0}, seg_end[3] = {0, 0, 0};
 		int base = 0;
-		for (int i0 = 0; i0 < N; i0 += SM_THREADS * 8) {
-			const int i = i0 + tid * 8;
-			unsigned flags = 0;
-			if (i + 8 <= N) {
-				const uint4 v = *reinterpret_cast<const uint4 *>(zc + i);
-				const unsigned wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-				for (int e = 0; e < 8; ++e) {
-					const int zz = (int)((wds[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu);
-					bool in = zz == p.th_slot[0];
-					if (p.nsrc > 1) in |= zz == p.th_slot[1];
-					if (p.nsrc > 2) in |= zz == p.th_slot[2];
-					flags |= (unsigned)in << e;
-				}
-			} else {
-				for (int e = 0; e < 8 && i + e < N; ++e) {
-					const int zz = zc[i + e];
-					bool in = zz == p.th_slot[0];
-					if (p.nsrc > 1) in |= zz == p.th_slot[1];
-					if (p.nsrc > 2) in |= zz == p.th_slot[2];
-					flags |= (unsigned)in << e;
-				}
-			}
-			const int cnt = __popc(flags);
-			int incl = cnt;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const int t = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o) incl += t;
-			}
-			if (lane == 31) s_scan[warp] = incl;
-			__syncthreads();
-			int woff = 0, total = 0;
-			for (int w = 0; w < SM_THREADS / 32; ++w) {
-				const int c = s_scan[w];
-				if (w < warp) woff += c;
-				total += c;
-			}
-			int pos = base + woff + incl - cnt;
-			for (unsigned f = flags; f; f &= f - 1) pool[pos++] = i + __ffs(f) - 1;
-			base += total;
-			__syncthreads();
+		for (int k = 0; k < p.nsrc; ++k) {
+			seg_start[k] = s_off[p.th_slot[k]] - base; // pool position t of source k maps to perm[t + seg_start[k]]
+			base += counts[p.th_slot[k]];
+			seg_end[k] = base;
 		}
+		auto pool_item = [&](int t) -> int {
+			const int k = t < seg_end[0] ? 0 : (t < seg_end[1] ? 1 : 2);
+			return pool[t + seg_start[k]];
+		};
 		const int npool = base;
+		__syncthreads(); // the keys of s_perm (thread 32) are in place before its size is patched (thread 0)
 		if (tid == 0) {
 			s_perm.N = (uint32_t)npool;
 			uint32_t bits = 2;
@@ -281,8 +289,7 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 			s_perm.half_bits = (bits + 1) / 2;
 			s_perm.half_mask = (1u << s_perm.half_bits) - 1u;
 		}
-		__syncthreads(); // pool (global) written by this block is read below: make it visible
-		__threadfence_block();
+		__syncthreads();
 
 		// ---------------- chunks: phase A (densities, all threads) + phase B (sequential scan, warp 0) ----------------
 		double own[3] = {0.0, 0.0, 0.0};   // sum over members of source c of log2 p(x|theta_c)
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 					const int j = tid + m * SM_THREADS;
 					id[m] = -1; ownk[m] = -1;
 					if (j < cnt) {
-						id[m] = pool[npb_scan_item(perm, (uint32_t)(t0 + j))];
+						id[m] = pool_item((int)npb_scan_item(perm, (uint32_t)(t0 + j)));
 						const int zz = zc[id[m]];
 						ownk[m] = zz == p.th_slot[0] ? 0 : (zz == p.th_slot[1] ? 1 : 2);
 					}
@@ -481,11 +488,13 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 			int tg[3];
 			for (int q = 0; q < 3; ++q) tg[q] = (q < p.Q) ? (p.tgt_slot[q] >= 0 ? p.tgt_slot[q] : newslot) : 0;
 			for (int t = tid; t < npool; t += SM_THREADS) {
-				const int id = pool[npb_scan_item(perm, (uint32_t)t)];
+				const int id = pool_item((int)npb_scan_item(perm, (uint32_t)t));
 				zc[id] = (npb_z_t)tg[dec[t]];
 			}
 			if (newslot >= 0)
 				for (int t = tid; t < PS; t += SM_THREADS) theta[(size_t)newslot * PS + t] = s_th[p.nth - 1][t];
+			__syncthreads();
+			rebuild_lists(); // the partition changed
 		}
 		__syncthreads();
 	}
@@ -542,6 +551,7 @@ npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposa
 	dim3 g1((C + 31) / 32, (N + 31) / 32), g2((N + 31) / 32, (C + 31) / 32);
 	k_z_transpose<<<g1, tb, 0, ctx->stream>>>(ch->z, ch->sm_zt, N, C, C, zstride);
 	NPB_CUDA_OK(cudaGetLastError());
+	const size_t smem_off = (size_t)(ch->Kmax + 1) * sizeof(int);
 	int64_t left = whole_sweeps ? (int64_t)whole_sweeps * N : n_proposals;
 	while (left > 0) {
 		const int n = (int)(left < N ? left : N);
@@ -550,11 +560,11 @@ npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposa
 		NPB_CUDA_OK(cudaGetLastError());
 		a.s0 = 0; a.s1 = n; a.sweep = ch->sweep;
 		switch (ch->D) {
-		case 2: k_split_merge<2><<<C, SM_THREADS, 0, ctx->stream>>>(a); break;
-		case 3: k_split_merge<3><<<C, SM_THREADS, 0, ctx->stream>>>(a); break;
-		case 4: k_split_merge<4><<<C, SM_THREADS, 0, ctx->stream>>>(a); break;
-		case 8: k_split_merge<8><<<C, SM_THREADS, 0, ctx->stream>>>(a); break;
-		case 16: k_split_merge<16><<<C, SM_THREADS, 0, ctx->stream>>>(a); break;
+		case 2: k_split_merge<2><<<C, SM_THREADS, smem_off, ctx->stream>>>(a); break;
+		case 3: k_split_merge<3><<<C, SM_THREADS, smem_off, ctx->stream>>>(a); break;
+		case 4: k_split_merge<4><<<C, SM_THREADS, smem_off, ctx->stream>>>(a); break;
+		case 8: k_split_merge<8><<<C, SM_THREADS, smem_off, ctx->stream>>>(a); break;
+		case 16: k_split_merge<16><<<C, SM_THREADS, smem_off, ctx->stream>>>(a); break;
 		default: return npb_fail(ctx, NPB_E_UNSUPPORTED, "split-merge kernels cover D = 2, 3, 4, 8, 16");
 		}
 		NPB_CUDA_OK(cudaGetLastError());
