@@ -176,6 +176,12 @@ npb_status npb_replay_split_merge(npb_ctx *ctx, npb_dataset *ds, int sampler, in
 		const double *uacc, const int32_t *new_slot, int32_t *type_out, int32_t *dec_out, int32_t *accept_out, double *logA_out,
 		int32_t *z_final_out);
 
+/* parity probe (Kmax = 32, D = 4 / 8 / 16): the [32 slots x 32 items] log-density tile exactly as the sweep kernel's producer
+ * warp computes it (packed FP32, the mean folded into a per-row offset), natural-log units, out[slot * 32 + j] for the 32
+ * given items; NaN for a slot without members.  For the 1e-5 relative bar on log-densities
+ * (multivariatenormal.cpp:106-136). */
+npb_status npb_chains_probe_tile_logdensity(npb_chains *ch, int64_t chain, const int32_t *items32, float *out);
+
 /* state readback: replaces membertrix::getClusterId / getClusters / count (membertrix.cpp:235-257,328-330) */
 npb_status npb_chains_get_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out /* [n,N] slot ids */);
 npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts,

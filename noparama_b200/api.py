@@ -29,6 +29,7 @@ EXPORTS = [
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
     "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
+    "npb_chains_probe_tile_logdensity",
 ]
 
 
@@ -90,6 +91,7 @@ def load_library():
                                          C.POINTER(i64), ip, dp, dp, ip, ip, ip, ip, dp, ip]
     L.npb_chains_get_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_consider_max_likelihood.argtypes = [vp, dp, dp]
+    L.npb_chains_probe_tile_logdensity.argtypes = [vp, i64, ip, C.POINTER(C.c_float)]
     L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -299,6 +301,15 @@ class Chains:
         st = SweepStats()
         self.ctx.check(self.ctx._lib.npb_chains_sweep(self._h, sampler, n_sweeps, C.byref(st) if want_stats else None))
         return st
+
+    def probe_tile_logdensity(self, chain, items32):
+        """[32 slots, 32 items] log-densities as the D >= 4 sweep kernel's producer warp computes them (parity probe)"""
+        items32 = np.ascontiguousarray(items32, dtype=np.int32)
+        assert len(items32) == 32
+        out = np.empty((32, 32), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.npb_chains_probe_tile_logdensity(self._h, chain, _ip(items32),
+                                                                       out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
 
     def update_item(self, item, chain=-1):
         """one NealAlgorithm8::update(membertrix&, {item}) on `chain` (every chain if negative): the single-item seam"""

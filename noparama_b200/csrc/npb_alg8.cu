@@ -153,7 +153,8 @@ NPB_DECL(3, 1) NPB_DECL(3, 2) NPB_DECL(3, 4) NPB_DECL(3, 8)
 NPB_TDECL(4, 32) NPB_TDECL(4, 64) NPB_TDECL(8, 32) NPB_TDECL(8, 64) NPB_TDECL(16, 32) NPB_TDECL(16, 64)
 #undef NPB_TDECL
 #define NPB_T4DECL(D) extern template npb_status npb_launch_alg8_tile4<D>(npb_chains *, const SweepArgs &); \
-	extern template npb_status npb_launch_aux_keys<D>(npb_chains *, const SweepArgs &);
+	extern template npb_status npb_launch_aux_keys<D>(npb_chains *, const SweepArgs &); \
+	extern template npb_status npb_launch_tile4_probe<D>(npb_chains *, const SweepArgs &, int, const int32_t *, float *);
 NPB_T4DECL(4) NPB_T4DECL(8) NPB_T4DECL(16)
 #undef NPB_T4DECL
 
@@ -330,4 +331,15 @@ npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int
 	k_update_item_alg8<<<(unsigned)n, 32, shmem, ctx->stream>>>(a, (int)chain0, (int)item, call++);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
+}
+
+npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out) {
+	SweepArgs a = make_args(ch, 0);
+	if (ch->Kmax != 32) return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers the Kmax = 32 kernels");
+	switch (ch->D) {
+	case 4: return npb_launch_tile4_probe<4>(ch, a, chain, d_items, d_out);
+	case 8: return npb_launch_tile4_probe<8>(ch, a, chain, d_items, d_out);
+	case 16: return npb_launch_tile4_probe<16>(ch, a, chain, d_items, d_out);
+	default: return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers D = 4, 8, 16");
+	}
 }

@@ -535,3 +535,41 @@ npb_status npb_launch_alg8_tile4(npb_chains *ch, const SweepArgs &a) {
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
+
+// Parity probe: the [32 slots x 32 items] log-density tile exactly as the producer warp of k_alg8_sweep_tile4 computes
+// it (same parameter form, same packed-FP32 instruction sequence), in natural-log units, for one chain and 32 given
+// items.  out[slot * 32 + j]; slots without members are written as NaN.
+template <int D>
+__global__ void __launch_bounds__(32) k_tile4_density_probe(const SweepArgs a, int chain, const int32_t *items, float *out) {
+	constexpr int PS = npb_ps(D), PSP = npb_psp(D);
+	__shared__ __align__(16) float xs[NPB_TILE * D];
+	const int lane = threadIdx.x;
+	float P[PSP];
+	load_theta_nb<D>(a.theta + ((size_t)chain * 32 + lane) * PS, P);
+	{
+		const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)items[lane] * D);
+		float *dst = xs + (lane >> 1) * (2 * D) + (lane & 1);
+#pragma unroll
+		for (int c = 0; c < D / 4; ++c) {
+			const float4 v = __ldg(src + c);
+			dst[(4 * c + 0) * 2] = v.x; dst[(4 * c + 1) * 2] = v.y;
+			dst[(4 * c + 2) * 2] = v.z; dst[(4 * c + 3) * 2] = v.w;
+		}
+	}
+	__syncwarp();
+	const bool occupied = a.counts[(size_t)chain * 32 + lane] > 0;
+	for (int j = 0; j < NPB_TILE; j += 2) {
+		float l0, l1;
+		log2density_pair<D>(P, reinterpret_cast<const f32x2_t *>(xs + j * D), l0, l1);
+		out[lane * 32 + j] = occupied ? l0 * NPB_LN2 : NAN;
+		out[lane * 32 + j + 1] = occupied ? l1 * NPB_LN2 : NAN;
+	}
+}
+
+template <int D>
+npb_status npb_launch_tile4_probe(npb_chains *ch, const SweepArgs &a, int chain, const int32_t *d_items, float *d_out) {
+	npb_ctx *ctx = ch->ctx;
+	k_tile4_density_probe<D><<<1, 32, 0, ctx->stream>>>(a, chain, d_items, d_out);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}

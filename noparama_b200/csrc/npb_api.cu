@@ -941,3 +941,21 @@ npb_status npb_chains_get_best_assignments(npb_chains *ch, int64_t chain0, int64
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }
+
+npb_status npb_chains_probe_tile_logdensity(npb_chains *ch, int64_t chain, const int32_t *items32, float *out) {
+	if (!ch || !items32 || !out || chain < 0 || chain >= ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	for (int j = 0; j < 32; ++j)
+		if (items32[j] < 0 || items32[j] >= ch->ds->N) return NPB_E_BAD_ARG;
+	DevBuf<int32_t> d_items;
+	DevBuf<float> d_out;
+	NPB_CUDA_OK(d_items.alloc(32));
+	NPB_CUDA_OK(d_out.alloc(32 * 32));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_items.p, items32, sizeof(int32_t) * 32, cudaMemcpyHostToDevice, ctx->stream));
+	npb_status s = npb_launch_tile_probe(ch, (int)chain, d_items.p, d_out.p);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaMemcpyAsync(out, d_out.p, sizeof(float) * 32 * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}

@@ -127,6 +127,7 @@ void npb_theta_to_sigma(int D, const double *T_packed_upper, double *Sigma);
 npb_status npb_launch_whiten(npb_dataset *ds);
 npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given);
 npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps);
+npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item);
 npb_status npb_launch_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);
 npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, int whole_sweeps, float *d_detail);

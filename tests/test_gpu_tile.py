@@ -184,3 +184,31 @@ def test_tile4_algorithm2_single_auxiliary_draw(npb, ctx):
         invariants(mc.chains, z[c], c, ds.N)
     assert mc.chains.metrics(y)["purity"].mean() > 0.99
     ds.close()
+
+
+@pytest.mark.parametrize("D", [4, 8, 16])
+def test_tile4_producer_logdensity_within_1e5_of_oracle(npb, ctx, oracle, D):
+    """The log-density tile of the sweep kernel's producer warp (packed FP32, y = T2 x - T2 mu with the mean folded into a
+    per-row offset) against the oracle's double-precision density: 1e-5 relative (north_star tolerance), for full
+    covariances, near and far clusters."""
+    rng = np.random.default_rng(D)
+    K = 32
+    X, y = syn.gmm(4000, D, 8, 200 + D)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(D)).bind(ctx)
+    ch = npb.Chains(ctx, ds, 3, Kmax=32, K0=8, seed=1)
+    mu = X[rng.integers(0, len(X), K)] + 0.5 * rng.standard_normal((K, D))
+    B = rng.standard_normal((K, D, D)) / np.sqrt(D)
+    Sigma = B @ np.transpose(B, (0, 2, 1)) + 0.3 * np.eye(D)
+    ch.init_from_params(mu, Sigma)
+    items = rng.integers(0, len(X), 32)
+    got = ch.probe_tile_logdensity(1, items).astype(np.float64)     # [slot, item]
+    slots, counts, _, _ = ch.params(1)
+    want = oracle.mvn_logpdf_batch(mu, Sigma, X[items]).T           # [slot, item]
+    occ = np.zeros(32, bool)
+    occ[slots] = True
+    assert occ.sum() >= 30 and np.all(np.isnan(got[~occ]))
+    err = np.abs(got[occ] - want[occ]) / np.maximum(1.0, np.abs(want[occ]))
+    assert err.max() < 1e-5, err.max()
+    ch.close()
+    ds.close()
