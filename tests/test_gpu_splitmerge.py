@@ -282,3 +282,44 @@ def test_split_merge_replay_bit_exact_config1(npb, ctx, oracle, sampler_name, se
     fin = np.isfinite(t["logA"])
     assert np.allclose(out["logA"][fin], t["logA"][fin], rtol=1e-9, atol=1e-7)
     ds.close()
+
+
+@pytest.mark.parametrize("D,kmax", [(2, 64), (16, 32)])
+def test_mixed_schedule_keeps_the_state_consistent(npb, ctx, D, kmax):
+    """One handle driven through every entry point in turn (Gibbs sweeps, triadic and Jain-Neal proposals, single-item
+    updates, parameter refresh, max-likelihood snapshot): the bookkeeping invariants must hold after each."""
+    X, y = syn.gmm(800, D, 5, 400 + D)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(D)).bind(ctx)
+    ch = npb.Chains(ctx, ds, 10, Kmax=kmax, K0=8, seed=8)
+    means = np.stack([X[y == k].mean(0) for k in range(5)])
+    ch.init_from_params(means + 0.3, np.tile(np.eye(D), (5, 1, 1)))
+    pr = dict(mu0=X.mean(0), kappa=0.01, nu=D + 2.0, Lambda=np.eye(D))
+
+    def check():
+        z = ch.assignments()
+        for c in (0, 9):
+            check_state(ch, z[c], c, ds.N)
+        m = ch.metrics(y)
+        assert np.array_equal(m["K"], [len(np.unique(z[c])) for c in range(10)])
+        return z
+
+    for rnd in range(2):
+        assert ch.sweep(npb.ALG8, 2).overflow_chains == 0
+        check()
+        ch.split_merge(npb.TRIADIC, 150)
+        check()
+        ch.update_params(npb.UPDATE_POSTERIOR_DRAW, pr)
+        check()
+        ch.sweep(npb.JAIN_NEAL, 1)
+        check()
+        if D == 2:
+            ch.update_item(17)
+            check()
+        cur, best = ch.consider_max_likelihood()
+        assert np.all(best >= cur - 1e-9)
+        ch.sweep(npb.ALG8, 1)
+        z = check()
+    assert ch.best_assignments().shape == z.shape
+    ch.close()
+    ds.close()
