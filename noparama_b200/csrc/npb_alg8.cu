@@ -180,11 +180,14 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	// earlier one-chain-per-CTA kernel for A/B measurements
 	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
 	if (!two_warp && ch->Kmax == 32 && (ch->D == 4 || ch->D == 8 || ch->D == 16)) key = -ch->D;
+	if (ch->Kmax == 32 && ch->D == 64) key = -64;
 	switch (key) {
 	// pre-pass (state independent, fully parallel): the race key of every (chain, step)'s auxiliary draws; then the sweep
 	case -4: s = npb_launch_aux_keys<4>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<4>(ch, a); break;
 	case -8: s = npb_launch_aux_keys<8>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<8>(ch, a); break;
 	case -16: s = npb_launch_aux_keys<16>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<16>(ch, a); break;
+	// D = 64: block-wise tcgen05 density table + warp-per-chain race (npb_alg8_gemm.cu)
+	case -64: s = npb_launch_alg8_gemm64(ch, a); break;
 	case 2001: s = npb_launch_alg8_reg<2, 1>(ch, a); break;
 	case 2002: s = npb_launch_alg8_reg<2, 2>(ch, a); break;
 	case 2004: s = npb_launch_alg8_reg<2, 4>(ch, a); break;
@@ -202,7 +205,7 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	case 16002: s = npb_launch_alg8_tile<16, 64>(ch, a); break;
 	default:
 		return npb_fail(ctx, NPB_E_UNSUPPORTED,
-				"Alg. 8 sweep kernels cover D = 2 (Kmax 32..512), D = 3 (Kmax 32..256) and D = 4, 8, 16 (Kmax 32/64)");
+				"Alg. 8 sweep kernels cover D = 2 (Kmax 32..512), D = 3 (Kmax 32..256), D = 4, 8, 16 (Kmax 32/64) and D = 64 (Kmax 32)");
 	}
 	if (s == NPB_OK) ch->sweep += (uint32_t)n_sweeps;
 	return s;
@@ -218,7 +221,7 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->scan_order, per_sweep * ch->scan_cap));
 	}
 	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
-	if (!two_warp && ch->Kmax == 32 && ch->D >= 4 && !ch->aux_keys) {
+	if ((!two_warp || ch->D == 64) && ch->Kmax == 32 && ch->D >= 4 && !ch->aux_keys) {
 		// as many sweeps per launch as fit 4 GB of auxiliary keys (one 32-bit word per chain and step)
 		const size_t per_sweep = (size_t)ch->ds->N * ch->C * sizeof(uint32_t);
 		size_t cap = ((size_t)4 << 30) / per_sweep;
@@ -337,9 +340,10 @@ npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_ite
 	SweepArgs a = make_args(ch, 0);
 	if (ch->Kmax != 32) return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers the Kmax = 32 kernels");
 	switch (ch->D) {
+	case 64: return npb_launch_gemm64_probe(ch, chain, d_items, d_out);
 	case 4: return npb_launch_tile4_probe<4>(ch, a, chain, d_items, d_out);
 	case 8: return npb_launch_tile4_probe<8>(ch, a, chain, d_items, d_out);
 	case 16: return npb_launch_tile4_probe<16>(ch, a, chain, d_items, d_out);
-	default: return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers D = 4, 8, 16");
+	default: return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers D = 4, 8, 16, 64");
 	}
 }

@@ -1,0 +1,730 @@
+// npb_alg8_gemm.cu -- Algorithm 8 / Algorithm 2 sweeps at D = 64 (Kmax = 32): the whitened quadratic forms of a block of
+// steps as a tcgen05 GEMM (BASELINE configs[3]: "tensor-core whitened quadratic forms"), the sequential race as a
+// warp-per-chain consumer.
+//
+// Same algorithm and the same reference lines as the D <= 16 kernels (NealAlgorithm8::update,
+// src/np_neal_algorithm8.cpp:49-167; density: src/statistics/multivariatenormal.cpp:106-136), a different mapping: at
+// D = 64 a cluster slot is 2145 floats, so neither the registers of a lane (npb_alg8_tile4.cuh) nor shared memory hold a
+// chain's slot table, and a density is 2080 FMAs -- GEMM-shaped work.  A sweep is cut into blocks of NPB_G_BS steps; per
+// block, in stream order:
+//   k_pre_aimg     gathers the block's item rows (scan order), centres them on the dataset mean, splits every
+//                  coordinate into two TF32 terms (hi + lo) and writes them as the shared-memory IMAGE of the A operand
+//                  (K-major, 128-byte swizzle), one 32 KB image per (128-step tile, half of K);
+//   k_pre_bimg     does the same for the slots whose parameters changed (births; everything at the first block of a
+//                  launch): the upper-triangular factor T2 as the B operand image, nb = -T2 (mu - xbar) and c2 aside;
+//   k_density_tc   persistent, one CTA per SM, unit of work = (chain, 4 slots): the four slots' B images stay resident
+//                  in shared memory (96 KB) while the block's A images stream through a three-stage ring of
+//                  cp.async.bulk copies (no register staging); one thread issues tcgen05.mma kind::tf32 128 x 256 x 8
+//                  (3xTF32: hi*hi + hi*lo + lo*hi, FP32 accumulation in TMEM, two accumulator buffers of 256 columns);
+//                  four epilogue warps read the accumulators back (tcgen05.ld 32x32b), form
+//                  c2 - sum_j (y_j + nb_j)^2 per (step, slot) and write the block's log2-density table
+//                  L[chain][step][slot].  T2 is upper triangular, so the first half of K only feeds rows j < 32: the
+//                  rows of B are ordered (j / 32, slot, j % 32) and the first K-half is issued with N = 128, a quarter
+//                  of the MMA work saved;
+//   k_alg8_sweep_pre  one warp per chain, lane = slot: the exponential race of every step of the block from L, the
+//                  auxiliary keys of k_aux_keys and the member counts -- the consumer of npb_alg8_tile4.cuh with the
+//                  producer warp replaced by a table in L2.  A birth writes theta' to the slot table, re-evaluates the
+//                  slot's column of L for the rest of the block on the CUDA cores and marks the slot for k_pre_bimg.
+// NPB_D64_DENSITY=fp32 replaces k_density_tc by a plain FP32 kernel (A/B measurements, cross-check in the tests).
+#include "npb_alg8_tile4.cuh"
+#include <cstdlib>
+
+namespace {
+constexpr int GD = 64;
+constexpr int GPS = npb_ps(GD);     // 2145
+constexpr int GTRI = npb_tri(GD);   // 2080
+constexpr int G_M = 128;            // steps per A tile (UMMA M)
+constexpr int G_NS = 4;             // slots per unit of work (UMMA N = 64 * 4)
+constexpr int G_STAGES = 3;         // A ring
+constexpr int G_CHUNK = 4096;       // 32 rows x 128 bytes, swizzled
+constexpr int G_SLOT_IMG = 6 * G_CHUNK;   // (kh0: hi, lo) x jh0; (kh1: hi, lo) x (jh0, jh1)
+constexpr int G_ASTAGE = 32768;     // 128 rows x 128 bytes, hi then lo
+constexpr int G_BBYTES = 98304;     // R0hi 16K, R0lo 16K, R1hi 32K, R1lo 32K
+constexpr int G_CONST = 68;         // nb[64], c2, pad
+constexpr int G_SMEM_MISC = 2048;
+constexpr int G_SMEM = 1024 + G_BBYTES + G_STAGES * G_ASTAGE + G_SMEM_MISC;
+constexpr uint32_t G_R0HI = 0, G_R0LO = 16384, G_R1HI = 32768, G_R1LO = 65536, G_A0 = G_BBYTES;
+}
+
+struct GemmArgs {
+	const uint8_t *Aimg;  // [ntiles][2][32 KB]
+	const uint8_t *Bimg;  // [C * 32][24 KB]
+	const float *Bconst;  // [C * 32][G_CONST]
+	float *L;             // [C][BS][32]
+	int C, ntiles, BS;
+};
+
+struct PreArgs {
+	SweepArgs a;
+	float *L;
+	uint8_t *dirty;       // [C * 32]
+	int BS, sw, s0, nsteps;
+};
+
+// byte offset of float k (0..31) of row `row` in a K-major, 128-byte-swizzled region (rows of 128 bytes, base 1024-aligned)
+__host__ __device__ __forceinline__ uint32_t g_sw128(uint32_t row, uint32_t k) {
+	return row * 128u + ((((k >> 2) ^ (row & 7u)) << 4) | ((k & 3u) << 2));
+}
+__device__ __forceinline__ float g_tf32(float v) {
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+	return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// column means of the dataset (double), once per dataset
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_colmean(const double *X, int64_t N, int D, double *out) {
+	__shared__ double red[256];
+	const int c = blockIdx.x;
+	double s = 0.0;
+	for (int64_t i = threadIdx.x; i < N; i += 256) s += X[i * D + c];
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[c] = red[0] / (double)N;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A images of one block of steps: thread = (step, 16-byte piece)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pre_aimg(const double *X64, const double *xbar, const int32_t *order, int nsteps, int ntiles,
+		uint8_t *Aimg) {
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	const int s = idx >> 4, q = idx & 15;
+	if (s >= ntiles * G_M) return;
+	float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+	if (s < nsteps) {
+		const double *x = X64 + (size_t)order[s] * GD + q * 4;
+#pragma unroll
+		for (int e = 0; e < 4; ++e) v[e] = (float)(x[e] - xbar[q * 4 + e]);
+	}
+	float4 hi, lo;
+	hi.x = g_tf32(v[0]); hi.y = g_tf32(v[1]); hi.z = g_tf32(v[2]); hi.w = g_tf32(v[3]);
+	lo.x = g_tf32(v[0] - hi.x); lo.y = g_tf32(v[1] - hi.y); lo.z = g_tf32(v[2] - hi.z); lo.w = g_tf32(v[3] - hi.w);
+	const int t = s / G_M, r = s % G_M, kh = q >> 3, kk = (q & 7) * 4;
+	uint8_t *dst = Aimg + ((size_t)t * 2 + kh) * G_ASTAGE + g_sw128(r, kk);
+	*reinterpret_cast<float4 *>(dst) = hi;
+	*reinterpret_cast<float4 *>(dst + 16384) = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// B images and epilogue constants of the slots marked dirty: CTA = (chain, slot)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pre_bimg(const float *theta, const double *xbar, uint8_t *dirty, uint8_t *Bimg, float *Bconst) {
+	__shared__ float th[GPS + 3];
+	const int cs = blockIdx.x; // chain * 32 + slot
+	if (!dirty[cs]) return;
+	const float *src = theta + (size_t)cs * GPS;
+	for (int i = threadIdx.x; i < GPS; i += 256) th[i] = src[i];
+	__syncthreads();
+	if (threadIdx.x < GD) {
+		const int j = threadIdx.x;
+		float s = 0.0f;
+		for (int c = j; c < GD; ++c) s = fmaf(th[GD + npb_tri_off(GD, j, c)], (float)((double)th[c] - xbar[c]), s);
+		Bconst[(size_t)cs * G_CONST + j] = -s;
+	}
+	if (threadIdx.x == GD) Bconst[(size_t)cs * G_CONST + GD] = th[GD + GTRI];
+	uint8_t *img = Bimg + (size_t)cs * G_SLOT_IMG;
+	// chunk: 0 (kh0, hi, jh0)  1 (kh0, lo, jh0)  2 (kh1, hi, jh0)  3 (kh1, hi, jh1)  4 (kh1, lo, jh0)  5 (kh1, lo, jh1)
+	for (int pc = threadIdx.x; pc < 6 * 256; pc += 256) {
+		const int chunk = pc >> 8, jl = (pc >> 3) & 31, p = pc & 7;
+		const int kh = chunk >= 2, part = (chunk == 1 || chunk >= 4), jh = (chunk == 3 || chunk == 5);
+		const int j = jh * 32 + jl;
+		float o[4];
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			const int c = kh * 32 + p * 4 + e;
+			const float t = c >= j ? th[GD + npb_tri_off(GD, j, c)] : 0.0f;
+			const float hi = g_tf32(t);
+			o[e] = part ? g_tf32(t - hi) : hi;
+		}
+		*reinterpret_cast<float4 *>(img + chunk * G_CHUNK + g_sw128(jl, p * 4)) = make_float4(o[0], o[1], o[2], o[3]);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) dirty[cs] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk copy, tcgen05
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t g_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile(
+			"{\n\t"
+			".reg .pred p;\n\t"
+			"WAIT_LOOP:\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+			"@p bra WAIT_DONE;\n\t"
+			"bra WAIT_LOOP;\n\t"
+			"WAIT_DONE:\n\t"
+			"}\n" ::"r"(bar), "r"(parity)
+			: "memory");
+}
+__device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+			"r"(bar)
+			: "memory");
+}
+__device__ __forceinline__ void g_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void g_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void g_tc_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor:
+// start address >> 4 at [0,14), leading byte offset >> 4 at [16,30) (= 1, unused with a swizzle), stride byte offset >> 4 at
+// [32,46), version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64))
+__device__ __forceinline__ uint64_t g_desc(uint32_t saddr) {
+	return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::tf32: D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10) and [10,13)), both K-major, N >> 3 at
+// [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t g_idesc(int M, int N) {
+	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void g_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+			"{\n\t"
+			".reg .pred p;\n\t"
+			"setp.ne.b32 p, %4, 0;\n\t"
+			"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+			"}\n" ::"r"(tmem_d),
+			"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+			: "memory");
+}
+__device__ __forceinline__ void g_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+	uint32_t r[32];
+	asm volatile(
+			"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+			"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+			"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+			: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+			  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+			  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+			  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+			: "r"(taddr)
+			: "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_density_tc: warps 0-3 epilogue (TMEM lanes 32 w .. 32 w + 31 = steps of the tile), warp 4 MMA issue + TMEM
+// allocation, warp 5 bulk-copy producer
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1) k_density_tc(const GemmArgs g) {
+	extern __shared__ uint8_t g_smem_raw[];
+	const uint32_t raw = g_smem_u32(g_smem_raw);
+	const uint32_t base = (raw + 1023u) & ~1023u;
+	uint8_t *gen = g_smem_raw + (base - raw);
+	// misc area: barriers, TMEM address, epilogue constants
+	const uint32_t misc = base + G_BBYTES + G_STAGES * G_ASTAGE;
+	const uint32_t bar_b_full = misc, bar_b_empty = misc + 8;
+	const uint32_t bar_a_full = misc + 16, bar_a_empty = misc + 16 + 8 * G_STAGES;
+	const uint32_t bar_t_full = misc + 16 + 16 * G_STAGES, bar_t_empty = bar_t_full + 16;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + 256);
+	float *econst = reinterpret_cast<float *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + 512); // [4][G_CONST]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n_units = g.C * (32 / G_NS);
+
+	if (warp == 5 && lane == 0) {
+		g_mbar_init(bar_b_full, 1);
+		g_mbar_init(bar_b_empty, 1);
+		for (int s = 0; s < G_STAGES; ++s) {
+			g_mbar_init(bar_a_full + 8 * s, 1);
+			g_mbar_init(bar_a_empty + 8 * s, 1);
+		}
+		for (int b = 0; b < 2; ++b) {
+			g_mbar_init(bar_t_full + 8 * b, 1);
+			g_mbar_init(bar_t_empty + 8 * b, 128);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async;" ::: "memory");
+	}
+	if (warp == 4) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	g_tc_fence_after();
+	const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+	if (warp == 5) {
+		// ===================== bulk-copy producer =====================
+		if (lane == 0) {
+			uint32_t a_it = 0, unit_it = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				g_mbar_wait(bar_b_empty, (unit_it & 1u) ^ 1u); // the MMAs of the previous unit have read B
+				g_mbar_expect_tx(bar_b_full, G_BBYTES);
+				const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
+				for (int sl = 0; sl < G_NS; ++sl) {
+					const uint8_t *src = g.Bimg + ((size_t)c * 32 + gq * G_NS + sl) * G_SLOT_IMG;
+					g_bulk_g2s(base + G_R0HI + sl * G_CHUNK, src + 0 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_R0LO + sl * G_CHUNK, src + 1 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_R1HI + sl * G_CHUNK, src + 2 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_R1HI + 16384 + sl * G_CHUNK, src + 3 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_R1LO + sl * G_CHUNK, src + 4 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_R1LO + 16384 + sl * G_CHUNK, src + 5 * G_CHUNK, G_CHUNK, bar_b_full);
+				}
+				for (int st = 0; st < g.ntiles * 2; ++st, ++a_it) {
+					const uint32_t s = a_it % G_STAGES, ph = (a_it / G_STAGES) & 1u;
+					g_mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+					g_mbar_expect_tx(bar_a_full + 8 * s, G_ASTAGE);
+					g_bulk_g2s(base + G_A0 + s * G_ASTAGE, g.Aimg + (size_t)st * G_ASTAGE, G_ASTAGE, bar_a_full + 8 * s);
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == 4) {
+		// ===================== MMA issue (one thread) =====================
+		if (lane == 0) {
+			constexpr uint32_t ID128 = g_idesc(G_M, 128), ID256 = g_idesc(G_M, 256);
+			uint32_t a_it = 0, tile_it = 0, unit_it = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				g_mbar_wait(bar_b_full, unit_it & 1u);
+				g_tc_fence_after();
+				for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+					const uint32_t buf = tile_it & 1u;
+					g_mbar_wait(bar_t_empty + 8 * buf, ((tile_it >> 1) & 1u) ^ 1u); // the epilogue has drained this accumulator
+					g_tc_fence_after();
+					const uint32_t dcol = tmem + buf * 256u;
+#pragma unroll
+					for (int kh = 0; kh < 2; ++kh, ++a_it) {
+						const uint32_t s = a_it % G_STAGES;
+						g_mbar_wait(bar_a_full + 8 * s, (a_it / G_STAGES) & 1u);
+						g_tc_fence_after();
+						const uint32_t Ahi = base + G_A0 + s * G_ASTAGE, Alo = Ahi + 16384;
+						const uint32_t Bhi = base + (kh ? G_R1HI : G_R0HI), Blo = base + (kh ? G_R1LO : G_R0LO);
+#pragma unroll
+						for (int prod = 0; prod < 3; ++prod) {
+							const uint32_t A = prod == 2 ? Alo : Ahi, B = prod == 1 ? Blo : Bhi;
+#pragma unroll
+							for (int k = 0; k < 4; ++k) {
+								const uint64_t ad = g_desc(A + k * 32), bd = g_desc(B + k * 32);
+								if (kh == 0) {
+									g_mma_tf32(dcol, ad, bd, ID128, (prod | k) != 0);
+								} else if (prod == 0 && k == 0) {
+									// columns 0-127 already hold the first K-half, columns 128-255 start here
+									g_mma_tf32(dcol, ad, bd, ID128, 1u);
+									g_mma_tf32(dcol + 128u, ad, g_desc(B + 16384 + k * 32), ID128, 0u);
+								} else {
+									g_mma_tf32(dcol, ad, bd, ID256, 1u);
+								}
+							}
+						}
+						g_tc_commit(bar_a_empty + 8 * s); // frees the stage once these MMAs have read it
+					}
+					g_tc_commit(bar_t_full + 8 * buf);
+				}
+				g_tc_commit(bar_b_empty);
+			}
+		}
+		__syncwarp();
+	} else {
+		// ===================== epilogue: thread = step of the tile =====================
+		const int row = warp * 32 + lane;
+		uint32_t tile_it = 0;
+		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+			const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			{
+				const float *src = g.Bconst + ((size_t)c * 32 + gq * G_NS) * G_CONST;
+				for (int i = threadIdx.x; i < G_NS * G_CONST; i += 128) econst[i] = __ldg(src + i);
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			float *Lc = g.L + ((size_t)c * g.BS) * 32 + gq * G_NS;
+			for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+				const uint32_t buf = tile_it & 1u;
+				g_mbar_wait(bar_t_full + 8 * buf, (tile_it >> 1) & 1u);
+				g_tc_fence_after();
+				const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + buf * 256u;
+				float out[G_NS];
+#pragma unroll
+				for (int sl = 0; sl < G_NS; ++sl) {
+					const float *ec = econst + sl * G_CONST;
+					float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+					for (int jh = 0; jh < 2; ++jh) {
+						float v[32];
+						g_tmem_ld32(taddr + jh * 128u + sl * 32u, v);
+#pragma unroll
+						for (int i = 0; i < 32; i += 4) {
+							const float4 nb = *reinterpret_cast<const float4 *>(ec + jh * 32 + i);
+							const float y0 = v[i] + nb.x, y1 = v[i + 1] + nb.y, y2 = v[i + 2] + nb.z, y3 = v[i + 3] + nb.w;
+							q0 = fmaf(y0, y0, q0);
+							q1 = fmaf(y1, y1, q1);
+							q0 = fmaf(y2, y2, q0);
+							q1 = fmaf(y3, y3, q1);
+						}
+					}
+					out[sl] = ec[GD] - (q0 + q1);
+				}
+				g_tc_fence_before();
+				g_mbar_arrive(bar_t_empty + 8 * buf);
+				*reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32) = make_float4(out[0], out[1], out[2], out[3]);
+			}
+		}
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	if (warp == 4) {
+		g_tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the same table on the FP32 pipe (NPB_D64_DENSITY=fp32): thread = step, loop over the 32 slots
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_density_fp32(const double *X64, const double *xbar, const int32_t *order, int nsteps,
+		const float *theta, float *L, int BS) {
+	const int s = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y;
+	if (s >= nsteps) return;
+	float x[GD];
+	{
+		const double *xr = X64 + (size_t)order[s] * GD;
+#pragma unroll
+		for (int i = 0; i < GD; ++i) x[i] = (float)(xr[i] - xbar[i]);
+	}
+	for (int k = 0; k < 32; ++k) {
+		const float *th = theta + ((size_t)c * 32 + k) * GPS;
+		float q = 0.0f;
+#pragma unroll 4
+		for (int r = 0; r < GD; ++r) {
+			float y = 0.0f;
+			for (int cc = r; cc < GD; ++cc) y = fmaf(__ldg(th + GD + npb_tri_off(GD, r, cc)), x[cc] - (float)((double)__ldg(th + cc) - xbar[cc]), y);
+			q = fmaf(y, y, q);
+		}
+		L[((size_t)c * BS + s) * 32 + k] = __ldg(th + GD + GTRI) - q;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// consumer: one warp per chain, lane = slot
+// ---------------------------------------------------------------------------------------------------------
+__device__ __noinline__ float g_log2density_stream64(const float *th, const float *xrow) {
+	float q = 0.0f;
+	for (int r = 0; r < GD; ++r) {
+		float y = 0.0f;
+		for (int c = r; c < GD; ++c) y = fmaf(__ldcg(th + GD + npb_tri_off(GD, r, c)), __ldg(xrow + c) - __ldcg(th + c), y);
+		q = fmaf(y, y, q);
+	}
+	return __ldcg(th + GD + GTRI) - q;
+}
+
+// Birth at D = 64: theta' of draw m of step `step`, consistent with the key that won the race (aux_birth_z of
+// npb_alg8_tile4.cuh with two coordinates per lane: lane and lane + 32), written to the slot table.
+__device__ __noinline__ void g_birth_theta64(const Philox &ph, const PriorDev &pr, const float *xw, float rn, uint32_t step, uint32_t sweep,
+		int m, int lane, float *th) {
+	uint32_t as[4];
+	aux_seed(ph, step, sweep, as);
+	float av = 1.0f, zpar = 0.0f, R2 = 0.0f;
+	for (int mm = 0; mm <= m; ++mm) aux_draw_chi<GD>(as, pr, av, zpar, R2);
+	const float a0 = rn > 0.0f ? __ldg(xw + lane) / rn : (lane == 0 ? 1.0f : 0.0f);
+	const float a1 = rn > 0.0f ? __ldg(xw + lane + 32) / rn : 0.0f;
+	uint32_t w[4];
+	ph(step, 2u + (uint32_t)lane, sweep, NPB_RNG_AUX, w);
+	float g0, g1;
+	npb_normal2(w[0], w[1], g0, g1);
+	float dot = g0 * a0 + g1 * a1;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+	g0 -= dot * a0;
+	g1 -= dot * a1;
+	float nn = g0 * g0 + g1 * g1;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+	const float rs = nn > 0.0f ? rsqrtf(nn) : 0.0f, sr = sqrtf(R2), sc = av * pr.inv_sqrt_kappa;
+	const float z0 = (zpar * a0 + sr * g0 * rs) * sc, z1 = (zpar * a1 + sr * g1 * rs) * sc;
+	float mu_lo = pr.mu0[lane], mu_hi = pr.mu0[lane + 32];
+	for (int c = 0; c < GD; ++c) {
+		const float gc = __shfl_sync(0xffffffffu, c < 32 ? z0 : z1, c & 31);
+		if (lane <= c) mu_lo = fmaf(__ldg(pr.S + npb_tri_off(GD, lane, c)), gc, mu_lo);
+		if (lane + 32 <= c) mu_hi = fmaf(__ldg(pr.S + npb_tri_off(GD, lane + 32, c)), gc, mu_hi);
+	}
+	th[lane] = mu_lo;
+	th[lane + 32] = mu_hi;
+	const float inv = 1.0f / av;
+	for (int q = lane; q < GTRI; q += 32) th[GD + q] = __ldg(pr.CT2 + q) * inv;
+	if (lane == 0) th[GD + GTRI] = pr.c0_2 - (float)GD * log2f(av);
+}
+
+template <int M>
+__global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
+	__shared__ float tile[32 * 33]; // [slot * 33 + step]
+	const SweepArgs &a = p.a;
+	const int lane = threadIdx.x, chain = blockIdx.x;
+	const int N = a.N, C = a.C;
+	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+	float *thc = a.theta + (size_t)chain * 32 * GPS;
+	float *Lc = p.L + (size_t)chain * p.BS * 32;
+	const uint32_t sweep = a.sweep0 + (uint32_t)p.sw;
+	const int32_t *order = a.scan_order + (size_t)p.sw * N;
+	float n = (float)a.counts[(size_t)chain * 32 + lane];
+	float lgn = n > 0.0f ? fast_lg2(n) : -INFINITY, lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
+	int kocc = __popc(__ballot_sync(0xffffffffu, n > 0.0f));
+	unsigned long long st_cand = 0ull, st_moved = 0ull, st_births = 0ull;
+	int overflow = 0;
+	const int ntile = (p.nsteps + 31) / 32;
+
+	float nxt[32];
+#pragma unroll
+	for (int jj = 0; jj < 32; ++jj) nxt[jj] = __ldcg(Lc + (size_t)jj * 32 + lane); // rows past nsteps exist (BS is padded)
+	bool reload = false;
+
+	for (int ti = 0; ti < ntile; ++ti) {
+		const int b0 = ti * 32;          // first step of the tile within the block
+		const int sj = p.s0 + b0 + lane; // lane = step (prologue)
+		const bool valid = b0 + lane < p.nsteps;
+		const int item = valid ? order[sj] : 0;
+		const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
+		int znew = zold;
+		uint32_t rs = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)sj * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
+		const int cnt = min(32, p.nsteps - b0);
+		const uint32_t auxp = valid ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + sj) : 0xff800000u;
+		const float auxkey_j = __uint_as_float(auxp);
+		const int zold_aux_j = zold | ((int)(auxp & 3u) << 16);
+		__syncwarp();
+		if (reload) {
+#pragma unroll
+			for (int jj = 0; jj < 32; ++jj) tile[lane * 33 + jj] = __ldcg(Lc + (size_t)(b0 + jj) * 32 + lane);
+			reload = false;
+		} else {
+#pragma unroll
+			for (int jj = 0; jj < 32; ++jj) tile[lane * 33 + jj] = nxt[jj];
+		}
+		if (ti + 1 < ntile) {
+#pragma unroll
+			for (int jj = 0; jj < 32; ++jj) nxt[jj] = __ldcg(Lc + (size_t)(b0 + 32 + jj) * 32 + lane);
+		}
+		__syncwarp();
+		unsigned cand_tile = 0u;
+
+		float noise_next = neg_lg2_exp1_open(rs = rs * 1664525u + 1013904223u);
+		float base_next = tile[lane * 33] + noise_next;
+		int zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, 0);
+		float ak_next = __shfl_sync(0xffffffffu, auxkey_j, 0);
+		for (int j = 0; j < cnt; ++j) {
+			const int zo_aux = zo_aux_next;
+			const float ak = ak_next;
+			const float base = base_next;
+			const int zo = zo_aux & 0xffff;
+			{
+				const int jn = min(j + 1, 31);
+				noise_next = neg_lg2_exp1_open(rs = rs * 1664525u + 1013904223u);
+				base_next = tile[lane * 33 + jn] + noise_next;
+				zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, jn);
+				ak_next = __shfl_sync(0xffffffffu, auxkey_j, jn);
+			}
+			const float lg = (zo == lane) ? lgn1 : lgn;
+			const float key = lg > -INFINITY ? base + lg : -INFINITY;
+			const float top = fmaxf(redux_max_f32(key), ak);
+			const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
+			cand_tile += (unsigned)(kocc + M);
+			int new_slot;
+			bool born = false;
+			if (bal != 0u) {
+				new_slot = __ffs(bal) - 1;
+			} else {
+				born = true;
+				new_slot = zo;
+			}
+			if (born || new_slot != zo) {
+				// retract (membertrix.cpp:175-233)
+				bool dead = false;
+				if (zo == lane) {
+					n -= 1.0f;
+					dead = n <= 0.0f;
+				}
+				const bool died = __any_sync(0xffffffffu, dead);
+				if (died) {
+					kocc--;
+					cand_tile--;
+				}
+				if (born) {
+					// np_neal_algorithm8.cpp:136-145: the lowest free slot takes theta' of the winning auxiliary draw
+					const unsigned fb = __ballot_sync(0xffffffffu, n <= 0.0f);
+					const int fs = fb ? __ffs(fb) - 1 : -1;
+					if (fs < 0) {
+						overflow = 1; // no room: the item goes back where it was
+						if (died) kocc++;
+					} else {
+						new_slot = fs;
+						const int m = (zo_aux >> 16) & 0xff;
+						const uint32_t step = (uint32_t)(p.s0 + b0 + j);
+						const int bitem = order[step];
+						g_birth_theta64(ph, a.prior, a.Xw + (size_t)bitem * GD, __ldg(a.Xwn + bitem), step, sweep, m, lane, thc + (size_t)fs * GPS);
+						__threadfence();
+						__syncwarp();
+						if (lane == 0) p.dirty[(size_t)chain * 32 + fs] = 1;
+						kocc++;
+						st_births++;
+						// the newborn slot's column of L for the rest of the block (lane = step)
+						for (int s = b0 + j + 1 + lane; s < p.nsteps; s += 32)
+							Lc[(size_t)s * 32 + fs] = g_log2density_stream64(thc + (size_t)fs * GPS, a.X + (size_t)order[p.s0 + s] * GD);
+						__threadfence();
+						__syncwarp();
+						{
+							const int s = b0 + lane;
+							if (lane > j && s < p.nsteps) tile[fs * 33 + lane] = __ldcg(Lc + (size_t)s * 32 + fs);
+						}
+						__syncwarp();
+						reload = true; // the prefetched rows of the next tile predate the column
+						if (lane == fs) base_next = tile[fs * 33 + min(j + 1, 31)] + noise_next;
+					}
+				}
+				if (new_slot == lane) n += 1.0f;
+				lgn = n > 0.0f ? fast_lg2(n) : -INFINITY;
+				lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
+				st_moved++;
+				if (lane == j) znew = new_slot;
+			}
+		}
+		if (valid && znew != zold) a.z[(size_t)item * C + chain] = (npb_z_t)znew;
+		st_cand += cand_tile;
+	}
+	a.counts[(size_t)chain * 32 + lane] = (int)n;
+	if (lane == 0) {
+		a.kocc[chain] = kocc;
+		if (overflow) a.overflow[chain] = 1;
+		a.st[(size_t)chain * 4 + 0] += st_cand;
+		a.st[(size_t)chain * 4 + 1] += st_moved;
+		a.st[(size_t)chain * 4 + 2] += st_births;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+template npb_status npb_launch_aux_keys<64>(npb_chains *, const SweepArgs &);
+
+// read at every use (cheap), so that one process can measure both settings
+static int g_block_steps() {
+	const char *e = getenv("NPB_D64_BLOCK");
+	int v = e ? atoi(e) : 4096;
+	if (v < 128) v = 128;
+	if (v > (1 << 20)) v = 1 << 20;
+	return (v + 127) & ~127;
+}
+static bool g_use_fp32() {
+	const char *e = getenv("NPB_D64_DENSITY");
+	return e && e[0] == 'f';
+}
+
+static npb_status g_ensure(npb_chains *ch) {
+	npb_ctx *ctx = ch->ctx;
+	npb_dataset *ds = ch->ds;
+	const int BS = g_block_steps();
+	if (!ds->Xbar) {
+		NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * GD));
+		k_colmean<<<GD, 256, 0, ctx->stream>>>(ds->X64, ds->N, GD, ds->Xbar);
+		NPB_CUDA_OK(cudaGetLastError());
+	}
+	if (!ch->g_L) {
+		const size_t C = (size_t)ch->C;
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * 2 * G_ASTAGE));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bimg, C * 32 * G_SLOT_IMG));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bconst, C * 32 * G_CONST * sizeof(float)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_L, C * (size_t)(BS + 32) * 32 * sizeof(float)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_dirty, C * 32));
+		NPB_CUDA_OK(cudaMemsetAsync(ch->g_L, 0, C * (size_t)(BS + 32) * 32 * sizeof(float), ctx->stream));
+		ch->g_bs = BS;
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+	}
+	return NPB_OK;
+}
+
+// the log2-density table of `nsteps` steps (scan order `d_order`) of every chain into ch->g_L
+static npb_status g_density_block(npb_chains *ch, const int32_t *d_order, int nsteps) {
+	npb_ctx *ctx = ch->ctx;
+	const int C = (int)ch->C, BSP = ch->g_bs + 32;
+	if (g_use_fp32()) {
+		dim3 grid((nsteps + 127) / 128, C);
+		k_density_fp32<<<grid, 128, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ch->theta, ch->g_L, BSP);
+		NPB_CUDA_OK(cudaGetLastError());
+		return NPB_OK;
+	}
+	const int ntiles = (nsteps + G_M - 1) / G_M;
+	k_pre_aimg<<<(ntiles * G_M * 16 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
+	NPB_CUDA_OK(cudaGetLastError());
+	k_pre_bimg<<<C * 32, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_bimg, ch->g_bconst);
+	NPB_CUDA_OK(cudaGetLastError());
+	GemmArgs g;
+	g.Aimg = ch->g_aimg;
+	g.Bimg = ch->g_bimg;
+	g.Bconst = ch->g_bconst;
+	g.L = ch->g_L;
+	g.C = C;
+	g.ntiles = ntiles;
+	g.BS = BSP;
+	static int n_sm = 0;
+	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+	const int n_units = C * (32 / G_NS);
+	k_density_tc<<<n_units < n_sm ? n_units : n_sm, 192, G_SMEM, ctx->stream>>>(g);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
+	npb_ctx *ctx = ch->ctx;
+	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D = 64 sweep kernels");
+	npb_status s = g_ensure(ch);
+	if (s != NPB_OK) return s;
+	s = npb_launch_aux_keys<64>(ch, a);
+	if (s != NPB_OK) return s;
+	// parameters may have changed since the last launch (init_from_params, update_params): every slot's image is rebuilt
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
+	const int BS = ch->g_bs, N = a.N;
+	PreArgs p;
+	p.a = a;
+	p.L = ch->g_L;
+	p.dirty = ch->g_dirty;
+	p.BS = BS + 32;
+	for (int sw = 0; sw < a.n_sweeps; ++sw) {
+		for (int s0 = 0; s0 < N; s0 += BS) {
+			const int nsteps = N - s0 < BS ? N - s0 : BS;
+			s = g_density_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps);
+			if (s != NPB_OK) return s;
+			p.sw = sw;
+			p.s0 = s0;
+			p.nsteps = nsteps;
+			if (ch->m_aux == 3) k_alg8_sweep_pre<3><<<(unsigned)ch->C, 32, 0, ctx->stream>>>(p);
+			else k_alg8_sweep_pre<1><<<(unsigned)ch->C, 32, 0, ctx->stream>>>(p);
+			NPB_CUDA_OK(cudaGetLastError());
+		}
+	}
+	return NPB_OK;
+}
+
+// parity probe (npb_chains_probe_tile_logdensity at D = 64): the [32 slots x 32 items] table exactly as the sweep reads it
+__global__ void k_gemm64_probe_out(const float *L, const int *counts, int chain, int BSP, float *out) {
+	const int k = threadIdx.x, j = blockIdx.x;
+	const bool occupied = counts[(size_t)chain * 32 + k] > 0;
+	out[k * 32 + j] = occupied ? L[((size_t)chain * BSP + j) * 32 + k] * NPB_LN2 : NAN;
+}
+
+npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out) {
+	npb_ctx *ctx = ch->ctx;
+	npb_status s = g_ensure(ch);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
+	s = g_density_block(ch, d_items, 32);
+	if (s != NPB_OK) return s;
+	k_gemm64_probe_out<<<32, 32, 0, ctx->stream>>>(ch->g_L, ch->counts, chain, ch->g_bs + 32, d_out);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}

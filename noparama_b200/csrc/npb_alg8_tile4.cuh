@@ -162,14 +162,18 @@ __device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &
 	av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
 	zpar = g1;
 	constexpr int KU = (D - 1) / 2; // uniforms; D <= 16 keeps their product far above FLT_MIN
-	float prod = 1.0f;
+	float prod = 1.0f, lsum = 0.0f;
 #pragma unroll
 	for (int i = 0; i < KU; i += 2) {
 		const uint32_t w = xoshiro_next(as);
 		prod *= __uint2float_rn((w & 0xffffu) + 1u) * (1.0f / 65536.0f);
 		if (i + 1 < KU) prod *= __uint2float_rn((w >> 16) + 1u) * (1.0f / 65536.0f);
+		if (KU > 7 && (i % 6) == 4) { // D > 16: one logarithm per six uniforms (their product stays above 2^-96)
+			lsum += fast_lg2(prod);
+			prod = 1.0f;
+		}
 	}
-	R2 = -2.0f * NPB_LN2 * fast_lg2(prod);
+	R2 = -2.0f * NPB_LN2 * (lsum + fast_lg2(prod));
 	if ((D - 1) & 1) R2 += z2sq;
 }
 

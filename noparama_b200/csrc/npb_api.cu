@@ -109,6 +109,7 @@ static npb_status dataset_push(npb_dataset *ds, const double *X) {
 	k_to_float<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ds->X64, ds->X32, n);
 	NPB_CUDA_OK(cudaGetLastError());
 	ds->whitened_epoch = 0;
+	if (ds->Xbar) { cudaFree(ds->Xbar); ds->Xbar = nullptr; } // recomputed on demand (npb_alg8_gemm.cu)
 	return NPB_OK;
 }
 
@@ -154,6 +155,7 @@ npb_status npb_dataset_destroy(npb_dataset *ds) {
 	if (ds->Xw) cudaFree(ds->Xw);
 	if (ds->Xwn) cudaFree(ds->Xwn);
 	if (ds->h_stage) cudaFreeHost(ds->h_stage);
+	if (ds->Xbar) cudaFree(ds->Xbar);
 	delete ds;
 	return NPB_OK;
 }
@@ -345,6 +347,11 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->cur_jll) cudaFree(ch->cur_jll);
 	if (ch->pLambda0) cudaFree(ch->pLambda0);
 	if (ch->pfail) cudaFree(ch->pfail);
+	if (ch->g_aimg) cudaFree(ch->g_aimg);
+	if (ch->g_bimg) cudaFree(ch->g_bimg);
+	if (ch->g_bconst) cudaFree(ch->g_bconst);
+	if (ch->g_L) cudaFree(ch->g_L);
+	if (ch->g_dirty) cudaFree(ch->g_dirty);
 	delete ch;
 	return NPB_OK;
 }

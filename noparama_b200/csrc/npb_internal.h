@@ -36,6 +36,7 @@ struct npb_dataset {
 	float *Xwn = nullptr;   // [N] Euclidean norm of the whitened row
 	uint64_t whitened_epoch = 0;
 	double *h_stage = nullptr; // pinned staging for uploads
+	double *Xbar = nullptr;    // [D] column means (D = 64 path: operands are centred before the TF32 split)
 };
 
 struct npb_chains {
@@ -74,6 +75,13 @@ struct npb_chains {
 	double *pLambda0 = nullptr;    // [D, D]
 	int *pfail = nullptr;
 	uint32_t param_epoch = 0;
+	// D = 64 path (npb_alg8_gemm.cu)
+	uint8_t *g_aimg = nullptr;     // [g_bs / 128][2][32 KB] A-operand images of the current block of steps
+	uint8_t *g_bimg = nullptr;     // [C, 32][24 KB] B-operand images of the slots
+	float *g_bconst = nullptr;     // [C, 32][68] nb = -T2 (mu - xbar), c2
+	float *g_L = nullptr;          // [C][g_bs + 32][32] log2-density table of the current block
+	uint8_t *g_dirty = nullptr;    // [C, 32] slots whose image is out of date
+	int g_bs = 0;                  // steps per block
 };
 
 struct SweepArgs {
@@ -128,6 +136,9 @@ npb_status npb_launch_whiten(npb_dataset *ds);
 npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given);
 npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps);
 npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
+struct SweepArgs;
+npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a);
+npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item);
 npb_status npb_launch_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);
 npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, int whole_sweeps, float *d_detail);
