@@ -57,7 +57,8 @@ struct GemmArgs {
 struct PreArgs {
 	SweepArgs a;
 	float *L;
-	uint8_t *dirty;       // [C * 32]
+	const uint32_t *born_prev; // [C] slots born during the previous block (their columns of L predate them), or NULL
+	uint32_t *born_out;        // [C] slots born during this block
 	int BS, sw, s0, nsteps;
 };
 
@@ -114,10 +115,11 @@ __global__ void __launch_bounds__(256) k_pre_aimg(const double *X64, const doubl
 // ---------------------------------------------------------------------------------------------------------
 // B images and epilogue constants of the slots marked dirty: CTA = (chain, slot)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pre_bimg(const float *theta, const double *xbar, uint8_t *dirty, uint8_t *Bimg, float *Bconst) {
+__global__ void __launch_bounds__(256) k_pre_bimg(const float *theta, const double *xbar, uint8_t *dirty, const uint32_t *born, uint8_t *Bimg,
+		float *Bconst) {
 	__shared__ float th[GPS + 3];
 	const int cs = blockIdx.x; // chain * 32 + slot
-	if (!dirty[cs]) return;
+	if (!dirty[cs] && !((born[cs >> 5] >> (cs & 31)) & 1u)) return;
 	const float *src = theta + (size_t)cs * GPS;
 	for (int i = threadIdx.x; i < GPS; i += 256) th[i] = src[i];
 	__syncthreads();
@@ -480,6 +482,21 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 	unsigned long long st_cand = 0ull, st_moved = 0ull, st_births = 0ull;
 	int overflow = 0;
 	const int ntile = (p.nsteps + 31) / 32;
+	uint32_t born_mask = 0u;
+
+	// The table of this block was computed while the previous block was still being consumed (the two kernels overlap on
+	// two streams): the columns of the slots born there are re-evaluated here, for the whole block (lane = step).
+	if (p.born_prev) {
+		uint32_t fix = p.born_prev[chain];
+		while (fix) {
+			const int k = __ffs(fix) - 1;
+			fix &= fix - 1;
+			for (int s = lane; s < p.nsteps; s += 32)
+				Lc[(size_t)s * 32 + k] = g_log2density_stream64(thc + (size_t)k * GPS, a.X + (size_t)order[p.s0 + s] * GD);
+		}
+		__threadfence();
+		__syncwarp();
+	}
 
 	float nxt[32];
 #pragma unroll
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 						g_birth_theta64(ph, a.prior, a.Xw + (size_t)bitem * GD, __ldg(a.Xwn + bitem), step, sweep, m, lane, thc + (size_t)fs * GPS);
 						__threadfence();
 						__syncwarp();
-						if (lane == 0) p.dirty[(size_t)chain * 32 + fs] = 1;
+						born_mask |= 1u << fs;
 						kocc++;
 						st_births++;
 						// the newborn slot's column of L for the rest of the block (lane = step)
@@ -599,6 +616,7 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 	}
 	a.counts[(size_t)chain * 32 + lane] = (int)n;
 	if (lane == 0) {
+		p.born_out[chain] = born_mask;
 		a.kocc[chain] = kocc;
 		if (overflow) a.overflow[chain] = 1;
 		a.st[(size_t)chain * 4 + 0] += st_cand;
@@ -639,35 +657,49 @@ static npb_status g_ensure(npb_chains *ch) {
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * 2 * G_ASTAGE));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bimg, C * 32 * G_SLOT_IMG));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bconst, C * 32 * G_CONST * sizeof(float)));
-		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_L, C * (size_t)(BS + 32) * 32 * sizeof(float)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_L, 2 * C * (size_t)(BS + 32) * 32 * sizeof(float)));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_dirty, C * 32));
-		NPB_CUDA_OK(cudaMemsetAsync(ch->g_L, 0, C * (size_t)(BS + 32) * 32 * sizeof(float), ctx->stream));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_born, 2 * C * sizeof(uint32_t)));
+		NPB_CUDA_OK(cudaMemsetAsync(ch->g_L, 0, 2 * C * (size_t)(BS + 32) * 32 * sizeof(float), ctx->stream));
+		NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * C * sizeof(uint32_t), ctx->stream));
+		NPB_CUDA_OK(cudaStreamCreateWithFlags(&ch->g_stream2, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; ++i) {
+			NPB_CUDA_OK(cudaEventCreateWithFlags(&ch->g_evD[i], cudaEventDisableTiming));
+			NPB_CUDA_OK(cudaEventCreateWithFlags(&ch->g_evC[i], cudaEventDisableTiming));
+		}
 		ch->g_bs = BS;
 		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+		// one shared-memory carveout for the kernels that must be co-resident (an SM does not host two configurations)
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_pre<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_pre<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_pre_aimg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_pre_bimg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	}
 	return NPB_OK;
 }
 
 // the log2-density table of `nsteps` steps (scan order `d_order`) of every chain into ch->g_L
-static npb_status g_density_block(npb_chains *ch, const int32_t *d_order, int nsteps) {
+static npb_status g_density_block(npb_chains *ch, const int32_t *d_order, int nsteps, int buf) {
 	npb_ctx *ctx = ch->ctx;
 	const int C = (int)ch->C, BSP = ch->g_bs + 32;
+	float *L = ch->g_L + (size_t)buf * C * BSP * 32;
 	if (g_use_fp32()) {
 		dim3 grid((nsteps + 127) / 128, C);
-		k_density_fp32<<<grid, 128, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ch->theta, ch->g_L, BSP);
+		k_density_fp32<<<grid, 128, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ch->theta, L, BSP);
 		NPB_CUDA_OK(cudaGetLastError());
 		return NPB_OK;
 	}
 	const int ntiles = (nsteps + G_M - 1) / G_M;
 	k_pre_aimg<<<(ntiles * G_M * 16 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
 	NPB_CUDA_OK(cudaGetLastError());
-	k_pre_bimg<<<C * 32, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_bimg, ch->g_bconst);
+	k_pre_bimg<<<C * 32, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_born + (size_t)buf * C, ch->g_bimg, ch->g_bconst);
 	NPB_CUDA_OK(cudaGetLastError());
 	GemmArgs g;
 	g.Aimg = ch->g_aimg;
 	g.Bimg = ch->g_bimg;
 	g.Bconst = ch->g_bconst;
-	g.L = ch->g_L;
+	g.L = L;
 	g.C = C;
 	g.ntiles = ntiles;
 	g.BS = BSP;
@@ -686,27 +718,46 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
 	if (s != NPB_OK) return s;
 	s = npb_launch_aux_keys<64>(ch, a);
 	if (s != NPB_OK) return s;
+	const size_t C = (size_t)ch->C;
 	// parameters may have changed since the last launch (init_from_params, update_params): every slot's image is rebuilt
-	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
-	const int BS = ch->g_bs, N = a.N;
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, C * 32, ctx->stream));
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * C * sizeof(uint32_t), ctx->stream));
+	// Two streams: the density table of block k + 1 (context stream) is computed while block k is consumed (second
+	// stream).  Table k is written into buffer k & 1 once the consumer of block k - 2 has released it; a slot born during
+	// block k - 1 is missing from table k (its column is re-evaluated by the consumer of block k, born_prev) and enters the
+	// operand images with block k + 1 (k_pre_bimg reads the births of block k - 1 from g_born[(k + 1) & 1]).
+	cudaStream_t sA = ctx->stream, sB = ch->g_stream2;
+	NPB_CUDA_OK(cudaEventRecord(ch->g_evD[0], sA));
+	NPB_CUDA_OK(cudaStreamWaitEvent(sB, ch->g_evD[0], 0));
+	const int BS = ch->g_bs, N = a.N, BSP = BS + 32;
+	const bool overlap = [] { const char *e = getenv("NPB_D64_OVERLAP"); return !(e && e[0] == '0'); }();
 	PreArgs p;
 	p.a = a;
-	p.L = ch->g_L;
-	p.dirty = ch->g_dirty;
-	p.BS = BS + 32;
+	p.BS = BSP;
+	int k = 0;
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
-		for (int s0 = 0; s0 < N; s0 += BS) {
+		for (int s0 = 0; s0 < N; s0 += BS, ++k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;
-			s = g_density_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps);
+			const int buf = k & 1;
+			if (k >= 2 || (!overlap && k >= 1)) NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[overlap ? buf : (buf ^ 1)], 0));
+			s = g_density_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps, buf);
 			if (s != NPB_OK) return s;
+			NPB_CUDA_OK(cudaEventRecord(ch->g_evD[buf], sA));
+			NPB_CUDA_OK(cudaStreamWaitEvent(sB, ch->g_evD[buf], 0));
+			p.L = ch->g_L + (size_t)buf * C * BSP * 32;
+			p.born_prev = k > 0 ? ch->g_born + (size_t)(buf ^ 1) * C : nullptr;
+			p.born_out = ch->g_born + (size_t)buf * C;
 			p.sw = sw;
 			p.s0 = s0;
 			p.nsteps = nsteps;
-			if (ch->m_aux == 3) k_alg8_sweep_pre<3><<<(unsigned)ch->C, 32, 0, ctx->stream>>>(p);
-			else k_alg8_sweep_pre<1><<<(unsigned)ch->C, 32, 0, ctx->stream>>>(p);
+			if (ch->m_aux == 3) k_alg8_sweep_pre<3><<<(unsigned)ch->C, 32, 0, sB>>>(p);
+			else k_alg8_sweep_pre<1><<<(unsigned)ch->C, 32, 0, sB>>>(p);
 			NPB_CUDA_OK(cudaGetLastError());
+			NPB_CUDA_OK(cudaEventRecord(ch->g_evC[buf], sB));
 		}
 	}
+	// join: the context stream continues after the last consumer
+	NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[(k - 1) & 1], 0));
 	return NPB_OK;
 }
 
@@ -722,7 +773,8 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 	npb_status s = g_ensure(ch);
 	if (s != NPB_OK) return s;
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
-	s = g_density_block(ch, d_items, 32);
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * (size_t)ch->C * sizeof(uint32_t), ctx->stream));
+	s = g_density_block(ch, d_items, 32, 0);
 	if (s != NPB_OK) return s;
 	k_gemm64_probe_out<<<32, 32, 0, ctx->stream>>>(ch->g_L, ch->counts, chain, ch->g_bs + 32, d_out);
 	NPB_CUDA_OK(cudaGetLastError());

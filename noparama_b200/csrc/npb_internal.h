@@ -79,9 +79,12 @@ struct npb_chains {
 	uint8_t *g_aimg = nullptr;     // [g_bs / 128][2][32 KB] A-operand images of the current block of steps
 	uint8_t *g_bimg = nullptr;     // [C, 32][24 KB] B-operand images of the slots
 	float *g_bconst = nullptr;     // [C, 32][68] nb = -T2 (mu - xbar), c2
-	float *g_L = nullptr;          // [C][g_bs + 32][32] log2-density table of the current block
+	float *g_L = nullptr;          // [2][C][g_bs + 32][32] log2-density tables of the current and the next block
 	uint8_t *g_dirty = nullptr;    // [C, 32] slots whose image is out of date
 	int g_bs = 0;                  // steps per block
+	uint32_t *g_born = nullptr;    // [2][C] slots born during block k (buffer k & 1)
+	cudaStream_t g_stream2 = nullptr; // consumer stream (the density table of the next block overlaps it)
+	cudaEvent_t g_evD[2] = {nullptr, nullptr}, g_evC[2] = {nullptr, nullptr};
 };
 
 struct SweepArgs {
