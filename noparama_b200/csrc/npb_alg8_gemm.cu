@@ -60,6 +60,7 @@ struct PreArgs {
 	const uint32_t *born_prev; // [C] slots born during the previous block (their columns of L predate them), or NULL
 	uint32_t *born_out;        // [C] slots born during this block
 	int BS, sw, s0, nsteps;
+	int spec;                  // 0: sequential pass only (NPB_D64_SPEC=0; the result must not depend on it)
 };
 
 // byte offset of float k (0..31) of row `row` in a K-major, 128-byte-swizzled region (rows of 128 bytes, base 1024-aligned)
@@ -465,9 +466,28 @@ __device__ __noinline__ void g_birth_theta64(const Philox &ph, const PriorDev &p
 	if (lane == 0) th[GD + GTRI] = pr.c0_2 - (float)GD * log2f(av);
 }
 
+// race noise of (tile, step j, slot k): a counter hash instead of a per-lane stream, so that the step-parallel pass
+// (lane = step) and the sequential pass (lane = slot) of k_alg8_sweep_pre draw the same number for the same candidate
+__device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
+	uint32_t x = T + (j * 32u + k) * 0x9E3779B9u;
+	x ^= x >> 16;
+	x *= 0x85EBCA6Bu;
+	x ^= x >> 13;
+	x *= 0xC2B2AE35u;
+	return neg_lg2_exp1_open(x);
+}
+
+// One warp per chain.  A tile of 32 steps is first decided SPECULATIVELY with lane = step: every lane walks the 32 slots
+// of its own step with the member counts as they stand at the start of the tile -- 32 independent instruction streams
+// instead of one dependent chain of warp reductions.  If no step of the tile moves its item (the steady state of a
+// converged chain: > 99.9 % of the tiles) the counts never changed and the tile is done.  Otherwise the steps before the
+// first move are final, and the sequential pass (lane = slot, the consumer of npb_alg8_tile4.cuh) takes over from that
+// step; both passes evaluate the same keys (same noise, same operation order), so the result does not depend on which
+// pass decided a step.  A chain that moves a lot (burn-in) skips the speculative pass.
 template <int M>
 __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 	__shared__ float tile[32 * 33]; // [slot * 33 + step]
+	__shared__ float lg_s[32], lg1_s[32]; // log2 n_k and log2 (n_k - 1) of every slot (-inf without members)
 	const SweepArgs &a = p.a;
 	const int lane = threadIdx.x, chain = blockIdx.x;
 	const int N = a.N, C = a.C;
@@ -478,11 +498,14 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 	const int32_t *order = a.scan_order + (size_t)p.sw * N;
 	float n = (float)a.counts[(size_t)chain * 32 + lane];
 	float lgn = n > 0.0f ? fast_lg2(n) : -INFINITY, lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
+	lg_s[lane] = lgn;
+	lg1_s[lane] = lgn1;
 	int kocc = __popc(__ballot_sync(0xffffffffu, n > 0.0f));
 	unsigned long long st_cand = 0ull, st_moved = 0ull, st_births = 0ull;
 	int overflow = 0;
 	const int ntile = (p.nsteps + 31) / 32;
 	uint32_t born_mask = 0u;
+	int recent_moves = 0;
 
 	// The table of this block was computed while the previous block was still being consumed (the two kernels overlap on
 	// two streams): the columns of the slots born there are re-evaluated here, for the whole block (lane = step).
@@ -510,7 +533,7 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 		const int item = valid ? order[sj] : 0;
 		const int zold = valid ? (int)a.z[(size_t)item * C + chain] : 0;
 		int znew = zold;
-		uint32_t rs = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)sj * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
+		const uint32_t T = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)(p.s0 + b0) * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
 		const int cnt = min(32, p.nsteps - b0);
 		const uint32_t auxp = valid ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + sj) : 0xff800000u;
 		const float auxkey_j = __uint_as_float(auxp);
@@ -531,85 +554,110 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 		__syncwarp();
 		unsigned cand_tile = 0u;
 
-		float noise_next = neg_lg2_exp1_open(rs = rs * 1664525u + 1013904223u);
-		float base_next = tile[lane * 33] + noise_next;
-		int zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, 0);
-		float ak_next = __shfl_sync(0xffffffffu, auxkey_j, 0);
-		for (int j = 0; j < cnt; ++j) {
-			const int zo_aux = zo_aux_next;
-			const float ak = ak_next;
-			const float base = base_next;
-			const int zo = zo_aux & 0xffff;
-			{
-				const int jn = min(j + 1, 31);
-				noise_next = neg_lg2_exp1_open(rs = rs * 1664525u + 1013904223u);
-				base_next = tile[lane * 33 + jn] + noise_next;
-				zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, jn);
-				ak_next = __shfl_sync(0xffffffffu, auxkey_j, jn);
+		int j0 = 0;
+		if (p.spec && recent_moves < 3) {
+			// ---- speculative pass: lane = step ----
+			float best = -INFINITY;
+			int bk = 0;
+#pragma unroll 8
+			for (int k = 0; k < 32; ++k) {
+				const float base = tile[k * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)k);
+				const float lg = (zold == k) ? lg1_s[k] : lg_s[k];
+				const float key = lg > -INFINITY ? base + lg : -INFINITY;
+				if (key > best) { best = key; bk = k; }
 			}
-			const float lg = (zo == lane) ? lgn1 : lgn;
-			const float key = lg > -INFINITY ? base + lg : -INFINITY;
-			const float top = fmaxf(redux_max_f32(key), ak);
-			const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
-			cand_tile += (unsigned)(kocc + M);
-			int new_slot;
-			bool born = false;
-			if (bal != 0u) {
-				new_slot = __ffs(bal) - 1;
-			} else {
-				born = true;
-				new_slot = zo;
-			}
-			if (born || new_slot != zo) {
-				// retract (membertrix.cpp:175-233)
-				bool dead = false;
-				if (zo == lane) {
-					n -= 1.0f;
-					dead = n <= 0.0f;
+			const bool stays = best > -INFINITY && best >= auxkey_j && bk == zold;
+			const unsigned mv = __ballot_sync(0xffffffffu, valid && !stays);
+			j0 = mv ? __ffs(mv) - 1 : cnt;
+			cand_tile += (unsigned)(j0 * (kocc + M));
+		}
+		recent_moves = 0;
+
+		if (j0 < cnt) {
+			// ---- sequential pass from step j0: lane = slot ----
+			float base_next = tile[lane * 33 + j0] + g_noise(T, (uint32_t)j0, (uint32_t)lane);
+			int zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, j0);
+			float ak_next = __shfl_sync(0xffffffffu, auxkey_j, j0);
+			for (int j = j0; j < cnt; ++j) {
+				const int zo_aux = zo_aux_next;
+				const float ak = ak_next;
+				const float base = base_next;
+				const int zo = zo_aux & 0xffff;
+				float noise_next;
+				{
+					const int jn = min(j + 1, 31);
+					noise_next = g_noise(T, (uint32_t)jn, (uint32_t)lane);
+					base_next = tile[lane * 33 + jn] + noise_next;
+					zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, jn);
+					ak_next = __shfl_sync(0xffffffffu, auxkey_j, jn);
 				}
-				const bool died = __any_sync(0xffffffffu, dead);
-				if (died) {
-					kocc--;
-					cand_tile--;
+				const float lg = (zo == lane) ? lgn1 : lgn;
+				const float key = lg > -INFINITY ? base + lg : -INFINITY; // a slot without (other) members never wins
+				const float top = fmaxf(redux_max_f32(key), ak);
+				const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
+				cand_tile += (unsigned)(kocc + M);
+				int new_slot;
+				bool born = false;
+				if (bal != 0u) {
+					new_slot = __ffs(bal) - 1;
+				} else {
+					born = true;
+					new_slot = zo;
 				}
-				if (born) {
-					// np_neal_algorithm8.cpp:136-145: the lowest free slot takes theta' of the winning auxiliary draw
-					const unsigned fb = __ballot_sync(0xffffffffu, n <= 0.0f);
-					const int fs = fb ? __ffs(fb) - 1 : -1;
-					if (fs < 0) {
-						overflow = 1; // no room: the item goes back where it was
-						if (died) kocc++;
-					} else {
-						new_slot = fs;
-						const int m = (zo_aux >> 16) & 0xff;
-						const uint32_t step = (uint32_t)(p.s0 + b0 + j);
-						const int bitem = order[step];
-						g_birth_theta64(ph, a.prior, a.Xw + (size_t)bitem * GD, __ldg(a.Xwn + bitem), step, sweep, m, lane, thc + (size_t)fs * GPS);
-						__threadfence();
-						__syncwarp();
-						born_mask |= 1u << fs;
-						kocc++;
-						st_births++;
-						// the newborn slot's column of L for the rest of the block (lane = step)
-						for (int s = b0 + j + 1 + lane; s < p.nsteps; s += 32)
-							Lc[(size_t)s * 32 + fs] = g_log2density_stream64(thc + (size_t)fs * GPS, a.X + (size_t)order[p.s0 + s] * GD);
-						__threadfence();
-						__syncwarp();
-						{
-							const int s = b0 + lane;
-							if (lane > j && s < p.nsteps) tile[fs * 33 + lane] = __ldcg(Lc + (size_t)s * 32 + fs);
-						}
-						__syncwarp();
-						reload = true; // the prefetched rows of the next tile predate the column
-						if (lane == fs) base_next = tile[fs * 33 + min(j + 1, 31)] + noise_next;
+				if (born || new_slot != zo) {
+					// retract (membertrix.cpp:175-233)
+					bool dead = false;
+					if (zo == lane) {
+						n -= 1.0f;
+						dead = n <= 0.0f;
 					}
+					const bool died = __any_sync(0xffffffffu, dead);
+					if (died) {
+						kocc--;
+						cand_tile--;
+					}
+					if (born) {
+						// np_neal_algorithm8.cpp:136-145: the lowest free slot takes theta' of the winning auxiliary draw
+						const unsigned fb = __ballot_sync(0xffffffffu, n <= 0.0f);
+						const int fs = fb ? __ffs(fb) - 1 : -1;
+						if (fs < 0) {
+							overflow = 1; // no room: the item goes back where it was
+							if (died) kocc++;
+						} else {
+							new_slot = fs;
+							const int m = (zo_aux >> 16) & 0xff;
+							const uint32_t step = (uint32_t)(p.s0 + b0 + j);
+							const int bitem = order[step];
+							g_birth_theta64(ph, a.prior, a.Xw + (size_t)bitem * GD, __ldg(a.Xwn + bitem), step, sweep, m, lane, thc + (size_t)fs * GPS);
+							__threadfence();
+							__syncwarp();
+							born_mask |= 1u << fs;
+							kocc++;
+							st_births++;
+							// the newborn slot's column of L for the rest of the block (lane = step)
+							for (int s = b0 + j + 1 + lane; s < p.nsteps; s += 32)
+								Lc[(size_t)s * 32 + fs] = g_log2density_stream64(thc + (size_t)fs * GPS, a.X + (size_t)order[p.s0 + s] * GD);
+							__threadfence();
+							__syncwarp();
+							{
+								const int s = b0 + lane;
+								if (lane > j && s < p.nsteps) tile[fs * 33 + lane] = __ldcg(Lc + (size_t)s * 32 + fs);
+							}
+							__syncwarp();
+							reload = true; // the prefetched rows of the next tile predate the column
+							if (lane == fs) base_next = tile[fs * 33 + min(j + 1, 31)] + noise_next;
+						}
+					}
+					if (new_slot == lane) n += 1.0f;
+					lgn = n > 0.0f ? fast_lg2(n) : -INFINITY;
+					lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
+					st_moved++;
+					recent_moves++;
+					if (lane == j) znew = new_slot;
 				}
-				if (new_slot == lane) n += 1.0f;
-				lgn = n > 0.0f ? fast_lg2(n) : -INFINITY;
-				lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
-				st_moved++;
-				if (lane == j) znew = new_slot;
 			}
+			lg_s[lane] = lgn;
+			lg1_s[lane] = lgn1;
 		}
 		if (valid && znew != zold) a.z[(size_t)item * C + chain] = (npb_z_t)znew;
 		st_cand += cand_tile;
@@ -721,11 +769,12 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
 	const size_t C = (size_t)ch->C;
 	// parameters may have changed since the last launch (init_from_params, update_params): every slot's image is rebuilt
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, C * 32, ctx->stream));
-	NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * C * sizeof(uint32_t), ctx->stream));
 	// Two streams: the density table of block k + 1 (context stream) is computed while block k is consumed (second
 	// stream).  Table k is written into buffer k & 1 once the consumer of block k - 2 has released it; a slot born during
 	// block k - 1 is missing from table k (its column is re-evaluated by the consumer of block k, born_prev) and enters the
-	// operand images with block k + 1 (k_pre_bimg reads the births of block k - 1 from g_born[(k + 1) & 1]).
+	// operand images with block k + 1 (k_pre_bimg reads the births of block k - 1 from g_born[(k + 1) & 1]).  The block
+	// counter runs on across launches, so that splitting a run into launches does not change which kernel evaluated which
+	// column (results are bit-identical however the sweeps are batched).
 	cudaStream_t sA = ctx->stream, sB = ch->g_stream2;
 	NPB_CUDA_OK(cudaEventRecord(ch->g_evD[0], sA));
 	NPB_CUDA_OK(cudaStreamWaitEvent(sB, ch->g_evD[0], 0));
@@ -734,18 +783,19 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
 	PreArgs p;
 	p.a = a;
 	p.BS = BSP;
+	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();
 	int k = 0;
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
-		for (int s0 = 0; s0 < N; s0 += BS, ++k) {
+		for (int s0 = 0; s0 < N; s0 += BS, ++k, ++ch->g_k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;
-			const int buf = k & 1;
+			const int buf = (int)(ch->g_k & 1u);
 			if (k >= 2 || (!overlap && k >= 1)) NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[overlap ? buf : (buf ^ 1)], 0));
 			s = g_density_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps, buf);
 			if (s != NPB_OK) return s;
 			NPB_CUDA_OK(cudaEventRecord(ch->g_evD[buf], sA));
 			NPB_CUDA_OK(cudaStreamWaitEvent(sB, ch->g_evD[buf], 0));
 			p.L = ch->g_L + (size_t)buf * C * BSP * 32;
-			p.born_prev = k > 0 ? ch->g_born + (size_t)(buf ^ 1) * C : nullptr;
+			p.born_prev = ch->g_born + (size_t)(buf ^ 1) * C;
 			p.born_out = ch->g_born + (size_t)buf * C;
 			p.sw = sw;
 			p.s0 = s0;
@@ -757,7 +807,7 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
 		}
 	}
 	// join: the context stream continues after the last consumer
-	NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[(k - 1) & 1], 0));
+	NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[(ch->g_k - 1u) & 1u], 0));
 	return NPB_OK;
 }
 
@@ -773,7 +823,6 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 	npb_status s = g_ensure(ch);
 	if (s != NPB_OK) return s;
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
-	NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * (size_t)ch->C * sizeof(uint32_t), ctx->stream));
 	s = g_density_block(ch, d_items, 32, 0);
 	if (s != NPB_OK) return s;
 	k_gemm64_probe_out<<<32, 32, 0, ctx->stream>>>(ch->g_L, ch->counts, chain, ch->g_bs + 32, d_out);

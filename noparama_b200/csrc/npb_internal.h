@@ -82,6 +82,7 @@ struct npb_chains {
 	float *g_L = nullptr;          // [2][C][g_bs + 32][32] log2-density tables of the current and the next block
 	uint8_t *g_dirty = nullptr;    // [C, 32] slots whose image is out of date
 	int g_bs = 0;                  // steps per block
+	uint32_t g_k = 0;              // blocks consumed so far (parity selects the table / born-mask buffer)
 	uint32_t *g_born = nullptr;    // [2][C] slots born during block k (buffer k & 1)
 	cudaStream_t g_stream2 = nullptr; // consumer stream (the density table of the next block overlaps it)
 	cudaEvent_t g_evD[2] = {nullptr, nullptr}, g_evC[2] = {nullptr, nullptr};

@@ -13,7 +13,7 @@ D = 64
 
 @pytest.fixture
 def env():
-    saved = {k: os.environ.get(k) for k in ("NPB_D64_BLOCK", "NPB_D64_DENSITY")}
+    saved = {k: os.environ.get(k) for k in ("NPB_D64_BLOCK", "NPB_D64_DENSITY", "NPB_D64_SPEC", "NPB_D64_OVERLAP")}
     yield os.environ
     for k, v in saved.items():
         if v is None:
@@ -122,4 +122,25 @@ def test_gemm64_recovers_given_clusters(npb, ctx, env, m_aux):
         assert np.all(m["K"] == K) and m["purity"].min() > 0.9999 and m["adjusted_rand"].min() > 0.9999
         zs[density] = z
     assert (zs["tc"] == zs["fp32"]).mean() > 0.9999
+    ds.close()
+
+
+def test_gemm64_schedule_does_not_change_the_result(npb, ctx, env):
+    """The step-parallel speculative pass, the sequential pass, the two-stream overlap and the batching of sweeps into launches are schedules of
+    the same computation: same seed, same assignments, bit for bit -- from a reference-style start (births, deaths, many
+    moves) into the converged regime (tiles without a move)."""
+    X, y = syn.gmm(3000, D, 6, 77)
+    ds = npb.Dataset(ctx, X)
+    zs = []
+    env["NPB_D64_BLOCK"] = "512"
+    for spec, overlap, per_launch in (("1", "1", None), ("0", "1", None), ("1", "0", None), ("1", "1", 1)):
+        env["NPB_D64_SPEC"], env["NPB_D64_OVERLAP"] = spec, overlap
+        mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=10, Kmax=32, K0=8, seed=11)
+        sts = mc.run(6, sweeps_per_launch=per_launch)
+        assert all(st.overflow_chains == 0 for st in sts)
+        zs.append((mc.getMembershipMatrix().copy(), sum(st.candidates for st in sts), sum(st.moved for st in sts),
+                   sum(st.new_clusters for st in sts)))
+    print("moved", zs[0][2], "births", zs[0][3])
+    for z, cand, moved, born in zs[1:]:
+        assert np.array_equal(z, zs[0][0]) and (cand, moved, born) == zs[0][1:]
     ds.close()
