@@ -331,6 +331,50 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
                                            "clusters; 16 lockstep proposals per chain (np_mcmc.cpp:146-163)")
     ch.close()
     ds.close()
+    out["cfg4"] = cfg4_measure(npb, syn, ctx, fp32_peak, rank)
+    return out
+
+
+def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=3):
+    """BASELINE configs[3] shape: 256 chains, 64-D, N = 1M, 32 given clusters, Algorithm 2 (one auxiliary draw) through the
+    D = 64 path (npb_alg8_gemm.cu): tcgen05 kind::tf32 density tables (3xTF32) overlapped with the warp-per-chain race."""
+    D, K = 64, 32
+    X, y = syn.gmm(N, D, K, syn.SEEDS[4])
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(D)).bind(ctx)
+    ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K0_REF, m_aux=1, seed=SEED + 41 * rank)
+    ch.init_from_params(*given_clusters(X, y))
+    for _ in range(3):  # the first sweep moves every item to its cluster
+        ch.sweep(npb.ALG2, 1, want_stats=False)
+    ms, cand = [], 0
+    for _ in range(timed):
+        st = ch.sweep(npb.ALG2, 1)
+        ms.append(st.kernel_ms)
+        cand += st.candidates
+    k_ms = float(np.mean(ms))
+    n_step = chains * N
+    m = ch.metrics(y)
+    bf16_peak = None
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        bf16_peak = json.load(open(pk)).get("bf16_tflops")
+    tf32_peak = bf16_peak / 2.0 if bf16_peak else 1125.0  # kind::tf32 runs at half the bf16 rate (nominal 2250 / 2 as fallback)
+    mma = n_step * 32 * 3 * 0.75 * 2 * D * D  # issued: 3 TF32 products, 3 of the 4 32x32 blocks of the triangular factor, all 32 slots
+    alg = (cand / timed) * (f_eval(D) + 6)
+    sec = k_ms * 1e-3
+    out = {"workload": "BASELINE configs[3] shape: %d chains, synthetic 32-component 64-D GMM, N=%d, Algorithm 2 (one auxiliary "
+                       "draw), Kmax=32, K0=K_true=32 given clusters" % (chains, N),
+           "value": n_step / sec, "unit": UNIT, "kernel_ms": k_ms, "steps": timed, "warmup": 3,
+           "candidates_per_reassignment": cand / (n_step * timed), "mean_purity": float(m["purity"].mean()),
+           "mean_K": float(m["K"].mean()), "algorithmic_tflops": alg / sec / 1e12,
+           "algorithmic_over_fp32_peak": alg / sec / 1e12 / fp32_peak if fp32_peak else None,
+           "roofline": {"bound": "tensor", "achieved": mma / sec / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": mma / sec / 1e12 / tf32_peak if tf32_peak else None, "kernel": "k_density_tc",
+                        "note": "achieved = TF32 MMA flops issued per sweep (3xTF32 of the triangular 64x64 factor for every "
+                                "(step, slot)) / sweep time, the race kernel overlapped on a second stream; peak = measured "
+                                "bf16 burst / 2"}}
+    ch.close()
+    ds.close()
     return out
 
 
