@@ -337,7 +337,8 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
 
 def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=3):
     """BASELINE configs[3] shape: 256 chains, 64-D, N = 1M, 32 given clusters, Algorithm 2 (one auxiliary draw) through the
-    D = 64 path (npb_alg8_gemm.cu): tcgen05 kind::tf32 density tables (3xTF32) overlapped with the warp-per-chain race."""
+    D = 64 path (npb_alg8_gemm.cu): tcgen05 kind::f16 density tables (three FP16 products per FP32 product) overlapped with
+    the warp-per-chain race."""
     D, K = 64, 32
     X, y = syn.gmm(N, D, K, syn.SEEDS[4])
     ds = npb.Dataset(ctx, X)
@@ -358,8 +359,8 @@ def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         bf16_peak = json.load(open(pk)).get("bf16_tflops")
-    tf32_peak = bf16_peak / 2.0 if bf16_peak else 1125.0  # kind::tf32 runs at half the bf16 rate (nominal 2250 / 2 as fallback)
-    mma = n_step * 32 * 3 * 0.75 * 2 * D * D  # issued: 3 TF32 products, 3 of the 4 32x32 blocks of the triangular factor, all 32 slots
+    f16_peak = bf16_peak if bf16_peak else 2250.0  # kind::f16 runs at the bf16 rate (nominal dense figure as fallback)
+    mma = n_step * 32 * 3 * 0.75 * 2 * D * D  # issued: 3 FP16 products, 3 of the 4 32x32 blocks of the triangular factor, all 32 slots
     alg = (cand / timed) * (f_eval(D) + 6)
     sec = k_ms * 1e-3
     out = {"workload": "BASELINE configs[3] shape: %d chains, synthetic 32-component 64-D GMM, N=%d, Algorithm 2 (one auxiliary "
@@ -368,11 +369,11 @@ def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=
            "candidates_per_reassignment": cand / (n_step * timed), "mean_purity": float(m["purity"].mean()),
            "mean_K": float(m["K"].mean()), "algorithmic_tflops": alg / sec / 1e12,
            "algorithmic_over_fp32_peak": alg / sec / 1e12 / fp32_peak if fp32_peak else None,
-           "roofline": {"bound": "tensor", "achieved": mma / sec / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": mma / sec / 1e12 / tf32_peak if tf32_peak else None, "kernel": "k_density_tc",
-                        "note": "achieved = TF32 MMA flops issued per sweep (3xTF32 of the triangular 64x64 factor for every "
-                                "(step, slot)) / sweep time, the race kernel overlapped on a second stream; peak = measured "
-                                "bf16 burst / 2"}}
+           "roofline": {"bound": "tensor", "achieved": mma / sec / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
+                        "frac": mma / sec / 1e12 / f16_peak, "kernel": "k_density_tc",
+                        "note": "achieved = kind::f16 MMA flops issued per sweep (three FP16 products per FP32 product, 3 of the 4 "
+                                "32x32 blocks of the triangular 64x64 factor, every (step, slot)) / sweep time, the race kernel "
+                                "overlapped on a second stream; peak = measured bf16 burst (MEASURED_PEAKS.json)"}}
     ch.close()
     ds.close()
     return out

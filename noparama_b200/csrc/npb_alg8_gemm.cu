@@ -7,20 +7,26 @@
 // D = 64 a cluster slot is 2145 floats, so neither the registers of a lane (npb_alg8_tile4.cuh) nor shared memory hold a
 // chain's slot table, and a density is 2080 FMAs -- GEMM-shaped work.  A sweep is cut into blocks of NPB_G_BS steps; per
 // block, in stream order:
-//   k_pre_aimg     gathers the block's item rows (scan order), centres them on the dataset mean, splits every
-//                  coordinate into two TF32 terms (hi + lo) and writes them as the shared-memory IMAGE of the A operand
-//                  (K-major, 128-byte swizzle), one 32 KB image per (128-step tile, half of K);
+//   k_pre_aimg     gathers the block's item rows (scan order), centres them on the dataset mean, scales them by a power
+//                  of two (largest |x - xbar| just below 2^14), splits every coordinate into two FP16 terms (hi + lo)
+//                  and writes them as the shared-memory IMAGE of the A operand (K-major, 128-byte swizzle: one row =
+//                  the 64 coordinates), one 32 KB image (hi, lo) per 128-step tile;
 //   k_pre_bimg     does the same for the slots whose parameters changed (births; everything at the first block of a
-//                  launch): the upper-triangular factor T2 as the B operand image, nb = -T2 (mu - xbar) and c2 aside;
+//                  launch): the upper-triangular factor T2 (scaled per slot) as the B operand image, nb = -T2 (mu - xbar),
+//                  c2 and the descaling factor aside;
 //   k_density_tc   persistent, one CTA per SM, unit of work = (chain, 4 slots): the four slots' B images stay resident
-//                  in shared memory (96 KB) while the block's A images stream through a three-stage ring of
-//                  cp.async.bulk copies (no register staging); one thread issues tcgen05.mma kind::tf32 128 x 256 x 8
-//                  (3xTF32: hi*hi + hi*lo + lo*hi, FP32 accumulation in TMEM, two accumulator buffers of 256 columns);
-//                  four epilogue warps read the accumulators back (tcgen05.ld 32x32b), form
-//                  c2 - sum_j (y_j + nb_j)^2 per (step, slot) and write the block's log2-density table
-//                  L[chain][step][slot].  T2 is upper triangular, so the first half of K only feeds rows j < 32: the
-//                  rows of B are ordered (j / 32, slot, j % 32) and the first K-half is issued with N = 128, a quarter
-//                  of the MMA work saved;
+//                  in shared memory (64 KB) while the block's A images stream through a four-stage ring of
+//                  cp.async.bulk copies (no register staging); one thread issues tcgen05.mma kind::f16 128 x 256 x 16
+//                  (three FP16 products per FP32 product: hi*hi + hi*lo + lo*hi, FP32 accumulation in TMEM, two
+//                  accumulator buffers of 256 columns); four epilogue warps read the accumulators back (tcgen05.ld
+//                  32x32b), form c2 - sum_j (s y_j + nb_j)^2 per (step, slot) and write the block's log2-density table
+//                  L[chain][step][slot].  The split is exact to 2^-25 of the operand's scale: FP16 carries 11 significant
+//                  bits like TF32 and, with the operands scaled to ~2^14, the low terms stay above the subnormal
+//                  quantum 2^-24, so the error is that of the dropped lo*lo product and of FP32 accumulation (3xTF32
+//                  accuracy at twice its MMA rate; the parity test holds it to 1e-5 of the oracle).  T2 is upper
+//                  triangular, so the first half of K only feeds rows j < 32: the rows of B are ordered
+//                  (j / 32, slot, j % 32) and the first two K-steps are issued with N = 128, a quarter of the MMA work
+//                  saved;
 //   k_alg8_sweep_pre  one warp per chain, lane = slot: the exponential race of every step of the block from L, the
 //                  auxiliary keys of k_aux_keys and the member counts -- the consumer of npb_alg8_tile4.cuh with the
 //                  producer warp replaced by a table in L2.  A birth writes theta' to the slot table, re-evaluates the
@@ -28,6 +34,7 @@
 // NPB_D64_DENSITY=fp32 replaces k_density_tc by a plain FP32 kernel (A/B measurements, cross-check in the tests).
 #include "npb_alg8_tile4.cuh"
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace {
 constexpr int GD = 64;
@@ -35,20 +42,21 @@ constexpr int GPS = npb_ps(GD);     // 2145
 constexpr int GTRI = npb_tri(GD);   // 2080
 constexpr int G_M = 128;            // steps per A tile (UMMA M)
 constexpr int G_NS = 4;             // slots per unit of work (UMMA N = 64 * 4)
-constexpr int G_STAGES = 3;         // A ring
-constexpr int G_CHUNK = 4096;       // 32 rows x 128 bytes, swizzled
-constexpr int G_SLOT_IMG = 6 * G_CHUNK;   // (kh0: hi, lo) x jh0; (kh1: hi, lo) x (jh0, jh1)
+constexpr int G_STAGES = 4;         // A ring (one stage = one tile)
+constexpr int G_CHUNK = 4096;       // 32 rows x 128 bytes (64 FP16), swizzled
+constexpr int G_SLOT_IMG = 4 * G_CHUNK;   // hi: rows j < 32, rows j >= 32; lo: the same
 constexpr int G_ASTAGE = 32768;     // 128 rows x 128 bytes, hi then lo
-constexpr int G_BBYTES = 98304;     // R0hi 16K, R0lo 16K, R1hi 32K, R1lo 32K
-constexpr int G_CONST = 68;         // nb[64], c2, pad
+constexpr int G_BBYTES = 65536;     // Bhi 32K (256 rows), Blo 32K
+constexpr int G_CONST = 68;         // nb[64], c2, descale, pad
+constexpr int G_XEXP = 14;          // operands are scaled so that their largest magnitude is just below 2^14
 constexpr int G_SMEM_MISC = 2048;
 constexpr int G_SMEM = 1024 + G_BBYTES + G_STAGES * G_ASTAGE + G_SMEM_MISC;
-constexpr uint32_t G_R0HI = 0, G_R0LO = 16384, G_R1HI = 32768, G_R1LO = 65536, G_A0 = G_BBYTES;
+constexpr uint32_t G_BHI = 0, G_BLO = 32768, G_A0 = G_BBYTES;
 }
 
 struct GemmArgs {
-	const uint8_t *Aimg;  // [ntiles][2][32 KB]
-	const uint8_t *Bimg;  // [C * 32][24 KB]
+	const uint8_t *Aimg;  // [ntiles][32 KB]
+	const uint8_t *Bimg;  // [C * 32][16 KB]
 	const float *Bconst;  // [C * 32][G_CONST]
 	float *L;             // [C][BS][32]
 	int C, ntiles, BS;
@@ -63,14 +71,22 @@ struct PreArgs {
 	int spec;                  // 0: sequential pass only (NPB_D64_SPEC=0; the result must not depend on it)
 };
 
-// byte offset of float k (0..31) of row `row` in a K-major, 128-byte-swizzled region (rows of 128 bytes, base 1024-aligned)
+// byte offset of FP16 element k (0..63) of row `row` in a K-major, 128-byte-swizzled region (rows of 128 bytes, base
+// 1024-aligned)
 __host__ __device__ __forceinline__ uint32_t g_sw128(uint32_t row, uint32_t k) {
-	return row * 128u + ((((k >> 2) ^ (row & 7u)) << 4) | ((k & 3u) << 2));
+	return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));
 }
-__device__ __forceinline__ float g_tf32(float v) {
-	uint32_t r;
-	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-	return __uint_as_float(r);
+// v = hi + lo, both FP16 (lo may be subnormal: quantum 2^-24)
+__device__ __forceinline__ void g_split(float v, __half &hi, __half &lo) {
+	hi = __float2half_rn(v);
+	lo = __float2half_rn(v - __half2float(hi));
+}
+// the power of two that brings a magnitude just below 2^G_XEXP
+__device__ __forceinline__ int g_scale_exp(float maxabs) {
+	if (!(maxabs > 0.0f) || !isfinite(maxabs)) return 0;
+	int m;
+	frexpf(maxabs, &m); // maxabs = f 2^m, f in [0.5, 1)
+	return G_XEXP - m;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -87,7 +103,27 @@ __global__ void k_colmean(const double *X, int64_t N, int D, double *out) {
 		if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) out[c] = red[0] / (double)N;
+	const double mean = red[0] / (double)N;
+	__syncthreads();
+	// largest centred magnitude of the column (out[D + 1 + c]); k_xscale reduces over the columns
+	double mx = 0.0;
+	for (int64_t i = threadIdx.x; i < N; i += 256) mx = fmax(mx, fabs(X[i * D + c] - mean));
+	red[threadIdx.x] = mx;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		out[c] = mean;
+		out[D + 1 + c] = red[0];
+	}
+}
+// out[D] = exponent of the power-of-two scale of the A operand
+__global__ void k_xscale(double *out, int D) {
+	double mx = 0.0;
+	for (int c = 0; c < D; ++c) mx = fmax(mx, out[D + 1 + c]);
+	out[D] = (double)g_scale_exp((float)mx);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -96,34 +132,48 @@ __global__ void k_colmean(const double *X, int64_t N, int D, double *out) {
 __global__ void __launch_bounds__(256) k_pre_aimg(const double *X64, const double *xbar, const int32_t *order, int nsteps, int ntiles,
 		uint8_t *Aimg) {
 	const int idx = blockIdx.x * 256 + threadIdx.x;
-	const int s = idx >> 4, q = idx & 15;
+	const int s = idx >> 3, q = idx & 7; // step, piece of 8 coordinates
 	if (s >= ntiles * G_M) return;
-	float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+	const float sx = ldexpf(1.0f, (int)xbar[GD]);
+	__align__(16) __half hi[8], lo[8];
 	if (s < nsteps) {
-		const double *x = X64 + (size_t)order[s] * GD + q * 4;
+		const double *x = X64 + (size_t)order[s] * GD + q * 8;
 #pragma unroll
-		for (int e = 0; e < 4; ++e) v[e] = (float)(x[e] - xbar[q * 4 + e]);
+		for (int e = 0; e < 8; ++e) g_split((float)(x[e] - xbar[q * 8 + e]) * sx, hi[e], lo[e]);
+	} else {
+#pragma unroll
+		for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
 	}
-	float4 hi, lo;
-	hi.x = g_tf32(v[0]); hi.y = g_tf32(v[1]); hi.z = g_tf32(v[2]); hi.w = g_tf32(v[3]);
-	lo.x = g_tf32(v[0] - hi.x); lo.y = g_tf32(v[1] - hi.y); lo.z = g_tf32(v[2] - hi.z); lo.w = g_tf32(v[3] - hi.w);
-	const int t = s / G_M, r = s % G_M, kh = q >> 3, kk = (q & 7) * 4;
-	uint8_t *dst = Aimg + ((size_t)t * 2 + kh) * G_ASTAGE + g_sw128(r, kk);
-	*reinterpret_cast<float4 *>(dst) = hi;
-	*reinterpret_cast<float4 *>(dst + 16384) = lo;
+	const int t = s / G_M, r = s % G_M;
+	uint8_t *dst = Aimg + (size_t)t * G_ASTAGE + g_sw128(r, q * 8);
+	*reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+	*reinterpret_cast<uint4 *>(dst + 16384) = *reinterpret_cast<const uint4 *>(lo);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// B images and epilogue constants of the slots marked dirty: CTA = (chain, slot)
+// B images and epilogue constants of the slots marked dirty (or born two blocks ago): CTA = (chain, slot)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pre_bimg(const float *theta, const double *xbar, uint8_t *dirty, const uint32_t *born, uint8_t *Bimg,
 		float *Bconst) {
 	__shared__ float th[GPS + 3];
+	__shared__ float red[256];
 	const int cs = blockIdx.x; // chain * 32 + slot
 	if (!dirty[cs] && !((born[cs >> 5] >> (cs & 31)) & 1u)) return;
 	const float *src = theta + (size_t)cs * GPS;
-	for (int i = threadIdx.x; i < GPS; i += 256) th[i] = src[i];
+	float mx = 0.0f;
+	for (int i = threadIdx.x; i < GPS; i += 256) {
+		const float v = src[i];
+		th[i] = v;
+		if (i >= GD && i < GD + GTRI) mx = fmaxf(mx, fabsf(v));
+	}
+	red[threadIdx.x] = mx;
 	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+		__syncthreads();
+	}
+	const int et = g_scale_exp(red[0]), ex = (int)xbar[GD];
+	const float st = ldexpf(1.0f, et);
 	if (threadIdx.x < GD) {
 		const int j = threadIdx.x;
 		float s = 0.0f;
@@ -131,21 +181,20 @@ __global__ void __launch_bounds__(256) k_pre_bimg(const float *theta, const doub
 		Bconst[(size_t)cs * G_CONST + j] = -s;
 	}
 	if (threadIdx.x == GD) Bconst[(size_t)cs * G_CONST + GD] = th[GD + GTRI];
+	if (threadIdx.x == GD + 1) Bconst[(size_t)cs * G_CONST + GD + 1] = ldexpf(1.0f, -(ex + et));
 	uint8_t *img = Bimg + (size_t)cs * G_SLOT_IMG;
-	// chunk: 0 (kh0, hi, jh0)  1 (kh0, lo, jh0)  2 (kh1, hi, jh0)  3 (kh1, hi, jh1)  4 (kh1, lo, jh0)  5 (kh1, lo, jh1)
-	for (int pc = threadIdx.x; pc < 6 * 256; pc += 256) {
-		const int chunk = pc >> 8, jl = (pc >> 3) & 31, p = pc & 7;
-		const int kh = chunk >= 2, part = (chunk == 1 || chunk >= 4), jh = (chunk == 3 || chunk == 5);
+	// chunk: 0 (hi, rows j < 32)  1 (hi, rows j >= 32)  2 (lo, j < 32)  3 (lo, j >= 32); a row is the 64 columns of T2 row j
+	for (int pc = threadIdx.x; pc < 2 * 256; pc += 256) {
+		const int jh = pc >> 8, jl = (pc >> 3) & 31, p = pc & 7;
 		const int j = jh * 32 + jl;
-		float o[4];
+		__align__(16) __half hi[8], lo[8];
 #pragma unroll
-		for (int e = 0; e < 4; ++e) {
-			const int c = kh * 32 + p * 4 + e;
-			const float t = c >= j ? th[GD + npb_tri_off(GD, j, c)] : 0.0f;
-			const float hi = g_tf32(t);
-			o[e] = part ? g_tf32(t - hi) : hi;
+		for (int e = 0; e < 8; ++e) {
+			const int c = p * 8 + e;
+			g_split(c >= j ? th[GD + npb_tri_off(GD, j, c)] * st : 0.0f, hi[e], lo[e]);
 		}
-		*reinterpret_cast<float4 *>(img + chunk * G_CHUNK + g_sw128(jl, p * 4)) = make_float4(o[0], o[1], o[2], o[3]);
+		*reinterpret_cast<uint4 *>(img + jh * G_CHUNK + g_sw128(jl, p * 8)) = *reinterpret_cast<const uint4 *>(hi);
+		*reinterpret_cast<uint4 *>(img + (2 + jh) * G_CHUNK + g_sw128(jl, p * 8)) = *reinterpret_cast<const uint4 *>(lo);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) dirty[cs] = 0;
@@ -192,17 +241,17 @@ __device__ __forceinline__ void g_tc_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t g_desc(uint32_t saddr) {
 	return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// instruction descriptor, kind::tf32: D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10) and [10,13)), both K-major, N >> 3 at
+// instruction descriptor, kind::f16: D = F32 (1 at [4,6)), A = B = F16 (0 at [7,10) and [10,13)), both K-major, N >> 3 at
 // [17,23), M >> 4 at [24,29)
 __host__ __device__ constexpr uint32_t g_idesc(int M, int N) {
-	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+	return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void g_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void g_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
 	asm volatile(
 			"{\n\t"
 			".reg .pred p;\n\t"
 			"setp.ne.b32 p, %4, 0;\n\t"
-			"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+			"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
 			"}\n" ::"r"(tmem_d),
 			"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
 			: "memory");
@@ -276,18 +325,16 @@ __global__ void __launch_bounds__(192, 1) k_density_tc(const GemmArgs g) {
 				const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
 				for (int sl = 0; sl < G_NS; ++sl) {
 					const uint8_t *src = g.Bimg + ((size_t)c * 32 + gq * G_NS + sl) * G_SLOT_IMG;
-					g_bulk_g2s(base + G_R0HI + sl * G_CHUNK, src + 0 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_R0LO + sl * G_CHUNK, src + 1 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_R1HI + sl * G_CHUNK, src + 2 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_R1HI + 16384 + sl * G_CHUNK, src + 3 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_R1LO + sl * G_CHUNK, src + 4 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_R1LO + 16384 + sl * G_CHUNK, src + 5 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BHI + sl * G_CHUNK, src + 0 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BHI + 16384 + sl * G_CHUNK, src + 1 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BLO + sl * G_CHUNK, src + 2 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BLO + 16384 + sl * G_CHUNK, src + 3 * G_CHUNK, G_CHUNK, bar_b_full);
 				}
-				for (int st = 0; st < g.ntiles * 2; ++st, ++a_it) {
+				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
 					const uint32_t s = a_it % G_STAGES, ph = (a_it / G_STAGES) & 1u;
 					g_mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
 					g_mbar_expect_tx(bar_a_full + 8 * s, G_ASTAGE);
-					g_bulk_g2s(base + G_A0 + s * G_ASTAGE, g.Aimg + (size_t)st * G_ASTAGE, G_ASTAGE, bar_a_full + 8 * s);
+					g_bulk_g2s(base + G_A0 + s * G_ASTAGE, g.Aimg + (size_t)t * G_ASTAGE, G_ASTAGE, bar_a_full + 8 * s);
 				}
 			}
 		}
@@ -300,37 +347,33 @@ __global__ void __launch_bounds__(192, 1) k_density_tc(const GemmArgs g) {
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
 				g_mbar_wait(bar_b_full, unit_it & 1u);
 				g_tc_fence_after();
-				for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+				for (int t = 0; t < g.ntiles; ++t, ++tile_it, ++a_it) {
 					const uint32_t buf = tile_it & 1u;
 					g_mbar_wait(bar_t_empty + 8 * buf, ((tile_it >> 1) & 1u) ^ 1u); // the epilogue has drained this accumulator
+					const uint32_t s = a_it % G_STAGES;
+					g_mbar_wait(bar_a_full + 8 * s, (a_it / G_STAGES) & 1u);
 					g_tc_fence_after();
 					const uint32_t dcol = tmem + buf * 256u;
+					const uint32_t Ahi = base + G_A0 + s * G_ASTAGE, Alo = Ahi + 16384;
 #pragma unroll
-					for (int kh = 0; kh < 2; ++kh, ++a_it) {
-						const uint32_t s = a_it % G_STAGES;
-						g_mbar_wait(bar_a_full + 8 * s, (a_it / G_STAGES) & 1u);
-						g_tc_fence_after();
-						const uint32_t Ahi = base + G_A0 + s * G_ASTAGE, Alo = Ahi + 16384;
-						const uint32_t Bhi = base + (kh ? G_R1HI : G_R0HI), Blo = base + (kh ? G_R1LO : G_R0LO);
+					for (int prod = 0; prod < 3; ++prod) {
+						const uint32_t A = prod == 2 ? Alo : Ahi, B = base + (prod == 1 ? G_BLO : G_BHI);
 #pragma unroll
-						for (int prod = 0; prod < 3; ++prod) {
-							const uint32_t A = prod == 2 ? Alo : Ahi, B = prod == 1 ? Blo : Bhi;
-#pragma unroll
-							for (int k = 0; k < 4; ++k) {
-								const uint64_t ad = g_desc(A + k * 32), bd = g_desc(B + k * 32);
-								if (kh == 0) {
-									g_mma_tf32(dcol, ad, bd, ID128, (prod | k) != 0);
-								} else if (prod == 0 && k == 0) {
-									// columns 0-127 already hold the first K-half, columns 128-255 start here
-									g_mma_tf32(dcol, ad, bd, ID128, 1u);
-									g_mma_tf32(dcol + 128u, ad, g_desc(B + 16384 + k * 32), ID128, 0u);
-								} else {
-									g_mma_tf32(dcol, ad, bd, ID256, 1u);
-								}
+						for (int k = 0; k < 4; ++k) { // K-step = 16 columns = 32 bytes of the swizzled row
+							const uint64_t ad = g_desc(A + k * 32), bd = g_desc(B + k * 32);
+							if (k < 2) {
+								// columns c < 32 only meet rows j < 32 of the triangular factor: N = 128 (accumulator columns 0-127)
+								g_mma_f16(dcol, ad, bd, ID128, (prod | k) != 0);
+							} else if (prod == 0 && k == 2) {
+								// columns 0-127 continue, columns 128-255 (rows j >= 32) start here
+								g_mma_f16(dcol, ad, bd, ID128, 1u);
+								g_mma_f16(dcol + 128u, ad, g_desc(B + 16384 + k * 32), ID128, 0u);
+							} else {
+								g_mma_f16(dcol, ad, bd, ID256, 1u);
 							}
 						}
-						g_tc_commit(bar_a_empty + 8 * s); // frees the stage once these MMAs have read it
 					}
+					g_tc_commit(bar_a_empty + 8 * s); // frees the stage once these MMAs have read it
 					g_tc_commit(bar_t_full + 8 * buf);
 				}
 				g_tc_commit(bar_b_empty);
@@ -359,6 +402,7 @@ __global__ void __launch_bounds__(192, 1) k_density_tc(const GemmArgs g) {
 #pragma unroll
 				for (int sl = 0; sl < G_NS; ++sl) {
 					const float *ec = econst + sl * G_CONST;
+					const float dsc = ec[GD + 1];
 					float q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
 					for (int jh = 0; jh < 2; ++jh) {
@@ -367,7 +411,8 @@ __global__ void __launch_bounds__(192, 1) k_density_tc(const GemmArgs g) {
 #pragma unroll
 						for (int i = 0; i < 32; i += 4) {
 							const float4 nb = *reinterpret_cast<const float4 *>(ec + jh * 32 + i);
-							const float y0 = v[i] + nb.x, y1 = v[i + 1] + nb.y, y2 = v[i + 2] + nb.z, y3 = v[i + 3] + nb.w;
+							const float y0 = fmaf(v[i], dsc, nb.x), y1 = fmaf(v[i + 1], dsc, nb.y), y2 = fmaf(v[i + 2], dsc, nb.z),
+									    y3 = fmaf(v[i + 3], dsc, nb.w);
 							q0 = fmaf(y0, y0, q0);
 							q1 = fmaf(y1, y1, q1);
 							q0 = fmaf(y2, y2, q0);
@@ -696,13 +741,15 @@ static npb_status g_ensure(npb_chains *ch) {
 	npb_dataset *ds = ch->ds;
 	const int BS = g_block_steps();
 	if (!ds->Xbar) {
-		NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * GD));
+		NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * (2 * GD + 1))); // means, scale exponent, column maxima
 		k_colmean<<<GD, 256, 0, ctx->stream>>>(ds->X64, ds->N, GD, ds->Xbar);
+		NPB_CUDA_OK(cudaGetLastError());
+		k_xscale<<<1, 1, 0, ctx->stream>>>(ds->Xbar, GD);
 		NPB_CUDA_OK(cudaGetLastError());
 	}
 	if (!ch->g_L) {
 		const size_t C = (size_t)ch->C;
-		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * 2 * G_ASTAGE));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * G_ASTAGE));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bimg, C * 32 * G_SLOT_IMG));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bconst, C * 32 * G_CONST * sizeof(float)));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_L, 2 * C * (size_t)(BS + 32) * 32 * sizeof(float)));
@@ -739,7 +786,7 @@ static npb_status g_density_block(npb_chains *ch, const int32_t *d_order, int ns
 		return NPB_OK;
 	}
 	const int ntiles = (nsteps + G_M - 1) / G_M;
-	k_pre_aimg<<<(ntiles * G_M * 16 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
+	k_pre_aimg<<<(ntiles * G_M * 8 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
 	NPB_CUDA_OK(cudaGetLastError());
 	k_pre_bimg<<<C * 32, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_born + (size_t)buf * C, ch->g_bimg, ch->g_bconst);
 	NPB_CUDA_OK(cudaGetLastError());

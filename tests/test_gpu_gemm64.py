@@ -1,4 +1,4 @@
-"""GPU (pytest -m gpu): the D = 64 sweep path (npb_alg8_gemm.cu): tcgen05 3xTF32 density table + warp-per-chain race."""
+"""GPU (pytest -m gpu): the D = 64 sweep path (npb_alg8_gemm.cu): tcgen05 FP16x3 density table + warp-per-chain race."""
 import os
 
 import numpy as np
@@ -31,8 +31,8 @@ def _full_cov_params(rng, X, K):
 
 @pytest.mark.parametrize("density", ["tc", "fp32"])
 def test_gemm64_density_table_within_1e5_of_oracle(npb, ctx, oracle, env, density):
-    """The log-density table the D = 64 sweep reads (tcgen05 kind::tf32, three TF32 products per FP32 product, operands
-    centred on the dataset mean; or the FP32 kernel) against the oracle's double-precision density: 1e-5 relative
+    """The log-density table the D = 64 sweep reads (tcgen05 kind::f16, three FP16 products per FP32 product, operands
+    centred on the dataset mean and scaled by powers of two; or the FP32 kernel) against the oracle's double-precision density: 1e-5 relative
     (north_star tolerance), full covariances, near and far clusters."""
     env["NPB_D64_DENSITY"] = density
     rng = np.random.default_rng(64)
@@ -52,6 +52,7 @@ def test_gemm64_density_table_within_1e5_of_oracle(npb, ctx, oracle, env, densit
         occ[slots] = True
         assert occ.sum() >= 30 and np.all(np.isnan(got[~occ]))
         err = np.abs(got[occ] - want[occ]) / np.maximum(1.0, np.abs(want[occ]))
+        print(density, "max relative error of the table", err.max())
         assert err.max() < 1e-5, (density, err.max())
     ch.close()
     ds.close()
