@@ -27,10 +27,11 @@
 //                  triangular, so the first half of K only feeds rows j < 32: the rows of B are ordered
 //                  (j / 32, slot, j % 32) and the first two K-steps are issued with N = 128, a quarter of the MMA work
 //                  saved;
-//   k_alg8_sweep_pre  one warp per chain, lane = slot: the exponential race of every step of the block from L, the
-//                  auxiliary keys of k_aux_keys and the member counts -- the consumer of npb_alg8_tile4.cuh with the
-//                  producer warp replaced by a table in L2.  A birth writes theta' to the slot table, re-evaluates the
-//                  slot's column of L for the rest of the block on the CUDA cores and marks the slot for k_pre_bimg.
+//   g_consume_chain  (two more warps of the same kernel, working on the PREVIOUS block's table) one warp per chain: the
+//                  exponential race of every step of the block from L, the auxiliary keys of k_aux_keys and the member
+//                  counts -- the consumer of npb_alg8_tile4.cuh with the producer warp replaced by a table in L2.  A birth
+//                  writes theta' to the slot table, re-evaluates the slot's column of L for the rest of the block on the
+//                  CUDA cores and marks the slot for k_pre_bimg.
 // NPB_D64_DENSITY=fp32 replaces k_density_tc by a plain FP32 kernel (A/B measurements, cross-check in the tests).
 #include "npb_alg8_tile4.cuh"
 #include <cstdlib>
@@ -50,7 +51,8 @@ constexpr int G_BBYTES = 65536;     // Bhi 32K (256 rows), Blo 32K
 constexpr int G_CONST = 68;         // nb[64], c2, descale, pad
 constexpr int G_XEXP = 14;          // operands are scaled so that their largest magnitude is just below 2^14
 constexpr int G_SMEM_MISC = 2048;
-constexpr int G_SMEM = 1024 + G_BBYTES + G_STAGES * G_ASTAGE + G_SMEM_MISC;
+constexpr int G_CONS_FLOATS = 32 * 33 + 64; // per race warp: tile, lg_s, lg1_s
+constexpr int G_SMEM = 1024 + G_BBYTES + G_STAGES * G_ASTAGE + G_SMEM_MISC + 2 * G_CONS_FLOATS * 4;
 constexpr uint32_t G_BHI = 0, G_BLO = 32768, G_A0 = G_BBYTES;
 }
 
@@ -256,6 +258,25 @@ __device__ __forceinline__ void g_mma_f16(uint32_t tmem_d, uint64_t adesc, uint6
 			"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
 			: "memory");
 }
+// the load alone: the registers are valid after g_tmem_wait_ld, which takes the arrays as in/out operands so that no use
+// of them is scheduled above the wait
+__device__ __forceinline__ void g_tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+	asm volatile(
+			"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+			"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+			"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+			: "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+			  "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+			  "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+			  "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+			: "r"(taddr)
+			: "memory");
+}
+__device__ __forceinline__ void g_tmem_wait_ld(float (&a)[32], float (&b)[32]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 32; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]));
+}
 __device__ __forceinline__ void g_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 	uint32_t r[32];
 	asm volatile(
@@ -271,194 +292,6 @@ __device__ __forceinline__ void g_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
 	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_density_tc: warps 0-3 epilogue (TMEM lanes 32 w .. 32 w + 31 = steps of the tile), warp 4 MMA issue + TMEM
-// allocation, warp 5 bulk-copy producer
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 1) k_density_tc(const GemmArgs g) {
-	extern __shared__ uint8_t g_smem_raw[];
-	const uint32_t raw = g_smem_u32(g_smem_raw);
-	const uint32_t base = (raw + 1023u) & ~1023u;
-	uint8_t *gen = g_smem_raw + (base - raw);
-	// misc area: barriers, TMEM address, epilogue constants
-	const uint32_t misc = base + G_BBYTES + G_STAGES * G_ASTAGE;
-	const uint32_t bar_b_full = misc, bar_b_empty = misc + 8;
-	const uint32_t bar_a_full = misc + 16, bar_a_empty = misc + 16 + 8 * G_STAGES;
-	const uint32_t bar_t_full = misc + 16 + 16 * G_STAGES, bar_t_empty = bar_t_full + 16;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + 256);
-	float *econst = reinterpret_cast<float *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + 512); // [4][G_CONST]
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int n_units = g.C * (32 / G_NS);
-
-	if (warp == 5 && lane == 0) {
-		g_mbar_init(bar_b_full, 1);
-		g_mbar_init(bar_b_empty, 1);
-		for (int s = 0; s < G_STAGES; ++s) {
-			g_mbar_init(bar_a_full + 8 * s, 1);
-			g_mbar_init(bar_a_empty + 8 * s, 1);
-		}
-		for (int b = 0; b < 2; ++b) {
-			g_mbar_init(bar_t_full + 8 * b, 1);
-			g_mbar_init(bar_t_empty + 8 * b, 128);
-		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		asm volatile("fence.proxy.async;" ::: "memory");
-	}
-	if (warp == 4) {
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
-		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-	}
-	g_tc_fence_before();
-	__syncthreads();
-	g_tc_fence_after();
-	const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
-
-	if (warp == 5) {
-		// ===================== bulk-copy producer =====================
-		if (lane == 0) {
-			uint32_t a_it = 0, unit_it = 0;
-			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
-				g_mbar_wait(bar_b_empty, (unit_it & 1u) ^ 1u); // the MMAs of the previous unit have read B
-				g_mbar_expect_tx(bar_b_full, G_BBYTES);
-				const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
-				for (int sl = 0; sl < G_NS; ++sl) {
-					const uint8_t *src = g.Bimg + ((size_t)c * 32 + gq * G_NS + sl) * G_SLOT_IMG;
-					g_bulk_g2s(base + G_BHI + sl * G_CHUNK, src + 0 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_BHI + 16384 + sl * G_CHUNK, src + 1 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_BLO + sl * G_CHUNK, src + 2 * G_CHUNK, G_CHUNK, bar_b_full);
-					g_bulk_g2s(base + G_BLO + 16384 + sl * G_CHUNK, src + 3 * G_CHUNK, G_CHUNK, bar_b_full);
-				}
-				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
-					const uint32_t s = a_it % G_STAGES, ph = (a_it / G_STAGES) & 1u;
-					g_mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
-					g_mbar_expect_tx(bar_a_full + 8 * s, G_ASTAGE);
-					g_bulk_g2s(base + G_A0 + s * G_ASTAGE, g.Aimg + (size_t)t * G_ASTAGE, G_ASTAGE, bar_a_full + 8 * s);
-				}
-			}
-		}
-		__syncwarp();
-	} else if (warp == 4) {
-		// ===================== MMA issue (one thread) =====================
-		if (lane == 0) {
-			constexpr uint32_t ID128 = g_idesc(G_M, 128), ID256 = g_idesc(G_M, 256);
-			uint32_t a_it = 0, tile_it = 0, unit_it = 0;
-			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
-				g_mbar_wait(bar_b_full, unit_it & 1u);
-				g_tc_fence_after();
-				for (int t = 0; t < g.ntiles; ++t, ++tile_it, ++a_it) {
-					const uint32_t buf = tile_it & 1u;
-					g_mbar_wait(bar_t_empty + 8 * buf, ((tile_it >> 1) & 1u) ^ 1u); // the epilogue has drained this accumulator
-					const uint32_t s = a_it % G_STAGES;
-					g_mbar_wait(bar_a_full + 8 * s, (a_it / G_STAGES) & 1u);
-					g_tc_fence_after();
-					const uint32_t dcol = tmem + buf * 256u;
-					const uint32_t Ahi = base + G_A0 + s * G_ASTAGE, Alo = Ahi + 16384;
-#pragma unroll
-					for (int prod = 0; prod < 3; ++prod) {
-						const uint32_t A = prod == 2 ? Alo : Ahi, B = base + (prod == 1 ? G_BLO : G_BHI);
-#pragma unroll
-						for (int k = 0; k < 4; ++k) { // K-step = 16 columns = 32 bytes of the swizzled row
-							const uint64_t ad = g_desc(A + k * 32), bd = g_desc(B + k * 32);
-							if (k < 2) {
-								// columns c < 32 only meet rows j < 32 of the triangular factor: N = 128 (accumulator columns 0-127)
-								g_mma_f16(dcol, ad, bd, ID128, (prod | k) != 0);
-							} else if (prod == 0 && k == 2) {
-								// columns 0-127 continue, columns 128-255 (rows j >= 32) start here
-								g_mma_f16(dcol, ad, bd, ID128, 1u);
-								g_mma_f16(dcol + 128u, ad, g_desc(B + 16384 + k * 32), ID128, 0u);
-							} else {
-								g_mma_f16(dcol, ad, bd, ID256, 1u);
-							}
-						}
-					}
-					g_tc_commit(bar_a_empty + 8 * s); // frees the stage once these MMAs have read it
-					g_tc_commit(bar_t_full + 8 * buf);
-				}
-				g_tc_commit(bar_b_empty);
-			}
-		}
-		__syncwarp();
-	} else {
-		// ===================== epilogue: thread = step of the tile =====================
-		const int row = warp * 32 + lane;
-		uint32_t tile_it = 0;
-		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-			const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-			{
-				const float *src = g.Bconst + ((size_t)c * 32 + gq * G_NS) * G_CONST;
-				for (int i = threadIdx.x; i < G_NS * G_CONST; i += 128) econst[i] = __ldg(src + i);
-			}
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-			float *Lc = g.L + ((size_t)c * g.BS) * 32 + gq * G_NS;
-			for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
-				const uint32_t buf = tile_it & 1u;
-				g_mbar_wait(bar_t_full + 8 * buf, (tile_it >> 1) & 1u);
-				g_tc_fence_after();
-				const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + buf * 256u;
-				float out[G_NS];
-#pragma unroll
-				for (int sl = 0; sl < G_NS; ++sl) {
-					const float *ec = econst + sl * G_CONST;
-					const float dsc = ec[GD + 1];
-					float q0 = 0.0f, q1 = 0.0f;
-#pragma unroll
-					for (int jh = 0; jh < 2; ++jh) {
-						float v[32];
-						g_tmem_ld32(taddr + jh * 128u + sl * 32u, v);
-#pragma unroll
-						for (int i = 0; i < 32; i += 4) {
-							const float4 nb = *reinterpret_cast<const float4 *>(ec + jh * 32 + i);
-							const float y0 = fmaf(v[i], dsc, nb.x), y1 = fmaf(v[i + 1], dsc, nb.y), y2 = fmaf(v[i + 2], dsc, nb.z),
-									    y3 = fmaf(v[i + 3], dsc, nb.w);
-							q0 = fmaf(y0, y0, q0);
-							q1 = fmaf(y1, y1, q1);
-							q0 = fmaf(y2, y2, q0);
-							q1 = fmaf(y3, y3, q1);
-						}
-					}
-					out[sl] = ec[GD] - (q0 + q1);
-				}
-				g_tc_fence_before();
-				g_mbar_arrive(bar_t_empty + 8 * buf);
-				*reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32) = make_float4(out[0], out[1], out[2], out[3]);
-			}
-		}
-	}
-	g_tc_fence_before();
-	__syncthreads();
-	if (warp == 4) {
-		g_tc_fence_after();
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// the same table on the FP32 pipe (NPB_D64_DENSITY=fp32): thread = step, loop over the 32 slots
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_density_fp32(const double *X64, const double *xbar, const int32_t *order, int nsteps,
-		const float *theta, float *L, int BS) {
-	const int s = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y;
-	if (s >= nsteps) return;
-	float x[GD];
-	{
-		const double *xr = X64 + (size_t)order[s] * GD;
-#pragma unroll
-		for (int i = 0; i < GD; ++i) x[i] = (float)(xr[i] - xbar[i]);
-	}
-	for (int k = 0; k < 32; ++k) {
-		const float *th = theta + ((size_t)c * 32 + k) * GPS;
-		float q = 0.0f;
-#pragma unroll 4
-		for (int r = 0; r < GD; ++r) {
-			float y = 0.0f;
-			for (int cc = r; cc < GD; ++cc) y = fmaf(__ldg(th + GD + npb_tri_off(GD, r, cc)), x[cc] - (float)((double)__ldg(th + cc) - xbar[cc]), y);
-			q = fmaf(y, y, q);
-		}
-		L[((size_t)c * BS + s) * 32 + k] = __ldg(th + GD + GTRI) - q;
-	}
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -529,12 +362,11 @@ __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
 // first move are final, and the sequential pass (lane = slot, the consumer of npb_alg8_tile4.cuh) takes over from that
 // step; both passes evaluate the same keys (same noise, same operation order), so the result does not depend on which
 // pass decided a step.  A chain that moves a lot (burn-in) skips the speculative pass.
+// tile: [32 * 33] floats, [slot * 33 + step]; lg_s, lg1_s: [32] floats each, log2 n_k and log2 (n_k - 1) of every slot
+// (-inf without members) -- shared memory private to the calling warp
 template <int M>
-__global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
-	__shared__ float tile[32 * 33]; // [slot * 33 + step]
-	__shared__ float lg_s[32], lg1_s[32]; // log2 n_k and log2 (n_k - 1) of every slot (-inf without members)
+__device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chain, const int lane, float *tile, float *lg_s, float *lg1_s) {
 	const SweepArgs &a = p.a;
-	const int lane = threadIdx.x, chain = blockIdx.x;
 	const int N = a.N, C = a.C;
 	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 	float *thc = a.theta + (size_t)chain * 32 * GPS;
@@ -719,6 +551,210 @@ __global__ void __launch_bounds__(32) k_alg8_sweep_pre(const PreArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_density_tc: the density table of block k + 1 AND the race of block k in one persistent kernel.
+// Warps 0 .. EW-1: epilogue (TMEM lanes 32 (w % 4) .. + 31 = steps of the tile), warp EW: MMA issue + TMEM allocation,
+// warp EW + 1: bulk-copy producer, warps EW + 2, EW + 3: the race (g_consume_chain) of chains blockIdx.x and
+// blockIdx.x + gridDim.x, ... of the PREVIOUS block, whose table sits in the other buffer.  (Two kernels on two streams did
+// the same, but whether they overlapped was left to the block scheduler: sweeps came out at 66 or at 94 ms.)
+// ---------------------------------------------------------------------------------------------------------
+template <int EW, int M> // EW epilogue warps: 4 (each takes the unit's four slots) or 8 (two slots each); M auxiliary draws
+__global__ void __launch_bounds__(EW * 32 + 128, 1) k_density_tc(const GemmArgs g, const PreArgs p, const int do_density, const int do_consume) {
+	constexpr int SPW = 16 / EW; // slots per epilogue warp
+	extern __shared__ uint8_t g_smem_raw[];
+	const uint32_t raw = g_smem_u32(g_smem_raw);
+	const uint32_t base = (raw + 1023u) & ~1023u;
+	uint8_t *gen = g_smem_raw + (base - raw);
+	// misc area: barriers, TMEM address, epilogue constants
+	const uint32_t misc = base + G_BBYTES + G_STAGES * G_ASTAGE;
+	const uint32_t bar_b_full = misc, bar_b_empty = misc + 8;
+	const uint32_t bar_a_full = misc + 16, bar_a_empty = misc + 16 + 8 * G_STAGES;
+	const uint32_t bar_t_full = misc + 16 + 16 * G_STAGES, bar_t_empty = bar_t_full + 16;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + 256);
+	float *econst = reinterpret_cast<float *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + 512); // [4][G_CONST]
+	float *cons_smem = reinterpret_cast<float *>(gen + G_BBYTES + G_STAGES * G_ASTAGE + G_SMEM_MISC); // [2][G_CONS_FLOATS]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n_units = do_density ? g.C * (32 / G_NS) : 0;
+
+	if (warp == EW + 1 && lane == 0) {
+		g_mbar_init(bar_b_full, 1);
+		g_mbar_init(bar_b_empty, 1);
+		for (int s = 0; s < G_STAGES; ++s) {
+			g_mbar_init(bar_a_full + 8 * s, 1);
+			g_mbar_init(bar_a_empty + 8 * s, 1);
+		}
+		for (int b = 0; b < 2; ++b) {
+			g_mbar_init(bar_t_full + 8 * b, 1);
+			g_mbar_init(bar_t_empty + 8 * b, EW * 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async;" ::: "memory");
+	}
+	if (warp == EW) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	g_tc_fence_after();
+	const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+	if (warp == EW + 1) {
+		// ===================== bulk-copy producer =====================
+		if (lane == 0) {
+			uint32_t a_it = 0, unit_it = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				g_mbar_wait(bar_b_empty, (unit_it & 1u) ^ 1u); // the MMAs of the previous unit have read B
+				g_mbar_expect_tx(bar_b_full, G_BBYTES);
+				const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
+				for (int sl = 0; sl < G_NS; ++sl) {
+					const uint8_t *src = g.Bimg + ((size_t)c * 32 + gq * G_NS + sl) * G_SLOT_IMG;
+					g_bulk_g2s(base + G_BHI + sl * G_CHUNK, src + 0 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BHI + 16384 + sl * G_CHUNK, src + 1 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BLO + sl * G_CHUNK, src + 2 * G_CHUNK, G_CHUNK, bar_b_full);
+					g_bulk_g2s(base + G_BLO + 16384 + sl * G_CHUNK, src + 3 * G_CHUNK, G_CHUNK, bar_b_full);
+				}
+				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
+					const uint32_t s = a_it % G_STAGES, ph = (a_it / G_STAGES) & 1u;
+					g_mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+					g_mbar_expect_tx(bar_a_full + 8 * s, G_ASTAGE);
+					g_bulk_g2s(base + G_A0 + s * G_ASTAGE, g.Aimg + (size_t)t * G_ASTAGE, G_ASTAGE, bar_a_full + 8 * s);
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == EW) {
+		// ===================== MMA issue (one thread) =====================
+		if (lane == 0) {
+			constexpr uint32_t ID128 = g_idesc(G_M, 128), ID256 = g_idesc(G_M, 256);
+			uint32_t a_it = 0, tile_it = 0, unit_it = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				g_mbar_wait(bar_b_full, unit_it & 1u);
+				g_tc_fence_after();
+				for (int t = 0; t < g.ntiles; ++t, ++tile_it, ++a_it) {
+					const uint32_t buf = tile_it & 1u;
+					g_mbar_wait(bar_t_empty + 8 * buf, ((tile_it >> 1) & 1u) ^ 1u); // the epilogue has drained this accumulator
+					const uint32_t s = a_it % G_STAGES;
+					g_mbar_wait(bar_a_full + 8 * s, (a_it / G_STAGES) & 1u);
+					g_tc_fence_after();
+					const uint32_t dcol = tmem + buf * 256u;
+					const uint32_t Ahi = base + G_A0 + s * G_ASTAGE, Alo = Ahi + 16384;
+#pragma unroll
+					for (int prod = 0; prod < 3; ++prod) {
+						const uint32_t A = prod == 2 ? Alo : Ahi, B = base + (prod == 1 ? G_BLO : G_BHI);
+#pragma unroll
+						for (int k = 0; k < 4; ++k) { // K-step = 16 columns = 32 bytes of the swizzled row
+							const uint64_t ad = g_desc(A + k * 32), bd = g_desc(B + k * 32);
+							if (k < 2) {
+								// columns c < 32 only meet rows j < 32 of the triangular factor: N = 128 (accumulator columns 0-127)
+								g_mma_f16(dcol, ad, bd, ID128, (prod | k) != 0);
+							} else if (prod == 0 && k == 2) {
+								// columns 0-127 continue, columns 128-255 (rows j >= 32) start here
+								g_mma_f16(dcol, ad, bd, ID128, 1u);
+								g_mma_f16(dcol + 128u, ad, g_desc(B + 16384 + k * 32), ID128, 0u);
+							} else {
+								g_mma_f16(dcol, ad, bd, ID256, 1u);
+							}
+						}
+					}
+					g_tc_commit(bar_a_empty + 8 * s); // frees the stage once these MMAs have read it
+					g_tc_commit(bar_t_full + 8 * buf);
+				}
+				g_tc_commit(bar_b_empty);
+			}
+		}
+		__syncwarp();
+	} else if (warp >= EW + 2) {
+		// ===================== the race of the previous block: one warp per chain =====================
+		if (do_consume) {
+			float *sm = cons_smem + (warp - (EW + 2)) * G_CONS_FLOATS;
+			for (int chain = blockIdx.x + (warp - (EW + 2)) * gridDim.x; chain < p.a.C; chain += 2 * gridDim.x)
+				g_consume_chain<M>(p, chain, lane, sm, sm + 32 * 33, sm + 32 * 33 + 32);
+		}
+	} else {
+		// ===================== epilogue: thread = (step of the tile, pair of slots) =====================
+		const int wq = warp & 3, eg = warp >> 2;
+		const int row = wq * 32 + lane;
+		uint32_t tile_it = 0;
+		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+			const int c = u / (32 / G_NS), gq = u % (32 / G_NS);
+			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+			{
+				const float *src = g.Bconst + ((size_t)c * 32 + gq * G_NS) * G_CONST;
+				for (int i = threadIdx.x; i < G_NS * G_CONST; i += EW * 32) econst[i] = __ldg(src + i);
+			}
+			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+			float *Lc = g.L + ((size_t)c * g.BS) * 32 + gq * G_NS + eg * SPW;
+			for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+				const uint32_t buf = tile_it & 1u;
+				g_mbar_wait(bar_t_full + 8 * buf, (tile_it >> 1) & 1u);
+				g_tc_fence_after();
+				const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u;
+				float out[SPW];
+#pragma unroll
+				for (int h = 0; h < SPW; ++h) {
+					const int sl = eg * SPW + h;
+					const float *ec = econst + sl * G_CONST;
+					const float dsc = ec[GD + 1];
+					float v0[32], v1[32];
+					g_tmem_ld32_nowait(taddr + sl * 32u, v0);
+					g_tmem_ld32_nowait(taddr + 128u + sl * 32u, v1);
+					g_tmem_wait_ld(v0, v1);
+					float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+					for (int i = 0; i < 32; i += 4) {
+						const float4 na = *reinterpret_cast<const float4 *>(ec + i);
+						const float4 nb = *reinterpret_cast<const float4 *>(ec + 32 + i);
+						const float a0 = fmaf(v0[i], dsc, na.x), a1 = fmaf(v0[i + 1], dsc, na.y), a2 = fmaf(v0[i + 2], dsc, na.z),
+									    a3 = fmaf(v0[i + 3], dsc, na.w);
+						const float b0 = fmaf(v1[i], dsc, nb.x), b1 = fmaf(v1[i + 1], dsc, nb.y), b2 = fmaf(v1[i + 2], dsc, nb.z),
+									    b3 = fmaf(v1[i + 3], dsc, nb.w);
+						q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+						q0 = fmaf(b0, b0, q0); q1 = fmaf(b1, b1, q1); q2 = fmaf(b2, b2, q2); q3 = fmaf(b3, b3, q3);
+					}
+					out[h] = ec[GD] - ((q0 + q1) + (q2 + q3));
+				}
+				g_tc_fence_before();
+				g_mbar_arrive(bar_t_empty + 8 * buf);
+				if constexpr (SPW == 4) *reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32) = make_float4(out[0], out[1], out[2], out[3]);
+				else *reinterpret_cast<float2 *>(Lc + (size_t)(t * G_M + row) * 32) = make_float2(out[0], out[1]);
+			}
+		}
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	if (warp == EW) {
+		g_tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the same table on the FP32 pipe (NPB_D64_DENSITY=fp32): thread = step, loop over the 32 slots
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_density_fp32(const double *X64, const double *xbar, const int32_t *order, int nsteps,
+		const float *theta, float *L, int BS) {
+	const int s = blockIdx.x * 128 + threadIdx.x, c = blockIdx.y;
+	if (s >= nsteps) return;
+	float x[GD];
+	{
+		const double *xr = X64 + (size_t)order[s] * GD;
+#pragma unroll
+		for (int i = 0; i < GD; ++i) x[i] = (float)(xr[i] - xbar[i]);
+	}
+	for (int k = 0; k < 32; ++k) {
+		const float *th = theta + ((size_t)c * 32 + k) * GPS;
+		float q = 0.0f;
+#pragma unroll 4
+		for (int r = 0; r < GD; ++r) {
+			float y = 0.0f;
+			for (int cc = r; cc < GD; ++cc) y = fmaf(__ldg(th + GD + npb_tri_off(GD, r, cc)), x[cc] - (float)((double)__ldg(th + cc) - xbar[cc]), y);
+			q = fmaf(y, y, q);
+		}
+		L[((size_t)c * BS + s) * 32 + k] = __ldg(th + GD + GTRI) - q;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 template npb_status npb_launch_aux_keys<64>(npb_chains *, const SweepArgs &);
@@ -757,51 +793,51 @@ static npb_status g_ensure(npb_chains *ch) {
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_born, 2 * C * sizeof(uint32_t)));
 		NPB_CUDA_OK(cudaMemsetAsync(ch->g_L, 0, 2 * C * (size_t)(BS + 32) * 32 * sizeof(float), ctx->stream));
 		NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * C * sizeof(uint32_t), ctx->stream));
-		NPB_CUDA_OK(cudaStreamCreateWithFlags(&ch->g_stream2, cudaStreamNonBlocking));
-		for (int i = 0; i < 2; ++i) {
-			NPB_CUDA_OK(cudaEventCreateWithFlags(&ch->g_evD[i], cudaEventDisableTiming));
-			NPB_CUDA_OK(cudaEventCreateWithFlags(&ch->g_evC[i], cudaEventDisableTiming));
-		}
 		ch->g_bs = BS;
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-		// one shared-memory carveout for the kernels that must be co-resident (an SM does not host two configurations)
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_pre<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_alg8_sweep_pre<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_pre_aimg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_pre_bimg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
 	}
 	return NPB_OK;
 }
 
-// the log2-density table of `nsteps` steps (scan order `d_order`) of every chain into ch->g_L
-static npb_status g_density_block(npb_chains *ch, const int32_t *d_order, int nsteps, int buf) {
+// One launch of the fused kernel: the log2-density table of `nsteps` steps (scan order `d_order`) of every chain into
+// table buffer `buf` (d_order != NULL), and / or the race of the block described by *cons (cons != NULL).
+static npb_status g_launch_block(npb_chains *ch, const int32_t *d_order, int nsteps, int buf, const PreArgs *cons) {
 	npb_ctx *ctx = ch->ctx;
 	const int C = (int)ch->C, BSP = ch->g_bs + 32;
 	float *L = ch->g_L + (size_t)buf * C * BSP * 32;
-	if (g_use_fp32()) {
+	GemmArgs g;
+	memset(&g, 0, sizeof(g));
+	int do_density = 0;
+	if (d_order && g_use_fp32()) {
 		dim3 grid((nsteps + 127) / 128, C);
 		k_density_fp32<<<grid, 128, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ch->theta, L, BSP);
 		NPB_CUDA_OK(cudaGetLastError());
-		return NPB_OK;
+	} else if (d_order) {
+		const int ntiles = (nsteps + G_M - 1) / G_M;
+		k_pre_aimg<<<(ntiles * G_M * 8 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
+		NPB_CUDA_OK(cudaGetLastError());
+		k_pre_bimg<<<C * 32, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_born + (size_t)buf * C, ch->g_bimg, ch->g_bconst);
+		NPB_CUDA_OK(cudaGetLastError());
+		g.Aimg = ch->g_aimg;
+		g.Bimg = ch->g_bimg;
+		g.Bconst = ch->g_bconst;
+		g.L = L;
+		g.ntiles = ntiles;
+		g.BS = BSP;
+		do_density = 1;
 	}
-	const int ntiles = (nsteps + G_M - 1) / G_M;
-	k_pre_aimg<<<(ntiles * G_M * 8 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
-	NPB_CUDA_OK(cudaGetLastError());
-	k_pre_bimg<<<C * 32, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_born + (size_t)buf * C, ch->g_bimg, ch->g_bconst);
-	NPB_CUDA_OK(cudaGetLastError());
-	GemmArgs g;
-	g.Aimg = ch->g_aimg;
-	g.Bimg = ch->g_bimg;
-	g.Bconst = ch->g_bconst;
-	g.L = L;
 	g.C = C;
-	g.ntiles = ntiles;
-	g.BS = BSP;
+	if (!do_density && !cons) return NPB_OK;
 	static int n_sm = 0;
 	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
 	const int n_units = C * (32 / G_NS);
-	k_density_tc<<<n_units < n_sm ? n_units : n_sm, 192, G_SMEM, ctx->stream>>>(g);
+	const int grid = n_units < n_sm ? n_units : n_sm;
+	PreArgs p;
+	if (cons) p = *cons;
+	else memset(&p, 0, sizeof(p));
+	if (ch->m_aux == 3) k_density_tc<4, 3><<<grid, 4 * 32 + 128, G_SMEM, ctx->stream>>>(g, p, do_density, cons ? 1 : 0);
+	else k_density_tc<4, 1><<<grid, 4 * 32 + 128, G_SMEM, ctx->stream>>>(g, p, do_density, cons ? 1 : 0);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
@@ -816,45 +852,44 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
 	const size_t C = (size_t)ch->C;
 	// parameters may have changed since the last launch (init_from_params, update_params): every slot's image is rebuilt
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, C * 32, ctx->stream));
-	// Two streams: the density table of block k + 1 (context stream) is computed while block k is consumed (second
-	// stream).  Table k is written into buffer k & 1 once the consumer of block k - 2 has released it; a slot born during
-	// block k - 1 is missing from table k (its column is re-evaluated by the consumer of block k, born_prev) and enters the
-	// operand images with block k + 1 (k_pre_bimg reads the births of block k - 1 from g_born[(k + 1) & 1]).  The block
-	// counter runs on across launches, so that splitting a run into launches does not change which kernel evaluated which
-	// column (results are bit-identical however the sweeps are batched).
-	cudaStream_t sA = ctx->stream, sB = ch->g_stream2;
-	NPB_CUDA_OK(cudaEventRecord(ch->g_evD[0], sA));
-	NPB_CUDA_OK(cudaStreamWaitEvent(sB, ch->g_evD[0], 0));
+	// Software pipeline over the blocks of steps: launch k computes the table of block k into buffer k & 1 while its race
+	// warps consume block k - 1 from the other buffer.  A slot born during block k - 1 is therefore missing from table k: its
+	// column is re-evaluated by the race of block k (born_prev), and it enters the operand images with block k + 1
+	// (k_pre_bimg reads the births of block k - 1 from g_born[(k + 1) & 1]).  The block counter runs on across launches, so
+	// that batching the sweeps differently does not change which code evaluated which column: results are bit-identical
+	// however a run is split, with the overlap (NPB_D64_OVERLAP=0: table and race in separate launches) or without.
 	const int BS = ch->g_bs, N = a.N, BSP = BS + 32;
 	const bool overlap = [] { const char *e = getenv("NPB_D64_OVERLAP"); return !(e && e[0] == '0'); }();
-	PreArgs p;
+	PreArgs p, pending;
+	bool have_pending = false;
 	p.a = a;
 	p.BS = BSP;
 	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();
-	int k = 0;
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
-		for (int s0 = 0; s0 < N; s0 += BS, ++k, ++ch->g_k) {
+		for (int s0 = 0; s0 < N; s0 += BS, ++ch->g_k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;
 			const int buf = (int)(ch->g_k & 1u);
-			if (k >= 2 || (!overlap && k >= 1)) NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[overlap ? buf : (buf ^ 1)], 0));
-			s = g_density_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps, buf);
+			s = g_launch_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps, buf, have_pending ? &pending : nullptr);
 			if (s != NPB_OK) return s;
-			NPB_CUDA_OK(cudaEventRecord(ch->g_evD[buf], sA));
-			NPB_CUDA_OK(cudaStreamWaitEvent(sB, ch->g_evD[buf], 0));
 			p.L = ch->g_L + (size_t)buf * C * BSP * 32;
 			p.born_prev = ch->g_born + (size_t)(buf ^ 1) * C;
 			p.born_out = ch->g_born + (size_t)buf * C;
 			p.sw = sw;
 			p.s0 = s0;
 			p.nsteps = nsteps;
-			if (ch->m_aux == 3) k_alg8_sweep_pre<3><<<(unsigned)ch->C, 32, 0, sB>>>(p);
-			else k_alg8_sweep_pre<1><<<(unsigned)ch->C, 32, 0, sB>>>(p);
-			NPB_CUDA_OK(cudaGetLastError());
-			NPB_CUDA_OK(cudaEventRecord(ch->g_evC[buf], sB));
+			if (overlap) {
+				pending = p;
+				have_pending = true;
+			} else {
+				s = g_launch_block(ch, nullptr, 0, buf, &p);
+				if (s != NPB_OK) return s;
+			}
 		}
 	}
-	// join: the context stream continues after the last consumer
-	NPB_CUDA_OK(cudaStreamWaitEvent(sA, ch->g_evC[(ch->g_k - 1u) & 1u], 0));
+	if (have_pending) {
+		s = g_launch_block(ch, nullptr, 0, 0, &pending);
+		if (s != NPB_OK) return s;
+	}
 	return NPB_OK;
 }
 
@@ -870,7 +905,7 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 	npb_status s = g_ensure(ch);
 	if (s != NPB_OK) return s;
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
-	s = g_density_block(ch, d_items, 32, 0);
+	s = g_launch_block(ch, d_items, 32, 0, nullptr);
 	if (s != NPB_OK) return s;
 	k_gemm64_probe_out<<<32, 32, 0, ctx->stream>>>(ch->g_L, ch->counts, chain, ch->g_bs + 32, d_out);
 	NPB_CUDA_OK(cudaGetLastError());

@@ -353,11 +353,6 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->g_L) cudaFree(ch->g_L);
 	if (ch->g_dirty) cudaFree(ch->g_dirty);
 	if (ch->g_born) cudaFree(ch->g_born);
-	if (ch->g_stream2) cudaStreamDestroy(ch->g_stream2);
-	for (int i = 0; i < 2; ++i) {
-		if (ch->g_evD[i]) cudaEventDestroy(ch->g_evD[i]);
-		if (ch->g_evC[i]) cudaEventDestroy(ch->g_evC[i]);
-	}
 	delete ch;
 	return NPB_OK;
 }

@@ -84,8 +84,6 @@ struct npb_chains {
 	int g_bs = 0;                  // steps per block
 	uint32_t g_k = 0;              // blocks consumed so far (parity selects the table / born-mask buffer)
 	uint32_t *g_born = nullptr;    // [2][C] slots born during block k (buffer k & 1)
-	cudaStream_t g_stream2 = nullptr; // consumer stream (the density table of the next block overlaps it)
-	cudaEvent_t g_evD[2] = {nullptr, nullptr}, g_evC[2] = {nullptr, nullptr};
 };
 
 struct SweepArgs {

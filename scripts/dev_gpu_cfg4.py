@@ -9,6 +9,7 @@ chains = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 blocks = [int(b) for b in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4096]
 m_aux = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+nsweeps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 t0 = time.time()
 X, y = syn.gmm(N, 64, 32, syn.SEEDS[4])
 K = int(y.max()) + 1
@@ -22,7 +23,7 @@ for bs in blocks:
     os.environ["NPB_D64_BLOCK"] = str(bs)
     ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=20, m_aux=m_aux, seed=3)
     ch.init_from_params(means, Sigma)
-    for it in range(3):
+    for it in range(nsweeps):
         st = ch.sweep(npb.ALG2 if m_aux == 1 else npb.ALG8, 1)
         s = st.kernel_ms * 1e-3
         print("block %d sweep %d: %.1f ms, %.3e reassignments/s, candidates/step %.2f moved %.4f births %d meanK %.2f" % (
