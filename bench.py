@@ -337,8 +337,8 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
 
 def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=3):
     """BASELINE configs[3] shape: 256 chains, 64-D, N = 1M, 32 given clusters, Algorithm 2 (one auxiliary draw) through the
-    D = 64 path (npb_alg8_gemm.cu): tcgen05 kind::f16 density tables (three FP16 products per FP32 product) overlapped with
-    the warp-per-chain race."""
+    D = 64 path (npb_alg8_gemm.cu): tcgen05 kind::f16 density tables (three FP16 products per FP32 product) fused with the
+    warp-per-chain race of the previous block."""
     D, K = 64, 32
     X, y = syn.gmm(N, D, K, syn.SEEDS[4])
     ds = npb.Dataset(ctx, X)
@@ -372,8 +372,8 @@ def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=
            "roofline": {"bound": "tensor", "achieved": mma / sec / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
                         "frac": mma / sec / 1e12 / f16_peak, "kernel": "k_density_tc",
                         "note": "achieved = kind::f16 MMA flops issued per sweep (three FP16 products per FP32 product, 3 of the 4 "
-                                "32x32 blocks of the triangular 64x64 factor, every (step, slot)) / sweep time, the race kernel "
-                                "overlapped on a second stream; peak = measured bf16 burst (MEASURED_PEAKS.json)"}}
+                                "32x32 blocks of the triangular 64x64 factor, every (step, slot)) / sweep time, the race of the "
+                                "previous block running in two more warps of the same kernel; peak = measured bf16 burst (MEASURED_PEAKS.json)"}}
     ch.close()
     ds.close()
     return out

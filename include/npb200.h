@@ -177,7 +177,8 @@ npb_status npb_replay_split_merge(npb_ctx *ctx, npb_dataset *ds, int sampler, in
 		int32_t *z_final_out);
 
 /* parity probe (Kmax = 32, D = 4 / 8 / 16): the [32 slots x 32 items] log-density tile exactly as the sweep kernel's producer
- * warp computes it (packed FP32, the mean folded into a per-row offset), natural-log units, out[slot * 32 + j] for the 32
+ * warp computes it (packed FP32, the mean folded into a per-row offset; at D = 64 the tcgen05 density table of
+ * npb_alg8_gemm.cu exactly as the race reads it), natural-log units, out[slot * 32 + j] for the 32
  * given items; NaN for a slot without members.  For the 1e-5 relative bar on log-densities
  * (multivariatenormal.cpp:106-136). */
 npb_status npb_chains_probe_tile_logdensity(npb_chains *ch, int64_t chain, const int32_t *items32, float *out);
