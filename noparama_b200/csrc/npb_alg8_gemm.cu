@@ -362,14 +362,44 @@ __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
 // first move are final, and the sequential pass (lane = slot, the consumer of npb_alg8_tile4.cuh) takes over from that
 // step; both passes evaluate the same keys (same noise, same operation order), so the result does not depend on which
 // pass decided a step.  A chain that moves a lot (burn-in) skips the speculative pass.
+// D-generic front ends of the rare paths of the race: density of one (item, slot) from the slot table in global memory, and
+// theta' of a birth (D = 64: two coordinates per lane; D <= 32: aux_birth_z of npb_alg8_tile4.cuh, one coordinate per lane)
+template <int CD>
+__device__ __forceinline__ float g_stream_density(const float *th, const float *xrow) {
+	if constexpr (CD == 64) return g_log2density_stream64(th, xrow);
+	else return log2density_stream<CD>(th, xrow);
+}
+template <int CD>
+__device__ __forceinline__ void g_birth_theta(const Philox &ph, const PriorDev &pr, const float *xw, float rn, uint32_t step, uint32_t sweep,
+		int m, int lane, float *th) {
+	if constexpr (CD == 64) {
+		g_birth_theta64(ph, pr, xw, rn, step, sweep, m, lane, th);
+	} else {
+		constexpr int TRI = npb_tri(CD);
+		float av;
+		const float zc = aux_birth_z<CD>(ph, pr, xw, rn, step, sweep, m, lane, av);
+		const float g = zc * (av * pr.inv_sqrt_kappa);
+		float mu_r = lane < CD ? pr.mu0[lane] : 0.0f;
+		for (int c = 0; c < CD; ++c) {
+			const float gc = __shfl_sync(0xffffffffu, g, c);
+			if (lane <= c && lane < CD) mu_r = fmaf(pr.S[npb_tri_off(CD, lane, c)], gc, mu_r);
+		}
+		if (lane < CD) th[lane] = mu_r;
+		const float inv = 1.0f / av;
+		for (int q = lane; q < TRI; q += 32) th[CD + q] = pr.CT2[q] * inv;
+		if (lane == 0) th[CD + TRI] = pr.c0_2 - (float)CD * log2f(av);
+	}
+}
+
 // tile: [32 * 33] floats, [slot * 33 + step]; lg_s, lg1_s: [32] floats each, log2 n_k and log2 (n_k - 1) of every slot
 // (-inf without members) -- shared memory private to the calling warp
-template <int M>
+template <int CD, int M>
 __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chain, const int lane, float *tile, float *lg_s, float *lg1_s) {
+	constexpr int CPS = npb_ps(CD);
 	const SweepArgs &a = p.a;
 	const int N = a.N, C = a.C;
 	const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
-	float *thc = a.theta + (size_t)chain * 32 * GPS;
+	float *thc = a.theta + (size_t)chain * 32 * CPS;
 	float *Lc = p.L + (size_t)chain * p.BS * 32;
 	const uint32_t sweep = a.sweep0 + (uint32_t)p.sw;
 	const int32_t *order = a.scan_order + (size_t)p.sw * N;
@@ -392,7 +422,7 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 			const int k = __ffs(fix) - 1;
 			fix &= fix - 1;
 			for (int s = lane; s < p.nsteps; s += 32)
-				Lc[(size_t)s * 32 + k] = g_log2density_stream64(thc + (size_t)k * GPS, a.X + (size_t)order[p.s0 + s] * GD);
+				Lc[(size_t)s * 32 + k] = g_stream_density<CD>(thc + (size_t)k * CPS, a.X + (size_t)order[p.s0 + s] * CD);
 		}
 		__threadfence();
 		__syncwarp();
@@ -505,7 +535,7 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 							const int m = (zo_aux >> 16) & 0xff;
 							const uint32_t step = (uint32_t)(p.s0 + b0 + j);
 							const int bitem = order[step];
-							g_birth_theta64(ph, a.prior, a.Xw + (size_t)bitem * GD, __ldg(a.Xwn + bitem), step, sweep, m, lane, thc + (size_t)fs * GPS);
+							g_birth_theta<CD>(ph, a.prior, a.Xw + (size_t)bitem * CD, __ldg(a.Xwn + bitem), step, sweep, m, lane, thc + (size_t)fs * CPS);
 							__threadfence();
 							__syncwarp();
 							born_mask |= 1u << fs;
@@ -513,7 +543,7 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 							st_births++;
 							// the newborn slot's column of L for the rest of the block (lane = step)
 							for (int s = b0 + j + 1 + lane; s < p.nsteps; s += 32)
-								Lc[(size_t)s * 32 + fs] = g_log2density_stream64(thc + (size_t)fs * GPS, a.X + (size_t)order[p.s0 + s] * GD);
+								Lc[(size_t)s * 32 + fs] = g_stream_density<CD>(thc + (size_t)fs * CPS, a.X + (size_t)order[p.s0 + s] * CD);
 							__threadfence();
 							__syncwarp();
 							{
@@ -668,7 +698,7 @@ __global__ void __launch_bounds__(EW * 32 + 128, 1) k_density_tc(const GemmArgs 
 		if (do_consume) {
 			float *sm = cons_smem + (warp - (EW + 2)) * G_CONS_FLOATS;
 			for (int chain = blockIdx.x + (warp - (EW + 2)) * gridDim.x; chain < p.a.C; chain += 2 * gridDim.x)
-				g_consume_chain<M>(p, chain, lane, sm, sm + 32 * 33, sm + 32 * 33 + 32);
+				g_consume_chain<GD, M>(p, chain, lane, sm, sm + 32 * 33, sm + 32 * 33 + 32);
 		}
 	} else {
 		// ===================== epilogue: thread = (step of the tile, pair of slots) =====================
@@ -906,6 +936,357 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 	if (s != NPB_OK) return s;
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
 	s = g_launch_block(ch, d_items, 32, 0, nullptr);
+	if (s != NPB_OK) return s;
+	k_gemm64_probe_out<<<32, 32, 0, ctx->stream>>>(ch->g_L, ch->counts, chain, ch->g_bs + 32, d_out);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+// =========================================================================================================
+// D = 16 on the same tensor path (NPB_D16_PATH=tc; the default at D = 16 stays k_alg8_sweep_tile4 unless this measures
+// faster).  A 16-D density is one K = 16 MMA step; the three FP16 products hi*hi + hi*lo + lo*hi are laid out ALONG K so that
+// the 128-byte swizzled row of the D = 64 images carries them: A row = [x_hi | x_hi | x_lo | 0], B row = [T_hi | T_lo | T_hi | 0]
+// (16 FP16 each), three K-steps of one accumulation.  Unit of work = (chain, 16 slots): N = 256 = 16 slots x 16 rows, the unit's B
+// image is one contiguous 32 KB copy.  With thousands of chains the race needs no fusion: k_race16 (one warp per chain)
+// fills the GPU on its own, so a block is table kernel, then race kernel, on one stream (the schedule NPB_D64_OVERLAP=0
+// tests at D = 64).
+// =========================================================================================================
+namespace {
+constexpr int HD = 16;
+constexpr int HPS = npb_ps(HD);       // 153
+constexpr int HTRI = npb_tri(HD);     // 136
+constexpr int H_NS = 16;              // slots per unit
+constexpr int H_STAGES = 4;
+constexpr int H_ASTAGE = 16384;       // 128 rows x 128 bytes
+constexpr int H_SLOT_IMG = 2048;      // 16 rows x 128 bytes
+constexpr int H_BBYTES = H_NS * H_SLOT_IMG; // 32 KB
+constexpr int H_CONST = 20;           // nb[16], c2, descale, pad
+constexpr int H_SMEM = 1024 + H_BBYTES + H_STAGES * H_ASTAGE + 4096;
+}
+
+__global__ void __launch_bounds__(256) k_pre_aimg16(const double *X64, const double *xbar, const int32_t *order, int nsteps, int ntiles,
+		uint8_t *Aimg) {
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	const int s = idx >> 1, q = idx & 1; // step, half of the 16 coordinates
+	if (s >= ntiles * G_M) return;
+	const float sx = ldexpf(1.0f, (int)xbar[HD]);
+	__align__(16) __half hi[8], lo[8];
+	if (s < nsteps) {
+		const double *x = X64 + (size_t)order[s] * HD + q * 8;
+#pragma unroll
+		for (int e = 0; e < 8; ++e) g_split((float)(x[e] - xbar[q * 8 + e]) * sx, hi[e], lo[e]);
+	} else {
+#pragma unroll
+		for (int e = 0; e < 8; ++e) hi[e] = lo[e] = __float2half_rn(0.0f);
+	}
+	const int t = s / G_M, r = s % G_M;
+	uint8_t *row = Aimg + (size_t)t * H_ASTAGE;
+	*reinterpret_cast<uint4 *>(row + g_sw128(r, q * 8)) = *reinterpret_cast<const uint4 *>(hi);      // K  0-15: x_hi
+	*reinterpret_cast<uint4 *>(row + g_sw128(r, 16 + q * 8)) = *reinterpret_cast<const uint4 *>(hi); // K 16-31: x_hi
+	*reinterpret_cast<uint4 *>(row + g_sw128(r, 32 + q * 8)) = *reinterpret_cast<const uint4 *>(lo); // K 32-47: x_lo
+	*reinterpret_cast<uint4 *>(row + g_sw128(r, 48 + q * 8)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// CTA = 8 slots, warp = slot, lane = (row j, half of the columns)
+__global__ void __launch_bounds__(256) k_pre_bimg16(const float *theta, const double *xbar, uint8_t *dirty, const uint32_t *born, uint8_t *Bimg,
+		float *Bconst, int n_slots) {
+	__shared__ float ths[8][HPS + 3];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int cs = blockIdx.x * 8 + w; // chain * 32 + slot
+	if (cs >= n_slots) return;
+	if (!dirty[cs] && !((born[cs >> 5] >> (cs & 31)) & 1u)) return;
+	float *th = ths[w];
+	const float *src = theta + (size_t)cs * HPS;
+	float mx = 0.0f;
+	for (int i = lane; i < HPS; i += 32) {
+		const float v = src[i];
+		th[i] = v;
+		if (i >= HD && i < HD + HTRI) mx = fmaxf(mx, fabsf(v));
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	__syncwarp();
+	const int et = g_scale_exp(mx), ex = (int)xbar[HD];
+	const float st = ldexpf(1.0f, et);
+	if (lane < HD) {
+		float s = 0.0f;
+		for (int c = lane; c < HD; ++c) s = fmaf(th[HD + npb_tri_off(HD, lane, c)], (float)((double)th[c] - xbar[c]), s);
+		Bconst[(size_t)cs * H_CONST + lane] = -s;
+	}
+	if (lane == HD) Bconst[(size_t)cs * H_CONST + HD] = th[HD + HTRI];
+	if (lane == HD + 1) Bconst[(size_t)cs * H_CONST + HD + 1] = ldexpf(1.0f, -(ex + et));
+	const int j = lane >> 1, q = lane & 1;
+	__align__(16) __half hi[8], lo[8];
+#pragma unroll
+	for (int e = 0; e < 8; ++e) {
+		const int c = q * 8 + e;
+		g_split(c >= j ? th[HD + npb_tri_off(HD, j, c)] * st : 0.0f, hi[e], lo[e]);
+	}
+	uint8_t *img = Bimg + (size_t)cs * H_SLOT_IMG;
+	*reinterpret_cast<uint4 *>(img + g_sw128(j, q * 8)) = *reinterpret_cast<const uint4 *>(hi);      // K  0-15: T_hi
+	*reinterpret_cast<uint4 *>(img + g_sw128(j, 16 + q * 8)) = *reinterpret_cast<const uint4 *>(lo); // K 16-31: T_lo
+	*reinterpret_cast<uint4 *>(img + g_sw128(j, 32 + q * 8)) = *reinterpret_cast<const uint4 *>(hi); // K 32-47: T_hi
+	*reinterpret_cast<uint4 *>(img + g_sw128(j, 48 + q * 8)) = make_uint4(0u, 0u, 0u, 0u);
+	__syncwarp();
+	if (lane == 0) dirty[cs] = 0;
+}
+
+// warps 0 .. EW-1 epilogue, warp EW MMA issue + TMEM allocation, warp EW + 1 bulk-copy producer
+template <int EW>
+__global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs g) {
+	constexpr int PPW = 32 / EW; // pairs of slots per epilogue warp: 8 (EW = 4) or 4 (EW = 8)
+	extern __shared__ uint8_t g_smem_raw[];
+	const uint32_t raw = g_smem_u32(g_smem_raw);
+	const uint32_t base = (raw + 1023u) & ~1023u;
+	uint8_t *gen = g_smem_raw + (base - raw);
+	constexpr uint32_t A0 = H_BBYTES, MISC = H_BBYTES + H_STAGES * H_ASTAGE;
+	const uint32_t misc = base + MISC;
+	const uint32_t bar_b_full = misc, bar_b_empty = misc + 8;
+	const uint32_t bar_a_full = misc + 16, bar_a_empty = misc + 16 + 8 * H_STAGES;
+	const uint32_t bar_t_full = misc + 16 + 16 * H_STAGES, bar_t_empty = bar_t_full + 16;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + MISC + 256);
+	float *econst = reinterpret_cast<float *>(gen + MISC + 512); // [16][H_CONST]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n_units = g.C * (32 / H_NS);
+
+	if (warp == EW + 1 && lane == 0) {
+		g_mbar_init(bar_b_full, 1);
+		g_mbar_init(bar_b_empty, 1);
+		for (int s = 0; s < H_STAGES; ++s) {
+			g_mbar_init(bar_a_full + 8 * s, 1);
+			g_mbar_init(bar_a_empty + 8 * s, 1);
+		}
+		for (int b = 0; b < 2; ++b) {
+			g_mbar_init(bar_t_full + 8 * b, 1);
+			g_mbar_init(bar_t_empty + 8 * b, EW * 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async;" ::: "memory");
+	}
+	if (warp == EW) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	g_tc_fence_after();
+	const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+	if (warp == EW + 1) {
+		if (lane == 0) {
+			uint32_t a_it = 0, unit_it = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				g_mbar_wait(bar_b_empty, (unit_it & 1u) ^ 1u);
+				g_mbar_expect_tx(bar_b_full, H_BBYTES);
+				g_bulk_g2s(base, g.Bimg + (size_t)u * H_BBYTES, H_BBYTES, bar_b_full); // slots 16 (u & 1) .. + 15 of chain u >> 1
+				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
+					const uint32_t s = a_it % H_STAGES, ph = (a_it / H_STAGES) & 1u;
+					g_mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
+					g_mbar_expect_tx(bar_a_full + 8 * s, H_ASTAGE);
+					g_bulk_g2s(base + A0 + s * H_ASTAGE, g.Aimg + (size_t)t * H_ASTAGE, H_ASTAGE, bar_a_full + 8 * s);
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == EW) {
+		if (lane == 0) {
+			constexpr uint32_t ID256 = g_idesc(G_M, 256);
+			uint32_t a_it = 0, tile_it = 0, unit_it = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				g_mbar_wait(bar_b_full, unit_it & 1u);
+				g_tc_fence_after();
+				for (int t = 0; t < g.ntiles; ++t, ++tile_it, ++a_it) {
+					const uint32_t buf = tile_it & 1u;
+					g_mbar_wait(bar_t_empty + 8 * buf, ((tile_it >> 1) & 1u) ^ 1u);
+					const uint32_t s = a_it % H_STAGES;
+					g_mbar_wait(bar_a_full + 8 * s, (a_it / H_STAGES) & 1u);
+					g_tc_fence_after();
+					const uint32_t dcol = tmem + buf * 256u, A = base + A0 + s * H_ASTAGE;
+#pragma unroll
+					for (int k = 0; k < 3; ++k) // hi*hi, hi*lo, lo*hi: three K-steps of the same rows
+						g_mma_f16(dcol, g_desc(A + k * 32), g_desc(base + k * 32), ID256, k != 0);
+					g_tc_commit(bar_a_empty + 8 * s);
+					g_tc_commit(bar_t_full + 8 * buf);
+				}
+				g_tc_commit(bar_b_empty);
+			}
+		}
+		__syncwarp();
+	} else {
+		// epilogue: thread = step of the tile; a warp takes PPW pairs of slots
+		const int wq = warp & 3, eg = warp >> 2;
+		const int row = wq * 32 + lane;
+		uint32_t tile_it = 0;
+		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+			{
+				const float *src = g.Bconst + (size_t)u * H_NS * H_CONST;
+				for (int i = threadIdx.x; i < H_NS * H_CONST; i += EW * 32) econst[i] = __ldg(src + i);
+			}
+			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+			float *Lc = g.L + ((size_t)(u >> 1) * g.BS) * 32 + (u & 1) * H_NS + eg * PPW * 2;
+			for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+				const uint32_t buf = tile_it & 1u;
+				g_mbar_wait(bar_t_full + 8 * buf, (tile_it >> 1) & 1u);
+				g_tc_fence_after();
+				const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u + eg * PPW * 32;
+				float out[PPW * 2];
+#pragma unroll
+				for (int pp = 0; pp < PPW; pp += 2) {
+					float v0[32], v1[32];
+					g_tmem_ld32_nowait(taddr + pp * 32u, v0);
+					g_tmem_ld32_nowait(taddr + (pp + 1) * 32u, v1);
+					g_tmem_wait_ld(v0, v1);
+#pragma unroll
+					for (int h = 0; h < 4; ++h) { // slots 2 pp .. 2 pp + 3 of this warp's range
+						const float(&v)[32] = h < 2 ? v0 : v1;
+						const int o = (h & 1) * 16;
+						const float *ec = econst + (eg * PPW * 2 + pp * 2 + h) * H_CONST;
+						const float dsc = ec[HD + 1];
+						float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+						for (int i = 0; i < 16; i += 4) {
+							const float4 nb = *reinterpret_cast<const float4 *>(ec + i);
+							const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
+									    a3 = fmaf(v[o + i + 3], dsc, nb.w);
+							q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+						}
+						out[pp * 2 + h] = ec[HD] - ((q0 + q1) + (q2 + q3));
+					}
+				}
+				g_tc_fence_before();
+				g_mbar_arrive(bar_t_empty + 8 * buf);
+				float4 *dst = reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32);
+#pragma unroll
+				for (int i = 0; i < PPW * 2; i += 4) dst[i / 4] = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
+			}
+		}
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	if (warp == EW) {
+		g_tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+	}
+}
+
+// the race as a kernel of its own: four chains per CTA
+template <int CD, int M>
+__global__ void __launch_bounds__(128, 4) k_race(const PreArgs p) {
+	__shared__ float sm[4][G_CONS_FLOATS];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int chain = blockIdx.x * 4 + w;
+	if (chain >= p.a.C) return;
+	g_consume_chain<CD, M>(p, chain, lane, sm[w], sm[w] + 32 * 33, sm[w] + 32 * 33 + 32);
+}
+
+extern template npb_status npb_launch_aux_keys<16>(npb_chains *, const SweepArgs &);
+
+static int h_block_steps() {
+	const char *e = getenv("NPB_D16_BLOCK");
+	int v = e ? atoi(e) : 1024;
+	if (v < 128) v = 128;
+	if (v > (1 << 16)) v = 1 << 16;
+	return (v + 127) & ~127;
+}
+
+static npb_status h_ensure(npb_chains *ch) {
+	npb_ctx *ctx = ch->ctx;
+	npb_dataset *ds = ch->ds;
+	if (!ds->Xbar) {
+		NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * (2 * HD + 1)));
+		k_colmean<<<HD, 256, 0, ctx->stream>>>(ds->X64, ds->N, HD, ds->Xbar);
+		NPB_CUDA_OK(cudaGetLastError());
+		k_xscale<<<1, 1, 0, ctx->stream>>>(ds->Xbar, HD);
+		NPB_CUDA_OK(cudaGetLastError());
+	}
+	if (!ch->g_L) {
+		const int BS = h_block_steps();
+		const size_t C = (size_t)ch->C;
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * H_ASTAGE));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bimg, C * 32 * H_SLOT_IMG));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bconst, C * 32 * H_CONST * sizeof(float)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_L, C * (size_t)(BS + 32) * 32 * sizeof(float)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_dirty, C * 32));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_born, 2 * C * sizeof(uint32_t)));
+		NPB_CUDA_OK(cudaMemsetAsync(ch->g_L, 0, C * (size_t)(BS + 32) * 32 * sizeof(float), ctx->stream));
+		NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * C * sizeof(uint32_t), ctx->stream));
+		ch->g_bs = BS;
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+	}
+	return NPB_OK;
+}
+
+static npb_status h_density_block(npb_chains *ch, const int32_t *d_order, int nsteps, int born_buf) {
+	npb_ctx *ctx = ch->ctx;
+	const int C = (int)ch->C;
+	const int ntiles = (nsteps + G_M - 1) / G_M;
+	k_pre_aimg16<<<(ntiles * G_M * 2 + 255) / 256, 256, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ntiles, ch->g_aimg);
+	NPB_CUDA_OK(cudaGetLastError());
+	k_pre_bimg16<<<(C * 32 + 7) / 8, 256, 0, ctx->stream>>>(ch->theta, ch->ds->Xbar, ch->g_dirty, ch->g_born + (size_t)born_buf * C, ch->g_bimg,
+			ch->g_bconst, C * 32);
+	NPB_CUDA_OK(cudaGetLastError());
+	GemmArgs g;
+	g.Aimg = ch->g_aimg;
+	g.Bimg = ch->g_bimg;
+	g.Bconst = ch->g_bconst;
+	g.L = ch->g_L;
+	g.C = C;
+	g.ntiles = ntiles;
+	g.BS = ch->g_bs + 32;
+	static int n_sm = 0;
+	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+	const int n_units = C * (32 / H_NS);
+	const int grid = n_units < n_sm ? n_units : n_sm;
+	const char *ew = getenv("NPB_D16_EPI");
+	if (ew && ew[0] == '4') k_density_tc16<4><<<grid, 4 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	else k_density_tc16<8><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
+	npb_ctx *ctx = ch->ctx;
+	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D = 16 tensor-core sweep");
+	npb_status s = h_ensure(ch);
+	if (s != NPB_OK) return s;
+	s = npb_launch_aux_keys<16>(ch, a);
+	if (s != NPB_OK) return s;
+	const size_t C = (size_t)ch->C;
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, C * 32, ctx->stream));
+	const int BS = ch->g_bs, N = a.N;
+	PreArgs p;
+	p.a = a;
+	p.BS = BS + 32;
+	p.L = ch->g_L;
+	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();
+	for (int sw = 0; sw < a.n_sweeps; ++sw) {
+		for (int s0 = 0; s0 < N; s0 += BS, ++ch->g_k) {
+			const int nsteps = N - s0 < BS ? N - s0 : BS;
+			const int buf = (int)(ch->g_k & 1u);
+			s = h_density_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps, buf);
+			if (s != NPB_OK) return s;
+			p.born_prev = ch->g_born + (size_t)(buf ^ 1) * C;
+			p.born_out = ch->g_born + (size_t)buf * C;
+			p.sw = sw;
+			p.s0 = s0;
+			p.nsteps = nsteps;
+			const unsigned blocks = (unsigned)((ch->C + 3) / 4);
+			if (ch->m_aux == 3) k_race<HD, 3><<<blocks, 128, 0, ctx->stream>>>(p);
+			else k_race<HD, 1><<<blocks, 128, 0, ctx->stream>>>(p);
+			NPB_CUDA_OK(cudaGetLastError());
+		}
+	}
+	return NPB_OK;
+}
+
+npb_status npb_launch_tc16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out) {
+	npb_ctx *ctx = ch->ctx;
+	npb_status s = h_ensure(ch);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, (size_t)ch->C * 32, ctx->stream));
+	s = h_density_block(ch, d_items, 32, 0);
 	if (s != NPB_OK) return s;
 	k_gemm64_probe_out<<<32, 32, 0, ctx->stream>>>(ch->g_L, ch->counts, chain, ch->g_bs + 32, d_out);
 	NPB_CUDA_OK(cudaGetLastError());

@@ -141,6 +141,8 @@ npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_ite
 struct SweepArgs;
 npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a);
 npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
+npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a);
+npb_status npb_launch_tc16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item);
 npb_status npb_launch_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);
 npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, int whole_sweeps, float *d_detail);

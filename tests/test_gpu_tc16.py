@@ -1,0 +1,99 @@
+"""GPU (pytest -m gpu): D = 16 on the tensor path of npb_alg8_gemm.cu (NPB_D16_PATH=tc): FP16x3 density tables + race kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from noparama_b200 import synthetic as syn
+from test_gpu_tile import invariants
+
+pytestmark = pytest.mark.gpu
+D = 16
+
+
+@pytest.fixture
+def env():
+    keys = ("NPB_D16_PATH", "NPB_D16_BLOCK", "NPB_D16_EPI", "NPB_D64_SPEC")
+    saved = {k: os.environ.get(k) for k in keys}
+    os.environ["NPB_D16_PATH"] = "tc"
+    yield os.environ
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("epi", ["4", "8"])
+def test_tc16_density_table_within_1e5_of_oracle(npb, ctx, oracle, env, epi):
+    env["NPB_D16_EPI"] = epi
+    rng = np.random.default_rng(16)
+    K = 32
+    X, y = syn.gmm(4000, D, 8, 216)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(D)).bind(ctx)
+    ch = npb.Chains(ctx, ds, 3, Kmax=32, K0=8, seed=1)
+    mu = X[rng.integers(0, len(X), K)] + 0.5 * rng.standard_normal((K, D))
+    B = rng.standard_normal((K, D, D)) / np.sqrt(D)
+    Sigma = B @ np.transpose(B, (0, 2, 1)) + 0.3 * np.eye(D)
+    ch.init_from_params(mu, Sigma)
+    for chain in (0, 2):
+        items = rng.integers(0, len(X), 32)
+        got = ch.probe_tile_logdensity(chain, items).astype(np.float64)
+        slots, counts, _, _ = ch.params(chain)
+        want = oracle.mvn_logpdf_batch(mu, Sigma, X[items]).T
+        occ = np.zeros(32, bool)
+        occ[slots] = True
+        assert occ.sum() >= 30 and np.all(np.isnan(got[~occ]))
+        err = np.abs(got[occ] - want[occ]) / np.maximum(1.0, np.abs(want[occ]))
+        print("epilogue warps", epi, "max relative error of the table", err.max())
+        assert err.max() < 1e-5, err.max()
+    ch.close()
+    ds.close()
+
+
+@pytest.mark.parametrize("block", [128, 1024])
+def test_tc16_invariants(npb, ctx, oracle, env, block):
+    env["NPB_D16_BLOCK"] = str(block)
+    N = 1000 + 13
+    X, y = syn.gmm(N, D, 4, 116)
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=24, Kmax=32, K0=8, seed=D)
+    births = 0
+    for _ in range(3):
+        st = mc.chains.sweep(npb.ALG8, 3)
+        births += st.new_clusters
+        assert st.overflow_chains == 0 and st.reassignments == 24 * N * 3
+        assert 4 * st.reassignments <= st.candidates <= 35 * st.reassignments
+    z = mc.getMembershipMatrix()
+    m = mc.chains.metrics(y)
+    for c in range(0, 24, 5):
+        k = invariants(mc.chains, z[c], c, N)
+        assert k == m["K"][c]
+        want = oracle.metrics(y, z[c])
+        assert np.allclose([m["purity"][c], m["rand_index"][c], m["adjusted_rand"][c]], want, atol=1e-12)
+    print("births", births, "mean K", st.mean_K)
+    zs = []
+    for spec, per_launch in (("1", None), ("0", None), ("1", 1)):
+        env["NPB_D64_SPEC"] = spec
+        a = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=32, K0=8, seed=77)
+        a.run(4, sweeps_per_launch=per_launch)
+        zs.append(a.getMembershipMatrix().copy())
+    assert np.array_equal(zs[0], zs[1]) and np.array_equal(zs[0], zs[2])
+    ds.close()
+
+
+def test_tc16_recovers_given_clusters(npb, ctx, env):
+    X, y = syn.gmm(4000, D, 8, 5)
+    means = np.stack([X[y == k].mean(0) for k in range(8)])
+    Sigma = np.tile(np.eye(D), (8, 1, 1))
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=32, Kmax=32, seed=3)
+    mc.chains.init_from_params(means, Sigma)
+    s1 = mc.chains.sweep(npb.ALG8, 1)
+    s2 = mc.chains.sweep(npb.ALG8, 1)
+    assert s1.overflow_chains == 0 and s1.candidates == 11 * s1.reassignments == s2.candidates
+    assert s1.moved > 0.8 * s1.reassignments and s2.moved < 1e-3 * s2.reassignments
+    m = mc.chains.metrics(y)
+    assert np.all(m["K"] == 8) and m["purity"].min() > 0.999
+    ds.close()
