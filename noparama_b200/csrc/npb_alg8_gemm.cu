@@ -344,6 +344,7 @@ __device__ __noinline__ void g_birth_theta64(const Philox &ph, const PriorDev &p
 	if (lane == 0) th[GD + GTRI] = pr.c0_2 - (float)GD * log2f(av);
 }
 
+#define G_NOISE_CAP 20.0f
 // race noise of (tile, step j, slot k): a counter hash instead of a per-lane stream, so that the step-parallel pass
 // (lane = step) and the sequential pass (lane = slot) of k_alg8_sweep_pre draw the same number for the same candidate
 __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
@@ -352,7 +353,10 @@ __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
 	x *= 0x85EBCA6Bu;
 	x ^= x >> 13;
 	x *= 0xC2B2AE35u;
-	return neg_lg2_exp1_open(x);
+	// capped: -log2 E > 20 has probability 1.4e-6 per candidate and would shift a pick probability by less than that -- below
+	// what FP32 log-densities resolve (1e-6 relative of ~1e2) -- and the cap is what lets the speculative pass exclude slots
+	// without drawing their noise
+	return fminf(neg_lg2_exp1_open(x), G_NOISE_CAP);
 }
 
 // One warp per chain.  A tile of 32 steps is first decided SPECULATIVELY with lane = step: every lane walks the 32 slots
@@ -464,16 +468,33 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 		int j0 = 0;
 		if (p.spec && recent_moves < 3) {
 			// ---- speculative pass: lane = step ----
-			float best = -INFINITY;
-			int bk = 0;
+			// The item stays iff its own slot's key is the largest.  The race noise is capped at G_NOISE_CAP (g_noise), so a
+			// slot whose noiseless key lies more than the cap (+1 for rounding) below the own key cannot win: in a converged chain
+			// that is every other slot, and the pass costs two shared loads, two adds and a compare per (step, slot) -- no
+			// logarithm.  Slots some lane cannot exclude are evaluated exactly (warp-uniform loop over the union).
+			const float lg_own = lg1_s[zold];
+			const float own = lg_own > -INFINITY ? (tile[zold * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)zold)) + lg_own : -INFINITY;
+			bool stays = own > -INFINITY && own >= auxkey_j;
+			unsigned need = 0u;
 #pragma unroll 8
 			for (int k = 0; k < 32; ++k) {
-				const float base = tile[k * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)k);
-				const float lg = (zold == k) ? lg1_s[k] : lg_s[k];
-				const float key = lg > -INFINITY ? base + lg : -INFINITY;
-				if (key > best) { best = key; bk = k; }
+				const float ub = (tile[k * 33 + lane] + lg_s[k]) + (G_NOISE_CAP + 1.0f);
+				need |= (ub >= own) ? (1u << k) : 0u;
 			}
-			const bool stays = best > -INFINITY && best >= auxkey_j && bk == zold;
+			need &= ~(1u << zold);
+			unsigned un = __reduce_or_sync(0xffffffffu, (valid && stays) ? need : 0u);
+			if (un) {
+				float best = own;
+				int bk = zold;
+				while (un) {
+					const int k = __ffs(un) - 1;
+					un &= un - 1;
+					const float lg = lg_s[k];
+					const float key = lg > -INFINITY ? (tile[k * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)k)) + lg : -INFINITY;
+					if (k != zold && (key > best || (key == best && k < bk))) { best = key; bk = k; }
+				}
+				stays = stays && bk == zold;
+			}
 			const unsigned mv = __ballot_sync(0xffffffffu, valid && !stays);
 			j0 = mv ? __ffs(mv) - 1 : cnt;
 			cand_tile += (unsigned)(j0 * (kocc + M));
@@ -729,6 +750,10 @@ __global__ void __launch_bounds__(EW * 32 + 128, 1) k_density_tc(const GemmArgs 
 					g_tmem_ld32_nowait(taddr + sl * 32u, v0);
 					g_tmem_ld32_nowait(taddr + 128u + sl * 32u, v1);
 					g_tmem_wait_ld(v0, v1);
+					if (h == SPW - 1) { // the last of the accumulator is in registers: hand the buffer back before the arithmetic
+						g_tc_fence_before();
+						g_mbar_arrive(bar_t_empty + 8 * buf);
+					}
 					float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
 #pragma unroll
 					for (int i = 0; i < 32; i += 4) {
@@ -743,8 +768,6 @@ __global__ void __launch_bounds__(EW * 32 + 128, 1) k_density_tc(const GemmArgs 
 					}
 					out[h] = ec[GD] - ((q0 + q1) + (q2 + q3));
 				}
-				g_tc_fence_before();
-				g_mbar_arrive(bar_t_empty + 8 * buf);
 				if constexpr (SPW == 4) *reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32) = make_float4(out[0], out[1], out[2], out[3]);
 				else *reinterpret_cast<float2 *>(Lc + (size_t)(t * G_M + row) * 32) = make_float2(out[0], out[1]);
 			}
@@ -946,7 +969,8 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 // D = 16 on the same tensor path (NPB_D16_PATH=tc; the default at D = 16 stays k_alg8_sweep_tile4 unless this measures
 // faster).  A 16-D density is one K = 16 MMA step; the three FP16 products hi*hi + hi*lo + lo*hi are laid out ALONG K so that
 // the 128-byte swizzled row of the D = 64 images carries them: A row = [x_hi | x_hi | x_lo | 0], B row = [T_hi | T_lo | T_hi | 0]
-// (16 FP16 each), three K-steps of one accumulation.  Unit of work = (chain, 16 slots): N = 256 = 16 slots x 16 rows, the unit's B
+// (16 FP16 each) -- the fourth quarter carries the per-row offset nb = -T2 (mu - xbar) against a constant column of A, so the
+// accumulator is y itself and the epilogue a plain sum of squares: four K-steps of one accumulation.  Unit of work = (chain, 16 slots): N = 256 = 16 slots x 16 rows, the unit's B
 // image is one contiguous 32 KB copy.  With thousands of chains the race needs no fusion: k_race16 (one warp per chain)
 // fills the GPU on its own, so a block is table kernel, then race kernel, on one stream (the schedule NPB_D64_OVERLAP=0
 // tests at D = 64).
@@ -960,7 +984,7 @@ constexpr int H_STAGES = 4;
 constexpr int H_ASTAGE = 16384;       // 128 rows x 128 bytes
 constexpr int H_SLOT_IMG = 2048;      // 16 rows x 128 bytes
 constexpr int H_BBYTES = H_NS * H_SLOT_IMG; // 32 KB
-constexpr int H_CONST = 20;           // nb[16], c2, descale, pad
+constexpr int H_CONST = 20;           // nb[16] (zero if folded into the GEMM), c2, descale, folded flag, descale^2
 constexpr int H_SMEM = 1024 + H_BBYTES + H_STAGES * H_ASTAGE + 4096;
 }
 
@@ -984,7 +1008,11 @@ __global__ void __launch_bounds__(256) k_pre_aimg16(const double *X64, const dou
 	*reinterpret_cast<uint4 *>(row + g_sw128(r, q * 8)) = *reinterpret_cast<const uint4 *>(hi);      // K  0-15: x_hi
 	*reinterpret_cast<uint4 *>(row + g_sw128(r, 16 + q * 8)) = *reinterpret_cast<const uint4 *>(hi); // K 16-31: x_hi
 	*reinterpret_cast<uint4 *>(row + g_sw128(r, 32 + q * 8)) = *reinterpret_cast<const uint4 *>(lo); // K 32-47: x_lo
-	*reinterpret_cast<uint4 *>(row + g_sw128(r, 48 + q * 8)) = make_uint4(0u, 0u, 0u, 0u);
+	// K 48-59: the constant 2^15 that multiplies the folded offset columns of B (k_pre_bimg16), K 60-63: zero
+	__align__(16) __half one[8];
+#pragma unroll
+	for (int e = 0; e < 8; ++e) one[e] = __float2half_rn((q == 0 || e < 4) ? 32768.0f : 0.0f);
+	*reinterpret_cast<uint4 *>(row + g_sw128(r, 48 + q * 8)) = *reinterpret_cast<const uint4 *>(one);
 }
 
 // CTA = 8 slots, warp = slot, lane = (row j, half of the columns)
@@ -1008,13 +1036,27 @@ __global__ void __launch_bounds__(256) k_pre_bimg16(const float *theta, const do
 	__syncwarp();
 	const int et = g_scale_exp(mx), ex = (int)xbar[HD];
 	const float st = ldexpf(1.0f, et);
+	// nb_j = -(T2 (mu - xbar))_j enters the GEMM as well: in accumulator units it is nbs_j = nb_j 2^(ex + et), written as
+	// 2^15 * 4 * (h1 + h2 + h3) with three FP16 terms of nbs_j / 2^17, each repeated over four K columns against the constant
+	// 2^15 of the A image -- if it fits (|nbs| < 2^31); a slot whose mean lies far outside the data keeps nb for the epilogue
+	// (flag in Bconst[18]; the epilogue takes its short form only for units whose 16 slots are all folded).
+	float nbj = 0.0f;
 	if (lane < HD) {
 		float s = 0.0f;
 		for (int c = lane; c < HD; ++c) s = fmaf(th[HD + npb_tri_off(HD, lane, c)], (float)((double)th[c] - xbar[c]), s);
-		Bconst[(size_t)cs * H_CONST + lane] = -s;
+		nbj = -s;
 	}
+	const float up = ldexpf(1.0f, ex + et - 17);
+	float nmax = fabsf(nbj) * up;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) nmax = fmaxf(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+	const bool fold = nmax < 16384.0f; // |nbs / 2^17| < 2^14
+	if (lane < HD) Bconst[(size_t)cs * H_CONST + lane] = fold ? 0.0f : nbj;
+	const float dsc = ldexpf(1.0f, -(ex + et));
 	if (lane == HD) Bconst[(size_t)cs * H_CONST + HD] = th[HD + HTRI];
-	if (lane == HD + 1) Bconst[(size_t)cs * H_CONST + HD + 1] = ldexpf(1.0f, -(ex + et));
+	if (lane == HD + 1) Bconst[(size_t)cs * H_CONST + HD + 1] = dsc;
+	if (lane == HD + 2) Bconst[(size_t)cs * H_CONST + HD + 2] = fold ? 1.0f : 0.0f;
+	if (lane == HD + 3) Bconst[(size_t)cs * H_CONST + HD + 3] = dsc * dsc;
 	const int j = lane >> 1, q = lane & 1;
 	__align__(16) __half hi[8], lo[8];
 #pragma unroll
@@ -1026,7 +1068,18 @@ __global__ void __launch_bounds__(256) k_pre_bimg16(const float *theta, const do
 	*reinterpret_cast<uint4 *>(img + g_sw128(j, q * 8)) = *reinterpret_cast<const uint4 *>(hi);      // K  0-15: T_hi
 	*reinterpret_cast<uint4 *>(img + g_sw128(j, 16 + q * 8)) = *reinterpret_cast<const uint4 *>(lo); // K 16-31: T_lo
 	*reinterpret_cast<uint4 *>(img + g_sw128(j, 32 + q * 8)) = *reinterpret_cast<const uint4 *>(hi); // K 32-47: T_hi
-	*reinterpret_cast<uint4 *>(img + g_sw128(j, 48 + q * 8)) = make_uint4(0u, 0u, 0u, 0u);
+	{
+		const float w = fold ? __shfl_sync(0xffffffffu, nbj, j) * up : 0.0f; // nbs_j / 2^17
+		const __half h1 = __float2half_rn(w);
+		const float r1 = w - __half2float(h1);
+		const __half h2 = __float2half_rn(r1);
+		const __half h3 = __float2half_rn(r1 - __half2float(h2));
+		const __half z = __float2half_rn(0.0f);
+		__align__(16) __half off[8];
+#pragma unroll
+		for (int e = 0; e < 8; ++e) off[e] = q == 0 ? (e < 4 ? h1 : h2) : (e < 4 ? h3 : z); // K 48-51 h1, 52-55 h2, 56-59 h3, 60-63 0
+		*reinterpret_cast<uint4 *>(img + g_sw128(j, 48 + q * 8)) = *reinterpret_cast<const uint4 *>(off);
+	}
 	__syncwarp();
 	if (lane == 0) dirty[cs] = 0;
 }
@@ -1103,7 +1156,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 					g_tc_fence_after();
 					const uint32_t dcol = tmem + buf * 256u, A = base + A0 + s * H_ASTAGE;
 #pragma unroll
-					for (int k = 0; k < 3; ++k) // hi*hi, hi*lo, lo*hi: three K-steps of the same rows
+					for (int k = 0; k < 4; ++k) // hi*hi, hi*lo, lo*hi, the folded offsets: four K-steps of the same rows
 						g_mma_f16(dcol, g_desc(A + k * 32), g_desc(base + k * 32), ID256, k != 0);
 					g_tc_commit(bar_a_empty + 8 * s);
 					g_tc_commit(bar_t_full + 8 * buf);
@@ -1124,6 +1177,9 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 				for (int i = threadIdx.x; i < H_NS * H_CONST; i += EW * 32) econst[i] = __ldg(src + i);
 			}
 			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+			bool folded = true; // every slot of the unit has its offsets inside the GEMM: short epilogue
+#pragma unroll
+			for (int sl = 0; sl < H_NS; ++sl) folded = folded && econst[sl * H_CONST + HD + 2] != 0.0f;
 			float *Lc = g.L + ((size_t)(u >> 1) * g.BS) * 32 + (u & 1) * H_NS + eg * PPW * 2;
 			for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
 				const uint32_t buf = tile_it & 1u;
@@ -1137,25 +1193,36 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 					g_tmem_ld32_nowait(taddr + pp * 32u, v0);
 					g_tmem_ld32_nowait(taddr + (pp + 1) * 32u, v1);
 					g_tmem_wait_ld(v0, v1);
+					if (pp + 2 >= PPW) { // the accumulator is in registers: hand the buffer back before the arithmetic
+						g_tc_fence_before();
+						g_mbar_arrive(bar_t_empty + 8 * buf);
+					}
 #pragma unroll
 					for (int h = 0; h < 4; ++h) { // slots 2 pp .. 2 pp + 3 of this warp's range
 						const float(&v)[32] = h < 2 ? v0 : v1;
 						const int o = (h & 1) * 16;
 						const float *ec = econst + (eg * PPW * 2 + pp * 2 + h) * H_CONST;
-						const float dsc = ec[HD + 1];
 						float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+						if (folded) {
 #pragma unroll
-						for (int i = 0; i < 16; i += 4) {
-							const float4 nb = *reinterpret_cast<const float4 *>(ec + i);
-							const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
-									    a3 = fmaf(v[o + i + 3], dsc, nb.w);
-							q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+							for (int i = 0; i < 16; i += 4) {
+								q0 = fmaf(v[o + i], v[o + i], q0); q1 = fmaf(v[o + i + 1], v[o + i + 1], q1);
+								q2 = fmaf(v[o + i + 2], v[o + i + 2], q2); q3 = fmaf(v[o + i + 3], v[o + i + 3], q3);
+							}
+							out[pp * 2 + h] = fmaf(-ec[HD + 3], (q0 + q1) + (q2 + q3), ec[HD]);
+						} else {
+							const float dsc = ec[HD + 1];
+#pragma unroll
+							for (int i = 0; i < 16; i += 4) {
+								const float4 nb = *reinterpret_cast<const float4 *>(ec + i);
+								const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
+										    a3 = fmaf(v[o + i + 3], dsc, nb.w);
+								q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+							}
+							out[pp * 2 + h] = ec[HD] - ((q0 + q1) + (q2 + q3));
 						}
-						out[pp * 2 + h] = ec[HD] - ((q0 + q1) + (q2 + q3));
 					}
 				}
-				g_tc_fence_before();
-				g_mbar_arrive(bar_t_empty + 8 * buf);
 				float4 *dst = reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32);
 #pragma unroll
 				for (int i = 0; i < PPW * 2; i += 4) dst[i / 4] = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
@@ -1184,7 +1251,7 @@ extern template npb_status npb_launch_aux_keys<16>(npb_chains *, const SweepArgs
 
 static int h_block_steps() {
 	const char *e = getenv("NPB_D16_BLOCK");
-	int v = e ? atoi(e) : 1024;
+	int v = e ? atoi(e) : 4096;
 	if (v < 128) v = 128;
 	if (v > (1 << 16)) v = 1 << 16;
 	return (v + 127) & ~127;
@@ -1214,6 +1281,7 @@ static npb_status h_ensure(npb_chains *ch) {
 		ch->g_bs = BS;
 		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
 		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
 	}
 	return NPB_OK;
 }
@@ -1241,6 +1309,7 @@ static npb_status h_density_block(npb_chains *ch, const int32_t *d_order, int ns
 	const int grid = n_units < n_sm ? n_units : n_sm;
 	const char *ew = getenv("NPB_D16_EPI");
 	if (ew && ew[0] == '4') k_density_tc16<4><<<grid, 4 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	else if (ew && ew[0] == '1') k_density_tc16<16><<<grid, 16 * 32 + 64, H_SMEM, ctx->stream>>>(g);
 	else k_density_tc16<8><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;

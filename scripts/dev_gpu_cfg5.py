@@ -18,7 +18,7 @@ for it in range(5):
     st = mc.chains.sweep(npb.ALG8, 1)
     D = X.shape[1]
     fl = st.candidates * (D * D + 4 * D + 3 + 6)
-    print(chains, kmax, it, "ms %.2f rate %.3e meanK %.1f cand/step %.1f moved %.3f births %d TFLOPs %.2f" % (
+    print(chains, kmax, it, "ms %.2f rate %.3e meanK %.1f cand/step %.1f moved %.6f births %d TFLOPs %.2f" % (
         st.kernel_ms, st.reassignments / (st.kernel_ms * 1e-3), st.mean_K, st.candidates / st.reassignments,
         st.moved / st.reassignments, st.new_clusters, fl / (st.kernel_ms * 1e-3) / 1e12), flush=True)
 m = mc.chains.metrics(y)
