@@ -332,7 +332,33 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
     ch.close()
     ds.close()
     out["cfg4"] = cfg4_measure(npb, syn, ctx, fp32_peak, rank)
+    out["fp32_pipe_kernel"] = fp32_path_measure(npb, syn, ctx, fp32_peak, rank)
     return out
+
+
+def fp32_path_measure(npb, syn, ctx, fp32_peak, rank):
+    """the headline shape on the FP32-pipe kernel (k_alg8_sweep_tile4, NPB_D16_PATH=fp32): the figure the tensor path replaced"""
+    cfg = CONFIGS["cfg5"]
+    old = os.environ.get("NPB_D16_PATH")
+    os.environ["NPB_D16_PATH"] = "fp32"
+    try:
+        X, y, ds, mc = build_chains(npb, syn, ctx, cfg, cfg["chains"], cfg["kmax"], SEED + 43 * rank)
+        for _ in range(3):
+            mc.chains.sweep(npb.ALG8, 1, want_stats=False)
+        ms, cand, moved, births, last = timed_sweeps(npb, mc.chains, 3)
+        k_ms = float(np.mean(ms))
+        n_step = cfg["chains"] * ds.N
+        fl = (cand / 3) * (f_eval(cfg["D"]) + 6)
+        mc.chains.close()
+        ds.close()
+    finally:
+        if old is None:
+            os.environ.pop("NPB_D16_PATH", None)
+        else:
+            os.environ["NPB_D16_PATH"] = old
+    return {"workload": cfg["workload"], "value": n_step / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": 3, "warmup": 3,
+            "roofline": {"bound": "fp32", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": fl / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None, "kernel": "k_alg8_sweep_tile4<16,3>"}}
 
 
 def cfg4_measure(npb, syn, ctx, fp32_peak, rank, chains=256, N=1_000_000, timed=3):
@@ -495,7 +521,48 @@ def main():
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
+        tc_path = DIM == 16 and kmax == 32 and not os.environ.get("NPB_D16_PATH", "").startswith("f")
         kernel = "k_alg8_sweep_tile4<%d,3>" % DIM if (DIM >= 4 and kmax == 32) else ("k_alg8_sweep_tile" if DIM >= 4 else "k_alg8_sweep_reg")
+        fp32_roofline = {"bound": "fp32", "achieved": flops_per_launch / (k_ms * 1e-3) / 1e12, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": flops_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read+write)",
+                         "algorithmic_bytes": bytes_per_launch, "kernel": kernel, "kernel_ms": k_ms,
+                         "peak_source": "FP32 FMA peak measured in this run by npb_fp32_peak (better of the scalar FFMA and the "
+                                        "packed FFMA2 instruction streams; MEASURED_PEAKS.json has no FP32 figure); algorithmic "
+                                        "flops = sum(K_i+m) * (D^2+4D+3+6), counter kept by the kernel"}
+        launches = args.steps * (3 if (DIM >= 4 and kmax == 32) else 2)
+        if tc_path:
+            # D = 16, Kmax = 32 runs on the tensor path (npb_alg8_gemm.cu): per block of 4096 steps k_pre_aimg16, k_pre_bimg16,
+            # k_density_tc16 (tcgen05 kind::f16 density table, three FP16 products per FP32 product + folded offsets: four K = 16
+            # MMA steps per (step, 16 slots)) and k_race (warp per chain).  The step's dominant kernel is k_density_tc16 (~2/3 of
+            # the step, ncu); no single resource is saturated (tensor pipe 44 %, L2 56 %, issue 41 %, DRAM 25 % in ncu), so the
+            # tensor figure is reported as `roofline`, the table's HBM round trip as `roofline_hbm` and the algorithmic FP32-
+            # equivalent work against the FP32 pipe as `roofline_fp32_equivalent` (> 1: the work left that pipe).
+            blocks = (n_items + 4095) // 4096
+            launches = args.steps * (2 + 4 * blocks)
+            bf16_peak = None
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(pk):
+                bf16_peak = json.load(open(pk)).get("bf16_tflops")
+            f16_peak = bf16_peak if bf16_peak else 2250.0
+            mma = n_step * 32 * 4 * 2 * DIM * DIM  # issued kind::f16 flops per sweep: 32 slots x 4 K-steps x 2 x 16 x 16
+            bytes_per_launch = n_step * (2 * 2 + 2 * 32 * 4)  # z read+write (u16) + the table row written and read once (fp32 x 32 slots)
+            traffic_tc = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.config + "_tc")
+                if tj and tj["chains"] == n_chains:
+                    traffic_tc = tj["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            roofline = {"bound": "tensor", "achieved": mma / (k_ms * 1e-3) / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
+                        "frac": mma / (k_ms * 1e-3) / 1e12 / f16_peak, "traffic": traffic_tc,
+                        "traffic_unit": "bytes per sweep (ncu, DRAM read+write of k_density_tc16 + k_race over the sweep's blocks)",
+                        "algorithmic_bytes": bytes_per_launch, "kernel": "k_density_tc16<16,4> (+ k_race<16,3>)", "kernel_ms": k_ms,
+                        "peak_source": "measured bf16 burst peak (MEASURED_PEAKS.json; kind::f16 runs at the bf16 rate); achieved = "
+                                       "issued MMA flops of a sweep / the whole sweep time (table and race kernels)"}
+            fp32_roofline = dict(fp32_roofline, kernel=roofline["kernel"], traffic=traffic_tc, algorithmic_bytes=bytes_per_launch)
+        else:
+            roofline = fp32_roofline
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -504,29 +571,26 @@ def main():
                        "l2": "per-GPU assignment state %d MB (+ %d MB of slot tables) exceeds the 126 MB L2; no flush needed"
                              % (n_items * n_chains * 2 // 2 ** 20, n_chains * kmax * (DIM + DIM * (DIM + 1) // 2 + 1) * 4 // 2 ** 20),
                        "mean_K": last.mean_K, "max_K": last.max_K, "candidates_per_reassignment": cand / (n_step * args.steps),
-                       "moved_fraction": moved / (n_step * args.steps), "new_clusters_per_step": births / args.steps},
+                       "moved_fraction": moved / (n_step * args.steps), "new_clusters_per_step": births / args.steps,
+                       "path": "tensor (tcgen05 kind::f16 density tables + race kernel)" if tc_path else "fp32 pipe"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_items * DIM * 8),
                     "d2h_bytes_per_step": int(n_items * n_chains * 2), "steps": args.e2e_steps,
                     "call": "npb_chains_sweep_host (X up from pinned host memory, every chain's assignments down into "
                             "page-locked host memory)"},
-            # per step: k_scan_order, (D >= 4, Kmax 32: k_aux_keys, the state-independent auxiliary race,) the sweep kernel
-            "gpu_launches": args.steps * (3 if (DIM >= 4 and kmax == 32) else 2),
+            # per step: k_scan_order, (D >= 4, Kmax 32: k_aux_keys, the state-independent auxiliary race,) the sweep kernel(s)
+            "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "achieved": flops_per_launch / (k_ms * 1e-3) / 1e12, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": flops_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read+write)",
-                         "algorithmic_bytes": bytes_per_launch, "kernel": kernel, "kernel_ms": k_ms,
-                         "peak_source": "FP32 FMA peak measured in this run by npb_fp32_peak (better of the scalar FFMA and the "
-                                        "packed FFMA2 instruction streams; MEASURED_PEAKS.json has no FP32 figure); algorithmic "
-                                        "flops = sum(K_i+m) * (D^2+4D+3+6), counter kept by the kernel"},
+            "roofline": roofline,
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
-                             "peak_source": hbm_src},
+                             "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": roofline.get("traffic"), "peak_source": hbm_src},
             "diagnostics": {"mean_purity": diag["mean_purity"], "mean_rand": diag["mean_rand"], "mean_ari": diag["mean_ari"],
                             "mean_K": diag["mean_K"], "chains": diag["chains"], "rhat": diag["rhat"],
                             "cocluster_anchor_diag_mean": float(S.diag().mean().item()),
                             "allreduce": "nccl" if world > 1 else "none (1 rank)"},
         }
+        if tc_path:
+            line["roofline_fp32_equivalent"] = fp32_roofline
         if world == 1 and not args.no_also and args.config == "cfg5":
             try:
                 line["also"] = also_measure(npb, syn, ctx, fp32_peak, rank)

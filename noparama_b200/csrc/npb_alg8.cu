@@ -181,8 +181,9 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
 	if (!two_warp && ch->Kmax == 32 && (ch->D == 4 || ch->D == 8 || ch->D == 16)) key = -ch->D;
 	if (ch->Kmax == 32 && ch->D == 64) key = -64;
-	// D = 16 on the tensor path of npb_alg8_gemm.cu (A/B switch, read at every launch)
-	if (ch->Kmax == 32 && ch->D == 16) { const char *e = getenv("NPB_D16_PATH"); if (e && e[0] == 't') key = -1600; }
+	// D = 16, Kmax = 32: the tensor path of npb_alg8_gemm.cu (2x the FP32-pipe kernel at the headline shape);
+	// NPB_D16_PATH=fp32 selects k_alg8_sweep_tile4 (read at every launch: A/B measurements, tests of both)
+	if (ch->Kmax == 32 && ch->D == 16) { const char *e = getenv("NPB_D16_PATH"); if (!(e && e[0] == 'f')) key = -1600; }
 	switch (key) {
 	// pre-pass (state independent, fully parallel): the race key of every (chain, step)'s auxiliary draws; then the sweep
 	case -4: s = npb_launch_aux_keys<4>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<4>(ch, a); break;
@@ -342,7 +343,7 @@ npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int
 npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out) {
 	SweepArgs a = make_args(ch, 0);
 	if (ch->Kmax != 32) return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers the Kmax = 32 kernels");
-	if (ch->D == 16) { const char *e = getenv("NPB_D16_PATH"); if (e && e[0] == 't') return npb_launch_tc16_probe(ch, chain, d_items, d_out); }
+	if (ch->D == 16) { const char *e = getenv("NPB_D16_PATH"); if (!(e && e[0] == 'f')) return npb_launch_tc16_probe(ch, chain, d_items, d_out); }
 	switch (ch->D) {
 	case 64: return npb_launch_gemm64_probe(ch, chain, d_items, d_out);
 	case 4: return npb_launch_tile4_probe<4>(ch, a, chain, d_items, d_out);

@@ -966,8 +966,8 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 }
 
 // =========================================================================================================
-// D = 16 on the same tensor path (NPB_D16_PATH=tc; the default at D = 16 stays k_alg8_sweep_tile4 unless this measures
-// faster).  A 16-D density is one K = 16 MMA step; the three FP16 products hi*hi + hi*lo + lo*hi are laid out ALONG K so that
+// D = 16 (Kmax = 32) on the same tensor path: the default there (NPB_D16_PATH=fp32 selects k_alg8_sweep_tile4, the FP32-pipe
+// kernel it measured 2x faster than at the headline shape).  A 16-D density is one K = 16 MMA step; the three FP16 products hi*hi + hi*lo + lo*hi are laid out ALONG K so that
 // the 128-byte swizzled row of the D = 64 images carries them: A row = [x_hi | x_hi | x_lo | 0], B row = [T_hi | T_lo | T_hi | 0]
 // (16 FP16 each) -- the fourth quarter carries the per-row offset nb = -T2 (mu - xbar) against a constant column of A, so the
 // accumulator is y itself and the epilogue a plain sum of squares: four K-steps of one accumulation.  Unit of work = (chain, 16 slots): N = 256 = 16 slots x 16 rows, the unit's B
@@ -985,7 +985,8 @@ constexpr int H_ASTAGE = 16384;       // 128 rows x 128 bytes
 constexpr int H_SLOT_IMG = 2048;      // 16 rows x 128 bytes
 constexpr int H_BBYTES = H_NS * H_SLOT_IMG; // 32 KB
 constexpr int H_CONST = 20;           // nb[16] (zero if folded into the GEMM), c2, descale, folded flag, descale^2
-constexpr int H_SMEM = 1024 + H_BBYTES + H_STAGES * H_ASTAGE + 4096;
+constexpr int H_NH_MAX = 4;
+constexpr int H_SMEM = 1024 + H_NH_MAX * H_BBYTES + H_STAGES * H_ASTAGE + 512 + H_NH_MAX * 16 * 20 * 4 + 256;
 }
 
 __global__ void __launch_bounds__(256) k_pre_aimg16(const double *X64, const double *xbar, const int32_t *order, int nsteps, int ntiles,
@@ -1084,23 +1085,28 @@ __global__ void __launch_bounds__(256) k_pre_bimg16(const float *theta, const do
 	if (lane == 0) dirty[cs] = 0;
 }
 
-// warps 0 .. EW-1 epilogue, warp EW MMA issue + TMEM allocation, warp EW + 1 bulk-copy producer
-template <int EW>
+// warps 0 .. EW-1 epilogue, warp EW MMA issue + TMEM allocation, warp EW + 1 bulk-copy producer.
+// Unit of work = NH half-chains (16 slots each, NH / 2 consecutive chains): their B images stay resident and every A tile that
+// streams in is used NH times -- the A stream through L2 was this kernel's largest traffic (ncu: 9.1 GB per block with
+// NH = 1, lts throughput 56 %).
+template <int EW, int NH>
 __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs g) {
-	constexpr int PPW = 32 / EW; // pairs of slots per epilogue warp: 8 (EW = 4) or 4 (EW = 8)
+	constexpr int PPW = 32 / EW; // pairs of slots per epilogue warp: 8 (EW = 4), 4 (EW = 8) or 2 (EW = 16)
+	constexpr uint32_t BB = NH * H_BBYTES;
 	extern __shared__ uint8_t g_smem_raw[];
 	const uint32_t raw = g_smem_u32(g_smem_raw);
 	const uint32_t base = (raw + 1023u) & ~1023u;
 	uint8_t *gen = g_smem_raw + (base - raw);
-	constexpr uint32_t A0 = H_BBYTES, MISC = H_BBYTES + H_STAGES * H_ASTAGE;
+	constexpr uint32_t A0 = BB, MISC = BB + H_STAGES * H_ASTAGE;
 	const uint32_t misc = base + MISC;
 	const uint32_t bar_b_full = misc, bar_b_empty = misc + 8;
 	const uint32_t bar_a_full = misc + 16, bar_a_empty = misc + 16 + 8 * H_STAGES;
 	const uint32_t bar_t_full = misc + 16 + 16 * H_STAGES, bar_t_empty = bar_t_full + 16;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + MISC + 256);
-	float *econst = reinterpret_cast<float *>(gen + MISC + 512); // [16][H_CONST]
+	float *econst = reinterpret_cast<float *>(gen + MISC + 512); // [NH * 16][H_CONST]
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int n_units = g.C * (32 / H_NS);
+	const int n_half = g.C * 2;
+	const int n_units = (n_half + NH - 1) / NH;
 
 	if (warp == EW + 1 && lane == 0) {
 		g_mbar_init(bar_b_full, 1);
@@ -1129,9 +1135,10 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 		if (lane == 0) {
 			uint32_t a_it = 0, unit_it = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				const int nh = min(NH, n_half - u * NH);
 				g_mbar_wait(bar_b_empty, (unit_it & 1u) ^ 1u);
-				g_mbar_expect_tx(bar_b_full, H_BBYTES);
-				g_bulk_g2s(base, g.Bimg + (size_t)u * H_BBYTES, H_BBYTES, bar_b_full); // slots 16 (u & 1) .. + 15 of chain u >> 1
+				g_mbar_expect_tx(bar_b_full, (uint32_t)nh * H_BBYTES);
+				g_bulk_g2s(base, g.Bimg + (size_t)u * BB, (uint32_t)nh * H_BBYTES, bar_b_full);
 				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
 					const uint32_t s = a_it % H_STAGES, ph = (a_it / H_STAGES) & 1u;
 					g_mbar_wait(bar_a_empty + 8 * s, ph ^ 1u);
@@ -1144,22 +1151,27 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 	} else if (warp == EW) {
 		if (lane == 0) {
 			constexpr uint32_t ID256 = g_idesc(G_M, 256);
-			uint32_t a_it = 0, tile_it = 0, unit_it = 0;
+			uint32_t a_it = 0, acc_it = 0, unit_it = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit_it) {
+				const int nh = min(NH, n_half - u * NH);
 				g_mbar_wait(bar_b_full, unit_it & 1u);
 				g_tc_fence_after();
-				for (int t = 0; t < g.ntiles; ++t, ++tile_it, ++a_it) {
-					const uint32_t buf = tile_it & 1u;
-					g_mbar_wait(bar_t_empty + 8 * buf, ((tile_it >> 1) & 1u) ^ 1u);
+				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
 					const uint32_t s = a_it % H_STAGES;
 					g_mbar_wait(bar_a_full + 8 * s, (a_it / H_STAGES) & 1u);
 					g_tc_fence_after();
-					const uint32_t dcol = tmem + buf * 256u, A = base + A0 + s * H_ASTAGE;
+					const uint32_t A = base + A0 + s * H_ASTAGE;
+					for (int hf = 0; hf < nh; ++hf, ++acc_it) {
+						const uint32_t buf = acc_it & 1u;
+						g_mbar_wait(bar_t_empty + 8 * buf, ((acc_it >> 1) & 1u) ^ 1u);
+						g_tc_fence_after();
+						const uint32_t dcol = tmem + buf * 256u, B = base + hf * H_BBYTES;
 #pragma unroll
-					for (int k = 0; k < 4; ++k) // hi*hi, hi*lo, lo*hi, the folded offsets: four K-steps of the same rows
-						g_mma_f16(dcol, g_desc(A + k * 32), g_desc(base + k * 32), ID256, k != 0);
+						for (int k = 0; k < 4; ++k) // hi*hi, hi*lo, lo*hi, the folded offsets: four K-steps of the same rows
+							g_mma_f16(dcol, g_desc(A + k * 32), g_desc(B + k * 32), ID256, k != 0);
+						g_tc_commit(bar_t_full + 8 * buf);
+					}
 					g_tc_commit(bar_a_empty + 8 * s);
-					g_tc_commit(bar_t_full + 8 * buf);
 				}
 				g_tc_commit(bar_b_empty);
 			}
@@ -1169,63 +1181,72 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 		// epilogue: thread = step of the tile; a warp takes PPW pairs of slots
 		const int wq = warp & 3, eg = warp >> 2;
 		const int row = wq * 32 + lane;
-		uint32_t tile_it = 0;
+		uint32_t acc_it = 0;
 		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+			const int nh = min(NH, n_half - u * NH);
 			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
 			{
-				const float *src = g.Bconst + (size_t)u * H_NS * H_CONST;
-				for (int i = threadIdx.x; i < H_NS * H_CONST; i += EW * 32) econst[i] = __ldg(src + i);
+				const float *src = g.Bconst + (size_t)u * NH * H_NS * H_CONST;
+				for (int i = threadIdx.x; i < nh * H_NS * H_CONST; i += EW * 32) econst[i] = __ldg(src + i);
 			}
 			asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-			bool folded = true; // every slot of the unit has its offsets inside the GEMM: short epilogue
+			unsigned folded_mask = 0u; // bit hf: every slot of that half has its offsets inside the GEMM (short epilogue)
+			for (int hf = 0; hf < nh; ++hf) {
+				bool f = true;
 #pragma unroll
-			for (int sl = 0; sl < H_NS; ++sl) folded = folded && econst[sl * H_CONST + HD + 2] != 0.0f;
-			float *Lc = g.L + ((size_t)(u >> 1) * g.BS) * 32 + (u & 1) * H_NS + eg * PPW * 2;
-			for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
-				const uint32_t buf = tile_it & 1u;
-				g_mbar_wait(bar_t_full + 8 * buf, (tile_it >> 1) & 1u);
-				g_tc_fence_after();
-				const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u + eg * PPW * 32;
-				float out[PPW * 2];
+				for (int sl = 0; sl < H_NS; ++sl) f = f && econst[(hf * H_NS + sl) * H_CONST + HD + 2] != 0.0f;
+				folded_mask |= f ? (1u << hf) : 0u;
+			}
+			for (int t = 0; t < g.ntiles; ++t) {
+				for (int hf = 0; hf < nh; ++hf, ++acc_it) {
+					const int half = u * NH + hf;
+					float *Lc = g.L + ((size_t)(half >> 1) * g.BS) * 32 + (half & 1) * H_NS + eg * PPW * 2;
+					const bool folded = (folded_mask >> hf) & 1u;
+					const uint32_t buf = acc_it & 1u;
+					g_mbar_wait(bar_t_full + 8 * buf, (acc_it >> 1) & 1u);
+					g_tc_fence_after();
+					const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u + eg * PPW * 32;
+					float out[PPW * 2];
 #pragma unroll
-				for (int pp = 0; pp < PPW; pp += 2) {
-					float v0[32], v1[32];
-					g_tmem_ld32_nowait(taddr + pp * 32u, v0);
-					g_tmem_ld32_nowait(taddr + (pp + 1) * 32u, v1);
-					g_tmem_wait_ld(v0, v1);
-					if (pp + 2 >= PPW) { // the accumulator is in registers: hand the buffer back before the arithmetic
-						g_tc_fence_before();
-						g_mbar_arrive(bar_t_empty + 8 * buf);
-					}
+					for (int pp = 0; pp < PPW; pp += 2) {
+						float v0[32], v1[32];
+						g_tmem_ld32_nowait(taddr + pp * 32u, v0);
+						g_tmem_ld32_nowait(taddr + (pp + 1) * 32u, v1);
+						g_tmem_wait_ld(v0, v1);
+						if (pp + 2 >= PPW) { // the accumulator is in registers: hand the buffer back before the arithmetic
+							g_tc_fence_before();
+							g_mbar_arrive(bar_t_empty + 8 * buf);
+						}
 #pragma unroll
-					for (int h = 0; h < 4; ++h) { // slots 2 pp .. 2 pp + 3 of this warp's range
-						const float(&v)[32] = h < 2 ? v0 : v1;
-						const int o = (h & 1) * 16;
-						const float *ec = econst + (eg * PPW * 2 + pp * 2 + h) * H_CONST;
-						float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
-						if (folded) {
+						for (int h = 0; h < 4; ++h) { // slots 2 pp .. 2 pp + 3 of this warp's range
+							const float(&v)[32] = h < 2 ? v0 : v1;
+							const int o = (h & 1) * 16;
+							const float *ec = econst + (hf * H_NS + eg * PPW * 2 + pp * 2 + h) * H_CONST;
+							float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+							if (folded) {
 #pragma unroll
-							for (int i = 0; i < 16; i += 4) {
-								q0 = fmaf(v[o + i], v[o + i], q0); q1 = fmaf(v[o + i + 1], v[o + i + 1], q1);
-								q2 = fmaf(v[o + i + 2], v[o + i + 2], q2); q3 = fmaf(v[o + i + 3], v[o + i + 3], q3);
+								for (int i = 0; i < 16; i += 4) {
+									q0 = fmaf(v[o + i], v[o + i], q0); q1 = fmaf(v[o + i + 1], v[o + i + 1], q1);
+									q2 = fmaf(v[o + i + 2], v[o + i + 2], q2); q3 = fmaf(v[o + i + 3], v[o + i + 3], q3);
+								}
+								out[pp * 2 + h] = fmaf(-ec[HD + 3], (q0 + q1) + (q2 + q3), ec[HD]);
+							} else {
+								const float dsc = ec[HD + 1];
+#pragma unroll
+								for (int i = 0; i < 16; i += 4) {
+									const float4 nb = *reinterpret_cast<const float4 *>(ec + i);
+									const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
+											    a3 = fmaf(v[o + i + 3], dsc, nb.w);
+									q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+								}
+								out[pp * 2 + h] = ec[HD] - ((q0 + q1) + (q2 + q3));
 							}
-							out[pp * 2 + h] = fmaf(-ec[HD + 3], (q0 + q1) + (q2 + q3), ec[HD]);
-						} else {
-							const float dsc = ec[HD + 1];
-#pragma unroll
-							for (int i = 0; i < 16; i += 4) {
-								const float4 nb = *reinterpret_cast<const float4 *>(ec + i);
-								const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
-										    a3 = fmaf(v[o + i + 3], dsc, nb.w);
-								q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
-							}
-							out[pp * 2 + h] = ec[HD] - ((q0 + q1) + (q2 + q3));
 						}
 					}
-				}
-				float4 *dst = reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32);
+					float4 *dst = reinterpret_cast<float4 *>(Lc + (size_t)(t * G_M + row) * 32);
 #pragma unroll
-				for (int i = 0; i < PPW * 2; i += 4) dst[i / 4] = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
+					for (int i = 0; i < PPW * 2; i += 4) dst[i / 4] = make_float4(out[i], out[i + 1], out[i + 2], out[i + 3]);
+				}
 			}
 		}
 	}
@@ -1279,9 +1300,10 @@ static npb_status h_ensure(npb_chains *ch) {
 		NPB_CUDA_OK(cudaMemsetAsync(ch->g_L, 0, C * (size_t)(BS + 32) * 32 * sizeof(float), ctx->stream));
 		NPB_CUDA_OK(cudaMemsetAsync(ch->g_born, 0, 2 * C * sizeof(uint32_t), ctx->stream));
 		ch->g_bs = BS;
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_density_tc16<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
 	}
 	return NPB_OK;
 }
@@ -1305,12 +1327,14 @@ static npb_status h_density_block(npb_chains *ch, const int32_t *d_order, int ns
 	g.BS = ch->g_bs + 32;
 	static int n_sm = 0;
 	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-	const int n_units = C * (32 / H_NS);
+	const char *ew = getenv("NPB_D16_EPI"), *nhs = getenv("NPB_D16_NH");
+	const int nh = nhs ? atoi(nhs) : 4;
+	const int n_units = (C * 2 + nh - 1) / nh;
 	const int grid = n_units < n_sm ? n_units : n_sm;
-	const char *ew = getenv("NPB_D16_EPI");
-	if (ew && ew[0] == '4') k_density_tc16<4><<<grid, 4 * 32 + 64, H_SMEM, ctx->stream>>>(g);
-	else if (ew && ew[0] == '1') k_density_tc16<16><<<grid, 16 * 32 + 64, H_SMEM, ctx->stream>>>(g);
-	else k_density_tc16<8><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	if (nh == 1) k_density_tc16<8, 1><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	else if (nh == 2) k_density_tc16<8, 2><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	else if (ew && ew[0] == '8') k_density_tc16<8, 4><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	else k_density_tc16<16, 4><<<grid, 16 * 32 + 64, H_SMEM, ctx->stream>>>(g);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }

@@ -15,7 +15,7 @@ D = 16
 def env():
     keys = ("NPB_D16_PATH", "NPB_D16_BLOCK", "NPB_D16_EPI", "NPB_D64_SPEC")
     saved = {k: os.environ.get(k) for k in keys}
-    os.environ["NPB_D16_PATH"] = "tc"
+    os.environ.pop("NPB_D16_PATH", None)  # the tensor path is the default at D = 16, Kmax = 32
     yield os.environ
     for k, v in saved.items():
         if v is None:
@@ -24,7 +24,7 @@ def env():
             os.environ[k] = v
 
 
-@pytest.mark.parametrize("epi", ["4", "8"])
+@pytest.mark.parametrize("epi", ["8", "16"])
 def test_tc16_density_table_within_1e5_of_oracle(npb, ctx, oracle, env, epi):
     env["NPB_D16_EPI"] = epi
     rng = np.random.default_rng(16)
@@ -96,4 +96,68 @@ def test_tc16_recovers_given_clusters(npb, ctx, env):
     assert s1.moved > 0.8 * s1.reassignments and s2.moved < 1e-3 * s2.reassignments
     m = mc.chains.metrics(y)
     assert np.all(m["K"] == 8) and m["purity"].min() > 0.999
+    ds.close()
+
+
+def test_fp32_pipe_kernel_still_serves_16d(npb, ctx, oracle, env):
+    """NPB_D16_PATH=fp32: k_alg8_sweep_tile4 at D = 16 (the default at D = 4, 8): recovery, candidates, and its producer's
+    density tile against the oracle -- the same checks the tensor path passes above."""
+    env["NPB_D16_PATH"] = "fp32"
+    X, y = syn.gmm(4000, D, 8, 5)
+    means = np.stack([X[y == k].mean(0) for k in range(8)])
+    Sigma = np.tile(np.eye(D), (8, 1, 1))
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=32, Kmax=32, seed=3)
+    mc.chains.init_from_params(means, Sigma)
+    s1 = mc.chains.sweep(npb.ALG8, 1)
+    s2 = mc.chains.sweep(npb.ALG8, 1)
+    assert s1.overflow_chains == 0 and s1.candidates == 11 * s1.reassignments == s2.candidates
+    assert s2.moved < 1e-3 * s2.reassignments
+    m = mc.chains.metrics(y)
+    assert np.all(m["K"] == 8) and m["purity"].min() > 0.999
+    items = np.arange(32, dtype=np.int32) * 100
+    got = mc.chains.probe_tile_logdensity(1, items).astype(np.float64)[:8]
+    want = oracle.mvn_logpdf_batch(means, Sigma, X[items]).T
+    assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 1e-5
+    ds.close()
+
+
+def _oracle_seed16(args):
+    seed, T, K0 = args
+    from oracle import binding as orc
+    X, y = syn.gmm(160, D, 3, 43, min_dist=6.0)
+    p = orc.make_prior(**syn.reference_prior(D))
+    r = orc.Run(p, X, T=T, K0=K0, seed_main=300 + seed, seed_shuffle=2900 + seed, flags=orc.LOG_DOMAIN)
+    s = r.stats()
+    pur, ri, ari = orc.metrics(y, r.assignments(0))
+    return s.K_final, pur, ari, s.new_cluster_events / s.updates, s.moved / s.updates
+
+
+def test_tc16_distribution_and_birth_rate_against_oracle(npb, ctx, oracle, env):
+    """The tensor path's race (counter-hash noise capped at 20, speculative step-parallel pass, births repaired in the
+    density table) against the oracle (log-domain mode) at D = 16: 96 oracle seeds against 768 device chains from the same
+    K0 = 8 start, T = 60 sweeps: K, purity, ARI in distribution, birth and move rates over the whole run."""
+    from multiprocessing import Pool
+    from scipy import stats as sps
+    env["NPB_D16_BLOCK"] = "128"
+    X, y = syn.gmm(160, D, 3, 43, min_dist=6.0)
+    T, K0 = 60, 8
+    with Pool(8) as pool:
+        res = np.array(pool.map(_oracle_seed16, [(s, T, K0) for s in range(96)]))
+    ds = npb.Dataset(ctx, X)
+    mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=768, Kmax=32, K0=K0, seed=17)
+    stats = mc.run(T, sweeps_per_launch=20)
+    assert all(s.overflow_chains == 0 for s in stats)
+    m = mc.chains.metrics(y)
+    for name, got, want in (("K", m["K"].astype(float), res[:, 0]), ("purity", m["purity"], res[:, 1]),
+                            ("ari", m["adjusted_rand"], res[:, 2])):
+        p = sps.ks_2samp(got, want).pvalue
+        assert p > 0.01, "%s: KS p=%.2e (gpu %.4f vs oracle %.4f)" % (name, p, got.mean(), want.mean())
+    n = sum(s.reassignments for s in stats)
+    births = sum(s.new_clusters for s in stats) / n
+    moved = sum(s.moved for s in stats) / n
+    print("births/step gpu %.5f oracle %.5f; moved gpu %.4f oracle %.4f; K gpu %.2f oracle %.2f" % (
+        births, res[:, 3].mean(), moved, res[:, 4].mean(), m["K"].mean(), res[:, 0].mean()))
+    assert abs(births - res[:, 3].mean()) < 0.1 * res[:, 3].mean() + 2e-5
+    assert abs(moved - res[:, 4].mean()) < 0.1 * res[:, 4].mean() + 2e-4
     ds.close()
