@@ -366,6 +366,40 @@ __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
 // first move are final, and the sequential pass (lane = slot, the consumer of npb_alg8_tile4.cuh) takes over from that
 // step; both passes evaluate the same keys (same noise, same operation order), so the result does not depend on which
 // pass decided a step.  A chain that moves a lot (burn-in) skips the speculative pass.
+// Upper bound of the race key of a step's best auxiliary draw, from the FIRST Box-Muller pair of every draw only (|v| and
+// z_par: key_m <= c0_2 - D log2|v| - (|xw|/|v| - s z_par)^2 + log2(alpha/m) + noise, the chi-square term dropped, noise <= 23 by
+// neg_lg2_exp1's clamp; + 1 for rounding and the two index bits packed into the key).  Walks the same stream as aux_race
+// (npb_alg8_tile4.cuh), skipping the words of a draw it does not need.
+template <int CD, int M>
+__device__ __forceinline__ float g_aux_bound(const Philox &ph, const PriorDev &pr, float rn, uint32_t sj, uint32_t sweep, float ik2) {
+	constexpr int TAILW = 2 + ((CD - 1) / 2 + 1) / 2; // words of a draw after its first pair: the z2^2 pair, the packed uniforms
+	uint32_t as[4];
+	aux_seed(ph, sj, sweep, as);
+	float ub = -INFINITY;
+#pragma unroll
+	for (int m = 0; m < M; ++m) {
+		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+		float g0, g1;
+		npb_normal2(r0, r1, g0, g1);
+		const float av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
+		const float along = rn * __frcp_rn(av) - ik2 * g1;
+		ub = fmaxf(ub, pr.c0_2 - (float)CD * fast_lg2(av) - along * along + pr.log2_alpha_m);
+		if (m + 1 < M) {
+#pragma unroll
+			for (int w = 0; w < TAILW; ++w) (void)xoshiro_next(as);
+		}
+	}
+	return ub + 24.0f;
+}
+// the exact key, packed like k_aux_keys packs it (draw index in the two low mantissa bits)
+template <int CD, int M>
+__device__ __forceinline__ uint32_t g_aux_exact(const Philox &ph, const PriorDev &pr, float rn, uint32_t sj, uint32_t sweep, float ik2) {
+	float ak;
+	int am;
+	aux_race<CD, M>(ph, pr, rn, sj, sweep, ik2, ak, am);
+	return (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+}
+
 // D-generic front ends of the rare paths of the race: density of one (item, slot) from the slot table in global memory, and
 // theta' of a birth (D = 64: two coordinates per lane; D <= 32: aux_birth_z of npb_alg8_tile4.cuh, one coordinate per lane)
 template <int CD>
@@ -446,9 +480,17 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 		int znew = zold;
 		const uint32_t T = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)(p.s0 + b0) * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
 		const int cnt = min(32, p.nsteps - b0);
-		const uint32_t auxp = valid ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + sj) : 0xff800000u;
-		const float auxkey_j = __uint_as_float(auxp);
-		const int zold_aux_j = zold | ((int)(auxp & 3u) << 16);
+		// The auxiliary draws' race key of step sj: read from the pre-pass (k_aux_keys) if the launch ran one, else LAZY: an
+		// upper bound from the draws' first normals now, the exact key (same function, same bits) only for the steps whose
+		// own key does not clear the bound, and for the whole tile if it enters the sequential pass.
+		const bool lazy = a.aux_keys == nullptr;
+		const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
+		const float rn_j = (lazy && valid) ? __ldg(a.Xwn + item) : 0.0f;
+		uint32_t auxp = 0xff800000u;
+		bool aux_exact = !lazy || !valid;
+		if (!lazy && valid) auxp = __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + sj);
+		float auxkey_j = __uint_as_float(auxp);
+		if (lazy && valid) auxkey_j = g_aux_bound<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2); // a bound until aux_exact
 		__syncwarp();
 		if (reload) {
 #pragma unroll
@@ -474,6 +516,11 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 			// logarithm.  Slots some lane cannot exclude are evaluated exactly (warp-uniform loop over the union).
 			const float lg_own = lg1_s[zold];
 			const float own = lg_own > -INFINITY ? (tile[zold * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)zold)) + lg_own : -INFINITY;
+			if (!aux_exact && own > -INFINITY && !(own >= auxkey_j)) { // the bound does not settle it: the exact key
+				auxp = g_aux_exact<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2);
+				auxkey_j = __uint_as_float(auxp);
+				aux_exact = true;
+			}
 			bool stays = own > -INFINITY && own >= auxkey_j;
 			unsigned need = 0u;
 #pragma unroll 8
@@ -503,6 +550,11 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 
 		if (j0 < cnt) {
 			// ---- sequential pass from step j0: lane = slot ----
+			if (!aux_exact) {
+				auxp = g_aux_exact<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2);
+				auxkey_j = __uint_as_float(auxp);
+			}
+			const int zold_aux_j = zold | ((int)(auxp & 3u) << 16);
 			float base_next = tile[lane * 33 + j0] + g_noise(T, (uint32_t)j0, (uint32_t)lane);
 			int zo_aux_next = __shfl_sync(0xffffffffu, zold_aux_j, j0);
 			float ak_next = __shfl_sync(0xffffffffu, auxkey_j, j0);
@@ -828,7 +880,8 @@ static bool g_use_fp32() {
 static npb_status g_ensure(npb_chains *ch) {
 	npb_ctx *ctx = ch->ctx;
 	npb_dataset *ds = ch->ds;
-	const int BS = g_block_steps();
+	int BS = g_block_steps();
+	if ((int64_t)BS > ((ds->N + 127) & ~(int64_t)127)) BS = (int)((ds->N + 127) & ~(int64_t)127); // no larger than the sweep
 	if (!ds->Xbar) {
 		NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * (2 * GD + 1))); // means, scale exponent, column maxima
 		k_colmean<<<GD, 256, 0, ctx->stream>>>(ds->X64, ds->N, GD, ds->Xbar);
@@ -1289,7 +1342,8 @@ static npb_status h_ensure(npb_chains *ch) {
 		NPB_CUDA_OK(cudaGetLastError());
 	}
 	if (!ch->g_L) {
-		const int BS = h_block_steps();
+		int BS = h_block_steps();
+		if ((int64_t)BS > ((ds->N + 127) & ~(int64_t)127)) BS = (int)((ds->N + 127) & ~(int64_t)127); // no larger than the sweep
 		const size_t C = (size_t)ch->C;
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * H_ASTAGE));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bimg, C * 32 * H_SLOT_IMG));
@@ -1344,13 +1398,21 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D = 16 tensor-core sweep");
 	npb_status s = h_ensure(ch);
 	if (s != NPB_OK) return s;
-	s = npb_launch_aux_keys<16>(ch, a);
-	if (s != NPB_OK) return s;
+	// NPB_D16_AUX=lazy drops the k_aux_keys pre-pass (16 % of the step): the race then bounds the auxiliary keys from the
+	// draws' first normals and evaluates them on demand (g_aux_bound / g_aux_exact; same keys, same results, 3.2 GB less
+	// memory).  Measured equal (101 against 102 ms per sweep): the bound leaves out the chi-square term, which is what makes
+	// an auxiliary draw hopeless at D = 16, so a third of the steps still need the exact key and every tile pays for it.
+	const bool prepass = [] { const char *e = getenv("NPB_D16_AUX"); return !(e && e[0] == 'l'); }();
+	if (prepass) {
+		s = npb_launch_aux_keys<16>(ch, a);
+		if (s != NPB_OK) return s;
+	}
 	const size_t C = (size_t)ch->C;
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, C * 32, ctx->stream));
 	const int BS = ch->g_bs, N = a.N;
 	PreArgs p;
 	p.a = a;
+	if (!prepass) p.a.aux_keys = nullptr;
 	p.BS = BS + 32;
 	p.L = ch->g_L;
 	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();

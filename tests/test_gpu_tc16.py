@@ -13,7 +13,7 @@ D = 16
 
 @pytest.fixture
 def env():
-    keys = ("NPB_D16_PATH", "NPB_D16_BLOCK", "NPB_D16_EPI", "NPB_D64_SPEC")
+    keys = ("NPB_D16_PATH", "NPB_D16_BLOCK", "NPB_D16_EPI", "NPB_D64_SPEC", "NPB_D16_AUX")
     saved = {k: os.environ.get(k) for k in keys}
     os.environ.pop("NPB_D16_PATH", None)  # the tensor path is the default at D = 16, Kmax = 32
     yield os.environ
@@ -74,12 +74,13 @@ def test_tc16_invariants(npb, ctx, oracle, env, block):
         assert np.allclose([m["purity"][c], m["rand_index"][c], m["adjusted_rand"][c]], want, atol=1e-12)
     print("births", births, "mean K", st.mean_K)
     zs = []
-    for spec, per_launch in (("1", None), ("0", None), ("1", 1)):
-        env["NPB_D64_SPEC"] = spec
+    # speculation on/off, batching of sweeps, auxiliary keys lazily in the race or from the k_aux_keys pre-pass: same result
+    for spec, per_launch, aux in (("1", None, "lazy"), ("0", None, "lazy"), ("1", 1, "lazy"), ("1", None, "pre"), ("0", 2, "pre")):
+        env["NPB_D64_SPEC"], env["NPB_D16_AUX"] = spec, aux
         a = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=32, K0=8, seed=77)
         a.run(4, sweeps_per_launch=per_launch)
         zs.append(a.getMembershipMatrix().copy())
-    assert np.array_equal(zs[0], zs[1]) and np.array_equal(zs[0], zs[2])
+    assert all(np.array_equal(zs[0], z) for z in zs[1:])
     ds.close()
 
 
