@@ -1,11 +1,12 @@
-// npb_alg8_gemm.cu -- Algorithm 8 / Algorithm 2 sweeps at D = 64 (Kmax = 32): the whitened quadratic forms of a block of
-// steps as a tcgen05 GEMM (BASELINE configs[3]: "tensor-core whitened quadratic forms"), the sequential race as a
-// warp-per-chain consumer.
+// npb_alg8_gemm.cu -- the tensor path: Algorithm 8 / Algorithm 2 sweeps at D = 64 and D = 16 (Kmax = 32) with the whitened
+// quadratic forms of a block of steps as a tcgen05 GEMM (BASELINE configs[3]: "tensor-core whitened quadratic forms") and the
+// sequential race as a warp-per-chain consumer.  D = 64 first (fused kernel); the D = 16 variant (the headline shape: table
+// kernel + race kernel) is the second half of the file.
 //
 // Same algorithm and the same reference lines as the D <= 16 kernels (NealAlgorithm8::update,
 // src/np_neal_algorithm8.cpp:49-167; density: src/statistics/multivariatenormal.cpp:106-136), a different mapping: at
 // D = 64 a cluster slot is 2145 floats, so neither the registers of a lane (npb_alg8_tile4.cuh) nor shared memory hold a
-// chain's slot table, and a density is 2080 FMAs -- GEMM-shaped work.  A sweep is cut into blocks of NPB_G_BS steps; per
+// chain's slot table, and a density is 2080 FMAs -- GEMM-shaped work.  A sweep is cut into blocks of 4096 steps; per
 // block, in stream order:
 //   k_pre_aimg     gathers the block's item rows (scan order), centres them on the dataset mean, scales them by a power
 //                  of two (largest |x - xbar| just below 2^14), splits every coordinate into two FP16 terms (hi + lo)
@@ -346,7 +347,7 @@ __device__ __noinline__ void g_birth_theta64(const Philox &ph, const PriorDev &p
 
 #define G_NOISE_CAP 20.0f
 // race noise of (tile, step j, slot k): a counter hash instead of a per-lane stream, so that the step-parallel pass
-// (lane = step) and the sequential pass (lane = slot) of k_alg8_sweep_pre draw the same number for the same candidate
+// (lane = step) and the sequential pass (lane = slot) of g_consume_chain draw the same number for the same candidate
 __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
 	uint32_t x = T + (j * 32u + k) * 0x9E3779B9u;
 	x ^= x >> 16;
@@ -452,8 +453,8 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 	uint32_t born_mask = 0u;
 	int recent_moves = 0;
 
-	// The table of this block was computed while the previous block was still being consumed (the two kernels overlap on
-	// two streams): the columns of the slots born there are re-evaluated here, for the whole block (lane = step).
+	// The table of this block was computed while the previous block was still being consumed (the fused schedule; with
+	// separate launches the bookkeeping is the same): the columns of the slots born there are re-evaluated here, for the whole block (lane = step).
 	if (p.born_prev) {
 		uint32_t fix = p.born_prev[chain];
 		while (fix) {
