@@ -135,11 +135,10 @@ npb_status npb_launch_whiten(npb_dataset *ds) {
 npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given) {
 	npb_ctx *ctx = ch->ctx;
 	SweepArgs a = make_args(ch, 0);
-	static uint32_t epoch = 0; // distinct initial assignments for repeated initialisations of a handle
 	const int warps = 4;
 	int64_t blocks = (ch->C + warps - 1) / warps;
 	size_t shmem = (size_t)warps * ch->Kmax * sizeof(int);
-	k_chains_init<<<(unsigned)blocks, warps * 32, shmem, ctx->stream>>>(a, K0, d_theta_given, d_theta_given ? ++epoch : 0u);
+	k_chains_init<<<(unsigned)blocks, warps * 32, shmem, ctx->stream>>>(a, K0, d_theta_given, d_theta_given ? ++ch->init_epoch : 0u); // distinct initial assignments for repeated initialisations of a handle
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
@@ -183,7 +182,11 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	if (ch->Kmax == 32 && ch->D == 64) key = -64;
 	// D = 16, Kmax = 32: the tensor path of npb_alg8_gemm.cu (2x the FP32-pipe kernel at the headline shape);
 	// NPB_D16_PATH=fp32 selects k_alg8_sweep_tile4 (read at every launch: A/B measurements, tests of both)
-	if (ch->Kmax == 32 && ch->D == 16) { const char *e = getenv("NPB_D16_PATH"); if (!(e && e[0] == 'f')) key = -1600; }
+	// (default: the fused kernel of npb_alg8_fused16.cu; NPB_D16_PATH=tc2: round 1's table kernel + race kernel)
+	if (ch->Kmax == 32 && ch->D == 16) {
+		const char *e = getenv("NPB_D16_PATH");
+		if (!(e && e[0] == 'f')) key = (e && e[0] == 't' && e[1] == 'c' && e[2] == '2') ? -1602 : -1600;
+	}
 	switch (key) {
 	// pre-pass (state independent, fully parallel): the race key of every (chain, step)'s auxiliary draws; then the sweep
 	case -4: s = npb_launch_aux_keys<4>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<4>(ch, a); break;
@@ -191,7 +194,8 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	case -16: s = npb_launch_aux_keys<16>(ch, a); if (s == NPB_OK) s = npb_launch_alg8_tile4<16>(ch, a); break;
 	// D = 64: block-wise tcgen05 density table + warp-per-chain race (npb_alg8_gemm.cu)
 	case -64: s = npb_launch_alg8_gemm64(ch, a); break;
-	case -1600: s = npb_launch_alg8_tc16(ch, a); break;
+	case -1600: s = npb_launch_alg8_fused16(ch, a); break;
+	case -1602: s = npb_launch_alg8_tc16(ch, a); break;
 	case 2001: s = npb_launch_alg8_reg<2, 1>(ch, a); break;
 	case 2002: s = npb_launch_alg8_reg<2, 2>(ch, a); break;
 	case 2004: s = npb_launch_alg8_reg<2, 4>(ch, a); break;
@@ -333,9 +337,8 @@ __global__ void __launch_bounds__(32) k_update_item_alg8(SweepArgs a, int chain0
 npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item) {
 	npb_ctx *ctx = ch->ctx;
 	SweepArgs a = make_args(ch, 0);
-	static uint32_t call = 0;
 	const size_t shmem = (size_t)ch->m_aux * npb_ps(ch->D) * sizeof(float);
-	k_update_item_alg8<<<(unsigned)n, 32, shmem, ctx->stream>>>(a, (int)chain0, (int)item, call++);
+	k_update_item_alg8<<<(unsigned)n, 32, shmem, ctx->stream>>>(a, (int)chain0, (int)item, ch->item_calls++);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
@@ -343,7 +346,11 @@ npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int
 npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out) {
 	SweepArgs a = make_args(ch, 0);
 	if (ch->Kmax != 32) return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers the Kmax = 32 kernels");
-	if (ch->D == 16) { const char *e = getenv("NPB_D16_PATH"); if (!(e && e[0] == 'f')) return npb_launch_tc16_probe(ch, chain, d_items, d_out); }
+	if (ch->D == 16) {
+		const char *e = getenv("NPB_D16_PATH");
+		if (e && e[0] == 't' && e[1] == 'c' && e[2] == '2') return npb_launch_tc16_probe(ch, chain, d_items, d_out);
+		if (!(e && e[0] == 'f')) return npb_launch_fused16_probe(ch, chain, d_items, d_out);
+	}
 	switch (ch->D) {
 	case 64: return npb_launch_gemm64_probe(ch, chain, d_items, d_out);
 	case 4: return npb_launch_tile4_probe<4>(ch, a, chain, d_items, d_out);

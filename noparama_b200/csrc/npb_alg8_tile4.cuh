@@ -63,6 +63,11 @@ __device__ __forceinline__ f32x2_t f2_bcast(float t) {
 	asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(t));
 	return r;
 }
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+	f32x2_t r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
 __device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
 	f32x2_t r;
 	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));

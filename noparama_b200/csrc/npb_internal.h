@@ -46,6 +46,8 @@ struct npb_chains {
 	int Kmax = 0, m_aux = 0, K0 = 0, D = 0;
 	uint64_t seed = 0;
 	uint32_t sweep = 0;         // sweeps done so far (Philox counter / scan-order key)
+	uint32_t init_epoch = 0;    // initialisations from given parameters so far (distinct initial assignments per call)
+	uint32_t item_calls = 0;    // single-item updates so far (Philox counter of npb_chain_update_alg8)
 	npb_z_t *z = nullptr;       // [N, C] item-major
 	float *theta = nullptr;     // [C, Kmax, PS]
 	int *counts = nullptr;      // [C, Kmax]
@@ -143,6 +145,8 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a);
 npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a);
 npb_status npb_launch_tc16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
+npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a);
+npb_status npb_launch_fused16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item);
 npb_status npb_launch_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);
 npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposals, int whole_sweeps, float *d_detail);

@@ -57,3 +57,31 @@ def config(cfg):
 def reference_prior(D):
     """np_main.cpp:164,367-371 generalised to D dims: mu0 = 6*1, kappa = 1/500, nu = D+2, Lambda = 0.01 I, alpha = 1."""
     return dict(mu0=np.full(D, 6.0), kappa=1.0 / 500, nu=float(D + 2), Lambda=0.01 * np.eye(D), alpha=1.0)
+
+
+def gmm_mixing(N, D, K_true, seed, pair_dist=2.5, min_dist=6.0, box=12.0):
+    """The mixing-regime twin of `gmm`: K_true unit-covariance components in PAIRS whose two means lie `pair_dist` apart
+    (pair centres uniform in [0,box]^D at pairwise distance >= min_dist), so that with the true parameters given a Gibbs
+    reassignment changes the item's cluster with probability E[2 p (1 - p)] ~ 0.14 at pair_dist 2.5 (Bayes error 0.106):
+    the sampler keeps moving items for ever, which is what the sequential part of a sweep kernel has to be measured on."""
+    rng = np.random.default_rng(seed)
+    centres, tries = [], 0
+    while len(centres) < (K_true + 1) // 2:
+        m = rng.uniform(0.0, box, size=D)
+        tries += 1
+        if all(np.linalg.norm(m - o) >= min_dist for o in centres):
+            centres.append(m)
+        elif tries > 100000:
+            raise RuntimeError("cannot place the pair centres")
+    means = []
+    for c in centres:
+        u = rng.standard_normal(D)
+        u *= 0.5 * pair_dist / np.linalg.norm(u)
+        means += [c - u, c + u]
+    means = np.stack(means[:K_true])
+    counts = np.full(K_true, N // K_true)
+    counts[: N - counts.sum()] += 1
+    y = np.repeat(np.arange(K_true, dtype=np.int32), counts)
+    X = means[y] + rng.standard_normal((N, D))
+    perm = rng.permutation(N)
+    return X[perm], y[perm]
