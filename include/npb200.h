@@ -109,6 +109,9 @@ npb_status npb_logdensity_sum(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows
 npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, int Kmax, int m_aux, int K0,
 		uint64_t seed, npb_chains **out);
 npb_status npb_chains_destroy(npb_chains *ch);
+/* behaviour switches of a handle (no reference counterpart; the library reads its NPB_* environment defaults once, when a
+ * handle is created).  "d16_path": "auto" | "tc" | "tc2" | "fp32" -- which kernels sweep D = 16, Kmax = 32 chains. */
+npb_status npb_chains_set_option(npb_chains *ch, const char *name, const char *value);
 /* overwrite the state of one chain (used by parity tests and by the single-item seam):
  * z [N] slot ids, K clusters with slot ids, means [K,D], covariances [K,D,D] */
 npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z, int K, const int32_t *slots,

@@ -29,7 +29,7 @@ EXPORTS = [
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
     "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
-    "npb_chains_probe_tile_logdensity",
+    "npb_chains_probe_tile_logdensity", "npb_chains_set_option",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
     L.npb_chains_get_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_consider_max_likelihood.argtypes = [vp, dp, dp]
     L.npb_chains_probe_tile_logdensity.argtypes = [vp, i64, ip, C.POINTER(C.c_float)]
+    L.npb_chains_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -310,6 +311,10 @@ class Chains:
         self.ctx.check(self.ctx._lib.npb_chains_probe_tile_logdensity(self._h, chain, _ip(items32),
                                                                        out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+    def set_option(self, name, value):
+        """behaviour switch of this handle, e.g. ("d16_path", "auto" | "tc" | "tc2" | "fp32")"""
+        self.ctx.check(self.ctx._lib.npb_chains_set_option(self._h, name.encode(), value.encode()))
 
     def update_item(self, item, chain=-1):
         """one NealAlgorithm8::update(membertrix&, {item}) on `chain` (every chain if negative): the single-item seam"""

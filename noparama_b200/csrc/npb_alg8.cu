@@ -182,10 +182,19 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	if (ch->Kmax == 32 && ch->D == 64) key = -64;
 	// D = 16, Kmax = 32: the tensor path of npb_alg8_gemm.cu (2x the FP32-pipe kernel at the headline shape);
 	// NPB_D16_PATH=fp32 selects k_alg8_sweep_tile4 (read at every launch: A/B measurements, tests of both)
-	// (default: the fused kernel of npb_alg8_fused16.cu; NPB_D16_PATH=tc2: round 1's table kernel + race kernel)
+	// D = 16, Kmax = 32: the tensor paths.  k_sweep_tc16 (npb_alg8_fused16.cu, one fused kernel, the density table never leaves
+	// the SM) and round 1's table kernel + race kernel (npb_alg8_gemm.cu) evaluate the same keys and give the same assignments
+	// bit for bit (tests/test_gpu_fused16.py), so the choice is a matter of speed only: the fused kernel runs two chains per SM
+	// and wins while few items move (92 against 101 ms per sweep at the headline shape); the kernel pair runs 55 chains per SM
+	// through its sequential pass and wins in a mixing chain (165 against 370 ms at 15 % moved).  NPB_D16_PATH: unset / auto =
+	// by the moved fraction of the handle's last sweep with statistics (unknown: fused); tc = fused; tc2 = pair; fp32 =
+	// k_alg8_sweep_tile4.
 	if (ch->Kmax == 32 && ch->D == 16) {
-		const char *e = getenv("NPB_D16_PATH");
-		if (!(e && e[0] == 'f')) key = (e && e[0] == 't' && e[1] == 'c' && e[2] == '2') ? -1602 : -1600;
+		const char *e = ch->opt_d16_path;
+		if (e[0] == 'f') key = -16;
+		else if (e[0] == 't' && e[1] == 'c' && e[2] == '2') key = -1602;
+		else if (e[0] == 't') key = -1600;
+		else key = ch->moved_frac_last > 0.01 ? -1602 : -1600;
 	}
 	switch (key) {
 	// pre-pass (state independent, fully parallel): the race key of every (chain, step)'s auxiliary draws; then the sweep
@@ -347,9 +356,9 @@ npb_status npb_launch_tile_probe(npb_chains *ch, int chain, const int32_t *d_ite
 	SweepArgs a = make_args(ch, 0);
 	if (ch->Kmax != 32) return npb_fail(ch->ctx, NPB_E_UNSUPPORTED, "the tile probe covers the Kmax = 32 kernels");
 	if (ch->D == 16) {
-		const char *e = getenv("NPB_D16_PATH");
-		if (e && e[0] == 't' && e[1] == 'c' && e[2] == '2') return npb_launch_tc16_probe(ch, chain, d_items, d_out);
-		if (!(e && e[0] == 'f')) return npb_launch_fused16_probe(ch, chain, d_items, d_out);
+		const char *e = ch->opt_d16_path;
+		if (e[0] == 't' && e[1] == 'c' && e[2] == '2') return npb_launch_tc16_probe(ch, chain, d_items, d_out);
+		if (e[0] != 'f') return npb_launch_fused16_probe(ch, chain, d_items, d_out);
 	}
 	switch (ch->D) {
 	case 64: return npb_launch_gemm64_probe(ch, chain, d_items, d_out);

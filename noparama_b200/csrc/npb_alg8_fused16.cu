@@ -36,6 +36,7 @@ constexpr int F_DW = 8;                         // decision warps, four per chai
 constexpr int F_THREADS = (F_EW + 2 + F_DW) * 32;
 constexpr int F_ASTAGES = 2;
 constexpr int F_DTBUFS = 3;
+constexpr float F_WINDOW = 32.0f;               // log2 units below a step's best density inside which a slot is one of its contenders
 constexpr int F_DTS = 36;                       // row stride of a density tile in floats: [step][36], 32 slots + 4 of padding, so that
                                                 // a lane's 128-bit accesses to its own row are conflict-free (rows 144 bytes apart)
 constexpr int F_DT_FLOATS = G_M * F_DTS;
@@ -49,13 +50,15 @@ constexpr uint32_t F_CHAIN = F_CD + 64 * 8;
 
 struct alignas(16) FChain {
 	float lg[32], lg1[32]; // log2 n_k, log2 (n_k - 1); -inf without (other) members
+	float occf[32];        // 0 with members, -inf without
 	int n[32];
-	unsigned version;      // bumped by every change of the tables above
+	float lgmax;           // upper bound of log2 n_k over the slots
+	unsigned version;      // bumped by every change of the counts
 	unsigned born_mask;    // slots born during this block: their column of every tile is re-evaluated on the CUDA cores
 	unsigned born_seq;
 	int kocc, overflow;
-	int pad;
-	unsigned long long st_cand, st_moved, st_births, st_redo;
+	int pad[2];
+	unsigned long long pad2[4];
 };
 constexpr int F_SMEM = 1024 + F_CHAIN + 2 * sizeof(FChain);
 static_assert(F_SMEM <= 232448, "shared memory of k_sweep_tc16");
@@ -66,7 +69,7 @@ enum { FB_B_FULL = 0, FB_B_EMPTY = 1, FB_A_FULL = 2, FB_A_EMPTY = 4, FB_T_FULL =
 
 template <int M, bool PROBE>
 __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, const PreArgs p) {
-	constexpr bool race = !PROBE;
+	const bool race = !PROBE && p.spec != 2; // (p.spec == 2: measurement switch, table pipeline alone, no decisions)
 	extern __shared__ uint8_t g_smem_raw[];
 	const uint32_t raw = g_smem_u32(g_smem_raw);
 	const uint32_t base = (raw + 1023u) & ~1023u;
@@ -102,8 +105,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		// the token of either chain starts at its first decision warp
 		g_mbar_arrive(bars + 8 * (FB_TOK + 0));
 		g_mbar_arrive(bars + 8 * (FB_TOK + 4));
-		fcs[0].version = 0u;
-		fcs[1].version = 0u;
 	}
 	if (warp == F_EW) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 				g_bulk_g2s(base + F_B, g.Bimg + (size_t)u * 4 * H_BBYTES, (uint32_t)ncc * 2u * H_BBYTES, bars + 8 * FB_B_FULL);
 				for (int t = 0; t < g.ntiles; ++t, ++a_it) {
 					const uint32_t s = a_it % F_ASTAGES, ph = (a_it / F_ASTAGES) & 1u;
-					g_mbar_wait(bars + 8 * (FB_A_EMPTY + s), ph ^ 1u);
+					if (p.flags & 256) g_mbar_wait_sleep(bars + 8 * (FB_A_EMPTY + s), ph ^ 1u, 200);
+					else g_mbar_wait(bars + 8 * (FB_A_EMPTY + s), ph ^ 1u);
 					g_mbar_expect_tx(bars + 8 * (FB_A_FULL + s), H_ASTAGE);
 					g_bulk_g2s(base + F_A + s * H_ASTAGE, g.Aimg + (size_t)t * H_ASTAGE, H_ASTAGE, bars + 8 * (FB_A_FULL + s));
 				}
@@ -187,7 +189,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 				for (int cc = 0; cc < ncc; ++cc, ++ct) {
 					const uint32_t dbuf = ct % F_DTBUFS, dk = ct / F_DTBUFS;
 					float *drow = Dt + dbuf * F_DT_FLOATS + row * F_DTS + eg * 8;
-					if (race) g_mbar_wait(bars + 8 * (FB_DT_FREE + dbuf), (dk & 1u) ^ 1u); // its previous tenant has been decided
+					if (race) { // its previous tenant has been read by the decision warps
+						if (p.flags & 512) g_mbar_wait_sleep(bars + 8 * (FB_DT_FREE + dbuf), (dk & 1u) ^ 1u, 100);
+						else g_mbar_wait(bars + 8 * (FB_DT_FREE + dbuf), (dk & 1u) ^ 1u);
+					}
 #pragma unroll 1
 					for (int h = 0; h < 2; ++h, ++acc_it) {
 						const int hf = cc * 2 + h;
@@ -265,187 +270,276 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		const int dw = warp - (F_EW + 2), cc = dw >> 2, wq = dw & 3;
 		FChain &fcn = fcs[cc];
 		volatile FChain &fc = fcs[cc];
-		const float *lg_t = fcn.lg, *lg1_t = fcn.lg1; // re-read after every barrier (the accesses sit behind memory clobbers)
+		const float *lg_t = fcn.lg, *lg1_t = fcn.lg1, *occ_t = fcn.occf; // re-read after every barrier (memory clobbers)
 		const SweepArgs &a = p.a;
 		const int N = a.N;
 		const uint32_t sweep = a.sweep0 + (uint32_t)p.sw;
 		const int32_t *order = a.scan_order + (size_t)p.sw * N;
 		const uint32_t tok_mine = bars + 8 * (FB_TOK + cc * 4 + wq), tok_next = bars + 8 * (FB_TOK + cc * 4 + ((wq + 1) & 3));
 		uint32_t kt = 0, ct_base = 0;
-		bool hot = false; // my previous sub-tile had to be re-speculated or moved items: the chain is mixing, speculate late
 		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 			const int ncc = min(2, C - 2 * u);
 			if (cc < ncc) {
 				const int chain = 2 * u + cc;
 				const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 				float *thc = a.theta + (size_t)chain * 32 * HPS;
-				const uint32_t *auxc = a.aux_keys + ((size_t)p.sw * C + chain) * N + p.s0;
-				// software pipeline of the step's inputs: item two tiles ahead, old assignment and auxiliary key one tile ahead
-				auto ld_item = [&](int t) -> int { const int sl = t * G_M + wq * 32 + lane; return sl < p.nsteps ? __ldg(order + p.s0 + sl) : 0; };
-				auto ld_z = [&](int t, int it) -> int { const int sl = t * G_M + wq * 32 + lane; return sl < p.nsteps ? (int)__ldcg(a.z + (size_t)it * C + chain) : 0; };
-				auto ld_aux = [&](int t) -> uint32_t { const int sl = t * G_M + wq * 32 + lane; return sl < p.nsteps ? __ldg(auxc + sl) : 0xff800000u; };
-				int item_n = ld_item(0), item_nn = ld_item(1);
-				int zold_n = ld_z(0, item_n);
-				uint32_t auxp_n = ld_aux(0);
+				// the step's inputs, two tiles ahead: old assignment (gathered per block into step order by k_gather_z, so that the
+				// decision warps stream it instead of chasing scan order -> z through DRAM latency) and auxiliary key
+				auto ld_z = [&](int t) -> int { const int sl = t * G_M + wq * 32 + lane; return sl < p.nsteps ? (int)__ldcg(p.zblk + (size_t)chain * p.zstride + sl) : 0; };
+				auto ld_aux = [&](int t) -> uint32_t {
+					const int sl = t * G_M + wq * 32 + lane;
+					return sl < p.nsteps ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + p.s0 + sl) : 0xff800000u;
+				};
+				unsigned acc_cand = 0u, acc_moved = 0u, acc_births = 0u, acc_redo = 0u; // per block: at most 65536 steps x 35
+				int zold_n = ld_z(0), zold_nn = ld_z(1);
+				uint32_t auxp_n = ld_aux(0), auxp_nn = ld_aux(1);
 				for (int t = 0; t < g.ntiles; ++t, ++kt) {
 					const uint32_t ct = ct_base + (uint32_t)(t * ncc + cc);
 					const uint32_t dbuf = ct % F_DTBUFS, dk = ct / F_DTBUFS;
 					float *drow = Dt + dbuf * F_DT_FLOATS + (wq * 32 + lane) * F_DTS; // d_k of my step = drow[k]
 					const int sl0 = t * G_M + wq * 32;  // first step of the sub-tile within the block
 					const bool valid = sl0 + lane < p.nsteps;
-					const int item = item_n, zold = zold_n;
+					const int zold = zold_n;
 					const uint32_t auxp = auxp_n;
-					item_n = item_nn;
-					item_nn = ld_item(t + 2);
-					zold_n = ld_z(t + 1, item_n);
-					auxp_n = ld_aux(t + 1);
+					zold_n = zold_nn;
+					auxp_n = auxp_nn;
+					zold_nn = ld_z(t + 2);
+					auxp_nn = ld_aux(t + 2);
+					auto item_of = [&]() -> int { return valid ? __ldg(order + p.s0 + sl0 + lane) : 0; }; // (rare paths only)
 					const float ak = __uint_as_float(auxp);
 					const uint32_t T = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)(p.s0 + sl0) * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
 					int znew = zold;
-					// speculation state of my step
-					int w = -1;
-					float keyw = -INFINITY, keyr = -INFINITY;
-					bool uncertain = false;
-					unsigned seq_seen = 0u;
-					bool patched = false;
-
-					auto key_exact = [&](int k) -> float {
-						const float lgx = (k == zold) ? lg1_t[k] : lg_t[k];
-						return lgx > -INFINITY ? (drow[k] + g_noise(T, (uint32_t)lane, (uint32_t)k)) + lgx : -INFINITY;
+					// ---- the step's CONTENDERS, independent of the member counts: the occupied slots whose density lies within
+					// F_WINDOW of the best, with their race noise already added (base = d + noise); every other slot's key is
+					// below rbound + log2 n_max whatever its noise.  At most three are kept; a step with more is evaluated in full.
+					unsigned cpack = 0u;  // slots c0 < c1 < c2, five bits each
+					int ncache = 0;       // 0..3, or 4 = not representable: full evaluation
+					float base0 = -INFINITY, base1 = -INFINITY, base2 = -INFINITY, rbound = -INFINITY;
+					unsigned seq_early = 0u;
+					bool noise0 = false;  // base0 already carries its slot's noise
+					float d[32];          // my step's row of the density tile: the tile buffer goes back to the epilogue at once
+					auto dsel = [&](int k) -> float { // d[k], k known at run time (rare paths only)
+						float r = d[0];
+#pragma unroll
+						for (int kk = 1; kk < 32; ++kk) r = kk == k ? d[kk] : r;
+						return r;
 					};
-					// columns of the slots born during this block: the operand images predate them
-					auto patch = [&]() {
-						unsigned bm = fc.born_mask;
-						if (bm == 0u) return;
-						const unsigned seq = fc.born_seq;
-						if (patched && seq == seq_seen) return;
-						while (bm) {
-							const int k = __ffs(bm) - 1;
-							bm &= bm - 1;
-							const float l = g_stream_density<HD>(thc + (size_t)k * HPS, a.X + (size_t)item * HD);
-							if (valid) drow[k] = l;
-						}
-						patched = true;
-						seq_seen = seq;
+					auto dput = [&](int k, float x) {
+#pragma unroll
+						for (int kk = 0; kk < 32; ++kk) d[kk] = kk == k ? x : d[kk];
 					};
-					// pass (1): winner, its key, and a bound of every other key, with the counts as they stand
-					auto speculate = [&]() {
+					// from_tile: first call of a tile (the row is read from the shared tile, the contenders' densities too, then the
+					// buffer is released); otherwise the row already sits in registers (a slot was born since)
+					auto contenders = [&](const bool from_tile) {
 						asm volatile("" ::: "memory");
-						float nk[32];
-						float pm = -INFINITY; // running maximum of the keys with the slot index in the five low mantissa bits
-#pragma unroll
-						for (int q = 0; q < 8; ++q) {
-							const float4 d = *reinterpret_cast<const float4 *>(drow + 4 * q);
-							const float4 l = *reinterpret_cast<const float4 *>(lg_t + 4 * q);
-							nk[4 * q + 0] = d.x + l.x; nk[4 * q + 1] = d.y + l.y; nk[4 * q + 2] = d.z + l.z; nk[4 * q + 3] = d.w + l.w;
+						if (p.flags & 32) { // measurement only: no scan at all
+							seq_early = fc.born_seq;
+							if (from_tile) { d[0] = drow[0]; __syncwarp(); if (lane == 0) g_mbar_arrive(bars + 8 * (FB_DT_FREE + dbuf)); }
+							cpack = (unsigned)zold; ncache = 1; base0 = 0.0f; noise0 = false; rbound = -1e30f;
+							return;
 						}
+						seq_early = fc.born_seq;
+						if (from_tile) {
 #pragma unroll
-						for (int k = 0; k < 32; ++k) pm = fmaxf(pm, __uint_as_float((__float_as_uint(nk[k]) & ~31u) | (uint32_t)k));
-						// the pivot: (about) the best noiseless key -- any slot would do, the best one prunes the most
-						const int k1 = (int)(__float_as_uint(pm) & 31u);
-						float best = key_exact(k1);
-						w = best > -INFINITY ? k1 : -1;
-						const float thr = best - (G_NOISE_CAP + 1.0f);
-						unsigned need = 0u;
-						float m2p = -INFINITY;
-#pragma unroll
-						for (int k = 0; k < 32; ++k) {
-							const bool nd = nk[k] >= thr && nk[k] > -INFINITY;
-							need |= nd ? (1u << k) : 0u;
-							m2p = nd ? m2p : fmaxf(m2p, nk[k]);
-						}
-						need &= ~(1u << k1);
-						keyr = m2p + (G_NOISE_CAP + 1.0f);
-						while (need) {
-							const int k = __ffs(need) - 1;
-							need &= need - 1;
-							const float key = key_exact(k);
-							if (key > best || (key == best && key > -INFINITY && k < w)) {
-								keyr = fmaxf(keyr, best);
-								best = key;
-								w = k;
-							} else {
-								keyr = fmaxf(keyr, key);
+							for (int q = 0; q < 8; ++q) {
+								const float4 x = *reinterpret_cast<const float4 *>(drow + 4 * q);
+								d[4 * q + 0] = x.x; d[4 * q + 1] = x.y; d[4 * q + 2] = x.z; d[4 * q + 3] = x.w;
 							}
 						}
-						if (ak > best) { // slots win ties against the auxiliary draws
-							keyr = fmaxf(keyr, best);
-							w = 32 + (int)(auxp & 3u);
-							keyw = ak;
-						} else {
-							keyr = fmaxf(keyr, ak);
-							keyw = best;
+						{ // columns of the slots born during this block: the operand images predate them
+							unsigned bm = fc.born_mask;
+							while (bm) {
+								const int k = __ffs(bm) - 1;
+								bm &= bm - 1;
+								const float l = g_stream_density<HD>(thc + (size_t)k * HPS, a.X + (size_t)item_of() * HD);
+								dput(k, l);
+								if (from_tile) drow[k] = l;
+							}
 						}
-						uncertain = false;
+						unsigned near = 0u;
+						float lim = -INFINITY;
+						bool scanned = false;
+						const float dsel_own = from_tile ? drow[zold] : dsel(zold);
+						if (valid && !(p.flags & 4)) {
+							// the usual case first: the item's own slot is the only contender -- one pass with its density as pivot
+							const float vown = dsel_own + occ_t[zold];
+							const float plim = vown - F_WINDOW;
+							unsigned pn = 0u;
+#pragma unroll
+							for (int q = 0; q < 8; ++q) {
+								const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q); // 0 with members, -inf without
+								pn |= (d[4 * q + 0] + o.x >= plim) ? (1u << (4 * q + 0)) : 0u;
+								pn |= (d[4 * q + 1] + o.y >= plim) ? (1u << (4 * q + 1)) : 0u;
+								pn |= (d[4 * q + 2] + o.z >= plim) ? (1u << (4 * q + 2)) : 0u;
+								pn |= (d[4 * q + 3] + o.w >= plim) ? (1u << (4 * q + 3)) : 0u;
+							}
+							if (vown > -INFINITY && pn == (1u << zold)) { // nothing else within the window of it: it is the best, alone
+								near = pn;
+								lim = plim;
+								scanned = true;
+							}
+						}
+						if (!scanned) {
+							// two passes over the row, so that only the row itself stays in registers
+							float m1 = -INFINITY;
+#pragma unroll
+							for (int q = 0; q < 8; ++q) {
+								const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q); // 0 with members, -inf without
+								m1 = fmaxf(m1, fmaxf(fmaxf(d[4 * q + 0] + o.x, d[4 * q + 1] + o.y), fmaxf(d[4 * q + 2] + o.z, d[4 * q + 3] + o.w)));
+							}
+							lim = m1 - F_WINDOW;
+#pragma unroll
+							for (int q = 0; q < 8; ++q) {
+								const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q);
+								const float v0 = d[4 * q + 0] + o.x, v1 = d[4 * q + 1] + o.y, v2 = d[4 * q + 2] + o.z, v3 = d[4 * q + 3] + o.w;
+								near |= (v0 >= lim && v0 > -INFINITY) ? (1u << (4 * q + 0)) : 0u;
+								near |= (v1 >= lim && v1 > -INFINITY) ? (1u << (4 * q + 1)) : 0u;
+								near |= (v2 >= lim && v2 > -INFINITY) ? (1u << (4 * q + 2)) : 0u;
+								near |= (v3 >= lim && v3 > -INFINITY) ? (1u << (4 * q + 3)) : 0u;
+							}
+						}
+						rbound = lim + (G_NOISE_CAP + 1.0f);
+						ncache = min(__popc(near), 4);
+						cpack = 0u;
+						float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+						int c0 = 0, c1 = 0, c2 = 0;
+						if (ncache <= 3) {
+							if (near) { c0 = __ffs(near) - 1; near &= near - 1; }
+							if (near) { c1 = __ffs(near) - 1; near &= near - 1; }
+							if (near) { c2 = __ffs(near) - 1; }
+							cpack = (unsigned)c0 | ((unsigned)c1 << 5) | ((unsigned)c2 << 10);
+							if (from_tile) { d0 = drow[c0]; d1 = drow[c1]; d2 = drow[c2]; }
+							else { d0 = dsel(c0); d1 = dsel(c1); d2 = dsel(c2); }
+						}
+						if (from_tile) { // the tile buffer back to the epilogue warps
+							__syncwarp();
+							if (lane == 0) g_mbar_arrive(bars + 8 * (FB_DT_FREE + dbuf));
+						}
+						// the contenders' race noise; a sole contender's is drawn only if its pick ever needs it (pick())
+						base0 = d0;
+						base1 = base2 = -INFINITY;
+						noise0 = (ncache >= 2 && ncache <= 3) || ((p.flags & 8) && ncache == 1);
+						if (noise0) base0 = d0 + g_noise(T, (uint32_t)lane, (uint32_t)c0);
+						if (ncache >= 2 && ncache <= 3) base1 = d1 + g_noise(T, (uint32_t)lane, (uint32_t)c1);
+						if (ncache == 3) base2 = d2 + g_noise(T, (uint32_t)lane, (uint32_t)c2);
+					};
+					// the step's pick from its contenders with the member counts as they stand; unsafe: the bound on the other
+					// slots does not clear the winner's key (or there were too many contenders): full evaluation at its turn
+					int w = zold;
+					bool unsafe = false;
+					unsigned v_pick = 0u;
+					auto pick = [&]() {
+						asm volatile("" ::: "memory");
+						v_pick = fc.version;
+						__threadfence_block();
+						if (ncache == 1 && !noise0) {
+							// one contender: it wins whatever its noise if even the lowest noise clears the other slots' bound and the
+							// auxiliary key; only otherwise is the noise drawn (once)
+							const int c = (int)(cpack & 31u);
+							const float lgx = (c == zold) ? lg1_t[c] : lg_t[c];
+							const float lb = (base0 + G_NOISE_FLOOR) + lgx;
+							if (lb > rbound + fc.lgmax + 1.0f && lb > ak + 1.0f) {
+								w = c;
+								unsafe = false;
+								return;
+							}
+							base0 = base0 + g_noise(T, (uint32_t)lane, (uint32_t)c);
+							noise0 = true;
+						}
+						float best = -INFINITY;
+						int ws = -1;
+#pragma unroll
+						for (int i = 0; i < 3; ++i) {
+							const int c = (int)((cpack >> (5 * i)) & 31u);
+							const float bs = i == 0 ? base0 : (i == 1 ? base1 : base2);
+							const float lgx = (c == zold) ? lg1_t[c] : lg_t[c];
+							const float key = (i < ncache && lgx > -INFINITY) ? bs + lgx : -INFINITY;
+							if (key > best) { best = key; ws = c; } // slots in ascending order: the lower one keeps a tie
+						}
+						if (ak > best) { // slots win ties against the auxiliary draws
+							best = ak;
+							ws = 32 + (int)(auxp & 3u);
+						}
+						w = ws;
+						unsafe = ncache > 3 || !(best > rbound + fc.lgmax);
 					};
 
-					g_mbar_wait(bars + 8 * (FB_DT_FULL + dbuf), dk & 1u);
-					unsigned v_spec = 0xffffffffu;
-					if (p.spec && t > 0 && !hot) {
-						v_spec = fc.version;
-						__threadfence_block();
-						patch();
-						speculate();
+					// (polled with a back-off: on power-capped boards eight spinning warps cost the epilogue clocks -- 96 -> 84 ms per
+					// sweep on one box, no difference on another)
+					if (p.flags & 64) g_mbar_wait(bars + 8 * (FB_DT_FULL + dbuf), dk & 1u);
+					else g_mbar_wait_sleep(bars + 8 * (FB_DT_FULL + dbuf), dk & 1u, 200);
+					if (t > 0) { // (the first tile of a unit waits for the chain's state)
+						contenders(true);
+						if (p.spec) pick();
 					}
-					g_mbar_wait(tok_mine, kt & 1u);
+					if (p.flags & 128) g_mbar_wait_sleep(tok_mine, kt & 1u, 100);
+					else if (!(p.flags & 16)) g_mbar_wait(tok_mine, kt & 1u); // (flag 16: measurement only, wrong once an item moves)
 					// ---- the chain's state is mine from here to the hand-over ----
 					if (t == 0 && wq == 0) { // a new unit: this chain's counts
 						const int n = a.counts[(size_t)chain * 32 + lane];
 						fc.n[lane] = n;
-						fc.lg[lane] = n > 0 ? fast_lg2((float)n) : -INFINITY;
+						const float l0 = n > 0 ? fast_lg2((float)n) : -INFINITY;
+						fc.lg[lane] = l0;
 						fc.lg1[lane] = n > 1 ? fast_lg2((float)(n - 1)) : -INFINITY;
+						fc.occf[lane] = n > 0 ? 0.0f : -INFINITY;
 						const int ko = __popc(__ballot_sync(0xffffffffu, n > 0));
+						const float lm = redux_max_f32(l0);
 						if (lane == 0) {
 							fc.kocc = ko;
+							fc.lgmax = lm;
 							fc.overflow = 0;
 							fc.born_mask = 0u;
 							fc.born_seq = 0u;
-							fc.st_cand = fc.st_moved = fc.st_births = fc.st_redo = 0ull;
 							fc.version = fc.version + 1u;
 						}
 					}
 					__syncwarp();
 					__threadfence_block();
 					bool redo = false;
-					if (!p.spec) {
-						patch();
-						uncertain = valid; // every step evaluated in full, in order
-						w = zold;
-					} else if (fc.version != v_spec) {
-						patch();
-						speculate();
-						redo = v_spec != 0xffffffffu;
+					if (t == 0) {
+						contenders(true);
+						if (p.spec) pick();
+					} else if (fc.born_seq != seq_early) { // a slot was born since: its column, and it may be a contender
+						redo = true;
+						contenders(false);
+						if (p.spec) pick();
+					} else if (p.spec && fc.version != v_pick) { // counts changed since the early pick: the contenders' keys again
+						redo = true;
+						pick();
 					}
-					// ---- pass (2): validation in step order ----
+					if (!p.spec) unsafe = true; // every step evaluated in full, in order
+					// ---- validation in step order ----
 					unsigned live = __ballot_sync(0xffffffffu, valid);
 					int kocc = fc.kocc;
-					unsigned long long cand = 0ull;
-					unsigned n_moved = 0u, n_births = 0u;
+					unsigned cand = 0u, n_moved = 0u, n_births = 0u;
 					while (true) {
-						const unsigned pend = __ballot_sync(0xffffffffu, valid && (uncertain || w != zold)) & live;
+						const unsigned pend = __ballot_sync(0xffffffffu, valid && (unsafe || w != zold)) & live;
 						const int jn = pend ? __ffs(pend) - 1 : 32;
 						{
 							const unsigned below = jn >= 32 ? live : (live & ((1u << jn) - 1u));
-							cand += (unsigned long long)(__popc(below) * (kocc + M));
+							cand += (unsigned)(__popc(below) * (kocc + M));
 							live &= ~below;
 						}
 						if (!pend) break;
 						const int zo = __shfl_sync(0xffffffffu, zold, jn);
-						if (__shfl_sync(0xffffffffu, (int)uncertain, jn)) {
+						if (__shfl_sync(0xffffffffu, (int)unsafe, jn)) {
 							// full evaluation of step jn: lane = slot (the sequential sampler's step)
 							const float akj = __shfl_sync(0xffffffffu, ak, jn);
 							const uint32_t auxj = __shfl_sync(0xffffffffu, auxp, jn);
 							const float lgx = (lane == zo) ? lg1_t[lane] : lg_t[lane];
-							const float key = lgx > -INFINITY ? (Dt[dbuf * F_DT_FLOATS + (wq * 32 + jn) * F_DTS + lane] + g_noise(T, (uint32_t)jn, (uint32_t)lane)) + lgx : -INFINITY;
+							float dj = 0.0f; // d[lane] of step jn: its row sits in lane jn's registers
+#pragma unroll
+							for (int kk = 0; kk < 32; ++kk) {
+								const float x = __shfl_sync(0xffffffffu, d[kk], jn);
+								dj = lane == kk ? x : dj;
+							}
+							const float key = lgx > -INFINITY ? (dj + g_noise(T, (uint32_t)jn, (uint32_t)lane)) + lgx : -INFINITY;
 							const float top = fmaxf(redux_max_f32(key), akj);
 							const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
 							const int ws = bal ? __ffs(bal) - 1 : 32 + (int)(auxj & 3u);
-							const float rest = redux_max_f32(lane == ws ? -INFINITY : key);
 							if (lane == jn) {
 								w = ws;
-								keyw = top;
-								keyr = bal ? fmaxf(rest, akj) : rest;
-								uncertain = false;
+								unsafe = false;
 							}
 							if (ws == zo) continue; // it stays
 						}
@@ -456,7 +550,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 						const bool born = wj >= 32;
 						int b = wj;
 						bool ovf = false;
-						cand += (unsigned long long)(kocc + M - (died ? 1 : 0));
+						cand += (unsigned)(kocc + M - (died ? 1 : 0));
 						if (born) {
 							// np_neal_algorithm8.cpp:136-145: the lowest free slot takes theta' of the winning auxiliary draw
 							const unsigned fb = __ballot_sync(0xffffffffu, fc.n[lane] - (lane == zo ? 1 : 0) <= 0);
@@ -466,7 +560,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 						n_moved++;
 						if (!ovf) {
 							if (born) {
-								const int bitem = __shfl_sync(0xffffffffu, item, jn);
+								const int bitem = __shfl_sync(0xffffffffu, item_of(), jn);
 								g_birth_theta<HD>(ph, a.prior, a.Xw + (size_t)bitem * HD, __ldg(a.Xwn + bitem), (uint32_t)(p.s0 + sl0 + jn), sweep, wj - 32, lane,
 										thc + (size_t)b * HPS);
 								__threadfence();
@@ -481,11 +575,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 									fc.n[zo] = na;
 									fc.lg[zo] = na > 0 ? fast_lg2((float)na) : -INFINITY;
 									fc.lg1[zo] = na > 1 ? fast_lg2((float)(na - 1)) : -INFINITY;
+									if (na <= 0) fc.occf[zo] = -INFINITY;
 									nb = fc.n[b] + 1;
 								}
 								fc.n[b] = nb;
-								fc.lg[b] = fast_lg2((float)nb);
+								const float lb = fast_lg2((float)nb);
+								fc.lg[b] = lb;
 								fc.lg1[b] = nb > 1 ? fast_lg2((float)(nb - 1)) : -INFINITY;
+								fc.occf[b] = 0.0f;
+								fc.lgmax = fmaxf(fc.lgmax, lb); // never lowered within a unit: an upper bound is all it has to be
 								if (born) {
 									p.dirty[(size_t)chain * 32 + b] = 1;
 									fc.born_mask = fc.born_mask | (1u << b);
@@ -496,67 +594,51 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 							}
 							kocc += (born ? 1 : 0) - (died ? 1 : 0);
 							__syncwarp();
-							if (born) { // the newborn slot's column for my step
-								const float l = g_stream_density<HD>(thc + (size_t)b * HPS, a.X + (size_t)item * HD);
-								if (valid) drow[b] = l;
-								seq_seen = fc.born_seq;
-							}
+							__threadfence_block();
 							if (lane == jn) znew = b;
-							// later steps: only the keys of the two slots whose counts changed can alter their pick
-							if (lane > jn && valid && !uncertain) {
-#pragma unroll 1
-								for (int e = 0; e < 2; ++e) {
-									const int k = e == 0 ? zo : b;
-									if (e == 1 && b == zo) break;
-									const float kn = key_exact(k);
-									if (w == k) {
-										keyw = kn;
-										if (!(kn > keyr)) uncertain = true;
-									} else if (kn > keyw || (kn == keyw && kn > -INFINITY && k < w)) {
-										keyr = keyw;
-										w = k;
-										keyw = kn;
-									} else {
-										keyr = fmaxf(keyr, kn);
-									}
-								}
+							if (born) {
+								// the newborn slot's column for my step; it may be anybody's contender: the rest of the sub-tile in full
+								const float l = g_stream_density<HD>(thc + (size_t)b * HPS, a.X + (size_t)item_of() * HD);
+								dput(b, l);
+								seq_early = fc.born_seq;
+								unsafe = true;
+							} else if (lane > jn && valid && !unsafe) {
+								pick(); // the counts of two slots changed: the contenders' keys again
 							}
 						} else if (lane == 0) {
 							fc.overflow = 1;
 						}
 						if (lane == jn) { // final
 							w = zold;
-							uncertain = false;
+							unsafe = false;
 						}
 						live &= ~(1u << jn);
 					}
-					if (valid && znew != zold) a.z[(size_t)item * C + chain] = (npb_z_t)znew;
-					hot = redo || n_moved != 0u;
-					if (lane == 0) {
-						fc.kocc = kocc;
-						fc.st_cand = fc.st_cand + cand;
-						fc.st_moved = fc.st_moved + n_moved;
-						fc.st_births = fc.st_births + n_births;
-						if (hot) fc.st_redo = fc.st_redo + 1ull;
+					if (valid && znew != zold) a.z[(size_t)item_of() * C + chain] = (npb_z_t)znew;
+					// statistics: per warp, flushed once per unit
+					acc_cand += cand;
+					acc_moved += n_moved;
+					acc_births += n_births;
+					acc_redo += (redo || n_moved) ? 1u : 0u;
+					if (n_moved) {
+						if (lane == 0) fc.kocc = kocc;
+						__syncwarp();
 					}
-					__syncwarp();
 					if (t == g.ntiles - 1 && wq == 3) { // the unit's last sub-tile: the chain's state back to memory
 						a.counts[(size_t)chain * 32 + lane] = fc.n[lane];
 						if (lane == 0) {
 							a.kocc[chain] = fc.kocc;
 							if (fc.overflow) a.overflow[chain] = 1;
-							a.st[(size_t)chain * 4 + 0] += fc.st_cand;
-							a.st[(size_t)chain * 4 + 1] += fc.st_moved;
-							a.st[(size_t)chain * 4 + 2] += fc.st_births;
-							a.st[(size_t)chain * 4 + 3] += fc.st_redo;
 						}
 					}
 					__threadfence_block();
-					__syncwarp();
-					if (lane == 0) {
-						g_mbar_arrive(tok_next);
-						g_mbar_arrive(bars + 8 * (FB_DT_FREE + dbuf));
-					}
+					if (lane == 0) g_mbar_arrive(tok_next);
+				}
+				if (lane == 0) { // (four warps per chain: atomics)
+					atomicAdd(a.st + (size_t)chain * 4 + 0, (unsigned long long)acc_cand);
+					atomicAdd(a.st + (size_t)chain * 4 + 1, (unsigned long long)acc_moved);
+					atomicAdd(a.st + (size_t)chain * 4 + 2, (unsigned long long)acc_births);
+					atomicAdd(a.st + (size_t)chain * 4 + 3, (unsigned long long)acc_redo);
 				}
 			}
 			ct_base += (uint32_t)(g.ntiles * ncc);
@@ -568,6 +650,26 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		g_tc_fence_after();
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Assignments of one block of steps, gathered from the item-major z[N][C] into step order, chain-major: zblk[c][s] =
+// z[order[s]][c].  A tile of 32 steps x 64 chains goes through shared memory: reads are 128-byte runs of one item's row,
+// writes 64-byte runs of one chain's steps.  The decision warps then stream their inputs (coalesced, L2-resident) instead
+// of chasing scan order -> z through DRAM latency once per tile.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_z(const int32_t *order, int nsteps, const npb_z_t *z, int C, npb_z_t *zblk, int zstride) {
+	__shared__ npb_z_t tile[32][64 + 2];
+	const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+	const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6; // 64 x 4
+	for (int r = ty; r < 32; r += 4) {
+		const int s = s0 + r;
+		if (s < nsteps && c0 + tx < C) tile[r][tx] = z[(size_t)order[s] * C + c0 + tx];
+	}
+	__syncthreads();
+	const int sx = threadIdx.x & 31, cy = threadIdx.x >> 5; // 32 x 8
+	for (int c = cy; c < 64; c += 8)
+		if (s0 + sx < nsteps && c0 + c < C) zblk[(size_t)(c0 + c) * zstride + s0 + sx] = tile[sx][c];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -616,17 +718,26 @@ npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a) {
 	g.L = nullptr;
 	g.C = (int)C;
 	g.BS = BS + 32;
+	if (!ch->g_zblk) NPB_CUDA_OK(cudaMalloc((void **)&ch->g_zblk, C * (size_t)BS * sizeof(npb_z_t)));
 	PreArgs p;
 	memset(&p, 0, sizeof(p));
 	p.a = a;
 	p.BS = BS + 32;
 	p.dirty = ch->g_dirty;
-	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();
+	p.zblk = ch->g_zblk;
+	p.zstride = BS;
+	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return e ? atoi(e) : 1; }();
+	p.flags = [] { const char *e = getenv("NPB_F16_FLAGS"); return e ? atoi(e) : 0; }(); // A/B measurement switches (results unchanged)
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
 		for (int s0 = 0; s0 < N; s0 += BS, ++ch->g_k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;
 			s = npb_tc16_pre_block(ch, a.scan_order + (size_t)sw * N + s0, nsteps, 0);
 			if (s != NPB_OK) return s;
+			{
+				dim3 gg((unsigned)((nsteps + 31) / 32), (unsigned)((C + 63) / 64));
+				k_gather_z<<<gg, 256, 0, ctx->stream>>>(a.scan_order + (size_t)sw * N + s0, nsteps, a.z, (int)C, ch->g_zblk, BS);
+				NPB_CUDA_OK(cudaGetLastError());
+			}
 			g.ntiles = (nsteps + G_M - 1) / G_M;
 			p.sw = sw;
 			p.s0 = s0;

@@ -299,6 +299,10 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 	ch->K0 = K0;
 	ch->D = ds->D;
 	ch->seed = seed;
+	{ // behaviour switches are read once, here (npb_chains_set_option changes them afterwards)
+		const char *e = getenv("NPB_D16_PATH");
+		strncpy(ch->opt_d16_path, e && e[0] ? e : "auto", sizeof(ch->opt_d16_path) - 1);
+	}
 	const size_t PS = npb_ps(ds->D);
 	cudaError_t e;
 	if ((e = cudaMalloc((void **)&ch->z, (size_t)ds->N * n_chains * sizeof(npb_z_t))) != cudaSuccess ||
@@ -318,6 +322,17 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	*out = ch;
 	return NPB_OK;
+}
+
+npb_status npb_chains_set_option(npb_chains *ch, const char *name, const char *value) {
+	if (!ch || !name || !value) return NPB_E_BAD_ARG;
+	if (!strcmp(name, "d16_path")) {
+		if (strcmp(value, "auto") && strcmp(value, "tc") && strcmp(value, "tc2") && strcmp(value, "fp32"))
+			return npb_fail(ch->ctx, NPB_E_BAD_ARG, "d16_path: auto | tc | tc2 | fp32");
+		strncpy(ch->opt_d16_path, value, sizeof(ch->opt_d16_path) - 1);
+		return NPB_OK;
+	}
+	return npb_fail(ch->ctx, NPB_E_BAD_ARG, "unknown option");
 }
 
 npb_status npb_chains_destroy(npb_chains *ch) {
@@ -353,6 +368,7 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->g_L) cudaFree(ch->g_L);
 	if (ch->g_dirty) cudaFree(ch->g_dirty);
 	if (ch->g_born) cudaFree(ch->g_born);
+	if (ch->g_zblk) cudaFree(ch->g_zblk);
 	delete ch;
 	return NPB_OK;
 }
@@ -466,6 +482,7 @@ static npb_status collect_stats(npb_chains *ch, const std::vector<unsigned long 
 	}
 	stats->mean_K = sumK / (double)C;
 	stats->kernel_ms = ms;
+	if (sampler == NPB_ALG8 && stats->reassignments > 0) ch->moved_frac_last = (double)stats->moved / (double)stats->reassignments;
 	return NPB_OK;
 }
 

@@ -46,6 +46,8 @@ struct npb_chains {
 	int Kmax = 0, m_aux = 0, K0 = 0, D = 0;
 	uint64_t seed = 0;
 	uint32_t sweep = 0;         // sweeps done so far (Philox counter / scan-order key)
+	char opt_d16_path[8] = {0}; // NPB_D16_PATH as read when the handle was created (auto / tc / tc2 / fp32)
+	double moved_frac_last = -1.0; // moved / reassignments of the last Algorithm 8 launch whose statistics were read; -1 unknown
 	uint32_t init_epoch = 0;    // initialisations from given parameters so far (distinct initial assignments per call)
 	uint32_t item_calls = 0;    // single-item updates so far (Philox counter of npb_chain_update_alg8)
 	npb_z_t *z = nullptr;       // [N, C] item-major
@@ -86,6 +88,7 @@ struct npb_chains {
 	int g_bs = 0;                  // steps per block
 	uint32_t g_k = 0;              // blocks consumed so far (parity selects the table / born-mask buffer)
 	uint32_t *g_born = nullptr;    // [2][C] slots born during block k (buffer k & 1)
+	npb_z_t *g_zblk = nullptr;     // [C][g_bs] fused D = 16 kernel: assignments of the current block's items, in step order
 };
 
 struct SweepArgs {

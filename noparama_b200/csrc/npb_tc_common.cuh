@@ -41,6 +41,9 @@ struct PreArgs {
 	uint32_t *born_out;        // [C] slots born during this block
 	int BS, sw, s0, nsteps;
 	int spec;                  // 0: sequential pass only (NPB_D64_SPEC=0; the result must not depend on it)
+	int flags;                 // k_sweep_tc16: measurement switches
+	const npb_z_t *zblk;       // [C][zstride] k_sweep_tc16: old assignments of the block's steps, in step order (k_gather_z)
+	int zstride;
 	uint8_t *dirty;            // [C * 32] k_sweep_tc16: set for a slot born during the block (its operand image is stale)
 };
 
@@ -86,6 +89,24 @@ __device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
 			"WAIT_DONE:\n\t"
 			"}\n" ::"r"(bar), "r"(parity)
 			: "memory");
+}
+// the same wait with a back-off between polls: for warps whose wait is long and whose polling would take issue slots from the
+// warps they wait for
+__device__ __forceinline__ void g_mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+	uint32_t done = 0;
+	while (true) {
+		asm volatile(
+				"{\n\t"
+				".reg .pred p;\n\t"
+				"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+				"selp.u32 %0, 1, 0, p;\n\t"
+				"}\n"
+				: "=r"(done)
+				: "r"(bar), "r"(parity)
+				: "memory");
+		if (done) break;
+		__nanosleep(ns);
+	}
 }
 __device__ __forceinline__ void g_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
@@ -205,6 +226,7 @@ static __device__ __noinline__ void g_birth_theta64(const Philox &ph, const Prio
 }
 
 #define G_NOISE_CAP 20.0f
+#define G_NOISE_FLOOR -6.0f
 // race noise of (tile, step j, slot k): a counter hash instead of a per-lane stream, so that the step-parallel pass
 // (lane = step) and the sequential pass (lane = slot) of g_consume_chain draw the same number for the same candidate
 __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
@@ -213,10 +235,12 @@ __device__ __forceinline__ float g_noise(uint32_t T, uint32_t j, uint32_t k) {
 	x *= 0x85EBCA6Bu;
 	x ^= x >> 13;
 	x *= 0xC2B2AE35u;
-	// capped: -log2 E > 20 has probability 1.4e-6 per candidate and would shift a pick probability by less than that -- below
-	// what FP32 log-densities resolve (1e-6 relative of ~1e2) -- and the cap is what lets the speculative pass exclude slots
-	// without drawing their noise
-	return fminf(neg_lg2_exp1_open(x), G_NOISE_CAP);
+	// capped above: -log2 E > 20 has probability 1.4e-6 per candidate and would shift a pick probability by less than that -- below
+	// what FP32 log-densities resolve (1e-6 relative of ~1e2) -- and the cap is what lets the speculative passes exclude slots
+	// without drawing their noise.  Bounded below: the 32-bit uniform gives E' <= 32, i.e. noise >= -5, except for the single
+	// word that rounds 1 - v to 0 (probability 2^-32 per draw), whose -inf becomes G_NOISE_FLOOR: a slot's key is then never
+	// below its noiseless key + G_NOISE_FLOOR, which lets a sole contender be decided without drawing its noise at all.
+	return fmaxf(fminf(neg_lg2_exp1_open(x), G_NOISE_CAP), G_NOISE_FLOOR);
 }
 
 // D-generic front ends of the rare paths of the race: density of one (item, slot) from the slot table in global memory, and

@@ -57,10 +57,7 @@ def test_fused_equals_kernel_pair_and_sequential(npb, ctx, env, chains, N, block
     ds = npb.Dataset(ctx, X)
     out = {}
     for name, path, spec in (("fused", None, "1"), ("fused_seq", None, "0"), ("pair", "tc2", "1")):
-        if path:
-            env["NPB_D16_PATH"] = path
-        else:
-            env.pop("NPB_D16_PATH", None)
+        env["NPB_D16_PATH"] = path or "tc"  # (unset = auto: by the moved fraction of the last sweep; here each path on its own)
         env["NPB_D64_SPEC"] = spec
         mc, z, tot = run(npb, ctx, ds, means, chains, 3, seed=11)
         out[name] = (z, tot)
@@ -80,6 +77,7 @@ def test_fused_births_deaths_and_batching(npb, ctx, oracle, env):
     """Reference regime (K0 = 8 prior clusters, births and deaths): invariants, metric parity, and identical results with
     the speculation on or off and however the sweeps are batched into launches."""
     env["NPB_D16_BLOCK"] = "128"
+    env["NPB_D16_PATH"] = "tc"
     N = 1000 + 13
     X, y = syn.gmm(N, D, 4, 116)
     ds = npb.Dataset(ctx, X)
@@ -112,6 +110,7 @@ def test_fused_births_deaths_and_batching(npb, ctx, oracle, env):
 def test_fused_probe_unfolded_epilogue(npb, ctx, oracle, env):
     """The density table of the fused kernel against the oracle, including slots whose mean lies far outside the data (a
     prior-born cluster): their offsets do not fit the folded FP16 columns and take the long epilogue."""
+    env["NPB_D16_PATH"] = "tc"
     rng = np.random.default_rng(3)
     X, y = syn.gmm(4000, D, 8, 216)
     ds = npb.Dataset(ctx, X)
@@ -135,4 +134,21 @@ def test_fused_probe_unfolded_epilogue(npb, ctx, oracle, env):
     print("max relative error: near slots %.2e, far slots %.2e" % (err[~far[occ]].max(), err[far[occ]].max()))
     assert occ.sum() >= 30 and err.max() < 1e-5
     ch.close()
+    ds.close()
+
+
+def test_auto_path_switches_without_changing_results(npb, ctx, env):
+    """NPB_D16_PATH unset: the handle picks the fused kernel or the kernel pair by the moved fraction of its last sweep;
+    without births the assignments are the same whichever it took."""
+    X, y, means = overlapping(2000, 6, 9)
+    ds = npb.Dataset(ctx, X)
+    out = []
+    for path in (None, "tc", "tc2"):
+        if path:
+            env["NPB_D16_PATH"] = path
+        else:
+            env.pop("NPB_D16_PATH", None)
+        mc, z, tot = run(npb, ctx, ds, means, 9, 4, seed=5, per_launch=1)
+        out.append((z, tot["moved"]))
+    assert out[0][1] > 0 and all(np.array_equal(out[0][0], z) and mv == out[0][1] for z, mv in out[1:])
     ds.close()

@@ -1,4 +1,5 @@
-"""GPU (pytest -m gpu): D = 16 on the tensor path of npb_alg8_gemm.cu (NPB_D16_PATH=tc): FP16x3 density tables + race kernel."""
+"""GPU (pytest -m gpu): D = 16 on the kernel pair of npb_alg8_gemm.cu (NPB_D16_PATH=tc2): FP16x3 density tables + race kernel
+(round 1's tensor path; the handle's default now also uses the fused kernel of npb_alg8_fused16.cu, tests/test_gpu_fused16.py)."""
 import os
 
 import numpy as np
@@ -15,7 +16,7 @@ D = 16
 def env():
     keys = ("NPB_D16_PATH", "NPB_D16_BLOCK", "NPB_D16_EPI", "NPB_D64_SPEC", "NPB_D16_AUX")
     saved = {k: os.environ.get(k) for k in keys}
-    os.environ.pop("NPB_D16_PATH", None)  # the tensor path is the default at D = 16, Kmax = 32
+    os.environ["NPB_D16_PATH"] = "tc2"
     yield os.environ
     for k, v in saved.items():
         if v is None:
