@@ -117,6 +117,8 @@ static SweepArgs make_args(npb_chains *ch, int n_sweeps) {
 	a.seed = ch->seed;
 	a.scan_order = ch->scan_order;
 	a.aux_keys = ch->aux_keys;
+	a.aux_max = ch->aux_max;
+	a.aux_groups = (int)((ch->ds->N + 31) / 32);
 	a.prior = npb_prior_dev(ch->ctx, ch->m_aux);
 	return a;
 }
@@ -244,6 +246,7 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 		size_t cap = ((size_t)4 << 30) / per_sweep;
 		ch->aux_cap = (int)(cap < 1 ? 1 : (cap > (size_t)ch->scan_cap ? (size_t)ch->scan_cap : cap));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->aux_keys, per_sweep * ch->aux_cap));
+		if (ch->D == 16) NPB_CUDA_OK(cudaMalloc((void **)&ch->aux_max, (size_t)ch->aux_cap * ch->C * ((ch->ds->N + 31) / 32) * sizeof(float)));
 	}
 	const int per_launch = ch->aux_keys ? ch->aux_cap : ch->scan_cap;
 	for (int done = 0; done < n_sweeps;) {

@@ -34,6 +34,7 @@ namespace {
 constexpr int F_EW = 8;                         // epilogue warps
 constexpr int F_DW = 8;                         // decision warps, four per chain
 constexpr int F_THREADS = (F_EW + 2 + F_DW) * 32;
+constexpr int F_W_MMA = F_EW + F_DW, F_W_PROD = F_EW + F_DW + 1; // warps 0-7 epilogue, 8-15 decision, 16 MMA, 17 copies
 constexpr int F_ASTAGES = 2;
 constexpr int F_DTBUFS = 3;
 constexpr float F_WINDOW = 32.0f;               // log2 units below a step's best density inside which a slot is one of its contenders
@@ -60,11 +61,106 @@ struct alignas(16) FChain {
 	int pad[2];
 	unsigned long long pad2[4];
 };
-constexpr int F_SMEM = 1024 + F_CHAIN + 2 * sizeof(FChain);
+constexpr uint32_t F_RING = F_CHAIN + 2 * sizeof(FChain);  // [8 decision warps][3 stages][80 bytes]: 32 old assignments + the group's auxiliary maximum
+constexpr int F_RING_STAGE = 80;
+constexpr int F_SMEM = 1024 + F_RING + F_DW * 3 * F_RING_STAGE;
 static_assert(F_SMEM <= 232448, "shared memory of k_sweep_tc16");
 
 // barrier slots (8 bytes each) in the misc area
 enum { FB_B_FULL = 0, FB_B_EMPTY = 1, FB_A_FULL = 2, FB_A_EMPTY = 4, FB_T_FULL = 6, FB_T_EMPTY = 8, FB_DT_FULL = 10, FB_DT_FREE = 13, FB_TOK = 16 };
+}
+
+
+__device__ __forceinline__ void f_tmem_wait_ld1(float (&a)[32]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 32; ++i) asm volatile("" : "+f"(a[i]));
+}
+
+// log2-densities of two slots from 32 accumulator columns (16 per slot): c2 - |y|^2, the offsets folded into the GEMM
+// (FOLDED) or added here.  q0 .. q3 accumulate columns i = 0, 1, 2, 3 mod 4 -- as two packed accumulators (FFMA2) in the
+// folded form -- and are summed (q0 + q1) + (q2 + q3): the same operations in the same order as k_density_tc16.
+template <bool FOLDED>
+__device__ __forceinline__ void f_density2(const float (&v)[32], const float *ec, const float2 *cd, float &o0, float &o1) {
+#pragma unroll
+	for (int hh = 0; hh < 2; ++hh) {
+		const int o = hh * 16;
+		float r;
+		if (FOLDED) {
+			const float2 c = cd[hh];
+			f32x2_t qa = f2_pack(0.0f, 0.0f), qb = qa;
+#pragma unroll
+			for (int i = 0; i < 16; i += 4) {
+				const f32x2_t va = f2_pack(v[o + i], v[o + i + 1]), vb = f2_pack(v[o + i + 2], v[o + i + 3]);
+				qa = f2_fma(va, va, qa);
+				qb = f2_fma(vb, vb, qb);
+			}
+			float q0, q1, q2, q3;
+			f2_unpack(qa, q0, q1);
+			f2_unpack(qb, q2, q3);
+			r = fmaf(-c.y, (q0 + q1) + (q2 + q3), c.x);
+		} else {
+			const float *e = ec + hh * H_CONST;
+			const float dsc = e[HD + 1];
+			float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+			for (int i = 0; i < 16; i += 4) {
+				const float4 nb = *reinterpret_cast<const float4 *>(e + i);
+				const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
+						    a3 = fmaf(v[o + i + 3], dsc, nb.w);
+				q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
+			}
+			r = e[HD] - ((q0 + q1) + (q2 + q3));
+		}
+		if (hh == 0) o0 = r; else o1 = r;
+	}
+}
+
+// One epilogue thread's share of an accumulator: 128 columns = 8 slots of its step, two tcgen05.ld of 32 columns per wait (a
+// staggered order -- one load in flight while the previous one is reduced -- measured 9 % slower); the accumulator goes back to
+// the MMA warp as soon as the last columns have landed.
+template <bool PROBE>
+__device__ __forceinline__ void f_epilogue_half(uint32_t taddr, const float2 *cd, float *drow, float *Lrow, uint32_t bar_t_empty) {
+	float o[8];
+#pragma unroll
+	for (int pp = 0; pp < 2; ++pp) {
+		float v0[32], v1[32];
+		g_tmem_ld32_nowait(taddr + pp * 64u, v0);
+		g_tmem_ld32_nowait(taddr + pp * 64u + 32u, v1);
+		g_tmem_wait_ld(v0, v1);
+		if (pp == 1) { // the accumulator is in registers: hand the buffer back before the arithmetic
+			g_tc_fence_before();
+			g_mbar_arrive(bar_t_empty);
+		}
+		f_density2<true>(v0, nullptr, cd + 4 * pp, o[4 * pp + 0], o[4 * pp + 1]);
+		f_density2<true>(v1, nullptr, cd + 4 * pp + 2, o[4 * pp + 2], o[4 * pp + 3]);
+		*reinterpret_cast<float4 *>(drow + 4 * pp) = make_float4(o[4 * pp], o[4 * pp + 1], o[4 * pp + 2], o[4 * pp + 3]);
+	}
+	if (PROBE) { // parity probe: the table as the decision warps see it
+		*reinterpret_cast<float4 *>(Lrow) = make_float4(o[0], o[1], o[2], o[3]);
+		*reinterpret_cast<float4 *>(Lrow + 4) = make_float4(o[4], o[5], o[6], o[7]);
+	}
+}
+// the same for a half-chain with a slot whose offsets stayed out of the GEMM (a mean far outside the data): rare, so a rolled
+// loop over pairs of slots -- compact code rather than fast code
+template <bool PROBE>
+__device__ __noinline__ void f_epilogue_half_unfolded(uint32_t taddr, const float *ec, float *drow, float *Lrow, uint32_t bar_t_empty) {
+#pragma unroll 1
+	for (int pr = 0; pr < 4; ++pr) {
+		float v[32], o0, o1;
+		g_tmem_ld32(taddr + 32u * pr, v);
+		if (pr == 3) {
+			g_tc_fence_before();
+			g_mbar_arrive(bar_t_empty);
+		}
+		f_density2<false>(v, ec + 2 * pr * H_CONST, nullptr, o0, o1);
+		drow[2 * pr] = o0;
+		drow[2 * pr + 1] = o1;
+		if (PROBE) {
+			Lrow[2 * pr] = o0;
+			Lrow[2 * pr + 1] = o1;
+		}
+	}
 }
 
 template <int M, bool PROBE>
@@ -84,7 +180,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 	const int C = g.C;
 	const int n_units = (C + 1) / 2;
 
-	if (warp == F_EW + 1 && lane == 0) {
+	if (warp == F_W_PROD && lane == 0) {
 		g_mbar_init(bars + 8 * FB_B_FULL, 1);
 		g_mbar_init(bars + 8 * FB_B_EMPTY, 1);
 		for (int s = 0; s < F_ASTAGES; ++s) {
@@ -106,7 +202,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		g_mbar_arrive(bars + 8 * (FB_TOK + 0));
 		g_mbar_arrive(bars + 8 * (FB_TOK + 4));
 	}
-	if (warp == F_EW) {
+	if (warp == F_W_MMA) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(g_smem_u32(tmem_slot)) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
@@ -115,7 +211,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 	g_tc_fence_after();
 	const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
-	if (warp == F_EW + 1) {
+	if (warp == F_W_PROD) {
 		// ===================== bulk-copy producer =====================
 		if (lane == 0) {
 			uint32_t a_it = 0, unit_it = 0;
@@ -134,7 +230,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 			}
 		}
 		__syncwarp();
-	} else if (warp == F_EW) {
+	} else if (warp == F_W_MMA) {
 		// ===================== MMA issue (one thread) =====================
 		if (lane == 0) {
 			constexpr uint32_t ID256 = g_idesc(G_M, 256);
@@ -196,67 +292,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 #pragma unroll 1
 					for (int h = 0; h < 2; ++h, ++acc_it) {
 						const int hf = cc * 2 + h;
-						const bool folded = (folded_mask >> hf) & 1u;
 						const uint32_t buf = acc_it & 1u;
 						g_mbar_wait(bars + 8 * (FB_T_FULL + buf), (acc_it >> 1) & 1u);
 						g_tc_fence_after();
 						const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u + eg * 128;
-						const float *ecb = econst + (hf * H_NS + eg * 8) * H_CONST;
-						const float2 *cdb = cd2 + hf * H_NS + eg * 8;
-#pragma unroll
-						for (int pp = 0; pp < 4; pp += 2) {
-							float v0[32], v1[32];
-							g_tmem_ld32_nowait(taddr + pp * 32u, v0);
-							g_tmem_ld32_nowait(taddr + (pp + 1) * 32u, v1);
-							g_tmem_wait_ld(v0, v1);
-							if (pp == 2) { // the accumulator is in registers: hand the buffer back before the arithmetic
-								g_tc_fence_before();
-								g_mbar_arrive(bars + 8 * (FB_T_EMPTY + buf));
-							}
-							float out[4];
-							if (folded) {
-#pragma unroll
-								for (int hh = 0; hh < 4; ++hh) {
-									const float(&v)[32] = hh < 2 ? v0 : v1;
-									const int o = (hh & 1) * 16;
-									const float2 cd = cdb[pp * 2 + hh];
-									// q0 .. q3 as two packed accumulators (FFMA2): (q0, q1) and (q2, q3), same sums as the scalar form
-									f32x2_t qa = f2_pack(0.0f, 0.0f), qb = qa;
-#pragma unroll
-									for (int i = 0; i < 16; i += 4) {
-										const f32x2_t va = f2_pack(v[o + i], v[o + i + 1]), vb = f2_pack(v[o + i + 2], v[o + i + 3]);
-										qa = f2_fma(va, va, qa);
-										qb = f2_fma(vb, vb, qb);
-									}
-									float q0, q1, q2, q3;
-									f2_unpack(qa, q0, q1);
-									f2_unpack(qb, q2, q3);
-									out[hh] = fmaf(-cd.y, (q0 + q1) + (q2 + q3), cd.x);
-								}
-							} else {
-#pragma unroll
-								for (int hh = 0; hh < 4; ++hh) {
-									const float(&v)[32] = hh < 2 ? v0 : v1;
-									const int o = (hh & 1) * 16;
-									const float *ec = ecb + (pp * 2 + hh) * H_CONST;
-									const float dsc = ec[HD + 1];
-									float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
-#pragma unroll
-									for (int i = 0; i < 16; i += 4) {
-										const float4 nb = *reinterpret_cast<const float4 *>(ec + i);
-										const float a0 = fmaf(v[o + i], dsc, nb.x), a1 = fmaf(v[o + i + 1], dsc, nb.y), a2 = fmaf(v[o + i + 2], dsc, nb.z),
-												    a3 = fmaf(v[o + i + 3], dsc, nb.w);
-										q0 = fmaf(a0, a0, q0); q1 = fmaf(a1, a1, q1); q2 = fmaf(a2, a2, q2); q3 = fmaf(a3, a3, q3);
-									}
-									out[hh] = ec[HD] - ((q0 + q1) + (q2 + q3));
-								}
-							}
-							*reinterpret_cast<float4 *>(drow + h * H_NS + pp * 2) = make_float4(out[0], out[1], out[2], out[3]);
-							if (PROBE) { // parity probe: the table as the decision warps see it
-								float *Lrow = g.L + ((size_t)(2 * u + cc) * g.BS + (size_t)t * G_M + row) * 32 + h * H_NS + eg * 8 + pp * 2;
-								*reinterpret_cast<float4 *>(Lrow) = make_float4(out[0], out[1], out[2], out[3]);
-							}
-						}
+						float *Lrow = PROBE ? g.L + ((size_t)(2 * u + cc) * g.BS + (size_t)t * G_M + row) * 32 + h * H_NS + eg * 8 : nullptr;
+						if ((folded_mask >> hf) & 1u) f_epilogue_half<PROBE>(taddr, cd2 + hf * H_NS + eg * 8, drow + h * H_NS, Lrow, bars + 8 * (FB_T_EMPTY + buf));
+						else f_epilogue_half_unfolded<PROBE>(taddr, econst + (hf * H_NS + eg * 8) * H_CONST, drow + h * H_NS, Lrow, bars + 8 * (FB_T_EMPTY + buf));
 					}
 					if (race) {
 						__syncwarp();
@@ -267,7 +309,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		}
 	} else if (race) {
 		// ===================== decision: four warps per chain, lane = step of a 32-step sub-tile =====================
-		const int dw = warp - (F_EW + 2), cc = dw >> 2, wq = dw & 3;
+		const int dw = warp - F_EW, cc = dw >> 2, wq = dw & 3;
 		FChain &fcn = fcs[cc];
 		volatile FChain &fc = fcs[cc];
 		const float *lg_t = fcn.lg, *lg1_t = fcn.lg1, *occ_t = fcn.occf; // re-read after every barrier (memory clobbers)
@@ -283,162 +325,69 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 				const int chain = 2 * u + cc;
 				const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 				float *thc = a.theta + (size_t)chain * 32 * HPS;
-				// the step's inputs, two tiles ahead: old assignment (gathered per block into step order by k_gather_z, so that the
-				// decision warps stream it instead of chasing scan order -> z through DRAM latency) and auxiliary key
-				auto ld_z = [&](int t) -> int { const int sl = t * G_M + wq * 32 + lane; return sl < p.nsteps ? (int)__ldcg(p.zblk + (size_t)chain * p.zstride + sl) : 0; };
-				auto ld_aux = [&](int t) -> uint32_t {
-					const int sl = t * G_M + wq * 32 + lane;
-					return sl < p.nsteps ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + p.s0 + sl) : 0xff800000u;
+				// The step's inputs, two tiles ahead, by cp.async into a three-stage ring in shared memory (as register prefetches
+				// ptxas spilled them straight after the load, i.e. waited for them): the old assignments, gathered per block into
+				// step order by k_gather_z so that they stream instead of chasing scan order -> z through DRAM latency, and the
+				// largest auxiliary key of the sub-tile's 32 steps (k_aux_keys writes it next to the keys: it settles nearly every
+				// step, a step's own key is fetched only when the maximum does not).
+				const float *auxg = a.aux_max + ((size_t)p.sw * C + chain) * a.aux_groups + (p.s0 >> 5);
+				const npb_z_t *zrow = p.zblk + (size_t)chain * p.zstride;
+				uint8_t *ring = gen + F_RING + dw * (3 * F_RING_STAGE);
+				auto prefetch = [&](int t) {
+					const int sl = t * G_M + wq * 32;
+					if (t < g.ntiles) {
+						const uint32_t dst = g_smem_u32(ring + (t % 3) * F_RING_STAGE);
+						if (lane < 16 && sl + 2 * lane < p.nsteps)
+							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * lane), "l"(zrow + sl + 2 * lane) : "memory");
+						if (lane == 16 && sl < p.nsteps)
+							asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 64u), "l"(auxg + (sl >> 5)) : "memory");
+					}
+					asm volatile("cp.async.commit_group;" ::: "memory");
 				};
+				prefetch(0);
+				prefetch(1);
 				unsigned acc_cand = 0u, acc_moved = 0u, acc_births = 0u, acc_redo = 0u; // per block: at most 65536 steps x 35
-				int zold_n = ld_z(0), zold_nn = ld_z(1);
-				uint32_t auxp_n = ld_aux(0), auxp_nn = ld_aux(1);
 				for (int t = 0; t < g.ntiles; ++t, ++kt) {
 					const uint32_t ct = ct_base + (uint32_t)(t * ncc + cc);
 					const uint32_t dbuf = ct % F_DTBUFS, dk = ct / F_DTBUFS;
 					float *drow = Dt + dbuf * F_DT_FLOATS + (wq * 32 + lane) * F_DTS; // d_k of my step = drow[k]
 					const int sl0 = t * G_M + wq * 32;  // first step of the sub-tile within the block
 					const bool valid = sl0 + lane < p.nsteps;
-					const int zold = zold_n;
-					const uint32_t auxp = auxp_n;
-					zold_n = zold_nn;
-					auxp_n = auxp_nn;
-					zold_nn = ld_z(t + 2);
-					auxp_nn = ld_aux(t + 2);
+					prefetch(t + 2);
+					asm volatile("cp.async.wait_group 2;" ::: "memory");
+					__syncwarp();
+					const int zold = valid ? (int)reinterpret_cast<const npb_z_t *>(ring + (t % 3) * F_RING_STAGE)[lane] : 0;
+					const float akmax = sl0 < p.nsteps ? *reinterpret_cast<const float *>(ring + (t % 3) * F_RING_STAGE + 64) : -INFINITY;
+					auto aux_of = [&]() -> uint32_t { // my step's packed auxiliary key (rare paths only)
+						return valid ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + p.s0 + sl0 + lane) : 0xff800000u;
+					};
 					auto item_of = [&]() -> int { return valid ? __ldg(order + p.s0 + sl0 + lane) : 0; }; // (rare paths only)
-					const float ak = __uint_as_float(auxp);
 					const uint32_t T = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)(p.s0 + sl0) * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
 					int znew = zold;
 					// ---- the step's CONTENDERS, independent of the member counts: the occupied slots whose density lies within
 					// F_WINDOW of the best, with their race noise already added (base = d + noise); every other slot's key is
 					// below rbound + log2 n_max whatever its noise.  At most three are kept; a step with more is evaluated in full.
 					unsigned cpack = 0u;  // slots c0 < c1 < c2, five bits each
-					int ncache = 0;       // 0..3, or 4 = not representable: full evaluation
+					int ncache = 4;       // 0..3, or 4 = not representable: full evaluation
 					float base0 = -INFINITY, base1 = -INFINITY, base2 = -INFINITY, rbound = -INFINITY;
-					unsigned seq_early = 0u;
 					bool noise0 = false;  // base0 already carries its slot's noise
 					float d[32];          // my step's row of the density tile: the tile buffer goes back to the epilogue at once
-					auto dsel = [&](int k) -> float { // d[k], k known at run time (rare paths only)
-						float r = d[0];
-#pragma unroll
-						for (int kk = 1; kk < 32; ++kk) r = kk == k ? d[kk] : r;
-						return r;
-					};
-					auto dput = [&](int k, float x) {
-#pragma unroll
-						for (int kk = 0; kk < 32; ++kk) d[kk] = kk == k ? x : d[kk];
-					};
-					// from_tile: first call of a tile (the row is read from the shared tile, the contenders' densities too, then the
-					// buffer is released); otherwise the row already sits in registers (a slot was born since)
-					auto contenders = [&](const bool from_tile) {
-						asm volatile("" ::: "memory");
-						if (p.flags & 32) { // measurement only: no scan at all
-							seq_early = fc.born_seq;
-							if (from_tile) { d[0] = drow[0]; __syncwarp(); if (lane == 0) g_mbar_arrive(bars + 8 * (FB_DT_FREE + dbuf)); }
-							cpack = (unsigned)zold; ncache = 1; base0 = 0.0f; noise0 = false; rbound = -1e30f;
-							return;
-						}
-						seq_early = fc.born_seq;
-						if (from_tile) {
-#pragma unroll
-							for (int q = 0; q < 8; ++q) {
-								const float4 x = *reinterpret_cast<const float4 *>(drow + 4 * q);
-								d[4 * q + 0] = x.x; d[4 * q + 1] = x.y; d[4 * q + 2] = x.z; d[4 * q + 3] = x.w;
-							}
-						}
-						{ // columns of the slots born during this block: the operand images predate them
-							unsigned bm = fc.born_mask;
-							while (bm) {
-								const int k = __ffs(bm) - 1;
-								bm &= bm - 1;
-								const float l = g_stream_density<HD>(thc + (size_t)k * HPS, a.X + (size_t)item_of() * HD);
-								dput(k, l);
-								if (from_tile) drow[k] = l;
-							}
-						}
-						unsigned near = 0u;
-						float lim = -INFINITY;
-						bool scanned = false;
-						const float dsel_own = from_tile ? drow[zold] : dsel(zold);
-						if (valid && !(p.flags & 4)) {
-							// the usual case first: the item's own slot is the only contender -- one pass with its density as pivot
-							const float vown = dsel_own + occ_t[zold];
-							const float plim = vown - F_WINDOW;
-							unsigned pn = 0u;
-#pragma unroll
-							for (int q = 0; q < 8; ++q) {
-								const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q); // 0 with members, -inf without
-								pn |= (d[4 * q + 0] + o.x >= plim) ? (1u << (4 * q + 0)) : 0u;
-								pn |= (d[4 * q + 1] + o.y >= plim) ? (1u << (4 * q + 1)) : 0u;
-								pn |= (d[4 * q + 2] + o.z >= plim) ? (1u << (4 * q + 2)) : 0u;
-								pn |= (d[4 * q + 3] + o.w >= plim) ? (1u << (4 * q + 3)) : 0u;
-							}
-							if (vown > -INFINITY && pn == (1u << zold)) { // nothing else within the window of it: it is the best, alone
-								near = pn;
-								lim = plim;
-								scanned = true;
-							}
-						}
-						if (!scanned) {
-							// two passes over the row, so that only the row itself stays in registers
-							float m1 = -INFINITY;
-#pragma unroll
-							for (int q = 0; q < 8; ++q) {
-								const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q); // 0 with members, -inf without
-								m1 = fmaxf(m1, fmaxf(fmaxf(d[4 * q + 0] + o.x, d[4 * q + 1] + o.y), fmaxf(d[4 * q + 2] + o.z, d[4 * q + 3] + o.w)));
-							}
-							lim = m1 - F_WINDOW;
-#pragma unroll
-							for (int q = 0; q < 8; ++q) {
-								const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q);
-								const float v0 = d[4 * q + 0] + o.x, v1 = d[4 * q + 1] + o.y, v2 = d[4 * q + 2] + o.z, v3 = d[4 * q + 3] + o.w;
-								near |= (v0 >= lim && v0 > -INFINITY) ? (1u << (4 * q + 0)) : 0u;
-								near |= (v1 >= lim && v1 > -INFINITY) ? (1u << (4 * q + 1)) : 0u;
-								near |= (v2 >= lim && v2 > -INFINITY) ? (1u << (4 * q + 2)) : 0u;
-								near |= (v3 >= lim && v3 > -INFINITY) ? (1u << (4 * q + 3)) : 0u;
-							}
-						}
-						rbound = lim + (G_NOISE_CAP + 1.0f);
-						ncache = min(__popc(near), 4);
-						cpack = 0u;
-						float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-						int c0 = 0, c1 = 0, c2 = 0;
-						if (ncache <= 3) {
-							if (near) { c0 = __ffs(near) - 1; near &= near - 1; }
-							if (near) { c1 = __ffs(near) - 1; near &= near - 1; }
-							if (near) { c2 = __ffs(near) - 1; }
-							cpack = (unsigned)c0 | ((unsigned)c1 << 5) | ((unsigned)c2 << 10);
-							if (from_tile) { d0 = drow[c0]; d1 = drow[c1]; d2 = drow[c2]; }
-							else { d0 = dsel(c0); d1 = dsel(c1); d2 = dsel(c2); }
-						}
-						if (from_tile) { // the tile buffer back to the epilogue warps
-							__syncwarp();
-							if (lane == 0) g_mbar_arrive(bars + 8 * (FB_DT_FREE + dbuf));
-						}
-						// the contenders' race noise; a sole contender's is drawn only if its pick ever needs it (pick())
-						base0 = d0;
-						base1 = base2 = -INFINITY;
-						noise0 = (ncache >= 2 && ncache <= 3) || ((p.flags & 8) && ncache == 1);
-						if (noise0) base0 = d0 + g_noise(T, (uint32_t)lane, (uint32_t)c0);
-						if (ncache >= 2 && ncache <= 3) base1 = d1 + g_noise(T, (uint32_t)lane, (uint32_t)c1);
-						if (ncache == 3) base2 = d2 + g_noise(T, (uint32_t)lane, (uint32_t)c2);
-					};
-					// the step's pick from its contenders with the member counts as they stand; unsafe: the bound on the other
-					// slots does not clear the winner's key (or there were too many contenders): full evaluation at its turn
 					int w = zold;
-					bool unsafe = false;
-					unsigned v_pick = 0u;
+					bool unsafe = true;
+					unsigned v_pick = 0xffffffffu;
+					// the pick from the contenders with the member counts as they stand; unsafe: the bound on the other slots does
+					// not clear the winner's key (or there were too many contenders): full evaluation at the step's turn
 					auto pick = [&]() {
 						asm volatile("" ::: "memory");
 						v_pick = fc.version;
 						__threadfence_block();
 						if (ncache == 1 && !noise0) {
 							// one contender: it wins whatever its noise if even the lowest noise clears the other slots' bound and the
-							// auxiliary key; only otherwise is the noise drawn (once)
+							// auxiliary keys; only otherwise is the noise drawn (once)
 							const int c = (int)(cpack & 31u);
 							const float lgx = (c == zold) ? lg1_t[c] : lg_t[c];
 							const float lb = (base0 + G_NOISE_FLOOR) + lgx;
-							if (lb > rbound + fc.lgmax + 1.0f && lb > ak + 1.0f) {
+							if (lb > rbound + fc.lgmax + 1.0f && lb > akmax + 1.0f) {
 								w = c;
 								unsafe = false;
 								return;
@@ -456,9 +405,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 							const float key = (i < ncache && lgx > -INFINITY) ? bs + lgx : -INFINITY;
 							if (key > best) { best = key; ws = c; } // slots in ascending order: the lower one keeps a tie
 						}
-						if (ak > best) { // slots win ties against the auxiliary draws
-							best = ak;
-							ws = 32 + (int)(auxp & 3u);
+						if (!(best > akmax)) { // slots win ties against the auxiliary draws
+							const uint32_t auxp = aux_of();
+							const float ak = __uint_as_float(auxp);
+							if (ak > best) {
+								best = ak;
+								ws = 32 + (int)(auxp & 3u);
+							}
 						}
 						w = ws;
 						unsafe = ncache > 3 || !(best > rbound + fc.lgmax);
@@ -468,46 +421,114 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 					// sweep on one box, no difference on another)
 					if (p.flags & 64) g_mbar_wait(bars + 8 * (FB_DT_FULL + dbuf), dk & 1u);
 					else g_mbar_wait_sleep(bars + 8 * (FB_DT_FULL + dbuf), dk & 1u, 200);
-					if (t > 0) { // (the first tile of a unit waits for the chain's state)
-						contenders(true);
-						if (p.spec) pick();
-					}
-					if (p.flags & 128) g_mbar_wait_sleep(tok_mine, kt & 1u, 100);
-					else if (!(p.flags & 16)) g_mbar_wait(tok_mine, kt & 1u); // (flag 16: measurement only, wrong once an item moves)
-					// ---- the chain's state is mine from here to the hand-over ----
-					if (t == 0 && wq == 0) { // a new unit: this chain's counts
-						const int n = a.counts[(size_t)chain * 32 + lane];
-						fc.n[lane] = n;
-						const float l0 = n > 0 ? fast_lg2((float)n) : -INFINITY;
-						fc.lg[lane] = l0;
-						fc.lg1[lane] = n > 1 ? fast_lg2((float)(n - 1)) : -INFINITY;
-						fc.occf[lane] = n > 0 ? 0.0f : -INFINITY;
-						const int ko = __popc(__ballot_sync(0xffffffffu, n > 0));
-						const float lm = redux_max_f32(l0);
-						if (lane == 0) {
-							fc.kocc = ko;
-							fc.lgmax = lm;
-							fc.overflow = 0;
-							fc.born_mask = 0u;
-							fc.born_seq = 0u;
-							fc.version = fc.version + 1u;
+					bool redo = false;
+					// two passes of one body: the row and its contenders before the token (after it, with the chain's state
+					// just loaded, on the first tile of a unit), the token in between
+#pragma unroll 1
+					for (int phase = 0; phase < 2; ++phase) {
+						if (phase == (t == 0 ? 1 : 0)) {
+							asm volatile("" ::: "memory");
+#pragma unroll
+							for (int q = 0; q < 8; ++q) {
+								const float4 x = *reinterpret_cast<const float4 *>(drow + 4 * q);
+								d[4 * q + 0] = x.x; d[4 * q + 1] = x.y; d[4 * q + 2] = x.z; d[4 * q + 3] = x.w;
+							}
+							// (a slot born during this block: its column of the tile predates it; the steps are evaluated in full,
+							// where a born slot's density comes from the CUDA cores)
+							if (p.spec && fc.born_mask == 0u) {
+								unsigned near = 0u;
+								float lim = -INFINITY;
+								bool scanned = false;
+								if (valid) {
+									// the usual case first: the item's own slot is the only contender -- one pass with its density as pivot
+									const float vown = drow[zold] + occ_t[zold];
+									const float plim = vown - F_WINDOW;
+									unsigned pn = 0u;
+#pragma unroll
+									for (int q = 0; q < 8; ++q) {
+										const float4 o = *reinterpret_cast<const float4 *>(occ_t + 4 * q); // 0 with members, -inf without
+										pn |= (d[4 * q + 0] + o.x >= plim) ? (1u << (4 * q + 0)) : 0u;
+										pn |= (d[4 * q + 1] + o.y >= plim) ? (1u << (4 * q + 1)) : 0u;
+										pn |= (d[4 * q + 2] + o.z >= plim) ? (1u << (4 * q + 2)) : 0u;
+										pn |= (d[4 * q + 3] + o.w >= plim) ? (1u << (4 * q + 3)) : 0u;
+									}
+									if (vown > -INFINITY && pn == (1u << zold)) { // nothing else within the window of it: the best, alone
+										near = pn;
+										lim = plim;
+										scanned = true;
+									}
+								}
+								if (!scanned) { // two passes over the row in the tile (rolled: code size matters more than this path's speed)
+									float m1 = -INFINITY;
+#pragma unroll 1
+									for (int k = 0; k < 32; ++k) m1 = fmaxf(m1, drow[k] + occ_t[k]);
+									lim = m1 - F_WINDOW;
+#pragma unroll 1
+									for (int k = 0; k < 32; ++k) {
+										const float vk = drow[k] + occ_t[k];
+										near |= (vk >= lim && vk > -INFINITY) ? (1u << k) : 0u;
+									}
+								}
+								rbound = lim + (G_NOISE_CAP + 1.0f);
+								ncache = min(__popc(near), 4);
+								if (ncache <= 3) {
+									int c0 = 0, c1 = 0, c2 = 0;
+									if (near) { c0 = __ffs(near) - 1; near &= near - 1; }
+									if (near) { c1 = __ffs(near) - 1; near &= near - 1; }
+									if (near) { c2 = __ffs(near) - 1; }
+									cpack = (unsigned)c0 | ((unsigned)c1 << 5) | ((unsigned)c2 << 10);
+									// the contenders' race noise; a sole contender's is drawn only if its pick ever needs it (pick())
+									base0 = drow[c0];
+									noise0 = ncache >= 2 || ((p.flags & 8) && ncache == 1);
+									if (noise0) base0 += g_noise(T, (uint32_t)lane, (uint32_t)c0);
+									if (ncache >= 2) base1 = drow[c1] + g_noise(T, (uint32_t)lane, (uint32_t)c1);
+									if (ncache == 3) base2 = drow[c2] + g_noise(T, (uint32_t)lane, (uint32_t)c2);
+								}
+							}
+							__syncwarp(); // the tile buffer back to the epilogue warps
+							if (lane == 0) g_mbar_arrive(bars + 8 * (FB_DT_FREE + dbuf));
+							if (p.spec && fc.born_mask == 0u) pick();
+						}
+						if (phase == 0) {
+							if (!(p.flags & 16)) g_mbar_wait(tok_mine, kt & 1u); // (flag 16: measurement only, wrong once an item moves)
+							// ---- the chain's state is mine from here to the hand-over ----
+							if (t == 0 && wq == 0) { // a new unit: this chain's counts
+								const int n = a.counts[(size_t)chain * 32 + lane];
+								fc.n[lane] = n;
+								const float l0 = n > 0 ? fast_lg2((float)n) : -INFINITY;
+								fc.lg[lane] = l0;
+								fc.lg1[lane] = n > 1 ? fast_lg2((float)(n - 1)) : -INFINITY;
+								fc.occf[lane] = n > 0 ? 0.0f : -INFINITY;
+								const int ko = __popc(__ballot_sync(0xffffffffu, n > 0));
+								const float lm = redux_max_f32(l0);
+								if (lane == 0) {
+									fc.kocc = ko;
+									fc.lgmax = lm;
+									fc.overflow = 0;
+									fc.born_mask = 0u;
+									fc.version = fc.version + 1u;
+								}
+							}
+							__syncwarp();
+							__threadfence_block();
 						}
 					}
-					__syncwarp();
-					__threadfence_block();
-					bool redo = false;
-					if (t == 0) {
-						contenders(true);
-						if (p.spec) pick();
-					} else if (fc.born_seq != seq_early) { // a slot was born since: its column, and it may be a contender
-						redo = true;
-						contenders(false);
-						if (p.spec) pick();
-					} else if (p.spec && fc.version != v_pick) { // counts changed since the early pick: the contenders' keys again
-						redo = true;
+					// The hand-over is the chain's serial path, four hops per tile: a sub-tile whose early pick still stands (no slot
+					// born, no count changed since) and keeps every item where it is passes the token on before any bookkeeping.
+					if (p.spec && t > 0 && !(t == g.ntiles - 1 && wq == 3) && fc.born_mask == 0u && fc.version == v_pick &&
+							__ballot_sync(0xffffffffu, valid && (unsafe || w != zold)) == 0u) {
+						const int kocc = fc.kocc;
+						if (lane == 0) g_mbar_arrive(tok_next);
+						acc_cand += (unsigned)(__popc(__ballot_sync(0xffffffffu, valid)) * (kocc + M));
+						continue;
+					}
+					const unsigned born_now = fc.born_mask;
+					if (!p.spec || born_now != 0u) {
+						unsafe = true; // every step evaluated in full, in order
+					} else if (v_pick == 0xffffffffu || fc.version != v_pick) { // counts changed since the early pick: the contenders' keys again
+						redo = t > 0;
 						pick();
 					}
-					if (!p.spec) unsafe = true; // every step evaluated in full, in order
 					// ---- validation in step order ----
 					unsigned live = __ballot_sync(0xffffffffu, valid);
 					int kocc = fc.kocc;
@@ -524,14 +545,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 						const int zo = __shfl_sync(0xffffffffu, zold, jn);
 						if (__shfl_sync(0xffffffffu, (int)unsafe, jn)) {
 							// full evaluation of step jn: lane = slot (the sequential sampler's step)
-							const float akj = __shfl_sync(0xffffffffu, ak, jn);
-							const uint32_t auxj = __shfl_sync(0xffffffffu, auxp, jn);
+							const uint32_t auxj = __shfl_sync(0xffffffffu, aux_of(), jn);
+							const float akj = __uint_as_float(auxj);
 							const float lgx = (lane == zo) ? lg1_t[lane] : lg_t[lane];
 							float dj = 0.0f; // d[lane] of step jn: its row sits in lane jn's registers
 #pragma unroll
 							for (int kk = 0; kk < 32; ++kk) {
 								const float x = __shfl_sync(0xffffffffu, d[kk], jn);
 								dj = lane == kk ? x : dj;
+							}
+							const unsigned bmk = fc.born_mask;
+							if (bmk) { // slots born during this block: the tile's column predates them
+								const int itj = __shfl_sync(0xffffffffu, item_of(), jn);
+								if ((bmk >> lane) & 1u) dj = g_stream_density<HD>(thc + (size_t)lane * HPS, a.X + (size_t)itj * HD);
 							}
 							const float key = lgx > -INFINITY ? (dj + g_noise(T, (uint32_t)jn, (uint32_t)lane)) + lgx : -INFINITY;
 							const float top = fmaxf(redux_max_f32(key), akj);
@@ -587,7 +613,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 								if (born) {
 									p.dirty[(size_t)chain * 32 + b] = 1;
 									fc.born_mask = fc.born_mask | (1u << b);
-									fc.born_seq = fc.born_seq + 1u;
 								}
 								__threadfence_block();
 								fc.version = fc.version + 1u;
@@ -597,11 +622,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 							__threadfence_block();
 							if (lane == jn) znew = b;
 							if (born) {
-								// the newborn slot's column for my step; it may be anybody's contender: the rest of the sub-tile in full
-								const float l = g_stream_density<HD>(thc + (size_t)b * HPS, a.X + (size_t)item_of() * HD);
-								dput(b, l);
-								seq_early = fc.born_seq;
-								unsafe = true;
+								unsafe = true; // the newborn slot may be anybody's contender: the rest of the sub-tile in full
 							} else if (lane > jn && valid && !unsafe) {
 								pick(); // the counts of two slots changed: the contenders' keys again
 							}
@@ -646,7 +667,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 	}
 	g_tc_fence_before();
 	__syncthreads();
-	if (warp == F_EW) {
+	if (warp == F_W_MMA) {
 		g_tc_fence_after();
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 	}

@@ -257,15 +257,20 @@ template <int D, int M>
 __global__ void __launch_bounds__(256) k_aux_keys(const SweepArgs a, uint32_t *out) {
 	const int sj = blockIdx.x * 256 + threadIdx.x;
 	const int sw = blockIdx.z;
-	if (sj >= a.N) return;
-	const int item = a.scan_order[(size_t)sw * a.N + sj];
+	const bool in = sj < a.N; // (whole warps stay: the group maximum is a warp reduction)
+	const int item = in ? a.scan_order[(size_t)sw * a.N + sj] : 0;
 	const float rn = __ldg(a.Xwn + item);
 	for (int chain = blockIdx.y; chain < a.C; chain += gridDim.y) { // grid.y is capped at 65535
 		const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 		float ak;
 		int am;
 		aux_race<D, M>(ph, a.prior, rn, (uint32_t)sj, a.sweep0 + (uint32_t)sw, a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT, ak, am);
-		out[((size_t)sw * a.C + chain) * a.N + sj] = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+		const uint32_t packed = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+		if (in) out[((size_t)sw * a.C + chain) * a.N + sj] = packed;
+		if (a.aux_max) { // the largest packed key of the 32 consecutive steps of this warp (what the consumer compares against)
+			const float gm = redux_max_f32(in ? __uint_as_float(packed) : -INFINITY);
+			if ((threadIdx.x & 31) == 0 && in) a.aux_max[((size_t)sw * a.C + chain) * a.aux_groups + (sj >> 5)] = gm;
+		}
 	}
 }
 

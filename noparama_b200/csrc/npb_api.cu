@@ -369,6 +369,7 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	if (ch->g_dirty) cudaFree(ch->g_dirty);
 	if (ch->g_born) cudaFree(ch->g_born);
 	if (ch->g_zblk) cudaFree(ch->g_zblk);
+	if (ch->aux_max) cudaFree(ch->aux_max);
 	delete ch;
 	return NPB_OK;
 }

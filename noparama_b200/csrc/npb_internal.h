@@ -61,6 +61,7 @@ struct npb_chains {
 	int scan_cap = 0;              // sweeps per launch the buffer holds
 	uint32_t *aux_keys = nullptr;  // [aux_cap, C, N] packed race key of the best auxiliary draw of every (chain, step)
 	int aux_cap = 0;               // sweeps per launch that buffer holds
+	float *aux_max = nullptr;      // [aux_cap, C, ceil(N / 32)] (fused D = 16 kernel)
 	// split-merge samplers (npb_splitmerge.cu)
 	unsigned long long *smst = nullptr; // [C, 12]: attempts[4], accepts[4], SAMS allocations, proposals, 2 reserved
 	npb_z_t *sm_zt = nullptr;      // [C, zstride] chain-major working copy of z
@@ -95,6 +96,8 @@ struct SweepArgs {
 	const float *X, *Xw, *Xwn;
 	const int32_t *scan_order; // [n_sweeps, N]
 	const uint32_t *aux_keys;  // [n_sweeps, C, N] (k_aux_keys) or NULL
+	float *aux_max;            // [n_sweeps, C, aux_groups] largest auxiliary key of every 32 consecutive steps, or NULL
+	int aux_groups;            // ceil(N / 32)
 	npb_z_t *z;
 	float *theta;
 	int *counts;
