@@ -163,6 +163,15 @@ __device__ __noinline__ void f_epilogue_half_unfolded(uint32_t taddr, const floa
 	}
 }
 
+// the packed race key of the best of a step's M auxiliary draws, exactly as k_aux_keys would have written it
+template <int M>
+__device__ __noinline__ uint32_t f_aux_exact(const Philox &ph, const PriorDev &pr, float rn, uint32_t sj, uint32_t sweep) {
+	float ak;
+	int am;
+	aux_race<HD, M>(ph, pr, rn, sj, sweep, pr.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT, ak, am);
+	return (__float_as_uint(ak) & ~3u) | (uint32_t)am;
+}
+
 template <int M, bool PROBE>
 __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, const PreArgs p) {
 	const bool race = !PROBE && p.spec != 2; // (p.spec == 2: measurement switch, table pipeline alone, no decisions)
@@ -327,9 +336,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 				float *thc = a.theta + (size_t)chain * 32 * HPS;
 				// The step's inputs, two tiles ahead, by cp.async into a three-stage ring in shared memory (as register prefetches
 				// ptxas spilled them straight after the load, i.e. waited for them): the old assignments, gathered per block into
-				// step order by k_gather_z so that they stream instead of chasing scan order -> z through DRAM latency, and the
-				// largest auxiliary key of the sub-tile's 32 steps (k_aux_keys writes it next to the keys: it settles nearly every
-				// step, a step's own key is fetched only when the maximum does not).
+				// step order by k_gather_z so that they stream instead of chasing scan order -> z through DRAM latency, and an
+				// upper bound of the auxiliary keys of the sub-tile's 32 steps (k_aux_bound): it settles nearly every step, a
+				// step's own key is drawn (f_aux_exact) only when the bound does not.
 				const float *auxg = a.aux_max + ((size_t)p.sw * C + chain) * a.aux_groups + (p.s0 >> 5);
 				const npb_z_t *zrow = p.zblk + (size_t)chain * p.zstride;
 				uint8_t *ring = gen + F_RING + dw * (3 * F_RING_STAGE);
@@ -358,10 +367,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 					__syncwarp();
 					const int zold = valid ? (int)reinterpret_cast<const npb_z_t *>(ring + (t % 3) * F_RING_STAGE)[lane] : 0;
 					const float akmax = sl0 < p.nsteps ? *reinterpret_cast<const float *>(ring + (t % 3) * F_RING_STAGE + 64) : -INFINITY;
-					auto aux_of = [&]() -> uint32_t { // my step's packed auxiliary key (rare paths only)
-						return valid ? __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + p.s0 + sl0 + lane) : 0xff800000u;
-					};
 					auto item_of = [&]() -> int { return valid ? __ldg(order + p.s0 + sl0 + lane) : 0; }; // (rare paths only)
+					auto aux_of = [&]() -> uint32_t { // my step's packed auxiliary key, drawn on demand (rare paths only)
+						return valid ? f_aux_exact<M>(ph, a.prior, __ldg(a.Xwn + item_of()), (uint32_t)(p.s0 + sl0 + lane), sweep) : 0xff800000u;
+					};
 					const uint32_t T = npb_mix32(npb_mix32(ph.k0 ^ ((uint32_t)(p.s0 + sl0) * 0x9E3779B1u)) ^ ph.k1 ^ (sweep * 0x85EBCA77u) ^ 0x5bd1e995u);
 					int znew = zold;
 					// ---- the step's CONTENDERS, independent of the member counts: the occupied slots whose density lies within
@@ -696,7 +705,6 @@ __global__ void __launch_bounds__(256) k_gather_z(const int32_t *order, int nste
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-extern template npb_status npb_launch_aux_keys<16>(npb_chains *, const SweepArgs &);
 npb_status npb_tc16_ensure(npb_chains *ch, bool need_table);
 npb_status npb_tc16_pre_block(npb_chains *ch, const int32_t *d_order, int nsteps, int born_buf);
 
@@ -725,7 +733,7 @@ npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a) {
 	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D = 16 tensor-core sweep");
 	npb_status s = npb_tc16_ensure(ch, false);
 	if (s != NPB_OK) return s;
-	s = npb_launch_aux_keys<16>(ch, a);
+	s = npb_launch_aux_bound<16>(ch, a); // group maxima of a bound of the auxiliary keys (exact keys on demand in the kernel)
 	if (s != NPB_OK) return s;
 	const size_t C = (size_t)ch->C;
 	// parameters may have changed since the last launch (init_from_params, update_params): every slot's image is rebuilt

@@ -163,24 +163,7 @@ __global__ void __launch_bounds__(256) k_pre_bimg(const float *theta, const doub
 // (npb_alg8_tile4.cuh), skipping the words of a draw it does not need.
 template <int CD, int M>
 __device__ __forceinline__ float g_aux_bound(const Philox &ph, const PriorDev &pr, float rn, uint32_t sj, uint32_t sweep, float ik2) {
-	constexpr int TAILW = 2 + ((CD - 1) / 2 + 1) / 2; // words of a draw after its first pair: the z2^2 pair, the packed uniforms
-	uint32_t as[4];
-	aux_seed(ph, sj, sweep, as);
-	float ub = -INFINITY;
-#pragma unroll
-	for (int m = 0; m < M; ++m) {
-		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-		float g0, g1;
-		npb_normal2(r0, r1, g0, g1);
-		const float av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
-		const float along = rn * __frcp_rn(av) - ik2 * g1;
-		ub = fmaxf(ub, pr.c0_2 - (float)CD * fast_lg2(av) - along * along + pr.log2_alpha_m);
-		if (m + 1 < M) {
-#pragma unroll
-			for (int w = 0; w < TAILW; ++w) (void)xoshiro_next(as);
-		}
-	}
-	return ub + 24.0f;
+	return aux_race_bound<CD, M>(ph, pr, rn, sj, sweep, ik2);
 }
 // the exact key, packed like k_aux_keys packs it (draw index in the two low mantissa bits)
 template <int CD, int M>

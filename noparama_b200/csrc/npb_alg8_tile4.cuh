@@ -152,17 +152,12 @@ __device__ __noinline__ float log2density_stream(const float *th, const float *x
 // ) + ceil((D-1)/4) words of 16-bit uniforms.
 template <int D>
 __device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &pr, float &av, float &zpar, float &R2) {
+	// word order of a draw's stream: the Box-Muller pair of (v, z_par), the packed uniforms of the chi-square, the pair of
+	// z2^2 -- so that a bound of the draw's key (aux_draw_bound) needs the first four words only
 	float g0, g1;
 	{
 		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
 		npb_normal2(r0, r1, g0, g1);
-	}
-	// z2^2 alone: the square of one Box-Muller output, (-2 ln u) cos^2(2 pi v), needs no square root and no sine
-	float z2sq;
-	{
-		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-		const float c = __cosf(__uint2float_rn(r1) * (6.283185307179586f * 2.3283064365386963e-10f));
-		z2sq = -2.0f * NPB_LN2 * fast_lg2(npb_u01(r0)) * c * c;
 	}
 	av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
 	zpar = g1;
@@ -179,7 +174,38 @@ __device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &
 		}
 	}
 	R2 = -2.0f * NPB_LN2 * (lsum + fast_lg2(prod));
-	if ((D - 1) & 1) R2 += z2sq;
+	if ((D - 1) & 1) {
+		// z2^2 alone: the square of one Box-Muller output, (-2 ln u) cos^2(2 pi v), needs no square root and no sine
+		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+		const float c = __cosf(__uint2float_rn(r1) * (6.283185307179586f * 2.3283064365386963e-10f));
+		R2 += -2.0f * NPB_LN2 * fast_lg2(npb_u01(r0)) * c * c;
+	}
+}
+
+// Upper bound of the race key of one draw for one item from the first four words of its stream: v, z_par and the first
+// four uniforms of the chi-square (-2 ln(U1 U2 U3 U4) <= R2), the race noise at its cap (neg_lg2_exp1 clamps at 23) and one
+// more for rounding and the index bits packed into a key.  At the reference prior the dropped part of the chi-square is
+// what makes the bound loose (by ~361 chi^2_7 log2 units at D = 16) and it does not matter: what is kept already puts a
+// draw thousands of log2 units below any item's own cluster.
+template <int D>
+__device__ __forceinline__ float aux_draw_bound(uint32_t (&as)[4], const PriorDev &pr, float rn, float ik2) {
+	float g0, g1;
+	{
+		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
+		npb_normal2(r0, r1, g0, g1);
+	}
+	const float av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
+	constexpr int KU = (D - 1) / 2;
+	float prod = 1.0f;
+#pragma unroll
+	for (int i = 0; i < (KU < 4 ? KU : 4); i += 2) {
+		const uint32_t w = xoshiro_next(as);
+		prod *= __uint2float_rn((w & 0xffffu) + 1u) * (1.0f / 65536.0f);
+		if (i + 1 < KU) prod *= __uint2float_rn((w >> 16) + 1u) * (1.0f / 65536.0f);
+	}
+	const float lb = -2.0f * NPB_LN2 * fast_lg2(prod);
+	const float along = rn * __frcp_rn(av) - ik2 * g1;
+	return pr.c0_2 - (float)D * fast_lg2(av) - fmaf(along, along, ik2 * ik2 * lb) + pr.log2_alpha_m + 24.0f;
 }
 
 // xoshiro state of the auxiliary stream of (chain, step, sweep): four words of a multiply-xorshift hash (the murmur3
@@ -194,6 +220,14 @@ __device__ __forceinline__ void aux_seed(const Philox &ph, uint32_t sj, uint32_t
 	as[3] = npb_mix32(h + 0xDAA66D2Bu) | 1u; // never the all-zero state
 }
 
+// stream of draw m: the step's state with the draw index hashed into two of its words
+__device__ __forceinline__ void aux_stream(const uint32_t (&base)[4], int m, uint32_t (&as)[4]) {
+	as[0] = npb_mix32(base[0] + (uint32_t)(m + 1) * 0x9E3779B9u);
+	as[1] = npb_mix32(base[1] ^ ((uint32_t)(m + 1) * 0x7F4A7C15u));
+	as[2] = base[2];
+	as[3] = base[3];
+}
+
 // The M auxiliary draws of step sj for one item and the race among them: best key and which draw it was.
 // rn = |xw| (k_whiten).
 template <int D, int M>
@@ -201,22 +235,34 @@ __device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, f
 		float &auxkey_j, int &auxm) {
 	auxkey_j = -INFINITY;
 	auxm = 0;
-	uint32_t as[4];
-	aux_seed(ph, sj, sweep, as);
-	float lkey[M];
+	uint32_t base[4];
+	aux_seed(ph, sj, sweep, base);
 #pragma unroll
 	for (int m = 0; m < M; ++m) {
+		uint32_t as[4];
+		aux_stream(base, m, as);
 		float av, zpar, R2;
 		aux_draw_chi<D>(as, pr, av, zpar, R2);
 		const float along = rn * __frcp_rn(av) - ik2 * zpar;
 		const float q = fmaf(along, along, ik2 * ik2 * R2);
-		lkey[m] = pr.c0_2 - (float)D * fast_lg2(av) - q + pr.log2_alpha_m;
-	}
-#pragma unroll
-	for (int m = 0; m < M; ++m) {
-		const float key = lkey[m] + neg_lg2_exp1(xoshiro_next(as));
+		const float key = (pr.c0_2 - (float)D * fast_lg2(av) - q + pr.log2_alpha_m) + neg_lg2_exp1(xoshiro_next(as));
 		if (key > auxkey_j) { auxkey_j = key; auxm = m; }
 	}
+}
+
+// upper bound of the packed race key of the best of step sj's M draws (aux_draw_bound): what k_aux_bound reduces per group
+template <int D, int M>
+__device__ __forceinline__ float aux_race_bound(const Philox &ph, const PriorDev &pr, float rn, uint32_t sj, uint32_t sweep, float ik2) {
+	uint32_t base[4];
+	aux_seed(ph, sj, sweep, base);
+	float ub = -INFINITY;
+#pragma unroll
+	for (int m = 0; m < M; ++m) {
+		uint32_t as[4];
+		aux_stream(base, m, as);
+		ub = fmaxf(ub, aux_draw_bound<D>(as, pr, rn, ik2));
+	}
+	return ub;
 }
 
 // Birth: coordinate `lane` (< D) of the full z of draw m of step `step`, consistent with the key that won the race.
@@ -224,10 +270,11 @@ __device__ __forceinline__ void aux_race(const Philox &ph, const PriorDev &pr, f
 template <int D>
 __device__ __forceinline__ float aux_birth_z(const Philox &ph, const PriorDev &pr, const float *xw, float rn, uint32_t step,
 		uint32_t sweep, int m, int lane, float &av_out) {
-	uint32_t as[4];
-	aux_seed(ph, step, sweep, as);
+	uint32_t base[4], as[4];
+	aux_seed(ph, step, sweep, base);
+	aux_stream(base, m, as);
 	float av = 1.0f, zpar = 0.0f, R2 = 0.0f;
-	for (int mm = 0; mm <= m; ++mm) aux_draw_chi<D>(as, pr, av, zpar, R2);
+	aux_draw_chi<D>(as, pr, av, zpar, R2);
 	av_out = av;
 	// unit vector along the item (any fixed direction if the item sits exactly on mu0)
 	const float ahat = lane < D ? (rn > 0.0f ? __ldg(xw + lane) / rn : (lane == 0 ? 1.0f : 0.0f)) : 0.0f;
@@ -257,21 +304,47 @@ template <int D, int M>
 __global__ void __launch_bounds__(256) k_aux_keys(const SweepArgs a, uint32_t *out) {
 	const int sj = blockIdx.x * 256 + threadIdx.x;
 	const int sw = blockIdx.z;
-	const bool in = sj < a.N; // (whole warps stay: the group maximum is a warp reduction)
-	const int item = in ? a.scan_order[(size_t)sw * a.N + sj] : 0;
+	const bool in = sj < a.N;
+	if (!in) return;
+	const int item = a.scan_order[(size_t)sw * a.N + sj];
 	const float rn = __ldg(a.Xwn + item);
 	for (int chain = blockIdx.y; chain < a.C; chain += gridDim.y) { // grid.y is capped at 65535
 		const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
 		float ak;
 		int am;
 		aux_race<D, M>(ph, a.prior, rn, (uint32_t)sj, a.sweep0 + (uint32_t)sw, a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT, ak, am);
-		const uint32_t packed = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
-		if (in) out[((size_t)sw * a.C + chain) * a.N + sj] = packed;
-		if (a.aux_max) { // the largest packed key of the 32 consecutive steps of this warp (what the consumer compares against)
-			const float gm = redux_max_f32(in ? __uint_as_float(packed) : -INFINITY);
-			if ((threadIdx.x & 31) == 0 && in) a.aux_max[((size_t)sw * a.C + chain) * a.aux_groups + (sj >> 5)] = gm;
-		}
+		if (in) out[((size_t)sw * a.C + chain) * a.N + sj] = (__float_as_uint(ak) & ~3u) | (uint32_t)am;
 	}
+}
+
+// The fused D = 16 kernel (npb_alg8_fused16.cu) compares a step's pick with the largest auxiliary key of its 32-step group and
+// evaluates a step's own key only when that does not settle it (a handful of steps per million at the reference prior), so its
+// pre-pass needs no exact key at all: a BOUND per step (four stream words per draw instead of nine, no race noise), reduced to
+// one number per (chain, group).  40 % of k_aux_keys' instructions and none of its 3.3 GB per sweep.
+template <int D, int M>
+__global__ void __launch_bounds__(256) k_aux_bound(const SweepArgs a) {
+	const int sj = blockIdx.x * 256 + threadIdx.x;
+	const int sw = blockIdx.z;
+	const bool in = sj < a.N;
+	const int item = in ? a.scan_order[(size_t)sw * a.N + sj] : 0;
+	const float rn = __ldg(a.Xwn + item);
+	for (int chain = blockIdx.y; chain < a.C; chain += gridDim.y) {
+		const Philox ph((uint32_t)a.seed, (uint32_t)(a.seed >> 32) + (uint32_t)chain);
+		const float ub = aux_race_bound<D, M>(ph, a.prior, rn, (uint32_t)sj, a.sweep0 + (uint32_t)sw, a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT);
+		const float gm = redux_max_f32(in ? ub : -INFINITY);
+		if ((threadIdx.x & 31) == 0 && in) a.aux_max[((size_t)sw * a.C + chain) * a.aux_groups + (sj >> 5)] = gm;
+	}
+}
+
+template <int D>
+npb_status npb_launch_aux_bound(npb_chains *ch, const SweepArgs &a) {
+	npb_ctx *ctx = ch->ctx;
+	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D >= 4 sweep kernel");
+	dim3 grid((unsigned)((a.N + 255) / 256), (unsigned)(ch->C < 65535 ? ch->C : 65535), (unsigned)a.n_sweeps);
+	if (ch->m_aux == 3) k_aux_bound<D, 3><<<grid, 256, 0, ctx->stream>>>(a);
+	else k_aux_bound<D, 1><<<grid, 256, 0, ctx->stream>>>(a);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
 }
 
 template <int D>

@@ -192,10 +192,11 @@ static __device__ __noinline__ float g_log2density_stream64(const float *th, con
 // npb_alg8_tile4.cuh with two coordinates per lane: lane and lane + 32), written to the slot table.
 static __device__ __noinline__ void g_birth_theta64(const Philox &ph, const PriorDev &pr, const float *xw, float rn, uint32_t step, uint32_t sweep,
 		int m, int lane, float *th) {
-	uint32_t as[4];
-	aux_seed(ph, step, sweep, as);
+	uint32_t base[4], as[4];
+	aux_seed(ph, step, sweep, base);
+	aux_stream(base, m, as);
 	float av = 1.0f, zpar = 0.0f, R2 = 0.0f;
-	for (int mm = 0; mm <= m; ++mm) aux_draw_chi<GD>(as, pr, av, zpar, R2);
+	aux_draw_chi<GD>(as, pr, av, zpar, R2);
 	const float a0 = rn > 0.0f ? __ldg(xw + lane) / rn : (lane == 0 ? 1.0f : 0.0f);
 	const float a1 = rn > 0.0f ? __ldg(xw + lane + 32) / rn : 0.0f;
 	uint32_t w[4];
