@@ -333,6 +333,40 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
     ds.close()
     out["cfg4"] = cfg4_measure(npb, syn, ctx, fp32_peak, rank)
     out["fp32_pipe_kernel"] = fp32_path_measure(npb, syn, ctx, fp32_peak, rank)
+    out["mixing"] = mixing_measure(npb, syn, ctx, rank)
+    return out
+
+
+def mixing_measure(npb, syn, ctx, rank, chains=8192, timed=3):
+    """The headline shape in a regime where items keep moving: the 32 components in pairs 2.5 apart (synthetic.gmm_mixing),
+    the true parameters given, so a reassignment changes the item's cluster with probability ~0.15 for ever.  This is what the
+    sequential part of the sweep kernels costs; the handle picks its kernels by the moved fraction of its previous sweep
+    (fused kernel while few items move, the table + race kernel pair in a mixing chain), and both are timed here."""
+    D, K, N = 16, 32, 100_000
+    X, y = syn.gmm_mixing(N, D, K, 20261005)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(D)).bind(ctx)
+    out = {"workload": "BASELINE configs[4] per-GPU shape (%d chains, N=%d, 16-D, 32 components, Kmax=32, m=3) with the components in "
+                       "pairs 2.5 apart (synthetic.gmm_mixing, seed 20261005) and their true parameters given: the chains mix for ever" % (chains, N)}
+    for name, path in (("auto", "auto"), ("fused_kernel", "tc"), ("kernel_pair", "tc2")):
+        ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K0_REF, m_aux=M_AUX, seed=SEED + 53 * rank)
+        ch.set_option("d16_path", path)
+        ch.init_from_params(*given_clusters(X, y))
+        for _ in range(2):
+            ch.sweep(npb.ALG8, 1)
+        ms, cand, moved, births, last = timed_sweeps(npb, ch, timed)
+        k_ms = float(np.mean(ms))
+        st = ch.sweep(npb.ALG8, 1)
+        out[name] = {"value": chains * N / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": timed, "warmup": 2,
+                     "moved_fraction": moved / (chains * N * timed), "new_clusters_per_step": births / timed,
+                     "candidates_per_reassignment": cand / (chains * N * timed), "mean_K": last.mean_K}
+        if name == "auto":
+            m = ch.metrics(y)
+            out["mean_purity"], out["mean_ari"] = float(m["purity"].mean()), float(m["adjusted_rand"].mean())
+        ch.close()
+    out["value"], out["unit"] = out["auto"]["value"], UNIT
+    out["moved_fraction"] = out["auto"]["moved_fraction"]
+    ds.close()
     return out
 
 
@@ -445,6 +479,10 @@ def main():
     X, y, ds, mc = build_chains(npb, syn, ctx, cfg, n_chains, kmax, dg.rank_seed(SEED, rank))
     chains = mc.chains
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    d16_path = os.environ.get("NPB_D16_PATH", "auto")
+    tc_path = DIM == 16 and kmax == 32 and not d16_path.startswith("f")
+    if tc_path:
+        chains.set_option("time_kernels", "1")
 
     def barrier():
         ctx.synchronize()
@@ -454,7 +492,9 @@ def main():
 
     # ---- warm-up (also moves the items from the random initial assignment to their clusters) ----
     for _ in range(args.warmup):
-        chains.sweep(npb.ALG8, 1, want_stats=False)
+        chains.sweep(npb.ALG8, 1)  # (with statistics: the handle picks its D = 16 kernels by the moved fraction of its last sweep)
+    if tc_path:
+        chains.kernel_time()  # reset
     # ---- timed region: exactly K sweeps, inputs resident in HBM ----
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -466,18 +506,32 @@ def main():
     barrier()
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
+    kt_ms, kt_n = chains.kernel_time() if tc_path else (0.0, 0)
 
-    # ---- end to end through the public call with host buffers: every step uploads X from pinned host memory and
-    # reads the assignments of all chains back into page-locked host memory ----
+    # ---- end to end through the public call with host buffers: every step uploads X from pinned host memory and brings the
+    # caller's page-locked copy of all assignments up to date (npb_chains_sweep_host_delta: the entries that changed travel as a
+    # list compacted on the device, everything when more than a quarter changed).  The full copy of every assignment every step
+    # (npb_chains_sweep_host, round 1's figure) is timed next to it. ----
     Xh = torch.from_numpy(np.ascontiguousarray(X)).pin_memory().numpy()
     z_host = torch.empty((ds.N, n_chains), dtype=torch.uint16, pin_memory=True).numpy()
-    chains.sweep_host(Xh, npb.ALG8, 1, z_out=z_host)  # warm the staging buffers
+    chains.sweep_host_delta(Xh, npb.ALG8, 1, z_mirror=z_host)  # first call: everything travels, staging buffers warm up
+    chains.sweep_host_delta(Xh, npb.ALG8, 1, z_mirror=z_host)
+    barrier()
+    t0 = time.perf_counter()
+    changed = 0
+    for _ in range(args.e2e_steps):
+        changed += chains.sweep_host_delta(Xh, npb.ALG8, 1, z_mirror=z_host)[1]
+    ctx.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    mirror_ok = bool(np.array_equal(z_host[:, :4].T.astype(np.int32), chains.assignments(0, 4)))
+    chains.sweep_host(Xh, npb.ALG8, 1, z_out=z_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         chains.sweep_host(Xh, npb.ALG8, 1, z_out=z_host)
     ctx.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_full_s = time.perf_counter() - t0
     barrier()
 
     # ---- diagnostics exchange (outside the timed region): a short traced phase for R-hat, then one all-reduce of
@@ -489,16 +543,14 @@ def main():
         k_trace.append(mm["K"].astype(np.float64))
         jll_trace.append(mm["joint_loglik"])
     m = chains.metrics(y)
-    anchors = np.arange(0, ds.N, ds.N // 256)[:256]
-    S = torch.zeros((len(anchors), len(anchors)), dtype=torch.float32, device="cuda")
-    chains.cocluster_into(anchors, S.data_ptr())
+    cocl = cocluster_measure(npb, chains, ds, torch, dist, world)
     diag = dg.combine(dg.score_partial(m), {"K": dg.rhat_partial(np.stack(k_trace, 1)),
                                             "joint_loglik": dg.rhat_partial(np.stack(jll_trace, 1))},
-                      cocluster=S, device="cuda")
-    t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
+                      cocluster=None, device="cuda")
+    t = torch.tensor([elapsed_ms, e2e_s, e2e_full_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_s = t.tolist()
+    elapsed_ms, e2e_s, e2e_full_s = t.tolist()
     n_items = ds.N
     chains.close()
     ds.close()
@@ -508,61 +560,64 @@ def main():
         total = world * n_step * args.steps
         value = total / (elapsed_ms * 1e-3)
         e2e_value = world * n_step * args.e2e_steps / e2e_s
-        # roofline of the dominant (only) kernel of a step, per launch, from this rank's counters and CUDA-event times
-        flops_per_launch = (cand / args.steps) * (f_eval(DIM) + 6)
         k_ms = float(np.mean(kernel_ms))
         fp32_peak = mc_fp32_peak(ctx)
         hbm_peak, hbm_src = measured_peaks()
-        bytes_per_launch = n_step * (2 * 2 + 4 * DIM / 32.0)  # z read+write (u16) + x shared by a 32-step tile
-        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.config)
-            if tj and tj["chains"] == n_chains:
-                traffic = tj["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        tc_path = DIM == 16 and kmax == 32 and not os.environ.get("NPB_D16_PATH", "").startswith("f")
+        # algorithmic work of a step = sum over its reassignments of (K_i + m) (D^2 + 4D + 3 + 6) flops (the kernels
+        # keep the exact sum (K_i + m)) and 2 sizeof(z) + 4 D / 32 bytes of HBM per reassignment
+        alg_flops_step = (cand / args.steps) * (f_eval(DIM) + 6)
+        alg_bytes_step = n_step * (2 * 2 + 4 * DIM / 32.0)
+        fp32_roofline = {"bound": "fp32", "achieved": alg_flops_step / (k_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": alg_flops_step / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                         "peak_source": "FP32 FMA peak measured in this run by npb_fp32_peak (better of the scalar FFMA and the packed "
+                                        "FFMA2 instruction streams; MEASURED_PEAKS.json has no FP32 figure)",
+                         "note": "algorithmic flops of a step / the whole step time"}
         kernel = "k_alg8_sweep_tile4<%d,3>" % DIM if (DIM >= 4 and kmax == 32) else ("k_alg8_sweep_tile" if DIM >= 4 else "k_alg8_sweep_reg")
-        fp32_roofline = {"bound": "fp32", "achieved": flops_per_launch / (k_ms * 1e-3) / 1e12, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": flops_per_launch / (k_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu, DRAM read+write)",
-                         "algorithmic_bytes": bytes_per_launch, "kernel": kernel, "kernel_ms": k_ms,
-                         "peak_source": "FP32 FMA peak measured in this run by npb_fp32_peak (better of the scalar FFMA and the "
-                                        "packed FFMA2 instruction streams; MEASURED_PEAKS.json has no FP32 figure); algorithmic "
-                                        "flops = sum(K_i+m) * (D^2+4D+3+6), counter kept by the kernel"}
         launches = args.steps * (3 if (DIM >= 4 and kmax == 32) else 2)
         if tc_path:
-            # D = 16, Kmax = 32 runs on the tensor path (npb_alg8_gemm.cu): per block of 4096 steps k_pre_aimg16, k_pre_bimg16,
-            # k_density_tc16 (tcgen05 kind::f16 density table, three FP16 products per FP32 product + folded offsets: four K = 16
-            # MMA steps per (step, 16 slots)) and k_race (warp per chain).  The step's dominant kernel is k_density_tc16 (~2/3 of
-            # the step, ncu); no single resource is saturated (tensor pipe 44 %, L2 56 %, issue 41 %, DRAM 25 % in ncu), so the
-            # tensor figure is reported as `roofline`, the table's HBM round trip as `roofline_hbm` and the algorithmic FP32-
-            # equivalent work against the FP32 pipe as `roofline_fp32_equivalent` (> 1: the work left that pipe).
-            blocks = (n_items + 4095) // 4096
+            # D = 16, Kmax = 32: per block of steps k_pre_aimg16, k_pre_bimg16, k_gather_z and k_sweep_tc16 (tcgen05 kind::f16
+            # quadratic forms, epilogue and race fused; npb_alg8_fused16.cu), once per sweep k_scan_order and k_aux_bound.
+            # `roofline` is the dominant kernel's: ALGORITHMIC flops per launch / its average launch duration (CUDA events on the
+            # library's stream around every launch of it inside the timed region) against the measured bf16 peak -- the FP16x3
+            # split issues 5.7 flops per algorithmic flop, reported as `issued`.
+            bs = int(os.environ.get("NPB_D16_BLOCK", "8192"))
+            blocks = (n_items + bs - 1) // bs
             launches = args.steps * (2 + 4 * blocks)
-            bf16_peak = None
-            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-            if os.path.exists(pk):
-                bf16_peak = json.load(open(pk)).get("bf16_tflops")
-            f16_peak = bf16_peak if bf16_peak else 2250.0
-            mma = n_step * 32 * 4 * 2 * DIM * DIM  # issued kind::f16 flops per sweep: 32 slots x 4 K-steps x 2 x 16 x 16
-            bytes_per_launch = n_step * (2 * 2 + 2 * 32 * 4)  # z read+write (u16) + the table row written and read once (fp32 x 32 slots)
-            traffic_tc = None
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            f16_peak = peaks.get("bf16_tflops")
+            peak_src = "measured bf16 burst peak (MEASURED_PEAKS.json; kind::f16 runs at the bf16 rate)"
+            if not f16_peak:
+                f16_peak, peak_src = 2250.0, "fallback: nominal dense bf16 peak of B200 (B200_PROFILING.md); MEASURED_PEAKS.json missing"
+            traffic, traffic_src = None, "missing: profiles/r2_traffic.json has no entry for this configuration"
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.config + "_tc")
-                if tj and tj["chains"] == n_chains:
-                    traffic_tc = tj["dram_bytes_per_launch"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(args.config)
+                if tj and tj["chains"] == n_chains and tj["block"] == bs:
+                    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
             except Exception:
                 pass
-            roofline = {"bound": "tensor", "achieved": mma / (k_ms * 1e-3) / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
-                        "frac": mma / (k_ms * 1e-3) / 1e12 / f16_peak, "traffic": traffic_tc,
-                        "traffic_unit": "bytes per sweep (ncu, DRAM read+write of k_density_tc16 + k_race over the sweep's blocks)",
-                        "algorithmic_bytes": bytes_per_launch, "kernel": "k_density_tc16<16,4> (+ k_race<16,3>)", "kernel_ms": k_ms,
-                        "peak_source": "measured bf16 burst peak (MEASURED_PEAKS.json; kind::f16 runs at the bf16 rate); achieved = "
-                                       "issued MMA flops of a sweep / the whole sweep time (table and race kernels)"}
-            fp32_roofline = dict(fp32_roofline, kernel=roofline["kernel"], traffic=traffic_tc, algorithmic_bytes=bytes_per_launch)
+            if kt_n:
+                lps = kt_n / args.steps
+                launch_ms = kt_ms / kt_n
+                issued = n_step * 32 * 4 * 2 * DIM * DIM / lps  # kind::f16 flops per launch: 32 slots x 4 K-steps x 2 x 16 x 16 per reassignment
+                roofline = {"bound": "tensor", "achieved": alg_flops_step / lps / (launch_ms * 1e-3) / 1e12, "peak": f16_peak, "unit": "TFLOP/s",
+                            "frac": alg_flops_step / lps / (launch_ms * 1e-3) / 1e12 / f16_peak, "traffic": traffic,
+                            "traffic_unit": "bytes per launch (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                            "traffic_source": traffic_src, "kernel": "k_sweep_tc16<3,0>", "launches_per_step": lps,
+                            "launch_ms": launch_ms, "share_of_step": kt_ms / elapsed_ms,
+                            "algorithmic_flops_per_launch": alg_flops_step / lps, "algorithmic_bytes_per_launch": alg_bytes_step / lps,
+                            "issued": {"flops_per_launch": issued, "achieved": issued / (launch_ms * 1e-3) / 1e12,
+                                       "frac": issued / (launch_ms * 1e-3) / 1e12 / f16_peak,
+                                       "note": "kind::f16 MMA flops the kernel issues: three FP16 products per FP32 product plus the folded "
+                                               "offsets = 4 K-steps of 16 per (step, slot row)"},
+                            "peak_source": peak_src,
+                            "note": "achieved = SURVEY 8(d) algorithmic flops, sum(K_i + m) (D^2 + 4D + 3 + 6) from the kernel's own counter, per "
+                                    "launch / the kernel's average launch duration measured with CUDA events on its stream"}
+            else:  # the handle ran another kernel set (NPB_D16_PATH=tc2): whole-step figure
+                roofline = dict(fp32_roofline, bound="tensor", peak=f16_peak, frac=alg_flops_step / (k_ms * 1e-3) / 1e12 / f16_peak,
+                                kernel="k_density_tc16 + k_race (round 1 kernel pair)", traffic=None, peak_source=peak_src)
+            fp32_roofline = dict(fp32_roofline, kernel="k_sweep_tc16<3,0> (+ pre-pass kernels)")
         else:
-            roofline = fp32_roofline
+            roofline = dict(fp32_roofline, kernel=kernel, traffic=None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -572,21 +627,26 @@ def main():
                              % (n_items * n_chains * 2 // 2 ** 20, n_chains * kmax * (DIM + DIM * (DIM + 1) // 2 + 1) * 4 // 2 ** 20),
                        "mean_K": last.mean_K, "max_K": last.max_K, "candidates_per_reassignment": cand / (n_step * args.steps),
                        "moved_fraction": moved / (n_step * args.steps), "new_clusters_per_step": births / args.steps,
-                       "path": "tensor (tcgen05 kind::f16 density tables + race kernel)" if tc_path else "fp32 pipe"},
+                       "regime": "stationary: the chains sit at the given clusters and next to no item moves (the fused kernel's best case); "
+                                 "the same shape with chains that keep mixing is also.mixing",
+                       "path": ("tensor, NPB_D16_PATH=%s (auto: fused kernel k_sweep_tc16 while few items move, table + race kernel pair "
+                                "in a mixing chain; same assignments either way)" % d16_path) if tc_path else "fp32 pipe"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_items * DIM * 8),
-                    "d2h_bytes_per_step": int(n_items * n_chains * 2), "steps": args.e2e_steps,
-                    "call": "npb_chains_sweep_host (X up from pinned host memory, every chain's assignments down into "
-                            "page-locked host memory)"},
-            # per step: k_scan_order, (D >= 4, Kmax 32: k_aux_keys, the state-independent auxiliary race,) the sweep kernel(s)
+                    "d2h_bytes_per_step": int(8 + 6 * changed / args.e2e_steps), "steps": args.e2e_steps,
+                    "call": "npb_chains_sweep_host_delta (X up from pinned host memory; the caller's page-locked copy of every chain's "
+                            "assignments brought up to date: the changed entries travel as an (index, slot) list compacted on the device)",
+                    "changed_entries_per_step": changed / args.e2e_steps, "mirror_checked": mirror_ok,
+                    "full_copy": {"value": world * n_step * args.e2e_steps / e2e_full_s, "unit": UNIT,
+                                  "d2h_bytes_per_step": int(n_items * n_chains * 2),
+                                  "call": "npb_chains_sweep_host (every assignment down every step: round 1's figure)"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
-            "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": bytes_per_launch / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": roofline.get("traffic"), "peak_source": hbm_src},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes_step / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes_step / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                             "note": "SURVEY 8(d) algorithmic bytes of a step (6 B per reassignment) / the step time: the path is not HBM-bound"},
             "diagnostics": {"mean_purity": diag["mean_purity"], "mean_rand": diag["mean_rand"], "mean_ari": diag["mean_ari"],
-                            "mean_K": diag["mean_K"], "chains": diag["chains"], "rhat": diag["rhat"],
-                            "cocluster_anchor_diag_mean": float(S.diag().mean().item()),
+                            "mean_K": diag["mean_K"], "chains": diag["chains"], "rhat": diag["rhat"], "cocluster": cocl,
                             "allreduce": "nccl" if world > 1 else "none (1 rank)"},
         }
         if tc_path:
@@ -604,6 +664,27 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cocluster_measure(npb, chains, ds, torch, dist, world):
+    """posterior co-clustering counts of an anchor subset over this rank's chains, all-reduced over the ranks (the path's only
+    exchange); returns the figures for the JSON line"""
+    anchors = np.arange(0, ds.N, max(1, ds.N // 256))[:256]
+    S = torch.zeros((len(anchors), len(anchors)), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    chains.cocluster_into(anchors, S.data_ptr())
+    chains.ctx.synchronize()
+    t_k = time.perf_counter() - t0
+    t_ar = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dist.all_reduce(S)
+        torch.cuda.synchronize()
+        t_ar = time.perf_counter() - t0
+    return {"anchors": int(len(anchors)), "kernel_ms": 1e3 * t_k, "allreduce_ms": 1e3 * t_ar,
+            "anchor_diag_mean": float(S.diag().mean().item())}
 
 
 def mc_fp32_peak(ctx):

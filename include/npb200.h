@@ -112,6 +112,9 @@ npb_status npb_chains_destroy(npb_chains *ch);
 /* behaviour switches of a handle (no reference counterpart; the library reads its NPB_* environment defaults once, when a
  * handle is created).  "d16_path": "auto" | "tc" | "tc2" | "fp32" -- which kernels sweep D = 16, Kmax = 32 chains. */
 npb_status npb_chains_set_option(npb_chains *ch, const char *name, const char *value);
+/* with option "time_kernels" = "1": accumulated duration (CUDA events on the library's stream) and number of launches of the
+ * dominant sweep kernel (k_sweep_tc16) since the previous call -- what a roofline of that kernel divides by */
+npb_status npb_chains_kernel_time(npb_chains *ch, double *ms, int64_t *launches);
 /* overwrite the state of one chain (used by parity tests and by the single-item seam):
  * z [N] slot ids, K clusters with slot ids, means [K,D], covariances [K,D,D] */
 npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z, int K, const int32_t *slots,
@@ -147,6 +150,24 @@ npb_status npb_chains_update_params(npb_chains *ch, int mode, const double *mu0,
  * all chains; z_out [N, n_chains] uint16 slot ids (item-major), may be NULL */
 npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,
 		npb_sweep_stats *stats);
+/* the same with an incremental result: z_mirror [N, n_chains] is the CALLER's copy of the assignments, which the call brings
+ * up to date -- only the entries that changed since the previous call on this handle travel (an (index, slot) list compacted
+ * on the device), the whole array on the first call or when more than a quarter of the entries changed.  The caller passes
+ * the same array, unmodified in between, every time; *n_changed (may be NULL) receives the number of entries written.
+ * (The reference's host reads every assignment after every sweep through membertrix::getAssignments, membertrix.cpp:315-322;
+ * a converged chain changes a handful of them.) */
+npb_status npb_chains_sweep_host_delta(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_mirror,
+		npb_sweep_stats *stats, int64_t *n_changed);
+
+/* membertrix::retract + membertrix::assign of one item of one chain (membertrix.cpp:147-233), for a host that drives single
+ * reassignments itself: the item moves to the occupied cluster `slot`; a cluster left without members disappears
+ * (membertrix.cpp:200-203).  NPB_E_ASSIGNMENT_ABSENT: no such cluster; NPB_E_ALREADY_ASSIGNED: the item is in it already.
+ * _new: addCluster + assign (membertrix.cpp:87-118): the item founds a cluster with the given parameters in the lowest free
+ * slot (*slot_out); NPB_E_KMAX_OVERFLOW without one. */
+npb_status npb_chain_move_item(npb_chains *ch, int64_t chain, int64_t item, int slot);
+npb_status npb_chain_move_item_new(npb_chains *ch, int64_t chain, int64_t item, const double *mu, const double *Sigma, int *slot_out);
+/* membertrix::remove (membertrix.cpp:213-228): NPB_E_ASSIGNMENT_REMAINING while the cluster has members */
+npb_status npb_chain_remove_cluster(npb_chains *ch, int64_t chain, int slot);
 
 /* one NealAlgorithm8::update(membertrix&, {item}) (np_neal_algorithm8.cpp:49-167) on one chain -- the reference's
  * single-item seam (np_mcmc.cpp:162); chain < 0 applies it to every chain of the handle.  Any D and Kmax. */
@@ -203,6 +224,10 @@ npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *puri
  * npb_chains_get_best_assignments reads the kept assignments back like npb_chains_get_assignments
  * (MCMC::getMaxLikelihoodMatrix, np_mcmc.h:90). */
 npb_status npb_chains_consider_max_likelihood(npb_chains *ch, double *joint_loglik_out, double *best_out);
+/* the clusters of the kept state, as npb_chains_get_params reports the current ones (slot ids are re-used after a death, so
+ * the current slot table does not describe a state kept earlier) */
+npb_status npb_chains_get_best_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts, double *mu,
+		double *Sigma);
 npb_status npb_chains_get_best_assignments(npb_chains *ch, int64_t chain0, int64_t n, int32_t *z_out /* [n,N] slot ids */);
 
 /* posterior co-clustering counts over this context's chains for an anchor subset: S[a,b] = #chains with

@@ -6,6 +6,7 @@ and argument meanings; all arithmetic happens in the CUDA library.  There is no 
 without a GPU (so that CPU-only checks can load the library and inspect its symbols), creating a Context does not.
 """
 import ctypes as C
+import weakref
 import os
 import numpy as np
 
@@ -29,7 +30,8 @@ EXPORTS = [
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
     "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
-    "npb_chains_probe_tile_logdensity", "npb_chains_set_option",
+    "npb_chains_probe_tile_logdensity", "npb_chains_set_option", "npb_chains_sweep_host_delta", "npb_chains_get_best_params",
+    "npb_chain_move_item", "npb_chain_move_item_new", "npb_chain_remove_cluster", "npb_chains_kernel_time",
 ]
 
 
@@ -93,6 +95,12 @@ def load_library():
     L.npb_chains_consider_max_likelihood.argtypes = [vp, dp, dp]
     L.npb_chains_probe_tile_logdensity.argtypes = [vp, i64, ip, C.POINTER(C.c_float)]
     L.npb_chains_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.npb_chains_sweep_host_delta.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.POINTER(SweepStats), C.POINTER(i64)]
+    L.npb_chains_get_best_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
+    L.npb_chain_move_item.argtypes = [vp, i64, i64, C.c_int]
+    L.npb_chain_move_item_new.argtypes = [vp, i64, i64, dp, dp, C.POINTER(C.c_int)]
+    L.npb_chain_remove_cluster.argtypes = [vp, i64, C.c_int]
+    L.npb_chains_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -172,6 +180,7 @@ class Dataset:
         h = C.c_void_p()
         ctx.check(ctx._lib.npb_dataset_upload(ctx._h, _dp(X), self.N, self.D, C.byref(h)))
         self._h = h
+        self._chains = weakref.WeakSet()  # the library refuses to destroy a dataset under live chain handles
 
     def update(self, X):
         X = _f64(X)
@@ -180,7 +189,9 @@ class Dataset:
 
     def close(self):
         if self._h:
-            self.ctx._lib.npb_dataset_destroy(self._h)
+            for ch in list(self._chains):
+                ch.close()
+            self.ctx.check(self.ctx._lib.npb_dataset_destroy(self._h))
             self._h = None
 
 
@@ -297,6 +308,7 @@ class Chains:
         h = C.c_void_p()
         ctx.check(ctx._lib.npb_chains_create(ctx._h, dataset._h, self.C, self.Kmax, self.m_aux, self.K0, seed, C.byref(h)))
         self._h = h
+        dataset._chains.add(self)
 
     def sweep(self, sampler=ALG8, n_sweeps=1, want_stats=True):
         st = SweepStats()
@@ -315,6 +327,12 @@ class Chains:
     def set_option(self, name, value):
         """behaviour switch of this handle, e.g. ("d16_path", "auto" | "tc" | "tc2" | "fp32")"""
         self.ctx.check(self.ctx._lib.npb_chains_set_option(self._h, name.encode(), value.encode()))
+
+    def kernel_time(self):
+        """(ms, launches) of the dominant sweep kernel since the last call (after set_option("time_kernels", "1"))"""
+        ms, n = C.c_double(), C.c_int64()
+        self.ctx.check(self.ctx._lib.npb_chains_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def update_item(self, item, chain=-1):
         """one NealAlgorithm8::update(membertrix&, {item}) on `chain` (every chain if negative): the single-item seam"""
@@ -351,6 +369,28 @@ class Chains:
         self.ctx.check(self.ctx._lib.npb_chains_sweep_host(self._h, _dp(X), sampler, n_sweeps, zp,
                                                            C.byref(st) if want_stats else None))
         return st
+
+    def sweep_host_delta(self, X, sampler=ALG8, n_sweeps=1, z_mirror=None, want_stats=False):
+        """end-to-end step with an incremental result: z_mirror [N, C] uint16 is the caller's copy of the assignments; only the
+        entries that changed since the previous call travel.  Returns (stats, entries written)."""
+        st = SweepStats()
+        n = C.c_int64()
+        assert z_mirror is not None and z_mirror.dtype == np.uint16 and z_mirror.flags.c_contiguous
+        self.ctx.check(self.ctx._lib.npb_chains_sweep_host_delta(self._h, _dp(X) if X is not None else None, sampler, n_sweeps,
+                                                                 z_mirror.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                                                 C.byref(st) if want_stats else None, C.byref(n)))
+        return st, n.value
+
+    def move_item(self, chain, item, slot):
+        """membertrix::retract + assign of one item (status codes mirror np_error_t)"""
+        self.ctx.check(self.ctx._lib.npb_chain_move_item(self._h, chain, item, slot))
+
+    def move_item_new(self, chain, item, mu, Sigma):
+        """membertrix::addCluster + assign: the item founds a cluster; returns its slot"""
+        mu, Sigma = _f64(mu), _f64(Sigma)
+        slot = C.c_int()
+        self.ctx.check(self.ctx._lib.npb_chain_move_item_new(self._h, chain, item, _dp(mu), _dp(Sigma), C.byref(slot)))
+        return slot.value
 
     def set_state(self, chain, z, slots, mu, Sigma):
         z = np.ascontiguousarray(z, dtype=np.int32)
@@ -391,6 +431,19 @@ class Chains:
         Sigma = np.empty((cap, D, D))
         self.ctx.check(self.ctx._lib.npb_chains_get_params(self._h, chain, cap, C.byref(K), _ip(slots),
                                                            counts.ctypes.data_as(C.POINTER(C.c_int64)), _dp(mu), _dp(Sigma)))
+        k = K.value
+        return slots[:k].copy(), counts[:k].copy(), mu[:k].copy(), Sigma[:k].copy()
+
+    def best_params(self, chain):
+        """the clusters of the state kept by consider_max_likelihood (not of the current state)"""
+        cap, D = self.Kmax, self.ds.D
+        K = C.c_int()
+        slots = np.empty(cap, np.int32)
+        counts = np.empty(cap, np.int64)
+        mu = np.empty((cap, D))
+        Sigma = np.empty((cap, D, D))
+        self.ctx.check(self.ctx._lib.npb_chains_get_best_params(self._h, chain, cap, C.byref(K), _ip(slots),
+                                                                counts.ctypes.data_as(C.POINTER(C.c_int64)), _dp(mu), _dp(Sigma)))
         k = K.value
         return slots[:k].copy(), counts[:k].copy(), mu[:k].copy(), Sigma[:k].copy()
 

@@ -771,8 +771,19 @@ npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a) {
 			p.sw = sw;
 			p.s0 = s0;
 			p.nsteps = nsteps;
+			cudaEvent_t e0 = nullptr, e1 = nullptr;
+			if (ch->time_kernels) { // (bench.py: the dominant kernel's own duration, per launch, on the launching stream)
+				NPB_CUDA_OK(cudaEventCreate(&e0));
+				NPB_CUDA_OK(cudaEventCreate(&e1));
+				NPB_CUDA_OK(cudaEventRecord(e0, ctx->stream));
+			}
 			s = f_launch(ch, g, p, 1);
 			if (s != NPB_OK) return s;
+			if (ch->time_kernels) {
+				NPB_CUDA_OK(cudaEventRecord(e1, ctx->stream));
+				ch->kt_ev.push_back(e0);
+				ch->kt_ev.push_back(e1);
+			}
 		}
 	}
 	return NPB_OK;

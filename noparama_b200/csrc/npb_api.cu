@@ -109,7 +109,7 @@ static npb_status dataset_push(npb_dataset *ds, const double *X) {
 	k_to_float<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ds->X64, ds->X32, n);
 	NPB_CUDA_OK(cudaGetLastError());
 	ds->whitened_epoch = 0;
-	if (ds->Xbar) { cudaFree(ds->Xbar); ds->Xbar = nullptr; } // recomputed on demand (npb_alg8_gemm.cu)
+	ds->xbar_valid = false; // recomputed on demand into the same buffer (npb_alg8_gemm.cu)
 	return NPB_OK;
 }
 
@@ -133,7 +133,10 @@ npb_status npb_dataset_upload(npb_ctx *ctx, const double *X, int64_t N, int D, n
 	}
 	npb_status s = dataset_push(ds, X);
 	if (s != NPB_OK) { npb_dataset_destroy(ds); return s; }
-	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+		npb_dataset_destroy(ds);
+		return npb_fail_cuda(ctx, e, "dataset upload", __FILE__, __LINE__);
+	}
 	*out = ds;
 	return NPB_OK;
 }
@@ -148,6 +151,7 @@ npb_status npb_dataset_update(npb_dataset *ds, const double *X) {
 
 npb_status npb_dataset_destroy(npb_dataset *ds) {
 	if (!ds) return NPB_OK;
+	if (ds->n_chains_alive > 0) return npb_fail(ds->ctx, NPB_E_BAD_ARG, "chain handles still reference this dataset: destroy them first");
 	cudaSetDevice(ds->ctx->device);
 	cudaStreamSynchronize(ds->ctx->stream);
 	if (ds->X64) cudaFree(ds->X64);
@@ -276,7 +280,11 @@ npb_status npb_logdensity_sum(npb_ctx *ctx, npb_dataset *ds, const int64_t *rows
 }
 
 // ---- chains -------------------------------------------------------------------------------------------------
+__global__ void k_best_init(double *best, int C);
+
 static npb_status ensure_whitened(npb_dataset *ds) {
+	// (npb_prior_set_niw may have been called with another dimension since the dataset was uploaded)
+	if (!ds->ctx->prior.set || ds->ctx->prior.D != ds->D) return npb_fail(ds->ctx, NPB_E_BAD_ARG, "the context's prior is not of the dataset's dimension");
 	if (ds->whitened_epoch == ds->ctx->prior_epoch) return NPB_OK;
 	return npb_launch_whiten(ds);
 }
@@ -320,6 +328,8 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 	if (s == NPB_OK) s = npb_launch_chains_init(ch, ch->K0, nullptr);
 	if (s != NPB_OK) { npb_chains_destroy(ch); return s; }
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	ds->n_chains_alive++;
+	ch->counted = true;
 	*out = ch;
 	return NPB_OK;
 }
@@ -332,13 +342,47 @@ npb_status npb_chains_set_option(npb_chains *ch, const char *name, const char *v
 		strncpy(ch->opt_d16_path, value, sizeof(ch->opt_d16_path) - 1);
 		return NPB_OK;
 	}
+	if (!strcmp(name, "time_kernels")) {
+		ch->time_kernels = value[0] == '1';
+		return NPB_OK;
+	}
 	return npb_fail(ch->ctx, NPB_E_BAD_ARG, "unknown option");
+}
+
+// accumulated duration and number of launches of the dominant sweep kernel since the last call (option "time_kernels")
+npb_status npb_chains_kernel_time(npb_chains *ch, double *ms, int64_t *launches) {
+	if (!ch || !ms || !launches) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	for (size_t i = 0; i + 1 < ch->kt_ev.size(); i += 2) {
+		float t = 0.0f;
+		NPB_CUDA_OK(cudaEventElapsedTime(&t, ch->kt_ev[i], ch->kt_ev[i + 1]));
+		ch->kt_ms += t;
+		ch->kt_launches++;
+		cudaEventDestroy(ch->kt_ev[i]);
+		cudaEventDestroy(ch->kt_ev[i + 1]);
+	}
+	ch->kt_ev.clear();
+	*ms = ch->kt_ms;
+	*launches = ch->kt_launches;
+	ch->kt_ms = 0.0;
+	ch->kt_launches = 0;
+	return NPB_OK;
 }
 
 npb_status npb_chains_destroy(npb_chains *ch) {
 	if (!ch) return NPB_OK;
 	cudaSetDevice(ch->ctx->device);
 	cudaStreamSynchronize(ch->ctx->stream);
+	if (ch->counted && ch->ds) ch->ds->n_chains_alive--;
+	for (cudaEvent_t e : ch->kt_ev) cudaEventDestroy(e);
+	if (ch->z_prev) cudaFree(ch->z_prev);
+	if (ch->dl_idx) cudaFree(ch->dl_idx);
+	if (ch->dl_val) cudaFree(ch->dl_val);
+	if (ch->dl_count) cudaFree(ch->dl_count);
+	if (ch->h_dl_idx) cudaFreeHost(ch->h_dl_idx);
+	if (ch->h_dl_val) cudaFreeHost(ch->h_dl_val);
 	if (ch->z) cudaFree(ch->z);
 	if (ch->theta) cudaFree(ch->theta);
 	if (ch->counts) cudaFree(ch->counts);
@@ -395,6 +439,11 @@ npb_status npb_chains_init_from_params(npb_chains *ch, int K, const double *mu, 
 	NPB_CUDA_OK(cudaMemcpyAsync(d_th.p, th.data(), sizeof(float) * th.size(), cudaMemcpyHostToDevice, ctx->stream));
 	npb_status s = npb_launch_chains_init(ch, K, d_th.p);
 	if (s != NPB_OK) return s;
+	if (ch->best_jll) { // a new run: nothing kept yet (MCMC::run starts from -inf, np_mcmc.cpp:187-203)
+		k_best_init<<<(unsigned)((ch->C + 255) / 256), 256, 0, ctx->stream>>>(ch->best_jll, (int)ch->C);
+		NPB_CUDA_OK(cudaGetLastError());
+	}
+	ch->moved_frac_last = -1.0;
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }
@@ -601,16 +650,16 @@ npb_status npb_chains_get_assignments(npb_chains *ch, int64_t chain0, int64_t n,
 	return NPB_OK;
 }
 
-npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts, double *mu,
-		double *Sigma) {
+static npb_status get_params_from(npb_chains *ch, const float *theta, const int *counts_dev, int64_t chain, int cap, int *K, int32_t *slots,
+		int64_t *counts, double *mu, double *Sigma) {
 	if (!ch || !K || chain < 0 || chain >= ch->C) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
 	const int D = ch->D, TRI = npb_tri(D), PS = npb_ps(D);
 	std::vector<float> th((size_t)ch->Kmax * PS);
 	std::vector<int> cnt(ch->Kmax);
-	NPB_CUDA_OK(cudaMemcpyAsync(th.data(), ch->theta + (size_t)chain * ch->Kmax * PS, sizeof(float) * th.size(), cudaMemcpyDeviceToHost, ctx->stream));
-	NPB_CUDA_OK(cudaMemcpyAsync(cnt.data(), ch->counts + (size_t)chain * ch->Kmax, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(th.data(), theta + (size_t)chain * ch->Kmax * PS, sizeof(float) * th.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(cnt.data(), counts_dev + (size_t)chain * ch->Kmax, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, ctx->stream));
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	int k = 0;
 	std::vector<double> T(TRI);
@@ -630,6 +679,208 @@ npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K,
 	}
 	*K = k;
 	return k <= cap ? NPB_OK : NPB_E_BAD_ARG;
+}
+
+npb_status npb_chains_get_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts, double *mu,
+		double *Sigma) {
+	if (!ch) return NPB_E_BAD_ARG;
+	return get_params_from(ch, ch->theta, ch->counts, chain, cap, K, slots, counts, mu, Sigma);
+}
+
+// the clusters of the KEPT state (npb_chains_consider_max_likelihood), not of the current one: slots are re-used after a
+// death, so the current slot table does not describe a snapshot taken earlier
+npb_status npb_chains_get_best_params(npb_chains *ch, int64_t chain, int cap, int *K, int32_t *slots, int64_t *counts, double *mu,
+		double *Sigma) {
+	if (!ch) return NPB_E_BAD_ARG;
+	if (!ch->best_theta) return npb_fail(ch->ctx, NPB_E_BAD_ARG, "no state has been kept on this handle yet");
+	return get_params_from(ch, ch->best_theta, ch->best_counts, chain, cap, K, slots, counts, mu, Sigma);
+}
+
+// ---- the single-item seam of membertrix: retract + assign of one item of one chain (membertrix.cpp:147-233) ----------
+// status: 0 ok, NPB_E_ALREADY_ASSIGNED (the item already sits in that cluster), NPB_E_ASSIGNMENT_ABSENT (no such cluster: the
+// slot has no members and no parameters were given), NPB_E_KMAX_OVERFLOW (a new cluster found no free slot)
+__global__ void k_move_item(npb_z_t *z, int *counts, int *kocc, float *theta, int C, int Kmax, int PS, int chain, int item, int slot,
+		const float *theta_new, int *status) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	int *cnt = counts + (size_t)chain * Kmax;
+	const int zo = (int)z[(size_t)item * C + chain];
+	int to = slot;
+	if (theta_new) { // addCluster + assign: the lowest free slot once the item is retracted (np_neal_algorithm8.cpp:136-145)
+		to = -1;
+		for (int k = 0; k < Kmax && to < 0; ++k)
+			if (cnt[k] - (k == zo ? 1 : 0) <= 0) to = k;
+		if (to < 0) { status[0] = NPB_E_KMAX_OVERFLOW; return; }
+		for (int t = 0; t < PS; ++t) theta[((size_t)chain * Kmax + to) * PS + t] = theta_new[t];
+	} else {
+		if (to < 0 || to >= Kmax || cnt[to] <= 0) { status[0] = NPB_E_ASSIGNMENT_ABSENT; return; }
+		if (to == zo) { status[0] = NPB_E_ALREADY_ASSIGNED; return; }
+	}
+	int occ = kocc[chain];
+	if (to != zo) {
+		cnt[zo] -= 1;
+		if (cnt[zo] == 0) occ--;
+		if (cnt[to] == 0) occ++;
+		cnt[to] += 1;
+	}
+	kocc[chain] = occ;
+	z[(size_t)item * C + chain] = (npb_z_t)to;
+	status[0] = 0;
+	status[1] = to;
+}
+
+static npb_status move_item(npb_chains *ch, int64_t chain, int64_t item, int slot, const double *mu, const double *Sigma, int *slot_out) {
+	if (!ch || chain < 0 || chain >= ch->C || item < 0 || item >= ch->ds->N) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ch->D, TRI = npb_tri(D), PS = npb_ps(D);
+	DevBuf<float> d_th;
+	DevBuf<int> d_status;
+	NPB_CUDA_OK(d_status.alloc(2));
+	if (mu) {
+		std::vector<float> th(PS);
+		std::vector<double> T(TRI);
+		double logdet;
+		if (!npb_prepare_theta(D, mu, Sigma, T.data(), &logdet))
+			return npb_fail(ctx, NPB_E_NOT_POSITIVE, "Sigma is not invertible with a positive definite symmetric precision");
+		for (int d = 0; d < D; ++d) th[d] = (float)mu[d];
+		for (int t = 0; t < TRI; ++t) th[D + t] = (float)(T[t] * NPB_HALF_LOG2E_SQRT);
+		th[D + TRI] = (float)(-0.5 * (D * std::log2(2.0 * M_PI) + logdet / std::log(2.0)));
+		NPB_CUDA_OK(d_th.alloc(PS));
+		NPB_CUDA_OK(cudaMemcpyAsync(d_th.p, th.data(), sizeof(float) * PS, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	k_move_item<<<1, 32, 0, ctx->stream>>>(ch->z, ch->counts, ch->kocc, ch->theta, (int)ch->C, ch->Kmax, PS, (int)chain, (int)item, slot,
+			mu ? d_th.p : nullptr, d_status.p);
+	NPB_CUDA_OK(cudaGetLastError());
+	int st[2] = {0, 0};
+	NPB_CUDA_OK(cudaMemcpyAsync(st, d_status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if (st[0] != 0) return npb_fail(ctx, (npb_status)st[0], st[0] == NPB_E_ALREADY_ASSIGNED ? "the item is already assigned to that cluster"
+			: st[0] == NPB_E_ASSIGNMENT_ABSENT ? "no such cluster on this chain" : "no free cluster slot");
+	if (slot_out) *slot_out = st[1];
+	return NPB_OK;
+}
+npb_status npb_chain_move_item(npb_chains *ch, int64_t chain, int64_t item, int slot) {
+	return move_item(ch, chain, item, slot, nullptr, nullptr, nullptr);
+}
+npb_status npb_chain_move_item_new(npb_chains *ch, int64_t chain, int64_t item, const double *mu, const double *Sigma, int *slot_out) {
+	if (!mu || !Sigma) return NPB_E_BAD_ARG;
+	return move_item(ch, chain, item, -1, mu, Sigma, slot_out);
+}
+
+// membertrix::remove (membertrix.cpp:213-228): a cluster can only be removed once it has no members -- at which point the
+// device has dropped it already (a slot without members is free)
+npb_status npb_chain_remove_cluster(npb_chains *ch, int64_t chain, int slot) {
+	if (!ch || chain < 0 || chain >= ch->C || slot < 0 || slot >= ch->Kmax) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	int n = 0;
+	NPB_CUDA_OK(cudaMemcpyAsync(&n, ch->counts + (size_t)chain * ch->Kmax + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	if (n > 0) return npb_fail(ctx, NPB_E_ASSIGNMENT_REMAINING, "the cluster still has members");
+	return NPB_OK;
+}
+
+// ---- incremental result copy ------------------------------------------------------------------------------------
+// entries of z that differ from the snapshot: (index, value) appended to a list (a warp reserves its run with one atomic),
+// the snapshot brought up to date.  Eight entries per thread (one 16-byte load of each array).
+__global__ void __launch_bounds__(256) k_z_delta(const npb_z_t *z, npb_z_t *prev, size_t n8, uint32_t *idx, npb_z_t *val, size_t cap,
+		unsigned long long *count) {
+	const size_t i8 = (size_t)blockIdx.x * 256 + threadIdx.x;
+	uint4 a = make_uint4(0, 0, 0, 0), b = a;
+	if (i8 < n8) {
+		a = reinterpret_cast<const uint4 *>(z)[i8];
+		b = reinterpret_cast<const uint4 *>(prev)[i8];
+	}
+	const unsigned short *pa = reinterpret_cast<const unsigned short *>(&a), *pb = reinterpret_cast<const unsigned short *>(&b);
+	unsigned diff = 0u;
+#pragma unroll
+	for (int e = 0; e < 8; ++e) diff |= (pa[e] != pb[e]) ? (1u << e) : 0u;
+	const int mine = __popc(diff);
+	// exclusive scan of the counts over the warp, one atomic per warp
+	int incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((int)(threadIdx.x & 31) >= o) incl += t;
+	}
+	const int total = __shfl_sync(0xffffffffu, incl, 31);
+	if (total == 0) return;
+	unsigned long long base = 0ull;
+	if ((threadIdx.x & 31) == 31) base = atomicAdd(count, (unsigned long long)total);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	if (mine) {
+		size_t o = (size_t)base + (size_t)(incl - mine);
+#pragma unroll
+		for (int e = 0; e < 8; ++e) {
+			if ((diff >> e) & 1u) {
+				if (o < cap) {
+					idx[o] = (uint32_t)(i8 * 8 + e);
+					val[o] = pa[e];
+				}
+				++o;
+			}
+		}
+		reinterpret_cast<uint4 *>(prev)[i8] = a;
+	}
+}
+
+npb_status npb_chains_sweep_host_delta(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_mirror,
+		npb_sweep_stats *stats, int64_t *n_changed) {
+	if (!ch || !z_mirror) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)ch->ds->N * ch->C;
+	if (n >= ((size_t)1 << 32) || (n & 7)) return npb_fail(ctx, NPB_E_UNSUPPORTED, "the incremental copy needs N * chains below 2^32 and a multiple of 8");
+	npb_status s = sweep_common(ch, sampler, n_sweeps, 0, stats, X, nullptr);
+	if (s != NPB_OK) return s;
+	const bool first = ch->z_prev == nullptr;
+	if (first) {
+		ch->dl_cap = n / 4;
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->z_prev, n * sizeof(npb_z_t)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->dl_idx, ch->dl_cap * sizeof(uint32_t)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->dl_val, ch->dl_cap * sizeof(npb_z_t)));
+		NPB_CUDA_OK(cudaMalloc((void **)&ch->dl_count, sizeof(unsigned long long)));
+	}
+	unsigned long long cnt = 0ull;
+	if (!first) {
+		NPB_CUDA_OK(cudaMemsetAsync(ch->dl_count, 0, sizeof(unsigned long long), ctx->stream));
+		k_z_delta<<<(unsigned)((n / 8 + 255) / 256), 256, 0, ctx->stream>>>(ch->z, ch->z_prev, n / 8, ch->dl_idx, ch->dl_val, ch->dl_cap, ch->dl_count);
+		NPB_CUDA_OK(cudaGetLastError());
+		NPB_CUDA_OK(cudaMemcpyAsync(&cnt, ch->dl_count, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+		NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	}
+	if (first || cnt > ch->dl_cap) {
+		// everything travels: the first call, or more than a quarter of the entries changed (the list would be larger than the array)
+		cudaPointerAttributes attr;
+		const bool direct = cudaPointerGetAttributes(&attr, z_mirror) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+		if (!direct) cudaGetLastError();
+		if (!direct && !ch->h_z) NPB_CUDA_OK(cudaMallocHost((void **)&ch->h_z, n * sizeof(npb_z_t)));
+		NPB_CUDA_OK(cudaMemcpyAsync(direct ? (void *)z_mirror : (void *)ch->h_z, ch->z, n * sizeof(npb_z_t), cudaMemcpyDeviceToHost, ctx->stream));
+		if (first) NPB_CUDA_OK(cudaMemcpyAsync(ch->z_prev, ch->z, n * sizeof(npb_z_t), cudaMemcpyDeviceToDevice, ctx->stream));
+		NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+		if (!direct) memcpy(z_mirror, ch->h_z, n * sizeof(npb_z_t));
+		if (n_changed) *n_changed = first ? (int64_t)n : (int64_t)cnt;
+		return NPB_OK;
+	}
+	if (cnt > 0) {
+		if (cnt > ch->h_dl_cap) {
+			if (ch->h_dl_idx) cudaFreeHost(ch->h_dl_idx);
+			if (ch->h_dl_val) cudaFreeHost(ch->h_dl_val);
+			ch->h_dl_idx = nullptr;
+			ch->h_dl_val = nullptr;
+			size_t cap = ch->h_dl_cap ? ch->h_dl_cap : 4096;
+			while (cap < cnt) cap *= 2;
+			NPB_CUDA_OK(cudaMallocHost((void **)&ch->h_dl_idx, cap * sizeof(uint32_t)));
+			NPB_CUDA_OK(cudaMallocHost((void **)&ch->h_dl_val, cap * sizeof(npb_z_t)));
+			ch->h_dl_cap = cap;
+		}
+		NPB_CUDA_OK(cudaMemcpyAsync(ch->h_dl_idx, ch->dl_idx, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		NPB_CUDA_OK(cudaMemcpyAsync(ch->h_dl_val, ch->dl_val, cnt * sizeof(npb_z_t), cudaMemcpyDeviceToHost, ctx->stream));
+		NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+		for (size_t i = 0; i < cnt; ++i) z_mirror[ch->h_dl_idx[i]] = ch->h_dl_val[i];
+	}
+	if (n_changed) *n_changed = (int64_t)cnt;
+	return NPB_OK;
 }
 
 npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *purity, double *rand_index, double *adjusted_rand,

@@ -36,7 +36,9 @@ struct npb_dataset {
 	float *Xwn = nullptr;   // [N] Euclidean norm of the whitened row
 	uint64_t whitened_epoch = 0;
 	double *h_stage = nullptr; // pinned staging for uploads
-	double *Xbar = nullptr;    // [D] column means (D = 64 path: operands are centred before the TF32 split)
+	double *Xbar = nullptr;    // [2 D + 1] column means, scale exponent, column maxima (tensor paths: operands are centred before the split)
+	bool xbar_valid = false;   // Xbar describes the current contents (npb_dataset_update invalidates it; the buffer is kept)
+	int n_chains_alive = 0;    // chain handles that reference this dataset
 };
 
 struct npb_chains {
@@ -48,6 +50,11 @@ struct npb_chains {
 	uint32_t sweep = 0;         // sweeps done so far (Philox counter / scan-order key)
 	char opt_d16_path[8] = {0}; // NPB_D16_PATH as read when the handle was created (auto / tc / tc2 / fp32)
 	double moved_frac_last = -1.0; // moved / reassignments of the last Algorithm 8 launch whose statistics were read; -1 unknown
+	bool time_kernels = false;  // option "time_kernels": CUDA events around every launch of the dominant sweep kernel
+	std::vector<cudaEvent_t> kt_ev; // pairs (start, stop) not yet read back
+	double kt_ms = 0.0;         // accumulated duration of the launches read back so far
+	int64_t kt_launches = 0;
+	bool counted = false;       // this handle is counted in ds->n_chains_alive
 	uint32_t init_epoch = 0;    // initialisations from given parameters so far (distinct initial assignments per call)
 	uint32_t item_calls = 0;    // single-item updates so far (Philox counter of npb_chain_update_alg8)
 	npb_z_t *z = nullptr;       // [N, C] item-major
@@ -89,6 +96,14 @@ struct npb_chains {
 	int g_bs = 0;                  // steps per block
 	uint32_t g_k = 0;              // blocks consumed so far (parity selects the table / born-mask buffer)
 	uint32_t *g_born = nullptr;    // [2][C] slots born during block k (buffer k & 1)
+	npb_z_t *z_prev = nullptr;     // [N, C] npb_chains_sweep_host_delta: the assignments the caller's mirror holds
+	uint32_t *dl_idx = nullptr;    // [dl_cap] indices (item * C + chain) of the entries that changed
+	npb_z_t *dl_val = nullptr;     // [dl_cap] their new values
+	unsigned long long *dl_count = nullptr; // device counter
+	size_t dl_cap = 0;
+	uint32_t *h_dl_idx = nullptr;  // pinned staging, grown on demand
+	npb_z_t *h_dl_val = nullptr;
+	size_t h_dl_cap = 0;
 	npb_z_t *g_zblk = nullptr;     // [C][g_bs] fused D = 16 kernel: assignments of the current block's items, in step order
 };
 

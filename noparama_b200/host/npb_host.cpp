@@ -33,10 +33,10 @@ membertrix::membertrix(device &dev, dataset_t &dataset, int D) : dev_(dev), data
 	}
 	dev_.check(npb_dataset_upload(dev_.ctx(), X.data(), N_, D_, &ds_));
 }
-membertrix::~membertrix() { npb_dataset_destroy(ds_); }
+membertrix::~membertrix() { if (!detached_) npb_dataset_destroy(ds_); }
 
 void membertrix::refresh() {
-	if (!dirty_ || !chains) return;
+	if (!dirty_ || !chains || detached_) return;
 	const int cap = npb_chains_kmax(chains);
 	z_.resize(N_);
 	slots_.resize(cap);
@@ -52,7 +52,66 @@ void membertrix::refresh() {
 }
 cluster_id_t membertrix::getClusterId(data_id_t i) {
 	refresh();
-	return (i >= 0 && i < N_) ? z_[i] : -1;
+	if (i < 0 || i >= N_ || pending_.count(i)) return -1;
+	return z_[i];
+}
+
+// ---- mutators: the reference's single-item interface (membertrix.cpp:87-233) over the device state ----
+cluster_id_t membertrix::addCluster(const Suffies_MultivariateNormal &suffies) {
+	// the reference hands out the next column index (membertrix.cpp:108-117); here a host-side id beyond the device's slot range
+	// until the cluster gets its first member, at which point it becomes the lowest free device slot
+	const cluster_id_t id = npb_chains_kmax(chains) + (cluster_id_t)added_.size() + (added_.empty() ? 0 : added_.rbegin()->first - npb_chains_kmax(chains));
+	added_[id] = suffies;
+	return id;
+}
+np_error_t membertrix::retract(data_id_t i, bool auto_remove) {
+	refresh();
+	if (i < 0 || i >= N_ || pending_.count(i)) return error_assignment_absent; // membertrix.cpp:177-180
+	(void)auto_remove; // the device drops a cluster with its last member (membertrix.cpp:200-203); the host copy follows on refresh
+	pending_[i] = z_[i];
+	return error_none;
+}
+np_error_t membertrix::assign(cluster_id_t k, data_id_t i) {
+	refresh();
+	if (i < 0 || i >= N_) return error_assignment_absent;
+	auto pend = pending_.find(i);
+	if (pend == pending_.end()) return error_already_assigned; // membertrix.cpp:148-151: retract first
+	npb_status s;
+	auto add = added_.find(k);
+	if (add != added_.end()) {
+		int slot = -1;
+		s = npb_chain_move_item_new(chains, chain_, i, add->second.mu.data(), add->second.sigma.data(), &slot);
+		if (s == NPB_OK) added_.erase(add);
+	} else if (k == pend->second) {
+		s = NPB_OK; // back where it was: nothing moved on the device
+	} else {
+		s = npb_chain_move_item(chains, chain_, i, k);
+	}
+	if (s == NPB_E_ASSIGNMENT_ABSENT) return error_assignment_absent;
+	if (s == NPB_E_ALREADY_ASSIGNED) return error_already_assigned;
+	dev_.check(s);
+	pending_.erase(pend);
+	dirty_ = true;
+	return error_none;
+}
+np_error_t membertrix::remove(cluster_id_t k) {
+	if (added_.erase(k)) return error_none;
+	const npb_status s = npb_chain_remove_cluster(chains, chain_, k);
+	if (s == NPB_E_ASSIGNMENT_REMAINING) return error_assignment_remaining; // membertrix.cpp:214-216
+	dev_.check(s);
+	return error_none;
+}
+np_error_t membertrix::cleanup() {
+	added_.clear(); // clusters without members; on the device a slot without members is free already
+	return error_none;
+}
+membertrix *membertrix::clone() {
+	refresh();
+	membertrix *c = new membertrix(*this);
+	c->detached_ = true; // a copy of the host view: it owns no device handle and never refreshes
+	c->chains = nullptr;
+	c->ds_ = nullptr;
+	return c;
 }
 size_t membertrix::getClusterCount() {
 	refresh();
@@ -181,6 +240,24 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam, UpdateClusters *up
 
 void MCMC::considerMaxLikelihood() {
 	dev_.check(npb_chains_consider_max_likelihood(trix_->chains, nullptr, nullptr));
+}
+std::map<cluster_id_t, Suffies_MultivariateNormal> MCMC::getMaxLikelihoodClusters(int64_t chain) {
+	// the clusters as they were when the state was kept: slot ids are re-used after a death, so the CURRENT slot table may
+	// describe other clusters under the same ids
+	const int cap = npb_chains_kmax(trix_->chains), D = trix_->dim();
+	std::vector<int32_t> slots(cap);
+	std::vector<int64_t> counts(cap);
+	std::vector<double> mu((size_t)cap * D), sigma((size_t)cap * D * D);
+	int K = 0;
+	dev_.check(npb_chains_get_best_params(trix_->chains, chain, cap, &K, slots.data(), counts.data(), mu.data(), sigma.data()));
+	std::map<cluster_id_t, Suffies_MultivariateNormal> out;
+	for (int k = 0; k < K; ++k) {
+		Suffies_MultivariateNormal s(D);
+		std::copy(mu.begin() + (size_t)k * D, mu.begin() + (size_t)(k + 1) * D, s.mu.begin());
+		std::copy(sigma.begin() + (size_t)k * D * D, sigma.begin() + (size_t)(k + 1) * D * D, s.sigma.begin());
+		out[slots[k]] = s;
+	}
+	return out;
 }
 std::vector<int32_t> MCMC::getMaxLikelihoodAssignments(int64_t chain) {
 	std::vector<int32_t> z(trix_->size());

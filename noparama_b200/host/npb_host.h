@@ -88,6 +88,18 @@ public:
 	void getAssignments(cluster_id_t k, data_ids_t &ids);                                // :315-322
 	bool assigned(data_id_t i) { return getClusterId(i) >= 0; }                          // :166-168
 	void relabel() {}                                                                    // :259-262
+	// mutators (membertrix.h:106-152, membertrix.cpp:87-233, 343-364).  The device holds complete states only (every item
+	// in a cluster), so a retracted item is pending on the host until it is assigned again; assign() then moves it on the
+	// device in one call (npb_chain_move_item / npb_chain_move_item_new).  A cluster added with addCluster lives on the
+	// host until its first member arrives.  Error codes are the reference's np_error_t.
+	cluster_id_t addCluster(const Suffies_MultivariateNormal &suffies);                  // :87-118
+	np_error_t assign(cluster_id_t k, data_id_t i);                                      // :147-164
+	np_error_t retract(data_id_t i, bool auto_remove = true);                            // :175-233 (both overloads)
+	np_error_t remove(cluster_id_t k);                                                   // :213-228
+	np_error_t cleanup();                                                                // :343-364: drop clusters without members
+	bool empty(cluster_id_t k) { return count(k) == 0; }                                 // :324-326
+	int pending() const { return (int)pending_.size(); }                                 // items retracted and not yet assigned
+	membertrix *clone();                                                                 // :57-78: a detached, read-only copy
 	void select_chain(int64_t chain) { chain_ = chain; dirty_ = true; }
 	// device side
 	npb_dataset *dataset_handle() const { return ds_; }
@@ -105,6 +117,9 @@ private:
 	std::vector<int32_t> slots_;
 	std::vector<int64_t> counts_;
 	std::vector<double> mu_, sigma_;
+	std::map<data_id_t, cluster_id_t> pending_;                       // retracted item -> the cluster it still occupies on the device
+	std::map<cluster_id_t, Suffies_MultivariateNormal> added_;        // clusters without members yet: host only, ids >= Kmax
+	bool detached_ = false;                                            // clone(): no device behind it
 };
 
 // include/np_update_cluster_population.h:13-44
@@ -216,6 +231,7 @@ public:
 	~MCMC();
 	void run(dataset_t &dataset, int T, bool per_item_seam = false, UpdateClusters *update_clusters = nullptr);
 	membertrix &getMembershipMatrix() { return *trix_; }                  // np_mcmc.h:88
+	std::map<cluster_id_t, Suffies_MultivariateNormal> getMaxLikelihoodClusters(int64_t chain = 0); // the kept state's clusters
 	std::vector<int32_t> getMaxLikelihoodAssignments(int64_t chain = 0);  // np_mcmc.h:90: the state kept by considerMaxLikelihood
 	void considerMaxLikelihood();                                         // np_mcmc.cpp:187-203, every chain at once
 	clustering_scores scores(const std::vector<int> &ground_truth);        // np_results.cpp:17-37 + clustering_performance

@@ -135,3 +135,39 @@ def test_cli_writes_results_like_the_reference(tmp_path):
         assert rows <= 200 and rows > 150  # every item of a cluster that still has parameters is dumped once
     pur = float(re.search(r"Purity: ([0-9.]+)", (d / "results.score.txt").read_text()).group(1))
     assert pur > 0.95
+
+
+@pytest.mark.gpu
+def test_cli_membertrix_mutators_selftest(tmp_path):
+    """membertrix::{addCluster, assign, retract, remove, clone} of the host mirror over the device state, with the reference's
+    np_error_t codes: the reference's own unit test of the class (test/test_membertrix.cpp:75-91) through the single-item ABI
+    calls npb_chain_move_item / npb_chain_move_item_new / npb_chain_remove_cluster."""
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    for seed in ("3", "11"):
+        r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-c", "clustering", "--seed", seed, "--selftest-membertrix"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and "membertrix selftest passed" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_gpus_flag_shards_chains(tmp_path):
+    """--gpus G: one host thread and object graph per device, chains split in contiguous blocks, scores gathered (here G = 1 and,
+    where a second device exists, G = 2)."""
+    import torch
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    for g in (1, 2):
+        if g > torch.cuda.device_count():
+            continue
+        r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "60", "-c", "clustering", "--chains", "16", "--kmax", "64",
+                            "--gpus", str(g)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        if g > 1:
+            m = re.search(r"All 16 chains on 2 devices: purity ([0-9.]+)", r.stdout)
+            assert m and float(m.group(1)) > 0.9, r.stdout
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "5", "-c", "clustering", "--chains", "2", "--gpus", "4"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "--gpus" in r.stderr
