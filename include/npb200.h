@@ -120,6 +120,10 @@ npb_status npb_chains_kernel_time(npb_chains *ch, double *ms, int64_t *launches)
 npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z, int K, const int32_t *slots,
 		const double *mu, const double *Sigma);
 
+/* every chain takes the state of chain `src` (assignments, clusters, counts); their random streams stay their own.  For tests
+ * of the sampler's law: many chains making the same reassignment independently. */
+npb_status npb_chains_broadcast_state(npb_chains *ch, int64_t src);
+
 /* re-initialise EVERY chain with the same K given clusters (slots 0..K-1) and a fresh uniform assignment of the items
  * to them: the InitClusters step (np_init_clusters.cpp:24-41) with caller-supplied instead of prior-drawn parameters */
 npb_status npb_chains_init_from_params(npb_chains *ch, int K, const double *mu /* [K,D] */, const double *Sigma /* [K,D,D] */);

@@ -31,7 +31,7 @@ EXPORTS = [
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
     "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
     "npb_chains_probe_tile_logdensity", "npb_chains_set_option", "npb_chains_sweep_host_delta", "npb_chains_get_best_params",
-    "npb_chain_move_item", "npb_chain_move_item_new", "npb_chain_remove_cluster", "npb_chains_kernel_time",
+    "npb_chain_move_item", "npb_chain_move_item_new", "npb_chain_remove_cluster", "npb_chains_kernel_time", "npb_chains_broadcast_state",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
     L.npb_chain_move_item_new.argtypes = [vp, i64, i64, dp, dp, C.POINTER(C.c_int)]
     L.npb_chain_remove_cluster.argtypes = [vp, i64, C.c_int]
     L.npb_chains_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.npb_chains_broadcast_state.argtypes = [vp, i64]
     L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -397,6 +398,10 @@ class Chains:
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         mu, Sigma = _f64(mu), _f64(Sigma)
         self.ctx.check(self.ctx._lib.npb_chains_set_state(self._h, chain, _ip(z), len(slots), _ip(slots), _dp(mu), _dp(Sigma)))
+
+    def broadcast_state(self, src=0):
+        """every chain takes chain src's assignments and clusters (their random streams stay their own)"""
+        self.ctx.check(self.ctx._lib.npb_chains_broadcast_state(self._h, src))
 
     def init_from_params(self, mu, Sigma):
         """every chain restarts from the same K clusters (given parameters) and a uniform random assignment"""

@@ -767,6 +767,37 @@ npb_status npb_chain_move_item_new(npb_chains *ch, int64_t chain, int64_t item, 
 	return move_item(ch, chain, item, -1, mu, Sigma, slot_out);
 }
 
+// every chain of the handle takes the state of chain `src` (assignments, slot table, counts): the starting point of the
+// categorical tests, where 2^17 chains make the same first reassignment independently
+__global__ void k_broadcast_z(npb_z_t *z, int N, int C, int src) {
+	const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+	if (i >= (size_t)N * C) return;
+	const size_t item = i / C;
+	z[i] = z[item * C + src];
+}
+__global__ void k_broadcast_slots(float *theta, int *counts, int *kocc, int *overflow, int C, int Kmax, int PS, int src) {
+	const int c = blockIdx.x;
+	if (c == src) return;
+	for (int t = threadIdx.x; t < Kmax * PS; t += blockDim.x) theta[(size_t)c * Kmax * PS + t] = theta[(size_t)src * Kmax * PS + t];
+	for (int t = threadIdx.x; t < Kmax; t += blockDim.x) counts[(size_t)c * Kmax + t] = counts[(size_t)src * Kmax + t];
+	if (threadIdx.x == 0) { kocc[c] = kocc[src]; overflow[c] = 0; }
+}
+npb_status npb_chains_broadcast_state(npb_chains *ch, int64_t src) {
+	if (!ch || src < 0 || src >= ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)ch->ds->N * ch->C;
+	// (z of chain src is read while other chains' entries of the same rows are written: entries of chain src itself are rewritten
+	// with their own value, so the race is benign)
+	k_broadcast_z<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ch->z, (int)ch->ds->N, (int)ch->C, (int)src);
+	NPB_CUDA_OK(cudaGetLastError());
+	k_broadcast_slots<<<(unsigned)ch->C, 128, 0, ctx->stream>>>(ch->theta, ch->counts, ch->kocc, ch->overflow, (int)ch->C, ch->Kmax, npb_ps(ch->D), (int)src);
+	NPB_CUDA_OK(cudaGetLastError());
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	ch->moved_frac_last = -1.0;
+	return NPB_OK;
+}
+
 // membertrix::remove (membertrix.cpp:213-228): a cluster can only be removed once it has no members -- at which point the
 // device has dropped it already (a slot without members is free)
 npb_status npb_chain_remove_cluster(npb_chains *ch, int64_t chain, int slot) {
