@@ -43,7 +43,12 @@ enum {
 /* samplers selectable by -a (src/np_main.cpp:212-236, 424-459).  NPB_ALG2 is the sampler src/np_neal_algorithm2.cpp:32-120
  * describes (the reference does not compile it): K weights p(x|theta_k) n_k plus ONE prior draw weighted p(x|theta') alpha --
  * the Algorithm 8 kernels with a single auxiliary draw; it needs chains created with m_aux = 1. */
-enum { NPB_ALG8 = 8, NPB_ALG2 = 2, NPB_JAIN_NEAL = 20, NPB_TRIADIC = 30 };
+enum { NPB_ALG8 = 8, NPB_ALG2 = 2, NPB_JAIN_NEAL = 20, NPB_TRIADIC = 30,
+       /* the CONJUGATE (collapsed) Algorithm 2 BASELINE configs[3] names: NIW posterior-predictive weights n_k pred_k(x) and
+        * alpha pred_0(x), sufficient statistics up- and down-dated on insert and removal.  The reference has no executable
+        * form of it (np_neal_algorithm2.cpp:32-120 is dead code, normalinvwishart.h:66-75 asserts false): textbook model,
+        * parity against the reference unpinned.  Kmax = 32; D = 2, 4, 8, 16, 64; the context's NIW prior with nu > D - 1. */
+       NPB_ALG2_CONJUGATE = 22 };
 
 /* behaviour switches of npb_prior_set_niw; the default (all bug-compatible flags set) reproduces the
  * reference, quirk numbers refer to SURVEY.md 7.4 */
@@ -162,6 +167,12 @@ npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, i
  * a converged chain changes a handful of them.) */
 npb_status npb_chains_sweep_host_delta(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_mirror,
 		npb_sweep_stats *stats, int64_t *n_changed);
+
+/* conjugate Algorithm 2 parity probes: the posterior-predictive log-densities of `items` under every cluster of `chain` as the
+ * sweep kernel evaluates them (out [n_items, 33]; NaN without members; column 32 = prior predictive), and the sufficient
+ * statistics the path keeps (counts [32], sum x [32, D], sum x x^T [32, D, D]) */
+npb_status npb_chains_alg2_logpred(npb_chains *ch, int64_t chain, const int32_t *items, int n_items, float *out);
+npb_status npb_chains_alg2_suffstats(npb_chains *ch, int64_t chain, int32_t *counts, double *sx, double *sxx);
 
 /* membertrix::retract + membertrix::assign of one item of one chain (membertrix.cpp:147-233), for a host that drives single
  * reassignments itself: the item moves to the occupied cluster `slot`; a cluster left without members disappears

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnpb200.so")
 
 ALG8, ALG2, JAIN_NEAL, TRIADIC = 8, 2, 20, 30
+ALG2_CONJUGATE = 22  # collapsed Gibbs with the NIW posterior predictive (BASELINE configs[3]; not in the reference)
 UPDATE_POSTERIOR_DRAW, UPDATE_POSTERIOR_MEAN = 1, 2
 BUGCOMPAT_DEGENERATE_IW, BUGCOMPAT_UNDERFLOW = 1, 2
 BUGCOMPAT_DEFAULT = BUGCOMPAT_DEGENERATE_IW
@@ -31,7 +32,7 @@ EXPORTS = [
     "npb_chains_count", "npb_chains_kmax", "npb_scan_order_host", "npb_fp32_peak", "npb_chains_init_from_params",
     "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
     "npb_chains_probe_tile_logdensity", "npb_chains_set_option", "npb_chains_sweep_host_delta", "npb_chains_get_best_params",
-    "npb_chain_move_item", "npb_chain_move_item_new", "npb_chain_remove_cluster", "npb_chains_kernel_time", "npb_chains_broadcast_state",
+    "npb_chain_move_item", "npb_chain_move_item_new", "npb_chain_remove_cluster", "npb_chains_kernel_time", "npb_chains_broadcast_state", "npb_chains_alg2_logpred", "npb_chains_alg2_suffstats",
 ]
 
 
@@ -102,6 +103,8 @@ def load_library():
     L.npb_chain_remove_cluster.argtypes = [vp, i64, C.c_int]
     L.npb_chains_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.npb_chains_broadcast_state.argtypes = [vp, i64]
+    L.npb_chains_alg2_logpred.argtypes = [vp, i64, ip, C.c_int, C.POINTER(C.c_float)]
+    L.npb_chains_alg2_suffstats.argtypes = [vp, i64, ip, dp, dp]
     L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -398,6 +401,21 @@ class Chains:
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         mu, Sigma = _f64(mu), _f64(Sigma)
         self.ctx.check(self.ctx._lib.npb_chains_set_state(self._h, chain, _ip(z), len(slots), _ip(slots), _dp(mu), _dp(Sigma)))
+
+    def alg2_logpred(self, chain, items):
+        """[n, 33] NIW posterior-predictive log-densities of `items` under the clusters of `chain` (column 32: the prior's)"""
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        out = np.empty((len(items), 33), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.npb_chains_alg2_logpred(self._h, chain, _ip(items), len(items), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def alg2_suffstats(self, chain):
+        """(counts [32], sum x [32, D], sum x x^T [32, D, D]) the conjugate path keeps for `chain`"""
+        D = self.ds.D
+        n = np.empty(32, np.int32)
+        sx, sxx = np.empty((32, D)), np.empty((32, D, D))
+        self.ctx.check(self.ctx._lib.npb_chains_alg2_suffstats(self._h, chain, _ip(n), _dp(sx), _dp(sxx)))
+        return n, sx, sxx
 
     def broadcast_state(self, src=0):
         """every chain takes chain src's assignments and clusters (their random streams stay their own)"""

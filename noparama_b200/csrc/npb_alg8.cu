@@ -168,12 +168,19 @@ __global__ void k_scan_order(int32_t *order, int N, uint64_t seed, uint32_t swee
 	order[(size_t)blockIdx.y * N + s] = (int32_t)npb_scan_item(so, (uint32_t)s);
 }
 
-static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
+npb_status npb_launch_scan_order(npb_chains *ch, int n_sweeps) {
 	npb_ctx *ctx = ch->ctx;
 	const int N = (int)ch->ds->N;
 	dim3 grid((N + 255) / 256, n_sweeps);
 	k_scan_order<<<grid, 256, 0, ctx->stream>>>(ch->scan_order, N, ch->seed, ch->sweep);
 	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}
+
+static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
+	npb_ctx *ctx = ch->ctx;
+	npb_status so = npb_launch_scan_order(ch, n_sweeps);
+	if (so != NPB_OK) return so;
 	SweepArgs a = make_args(ch, n_sweeps);
 	npb_status s = NPB_E_UNSUPPORTED;
 	int key = ch->D * 1000 + ch->Kmax / 32;

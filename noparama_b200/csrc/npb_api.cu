@@ -377,6 +377,9 @@ npb_status npb_chains_destroy(npb_chains *ch) {
 	cudaStreamSynchronize(ch->ctx->stream);
 	if (ch->counted && ch->ds) ch->ds->n_chains_alive--;
 	for (cudaEvent_t e : ch->kt_ev) cudaEventDestroy(e);
+	for (void *q : {(void *)ch->a2_sx, (void *)ch->a2_sxx, (void *)ch->a2_work, (void *)ch->a2_prior, (void *)ch->a2_mu, (void *)ch->a2_P, (void *)ch->a2_ld,
+			(void *)ch->a2_G, (void *)ch->a2_lp0})
+		if (q) cudaFree(q);
 	if (ch->z_prev) cudaFree(ch->z_prev);
 	if (ch->dl_idx) cudaFree(ch->dl_idx);
 	if (ch->dl_val) cudaFree(ch->dl_val);
@@ -444,6 +447,7 @@ npb_status npb_chains_init_from_params(npb_chains *ch, int K, const double *mu, 
 		NPB_CUDA_OK(cudaGetLastError());
 	}
 	ch->moved_frac_last = -1.0;
+	ch->z_gen++;
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }
@@ -499,6 +503,7 @@ npb_status npb_chains_set_state(npb_chains *ch, int64_t chain, const int32_t *z,
 	NPB_CUDA_OK(cudaMemcpyAsync(ch->counts + (size_t)chain * ch->Kmax, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, ctx->stream));
 	NPB_CUDA_OK(cudaMemcpyAsync(ch->kocc + chain, &occ, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	ch->z_gen++;
 	return NPB_OK;
 }
 
@@ -548,6 +553,8 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_
 		if (ch->m_aux != 1) return npb_fail(ctx, NPB_E_BAD_ARG, "Algorithm 2 runs on chains created with m_aux = 1");
 		sampler = NPB_ALG8;
 	}
+	const bool conjugate = sampler == NPB_ALG2_CONJUGATE;
+	if (conjugate) sampler = NPB_ALG8; // (statistics are the Algorithm 8 ones: candidates, moved, births)
 	if (sampler != NPB_ALG8 && sampler != NPB_JAIN_NEAL && sampler != NPB_TRIADIC) return NPB_E_BAD_ARG;
 	if (sampler == NPB_ALG8 && n_proposals) return NPB_E_BAD_ARG;
 	std::vector<unsigned long long> before, sm_before;
@@ -566,9 +573,13 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_
 	s = ensure_whitened(ch->ds);
 	if (s != NPB_OK) return s;
 	NPB_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
-	if (sampler == NPB_ALG8 && n_sweeps > 0) {
+	if (conjugate && n_sweeps > 0) {
+		s = npb_launch_alg2_conjugate(ch, n_sweeps); // keeps its own statistics in step with the assignments
+		if (s != NPB_OK) return s;
+	} else if (sampler == NPB_ALG8 && n_sweeps > 0) {
 		s = npb_launch_alg8_sweep(ch, n_sweeps);
 		if (s != NPB_OK) return s;
+		ch->z_gen++;
 	} else if (sampler != NPB_ALG8 && (n_sweeps > 0 || n_proposals > 0)) {
 		if (!ch->sm_detail) {
 			NPB_CUDA_OK(cudaMalloc((void **)&ch->sm_detail, (size_t)ch->C * 16 * sizeof(float)));
@@ -576,6 +587,7 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_
 		}
 		s = npb_launch_split_merge(ch, sampler, n_proposals, n_sweeps, ch->sm_detail);
 		if (s != NPB_OK) return s;
+		ch->z_gen++;
 	}
 	NPB_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
 	bool z_direct = false;
@@ -757,6 +769,7 @@ static npb_status move_item(npb_chains *ch, int64_t chain, int64_t item, int slo
 	if (st[0] != 0) return npb_fail(ctx, (npb_status)st[0], st[0] == NPB_E_ALREADY_ASSIGNED ? "the item is already assigned to that cluster"
 			: st[0] == NPB_E_ASSIGNMENT_ABSENT ? "no such cluster on this chain" : "no free cluster slot");
 	if (slot_out) *slot_out = st[1];
+	ch->z_gen++;
 	return NPB_OK;
 }
 npb_status npb_chain_move_item(npb_chains *ch, int64_t chain, int64_t item, int slot) {
@@ -795,6 +808,7 @@ npb_status npb_chains_broadcast_state(npb_chains *ch, int64_t src) {
 	NPB_CUDA_OK(cudaGetLastError());
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	ch->moved_frac_last = -1.0;
+	ch->z_gen++;
 	return NPB_OK;
 }
 
@@ -808,6 +822,40 @@ npb_status npb_chain_remove_cluster(npb_chains *ch, int64_t chain, int slot) {
 	NPB_CUDA_OK(cudaMemcpyAsync(&n, ch->counts + (size_t)chain * ch->Kmax + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	if (n > 0) return npb_fail(ctx, NPB_E_ASSIGNMENT_REMAINING, "the cluster still has members");
+	return NPB_OK;
+}
+
+// ---- conjugate Algorithm 2: parity probes ------------------------------------------------------------------------
+// out [n_items, 33]: NIW posterior-predictive log-density of the items under every cluster of `chain` (NaN without members),
+// as the sweep kernel evaluates it for a cluster the item is not a member of; column 32 = the prior predictive
+npb_status npb_chains_alg2_logpred(npb_chains *ch, int64_t chain, const int32_t *items, int n_items, float *out) {
+	if (!ch || !items || !out || n_items <= 0 || chain < 0 || chain >= ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	for (int j = 0; j < n_items; ++j)
+		if (items[j] < 0 || items[j] >= ch->ds->N) return NPB_E_BAD_ARG;
+	DevBuf<int32_t> d_items;
+	DevBuf<float> d_out;
+	NPB_CUDA_OK(d_items.alloc(n_items));
+	NPB_CUDA_OK(d_out.alloc((size_t)n_items * 33));
+	NPB_CUDA_OK(cudaMemcpyAsync(d_items.p, items, sizeof(int32_t) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+	npb_status s = npb_launch_alg2_probe(ch, (int)chain, d_items.p, n_items, d_out.p);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaMemcpyAsync(out, d_out.p, sizeof(float) * n_items * 33, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+// the sufficient statistics the conjugate path keeps for `chain`: counts [32], sum x [32, D], sum x x^T [32, D, D] (fp64)
+npb_status npb_chains_alg2_suffstats(npb_chains *ch, int64_t chain, int32_t *counts, double *sx, double *sxx) {
+	if (!ch || !counts || !sx || !sxx || chain < 0 || chain >= ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	if (!ch->a2_sx) return npb_fail(ctx, NPB_E_BAD_ARG, "the conjugate Algorithm 2 path has not run on this handle");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	const int D = ch->D;
+	NPB_CUDA_OK(cudaMemcpyAsync(counts, ch->counts + (size_t)chain * 32, sizeof(int) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(sx, ch->a2_sx + (size_t)chain * 32 * D, sizeof(double) * 32 * D, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaMemcpyAsync(sxx, ch->a2_sxx + (size_t)chain * 32 * D * D, sizeof(double) * 32 * D * D, cudaMemcpyDeviceToHost, ctx->stream));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }
 
@@ -981,6 +1029,7 @@ npb_status npb_fp32_peak(npb_ctx *ctx, double *tflops) {
 }
 
 npb_status npb_chain_update_alg8(npb_chains *ch, int64_t chain, int64_t item) {
+	if (ch) ch->z_gen++;
 	if (!ch) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	// chain < 0: the same item on every chain (what a lockstep driver of the reference's per-item loop does)

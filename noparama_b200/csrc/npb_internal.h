@@ -104,6 +104,13 @@ struct npb_chains {
 	uint32_t *h_dl_idx = nullptr;  // pinned staging, grown on demand
 	npb_z_t *h_dl_val = nullptr;
 	size_t h_dl_cap = 0;
+	// conjugate Algorithm 2 (npb_alg2.cu)
+	uint64_t z_gen = 0;            // bumped by everything that changes the assignments outside npb_alg2.cu
+	uint64_t a2_gen = ~0ull;       // z_gen the statistics below correspond to
+	uint64_t a2_prior_epoch = ~0ull;
+	double *a2_sx = nullptr, *a2_sxx = nullptr, *a2_work = nullptr, *a2_prior = nullptr;
+	float *a2_mu = nullptr, *a2_P = nullptr, *a2_ld = nullptr, *a2_G = nullptr, *a2_lp0 = nullptr;
+	float a2_ld0 = 0.0f;
 	npb_z_t *g_zblk = nullptr;     // [C][g_bs] fused D = 16 kernel: assignments of the current block's items, in step order
 };
 
@@ -167,6 +174,9 @@ npb_status npb_launch_gemm64_probe(npb_chains *ch, int chain, const int32_t *d_i
 npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a);
 npb_status npb_launch_tc16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a);
+npb_status npb_launch_scan_order(npb_chains *ch, int n_sweeps);
+npb_status npb_launch_alg2_conjugate(npb_chains *ch, int n_sweeps);
+npb_status npb_launch_alg2_probe(npb_chains *ch, int chain, const int32_t *d_items, int n_items, float *d_out);
 npb_status npb_launch_fused16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_update_item(npb_chains *ch, int64_t chain0, int64_t n, int64_t item);
 npb_status npb_launch_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0);

@@ -36,7 +36,7 @@ class Stats(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libnp_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("np_oracle.cpp", "np_oracle.h", "np_oracle_sm.inc")]
+    src = [os.path.join(_HERE, f) for f in ("np_oracle.cpp", "np_oracle.h", "np_oracle_sm.inc", "np_oracle_alg2.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "libnp_oracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -277,3 +277,32 @@ class Run:
                                          "new_slot", "z_after")])
         t["max_slot"] = lib().npo_trace_max_slot(self._h)
         return t
+
+
+# ---- conjugate Algorithm 2 (np_oracle_alg2.inc; not in the reference: pinned against scipy.stats.multivariate_t) ----
+def niw_logpred(prior, Xm, x, incremental=False, remove_first=0):
+    """log posterior-predictive density of x for the cluster made of the rows of Xm (none: the prior predictive)"""
+    L = lib()
+    Xm = _f64(np.asarray(Xm, dtype=np.float64).reshape(-1, prior.D))
+    x = _f64(x)
+    if incremental:
+        L.npo_niw_logpred_incremental.restype = C.c_double
+        L.npo_niw_logpred_incremental.argtypes = [C.POINTER(Prior), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        return L.npo_niw_logpred_incremental(C.byref(prior), len(Xm), _dp(Xm), remove_first, _dp(x))
+    L.npo_niw_logpred.restype = C.c_double
+    L.npo_niw_logpred.argtypes = [C.POINTER(Prior), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    return L.npo_niw_logpred(C.byref(prior), len(Xm), _dp(Xm), _dp(x))
+
+
+def alg2_run(prior, X, T, K0, seed):
+    """T sweeps of conjugate Algorithm 2 -> (z [N] compact labels, K after every sweep [T], moved, births)"""
+    L = lib()
+    X = _f64(X)
+    N = len(X)
+    z = np.empty(N, dtype=np.int32)
+    Kt = np.empty(T, dtype=np.int32)
+    moved, births = C.c_int64(), C.c_int64()
+    L.npo_alg2_run.argtypes = [C.POINTER(Prior), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int),
+                               C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.npo_alg2_run(C.byref(prior), _dp(X), N, T, K0, seed, _ip(z), _ip(Kt), C.byref(moved), C.byref(births))
+    return z, Kt, moved.value, births.value

@@ -1055,3 +1055,5 @@ void npo_trace_copy(const npo_run *r, int *item, int *K, int64_t *order_off, int
 }
 
 } /* extern "C" */
+
+#include "np_oracle_alg2.inc"

@@ -144,6 +144,13 @@ void npo_trace_copy(const npo_run *r,
 		double *aux_mu /*[S,M,D]*/, double *aux_Sigma /*[S,M,D,D]*/, double *u /*[S]*/,
 		int *picked /*[S]*/, int *new_slot /*[S], -1 if existing*/, int *z_after /*[T,N] slot ids*/);
 
+/* ---- conjugate Algorithm 2 (np_oracle_alg2.inc): NOT in the reference (np_neal_algorithm2.cpp is dead code, the conjugate
+ * headers are empty) => PARITY UNPINNED against the reference; pinned against scipy.stats.multivariate_t instead ---- */
+double npo_niw_logpred(const npo_prior *prior, int n, const double *Xm /*[n,D]*/, const double *x);
+double npo_niw_logpred_incremental(const npo_prior *prior, int n, const double *Xm, int remove_first, const double *x);
+void npo_alg2_run(const npo_prior *prior, const double *X, int N, int T, int K0, uint64_t seed, int *z_out, int *K_trace,
+		int64_t *moved_out, int64_t *births_out);
+
 #ifdef __cplusplus
 }
 #endif
