@@ -334,6 +334,39 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
     out["cfg4"] = cfg4_measure(npb, syn, ctx, fp32_peak, rank)
     out["fp32_pipe_kernel"] = fp32_path_measure(npb, syn, ctx, fp32_peak, rank)
     out["mixing"] = mixing_measure(npb, syn, ctx, rank)
+    out["conjugate_alg2"] = conjugate_measure(npb, syn, ctx, rank)
+    return out
+
+
+def conjugate_measure(npb, syn, ctx, rank):
+    """BASELINE configs[3]: CONJUGATE Algorithm 2 (collapsed Gibbs, NIW posterior predictive, statistics up- and down-dated per
+    move; npb_alg2.cu) -- a first correct device path, latency-bound: at 64-D the 32 slots' P = Lambda_n^-1 (512 KB per chain) do
+    not fit the register file and stream from L2 every step, so the shape is run at N = 20 000 instead of 1 000 000 (the rate
+    does not depend on N); the tensor-core precompute with rank-1 corrections of the dirty slots is the next step."""
+    out = {}
+    for name, D, N, chains, K in (("cfg4_64d", 64, 20_000, 256, 16), ("headline_shape_16d", 16, 100_000, 1024, 20)):
+        X, y = syn.gmm(N, D, K, 20261004)
+        ds = npb.Dataset(ctx, X)
+        npb.NormalInverseWishart(mu0=X.mean(0), kappa=0.01, nu=D + 2.0, Lambda=np.eye(D), alpha=1.0).bind(ctx)
+        ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K, m_aux=M_AUX, seed=SEED + 59 * rank)
+        ch.init_from_params(*given_clusters(X, y))
+        for _ in range(3):
+            ch.sweep(npb.ALG2_CONJUGATE, 1)
+        ms, cand, moved, births = [], 0, 0, 0
+        for _ in range(2):
+            st = ch.sweep(npb.ALG2_CONJUGATE, 1)
+            ms.append(st.kernel_ms)
+            cand, moved, births = cand + st.candidates, moved + st.moved, births + st.new_clusters
+        k_ms = float(np.mean(ms))
+        m = ch.metrics(y)
+        # SURVEY 8(d): an Algorithm 2 step = (K_i + 1) (F_eval(D) + 12) flops + 2 (2 D^2 + 6 D) per rank-1 down- / up-date (moves only here)
+        fl = (cand / 2) * (f_eval(D) + 12) + (moved / 2) * 2 * (2 * D * D + 6 * D)
+        out[name] = {"workload": "%d chains x N=%d x %d-D, %d components, conjugate NIW (mu0 = data mean, kappa0 = 0.01, nu0 = D + 2, Lambda0 = I), "
+                                 "Kmax=32" % (chains, N, D, K), "value": chains * N / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": 2,
+                     "warmup": 3, "moved_fraction": moved / (2 * chains * N), "candidates_per_reassignment": cand / (2 * chains * N),
+                     "mean_K": float(m["K"].mean()), "mean_purity": float(m["purity"].mean()), "algorithmic_tflops": fl / (k_ms * 1e-3) / 1e12}
+        ch.close()
+        ds.close()
     return out
 
 
@@ -543,7 +576,7 @@ def main():
         k_trace.append(mm["K"].astype(np.float64))
         jll_trace.append(mm["joint_loglik"])
     m = chains.metrics(y)
-    cocl = cocluster_measure(npb, chains, ds, torch, dist, world)
+    cocl = cocluster_measure(npb, chains, ds, torch, dist, world, rank)
     diag = dg.combine(dg.score_partial(m), {"K": dg.rhat_partial(np.stack(k_trace, 1)),
                                             "joint_loglik": dg.rhat_partial(np.stack(jll_trace, 1))},
                       cocluster=None, device="cuda")
@@ -666,25 +699,36 @@ def main():
         dist.destroy_process_group()
 
 
-def cocluster_measure(npb, chains, ds, torch, dist, world):
-    """posterior co-clustering counts of an anchor subset over this rank's chains, all-reduced over the ranks (the path's only
-    exchange); returns the figures for the JSON line"""
-    anchors = np.arange(0, ds.N, max(1, ds.N // 256))[:256]
-    S = torch.zeros((len(anchors), len(anchors)), dtype=torch.float32, device="cuda")
+def cocluster_measure(npb, chains, ds, torch, dist, world, rank=0, n_anchor=4096):
+    """posterior co-clustering counts of an anchor subset over this rank's chains (k_cc_gather + k_cc_tile), summed over the ranks
+    by ncclAllReduce INSIDE the library (npb_cocluster_allreduce; the communicator is the library's own, its unique id handed round
+    through torch.distributed) -- the path's only exchange; returns the figures for the JSON line"""
+    anchors = np.arange(0, ds.N, max(1, ds.N // n_anchor))[:n_anchor]
+    A = len(anchors)
+    comm = None
+    if world > 1:
+        uid = npb.Comm.unique_id(chains.ctx) if rank == 0 else bytes(128)
+        t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        comm = npb.Comm(chains.ctx, bytes(t.cpu().tolist()), rank, world)
+    S = torch.zeros((A, A), dtype=torch.float32, device="cuda")
+    chains.cocluster_allreduce(anchors, S.data_ptr(), comm)  # warm-up (NCCL sets its rings up on the first call)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     chains.cocluster_into(anchors, S.data_ptr())
     chains.ctx.synchronize()
     t_k = time.perf_counter() - t0
-    t_ar = 0.0
-    if world > 1:
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dist.all_reduce(S)
-        torch.cuda.synchronize()
-        t_ar = time.perf_counter() - t0
-    return {"anchors": int(len(anchors)), "kernel_ms": 1e3 * t_k, "allreduce_ms": 1e3 * t_ar,
-            "anchor_diag_mean": float(S.diag().mean().item())}
+    t0 = time.perf_counter()
+    chains.cocluster_allreduce(anchors, S.data_ptr(), comm)
+    chains.ctx.synchronize()
+    t_all = time.perf_counter() - t0
+    if comm is not None:
+        comm.close()
+    pairs = A * (A + 1) / 2
+    return {"anchors": int(A), "chains_per_gpu": int(chains.C), "kernel_ms": 1e3 * t_k, "with_allreduce_ms": 1e3 * t_all,
+            "allreduce_ms": max(0.0, 1e3 * (t_all - t_k)), "allreduce_bytes": int(A * A * 4),
+            "byte_compares_per_s": pairs * chains.C / t_k, "anchor_diag_mean": float(S.diag().mean().item()),
+            "expected_diag": int(chains.C) * world}
 
 
 def mc_fp32_peak(ctx):

@@ -34,6 +34,7 @@ enum {
 	NPB_E_UNSUPPORTED = -5,
 	NPB_E_REPLAY_MISMATCH = -6,   /* replay picked a different candidate than the recorded trace */
 	NPB_E_NOMEM = -7,
+	NPB_E_NCCL = -8,              /* NCCL missing or a collective failed */
 	/* mirrors of np_error_t (include/membertrix.h:16-23) for the single-item seam */
 	NPB_E_ALREADY_ASSIGNED = -16,
 	NPB_E_ASSIGNMENT_REMAINING = -17,
@@ -249,6 +250,23 @@ npb_status npb_chains_get_best_assignments(npb_chains *ch, int64_t chain0, int64
  * z[anchors[a]] == z[anchors[b]].  S_dev is a DEVICE pointer to n_anchor*n_anchor floats (so that the caller can
  * all-reduce it over NCCL without a host round trip); accumulate != 0 adds to S_dev. */
 npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, float *S_dev, int accumulate);
+
+/* ---- the path's only exchange: all-reduce of the co-clustering matrix and the diagnostics over the GPUs of a node.
+ * NCCL is bound at run time (dlopen of libnccl.so.2; NPB_E_NCCL without it).  A communicator belongs to one context (device).
+ * Multi-process (one rank per GPU): rank 0 calls npb_comm_unique_id and hands the 128 bytes to the others by any means, every
+ * rank calls npb_comm_create.  Single process (the CLI's --gpus): npb_comm_create_all, one communicator per context.
+ * npb_cocluster_allreduce = npb_cocluster followed by the in-place sum of S_dev over the communicator's ranks, on the
+ * context's stream; npb_comm_allreduce_sum reduces any device buffer of 32- or 64-bit floats in place (R-hat partial sums,
+ * score sums).  In a single process the collective calls of all ranks go between npb_comm_group(1) and npb_comm_group(0). */
+typedef struct npb_comm npb_comm;
+npb_status npb_comm_unique_id(char out[128]);
+npb_status npb_comm_create(npb_ctx *ctx, const char id[128], int rank, int world, npb_comm **out);
+npb_status npb_comm_create_all(npb_ctx *const *ctxs, int n, npb_comm **out /* [n] */);
+npb_status npb_comm_destroy(npb_comm *c);
+npb_status npb_comm_allreduce_sum(npb_comm *c, void *dev_buf, int64_t count, int bits);
+npb_status npb_comm_group(int start);
+npb_status npb_cocluster_allreduce(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, npb_comm *comm_or_null, float *S_dev);
+npb_status npb_cocluster_host(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, npb_comm *comm_or_null, float *S_host);
 
 /* The scan order of sweep number `sweep` (replaces the per-sweep std::shuffle of np_mcmc.cpp:120-125): a keyed
  * permutation of 0..N-1 shared by all chains of a run; order_out[s] = item visited at step s.  Pure host

@@ -33,6 +33,8 @@ EXPORTS = [
     "npb_chains_split_merge", "npb_chains_last_proposal", "npb_chains_update_params", "npb_replay_split_merge", "npb_chains_consider_max_likelihood", "npb_chains_get_best_assignments",
     "npb_chains_probe_tile_logdensity", "npb_chains_set_option", "npb_chains_sweep_host_delta", "npb_chains_get_best_params",
     "npb_chain_move_item", "npb_chain_move_item_new", "npb_chain_remove_cluster", "npb_chains_kernel_time", "npb_chains_broadcast_state", "npb_chains_alg2_logpred", "npb_chains_alg2_suffstats",
+    "npb_comm_unique_id", "npb_comm_create", "npb_comm_create_all", "npb_comm_destroy", "npb_comm_allreduce_sum", "npb_comm_group",
+    "npb_cocluster_allreduce", "npb_cocluster_host",
 ]
 
 
@@ -105,6 +107,13 @@ def load_library():
     L.npb_chains_broadcast_state.argtypes = [vp, i64]
     L.npb_chains_alg2_logpred.argtypes = [vp, i64, ip, C.c_int, C.POINTER(C.c_float)]
     L.npb_chains_alg2_suffstats.argtypes = [vp, i64, ip, dp, dp]
+    L.npb_comm_unique_id.argtypes = [C.c_char_p]
+    L.npb_comm_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.npb_comm_destroy.argtypes = [vp]
+    L.npb_comm_allreduce_sum.argtypes = [vp, vp, i64, C.c_int]
+    L.npb_comm_group.argtypes = [C.c_int]
+    L.npb_cocluster_allreduce.argtypes = [vp, C.POINTER(i64), i64, vp, vp]
+    L.npb_cocluster_host.argtypes = [vp, C.POINTER(i64), i64, vp, C.POINTER(C.c_float)]
     L.npb_chains_get_best_assignments.argtypes = [vp, i64, i64, ip]
     L.npb_chains_get_params.argtypes = [vp, i64, C.c_int, C.POINTER(C.c_int), ip, C.POINTER(i64), dp, dp]
     L.npb_chains_metrics.argtypes = [vp, ip, dp, dp, dp, dp, ip]
@@ -172,6 +181,30 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """NCCL communicator of one context (npb_comm): rank 0 makes the unique id, every rank creates its communicator with it."""
+
+    @staticmethod
+    def unique_id(ctx):
+        buf = C.create_string_buffer(128)
+        ctx.check(ctx._lib.npb_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, ctx, uid, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        ctx.check(ctx._lib.npb_comm_create(ctx._h, uid, rank, world, C.byref(h)))
+        self._h = h
+
+    def allreduce_sum(self, dev_ptr, count, bits=32):
+        self.ctx.check(self.ctx._lib.npb_comm_allreduce_sum(self._h, C.c_void_p(dev_ptr), count, bits))
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.npb_comm_destroy(self._h)
+            self._h = None
 
 
 class Dataset:
@@ -488,6 +521,21 @@ class Chains:
         anchors = np.ascontiguousarray(anchors, dtype=np.int64)
         self.ctx.check(self.ctx._lib.npb_cocluster(self._h, anchors.ctypes.data_as(C.POINTER(C.c_int64)), len(anchors),
                                                    C.c_void_p(S_dev_ptr), int(accumulate)))
+
+    def cocluster(self, anchors, comm=None):
+        """[A, A] float32 co-clustering counts of the anchors (summed over the communicator's ranks if one is given)"""
+        anchors = np.ascontiguousarray(anchors, dtype=np.int64)
+        out = np.empty((len(anchors), len(anchors)), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.npb_cocluster_host(self._h, anchors.ctypes.data_as(C.POINTER(C.c_int64)), len(anchors),
+                                                        comm._h if comm is not None else None, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def cocluster_allreduce(self, anchors, S_dev_ptr, comm=None):
+        """co-clustering counts of the anchors over this handle's chains, summed over the communicator's ranks (in the library:
+        k_cc_gather + k_cc_tile, then ncclAllReduce on the context's stream)"""
+        anchors = np.ascontiguousarray(anchors, dtype=np.int64)
+        self.ctx.check(self.ctx._lib.npb_cocluster_allreduce(self._h, anchors.ctypes.data_as(C.POINTER(C.c_int64)), len(anchors),
+                                                             comm._h if comm is not None else None, C.c_void_p(S_dev_ptr)))
 
     def close(self):
         if self._h:

@@ -5,7 +5,7 @@
 // The reference's intent is src/np_neal_algorithm2.cpp:32-120 -- retract (:46), updateSuffies (:54), weights n_k * p (:79-108)
 // and alpha * p for a new cluster (:110-119) -- but that file is not compiled and cannot compile, and the conjugate arithmetic
 // (include/statistics/normalinvwishart.h:66-75 `update(data, downdate)`, include/statistics/conjugate/*.h) does not exist.
-// What runs here is therefore the textbook model, checked against oracle/np_oracle_alg2.inc (itself pinned
+// What runs here is therefore the textbook model, checked against the test oracle's fp64 restatement (itself pinned
 // to scipy.stats.multivariate_t): parity with the reference is UNPINNED by construction.
 //
 // Per cluster the chain keeps, next to the member count, the posterior mean mu_n, P = Lambda_n^-1 and log det Lambda_n (fp32
@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(32 * LPS) k_a2_sweep(const A2Args a) {
 			for (int i = 0; i < RPL; ++i) {
 				const int r = l + i * LPS;
 				float acc = 0.0f;
-				if (PREG) {
+				if (n <= 0) { // a slot without members has no candidate (and, out of registers, no P worth 16 KB of L2 traffic)
+				} else if (PREG) {
 #pragma unroll
 					for (int c = 0; c < D; ++c) acc = fmaf(Prow[i * D + c], sd[slot][c], acc);
 				} else {

@@ -47,6 +47,7 @@ const char *npb_status_str(npb_status s) {
 	case NPB_E_UNSUPPORTED: return "unsupported configuration";
 	case NPB_E_REPLAY_MISMATCH: return "replay diverged from the recorded trace";
 	case NPB_E_NOMEM: return "out of device memory";
+	case NPB_E_NCCL: return "NCCL error";
 	case NPB_E_ALREADY_ASSIGNED: return "already assigned";
 	case NPB_E_ASSIGNMENT_REMAINING: return "assignment remaining";
 	case NPB_E_ASSIGNMENT_ABSENT: return "assignment absent";
@@ -1011,6 +1012,30 @@ npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_ancho
 	NPB_CUDA_OK(cudaMemcpyAsync(d_a.p, anchors, sizeof(int64_t) * n_anchor, cudaMemcpyHostToDevice, ctx->stream));
 	npb_status s = npb_launch_cocluster(ch, d_a.p, (int)n_anchor, S_dev, accumulate);
 	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+npb_status npb_cocluster_allreduce(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, npb_comm *comm, float *S_dev) {
+	npb_status s = npb_cocluster(ch, anchors, n_anchor, S_dev, 0);
+	if (s != NPB_OK || !comm) return s;
+	s = npb_comm_allreduce_sum(comm, S_dev, n_anchor * n_anchor, 32);
+	if (s != NPB_OK) return s;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	return NPB_OK;
+}
+
+// the same into a HOST matrix (a host above the ABI needs no CUDA of its own)
+npb_status npb_cocluster_host(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, npb_comm *comm, float *S_host) {
+	if (!ch || !S_host || n_anchor <= 0) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	DevBuf<float> d_S;
+	NPB_CUDA_OK(d_S.alloc((size_t)n_anchor * n_anchor));
+	npb_status s = npb_cocluster_allreduce(ch, anchors, n_anchor, comm, d_S.p);
+	if (s != NPB_OK) return s;
+	NPB_CUDA_OK(cudaMemcpyAsync(S_host, d_S.p, sizeof(float) * n_anchor * n_anchor, cudaMemcpyDeviceToHost, ctx->stream));
 	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
 	return NPB_OK;
 }

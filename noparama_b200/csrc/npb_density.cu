@@ -162,18 +162,6 @@ __global__ void k_chain_metrics(const npb_z_t *z, const float *X, const float *t
 	}
 }
 
-// co-clustering counts over an anchor subset: S[a][b] += #chains with z[anchor a] == z[anchor b]
-// (plain CUDA-core version; the tensor-core one-hot GEMM is a later row of SURVEY 8)
-__global__ void k_cocluster(const npb_z_t *z, const int64_t *anchors, int n_anchor, int C, float *S, int accumulate) {
-	const int a = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= n_anchor) return;
-	const npb_z_t *za = z + (size_t)anchors[a] * C, *zb = z + (size_t)anchors[b] * C;
-	int cnt = 0;
-	for (int c = 0; c < C; ++c) cnt += za[c] == zb[c];
-	float *o = S + (size_t)a * n_anchor + b;
-	*o = (accumulate ? *o : 0.0f) + (float)cnt;
-}
-
 // ---- launchers used by npb_api.cu -------------------------------------------------------------------------
 npb_status npb_launch_logdensity(npb_ctx *ctx, npb_dataset *ds, const int64_t *d_rows, int64_t n_rows, int K,
 		const double *d_mu, const double *d_T, const double *d_c, const float *f_mu, const float *f_T, const float *f_c,
@@ -220,14 +208,6 @@ npb_status npb_launch_metrics(npb_chains *ch, const int32_t *d_truth, int Ktrue,
 	default: NPB_METRICS_LAUNCH(0); break;
 	}
 #undef NPB_METRICS_LAUNCH
-	NPB_CUDA_OK(cudaGetLastError());
-	return NPB_OK;
-}
-
-npb_status npb_launch_cocluster(npb_chains *ch, const int64_t *d_anchors, int n_anchor, float *S_dev, int accumulate) {
-	npb_ctx *ctx = ch->ctx;
-	dim3 grid((n_anchor + 127) / 128, n_anchor);
-	k_cocluster<<<grid, 128, 0, ctx->stream>>>(ch->z, d_anchors, n_anchor, (int)ch->C, S_dev, accumulate);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }

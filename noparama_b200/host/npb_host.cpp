@@ -241,6 +241,14 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam, UpdateClusters *up
 void MCMC::considerMaxLikelihood() {
 	dev_.check(npb_chains_consider_max_likelihood(trix_->chains, nullptr, nullptr));
 }
+double MCMC::coclusterDiagonalCheck(const std::vector<int64_t> &anchors, npb_comm *comm) {
+	const size_t n = anchors.size();
+	std::vector<float> h(n * n);
+	dev_.check(npb_cocluster_host(trix_->chains, anchors.data(), (int64_t)n, comm, h.data()));
+	double d = 0.0;
+	for (size_t i = 0; i < n; ++i) d += h[i * n + i];
+	return d / (double)n;
+}
 std::map<cluster_id_t, Suffies_MultivariateNormal> MCMC::getMaxLikelihoodClusters(int64_t chain) {
 	// the clusters as they were when the state was kept: slot ids are re-used after a death, so the CURRENT slot table may
 	// describe other clusters under the same ids

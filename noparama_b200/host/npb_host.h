@@ -234,6 +234,9 @@ public:
 	std::map<cluster_id_t, Suffies_MultivariateNormal> getMaxLikelihoodClusters(int64_t chain = 0); // the kept state's clusters
 	std::vector<int32_t> getMaxLikelihoodAssignments(int64_t chain = 0);  // np_mcmc.h:90: the state kept by considerMaxLikelihood
 	void considerMaxLikelihood();                                         // np_mcmc.cpp:187-203, every chain at once
+	// co-clustering counts of `anchors` over this object's chains (npb_cocluster_allreduce: summed over the communicator's ranks when
+	// one is given); returns the mean diagonal entry = the total number of chains that contributed
+	double coclusterDiagonalCheck(const std::vector<int64_t> &anchors, npb_comm *comm);
 	clustering_scores scores(const std::vector<int> &ground_truth);        // np_results.cpp:17-37 + clustering_performance
 	int64_t chains() const { return chains_; }
 private:

@@ -18,6 +18,7 @@
 #include <iostream>
 #include <numeric>
 #include <sstream>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <thread>
@@ -142,9 +143,8 @@ int main(int argc, char **argv) {
 	std::cout << "Read " << dataset.size() << " items of dimension " << D << std::endl;
 
 	// one device: its own context, object graph and share of the chains
-	auto run_on_device = [&](int dev_index, long long chains, unsigned long long seed, bool lead, clustering_scores &sc_out, std::mutex &io) -> int {
+	auto run_on_device = [&](device &dev, npb_comm *comm, int dev_index, long long chains, unsigned long long seed, bool lead, clustering_scores &sc_out, std::mutex &io) -> int {
 	try {
-			device dev(dev_index);
 			Suffies_Dirichlet sd;
 			sd.alpha = 1.0; // np_main.cpp:164
 			Suffies_NormalInvWishart niw(D);
@@ -168,7 +168,15 @@ int main(int argc, char **argv) {
 			sampler.printStatistics();
 			clustering_scores sc = mcmc.scores(ground_truth);
 			sc_out = sc;
+			// posterior co-clustering counts of (up to) 1024 evenly spaced items over this device's chains, summed over the devices
+			// (ncclAllReduce inside the library; the only exchange of a run)
+			std::vector<int64_t> anchors;
+			const int64_t Nn = (int64_t)dataset.size(), step = std::max<int64_t>(1, Nn / 1024);
+			for (int64_t i = 0; i < Nn && anchors.size() < 1024; i += step) anchors.push_back(i);
+			const double cc = mcmc.coclusterDiagonalCheck(anchors, comm);
 			std::lock_guard<std::mutex> lock(io);
+			if (lead) std::cout << "Co-clustering matrix of " << anchors.size() << " anchors over all chains: mean self-count " << cc
+					      << (comm ? " (all-reduced over NCCL)" : "") << std::endl;
 			if (!lead) {
 				std::cout << "device " << dev_index << ": " << chains << " chain(s) done" << std::endl;
 				return 0;
@@ -215,10 +223,24 @@ int main(int argc, char **argv) {
 	int rc = 0;
 	std::vector<clustering_scores> all(gpus);
 	std::mutex io;
+	// one context per device, created up front so that the communicators can be (ncclCommInitAll through npb_comm_create_all)
+	std::vector<std::unique_ptr<device>> devs;
+	std::vector<npb_comm *> comms(gpus, nullptr);
+	try {
+		for (int g = 0; g < gpus; ++g) devs.emplace_back(new device(g));
+		if (gpus > 1 && !selftest) {
+			std::vector<npb_ctx *> ctxs;
+			for (auto &d : devs) ctxs.push_back(d->ctx());
+			devs[0]->check(npb_comm_create_all(ctxs.data(), gpus, comms.data()));
+		}
+	} catch (const npb_error &e) {
+		std::cerr << "npb200: " << e.what() << std::endl;
+		return e.status == NPB_E_CUDA ? 2 : 1;
+	}
 	auto run_device = [&](int g) {
 		// chains g * chains / gpus .. (g + 1) * chains / gpus - 1 on device g (contiguous blocks, dataset replicated)
 		const long long c0 = chains * g / gpus, c1 = chains * (g + 1) / gpus;
-		int r = run_on_device(g, c1 - c0, seed + 0x9E3779B97F4A7C15ull * (unsigned long long)g, g == 0, all[g], io);
+		int r = run_on_device(*devs[g], comms[g], g, c1 - c0, seed + 0x9E3779B97F4A7C15ull * (unsigned long long)g, g == 0, all[g], io);
 		if (r) rc = r;
 	};
 	if (gpus == 1) {
@@ -236,6 +258,7 @@ int main(int argc, char **argv) {
 				  << " clusters " << k / n << std::endl;
 		}
 	}
+	for (auto c : comms) npb_comm_destroy(c);
 	for (auto p : dataset) delete p;
 	return rc;
 }

@@ -2,6 +2,7 @@
 clusters, the single-item membertrix calls with the np_error_t mirror codes, and the lifetime / dimension guards."""
 import numpy as np
 import pytest
+import torch  # noqa: F401  (first: the library binds NCCL at run time and must find PyTorch's copy, not load the system's before it)
 
 from noparama_b200 import synthetic as syn
 
@@ -99,5 +100,30 @@ def test_move_item_status_codes_and_guards(npb, ctx):
         ch.sweep(npb.ALG8, 1)
     npb.NormalInverseWishart(**syn.reference_prior(2)).bind(ctx)
     ch.sweep(npb.ALG8, 1)
+    ch.close()
+    ds.close()
+
+
+@pytest.mark.parametrize("chains,n_anchor", [(37, 150), (256, 1024), (1001, 333)])
+def test_cocluster_counts_exact(npb, ctx, chains, n_anchor):
+    """k_cc_gather + k_cc_tile (byte-compare of four chains per word, 64 x 64 tiles, upper triangle mirrored) against numpy:
+    exact counts for chain counts that are not multiples of four and anchor counts that are not multiples of the tile; and the
+    same through a one-rank NCCL communicator (npb_comm_create / ncclAllReduce bound at run time)."""
+    X, _ = syn.config(1)
+    X = np.tile(X, (8, 1))[:n_anchor + 57]
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(2)).bind(ctx)
+    ch = npb.Chains(ctx, ds, chains, Kmax=64, K0=20, seed=3)
+    ch.sweep(npb.ALG8, 3)
+    anchors = np.random.default_rng(1).permutation(len(X))[:n_anchor]
+    z = ch.assignments()[:, anchors]  # [C, A]
+    want = (z[:, :, None] == z[:, None, :]).sum(0).astype(np.float32)
+    got = ch.cocluster(anchors)
+    assert np.array_equal(got, want)
+    assert np.all(np.diag(got) == chains)
+    comm = npb.Comm(ctx, npb.Comm.unique_id(ctx), 0, 1)
+    got2 = ch.cocluster(anchors, comm)
+    comm.close()
+    assert np.array_equal(got2, want)
     ch.close()
     ds.close()
