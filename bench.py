@@ -294,9 +294,6 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
     X, y = syn.config(3)
     ds = npb.Dataset(ctx, X)
     npb.NormalInverseWishart(**syn.reference_prior(cfg["D"])).bind(ctx)
-    ch = npb.Chains(ctx, ds, 4096, Kmax=64, K0=K0_REF, seed=SEED + 31 * rank)
-    ch.init_from_params(*given_clusters(X, y))
-    ch.sweep(npb.ALG8, 1, want_stats=False)
     # the `fixed` regime of SURVEY 8d on the headline shape at reduced chain count: every sweep is followed by a draw of all
     # cluster parameters from their conjugate NIW posterior (npb_chains_update_params)
     pr_fixed = dict(mu0=X.mean(0), kappa=0.01, nu=cfg["D"] + 2.0, Lambda=np.eye(cfg["D"]))
@@ -319,22 +316,84 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
                                      "(mu, Sigma) per step", "sweep_ms": float(np.mean(t_sw)), "update_params_ms": float(np.mean(t_up)),
                          "value": 4096 * ds.N / ((np.mean(t_sw) + np.mean(t_up)) * 1e-3), "unit": UNIT,
                          "mean_purity": float(mfix["purity"].mean()), "mean_K": float(mfix["K"].mean())}
-    sm = {}
-    for name, sampler in (("jain_neal", npb.JAIN_NEAL), ("triadic", npb.TRIADIC)):
-        ch.split_merge(sampler, 8)
-        st = ch.split_merge(sampler, 16)
-        sec = st.kernel_ms * 1e-3
-        sm[name] = {"proposals_per_s": st.reassignments / sec, "sams_allocations_per_s": st.sams_allocations / sec,
-                    "kernel_ms": st.kernel_ms, "proposals": int(st.reassignments), "attempts": list(st.sm_attempts),
-                    "accepts": list(st.sm_accepts)}
-    out["split_merge"] = dict(sm, workload="BASELINE configs[2] shape: 4096 chains, 16-D 32-component GMM, N=100000, K=32 given "
-                                           "clusters; 16 lockstep proposals per chain (np_mcmc.cpp:146-163)")
-    ch.close()
+    out["split_merge"] = split_merge_measure(npb, syn, ctx, ds, X, y, fp32_peak, rank)
     ds.close()
     out["cfg4"] = cfg4_measure(npb, syn, ctx, fp32_peak, rank)
     out["fp32_pipe_kernel"] = fp32_path_measure(npb, syn, ctx, fp32_peak, rank)
     out["mixing"] = mixing_measure(npb, syn, ctx, rank)
     out["conjugate_alg2"] = conjugate_measure(npb, syn, ctx, rank)
+    return out
+
+
+def split_merge_measure(npb, syn, ctx, ds, X, y, fp32_peak, rank, chains=1024, proposals=10_000):
+    """Jain-Neal and triadic proposals at BASELINE configs[2]'s shape (16-D, N = 100 000, 32 components) in a regime where moves
+    are ACCEPTED: the chains start from 16 clusters, each the merger of two true components (their pooled mean and covariance), so
+    splits are there to be found and merges of the halves to be refused; 10 000 lockstep proposals per chain (np_mcmc.cpp:146-163:
+    a sweep is N of them).  Reported: proposals/s, SAMS item-allocations/s, accepts, and the FP32 figure of the counted
+    density evaluations.  CPU: the reference's own samplers (oracle/_ref np_ref_run jain_neal_split | triadic), one chain per core,
+    on a bounded prefix of the items."""
+    K = int(y.max()) + 1
+    pairs = [(2 * i, 2 * i + 1) for i in range(K // 2)]
+    mu = np.stack([X[(y == a) | (y == b)].mean(0) for a, b in pairs])
+    Sig = np.stack([np.cov(X[(y == a) | (y == b)].T) for a, b in pairs])
+    D = X.shape[1]
+    res = {}
+    for name, sampler, q_eval in (("jain_neal", npb.JAIN_NEAL, 2.0), ("triadic", npb.TRIADIC, 2.5)):
+        ch = npb.Chains(ctx, ds, chains, Kmax=64, K0=K0_REF, seed=SEED + 31 * rank)
+        ch.init_from_params(mu, Sig)
+        ch.sweep(npb.ALG8, 1, want_stats=False)  # the items settle on the merged clusters
+        ch.split_merge(sampler, 256)
+        st = ch.split_merge(sampler, proposals)
+        sec = st.kernel_ms * 1e-3
+        m = ch.metrics(y)
+        # a SAMS allocation weighs its member under the Q parameter sets of the move (2 for Jain-Neal, 2 or 3 for the triadic
+        # sampler), the acceptance sums evaluate every member once more per set: ~2 Q evaluations per allocated member
+        evals = st.sams_allocations * 2.0 * q_eval
+        fl = evals * f_eval(D)
+        res[name] = {"proposals_per_s": st.reassignments / sec, "sams_allocations_per_s": st.sams_allocations / sec,
+                     "kernel_ms": st.kernel_ms, "proposals": int(st.reassignments), "proposals_per_chain": proposals,
+                     "attempts": list(st.sm_attempts), "accepts": list(st.sm_accepts), "mean_K_after": float(m["K"].mean()),
+                     "mean_purity_after": float(m["purity"].mean()),
+                     "roofline": {"bound": "fp32", "achieved": fl / sec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                                  "frac": fl / sec / 1e12 / fp32_peak if fp32_peak else None, "kernel": "k_split_merge<16>",
+                                  "note": "density evaluations estimated as 2 Q per SAMS allocation (Q = parameter sets of the move) x (D^2 + 4D + 3) flops"}}
+        ch.close()
+    res["workload"] = ("BASELINE configs[2] shape: %d chains (of 4096), 16-D 32-component GMM, N=100000, Kmax=64; start = 16 clusters, each two true "
+                       "components merged; %d lockstep proposals per chain" % (chains, proposals))
+    try:
+        res["cpu_baseline"] = split_merge_cpu(X, D)
+    except Exception as e:
+        res["cpu_baseline"] = {"failed": repr(e)}
+    return res
+
+
+def split_merge_cpu(X, D, n_items=1500, sweeps=2):
+    """the reference's own split-merge samplers on the host cores: one chain per core over the first n_items items, `sweeps`
+    sweeps (= n_items proposals each, np_mcmc.cpp:146-163) after its own initialisation"""
+    from oracle import refrun
+    from noparama_b200 import synthetic as syn
+    if not refrun.available():
+        return {"unavailable": "oracle/_ref/np_ref_run was not built"}
+    cores = os.cpu_count() or 1
+    out = {"cores": cores, "kind": "reference", "items": n_items}
+    pr = syn.reference_prior(D)
+    with tempfile.TemporaryDirectory() as d:
+        req = os.path.join(d, "req.bin")
+        refrun.write_request(req, X[:n_items], pr)
+        for alg, name in ((2, "jain_neal"), (3, "triadic")):
+            procs = []
+            for c in range(cores):
+                r = os.path.join(d, "res%d_%d.bin" % (alg, c))
+                procs.append((r, subprocess.Popen(refrun.command(alg, sweeps, 3000 + c, 4000 + c, req, r), stdout=subprocess.DEVNULL)))
+            t, calls = 0.0, 0
+            for r, pp in procs:
+                if pp.wait() != 0:
+                    raise RuntimeError("np_ref_run failed")
+                rr = refrun.read_result(r)
+                t = max(t, rr["seconds_update"])
+                calls += rr["calls"]
+            out[name] = {"proposals_per_s": calls / t, "proposals": int(calls), "seconds": t}
+    out["sample"] = "%d chains (one per core) x %d sweeps over the first %d items, reference initialisation (K0 = 20 prior draws)" % (cores, sweeps, n_items)
     return out
 
 
