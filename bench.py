@@ -269,7 +269,7 @@ def timed_sweeps(npb, chains, steps):
     return ms, cand, moved, births, last
 
 
-def also_measure(npb, syn, ctx, fp32_peak, rank):
+def also_measure(npb, syn, ctx, fp32_peak, rank, cpu=True):
     """secondary figures of the default run: BASELINE configs[1] (2-D) and the split-merge samplers at configs[2]'s shape"""
     out = {}
     cfg = CONFIGS["cfg2"]
@@ -316,7 +316,7 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
                                      "(mu, Sigma) per step", "sweep_ms": float(np.mean(t_sw)), "update_params_ms": float(np.mean(t_up)),
                          "value": 4096 * ds.N / ((np.mean(t_sw) + np.mean(t_up)) * 1e-3), "unit": UNIT,
                          "mean_purity": float(mfix["purity"].mean()), "mean_K": float(mfix["K"].mean())}
-    out["split_merge"] = split_merge_measure(npb, syn, ctx, ds, X, y, fp32_peak, rank)
+    out["split_merge"] = split_merge_measure(npb, syn, ctx, ds, X, y, fp32_peak, rank, cpu=cpu)
     ds.close()
     out["cfg4"] = cfg4_measure(npb, syn, ctx, fp32_peak, rank)
     out["fp32_pipe_kernel"] = fp32_path_measure(npb, syn, ctx, fp32_peak, rank)
@@ -325,49 +325,71 @@ def also_measure(npb, syn, ctx, fp32_peak, rank):
     return out
 
 
-def split_merge_measure(npb, syn, ctx, ds, X, y, fp32_peak, rank, chains=1024, proposals=10_000):
-    """Jain-Neal and triadic proposals at BASELINE configs[2]'s shape (16-D, N = 100 000, 32 components) in a regime where moves
-    are ACCEPTED: the chains start from 16 clusters, each the merger of two true components (their pooled mean and covariance), so
-    splits are there to be found and merges of the halves to be refused; 10 000 lockstep proposals per chain (np_mcmc.cpp:146-163:
-    a sweep is N of them).  Reported: proposals/s, SAMS item-allocations/s, accepts, and the FP32 figure of the counted
-    density evaluations.  CPU: the reference's own samplers (oracle/_ref np_ref_run jain_neal_split | triadic), one chain per core,
-    on a bounded prefix of the items."""
+def split_merge_measure(npb, syn, ctx, ds, X, y, fp32_peak, rank, proposals=10_000, cpu=True):
+    """Jain-Neal and triadic proposals, 10 000 lockstep proposals per chain (np_mcmc.cpp:146-163: a sweep is N of them), in two
+    regimes.  (1) BASELINE configs[2]'s shape (16-D, N = 100 000, 32 components), the chains started from 16 clusters that each
+    merge two true components: a split draws its new cluster's parameters from the PRIOR (np_jain_neal_algorithm.cpp:148,
+    np_triadic_algorithm.cpp:260), which in 16 dimensions never lands near the data, so the reference's samplers accept nothing
+    here -- the figure is the cost of the proposals.  (2) BASELINE configs[1]'s data (2-D, N = 100 000, 10 components), where the
+    reference's own tests run these samplers, from the reference's initialisation (K0 = 20 prior draws): merges and splits ARE
+    accepted.  Reported: proposals/s, SAMS item-allocations/s, attempts / accepts, the FP32 figure of the counted
+    density evaluations.  CPU: the reference's own samplers (oracle/_ref np_ref_run), one chain per core, on a bounded prefix."""
     K = int(y.max()) + 1
     pairs = [(2 * i, 2 * i + 1) for i in range(K // 2)]
     mu = np.stack([X[(y == a) | (y == b)].mean(0) for a, b in pairs])
     Sig = np.stack([np.cov(X[(y == a) | (y == b)].T) for a, b in pairs])
-    D = X.shape[1]
     res = {}
-    for name, sampler, q_eval in (("jain_neal", npb.JAIN_NEAL, 2.0), ("triadic", npb.TRIADIC, 2.5)):
-        ch = npb.Chains(ctx, ds, chains, Kmax=64, K0=K0_REF, seed=SEED + 31 * rank)
-        ch.init_from_params(mu, Sig)
-        ch.sweep(npb.ALG8, 1, want_stats=False)  # the items settle on the merged clusters
+
+    def one(ch, sampler, q_eval, D, truth, kernel):
         ch.split_merge(sampler, 256)
         st = ch.split_merge(sampler, proposals)
         sec = st.kernel_ms * 1e-3
-        m = ch.metrics(y)
+        m = ch.metrics(truth)
         # a SAMS allocation weighs its member under the Q parameter sets of the move (2 for Jain-Neal, 2 or 3 for the triadic
         # sampler), the acceptance sums evaluate every member once more per set: ~2 Q evaluations per allocated member
-        evals = st.sams_allocations * 2.0 * q_eval
-        fl = evals * f_eval(D)
-        res[name] = {"proposals_per_s": st.reassignments / sec, "sams_allocations_per_s": st.sams_allocations / sec,
-                     "kernel_ms": st.kernel_ms, "proposals": int(st.reassignments), "proposals_per_chain": proposals,
-                     "attempts": list(st.sm_attempts), "accepts": list(st.sm_accepts), "mean_K_after": float(m["K"].mean()),
-                     "mean_purity_after": float(m["purity"].mean()),
-                     "roofline": {"bound": "fp32", "achieved": fl / sec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                                  "frac": fl / sec / 1e12 / fp32_peak if fp32_peak else None, "kernel": "k_split_merge<16>",
-                                  "note": "density evaluations estimated as 2 Q per SAMS allocation (Q = parameter sets of the move) x (D^2 + 4D + 3) flops"}}
+        fl = st.sams_allocations * 2.0 * q_eval * f_eval(D)
+        return {"proposals_per_s": st.reassignments / sec, "sams_allocations_per_s": st.sams_allocations / sec,
+                "kernel_ms": st.kernel_ms, "chains": ch.C, "proposals": int(st.reassignments), "proposals_per_chain": proposals,
+                "attempts": list(st.sm_attempts), "accepts": list(st.sm_accepts),
+                "accept_rate": float(sum(st.sm_accepts)) / max(1, sum(st.sm_attempts)), "mean_K_after": float(m["K"].mean()),
+                "mean_purity_after": float(m["purity"].mean()),
+                "roofline": {"bound": "fp32", "achieved": fl / sec / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": fl / sec / 1e12 / fp32_peak if fp32_peak else None, "kernel": kernel,
+                             "note": "density evaluations estimated as 2 Q per SAMS allocation (Q = parameter sets of the move) x (D^2 + 4D + 3) flops"}}
+
+    D = X.shape[1]
+    for name, sampler, q_eval, chains in (("jain_neal", npb.JAIN_NEAL, 2.0, 592), ("triadic", npb.TRIADIC, 2.5, 148)):
+        ch = npb.Chains(ctx, ds, chains, Kmax=64, K0=K0_REF, seed=SEED + 31 * rank)
+        ch.init_from_params(mu, Sig)
+        ch.sweep(npb.ALG8, 1, want_stats=False)  # the items settle on the merged clusters
+        res[name] = one(ch, sampler, q_eval, D, y, "k_split_merge<16>")
         ch.close()
-    res["workload"] = ("BASELINE configs[2] shape: %d chains (of 4096), 16-D 32-component GMM, N=100000, Kmax=64; start = 16 clusters, each two true "
-                       "components merged; %d lockstep proposals per chain" % (chains, proposals))
-    try:
-        res["cpu_baseline"] = split_merge_cpu(X, D)
-    except Exception as e:
-        res["cpu_baseline"] = {"failed": repr(e)}
+    res["workload"] = ("BASELINE configs[2] shape (of its 4096 chains: 592 Jain-Neal, 148 triadic), 16-D 32-component GMM, N=100000, Kmax=64; start = "
+                       "16 clusters, each two true components merged; %d lockstep proposals per chain; a split's parameters are a prior "
+                       "draw, hopeless at 16-D: nothing is accepted, in the reference either" % proposals)
+    # regime 2: the reference's own territory (2-D), accepted moves
+    X2, y2 = syn.config(2)
+    X2, y2 = X2[:4000], y2[:4000]  # (from this start the chains soon hold a few clusters of ~N items: a proposal re-allocates ~N of them)
+    ds2 = npb.Dataset(ctx, X2)
+    acc = {}
+    for name, sampler, q_eval in (("jain_neal", npb.JAIN_NEAL, 2.0), ("triadic", npb.TRIADIC, 2.5)):
+        mc = npb.MCMC(ctx, ds2, npb.NormalInverseWishart(**syn.reference_prior(2)), chains=148, Kmax=256, K0=K0_REF, seed=SEED + 41 * rank)
+        acc[name] = one(mc.chains, sampler, q_eval, 2, y2, "k_split_merge<2>")
+        mc.chains.close()
+    ds2.close()
+    acc["workload"] = ("BASELINE configs[1] data, its first 4000 items (2-D 10-component GMM), 148 chains, Kmax=256, reference initialisation (K0 = 20 "
+                       "prior draws), %d lockstep proposals per chain" % proposals)
+    res["accepting_regime_2d"] = acc
+    npb.NormalInverseWishart(**syn.reference_prior(D)).bind(ctx)
+    if cpu:
+        try:
+            res["cpu_baseline"] = split_merge_cpu(X, D)
+        except Exception as e:
+            res["cpu_baseline"] = {"failed": repr(e)}
     return res
 
 
-def split_merge_cpu(X, D, n_items=1500, sweeps=2):
+def split_merge_cpu(X, D, n_items=1000, sweeps=1):
     """the reference's own split-merge samplers on the host cores: one chain per core over the first n_items items, `sweeps`
     sweeps (= n_items proposals each, np_mcmc.cpp:146-163) after its own initialisation"""
     from oracle import refrun
@@ -745,7 +767,7 @@ def main():
             line["roofline_fp32_equivalent"] = fp32_roofline
         if world == 1 and not args.no_also and args.config == "cfg5":
             try:
-                line["also"] = also_measure(npb, syn, ctx, fp32_peak, rank)
+                line["also"] = also_measure(npb, syn, ctx, fp32_peak, rank, cpu=not args.no_cpu_baseline)
             except Exception as e:
                 line["also"] = {"failed": repr(e)}
         if not args.no_cpu_baseline and world == 1:

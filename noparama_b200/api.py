@@ -539,8 +539,16 @@ class Chains:
 
     def close(self):
         if self._h:
-            self.ctx._lib.npb_chains_destroy(self._h)
+            if self.ctx._h:  # (a context closed first took its stream with it: nothing left to release the handle on)
+                self.ctx._lib.npb_chains_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        # a handle dropped without close() must not pin its dataset (npb_dataset_destroy refuses under live chain handles)
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class NealAlgorithm8:

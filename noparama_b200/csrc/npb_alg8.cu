@@ -186,7 +186,7 @@ static npb_status launch_chunk(npb_chains *ch, int n_sweeps) {
 	int key = ch->D * 1000 + ch->Kmax / 32;
 	// Kmax = 32, D >= 4: four chains per CTA with setmaxnreg (npb_alg8_tile4.cuh); NPB_TILE_KERNEL=2warp selects the
 	// earlier one-chain-per-CTA kernel for A/B measurements
-	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
+	const bool two_warp = ch->sw.two_warp;
 	if (!two_warp && ch->Kmax == 32 && (ch->D == 4 || ch->D == 8 || ch->D == 16)) key = -ch->D;
 	if (ch->Kmax == 32 && ch->D == 64) key = -64;
 	// D = 16, Kmax = 32: the tensor path of npb_alg8_gemm.cu (2x the FP32-pipe kernel at the headline shape);
@@ -246,7 +246,7 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 		ch->scan_cap = (int)(cap < 1 ? 1 : (cap > 1024 ? 1024 : cap));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->scan_order, per_sweep * ch->scan_cap));
 	}
-	static const bool two_warp = [] { const char *e = getenv("NPB_TILE_KERNEL"); return e && e[0] == '2'; }();
+	const bool two_warp = ch->sw.two_warp;
 	if ((!two_warp || ch->D == 64) && ch->Kmax == 32 && ch->D >= 4 && !ch->aux_keys) {
 		// as many sweeps per launch as fit 4 GB of auxiliary keys (one 32-bit word per chain and step)
 		const size_t per_sweep = (size_t)ch->ds->N * ch->C * sizeof(uint32_t);

@@ -733,7 +733,10 @@ npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a) {
 	if (ch->m_aux != 3 && ch->m_aux != 1) return npb_fail(ctx, NPB_E_UNSUPPORTED, "m_aux must be 1 or 3 for the D = 16 tensor-core sweep");
 	npb_status s = npb_tc16_ensure(ch, false);
 	if (s != NPB_OK) return s;
-	s = npb_launch_aux_bound<16>(ch, a); // group maxima of a bound of the auxiliary keys (exact keys on demand in the kernel)
+	// group maxima of a bound of the auxiliary keys (exact keys on demand in the kernel).  (Measured and dropped: the same bounds
+	// block by block on a second, low-priority stream in 32-register CTAs meant to sit beside the sweep kernel's CTA -- the sweep
+	// kernel's launches grew by what the bounds took, 51.4 -> 58.5 ms per sweep, and the step stayed at 65.7 ms.)
+	s = npb_launch_aux_bound<16>(ch, a);
 	if (s != NPB_OK) return s;
 	const size_t C = (size_t)ch->C;
 	// parameters may have changed since the last launch (init_from_params, update_params): every slot's image is rebuilt
@@ -755,8 +758,8 @@ npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a) {
 	p.dirty = ch->g_dirty;
 	p.zblk = ch->g_zblk;
 	p.zstride = BS;
-	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return e ? atoi(e) : 1; }();
-	p.flags = [] { const char *e = getenv("NPB_F16_FLAGS"); return e ? atoi(e) : 0; }(); // A/B measurement switches (results unchanged)
+	p.spec = ch->sw.spec;
+	p.flags = ch->sw.f16_flags; // A/B measurement switches (results unchanged)
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
 		for (int s0 = 0; s0 < N; s0 += BS, ++ch->g_k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;

@@ -610,23 +610,18 @@ __global__ void __launch_bounds__(128) k_density_fp32(const double *X64, const d
 // ---------------------------------------------------------------------------------------------------------
 template npb_status npb_launch_aux_keys<64>(npb_chains *, const SweepArgs &);
 
-// read at every use (cheap), so that one process can measure both settings
-static int g_block_steps() {
-	const char *e = getenv("NPB_D64_BLOCK");
-	int v = e ? atoi(e) : 4096;
+static int g_block_steps(const npb_chains *ch) {
+	int v = ch->sw.d64_block;
 	if (v < 128) v = 128;
 	if (v > (1 << 20)) v = 1 << 20;
 	return (v + 127) & ~127;
 }
-static bool g_use_fp32() {
-	const char *e = getenv("NPB_D64_DENSITY");
-	return e && e[0] == 'f';
-}
+static bool g_use_fp32(const npb_chains *ch) { return ch->sw.d64_fp32; }
 
 static npb_status g_ensure(npb_chains *ch) {
 	npb_ctx *ctx = ch->ctx;
 	npb_dataset *ds = ch->ds;
-	int BS = g_block_steps();
+	int BS = g_block_steps(ch);
 	if ((int64_t)BS > ((ds->N + 127) & ~(int64_t)127)) BS = (int)((ds->N + 127) & ~(int64_t)127); // no larger than the sweep
 	if (!ds->Xbar) NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * (2 * GD + 1))); // means, scale exponent, column maxima
 	if (!ds->xbar_valid) {
@@ -662,7 +657,7 @@ static npb_status g_launch_block(npb_chains *ch, const int32_t *d_order, int nst
 	GemmArgs g;
 	memset(&g, 0, sizeof(g));
 	int do_density = 0;
-	if (d_order && g_use_fp32()) {
+	if (d_order && g_use_fp32(ch)) {
 		dim3 grid((nsteps + 127) / 128, C);
 		k_density_fp32<<<grid, 128, 0, ctx->stream>>>(ch->ds->X64, ch->ds->Xbar, d_order, nsteps, ch->theta, L, BSP);
 		NPB_CUDA_OK(cudaGetLastError());
@@ -712,12 +707,12 @@ npb_status npb_launch_alg8_gemm64(npb_chains *ch, const SweepArgs &a) {
 	// that batching the sweeps differently does not change which code evaluated which column: results are bit-identical
 	// however a run is split, with the overlap (NPB_D64_OVERLAP=0: table and race in separate launches) or without.
 	const int BS = ch->g_bs, N = a.N, BSP = BS + 32;
-	const bool overlap = [] { const char *e = getenv("NPB_D64_OVERLAP"); return !(e && e[0] == '0'); }();
+	const bool overlap = ch->sw.d64_overlap;
 	PreArgs p, pending;
 	bool have_pending = false;
 	p.a = a;
 	p.BS = BSP;
-	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();
+	p.spec = ch->sw.spec != 0;
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
 		for (int s0 = 0; s0 < N; s0 += BS, ++ch->g_k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;
@@ -1057,9 +1052,8 @@ __global__ void __launch_bounds__(128, 4) k_race(const PreArgs p) {
 
 extern template npb_status npb_launch_aux_keys<16>(npb_chains *, const SweepArgs &);
 
-static int h_block_steps() {
-	const char *e = getenv("NPB_D16_BLOCK");
-	int v = e ? atoi(e) : 8192; // (4096 in round 1: the slots' operand images, 537 MB at 8192 chains, are re-read from HBM once per block)
+static int h_block_steps(const npb_chains *ch) {
+	int v = ch->sw.d16_block; // default 8192 (4096 in round 1: the slots' operand images, 537 MB at 8192 chains, are re-read from HBM once per block)
 	if (v < 128) v = 128;
 	if (v > (1 << 16)) v = 1 << 16;
 	return (v + 127) & ~127;
@@ -1079,7 +1073,7 @@ npb_status npb_tc16_ensure(npb_chains *ch, bool need_table) {
 	}
 	const size_t C = (size_t)ch->C;
 	if (!ch->g_aimg) {
-		int BS = h_block_steps();
+		int BS = h_block_steps(ch);
 		if ((int64_t)BS > ((ds->N + 127) & ~(int64_t)127)) BS = (int)((ds->N + 127) & ~(int64_t)127); // no larger than the sweep
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_aimg, (size_t)(BS / G_M) * H_ASTAGE));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->g_bimg, (C + 1) * 32 * H_SLOT_IMG));
@@ -1131,13 +1125,12 @@ static npb_status h_density_block(npb_chains *ch, const int32_t *d_order, int ns
 	g.BS = ch->g_bs + 32;
 	static int n_sm = 0;
 	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-	const char *ew = getenv("NPB_D16_EPI"), *nhs = getenv("NPB_D16_NH");
-	const int nh = nhs ? atoi(nhs) : 4;
+	const int nh = ch->sw.d16_nh;
 	const int n_units = (C * 2 + nh - 1) / nh;
 	const int grid = n_units < n_sm ? n_units : n_sm;
 	if (nh == 1) k_density_tc16<8, 1><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
 	else if (nh == 2) k_density_tc16<8, 2><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
-	else if (ew && ew[0] == '8') k_density_tc16<8, 4><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
+	else if (ch->sw.d16_epi == 8) k_density_tc16<8, 4><<<grid, 8 * 32 + 64, H_SMEM, ctx->stream>>>(g);
 	else k_density_tc16<16, 4><<<grid, 16 * 32 + 64, H_SMEM, ctx->stream>>>(g);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
@@ -1152,7 +1145,7 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	// draws' first normals and evaluates them on demand (g_aux_bound / g_aux_exact; same keys, same results, 3.2 GB less
 	// memory).  Measured equal (101 against 102 ms per sweep): the bound leaves out the chi-square term, which is what makes
 	// an auxiliary draw hopeless at D = 16, so a third of the steps still need the exact key and every tile pays for it.
-	const bool prepass = [] { const char *e = getenv("NPB_D16_AUX"); return !(e && e[0] == 'l'); }();
+	const bool prepass = ch->sw.d16_aux_pre;
 	if (prepass) {
 		s = npb_launch_aux_keys<16>(ch, a);
 		if (s != NPB_OK) return s;
@@ -1165,7 +1158,7 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	if (!prepass) p.a.aux_keys = nullptr;
 	p.BS = BS + 32;
 	p.L = ch->g_L;
-	p.spec = [] { const char *e = getenv("NPB_D64_SPEC"); return !(e && e[0] == '0'); }();
+	p.spec = ch->sw.spec != 0;
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
 		for (int s0 = 0; s0 < N; s0 += BS, ++ch->g_k) {
 			const int nsteps = N - s0 < BS ? N - s0 : BS;

@@ -189,10 +189,16 @@ __device__ __forceinline__ void aux_draw_chi(uint32_t (&as)[4], const PriorDev &
 // draw thousands of log2 units below any item's own cluster.
 template <int D>
 __device__ __forceinline__ float aux_draw_bound(uint32_t (&as)[4], const PriorDev &pr, float rn, float ik2) {
+	// (single-instruction approximations of the square root and the reciprocal: their 2^-22 relative error moves the bound by
+	// ~0.02 log2 units at most, inside the slack below; aux_draw_chi's IEEE versions cost two slow-path branches per draw)
 	float g0, g1;
 	{
 		const uint32_t r0 = xoshiro_next(as), r1 = xoshiro_next(as);
-		npb_normal2(r0, r1, g0, g1);
+		float rad, s, c;
+		asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * NPB_LN2 * __log2f(npb_u01(r0))));
+		__sincosf(__uint2float_rn(r1) * (6.283185307179586f * 2.3283064365386963e-10f), &s, &c);
+		g0 = rad * c;
+		g1 = rad * s;
 	}
 	const float av = fmaxf(fabsf(pr.v_mean + pr.nu * g0), 1e-20f);
 	constexpr int KU = (D - 1) / 2;
@@ -204,7 +210,9 @@ __device__ __forceinline__ float aux_draw_bound(uint32_t (&as)[4], const PriorDe
 		if (i + 1 < KU) prod *= __uint2float_rn((w >> 16) + 1u) * (1.0f / 65536.0f);
 	}
 	const float lb = -2.0f * NPB_LN2 * fast_lg2(prod);
-	const float along = rn * __frcp_rn(av) - ik2 * g1;
+	float rav;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rav) : "f"(av));
+	const float along = rn * rav - ik2 * g1;
 	return pr.c0_2 - (float)D * fast_lg2(av) - fmaf(along, along, ik2 * ik2 * lb) + pr.log2_alpha_m + 24.0f;
 }
 

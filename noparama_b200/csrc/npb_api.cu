@@ -290,6 +290,7 @@ static npb_status ensure_whitened(npb_dataset *ds) {
 	return npb_launch_whiten(ds);
 }
 
+static npb_status set_switch(npb_chains *ch, const char *name, const char *value);
 npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, int Kmax, int m_aux, int K0, uint64_t seed,
 		npb_chains **out) {
 	if (!ctx || !ds || !out || ds->ctx != ctx || n_chains <= 0 || n_chains > 0x7fffffff || Kmax <= 0 || Kmax > 65535 ||
@@ -311,6 +312,15 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 	{ // behaviour switches are read once, here (npb_chains_set_option changes them afterwards)
 		const char *e = getenv("NPB_D16_PATH");
 		strncpy(ch->opt_d16_path, e && e[0] ? e : "auto", sizeof(ch->opt_d16_path) - 1);
+		static const char *const names[] = {"NPB_D64_SPEC", "NPB_F16_FLAGS", "NPB_D16_BLOCK", "NPB_D64_BLOCK", "NPB_D16_EPI", "NPB_D16_NH",
+				"NPB_D16_AUX", "NPB_D64_OVERLAP", "NPB_D64_DENSITY", "NPB_TILE_KERNEL"};
+		static const char *const opts[] = {"spec", "f16_flags", "d16_block", "d64_block", "d16_epi", "d16_nh", "d16_aux", "d64_overlap",
+				"d64_density", "tile_kernel"};
+		for (int i = 0; i < 10; ++i)
+			if ((e = getenv(names[i])) && e[0] && set_switch(ch, opts[i], e) != NPB_OK) {
+				npb_chains_destroy(ch);
+				return npb_fail(ctx, NPB_E_BAD_ARG, "bad value in an NPB_* environment switch");
+			}
 	}
 	const size_t PS = npb_ps(ds->D);
 	cudaError_t e;
@@ -335,8 +345,27 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 	return NPB_OK;
 }
 
+// the measurement / behaviour switches of npb_chains::Switches by option name; NPB_E_BAD_ARG for an unknown name or value
+static npb_status set_switch(npb_chains *ch, const char *name, const char *value) {
+	npb_chains::Switches &w = ch->sw;
+	const int v = atoi(value);
+	if (!strcmp(name, "spec")) { if (v < 0 || v > 2) return NPB_E_BAD_ARG; w.spec = v; }
+	else if (!strcmp(name, "f16_flags")) w.f16_flags = v;
+	else if (!strcmp(name, "d16_block")) { if (v < 1) return NPB_E_BAD_ARG; w.d16_block = v; }
+	else if (!strcmp(name, "d64_block")) { if (v < 1) return NPB_E_BAD_ARG; w.d64_block = v; }
+	else if (!strcmp(name, "d16_epi")) { if (v != 8 && v != 16) return NPB_E_BAD_ARG; w.d16_epi = v; }
+	else if (!strcmp(name, "d16_nh")) { if (v != 1 && v != 2 && v != 4) return NPB_E_BAD_ARG; w.d16_nh = v; }
+	else if (!strcmp(name, "d16_aux")) w.d16_aux_pre = value[0] != 'l';
+	else if (!strcmp(name, "d64_overlap")) w.d64_overlap = value[0] != '0';
+	else if (!strcmp(name, "d64_density")) w.d64_fp32 = value[0] == 'f';
+	else if (!strcmp(name, "tile_kernel")) w.two_warp = value[0] == '2';
+	else return NPB_E_BAD_ARG;
+	return NPB_OK;
+}
+
 npb_status npb_chains_set_option(npb_chains *ch, const char *name, const char *value) {
 	if (!ch || !name || !value) return NPB_E_BAD_ARG;
+	if (set_switch(ch, name, value) == NPB_OK) return NPB_OK;
 	if (!strcmp(name, "d16_path")) {
 		if (strcmp(value, "auto") && strcmp(value, "tc") && strcmp(value, "tc2") && strcmp(value, "fp32"))
 			return npb_fail(ch->ctx, NPB_E_BAD_ARG, "d16_path: auto | tc | tc2 | fp32");

@@ -49,6 +49,20 @@ struct npb_chains {
 	uint64_t seed = 0;
 	uint32_t sweep = 0;         // sweeps done so far (Philox counter / scan-order key)
 	char opt_d16_path[8] = {0}; // NPB_D16_PATH as read when the handle was created (auto / tc / tc2 / fp32)
+	// behaviour / measurement switches: the NPB_* environment variables are read ONCE, in npb_chains_create
+	// (npb_switches_from_env), and changed afterwards only through npb_chains_set_option; no launch path reads the environment
+	struct Switches {
+		int spec = 1;             // NPB_D64_SPEC: 0 sequential evaluation, 1 speculation (default), 2 table only (measurement)
+		int f16_flags = 0;        // NPB_F16_FLAGS: A/B measurement bits of k_sweep_tc16 (results unchanged)
+		int d16_block = 8192;     // NPB_D16_BLOCK: steps per launch of the D = 16 tensor paths
+		int d64_block = 4096;     // NPB_D64_BLOCK: steps per launch of the D = 64 path
+		int d16_epi = 16;         // NPB_D16_EPI: epilogue warps of k_density_tc16 (8 | 16)
+		int d16_nh = 4;           // NPB_D16_NH: chain halves per unit of k_density_tc16 (1 | 2 | 4)
+		bool d16_aux_pre = true;  // NPB_D16_AUX=lazy -> false: no k_aux_keys pre-pass on the kernel pair
+		bool d64_overlap = true;  // NPB_D64_OVERLAP=0 -> false
+		bool d64_fp32 = false;    // NPB_D64_DENSITY=fp32
+		bool two_warp = false;    // NPB_TILE_KERNEL=2warp: round-1 one-chain-per-CTA kernel
+	} sw;
 	double moved_frac_last = -1.0; // moved / reassignments of the last Algorithm 8 launch whose statistics were read; -1 unknown
 	bool time_kernels = false;  // option "time_kernels": CUDA events around every launch of the dominant sweep kernel
 	std::vector<cudaEvent_t> kt_ev; // pairs (start, stop) not yet read back

@@ -20,8 +20,12 @@ ctx = npb.Context(0)
 ds = npb.Dataset(ctx, X)
 mc = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=chains, Kmax=32, K0=20, seed=3)
 mc.chains.init_from_params(means, Sigma)
+if os.environ.get("TK"):
+    mc.chains.set_option("time_kernels", "1")
 for it in range(sweeps):
     st = mc.chains.sweep(npb.ALG8, 1)
+    if os.environ.get("TK"):
+        print("   sweep-kernel launches: ms, n =", mc.chains.kernel_time())
     print(os.environ.get("NPB_D16_PATH", "fused"), regime, chains, it, "ms %.2f rate %.3e meanK %.1f cand/step %.1f moved %.6f births %d" % (
         st.kernel_ms, st.reassignments / (st.kernel_ms * 1e-3), st.mean_K, st.candidates / st.reassignments,
         st.moved / st.reassignments, st.new_clusters), flush=True)
