@@ -115,6 +115,7 @@ static npb_status dataset_push(npb_dataset *ds, const double *X) {
 }
 
 npb_status npb_dataset_upload(npb_ctx *ctx, const double *X, int64_t N, int D, npb_dataset **out) {
+	NpbRange nvtx_range("npb:dataset_upload");
 	if (!ctx || !X || !out || N <= 0 || D <= 0 || D > NPB_MAX_D || N > 0x7fffffff) return NPB_E_BAD_ARG;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
 	npb_dataset *ds = new (std::nothrow) npb_dataset();
@@ -143,6 +144,7 @@ npb_status npb_dataset_upload(npb_ctx *ctx, const double *X, int64_t N, int D, n
 }
 
 npb_status npb_dataset_update(npb_dataset *ds, const double *X) {
+	NpbRange nvtx_range("npb:dataset_update");
 	if (!ds || !X) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ds->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -573,6 +575,7 @@ static npb_status collect_stats(npb_chains *ch, const std::vector<unsigned long 
 
 static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_t n_proposals, npb_sweep_stats *stats,
 		const double *X, uint16_t *z_out) {
+	NpbRange nvtx_range(sampler == NPB_ALG8 ? "npb:sweep alg8" : sampler == NPB_ALG2 ? "npb:sweep alg2" : sampler == NPB_ALG2_CONJUGATE ? "npb:sweep alg2 conjugate" : sampler == NPB_JAIN_NEAL ? "npb:split-merge jain-neal" : "npb:split-merge triadic");
 	if (!ch || n_sweeps < 0 || n_proposals < 0) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -651,6 +654,7 @@ npb_status npb_chains_split_merge(npb_chains *ch, int sampler, int64_t n_proposa
 	return sweep_common(ch, sampler, 0, n_proposals, stats, nullptr, nullptr);
 }
 npb_status npb_chains_update_params(npb_chains *ch, int mode, const double *mu0, double kappa0, double nu0, const double *Lambda0) {
+	NpbRange nvtx_range("npb:update_params");
 	if (!ch || (mode != NPB_UPDATE_POSTERIOR_DRAW && mode != NPB_UPDATE_POSTERIOR_MEAN)) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -673,6 +677,7 @@ npb_status npb_chains_last_proposal(npb_chains *ch, float *detail_out) {
 }
 npb_status npb_chains_sweep_host(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_out,
 		npb_sweep_stats *stats) {
+	NpbRange nvtx_range("npb:sweep_host (h2d + sweep + d2h)");
 	if (!X) return NPB_E_BAD_ARG;
 	return sweep_common(ch, sampler, n_sweeps, 0, stats, X, z_out);
 }
@@ -935,6 +940,7 @@ __global__ void __launch_bounds__(256) k_z_delta(const npb_z_t *z, npb_z_t *prev
 
 npb_status npb_chains_sweep_host_delta(npb_chains *ch, const double *X, int sampler, int n_sweeps, uint16_t *z_mirror,
 		npb_sweep_stats *stats, int64_t *n_changed) {
+	NpbRange nvtx_range("npb:sweep_host_delta (h2d + sweep + changed entries d2h)");
 	if (!ch || !z_mirror) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -994,6 +1000,7 @@ npb_status npb_chains_sweep_host_delta(npb_chains *ch, const double *X, int samp
 
 npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *purity, double *rand_index, double *adjusted_rand,
 		double *joint_loglik, int32_t *K) {
+	NpbRange nvtx_range("npb:metrics");
 	if (!ch) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -1031,6 +1038,7 @@ npb_status npb_chains_metrics(npb_chains *ch, const int32_t *truth, double *puri
 }
 
 npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, float *S_dev, int accumulate) {
+	NpbRange nvtx_range("npb:cocluster");
 	if (!ch || !anchors || !S_dev || n_anchor <= 0 || n_anchor > 65535) return NPB_E_BAD_ARG;
 	npb_ctx *ctx = ch->ctx;
 	NPB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -1046,6 +1054,7 @@ npb_status npb_cocluster(npb_chains *ch, const int64_t *anchors, int64_t n_ancho
 }
 
 npb_status npb_cocluster_allreduce(npb_chains *ch, const int64_t *anchors, int64_t n_anchor, npb_comm *comm, float *S_dev) {
+	NpbRange nvtx_range("npb:cocluster_allreduce");
 	npb_status s = npb_cocluster(ch, anchors, n_anchor, S_dev, 0);
 	if (s != NPB_OK || !comm) return s;
 	s = npb_comm_allreduce_sum(comm, S_dev, n_anchor * n_anchor, 32);

@@ -1,5 +1,6 @@
 // npb_internal.h -- host-side structs behind the opaque handles of include/npb200.h
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/npb200.h"
 #include "npb_common.cuh"
 #include <vector>
@@ -14,6 +15,15 @@ struct PriorHost {
 	std::vector<double> CT;  // C^T packed upper (A^-1 = C C^T)
 	std::vector<double> S;   // C^-T packed upper
 	double logdetA = 0;
+};
+
+// NVTX range around every public entry point that launches device work (visible in Nsight Systems / ncu --nvtx; free when no
+// tool is attached: the header-only NVTX 3 stubs return at once)
+struct NpbRange {
+	explicit NpbRange(const char *name) { nvtxRangePushA(name); }
+	~NpbRange() { nvtxRangePop(); }
+	NpbRange(const NpbRange &) = delete;
+	NpbRange &operator=(const NpbRange &) = delete;
 };
 
 struct npb_ctx {

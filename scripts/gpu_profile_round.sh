@@ -11,6 +11,8 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-also"
    --log-file $O/r2_launches_bench_steps2.csv $CMD > $O/r2_ncu_list.log 2>&1; echo "ncu list exit $?")
 (timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep_tc16 -s 40 -c 1 -f -o $O/r2_fused16 \
    $CMD > $O/r2_ncu_full.log 2>&1; echo "ncu full exit $?")
-(timeout 600 compute-sanitizer --tool memcheck --log-file $O/r2_sanitizer_memcheck.log python scripts/sanitize_small.py all > $O/r2_sanitize_all.out 2>&1; echo "memcheck exit $?")
-(timeout 400 compute-sanitizer --tool racecheck --log-file $O/r2_sanitizer_racecheck_fused.log python scripts/sanitize_small.py fused > $O/r2_sanitize_race.out 2>&1; echo "racecheck exit $?")
-tail -3 $O/r2_smoke.log; tail -c 600 $O/r2_prof_bench.json; tail -5 $O/r2_sanitizer_memcheck.log; tail -5 $O/r2_sanitizer_racecheck_fused.log
+# compute-sanitizer: one attempt, kept for the record (this pool answers that the tool is closed; see profiles/README.md)
+(timeout 300 compute-sanitizer --tool memcheck --log-file $O/r2_sanitizer_memcheck.log python scripts/sanitize_small.py all > $O/r2_sanitize_all.out 2>&1; echo "memcheck exit $?")
+# the same small configurations without the tool: every kernel family runs and the library's own checks pass
+(timeout 300 python scripts/sanitize_small.py all > $O/r2_small_all.out 2>&1; echo "small configurations exit $?")
+tail -3 $O/r2_smoke.log; tail -c 300 $O/r2_prof_bench.json; tail -3 $O/r2_sanitize_all.out; tail -8 $O/r2_small_all.out
