@@ -85,3 +85,32 @@ def gmm_mixing(N, D, K_true, seed, pair_dist=2.5, min_dist=6.0, box=12.0):
     X = means[y] + rng.standard_normal((N, D))
     perm = rng.permutation(N)
     return X[perm], y[perm]
+
+
+def reference_nig_prior():
+    """np_main.cpp:357-364: the normal-inverse-gamma base measure of `-c regression` / `-c angular`."""
+    return dict(mu0=np.zeros(2), Lambda=0.01 * np.eye(2), nig_alpha=10.0, nig_beta=0.1, alpha=1.0)
+
+
+def regression_lines(N, K_true, seed, noise=0.1, span=5.0):
+    """N points on K_true lines b = c0 + c1 a + noise, in the row format read_data builds for `-c regression`
+    (np_main.cpp:83-92): (1, a, b).  Returns (rows [N,3], labels)."""
+    rng = np.random.default_rng(seed)
+    coef = np.stack([rng.uniform(-4.0, 4.0, K_true), rng.uniform(-3.0, 3.0, K_true)], 1)
+    y = rng.permutation(np.arange(N) % K_true).astype(np.int32)
+    a = rng.uniform(-span, span, N)
+    b = coef[y, 0] + coef[y, 1] * a + noise * rng.standard_normal(N)
+    return np.stack([np.ones(N), a, b], 1), y
+
+
+def angular_lines(N, K_true, seed, noise=0.05, span=5.0):
+    """N points of the plane on K_true lines in normal form (d, theta) -- signed distance d > 0 along the normal
+    (-sin theta, cos theta) -- the data `-c angular` models (np_main.cpp:93-101 rows (a, b)).  Returns (rows [N,2], labels)."""
+    rng = np.random.default_rng(seed)
+    theta, d = rng.uniform(0.2, np.pi - 0.2, K_true), rng.uniform(1.0, 8.0, K_true)
+    y = rng.permutation(np.arange(N) % K_true).astype(np.int32)
+    t = rng.uniform(-span, span, N)
+    nrm = np.stack([-np.sin(theta[y]), np.cos(theta[y])], 1)
+    along = np.stack([np.cos(theta[y]), np.sin(theta[y])], 1)
+    P = nrm * d[y, None] + along * t[:, None] + noise * rng.standard_normal((N, 2))
+    return P, y

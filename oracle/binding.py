@@ -306,3 +306,68 @@ def alg2_run(prior, X, T, K0, seed):
                                C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.npo_alg2_run(C.byref(prior), _dp(X), N, T, K0, seed, _ip(z), _ip(Kt), C.byref(moved), C.byref(births))
     return z, Kt, moved.value, births.value
+
+
+# ---- scalar-noise families (`-c regression` / `-c angular`): scalarnoise_multivariatenormal.cpp + normalinvgamma.h ----
+REGRESSION, ANGULAR = 1, 2
+
+
+def _sn_setup():
+    L = lib()
+    if getattr(L, "_sn_ready", False):
+        return L
+    dp = C.POINTER(C.c_double)
+    for name in ("npo_scalarnoise_logpdf", "npo_scalarnoise_pdf"):
+        getattr(L, name).restype = C.c_double
+        getattr(L, name).argtypes = [C.c_int, dp, C.c_double, dp]
+    L.npo_sample_base_nig.argtypes = [dp, dp, C.c_double, C.c_double, C.c_uint32, C.c_int, dp, dp]
+    L.npo_mcmc_run_scalarnoise.restype = C.c_void_p
+    L.npo_mcmc_run_scalarnoise.argtypes = [C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, C.POINTER(Options), dp, C.c_int]
+    L.npo_run_params_scalarnoise.argtypes = [C.c_void_p, C.POINTER(C.c_int), dp, dp, C.POINTER(C.c_int64), C.c_int]
+    L._sn_ready = True
+    return L
+
+
+def scalarnoise_logpdf(family, mu, sigma, x, log=True):
+    L = _sn_setup()
+    mu, x = _f64(mu), _f64(x)
+    return (L.npo_scalarnoise_logpdf if log else L.npo_scalarnoise_pdf)(family, _dp(mu), float(sigma), _dp(x))
+
+
+def scalarnoise_logpdf_batch(family, mu, sigma, X):
+    """[n, K] log-densities of the rows of X under the K parameter sets (mu [K,2], sigma [K])"""
+    mu, X = _f64(mu), _f64(X)
+    return np.array([[scalarnoise_logpdf(family, mu[k], sigma[k], X[i]) for k in range(len(mu))] for i in range(len(X))])
+
+
+def sample_base_nig(prior, seed, count):
+    """count draws of (mu [2], sigma) from the normal-inverse-gamma base measure; prior: dict(mu0, Lambda, nig_alpha, nig_beta)"""
+    L = _sn_setup()
+    mu0, Lam = _f64(prior["mu0"]), _f64(prior["Lambda"])
+    mu, sg = np.empty((count, 2)), np.empty(count)
+    L.npo_sample_base_nig(_dp(mu0), _dp(Lam), float(prior["nig_alpha"]), float(prior["nig_beta"]), seed, count, _dp(mu), _dp(sg))
+    return mu, sg
+
+
+class ScalarNoiseRun(Run):
+    """One oracle run of MCMC::run with the scalar-noise likelihood; X: the rows read_data builds ((1, a, b) | (a, b))."""
+
+    def __init__(self, family, prior, X, algorithm=ALG8, T=1000, K0=20, M_aux=3, mh_steps=20, seed_main=1, seed_shuffle=2,
+                 flags=FAITHFUL):
+        L = _sn_setup()
+        X = _f64(X)
+        self.N, self.D = X.shape
+        assert self.D == (3 if family == REGRESSION else 2)
+        self.M_aux, self.T = M_aux, T
+        opt = Options(algorithm, T, K0, M_aux, mh_steps, seed_main, seed_shuffle, flags)
+        mu0, Lam = _f64(prior["mu0"]), _f64(prior["Lambda"])
+        self._h = L.npo_mcmc_run_scalarnoise(family, _dp(mu0), _dp(Lam), float(prior["nig_alpha"]), float(prior["nig_beta"]),
+                                             float(prior["alpha"]), C.byref(opt), _dp(X), self.N)
+        assert self._h
+
+    def params(self, cap=4096):
+        L = _sn_setup()
+        K = C.c_int()
+        mu, sg, cnt = np.empty((cap, 2)), np.empty(cap), np.empty(cap, dtype=np.int64)
+        assert L.npo_run_params_scalarnoise(self._h, C.byref(K), _dp(mu), _dp(sg), cnt.ctypes.data_as(C.POINTER(C.c_int64)), cap) == 0
+        return mu[:K.value].copy(), sg[:K.value].copy(), cnt[:K.value].copy()

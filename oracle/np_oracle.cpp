@@ -201,10 +201,44 @@ struct Counters {
  * left-to-right evaluation order; constant = sqrt(pow(2 pi, D) * det). */
 struct Density {
 	bool per_call_lu = true;
+	int family = 0; /* 0: multivariate normal; NPO_FAMILY_REGRESSION / NPO_FAMILY_ANGULAR: scalarnoise_multivariatenormal.cpp */
 	Counters *cnt = nullptr;
 	std::vector<double> inv_tmp, row_tmp, diff_tmp;
 
+	/* scalarnoise_multivariate_normal_distribution::probability / logprobability (scalarnoise_multivariatenormal.cpp:77-150,
+	 * :182-250): a one-dimensional normal of standard deviation sigma on a residual -- regression_mode (:86-101, :190-207): the
+	 * row is (x_0 .. x_{D-1}, y) and the residual y - x . mu; angular_mode (:120-140, :225-249): the row is a point of the plane,
+	 * mu = (d, theta) is a line in normal form, made canonical by prepare() (:31-47) every time the object is bound to a theta,
+	 * and the residual |d - q_1| with q = R(theta) x.  The probability divides by sqrt(2 pi sigma^2), the log-probability
+	 * subtracts log(2 pi sigma^2) / 2. */
+	double scalarnoise_exponent(const Theta &th, const double *x) const {
+		const double var = th.sigma[0];
+		double diff;
+		if (family == NPO_FAMILY_REGRESSION) {
+			const int D = (int)th.mu.size();
+			double y_proj = 0.0;
+			for (int i = 0; i < D; ++i) y_proj += x[i] * th.mu[i];
+			diff = x[D] - y_proj;
+		} else {
+			/* prepare() calls the unqualified abs(): in this translation unit (as in a build against the real Eigen, which
+			 * pulls in <cmath> and <cstdlib> but not <math.h>) overload resolution finds only ::abs(int), so both parameters
+			 * are TRUNCATED to integers before the absolute value (quirk Q12; verified against oracle/_ref) */
+			const double d = (double)std::abs((int)th.mu[0]);
+			const double theta = std::fmod((double)std::abs((int)th.mu[1]), 2 * M_PI);
+			const double q1 = -std::sin(theta) * x[0] + std::cos(theta) * x[1];
+			diff = std::abs(d - q1);
+		}
+		const double inverse = 1 / (var * var);
+		return -0.5 * (diff * diff) * inverse;
+	}
+
 	void terms(const Theta &th, const double *x, double &exponent, double &constant) {
+		if (family) { /* (callers below never get here for the scalar-noise families) */
+			exponent = scalarnoise_exponent(th, x);
+			constant = std::sqrt(2 * M_PI * th.sigma[0] * th.sigma[0]);
+			if (cnt) cnt->density_evals++;
+			return;
+		}
 		const int D = (int)th.mu.size();
 		const double *inv;
 		if (per_call_lu) {
@@ -243,6 +277,11 @@ struct Density {
 		return std::exp(e) / c;
 	}
 	double logprobability(const Theta &th, const double *x) {
+		if (family) {
+			if (cnt) cnt->density_evals++;
+			const double constant = 2 * M_PI * th.sigma[0] * th.sigma[0];
+			return scalarnoise_exponent(th, x) - std::log(constant) / 2;
+		}
 		double e, c;
 		terms(th, x, e, c);
 		return e - std::log(c);
@@ -256,6 +295,9 @@ struct Prior {
 	int D;
 	std::vector<double> mu0, Lambda;
 	double kappa, nu, alpha;
+	/* scalar-noise families: normal-inverse-gamma base measure (normalinvgamma.h), D = 2 parameters */
+	int family = 0;
+	double ig_alpha = 1.0, ig_beta = 1.0;
 };
 
 struct Process {
@@ -266,13 +308,15 @@ struct Process {
 	 * parameters frozen at first use, saved spare value shared by all callers */
 	std::normal_distribution<> static_scalar;
 	std::normal_distribution<> static_std;
+	/* gamma.h:41: function-static std::gamma_distribution, parameters frozen at the first draw */
+	std::gamma_distribution<> static_gamma;
 	/* static mt19937 of the 1-argument random_order (dim1algebra.hpp:2066-2073) */
 	std::mt19937 mt;
 
 	Process(const Prior &prior, uint32_t seed_main, uint32_t seed_shuffle)
 		: gen_main(seed_main), gen_init(gen_main), gen_upd(gen_main), gen_pop(gen_main),
 		  static_scalar((double)prior.D, prior.nu) /* mean=D, "variance" passed as stddev: invwishart.h:30-31 */,
-		  static_std(0.0, 1.0), mt(seed_shuffle) {}
+		  static_std(0.0, 1.0), static_gamma(prior.ig_alpha, prior.ig_beta), mt(seed_shuffle) {}
 };
 
 /* dirichlet_process::sample_base (dirichlet.h:91-93) -> normal_inverse_wishart_distribution::operator()
@@ -283,6 +327,26 @@ static Theta *sample_base(const Prior &prior, Process &proc, engine_t &gen) {
 	const int D = prior.D;
 	Theta *th = new Theta();
 	th->mu.resize(D);
+	if (prior.family) {
+		/* normal_inverse_gamma_distribution::operator() (normalinvgamma.h:58-84): sigma^2 = 1 / Gamma(alpha, beta) (gamma.h:37-46,
+		 * std::gamma_distribution(shape, scale)), then mu ~ N(mu0, sigma^2 Lambda^-1) through
+		 * multivariate_normal_distribution::operator() (multivariatenormal.cpp:37-50) */
+		const double val = proc.static_gamma(gen);
+		const double sigma_pow2 = 1.0 / val;
+		th->sigma.assign(1, std::sqrt(sigma_pow2));
+		std::vector<double> inv(D * D), cov(D * D), evals, evecs;
+		lu_inverse(D, prior.Lambda.data(), inv.data());
+		for (int i = 0; i < D * D; ++i) cov[i] = sigma_pow2 * inv[i];
+		sym_eigen(D, cov.data(), evals, evecs);
+		std::vector<double> z(D);
+		for (int d = 0; d < D; ++d) z[d] = proc.static_std(gen);
+		for (int i = 0; i < D; ++i) {
+			double acc = 0.0;
+			for (int k = 0; k < D; ++k) acc += (evecs[i * D + k] * std::sqrt(evals[k])) * z[k];
+			th->mu[i] = prior.mu0[i] + acc;
+		}
+		return th;
+	}
 	th->sigma.resize(D * D);
 	/* invwishart.h:38-43: v scalar; x = L^T * v ; sigma = x * x^T = v^2 L^T L */
 	double v = proc.static_scalar(gen);
@@ -574,6 +638,7 @@ struct Sampler {
 		  trix((r.opt.flags & NPO_DENSE_MATRIX) != 0), N(r.N), D(r.D), X(r.X.data()),
 		  record((r.opt.flags & NPO_RECORD_TRACE) != 0), log_domain((r.opt.flags & NPO_LOG_DOMAIN) != 0) {
 		density.per_call_lu = (r.opt.flags & NPO_PER_CALL_LU) != 0;
+		density.family = r.prior.family;
 		density.cnt = &counters;
 	}
 	const double *x(int i) const { return X + (size_t)i * D; }
@@ -985,6 +1050,77 @@ npo_run *npo_mcmc_run_given(const npo_prior *prior, const npo_options *opt, cons
 	Sampler s(*r);
 	s.mcmc_run();
 	return r;
+}
+/* the same run with the scalar-noise likelihood and the normal-inverse-gamma base measure of `-c regression` / `-c angular`
+ * (np_main.cpp:322-328, :357-364): X [N, row] with row = 3 (1, a, b) for regression, 2 for angular (np_main.cpp:83-101) */
+static Prior make_nig_prior(int family, const double *mu0, const double *Lambda, double ig_alpha, double ig_beta, double dp_alpha) {
+	Prior pr;
+	pr.D = 2;
+	pr.mu0.assign(mu0, mu0 + 2);
+	pr.Lambda.assign(Lambda, Lambda + 4);
+	pr.kappa = pr.nu = 1.0;
+	pr.alpha = dp_alpha;
+	pr.family = family;
+	pr.ig_alpha = ig_alpha;
+	pr.ig_beta = ig_beta;
+	return pr;
+}
+npo_run *npo_mcmc_run_scalarnoise(int family, const double *mu0, const double *Lambda, double ig_alpha, double ig_beta, double dp_alpha,
+		const npo_options *opt, const double *X, int N) {
+	if (family != NPO_FAMILY_REGRESSION && family != NPO_FAMILY_ANGULAR) return nullptr;
+	npo_run *r = new npo_run();
+	r->prior = make_nig_prior(family, mu0, Lambda, ig_alpha, ig_beta, dp_alpha);
+	r->opt = *opt;
+	r->opt.flags &= ~NPO_RECORD_TRACE; /* the replay traces are laid out for (mu [D], Sigma [D, D]) */
+	r->N = N;
+	r->D = family == NPO_FAMILY_REGRESSION ? 3 : 2; /* row width of X */
+	r->X.assign(X, X + (size_t)N * r->D);
+	std::memset(&r->stats, 0, sizeof(r->stats));
+	r->stats.max_loglik = -std::numeric_limits<double>::infinity();
+	Sampler s(*r);
+	s.mcmc_run();
+	return r;
+}
+double npo_scalarnoise_logpdf(int family, const double *mu, double sigma, const double *x) {
+	Density d;
+	d.family = family;
+	Theta th;
+	th.mu.assign(mu, mu + 2);
+	th.sigma.assign(1, sigma);
+	return d.logprobability(th, x);
+}
+double npo_scalarnoise_pdf(int family, const double *mu, double sigma, const double *x) {
+	Density d;
+	d.family = family;
+	Theta th;
+	th.mu.assign(mu, mu + 2);
+	th.sigma.assign(1, sigma);
+	return d.probability(th, x);
+}
+void npo_sample_base_nig(const double *mu0, const double *Lambda, double ig_alpha, double ig_beta, uint32_t seed, int count, double *mu_out,
+		double *sigma_out) {
+	Prior pr = make_nig_prior(NPO_FAMILY_REGRESSION, mu0, Lambda, ig_alpha, ig_beta, 1.0);
+	Process proc(pr, seed, 0);
+	for (int c = 0; c < count; ++c) {
+		Theta *th = sample_base(pr, proc, proc.gen_main);
+		mu_out[2 * c] = th->mu[0];
+		mu_out[2 * c + 1] = th->mu[1];
+		sigma_out[c] = th->sigma[0];
+		delete th;
+	}
+}
+/* final clusters of a scalar-noise run: mu [K, 2], sigma [K] */
+int npo_run_params_scalarnoise(const npo_run *r, int *K, double *mu, double *sigma, int64_t *counts, int cap) {
+	int k = (int)r->final_mu.size();
+	*K = k;
+	if (k > cap || !r->prior.family) return -1;
+	for (int j = 0; j < k; ++j) {
+		mu[2 * j] = r->final_mu[j][0];
+		mu[2 * j + 1] = r->final_mu[j][1];
+		sigma[j] = r->final_sigma[j][0];
+		counts[j] = r->final_counts[j];
+	}
+	return 0;
 }
 void npo_run_free(npo_run *r) { delete r; }
 void npo_run_stats(const npo_run *r, npo_stats *out) { *out = r->stats; }

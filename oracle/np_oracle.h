@@ -151,6 +151,18 @@ double npo_niw_logpred_incremental(const npo_prior *prior, int n, const double *
 void npo_alg2_run(const npo_prior *prior, const double *X, int N, int T, int K0, uint64_t seed, int *z_out, int *K_trace,
 		int64_t *moved_out, int64_t *births_out);
 
+/* ---- scalar-noise likelihood families (`-c regression` / `-c angular`, np_main.cpp:196-205): scalarnoise_multivariatenormal.cpp
+ * + normalinvgamma.h + gamma.h.  PINNED against the reference's own sources (oracle/_ref np_ref_run ... FAMILY): same assignments
+ * after every run of tests/test_oracle_scalarnoise.py ---- */
+enum { NPO_FAMILY_MVN = 0, NPO_FAMILY_REGRESSION = 1, NPO_FAMILY_ANGULAR = 2 };
+double npo_scalarnoise_logpdf(int family, const double *mu /*[2]*/, double sigma, const double *x /*[3] (1, a, b) | [2]*/);
+double npo_scalarnoise_pdf(int family, const double *mu, double sigma, const double *x);
+void npo_sample_base_nig(const double *mu0 /*[2]*/, const double *Lambda /*[2,2]*/, double ig_alpha, double ig_beta, uint32_t seed, int count,
+		double *mu_out /*[count,2]*/, double *sigma_out /*[count]*/);
+npo_run *npo_mcmc_run_scalarnoise(int family, const double *mu0, const double *Lambda, double ig_alpha, double ig_beta, double dp_alpha,
+		const npo_options *opt, const double *X /*[N, 3 | 2]*/, int N);
+int npo_run_params_scalarnoise(const npo_run *r, int *K, double *mu /*[K,2]*/, double *sigma /*[K]*/, int64_t *counts, int cap);
+
 #ifdef __cplusplus
 }
 #endif

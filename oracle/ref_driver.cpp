@@ -13,9 +13,12 @@
  * One process = one run: the reference keeps process-wide static distributions (normal.h:61,
  * multivariatenormal.cpp:41) whose cached state is part of the random stream.
  *
- * usage: np_ref_run ALG T SEED_MAIN SEED_SHUFFLE request.bin result.bin [record_every_sweep]
+ * usage: np_ref_run ALG T SEED_MAIN SEED_SHUFFLE request.bin result.bin [record_every_sweep [FAMILY]]
  *   ALG: algorithm8 | jain_neal_split | triadic           (np_main.cpp:228-238)
- *   request.bin : int32 N, int32 D, double kappa, nu, alpha, mu0[D], Lambda[D*D] (row-major), X[N*D] (row-major)
+ *   FAMILY: clustering (default) | regression | angular   (np_main.cpp:196-205, `-c`)
+ *   request.bin : int32 N, int32 D, double kappa, nu, alpha, mu0[P], Lambda[P*P] (row-major), X[N*D] (row-major); P = D for
+ *                 clustering; for regression / angular P = 2 (np_main.cpp:324,358), the rows are what read_data builds
+ *                 (np_main.cpp:83-101: (1, a, b) resp. (a, b)) and kappa, nu carry the inverse-gamma's alpha, beta (np_main.cpp:360-361)
  *   result.bin  : int32 N, int32 T, int64 calls, double seconds_run, double seconds_update,
  *                 int32 K_final, int32 n_snap, int32 z_final[N], int32 z_maxlik[N],
  *                 int64 n_K, int32 K_after_call[n_K], int32 z_snap[n_snap][N],
@@ -43,6 +46,8 @@
 #include <statistics/dirichlet.h>
 #include <statistics/multivariatenormal.h>
 #include <statistics/normalinvwishart.h>
+#include <statistics/normalinvgamma.h>
+#include <statistics/scalarnoise_multivariatenormal.h>
 
 unsigned npo_ref_seed_value = 0; /* read by oracle/ref_seed_hook.h */
 
@@ -103,13 +108,19 @@ int main(int argc, char **argv) {
 	const unsigned seed_main = (unsigned)std::strtoul(argv[3], nullptr, 10);
 	npo_ref_seed_value = (unsigned)std::strtoul(argv[4], nullptr, 10);
 	const int record = argc > 7 ? std::atoi(argv[7]) : 0;
+	const std::string family = argc > 8 ? argv[8] : "clustering";
+	if (family != "clustering" && family != "regression" && family != "angular") {
+		std::fprintf(stderr, "Unknown family: %s\n", family.c_str());
+		return 1;
+	}
 
 	FILE *fin = std::fopen(argv[5], "rb");
 	if (!fin) { std::perror(argv[5]); return 2; }
 	int32_t N, D;
 	double kappa, nu, alpha;
 	rd(fin, &N, 1); rd(fin, &D, 1); rd(fin, &kappa, 1); rd(fin, &nu, 1); rd(fin, &alpha, 1);
-	std::vector<double> mu0(D), Lambda((size_t)D * D), X((size_t)N * D);
+	const int P = family == "clustering" ? D : 2;
+	std::vector<double> mu0(P), Lambda((size_t)P * P), X((size_t)N * D);
 	rd(fin, mu0.data(), mu0.size()); rd(fin, Lambda.data(), Lambda.size()); rd(fin, X.data(), X.size());
 	std::fclose(fin);
 
@@ -122,22 +133,38 @@ int main(int argc, char **argv) {
 	dataset_t dataset;
 	for (int i = 0; i < N; ++i) dataset.push_back(new data_t(X.begin() + (size_t)i * D, X.begin() + (size_t)(i + 1) * D));
 
-	/* np_main.cpp:330-334 */
-	Suffies_MultivariateNormal *suffies_mvn = new Suffies_MultivariateNormal(D);
-	suffies_mvn->mu.setZero();
-	suffies_mvn->sigma = Eigen::MatrixXd::Identity(D, D);
-	distribution_t *likelihood = new multivariate_normal_distribution(*suffies_mvn);
-
-	/* np_main.cpp:353-372 */
 	Suffies_Dirichlet suffies_dirichlet;
 	suffies_dirichlet.alpha = alpha;
-	Suffies_NormalInvWishart *niw = new Suffies_NormalInvWishart(D);
-	for (int d = 0; d < D; ++d) niw->mu(d) = mu0[d];
-	niw->kappa = kappa;
-	niw->nu = nu;
-	for (int r = 0; r < D; ++r)
-		for (int c = 0; c < D; ++c) niw->Lambda(r, c) = Lambda[(size_t)r * D + c];
-	distribution_t *prior = new normal_inverse_wishart_distribution(*niw);
+	distribution_t *likelihood, *prior;
+	if (family == "clustering") {
+		/* np_main.cpp:330-334 */
+		Suffies_MultivariateNormal *suffies_mvn = new Suffies_MultivariateNormal(D);
+		suffies_mvn->mu.setZero();
+		suffies_mvn->sigma = Eigen::MatrixXd::Identity(D, D);
+		likelihood = new multivariate_normal_distribution(*suffies_mvn);
+		/* np_main.cpp:353-372 */
+		Suffies_NormalInvWishart *niw = new Suffies_NormalInvWishart(D);
+		for (int d = 0; d < D; ++d) niw->mu(d) = mu0[d];
+		niw->kappa = kappa;
+		niw->nu = nu;
+		for (int r = 0; r < D; ++r)
+			for (int c = 0; c < D; ++c) niw->Lambda(r, c) = Lambda[(size_t)r * D + c];
+		prior = new normal_inverse_wishart_distribution(*niw);
+	} else {
+		/* np_main.cpp:322-328 */
+		Suffies_ScalarNoise_MultivariateNormal *suffies_sn = new Suffies_ScalarNoise_MultivariateNormal(2);
+		suffies_sn->mu.setZero();
+		suffies_sn->sigma = 1;
+		likelihood = new scalarnoise_multivariate_normal_distribution(*suffies_sn, family == "regression" ? regression_mode : angular_mode);
+		/* np_main.cpp:357-364 */
+		Suffies_NormalInvGamma *nig = new Suffies_NormalInvGamma(2);
+		for (int d = 0; d < 2; ++d) nig->mu(d) = mu0[d];
+		nig->alpha = kappa;
+		nig->beta = nu;
+		for (int r = 0; r < 2; ++r)
+			for (int c = 0; c < 2; ++c) nig->Lambda(r, c) = Lambda[(size_t)r * 2 + c];
+		prior = new normal_inverse_gamma_distribution(*nig);
+	}
 	dirichlet_process hyper(suffies_dirichlet, *prior);
 
 	InitClusters init_clusters(generator, hyper);           /* np_main.cpp:388 */

@@ -33,7 +33,9 @@ def write_request(path, X, prior):
     N, D = X.shape
     with open(path, "wb") as f:
         f.write(struct.pack("<ii", N, D))
-        f.write(struct.pack("<ddd", float(prior["kappa"]), float(prior["nu"]), float(prior["alpha"])))
+        # the scalar-noise families (regression / angular) send the inverse-gamma's (alpha, beta) in the kappa, nu fields
+        k, n = (prior["kappa"], prior["nu"]) if "kappa" in prior else (prior["nig_alpha"], prior["nig_beta"])
+        f.write(struct.pack("<ddd", float(k), float(n), float(prior["alpha"])))
         f.write(np.ascontiguousarray(prior["mu0"], dtype=np.float64).tobytes())
         f.write(np.ascontiguousarray(prior["Lambda"], dtype=np.float64).tobytes())
         f.write(X.tobytes())
@@ -56,18 +58,19 @@ def read_result(path):
                 z_maxlik=z_maxlik.copy(), K_after=K_after.copy(), z_snaps=snaps.copy())
 
 
-def command(algorithm, T, seed_main, seed_shuffle, request, result, record=False):
-    return [BINARY, ALGORITHMS[algorithm], str(T), str(seed_main), str(seed_shuffle), request, result, "1" if record else "0"]
+def command(algorithm, T, seed_main, seed_shuffle, request, result, record=False, family="clustering"):
+    return [BINARY, ALGORITHMS[algorithm], str(T), str(seed_main), str(seed_shuffle), request, result, "1" if record else "0", family]
 
 
-def run(X, prior, algorithm=8, T=1000, seed_main=1, seed_shuffle=2, record=False, timeout=None):
+def run(X, prior, algorithm=8, T=1000, seed_main=1, seed_shuffle=2, record=False, timeout=None, family="clustering"):
     """One run of the reference's MCMC::run (np_mcmc.cpp:48-175) in a fresh process (its static distributions are
-    process-wide state).  prior: dict(mu0, kappa, nu, Lambda, alpha)."""
+    process-wide state).  prior: dict(mu0, kappa, nu, Lambda, alpha); for family "regression" / "angular" (np_main.cpp -c):
+    dict(mu0[2], Lambda[2,2], nig_alpha, nig_beta, alpha) and X the rows read_data builds ((1, a, b) resp. (a, b))."""
     if not available():
         raise RuntimeError("oracle/_ref/np_ref_run is not built (make -C oracle _ref needs /root/reference)")
     with tempfile.TemporaryDirectory() as d:
         req, res = os.path.join(d, "req.bin"), os.path.join(d, "res.bin")
         write_request(req, X, prior)
-        subprocess.run(command(algorithm, T, seed_main, seed_shuffle, req, res, record), check=True,
+        subprocess.run(command(algorithm, T, seed_main, seed_shuffle, req, res, record, family), check=True,
                        stdout=subprocess.DEVNULL, timeout=timeout)
         return read_result(res)
