@@ -99,6 +99,25 @@ npb_status npb_dataset_destroy(npb_dataset *ds);
 npb_status npb_prior_set_niw(npb_ctx *ctx, int D, const double *mu0, double kappa, double nu, const double *Lambda,
 		double alpha, int flags);
 
+/* ---- the other two likelihood families of `-c` (np_main.cpp:196-205): scalar-noise normal likelihood + normal-inverse-gamma
+ * base measure.  Replaces scalarnoise_multivariate_normal_distribution::{init, prepare, probability, logprobability}
+ * (scalarnoise_multivariatenormal.cpp:16-47, 77-250) and normal_inverse_gamma_distribution::operator() (normalinvgamma.h:58-84,
+ * gamma.h:37-46); constants of np_main.cpp:322-328, 357-364: mu0 = (0, 0), alpha = 10, beta = 0.1, Lambda = 0.01 I.
+ * A cluster's theta = (mu [2], sigma).  Dataset rows are what read_data builds (np_main.cpp:83-101): (1, a, b) for regression
+ * (D = 3: residual b - mu . (1, a)), (a, b) for angular (D = 2: residual |d - (-sin(t) a + cos(t) b)| with (d, t) made canonical
+ * through abs(int), the reference's prepare(): SURVEY quirk list, Q12).  With such a prior bound, npb_chains_create draws the K0
+ * initial clusters from it, npb_chains_sweep(NPB_ALG8) runs k_sn_sweep (npb_scalarnoise.cu), npb_chains_get_params returns
+ * mu[k, 0..1] = (mu_0, mu_1) and Sigma[k, 0, 0] = sigma^2 (other entries 0); the split-merge samplers, Algorithm 2 and the
+ * parameter update are multivariate-normal only (NPB_E_UNSUPPORTED). */
+enum { NPB_FAMILY_MVN = 0, NPB_FAMILY_REGRESSION = 1, NPB_FAMILY_ANGULAR = 2 };
+npb_status npb_prior_set_nig(npb_ctx *ctx, int family, const double *mu0 /*[2]*/, const double *Lambda /*[2,2]*/, double ig_alpha,
+		double ig_beta, double alpha);
+/* out[r*K+k] = log p(X[rows[r]] | mu[k], sigma[k]) in double (rows == NULL: rows 0..n_rows-1) */
+npb_status npb_scalarnoise_logdensity_batch(npb_ctx *ctx, npb_dataset *ds, int family, const int64_t *rows, int64_t n_rows,
+		const double *mu /*[K,2]*/, const double *sigma /*[K]*/, int K, double *out);
+/* parity probe: `count` raw draws (mu_0, mu_1, sigma) of the base measure from chain `chain`'s generator; out [count, 3] */
+npb_status npb_chains_sample_base_nig(npb_chains *ch, int64_t chain, int count, float *out);
+
 /* ---- density: replaces multivariate_normal_distribution::{init, probability, logprobability} -----------
  * (multivariatenormal.cpp:16-35, 64-146).  out[r*K+k] = log N(X[rows[r]] | mu[k], Sigma[k]); rows == NULL
  * means rows 0..n_rows-1.  Sigma[k] is a general D x D matrix (row-major; the reference's known-answer test

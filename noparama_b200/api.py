@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnpb200.so")
 
 ALG8, ALG2, JAIN_NEAL, TRIADIC = 8, 2, 20, 30
+FAMILY_MVN, FAMILY_REGRESSION, FAMILY_ANGULAR = 0, 1, 2  # likelihood families of -c (np_main.cpp:196-205)
 ALG2_CONJUGATE = 22  # collapsed Gibbs with the NIW posterior predictive (BASELINE configs[3]; not in the reference)
 UPDATE_POSTERIOR_DRAW, UPDATE_POSTERIOR_MEAN = 1, 2
 BUGCOMPAT_DEGENERATE_IW, BUGCOMPAT_UNDERFLOW = 1, 2
@@ -26,6 +27,7 @@ E_UNSUPPORTED = -5
 EXPORTS = [
     "npb_ctx_create", "npb_ctx_destroy", "npb_ctx_stream", "npb_ctx_synchronize", "npb_status_str",
     "npb_ctx_last_error", "npb_dataset_upload", "npb_dataset_update", "npb_dataset_destroy", "npb_prior_set_niw",
+    "npb_prior_set_nig", "npb_scalarnoise_logdensity_batch", "npb_chains_sample_base_nig",
     "npb_logdensity_batch", "npb_logdensity_sum", "npb_chains_create", "npb_chains_destroy", "npb_chains_set_state",
     "npb_chains_sweep", "npb_chains_sweep_host", "npb_chain_update_alg8", "npb_replay_alg8",
     "npb_chains_get_assignments", "npb_chains_get_params", "npb_chains_metrics", "npb_cocluster",
@@ -245,6 +247,44 @@ class NormalInverseWishart:
                                              self.alpha, self.flags))
 
 
+class NormalInverseGamma:
+    """Suffies_NormalInvGamma + Suffies_Dirichlet (np_suffies.h:112-128; constants np_main.cpp:357-364): the base measure of the
+    scalar-noise families `-c regression` (family=REGRESSION, rows (1, a, b)) and `-c angular` (family=ANGULAR, rows (a, b))."""
+
+    def __init__(self, family, mu0=(0.0, 0.0), Lambda=((0.01, 0.0), (0.0, 0.01)), nig_alpha=10.0, nig_beta=0.1, alpha=1.0):
+        self.family = int(family)
+        self.mu0, self.Lambda = _f64(mu0), _f64(Lambda)
+        self.nig_alpha, self.nig_beta, self.alpha = float(nig_alpha), float(nig_beta), float(alpha)
+        self.D = 3 if self.family == FAMILY_REGRESSION else 2  # width of a data row
+
+    def bind(self, ctx):
+        ctx.check(ctx._lib.npb_prior_set_nig(ctx._h, self.family, _dp(self.mu0), _dp(self.Lambda), C.c_double(self.nig_alpha),
+                                             C.c_double(self.nig_beta), C.c_double(self.alpha)))
+
+
+class ScalarNoiseNormal:
+    """scalarnoise_multivariate_normal_distribution (statistics/scalarnoise_multivariatenormal.h) in regression or angular mode:
+    batched log-densities on the device."""
+
+    def __init__(self, ctx, dataset, family):
+        self.ctx, self.ds, self.family = ctx, dataset, int(family)
+
+    def logprobability(self, mu, sigma, rows=None):
+        """log p(X[rows] | mu[k], sigma[k]) -> [n_rows, K]  (scalarnoise_multivariatenormal.cpp:182-250)"""
+        mu, sigma = _f64(mu), _f64(sigma)
+        K = len(sigma)
+        assert mu.shape == (K, 2)
+        if rows is None:
+            n, rp = self.ds.N, None
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.int64)
+            n, rp = len(rows), rows.ctypes.data_as(C.POINTER(C.c_int64))
+        out = np.empty((n, K), dtype=np.float64)
+        self.ctx.check(self.ctx._lib.npb_scalarnoise_logdensity_batch(self.ctx._h, self.ds._h, self.family, rp, C.c_int64(n), _dp(mu),
+                                                                      _dp(sigma), K, _dp(out)))
+        return out
+
+
 class MultivariateNormal:
     """multivariate_normal_distribution (statistics/multivariatenormal.h): batched log-densities on the device."""
 
@@ -359,6 +399,12 @@ class Chains:
         out = np.empty((32, 32), dtype=np.float32)
         self.ctx.check(self.ctx._lib.npb_chains_probe_tile_logdensity(self._h, chain, _ip(items32),
                                                                        out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def sample_base_nig(self, chain, count):
+        """[count, 3] raw draws (mu_0, mu_1, sigma) of the normal-inverse-gamma base measure from `chain`'s generator"""
+        out = np.empty((count, 3), dtype=np.float32)
+        self.ctx.check(self.ctx._lib.npb_chains_sample_base_nig(self._h, C.c_int64(chain), count, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
     def set_option(self, name, value):

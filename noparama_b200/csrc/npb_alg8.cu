@@ -136,6 +136,10 @@ npb_status npb_launch_whiten(npb_dataset *ds) {
 
 npb_status npb_launch_chains_init(npb_chains *ch, int K0, const float *d_theta_given) {
 	npb_ctx *ctx = ch->ctx;
+	if (ctx->prior.family) {
+		if (d_theta_given) return npb_fail(ctx, NPB_E_UNSUPPORTED, "scalar-noise families: chains start from prior draws only");
+		return npb_launch_sn_init(ch, K0);
+	}
 	SweepArgs a = make_args(ch, 0);
 	const int warps = 4;
 	int64_t blocks = (ch->C + warps - 1) / warps;
@@ -245,6 +249,15 @@ npb_status npb_launch_alg8_sweep(npb_chains *ch, int n_sweeps) {
 		size_t cap = (64u << 20) / per_sweep;
 		ch->scan_cap = (int)(cap < 1 ? 1 : (cap > 1024 ? 1024 : cap));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->scan_order, per_sweep * ch->scan_cap));
+	}
+	if (ctx->prior.family) { // `-c regression` / `-c angular`: npb_scalarnoise.cu
+		for (int done = 0; done < n_sweeps;) {
+			const int n = (n_sweeps - done < ch->scan_cap) ? n_sweeps - done : ch->scan_cap;
+			npb_status s = npb_launch_sn_sweep(ch, n);
+			if (s != NPB_OK) return s;
+			done += n;
+		}
+		return NPB_OK;
 	}
 	const bool two_warp = ch->sw.two_warp;
 	if ((!two_warp || ch->D == 64) && ch->Kmax == 32 && ch->D >= 4 && !ch->aux_keys) {

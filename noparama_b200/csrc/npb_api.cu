@@ -203,6 +203,79 @@ npb_status npb_prior_set_niw(npb_ctx *ctx, int D, const double *mu0, double kapp
 	return NPB_OK;
 }
 
+// `-c regression` / `-c angular` (np_main.cpp:322-328, :357-364): scalar-noise likelihood, normal-inverse-gamma base measure
+npb_status npb_prior_set_nig(npb_ctx *ctx, int family, const double *mu0, const double *Lambda, double ig_alpha, double ig_beta, double alpha) {
+	if (!ctx || !mu0 || !Lambda || !(ig_alpha > 0) || !(ig_beta > 0) || !(alpha > 0)) return NPB_E_BAD_ARG;
+	if (family != NPB_FAMILY_REGRESSION && family != NPB_FAMILY_ANGULAR) return npb_fail(ctx, NPB_E_BAD_ARG, "family: NPB_FAMILY_REGRESSION | NPB_FAMILY_ANGULAR");
+	const double det = Lambda[0] * Lambda[3] - Lambda[1] * Lambda[2];
+	if (!(Lambda[0] > 0) || !(det > 0) || Lambda[1] != Lambda[2]) return npb_fail(ctx, NPB_E_NOT_POSITIVE, "Lambda is not symmetric positive definite");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+	PriorHost p;
+	p.family = family;
+	p.D = family == NPB_FAMILY_REGRESSION ? 3 : 2; // width of a data row: (1, a, b) | (a, b) (np_main.cpp:83-101)
+	p.kappa = p.nu = 1.0;
+	p.alpha = alpha;
+	p.ig_alpha = ig_alpha;
+	p.ig_beta = ig_beta;
+	p.mu0.assign(mu0, mu0 + 2);
+	p.Lambda.assign(Lambda, Lambda + 4);
+	p.set = true;
+	ctx->prior = p;
+	ctx->prior_epoch++;
+	return NPB_OK;
+}
+
+// [n_rows, K] log-densities (natural log) of dataset rows under K scalar-noise parameter sets (mu [K, 2], sigma [K]): the raw
+// parameters are brought into the slot layout on the host, the evaluation is k_logdensity's (scalarnoise_multivariatenormal.cpp:182-250)
+npb_status npb_scalarnoise_logdensity_batch(npb_ctx *ctx, npb_dataset *ds, int family, const int64_t *rows, int64_t n_rows, const double *mu,
+		const double *sigma, int K, double *out) {
+	if (!ctx || !ds || !mu || !sigma || !out || K <= 0 || n_rows <= 0) return NPB_E_BAD_ARG;
+	if (family != NPB_FAMILY_REGRESSION && family != NPB_FAMILY_ANGULAR) return NPB_E_BAD_ARG;
+	const int D = ds->D, TRI = npb_tri(D);
+	if (D != (family == NPB_FAMILY_REGRESSION ? 3 : 2)) return npb_fail(ctx, NPB_E_BAD_ARG, "rows are (1, a, b) for regression and (a, b) for angular");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	std::vector<double> h((size_t)K * (D + TRI + 1));
+	double *hm = h.data(), *hT = hm + (size_t)K * D, *hc = hT + (size_t)K * TRI;
+	for (int k = 0; k < K; ++k) {
+		if (!(sigma[k] > 0)) return npb_fail(ctx, NPB_E_NOT_POSITIVE, "sigma must be positive");
+		npb_sn_slot_from_raw(family, D, mu + 2 * (size_t)k, sigma[k], hm + (size_t)k * D, hT + (size_t)k * TRI, hc + k);
+	}
+	double *d = nullptr, *d_out = nullptr;
+	int64_t *d_rows = nullptr;
+	cudaError_t e = cudaMalloc((void **)&d, h.size() * sizeof(double));
+	if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (size_t)n_rows * K * sizeof(double));
+	if (e == cudaSuccess && rows) e = cudaMalloc((void **)&d_rows, (size_t)n_rows * sizeof(int64_t));
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess && rows) e = cudaMemcpyAsync(d_rows, rows, (size_t)n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+	npb_status s = NPB_OK;
+	if (e == cudaSuccess) s = npb_launch_logdensity(ctx, ds, d_rows, n_rows, K, d, d + (size_t)K * D, d + (size_t)K * (D + TRI), nullptr, nullptr, nullptr, 64, d_out);
+	if (e == cudaSuccess && s == NPB_OK) e = cudaMemcpyAsync(out, d_out, (size_t)n_rows * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d);
+	cudaFree(d_out);
+	cudaFree(d_rows);
+	if (e != cudaSuccess) return npb_fail_cuda(ctx, e, "npb_scalarnoise_logdensity_batch", __FILE__, __LINE__);
+	return s;
+}
+
+// count raw draws (mu_0, mu_1, sigma) from the normal-inverse-gamma base measure as the sweep kernel makes them (parity probe)
+npb_status npb_chains_sample_base_nig(npb_chains *ch, int64_t chain, int count, float *out) {
+	if (!ch || !out || count <= 0 || chain < 0 || chain >= ch->C) return NPB_E_BAD_ARG;
+	npb_ctx *ctx = ch->ctx;
+	if (!ctx->prior.family) return npb_fail(ctx, NPB_E_BAD_ARG, "the context's prior is not a normal-inverse-gamma one");
+	NPB_CUDA_OK(cudaSetDevice(ctx->device));
+	float *d = nullptr;
+	NPB_CUDA_OK(cudaMalloc((void **)&d, (size_t)count * 3 * sizeof(float)));
+	npb_status s = npb_launch_sn_sample_base(ch, (int)chain, count, d);
+	cudaError_t e = cudaSuccess;
+	if (s == NPB_OK) e = cudaMemcpyAsync(out, d, (size_t)count * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return npb_fail_cuda(ctx, e, "npb_chains_sample_base_nig", __FILE__, __LINE__);
+	return s;
+}
+
 // ---- density ------------------------------------------------------------------------------------------------
 struct ThetaStaging {
 	std::vector<double> T, c;
@@ -288,6 +361,7 @@ __global__ void k_best_init(double *best, int C);
 static npb_status ensure_whitened(npb_dataset *ds) {
 	// (npb_prior_set_niw may have been called with another dimension since the dataset was uploaded)
 	if (!ds->ctx->prior.set || ds->ctx->prior.D != ds->D) return npb_fail(ds->ctx, NPB_E_BAD_ARG, "the context's prior is not of the dataset's dimension");
+	if (ds->ctx->prior.family) return NPB_OK; // the scalar-noise kernels read the rows as they are
 	if (ds->whitened_epoch == ds->ctx->prior_epoch) return NPB_OK;
 	return npb_launch_whiten(ds);
 }
@@ -605,6 +679,8 @@ static npb_status sweep_common(npb_chains *ch, int sampler, int n_sweeps, int64_
 	}
 	s = ensure_whitened(ch->ds);
 	if (s != NPB_OK) return s;
+	if (ctx->prior.family && sampler != NPB_ALG8)
+		return npb_fail(ctx, NPB_E_UNSUPPORTED, "scalar-noise families (regression / angular): Algorithm 8 only on the device");
 	NPB_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (conjugate && n_sweeps > 0) {
 		s = npb_launch_alg2_conjugate(ch, n_sweeps); // keeps its own statistics in step with the assignments
@@ -716,6 +792,29 @@ static npb_status get_params_from(npb_chains *ch, const float *theta, const int 
 			if (slots) slots[k] = s;
 			if (counts) counts[k] = cnt[s];
 			const float *o = th.data() + (size_t)s * PS;
+			if (ctx->prior.family) {
+				// scalar-noise slot -> (mu_0, mu_1) in mu[k, 0..1] and sigma^2 in Sigma[k, 0, 0], everything else 0; the angular
+				// family reports the canonical (d, theta) its density uses (prepare(), scalarnoise_multivariatenormal.cpp:31-47)
+				const double g = ctx->prior.family == NPB_FAMILY_REGRESSION ? (double)o[D + 2] : hypot((double)o[D], (double)o[D + 1]);
+				if (mu) {
+					for (int d = 0; d < D; ++d) mu[(size_t)k * D + d] = 0.0;
+					if (ctx->prior.family == NPB_FAMILY_REGRESSION) {
+						mu[(size_t)k * D] = -(double)o[D] / g;
+						mu[(size_t)k * D + 1] = -(double)o[D + 1] / g;
+					} else {
+						mu[(size_t)k * D] = hypot((double)o[0], (double)o[1]);
+						double th_ = atan2((double)o[D] / g, -(double)o[D + 1] / g);
+						mu[(size_t)k * D + 1] = th_ < 0 ? th_ + 2.0 * M_PI : th_;
+					}
+				}
+				if (Sigma) {
+					for (int t = 0; t < D * D; ++t) Sigma[(size_t)k * D * D + t] = 0.0;
+					const double sg = NPB_HALF_LOG2E_SQRT / g;
+					Sigma[(size_t)k * D * D] = sg * sg;
+				}
+				k++;
+				continue;
+			}
 			if (mu) for (int d = 0; d < D; ++d) mu[(size_t)k * D + d] = o[d];
 			if (Sigma) {
 				for (int t = 0; t < TRI; ++t) T[t] = (double)o[D + t] / NPB_HALF_LOG2E_SQRT;

@@ -15,6 +15,9 @@ struct PriorHost {
 	std::vector<double> CT;  // C^T packed upper (A^-1 = C C^T)
 	std::vector<double> S;   // C^-T packed upper
 	double logdetA = 0;
+	// scalar-noise families (npb_prior_set_nig): family != 0, D = width of a data row, mu0 [2], Lambda [2, 2]
+	int family = 0;
+	double ig_alpha = 0, ig_beta = 0;
 };
 
 // NVTX range around every public entry point that launches device work (visible in Nsight Systems / ncu --nvtx; free when no
@@ -199,6 +202,11 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a);
 npb_status npb_launch_tc16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
 npb_status npb_launch_alg8_fused16(npb_chains *ch, const SweepArgs &a);
 npb_status npb_launch_scan_order(npb_chains *ch, int n_sweeps);
+// scalar-noise likelihood families (npb_scalarnoise.cu)
+npb_status npb_launch_sn_init(npb_chains *ch, int K0);
+npb_status npb_launch_sn_sweep(npb_chains *ch, int n_sweeps);
+npb_status npb_launch_sn_sample_base(npb_chains *ch, int chain, int count, float *d_out);
+void npb_sn_slot_from_raw(int family, int D, const double *mu, double sigma, double *mu_slot, double *T_packed, double *cst);
 npb_status npb_launch_alg2_conjugate(npb_chains *ch, int n_sweeps);
 npb_status npb_launch_alg2_probe(npb_chains *ch, int chain, const int32_t *d_items, int n_items, float *d_out);
 npb_status npb_launch_fused16_probe(npb_chains *ch, int chain, const int32_t *d_items, float *d_out);
