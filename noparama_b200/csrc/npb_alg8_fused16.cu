@@ -5,26 +5,31 @@
 // 128 bytes per reassignment, was written to HBM by one kernel and read back by the other -- 232 GB of DRAM traffic per sweep
 // at the headline shape against 5 GB algorithmic, and the race's 30 ms per sweep were a table reader's.)
 //
-// CTA = one SM, persistent over units of TWO chains (their B operand images, 128 KB, stay in shared memory for the block;
-// an A tile of 128 steps streamed in by cp.async.bulk is used for both).  Warp roles:
-//   warp 8        issues tcgen05.mma kind::f16, M = 128 steps x N = 256 (16 slots x 16 rows) x K = 64 (FP16x3 split + folded
+// CTA = one SM (576 threads, 96 registers, 224 KB of shared memory, all 512 TMEM columns), persistent over units of TWO chains
+// (their B operand images, 128 KB, stay in shared memory for the block; an A tile of 128 steps streamed in by cp.async.bulk is
+// used for both).  Warp roles:
+//   warp 16       issues tcgen05.mma kind::f16, M = 128 steps x N = 256 (16 slots x 16 rows) x K = 64 (FP16x3 split + folded
 //                 offsets, see k_pre_aimg16 / k_pre_bimg16), two TMEM accumulators of 256 columns;
-//   warp 9        bulk-copy producer (B images of the unit, A tiles through a two-stage ring);
-//   warps 0-7     EPILOGUE: tcgen05.ld of an accumulator (thread = step, 8 slots each), c2 - |y|^2 per (step, slot), written
-//                 to a [slot][step] tile in SHARED memory (16 KB per (chain, 128 steps), three tiles in rotation);
-//   warps 10-17   DECISION, four per chain of the unit, lane = step of a 32-step sub-tile:
-//                 (1) speculative pass, all four sub-tiles in parallel: with the member counts as they stand, the noiseless key
-//                     d_k + log2 n_k of every slot, the exact key (counter-hash race noise, g_noise) of the best, and of every
-//                     slot the capped noise cannot rule out; the winner w, its key and an upper bound r of every other key;
-//                 (2) validation, in step order (a token goes round the chain's four warps): steps that stay are final as long
-//                     as no earlier step moved; the first step that moves is applied (retract, assign or birth:
-//                     membertrix.cpp:147-233, np_neal_algorithm8.cpp:136-157), and the LATER steps of the sub-tile re-evaluate
-//                     only the two slots whose counts changed against their (w, key, r) -- the argmax of independent keys can
-//                     only change through those two -- falling back to a full evaluation of a step when that does not settle
-//                     it (key of the winner dropped to the bound).  A sub-tile whose speculation predates a change of its
-//                     chain's counts (another sub-tile moved an item meanwhile) repeats pass (1) when it gets the token.
+//   warp 17       bulk-copy producer (B images of the unit, A tiles through a two-stage ring);
+//   warps 0-7     EPILOGUE: tcgen05.ld of an accumulator (thread = step, 8 slots each, two 32-column loads per wait), packed
+//                 FP32 (FFMA2) sum of the 16 squares, c2 - dsc^2 |y|^2 per (step, slot), one 16-byte store per 4 slots into a
+//                 [step][36] row of a density tile in SHARED memory (18 KB per (chain, 128 steps), three tiles in rotation);
+//   warps 8-15    DECISION, four per chain of the unit, lane = step of a 32-step sub-tile:
+//                 (1) count-independent pass, all four sub-tiles in parallel: the lane reads its row (32 densities, kept in
+//                     registers), finds the best density and the CONTENDERS -- slots within F_WINDOW = 32 log2 units of it:
+//                     the race noise lies in [-6, 20] (g_noise) and log2 n_k in [0, 17], so no other slot can win whatever the
+//                     counts become -- and caches up to three of them as base = d_k + noise_k (the noise of a sole contender is
+//                     drawn lazily), plus a bound for the rest; the item's old slot, the largest auxiliary bound of the 32-step
+//                     group (k_aux_bound) come in through a three-stage cp.async ring;
+//                 (2) decision, in step order (a token goes round the chain's four warps): with the counts as they stand a step
+//                     compares base_k + log2 n_k of its cached contenders (own slot first: it wins next to always) against the
+//                     bound of everything else and the group's auxiliary bound; only when that does not settle it is the row
+//                     evaluated in full (all 32 keys, the exact auxiliary key by f_aux_exact).  A step that stays changes
+//                     nothing, so the token is handed on before any bookkeeping; a move is applied (retract, assign or birth:
+//                     membertrix.cpp:147-233, np_neal_algorithm8.cpp:136-157), bumps the chain's version and later steps simply
+//                     read the new counts -- their caches do not depend on counts.
 //                 Every key is evaluated with the same operations in the same order wherever it is evaluated, so the result
-//                 is the sequential sampler's, bit for bit, with or without the speculation (p.spec = 0 evaluates every step
+//                 is the sequential sampler's, bit for bit, with or without the short cuts (p.spec = 0 evaluates every step
 //                 in full, in order; tests/test_gpu_fused16.py compares the two and the round-1 kernel pair).
 // A birth writes theta' to the slot table, marks the slot's operand image dirty (rebuilt by k_pre_bimg16 before the next
 // block) and from then on the decision warps replace that slot's column of every tile of the block by CUDA-core densities.

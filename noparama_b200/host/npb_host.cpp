@@ -203,7 +203,13 @@ void MCMC::run(dataset_t &dataset, int T, bool per_item_seam, UpdateClusters *up
 	const Suffies_NormalInvWishart &niw = hyper_.getSuffies();
 	if (!trix_) {
 		trix_ = new membertrix(dev_, dataset, niw.D);
-		dev_.check(npb_prior_set_niw(dev_.ctx(), niw.D, niw.mu.data(), niw.kappa, niw.nu, niw.Lambda.data(), hyper_.alpha(), NPB_BUGCOMPAT_DEFAULT));
+		if (hyper_.mode() == clustering_mode) {
+			dev_.check(npb_prior_set_niw(dev_.ctx(), niw.D, niw.mu.data(), niw.kappa, niw.nu, niw.Lambda.data(), hyper_.alpha(), NPB_BUGCOMPAT_DEFAULT));
+		} else { // np_main.cpp:322-328, 357-364
+			const Suffies_NormalInvGamma &nig = hyper_.getSuffiesNIG();
+			dev_.check(npb_prior_set_nig(dev_.ctx(), hyper_.mode() == regression_mode ? NPB_FAMILY_REGRESSION : NPB_FAMILY_ANGULAR, nig.mu.data(),
+					nig.Lambda.data(), nig.alpha, nig.beta, hyper_.alpha()));
+		}
 		// np_mcmc.cpp:49-91: K0 prior clusters, uniform assignment, empty clusters dropped
 		dev_.check(npb_chains_create(dev_.ctx(), trix_->dataset_handle(), chains_, Kmax_, m_aux_, K0_, seed_, &trix_->chains));
 	}

@@ -43,6 +43,16 @@ struct Suffies_MultivariateNormal {
 struct Suffies_Dirichlet {
 	double alpha = 1.0;
 };
+// include/np_suffies.h:112-128: the base measure of `-c regression` / `-c angular` (constants np_main.cpp:357-364)
+struct Suffies_NormalInvGamma {
+	int D;
+	std::vector<double> mu;     // [2]
+	double alpha, beta;
+	std::vector<double> Lambda; // [2,2] row-major
+	explicit Suffies_NormalInvGamma(int d = 2) : D(d), mu(d, 0.0), alpha(10.0), beta(0.1), Lambda((size_t)d * d, 0.0) {}
+};
+// include/statistics/scalarnoise_multivariatenormal.h:14
+enum representation_mode_t { clustering_mode, regression_mode, angular_mode, points3d_mode };
 
 struct npb_error : std::runtime_error {
 	npb_status status;
@@ -65,11 +75,18 @@ private:
 class dirichlet_process {
 public:
 	dirichlet_process(const Suffies_Dirichlet &d, const Suffies_NormalInvWishart &niw) : alpha_(d.alpha), niw_(niw) {}
-	const Suffies_NormalInvWishart &getSuffies() const { return niw_; }
+	// scalar-noise likelihood (regression_mode: rows (1, a, b); angular_mode: rows (a, b)) with a normal-inverse-gamma base measure
+	dirichlet_process(const Suffies_Dirichlet &d, const Suffies_NormalInvGamma &nig, representation_mode_t mode)
+		: alpha_(d.alpha), niw_(mode == regression_mode ? 3 : 2), nig_(nig), mode_(mode) {}
+	const Suffies_NormalInvWishart &getSuffies() const { return niw_; } // (niw.D = width of a data row in either case)
+	const Suffies_NormalInvGamma &getSuffiesNIG() const { return nig_; }
+	representation_mode_t mode() const { return mode_; }
 	double alpha() const { return alpha_; }
 private:
 	double alpha_;
 	Suffies_NormalInvWishart niw_;
+	Suffies_NormalInvGamma nig_;
+	representation_mode_t mode_ = clustering_mode;
 };
 
 // The membership state (include/membertrix.h:52-314) of the device chains.  Cluster ids are device slot ids: stable,

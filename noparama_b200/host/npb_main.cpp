@@ -1,11 +1,11 @@
 // npb_main.cpp -- the reference's command line (src/np_main.cpp:187-267) on top of the device path:
-//   noparama_b200 -d <datafile> -a <algorithm8|jain_neal_split|triadic> -T <sweeps> -c clustering [--chains C] [--gpus G] [--seed S] [--kmax K] [--seam] [--fix-q1]
+//   noparama_b200 -d <datafile> -a <algorithm8|jain_neal_split|triadic> -T <sweeps> -c clustering|regression|angular [--chains C] [--gpus G] [--seed S] [--kmax K] [--seam] [--fix-q1]
 // --gpus G  the chains are split over G devices of this node, one host thread and one object graph per device (chains are
 //     independent: no exchange during the run); the scores of all chains are gathered at the end
 // -d  text file, one item per line: D coordinates then the ground-truth label (the reference reads exactly 2 + 1
 //     columns, np_main.cpp:93-101; here D = columns - 1 <= 3 for the register kernel, 4/8/16 for the tile kernel)
 // -a  algorithm8 | jain_neal_split | triadic (np_main.cpp:228-238) | algorithm2 (commented out there, :222-227)
-// -T  sweeps (default 2000, np_main.cpp:242)    -c  clustering only (regression/angular/points3d are out of scope)
+// -T  sweeps (default 2000, np_main.cpp:242)    -c  clustering | regression | angular (points3d is out of scope)
 // Prior and constants as hard-wired in the reference: alpha = 1, NIW{mu = 6, kappa = 1/500, nu = D + 2, Lambda = 0.01 I}
 // (np_main.cpp:164,367-371), K0 = 20, M = 3.  No 200-row subsampling (np_main.cpp:166-167): every row is used.
 #include "npb_host.h"
@@ -26,7 +26,7 @@
 using namespace npb;
 
 static void usage() {
-	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|algorithm2|jain_neal_split|triadic -T sweeps -c clustering [--chains C] [--gpus G] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR] [--selftest-membertrix]\n";
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|algorithm2|jain_neal_split|triadic -T sweeps -c clustering|regression|angular [--chains C] [--gpus G] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR] [--selftest-membertrix]\n";
 }
 
 // test/test_membertrix.cpp (the reference's unit test of the state class) through the host mutators over the DEVICE state:
@@ -115,7 +115,12 @@ int main(int argc, char **argv) {
 		else { std::cerr << "unknown option " << a << std::endl; usage(); return 1; }
 	}
 	if (datafile.empty()) { usage(); return 1; }
-	if (config != "clustering") { std::cerr << "Unknown likelihood (only -c clustering is on the device path)" << std::endl; return 107; }
+	if (config != "clustering" && config != "regression" && config != "angular") { std::cerr << "Unknown likelihood" << std::endl; return 107; } // np_main.cpp:196-205, exit code :349
+	const representation_mode_t mode = config == "regression" ? regression_mode : (config == "angular" ? angular_mode : clustering_mode);
+	if (mode != clustering_mode && algorithm != "algorithm8") {
+		std::cerr << "-c " << config << " runs Algorithm 8 on the device (the split-merge samplers are multivariate-normal only)" << std::endl;
+		return 1;
+	}
 	if (algorithm != "algorithm8" && algorithm != "algorithm2" && algorithm != "jain_neal_split" && algorithm != "triadic") { // np_main.cpp:222-238
 		std::cerr << "Unknown algorithm: " << algorithm << std::endl;
 		return 1;
@@ -138,8 +143,11 @@ int main(int argc, char **argv) {
 		if ((int)row.size() != D + 1 || D < 1) { std::cerr << "ragged line in " << datafile << std::endl; return 7; }
 		ground_truth.push_back((int)row.back());
 		row.pop_back();
+		if (mode == regression_mode) row.insert(row.begin(), 1.0); // np_main.cpp:83-92: prepend the constant
 		dataset.push_back(new data_t(row));
 	}
+	if (mode != clustering_mode && D != 2) { std::cerr << "-c " << config << " expects lines \"a b label\" (np_main.cpp:76-101)" << std::endl; return 7; }
+	if (mode == regression_mode) D = 3;
 	std::cout << "Read " << dataset.size() << " items of dimension " << D << std::endl;
 
 	// one device: its own context, object graph and share of the chains
@@ -151,7 +159,9 @@ int main(int argc, char **argv) {
 			for (int d = 0; d < D; ++d) { niw.mu[d] = 6.0; niw.Lambda[(size_t)d * D + d] = 0.01; }
 			niw.kappa = 1.0 / 500;
 			niw.nu = D + 2.0;
-			dirichlet_process hyper(sd, niw);
+			Suffies_NormalInvGamma nig(2); // np_main.cpp:357-364
+			nig.Lambda[0] = nig.Lambda[3] = 0.01;
+			dirichlet_process hyper = mode == clustering_mode ? dirichlet_process(sd, niw) : dirichlet_process(sd, nig, mode);
 			// np_main.cpp:424-459
 			NealAlgorithm8 alg8(dev, hyper);
 			JainNealAlgorithm jain_neal(dev, hyper);

@@ -31,7 +31,10 @@ def test_cli_usage_and_refusals(tmp_path):
     data = tmp_path / "twogaussians.data"
     write_data(str(data))
     # the reference exits 107 on an unknown likelihood (np_main.cpp:346,385) and 1 on an unknown algorithm (:236)
-    assert subprocess.run([CLI, "-d", str(data), "-c", "regression"], capture_output=True).returncode == 107
+    assert subprocess.run([CLI, "-d", str(data), "-c", "points3d"], capture_output=True).returncode == 107
+    # the scalar-noise families run Algorithm 8 only on the device
+    r = subprocess.run([CLI, "-d", str(data), "-c", "regression", "-a", "triadic"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Algorithm 8" in r.stderr
     r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm9"], capture_output=True, text=True)
     assert r.returncode == 1 and "Unknown algorithm" in r.stderr
     assert subprocess.run([CLI, "-d", str(tmp_path / "missing")], capture_output=True).returncode == 7
@@ -171,3 +174,20 @@ def test_cli_gpus_flag_shards_chains(tmp_path):
     r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "5", "-c", "clustering", "--chains", "2", "--gpus", "4"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "--gpus" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", ["regression", "angular"])
+def test_cli_runs_the_scalar_noise_families(tmp_path, config):
+    """`-c regression` / `-c angular` (np_main.cpp:196-205): lines "a b label", two lines to find"""
+    ensure_built()
+    X, y = (syn.regression_lines(300, 2, 4) if config == "regression" else syn.angular_lines(300, 2, 4))
+    data = tmp_path / "lines.data"
+    with open(str(data), "w") as f:
+        for row, lab in zip(X, y):
+            f.write("%.9f %.9f %d\n" % (row[-2], row[-1], lab))
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "200", "-c", config, "--chains", "64", "--kmax", "64", "--seed", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mean_pur = float(re.search(r"chains: purity ([0-9.]+)", r.stdout).group(1))
+    assert mean_pur > 0.8, r.stdout
