@@ -559,8 +559,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 						const int zo = __shfl_sync(0xffffffffu, zold, jn);
 						if (__shfl_sync(0xffffffffu, (int)unsafe, jn)) {
 							// full evaluation of step jn: lane = slot (the sequential sampler's step)
-							const uint32_t auxj = __shfl_sync(0xffffffffu, aux_of(), jn);
-							const float akj = __uint_as_float(auxj);
 							const float lgx = (lane == zo) ? lg1_t[lane] : lg_t[lane];
 							float dj = 0.0f; // d[lane] of step jn: its row sits in lane jn's registers
 #pragma unroll
@@ -574,7 +572,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 								if ((bmk >> lane) & 1u) dj = g_stream_density<HD>(thc + (size_t)lane * HPS, a.X + (size_t)itj * HD);
 							}
 							const float key = lgx > -INFINITY ? (dj + g_noise(T, (uint32_t)jn, (uint32_t)lane)) + lgx : -INFINITY;
-							const float top = fmaxf(redux_max_f32(key), akj);
+							// the step's own auxiliary key only if the group's bound does not already lose to the best slot (akmax is the
+							// same for the 32 steps of the sub-tile, so the branch is uniform); slots win ties
+							const float kmax = redux_max_f32(key);
+							uint32_t auxj = 0xff800000u;
+							if (!(kmax > akmax)) auxj = __shfl_sync(0xffffffffu, aux_of(), jn);
+							const float akj = __uint_as_float(auxj);
+							const float top = fmaxf(kmax, akj);
 							const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
 							const int ws = bal ? __ffs(bal) - 1 : 32 + (int)(auxj & 3u);
 							if (lane == jn) {
