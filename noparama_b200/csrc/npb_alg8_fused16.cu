@@ -719,15 +719,13 @@ npb_status npb_tc16_pre_block(npb_chains *ch, const int32_t *d_order, int nsteps
 
 static npb_status f_launch(npb_chains *ch, const GemmArgs &g, const PreArgs &p, int race) {
 	npb_ctx *ctx = ch->ctx;
-	static bool attr_set = false;
-	if (!attr_set) {
+	if (!ctx->fused_attr_set) { // (a function attribute is per device: one process may drive several, noparama_b200 --gpus G)
 		NPB_CUDA_OK(cudaFuncSetAttribute(k_sweep_tc16<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
 		NPB_CUDA_OK(cudaFuncSetAttribute(k_sweep_tc16<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
 		NPB_CUDA_OK(cudaFuncSetAttribute(k_sweep_tc16<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-		attr_set = true;
+		ctx->fused_attr_set = true;
 	}
-	int n_sm = 0;
-	NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+	const int n_sm = ctx->n_sm;
 	const int n_units = (g.C + 1) / 2;
 	const int grid = n_units < n_sm ? n_units : n_sm;
 	if (!race) k_sweep_tc16<1, true><<<grid, F_THREADS, F_SMEM, ctx->stream>>>(g, p);

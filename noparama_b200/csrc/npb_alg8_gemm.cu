@@ -677,8 +677,7 @@ static npb_status g_launch_block(npb_chains *ch, const int32_t *d_order, int nst
 	}
 	g.C = C;
 	if (!do_density && !cons) return NPB_OK;
-	static int n_sm = 0;
-	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+	const int n_sm = ctx->n_sm;
 	const int n_units = C * (32 / G_NS);
 	const int grid = n_units < n_sm ? n_units : n_sm;
 	PreArgs p;
@@ -1123,8 +1122,7 @@ static npb_status h_density_block(npb_chains *ch, const int32_t *d_order, int ns
 	g.C = C;
 	g.ntiles = ntiles;
 	g.BS = ch->g_bs + 32;
-	static int n_sm = 0;
-	if (!n_sm) NPB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+	const int n_sm = ctx->n_sm;
 	const int nh = ch->sw.d16_nh;
 	const int n_units = (C * 2 + nh - 1) / nh;
 	const int grid = n_units < n_sm ? n_units : n_sm;

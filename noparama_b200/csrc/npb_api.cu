@@ -69,6 +69,10 @@ npb_status npb_ctx_create(int device, npb_ctx **out) {
 		delete ctx;
 		return NPB_E_CUDA;
 	}
+	if (cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sm <= 0) {
+		npb_ctx_destroy(ctx);
+		return NPB_E_CUDA;
+	}
 	*out = ctx;
 	return NPB_OK;
 }

@@ -34,6 +34,8 @@ struct npb_ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	char err[512] = {0};
+	int n_sm = 0;               // multiprocessors of this context's device (grid size of the persistent kernels)
+	bool fused_attr_set = false; // per device: the shared-memory opt-in of k_sweep_tc16 has been made on this context's device
 	PriorHost prior;
 	float *d_CT2 = nullptr, *d_S = nullptr; // device copies of the packed prior factors
 	uint64_t prior_epoch = 0;               // bumped by npb_prior_set_niw; datasets re-whiten lazily

@@ -174,6 +174,18 @@ def test_cli_gpus_flag_shards_chains(tmp_path):
     r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm8", "-T", "5", "-c", "clustering", "--chains", "2", "--gpus", "4"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "--gpus" in r.stderr
+    # 16-D, Kmax = 32: the tcgen05 kernels (their shared-memory opt-in is per device) on every device of the process
+    X, y = syn.gmm(1500, 16, 4, 12)
+    d16 = tmp_path / "d16.data"
+    with open(str(d16), "w") as f:
+        for row, lab in zip(X, y):
+            f.write(" ".join("%.9f" % v for v in row) + " %d\n" % lab)
+    for g in (1, 2):
+        if g > n_dev:
+            continue
+        r = subprocess.run([CLI, "-d", str(d16), "-a", "algorithm8", "-T", "6", "-c", "clustering", "--chains", "12", "--kmax", "32",
+                            "--gpus", str(g)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
 
 
 @pytest.mark.gpu
