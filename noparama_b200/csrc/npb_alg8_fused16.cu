@@ -11,7 +11,7 @@
 //   warp 16       issues tcgen05.mma kind::f16, M = 128 steps x N = 256 (16 slots x 16 rows) x K = 64 (FP16x3 split + folded
 //                 offsets, see k_pre_aimg16 / k_pre_bimg16), two TMEM accumulators of 256 columns;
 //   warp 17       bulk-copy producer (B images of the unit, A tiles through a two-stage ring);
-//   warps 0-7     EPILOGUE: tcgen05.ld of an accumulator (thread = step, 8 slots each, two 32-column loads per wait), packed
+//   warps 0-7     EPILOGUE, two groups of four, one per accumulator: tcgen05.ld (thread = step, 16 slots, two 32-column loads per wait), packed
 //                 FP32 (FFMA2) sum of the 16 squares, c2 - dsc^2 |y|^2 per (step, slot), one 16-byte store per 4 slots into a
 //                 [step][36] row of a density tile in SHARED memory (18 KB per (chain, 128 steps), three tiles in rotation);
 //   warps 8-15    DECISION, four per chain of the unit, lane = step of a 32-step sub-tile:
@@ -124,7 +124,7 @@ __device__ __forceinline__ void f_density2(const float (&v)[32], const float *ec
 // One epilogue thread's share of an accumulator: 128 columns = 8 slots of its step, two tcgen05.ld of 32 columns per wait (a
 // staggered order -- one load in flight while the previous one is reduced -- measured 9 % slower); the accumulator goes back to
 // the MMA warp as soon as the last columns have landed.
-template <bool PROBE>
+template <bool PROBE, bool ARRIVE = true>
 __device__ __forceinline__ void f_epilogue_half(uint32_t taddr, const float2 *cd, float *drow, float *Lrow, uint32_t bar_t_empty) {
 	float o[8];
 #pragma unroll
@@ -133,7 +133,7 @@ __device__ __forceinline__ void f_epilogue_half(uint32_t taddr, const float2 *cd
 		g_tmem_ld32_nowait(taddr + pp * 64u, v0);
 		g_tmem_ld32_nowait(taddr + pp * 64u + 32u, v1);
 		g_tmem_wait_ld(v0, v1);
-		if (pp == 1) { // the accumulator is in registers: hand the buffer back before the arithmetic
+		if (ARRIVE && pp == 1) { // the accumulator is in registers: hand the buffer back before the arithmetic
 			g_tc_fence_before();
 			g_mbar_arrive(bar_t_empty);
 		}
@@ -154,7 +154,7 @@ __device__ __noinline__ void f_epilogue_half_unfolded(uint32_t taddr, const floa
 	for (int pr = 0; pr < 4; ++pr) {
 		float v[32], o0, o1;
 		g_tmem_ld32(taddr + 32u * pr, v);
-		if (pr == 3) {
+		if (pr == 3 && bar_t_empty) { // (0: the caller's second call hands the accumulator back)
 			g_tc_fence_before();
 			g_mbar_arrive(bar_t_empty);
 		}
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		}
 		for (int b = 0; b < 2; ++b) {
 			g_mbar_init(bars + 8 * (FB_T_FULL + b), 1);
-			g_mbar_init(bars + 8 * (FB_T_EMPTY + b), F_EW * 32);
+			g_mbar_init(bars + 8 * (FB_T_EMPTY + b), F_EW * 16);
 		}
 		for (int b = 0; b < F_DTBUFS; ++b) {
 			g_mbar_init(bars + 8 * (FB_DT_FULL + b), F_EW);
@@ -275,7 +275,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 		}
 		__syncwarp();
 	} else if (warp < F_EW) {
-		// ===================== epilogue: thread = step of the tile, 8 slots of the accumulator =====================
+		// ===================== epilogue: thread = step of the tile =====================
+		// Two groups of four warps, group eg bound to TMEM accumulator eg (= half-chain eg of every chain tile, 16 slots): the two
+		// epilogue warps of a scheduler work on different accumulators, out of phase, instead of waiting for the same loads and
+		// then competing for the same issue slots (all eight on one accumulator, 8 slots each: 64.4 against 62.4 ms per sweep)
 		const int wq = warp & 3, eg = warp >> 2;
 		const int row = wq * 32 + lane;
 		uint32_t acc_it = 0, ct = 0;
@@ -298,21 +301,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_sweep_tc16(const GemmArgs g, c
 			for (int t = 0; t < g.ntiles; ++t) {
 				for (int cc = 0; cc < ncc; ++cc, ++ct) {
 					const uint32_t dbuf = ct % F_DTBUFS, dk = ct / F_DTBUFS;
-					float *drow = Dt + dbuf * F_DT_FLOATS + row * F_DTS + eg * 8;
 					if (race) { // its previous tenant has been read by the decision warps
 						if (p.flags & 512) g_mbar_wait_sleep(bars + 8 * (FB_DT_FREE + dbuf), (dk & 1u) ^ 1u, 100);
 						else g_mbar_wait(bars + 8 * (FB_DT_FREE + dbuf), (dk & 1u) ^ 1u);
 					}
-#pragma unroll 1
-					for (int h = 0; h < 2; ++h, ++acc_it) {
-						const int hf = cc * 2 + h;
-						const uint32_t buf = acc_it & 1u;
-						g_mbar_wait(bars + 8 * (FB_T_FULL + buf), (acc_it >> 1) & 1u);
+					{
+						// group eg takes accumulator eg of the chain tile: all 16 slots of half-chain eg for this warp's 32 steps
+						const int h = eg, hf = cc * 2 + h;
+						const uint32_t ai = acc_it + (uint32_t)h, buf = ai & 1u;
+						acc_it += 2;
+						g_mbar_wait(bars + 8 * (FB_T_FULL + buf), (ai >> 1) & 1u);
 						g_tc_fence_after();
-						const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u + eg * 128;
-						float *Lrow = PROBE ? g.L + ((size_t)(2 * u + cc) * g.BS + (size_t)t * G_M + row) * 32 + h * H_NS + eg * 8 : nullptr;
-						if ((folded_mask >> hf) & 1u) f_epilogue_half<PROBE>(taddr, cd2 + hf * H_NS + eg * 8, drow + h * H_NS, Lrow, bars + 8 * (FB_T_EMPTY + buf));
-						else f_epilogue_half_unfolded<PROBE>(taddr, econst + (hf * H_NS + eg * 8) * H_CONST, drow + h * H_NS, Lrow, bars + 8 * (FB_T_EMPTY + buf));
+						const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + buf * 256u;
+						float *dr = Dt + dbuf * F_DT_FLOATS + row * F_DTS + h * H_NS;
+						float *Lrow = PROBE ? g.L + ((size_t)(2 * u + cc) * g.BS + (size_t)t * G_M + row) * 32 + h * H_NS : nullptr;
+						if ((folded_mask >> hf) & 1u) {
+							f_epilogue_half<PROBE, false>(taddr, cd2 + hf * H_NS, dr, Lrow, 0u);
+							f_epilogue_half<PROBE, true>(taddr + 128u, cd2 + hf * H_NS + 8, dr + 8, PROBE ? Lrow + 8 : nullptr, bars + 8 * (FB_T_EMPTY + buf));
+						} else {
+							f_epilogue_half_unfolded<PROBE>(taddr, econst + (hf * H_NS) * H_CONST, dr, Lrow, 0u);
+							f_epilogue_half_unfolded<PROBE>(taddr + 128u, econst + (hf * H_NS + 8) * H_CONST, dr + 8, PROBE ? Lrow + 8 : nullptr, bars + 8 * (FB_T_EMPTY + buf));
+						}
 					}
 					if (race) {
 						__syncwarp();

@@ -120,3 +120,38 @@ def test_law_d16_paths(npb, ctx, oracle, env, path, spec, aux):
 def test_law_d64_fused_race(npb, ctx, oracle, env, spec):
     env["NPB_D64_SPEC"] = spec
     assert_law(law_check(npb, ctx, oracle, 64, 32, 1, 1 << 14, 32, 6464, sampler=npb.ALG2), "D=64 k_density_tc spec=%s" % spec)
+
+
+@pytest.mark.parametrize("D", [2, 16])
+def test_base_measure_draws_follow_the_reference_law(npb, ctx, oracle, D):
+    """a5: the device's draws from the base measure (npb_draw_theta: the K0 initial clusters of every chain) against the
+    oracle's restatement of dirichlet_process::sample_base (dirichlet.h:91-93 -> normalinvwishart.h:44-64 -> invwishart.h:34-46,
+    bug-compatible Q2: Sigma = v^2 L^T L with one scalar v ~ N(D, nu)): two-sample KS on the scale v^2 = Sigma_00 / Lambda_00, on
+    the standardised mean coordinates, and the exact structure Sigma = s Lambda of the degenerate inverse-Wishart draw."""
+    from scipy import stats as sps
+    pr = syn.reference_prior(D)
+    X, _ = syn.gmm(400, D, 2, 5)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**pr).bind(ctx)
+    ch = npb.Chains(ctx, ds, 256, Kmax=32, K0=20, seed=31)
+    mus, sig = [], []
+    for c in range(256):
+        _, _, mu, Sigma = ch.params(c)  # the clusters that kept a member: all 20 at N = 400 with overwhelming probability
+        mus.append(mu)
+        sig.append(Sigma)
+    mu, Sigma = np.concatenate(mus), np.concatenate(sig)
+    assert len(mu) > 4000
+    s = Sigma[:, 0, 0] / pr["Lambda"][0, 0]
+    assert np.allclose(Sigma, s[:, None, None] * pr["Lambda"][None], rtol=2e-4, atol=1e-9)
+    omu, oSigma = oracle.sample_base(oracle.make_prior(**pr), 77, 6000)
+    os_ = oSigma[:, 0, 0] / pr["Lambda"][0, 0]
+    p = sps.ks_2samp(s, os_).pvalue
+    assert p > 1e-3, ("scale", p, s.mean(), os_.mean())
+    # mu | Sigma ~ N(mu0, Sigma / kappa): standardised coordinates are N(0, 1) on both sides
+    z = (mu - pr["mu0"]) / np.sqrt(Sigma[:, 0, 0] / pr["kappa"])[:, None]
+    oz = (omu - pr["mu0"]) / np.sqrt(oSigma[:, 0, 0] / pr["kappa"])[:, None]
+    for d in (0, D - 1):
+        assert sps.ks_2samp(z[:, d], oz[:, d]).pvalue > 1e-3, d
+    assert sps.kstest(z.ravel(), "norm").pvalue > 1e-3
+    ch.close()
+    ds.close()
