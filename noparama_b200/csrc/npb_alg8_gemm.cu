@@ -177,7 +177,11 @@ __device__ __forceinline__ uint32_t g_aux_exact(const Philox &ph, const PriorDev
 
 // tile: [32 * 33] floats, [slot * 33 + step]; lg_s, lg1_s: [32] floats each, log2 n_k and log2 (n_k - 1) of every slot
 // (-inf without members) -- shared memory private to the calling warp
-template <int CD, int M>
+// PF: the next tile's rows prefetched into registers while the current one is worked on (32 registers; pays when few warps are
+// resident: the fused D = 64 kernel, k_race at four CTAs per SM) or loaded when needed (k_race at eight CTAs per SM)
+// AM: where the auxiliary keys come from -- 0 the k_aux_keys pre-pass (a.aux_keys), 1 bounds per step computed here, 2 group
+// bounds from k_aux_bound (a.aux_max); exact keys on demand in modes 1 and 2
+template <int CD, int M, bool PF = true, int AM = 0>
 __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chain, const int lane, float *tile, float *lg_s, float *lg1_s) {
 	constexpr int CPS = npb_ps(CD);
 	const SweepArgs &a = p.a;
@@ -212,10 +216,12 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 		__syncwarp();
 	}
 
-	float nxt[32];
+	float nxt[PF ? 32 : 1];
+	if (PF) {
 #pragma unroll
-	for (int jj = 0; jj < 32; ++jj) nxt[jj] = __ldcg(Lc + (size_t)jj * 32 + lane); // rows past nsteps exist (BS is padded)
-	bool reload = false;
+		for (int jj = 0; jj < 32; ++jj) nxt[PF ? jj : 0] = __ldcg(Lc + (size_t)jj * 32 + lane); // rows past nsteps exist (BS is padded)
+	}
+	bool reload = !PF;
 
 	for (int ti = 0; ti < ntile; ++ti) {
 		const int b0 = ti * 32;          // first step of the tile within the block
@@ -229,26 +235,29 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 		// The auxiliary draws' race key of step sj: read from the pre-pass (k_aux_keys) if the launch ran one, else LAZY: an
 		// upper bound from the draws' first normals now, the exact key (same function, same bits) only for the steps whose
 		// own key does not clear the bound, and for the whole tile if it enters the sequential pass.
-		const bool lazy = a.aux_keys == nullptr;
+		// GROUP BOUNDS (a.aux_max from k_aux_bound, no aux_keys): the bound is the largest over the tile's 32 steps, read once;
+		// the sequential pass needs the exact keys only if some step's own slot does not clear the bound (see there).
+		constexpr bool lazy = AM != 0, grp = AM == 2;
 		const float ik2 = a.prior.inv_sqrt_kappa * (float)NPB_HALF_LOG2E_SQRT;
 		const float rn_j = (lazy && valid) ? __ldg(a.Xwn + item) : 0.0f;
 		uint32_t auxp = 0xff800000u;
 		bool aux_exact = !lazy || !valid;
 		if (!lazy && valid) auxp = __ldg(a.aux_keys + ((size_t)p.sw * C + chain) * N + sj);
 		float auxkey_j = __uint_as_float(auxp);
-		if (lazy && valid) auxkey_j = g_aux_bound<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2); // a bound until aux_exact
+		if (grp && valid) auxkey_j = __ldg(a.aux_max + ((size_t)p.sw * C + chain) * a.aux_groups + ((p.s0 + b0) >> 5)); // a bound until aux_exact
+		else if (lazy && valid) auxkey_j = g_aux_bound<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2);
 		__syncwarp();
 		if (reload) {
 #pragma unroll
 			for (int jj = 0; jj < 32; ++jj) tile[lane * 33 + jj] = __ldcg(Lc + (size_t)(b0 + jj) * 32 + lane);
-			reload = false;
+			reload = !PF;
 		} else {
 #pragma unroll
-			for (int jj = 0; jj < 32; ++jj) tile[lane * 33 + jj] = nxt[jj];
+			for (int jj = 0; jj < 32; ++jj) tile[lane * 33 + jj] = nxt[PF ? jj : 0];
 		}
-		if (ti + 1 < ntile) {
+		if (PF && ti + 1 < ntile) {
 #pragma unroll
-			for (int jj = 0; jj < 32; ++jj) nxt[jj] = __ldcg(Lc + (size_t)(b0 + 32 + jj) * 32 + lane);
+			for (int jj = 0; jj < 32; ++jj) nxt[PF ? jj : 0] = __ldcg(Lc + (size_t)(b0 + 32 + jj) * 32 + lane);
 		}
 		__syncwarp();
 		unsigned cand_tile = 0u;
@@ -296,6 +305,20 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 
 		if (j0 < cnt) {
 			// ---- sequential pass from step j0: lane = slot ----
+			if (grp) {
+				// Group bound: no auxiliary draw of this tile can win if every step's OWN slot clears the bound even with its
+				// member count run down to one other member by the tile's up to 31 earlier moves (log2 n >= 0): then the best
+				// slot key of every step exceeds every auxiliary key whatever the sequential pass does, and the keys are not needed.
+				const bool safe = !valid || aux_exact ||
+						(lg1_s[zold] >= 5.1f && tile[zold * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)zold) > auxkey_j);
+				if (__all_sync(0xffffffffu, safe)) {
+					if (!aux_exact) {
+						auxp = 0xff800000u;
+						auxkey_j = -INFINITY;
+						aux_exact = true;
+					}
+				}
+			}
 			if (!aux_exact) {
 				auxp = g_aux_exact<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2);
 				auxkey_j = __uint_as_float(auxp);
@@ -1039,14 +1062,17 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 	}
 }
 
-// the race as a kernel of its own: four chains per CTA
-template <int CD, int M>
-__global__ void __launch_bounds__(128, 4) k_race(const PreArgs p) {
+// the race as a kernel of its own: four chains per CTA, 64 registers, eight CTAs per SM, the tile loaded when needed instead of
+// prefetched into registers.  (Round 1: 128 registers with the prefetch, four CTAs per SM.  In a chain that keeps moving items
+// the race is a sequential pass of ~52 dependent instructions per step and was issuing 49 % of the time at 4 warps per scheduler;
+// twice the warps: 165 -> 144 ms per sweep at 15 % moved, 97 -> 95 ms with the chains stationary; 10 or 12 CTAs per SM spill.)
+template <int CD, int M, int AM>
+__global__ void __launch_bounds__(128, 8) k_race(const PreArgs p) {
 	__shared__ float sm[4][G_CONS_FLOATS];
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int chain = blockIdx.x * 4 + w;
 	if (chain >= p.a.C) return;
-	g_consume_chain<CD, M>(p, chain, lane, sm[w], sm[w] + 32 * 33, sm[w] + 32 * 33 + 32);
+	g_consume_chain<CD, M, false, AM>(p, chain, lane, sm[w], sm[w] + 32 * 33, sm[w] + 32 * 33 + 32);
 }
 
 extern template npb_status npb_launch_aux_keys<16>(npb_chains *, const SweepArgs &);
@@ -1147,6 +1173,9 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	if (prepass) {
 		s = npb_launch_aux_keys<16>(ch, a);
 		if (s != NPB_OK) return s;
+	} else if (ch->sw.d16_aux_grp) { // group maxima of a bound (k_aux_bound), exact keys on demand: the default
+		s = npb_launch_aux_bound<16>(ch, a);
+		if (s != NPB_OK) return s;
 	}
 	const size_t C = (size_t)ch->C;
 	NPB_CUDA_OK(cudaMemsetAsync(ch->g_dirty, 1, C * 32, ctx->stream));
@@ -1154,6 +1183,7 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	PreArgs p;
 	p.a = a;
 	if (!prepass) p.a.aux_keys = nullptr;
+	if (prepass || !ch->sw.d16_aux_grp) p.a.aux_max = nullptr;
 	p.BS = BS + 32;
 	p.L = ch->g_L;
 	p.spec = ch->sw.spec != 0;
@@ -1169,8 +1199,13 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 			p.s0 = s0;
 			p.nsteps = nsteps;
 			const unsigned blocks = (unsigned)((ch->C + 3) / 4);
-			if (ch->m_aux == 3) k_race<HD, 3><<<blocks, 128, 0, ctx->stream>>>(p);
-			else k_race<HD, 1><<<blocks, 128, 0, ctx->stream>>>(p);
+			const int am = prepass ? 0 : (ch->sw.d16_aux_grp ? 2 : 1);
+			if (ch->m_aux == 3 && am == 0) k_race<HD, 3, 0><<<blocks, 128, 0, ctx->stream>>>(p);
+			else if (ch->m_aux == 3 && am == 1) k_race<HD, 3, 1><<<blocks, 128, 0, ctx->stream>>>(p);
+			else if (ch->m_aux == 3) k_race<HD, 3, 2><<<blocks, 128, 0, ctx->stream>>>(p);
+			else if (am == 0) k_race<HD, 1, 0><<<blocks, 128, 0, ctx->stream>>>(p);
+			else if (am == 1) k_race<HD, 1, 1><<<blocks, 128, 0, ctx->stream>>>(p);
+			else k_race<HD, 1, 2><<<blocks, 128, 0, ctx->stream>>>(p);
 			NPB_CUDA_OK(cudaGetLastError());
 		}
 	}

@@ -73,7 +73,8 @@ struct npb_chains {
 		int d64_block = 4096;     // NPB_D64_BLOCK: steps per launch of the D = 64 path
 		int d16_epi = 16;         // NPB_D16_EPI: epilogue warps of k_density_tc16 (8 | 16)
 		int d16_nh = 4;           // NPB_D16_NH: chain halves per unit of k_density_tc16 (1 | 2 | 4)
-		bool d16_aux_pre = true;  // NPB_D16_AUX=lazy -> false: no k_aux_keys pre-pass on the kernel pair
+		bool d16_aux_pre = false; // NPB_D16_AUX=pre: the kernel pair reads exact auxiliary keys from the k_aux_keys pre-pass (round 1)
+		bool d16_aux_grp = true;  // NPB_D16_AUX=lazy -> false: no pre-pass at all, bounds per step inside the race; default: k_aux_bound group maxima
 		bool d64_overlap = true;  // NPB_D64_OVERLAP=0 -> false
 		bool d64_fp32 = false;    // NPB_D64_DENSITY=fp32
 		bool two_warp = false;    // NPB_TILE_KERNEL=2warp: round-1 one-chain-per-CTA kernel

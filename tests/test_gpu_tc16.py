@@ -75,8 +75,10 @@ def test_tc16_invariants(npb, ctx, oracle, env, block):
         assert np.allclose([m["purity"][c], m["rand_index"][c], m["adjusted_rand"][c]], want, atol=1e-12)
     print("births", births, "mean K", st.mean_K)
     zs = []
-    # speculation on/off, batching of sweeps, auxiliary keys lazily in the race or from the k_aux_keys pre-pass: same result
-    for spec, per_launch, aux in (("1", None, "lazy"), ("0", None, "lazy"), ("1", 1, "lazy"), ("1", None, "pre"), ("0", 2, "pre")):
+    # speculation on/off, batching of sweeps, auxiliary keys lazily in the race, from the k_aux_keys pre-pass, or bounded per 32-step
+    # group by k_aux_bound and drawn on demand (the default): same result
+    for spec, per_launch, aux in (("1", None, "lazy"), ("0", None, "lazy"), ("1", 1, "lazy"), ("1", None, "pre"), ("0", 2, "pre"),
+                                  ("1", None, "bound"), ("0", 3, "bound")):
         env["NPB_D64_SPEC"], env["NPB_D16_AUX"] = spec, aux
         a = npb.MCMC(ctx, ds, npb.NormalInverseWishart(**syn.reference_prior(D)), chains=6, Kmax=32, K0=8, seed=77)
         a.run(4, sweeps_per_launch=per_launch)
