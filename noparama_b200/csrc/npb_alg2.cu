@@ -25,31 +25,9 @@
 // floats exceed the register file (D = 64: 512 KB per chain; 1024-thread CTA).  The categorical draw is the exponential race
 // of the other sweep kernels.  The sequential chain is latency-bound; this is the first correct device path of configs[3], not
 // yet a tuned one (the tensor-core precompute with rank-1 corrections of the few dirty slots, SURVEY 7.3-5, is the next step).
-#include "npb_alg8_tile4.cuh"
+#include "npb_alg2.cuh"
 
-struct A2Args {
-	const float *X;        // [N, D]
-	const double *X64;     // [N, D] the same rows in double: what the sufficient statistics add and subtract
-	const int32_t *order;  // [n_sweeps, N]
-	npb_z_t *z;            // [N, C]
-	int *counts;           // [C, 32]
-	int *kocc, *overflow;
-	unsigned long long *st; // [C, 4]
-	double *sx, *sxx;      // [C, 32, D], [C, 32, D, D]
-	float *mu, *P, *ld;    // [C, 32, D], [C, 32, D, D], [C, 32]
-	const float *G;        // [N + 2] the count-dependent constant of the predictive
-	const float *lp0;      // [N] prior-predictive log-density of every item (a new cluster's candidate)
-	const float *P0;       // [D, D] Lambda_0^-1
-	float mu0[NPB_MAX_D];
-	float ld0, kappa0, nu0, log2_alpha;
-	int N, C, n_sweeps;
-	uint32_t sweep0;
-	uint64_t seed;
-};
-
-__device__ __forceinline__ float a2_noise(uint32_t a, uint32_t b, uint32_t c) {
-	return neg_lg2_exp1(npb_mix32(npb_mix32(a ^ (b * 0x9E3779B1u)) ^ (c * 0x85EBCA77u)));
-}
+npb_status npb_launch_a2_tile(npb_chains *ch, const A2Args &a); // npb_alg2_tile.cu
 
 template <int D, int LPS, bool PREG>
 __global__ void __launch_bounds__(32 * LPS) k_a2_sweep(const A2Args a) {
@@ -293,19 +271,24 @@ __global__ void __launch_bounds__(32 * LPS) k_a2_sweep(const A2Args a) {
 __global__ void __launch_bounds__(256) k_a2_recount(const double *X64, const npb_z_t *z, int N, int C, int D, double *sx, double *sxx, int *counts_out) {
 	extern __shared__ double a2sm[]; // [D] the current member
 	__shared__ int list[256];
-	__shared__ int nlist;
+	__shared__ int wcnt[8];
 	const int slot = blockIdx.x, chain = blockIdx.y, tid = threadIdx.x;
 	const int E = D * D + D; // elements: D of sum x, D^2 of sum x x^T
 	double acc[17];          // up to (64 * 64 + 64) / 256 = 16.25 elements per thread
 	for (int e = 0; e < 17; ++e) acc[e] = 0.0;
 	int total = 0;
 	for (int i0 = 0; i0 < N; i0 += 256) {
-		if (tid == 0) nlist = 0;
-		__syncthreads();
+		// members of this block of 256 items, in item order (a fixed summation order: the recount is reproducible bit for bit)
 		const int i = i0 + tid;
-		if (i < N && (int)z[(size_t)i * C + chain] == slot) list[atomicAdd(&nlist, 1)] = i;
+		const bool hit = i < N && (int)z[(size_t)i * C + chain] == slot;
+		const unsigned bal = __ballot_sync(0xffffffffu, hit);
+		__syncthreads(); // the previous block's list and warp counts have been read
+		if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
 		__syncthreads();
-		const int nl = nlist;
+		int base = 0, nl = 0;
+		for (int w = 0; w < 8; ++w) { base += w < (tid >> 5) ? wcnt[w] : 0; nl += wcnt[w]; }
+		if (hit) list[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = i;
+		__syncthreads();
 		total += nl;
 		for (int j = 0; j < nl; ++j) {
 			const double *x = X64 + (size_t)list[j] * D;
@@ -477,6 +460,7 @@ static A2Args a2_args(npb_chains *ch, int n_sweeps) {
 	a.n_sweeps = n_sweeps;
 	a.sweep0 = ch->sweep;
 	a.seed = ch->seed;
+	a.tile = ch->sw.a2_tile;
 	return a;
 }
 
@@ -545,8 +529,14 @@ npb_status npb_launch_alg2_conjugate(npb_chains *ch, int n_sweeps) {
 		case 2: k_a2_sweep<2, 1, true><<<C, 32, 0, ctx->stream>>>(a); break;
 		case 4: k_a2_sweep<4, 1, true><<<C, 32, 0, ctx->stream>>>(a); break;
 		case 8: k_a2_sweep<8, 1, true><<<C, 32, 0, ctx->stream>>>(a); break;
-		case 16: k_a2_sweep<16, 2, true><<<C, 64, 0, ctx->stream>>>(a); break;
-		case 64: k_a2_sweep<64, 32, false><<<C, 1024, 0, ctx->stream>>>(a); break;
+		case 16:
+			if (ch->sw.a2_tile > 0) { s = npb_launch_a2_tile(ch, a); if (s != NPB_OK) return s; }
+			else k_a2_sweep<16, 2, true><<<C, 64, 0, ctx->stream>>>(a);
+			break;
+		case 64:
+			if (ch->sw.a2_tile > 0) { s = npb_launch_a2_tile(ch, a); if (s != NPB_OK) return s; }
+			else k_a2_sweep<64, 32, false><<<C, 1024, 0, ctx->stream>>>(a);
+			break;
 		default: return npb_fail(ctx, NPB_E_UNSUPPORTED, "D");
 		}
 		NPB_CUDA_OK(cudaGetLastError());

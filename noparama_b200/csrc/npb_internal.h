@@ -35,6 +35,7 @@ struct npb_ctx {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	char err[512] = {0};
 	int n_sm = 0;               // multiprocessors of this context's device (grid size of the persistent kernels)
+	bool a2_tile_attr_set = false; // the same for k_a2_tile (npb_alg2_tile.cu)
 	bool fused_attr_set = false; // per device: the shared-memory opt-in of k_sweep_tc16 has been made on this context's device
 	PriorHost prior;
 	float *d_CT2 = nullptr, *d_S = nullptr; // device copies of the packed prior factors
@@ -78,6 +79,7 @@ struct npb_chains {
 		bool d64_overlap = true;  // NPB_D64_OVERLAP=0 -> false
 		bool d64_fp32 = false;    // NPB_D64_DENSITY=fp32
 		bool two_warp = false;    // NPB_TILE_KERNEL=2warp: round-1 one-chain-per-CTA kernel
+		int a2_tile = 64;         // NPB_A2_TILE: conjugate Algorithm 2 at D = 16, 64: steps evaluated ahead by k_a2_tile (1..64, same results); 0 = the step-at-a-time kernel k_a2_sweep
 	} sw;
 	double moved_frac_last = -1.0; // moved / reassignments of the last Algorithm 8 launch whose statistics were read; -1 unknown
 	bool time_kernels = false;  // option "time_kernels": CUDA events around every launch of the dominant sweep kernel

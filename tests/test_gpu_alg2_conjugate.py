@@ -120,3 +120,56 @@ def test_distribution_against_oracle(npb, ctx, oracle, which, T, seeds):
     assert abs(br - res[:, 4].mean()) < 0.15 * res[:, 4].mean() + 2e-4
     ch.close()
     ds.close()
+
+
+@pytest.mark.parametrize("D,N,K0", [(16, 900, 10), (64, 500, 8)])
+def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0):
+    """k_a2_tile (npb_alg2_tile.cu) evaluates up to 64 steps ahead of the chain and corrects the two changed columns after every
+    move: the assignments, counts and FP64 statistics must equal those of the strictly sequential schedule (a2_tile = 1) bit for
+    bit, from a start where most items move (K0 random clusters) to the settled chain"""
+    X, y = syn.gmm(N, D, 4, 700 + D, min_dist=3.0)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**conj_prior(X)).bind(ctx)
+    res = {}
+    for tile in (1, 8, 64):
+        ch = npb.Chains(ctx, ds, 7, Kmax=32, K0=K0, seed=21)
+        ch.set_option("a2_tile", str(tile))
+        moved = births = 0
+        zs = []
+        for _ in range(3):
+            st = ch.sweep(npb.ALG2_CONJUGATE, 2)
+            assert st.overflow_chains == 0
+            moved += st.moved
+            births += st.new_clusters
+            zs.append(ch.assignments().copy())
+        res[tile] = (zs, moved, births, st.candidates, [ch.alg2_suffstats(c) for c in (0, 6)])
+        ch.close()
+    assert res[1][1] > 2 * N  # items moved: the correction path ran
+    for tile in (8, 64):
+        for a, b in zip(res[1][0], res[tile][0]):
+            assert np.array_equal(a, b), tile
+        assert res[1][1:4] == res[tile][1:4], tile
+        for (n0, sx0, sxx0), (n1, sx1, sxx1) in zip(res[1][4], res[tile][4]):
+            assert np.array_equal(n0, n1) and np.array_equal(sx0[n0 > 0], sx1[n1 > 0]) and np.array_equal(sxx0[n0 > 0], sxx1[n1 > 0])
+    print("D = %d: tiles of 1, 8, 64 steps give the same chain (%d moves, %d births over 6 sweeps of 7 chains)" % (D, res[1][1], res[1][2]))
+    ds.close()
+
+
+@pytest.mark.parametrize("D,N", [(16, 600), (64, 300)])
+def test_step_at_a_time_kernel_still_follows_the_moves(npb, ctx, D, N):
+    """the round-2 first path (k_a2_sweep, option a2_tile = 0) stays available for A/B measurements: statistics against a recount"""
+    X, y = syn.gmm(N, D, 3, 500 + D, min_dist=3.0)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**conj_prior(X)).bind(ctx)
+    ch = npb.Chains(ctx, ds, 4, Kmax=32, K0=12, seed=8)
+    ch.set_option("a2_tile", "0")
+    st = ch.sweep(npb.ALG2_CONJUGATE, 3)
+    assert st.overflow_chains == 0 and st.moved > N
+    z = ch.assignments()
+    n, sx, sxx = ch.alg2_suffstats(2)
+    assert np.array_equal(n, np.bincount(z[2], minlength=32))
+    for k in np.nonzero(n)[0]:
+        M = X[z[2] == k]
+        assert np.allclose(sx[k], M.sum(0), rtol=1e-10, atol=1e-9) and np.allclose(sxx[k], M.T @ M, rtol=1e-10, atol=1e-8)
+    ch.close()
+    ds.close()
