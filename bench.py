@@ -421,17 +421,27 @@ def split_merge_cpu(X, D, n_items=1000, sweeps=1):
 
 def conjugate_measure(npb, syn, ctx, rank):
     """BASELINE configs[3]: CONJUGATE Algorithm 2 (collapsed Gibbs, NIW posterior predictive, statistics up- and down-dated per
-    move; npb_alg2.cu) -- a first correct device path, latency-bound: at 64-D the 32 slots' P = Lambda_n^-1 (512 KB per chain) do
-    not fit the register file and stream from L2 every step, so the shape is run at N = 20 000 instead of 1 000 000 (the rate
-    does not depend on N); the tensor-core precompute with rank-1 corrections of the dirty slots is the next step."""
+    move).  `cfg4_64d` is configs[3]'s own shape, 256 chains x N = 1 000 000 x 64-D, on k_a2_tile (npb_alg2_tile.cu: a tile of 64
+    steps evaluated ahead of the chain, the two changed columns corrected after every move; same chain as the sequential
+    schedule bit for bit); the chains start from the true partition (one state broadcast to all chains, their random streams
+    their own) so that the warm-up does not have to move a million items per chain.  `step_at_a_time_kernel` is round 2's
+    first path (k_a2_sweep) on a short prefix of the same data, for the ratio."""
     out = {}
-    for name, D, N, chains, K in (("cfg4_64d", 64, 20_000, 256, 16), ("headline_shape_16d", 16, 100_000, 1024, 20)):
+    for name, D, N, chains, K, tile, truth in (("cfg4_64d", 64, 1_000_000, 256, 16, 64, True), ("headline_shape_16d", 16, 100_000, 1024, 20, 64, False),
+                                                 ("step_at_a_time_kernel_64d", 64, 20_000, 256, 16, 0, True)):
         X, y = syn.gmm(N, D, K, 20261004)
         ds = npb.Dataset(ctx, X)
         npb.NormalInverseWishart(mu0=X.mean(0), kappa=0.01, nu=D + 2.0, Lambda=np.eye(D), alpha=1.0).bind(ctx)
         ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K, m_aux=M_AUX, seed=SEED + 59 * rank)
-        ch.init_from_params(*given_clusters(X, y))
-        for _ in range(3):
+        ch.set_option("a2_tile", str(tile))
+        mu, Sig = given_clusters(X, y)
+        if truth:
+            ch.set_state(0, y.astype(np.int32), np.arange(K, dtype=np.int32), mu, Sig)
+            ch.broadcast_state(0)
+        else:
+            ch.init_from_params(mu, Sig)
+        warm = 2 if truth else 3
+        for _ in range(warm):
             ch.sweep(npb.ALG2_CONJUGATE, 1)
         ms, cand, moved, births = [], 0, 0, 0
         for _ in range(2):
@@ -443,9 +453,13 @@ def conjugate_measure(npb, syn, ctx, rank):
         # an Algorithm 2 step = (K_i + 1) (F_eval(D) + 12) flops + 2 (2 D^2 + 6 D) per rank-1 down- / up-date (moves only here)
         fl = (cand / 2) * (f_eval(D) + 12) + (moved / 2) * 2 * (2 * D * D + 6 * D)
         out[name] = {"workload": "%d chains x N=%d x %d-D, %d components, conjugate NIW (mu0 = data mean, kappa0 = 0.01, nu0 = D + 2, Lambda0 = I), "
-                                 "Kmax=32" % (chains, N, D, K), "value": chains * N / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": 2,
-                     "warmup": 3, "moved_fraction": moved / (2 * chains * N), "candidates_per_reassignment": cand / (2 * chains * N),
+                                 "Kmax=32; start: %s" % (chains, N, D, K, "the true partition" if truth else "the true clusters' parameters, random assignment"),
+                     "kernel": "k_a2_tile<%d> (tile of %d steps)" % (D, tile) if tile else "k_a2_sweep<%d> (one step at a time)" % D,
+                     "value": chains * N / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": 2,
+                     "warmup": warm, "moved_fraction": moved / (2 * chains * N), "candidates_per_reassignment": cand / (2 * chains * N),
                      "mean_K": float(m["K"].mean()), "mean_purity": float(m["purity"].mean()), "algorithmic_tflops": fl / (k_ms * 1e-3) / 1e12}
+        out[name]["roofline"] = {"bound": "fp32", "achieved": out[name]["algorithmic_tflops"], "unit": "TFLOP/s", "kernel": out[name]["kernel"],
+                                 "note": "SURVEY 8(d) algorithmic flops of the sweep / the sweep time; FP32 FMA peak: roofline_fp32_equivalent.peak"}
         ch.close()
         ds.close()
     return out

@@ -36,9 +36,9 @@ template <int D> struct A2T {
 	static constexpr int O_XT = 0;                          // [D][XS] items of the tile, transposed
 	static constexpr int O_DW = O_XT + D * XS;              // [WARPS][D][UI] x - mu of a unit, chunk-swizzled
 	static constexpr int O_MU = O_DW + WARPS * D * UI;      // [32][D]
-	static constexpr int O_TT = O_MU + 32 * D;              // [TMAX][32] quadratic forms
-	static constexpr int O_KT = O_TT + TMAX * 32;           // [TMAX][33] race keys
-	static constexpr int O_DM = O_KT + TMAX * 33;           // [2][D] x - mu of a moving item against (old, new) cluster
+	static constexpr int O_TT = O_MU + 32 * D;              // [TMAX][33] quadratic forms (column 32 unused: the stride keeps a column conflict-free)
+	static constexpr int O_KT = O_TT + TMAX * 33 + 1;       // [TMAX][33] race keys
+	static constexpr int O_DM = O_KT + TMAX * 33 + 1;       // [2][D] x - mu of a moving item against (old, new) cluster
 	static constexpr int O_PU = O_DM + 2 * D;               // [2][D] P (x - mu)
 	static constexpr int O_XD = O_PU + 2 * D;               // [D] doubles: the moving item in FP64 (8-byte aligned: all terms even)
 	static constexpr int O_LD = O_XD + 2 * D;               // [32] log det Lambda_n
@@ -47,7 +47,8 @@ template <int D> struct A2T {
 	static constexpr int O_ITEM = O_ZOLD + TMAX;            // [TMAX] int
 	static constexpr int O_WIN = O_ITEM + TMAX;             // [TMAX] int
 	static constexpr int O_RED = O_WIN + TMAX;              // [8] float
-	static constexpr int FLOATS = O_RED + 8;
+	static constexpr int O_SL = O_RED + 8;                  // [34] int: the occupied slots at the start of the tile, then 32 (a new cluster)
+	static constexpr int FLOATS = O_SL + 36;
 };
 
 // the quadratic forms of the clusters in `mask` for the tile's items [j_lo, T): ttab[j][k]
@@ -65,9 +66,13 @@ __device__ __forceinline__ void a2_columns(float *sm, const float *Pc, unsigned 
 		const int k = __fns(mask, 0, u / nups + 1);
 		const int u0 = (iu_lo + u % nups) * L::UI;
 		// x - mu_k of the unit's items, row r = dimension, 16-byte chunks swizzled by the row's column group
-		for (int e = lane; e < D * L::UI; e += 32) {
-			const int r = e / L::UI, i = e % L::UI;
-			dw[r * L::UI + ((((i >> 2) ^ (r >> 2)) & (L::NCH - 1)) << 2) + (i & 3)] = xT[r * L::XS + u0 + i] - mus[k * D + r];
+#pragma unroll 4
+		for (int e = lane; e < D * L::NCH; e += 32) {
+			const int r = e / L::NCH, c = e % L::NCH;
+			float4 v = *reinterpret_cast<const float4 *>(xT + r * L::XS + u0 + 4 * c);
+			const float m = mus[k * D + r];
+			v.x -= m; v.y -= m; v.z -= m; v.w -= m;
+			*reinterpret_cast<float4 *>(dw + r * L::UI + (((c ^ (r >> 2)) & (L::NCH - 1)) << 2)) = v;
 		}
 		__syncwarp();
 		float acc[L::IT][4];
@@ -114,7 +119,7 @@ __device__ __forceinline__ void a2_columns(float *sm, const float *Pc, unsigned 
 #pragma unroll
 			for (int o = L::CG / 2; o > 0; o >>= 1) tt[it] += __shfl_xor_sync(0xffffffffu, tt[it], o);
 			const int j = u0 + ig * L::IT + it;
-			if (cg == 0 && j >= j_lo && j < T) ttab[j * 32 + k] = tt[it];
+			if (cg == 0 && j >= j_lo && j < T) ttab[j * 33 + k] = tt[it];
 		}
 		__syncwarp();
 	}
@@ -131,7 +136,7 @@ __device__ __forceinline__ float a2_key(const A2Args &a, const float *sm, int j,
 	const bool own = k == zold[j];
 	const int n_eff = n - (own ? 1 : 0);
 	if (n_eff <= 0) return -INFINITY;
-	const float t = sm[L::O_TT + j * 32 + k];
+	const float t = sm[L::O_TT + j * 33 + k];
 	float q_eff = t, ld_eff = sm[L::O_LD + k];
 	if (own) { // the item's own cluster with the item removed, in closed form (Sherman-Morrison)
 		const float kp = a.kappa0 + (float)n, cdown = kp / (kp - 1.0f);
@@ -145,7 +150,7 @@ __device__ __forceinline__ float a2_key(const A2Args &a, const float *sm, int j,
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) k_a2_tile(const A2Args a) {
+__global__ void __launch_bounds__(256, (D == 16 ? 3 : 2)) k_a2_tile(const A2Args a) {
 	using L = A2T<D>;
 	extern __shared__ __align__(16) float sm[];
 	const int chain = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(256) k_a2_tile(const A2Args a) {
 	float *dm = sm + L::O_DM, *pu = sm + L::O_PU, *red = sm + L::O_RED;
 	double *xd = reinterpret_cast<double *>(sm + L::O_XD);
 	int *cnt = reinterpret_cast<int *>(sm + L::O_CNT), *zold = reinterpret_cast<int *>(sm + L::O_ZOLD);
-	int *items = reinterpret_cast<int *>(sm + L::O_ITEM), *win = reinterpret_cast<int *>(sm + L::O_WIN);
+	int *items = reinterpret_cast<int *>(sm + L::O_ITEM), *win = reinterpret_cast<int *>(sm + L::O_WIN), *slist = reinterpret_cast<int *>(sm + L::O_SL);
 	float *Pc = a.P + (size_t)chain * 32 * D * D;
 	double *sxc = a.sx + (size_t)chain * 32 * D, *sxxc = a.sxx + (size_t)chain * 32 * D * D;
 
@@ -191,19 +196,22 @@ __global__ void __launch_bounds__(256) k_a2_tile(const A2Args a) {
 			unsigned occ = 0u;
 #pragma unroll
 			for (int k = 0; k < 32; ++k) occ |= cnt[k] > 0 ? 1u << k : 0u;
+			const int nocc = __popc(occ);
+			if (tid < 32 && (occ >> tid & 1u)) slist[__popc(occ & ((1u << tid) - 1u))] = tid;
+			if (tid == 32) slist[nocc] = 32;
 			__syncthreads();
 			a2_columns<D>(sm, Pc, occ, 0, T);
 			__syncthreads();
-			for (int e = tid; e < T * 33; e += 256) {
-				const int j = e / 33, k = e % 33;
-				ktab[j * 33 + k] = a2_key<D>(a, sm, j, k, (uint32_t)(s + j), ka, kb);
+			for (int kk = warp; kk <= nocc; kk += L::WARPS) { // a warp per candidate column (occupied slots, then a new cluster), lanes over the steps
+				const int k = slist[kk];
+				for (int j = lane; j < T; j += 32) ktab[j * 33 + k] = a2_key<D>(a, sm, j, k, (uint32_t)(s + j), ka, kb);
 			}
 			__syncthreads();
 			int j0 = 0, tile_moves = 0;
 			while (j0 < T) {
 				// ---- winners of the steps not yet final ----
 				for (int j = j0 + warp; j < T; j += L::WARPS) {
-					const float key = ktab[j * 33 + lane];
+					const float key = cnt[lane] - (lane == zold[j] ? 1 : 0) > 0 ? ktab[j * 33 + lane] : -INFINITY; // only columns of clusters with (other) members hold keys
 					const float top = fmaxf(redux_max_f32(key), ktab[j * 33 + 32]);
 					const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
 					int w = bal ? __ffs(bal) - 1 : 32;
@@ -334,9 +342,9 @@ __global__ void __launch_bounds__(256) k_a2_tile(const A2Args a) {
 					const unsigned dirty = (died ? 0u : 1u << src) | 1u << dst;
 					a2_columns<D>(sm, Pc, dirty, j0, T);
 					__syncthreads();
-					for (int e = tid; e < (T - j0) * 2; e += 256) {
-						const int j = j0 + (e >> 1), k = (e & 1) ? dst : src;
-						ktab[j * 33 + k] = a2_key<D>(a, sm, j, k, (uint32_t)(s + j), ka, kb);
+					if (warp < 2 && !(warp == 0 && died)) {
+						const int k = warp ? dst : src;
+						for (int j = j0 + lane; j < T; j += 32) ktab[j * 33 + k] = a2_key<D>(a, sm, j, k, (uint32_t)(s + j), ka, kb);
 					}
 					__syncthreads();
 				}
