@@ -200,7 +200,6 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 	int overflow = 0;
 	const int ntile = (p.nsteps + 31) / 32;
 	uint32_t born_mask = 0u;
-	int recent_moves = 0;
 
 	// The table of this block was computed while the previous block was still being consumed (the fused schedule; with
 	// separate launches the bookkeeping is the same): the columns of the slots born there are re-evaluated here, for the whole block (lane = step).
@@ -263,46 +262,86 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 		unsigned cand_tile = 0u;
 
 		int j0 = 0;
-		if (p.spec && recent_moves < 3) {
-			// ---- speculative pass: lane = step ----
-			// The item stays iff its own slot's key is the largest.  The race noise is capped at G_NOISE_CAP (g_noise), so a
-			// slot whose noiseless key lies more than the cap (+1 for rounding) below the own key cannot win: in a converged chain
-			// that is every other slot, and the pass costs two shared loads, two adds and a compare per (step, slot) -- no
-			// logarithm.  Slots some lane cannot exclude are evaluated exactly (warp-uniform loop over the union).
+		if (p.spec) {
+			// ---- step-parallel pass: lane = step, repeated after every move ----
+			// Every lane finds its step's winner with the member counts as they stand: its own slot's key first; the race noise is
+			// capped at G_NOISE_CAP (g_noise), so a slot whose noiseless key lies more than the cap (+1 for rounding) below the own
+			// key cannot win -- two shared loads, two adds and a compare per (step, slot), no logarithm -- and only the slots a lane
+			// cannot exclude are evaluated exactly (same keys, same operation order as the sequential pass).  The lane keeps its
+			// winner (slot w, count-independent part basew, key top) and an upper bound ubmax of every other slot's key.
+			// The first lane whose item does not stay is the chain's next move: the steps before it are final.  A move changes
+			// two member counts and nothing else (parameters are frozen between births), so the later lanes only re-evaluate the
+			// keys of those two slots: the gaining slot's exactly (it may take over), the losing slot's if it is the lane's
+			// winner (it must still clear ubmax).  A lane that cannot be decided this way -- a tie with the bound, an auxiliary
+			// draw that may win, a slot left without members -- ends the pass: the sequential pass takes over at its step.
+			int w = zold;
+			float basew = tile[zold * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)zold);
 			const float lg_own = lg1_s[zold];
-			const float own = lg_own > -INFINITY ? (tile[zold * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)zold)) + lg_own : -INFINITY;
-			if (!aux_exact && own > -INFINITY && !(own >= auxkey_j)) { // the bound does not settle it: the exact key
-				auxp = g_aux_exact<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2);
-				auxkey_j = __uint_as_float(auxp);
-				aux_exact = true;
-			}
-			bool stays = own > -INFINITY && own >= auxkey_j;
+			float top = lg_own > -INFINITY ? basew + lg_own : -INFINITY;
+			float ubmax = -INFINITY;
 			unsigned need = 0u;
 #pragma unroll 8
 			for (int k = 0; k < 32; ++k) {
 				const float ub = (tile[k * 33 + lane] + lg_s[k]) + (G_NOISE_CAP + 1.0f);
-				need |= (ub >= own) ? (1u << k) : 0u;
+				const bool nd = ub >= top;
+				need |= nd ? (1u << k) : 0u;
+				ubmax = (nd || k == zold) ? ubmax : fmaxf(ubmax, ub);
 			}
 			need &= ~(1u << zold);
-			unsigned un = __reduce_or_sync(0xffffffffu, (valid && stays) ? need : 0u);
-			if (un) {
-				float best = own;
-				int bk = zold;
-				while (un) {
-					const int k = __ffs(un) - 1;
-					un &= un - 1;
-					const float lg = lg_s[k];
-					const float key = lg > -INFINITY ? (tile[k * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)k)) + lg : -INFINITY;
-					if (k != zold && (key > best || (key == best && k < bk))) { best = key; bk = k; }
-				}
-				stays = stays && bk == zold;
+			if (!valid) need = 0u;
+			while (need) {
+				const int k = __ffs(need) - 1;
+				need &= need - 1;
+				const float lg = lg_s[k];
+				const float b = tile[k * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)k);
+				const float key = lg > -INFINITY ? b + lg : -INFINITY;
+				if (key > top || (key == top && k < w)) { ubmax = fmaxf(ubmax, top); w = k; basew = b; top = key; }
+				else ubmax = fmaxf(ubmax, key);
 			}
-			const unsigned mv = __ballot_sync(0xffffffffu, valid && !stays);
-			j0 = mv ? __ffs(mv) - 1 : cnt;
-			cand_tile += (unsigned)(j0 * (kocc + M));
+			if (!aux_exact && !(top >= auxkey_j)) { // the bound does not settle it: the exact key
+				auxp = g_aux_exact<CD, M>(ph, a.prior, rn_j, (uint32_t)sj, sweep, ik2);
+				auxkey_j = __uint_as_float(auxp);
+				aux_exact = true;
+			}
+			for (;;) {
+				const bool safe = top > ubmax && top >= auxkey_j;
+				const unsigned evm = __ballot_sync(0xffffffffu, valid && lane >= j0 && (!safe || w != zold));
+				const int je = evm ? __ffs(evm) - 1 : cnt;
+				cand_tile += (unsigned)((je - j0) * (kocc + M));
+				j0 = je;
+				if (je >= cnt) break;
+				if (!__shfl_sync(0xffffffffu, (int)safe, je)) break; // the sequential pass decides step je and what follows
+				const int src = __shfl_sync(0xffffffffu, zold, je), dst = __shfl_sync(0xffffffffu, w, je);
+				cand_tile += (unsigned)(kocc + M);
+				if (lane == src) n -= 1.0f;
+				if (lane == dst) n += 1.0f;
+				if (__any_sync(0xffffffffu, lane == src && n <= 0.0f)) { kocc--; cand_tile--; }
+				if (lane == src || lane == dst) {
+					lgn = n > 0.0f ? fast_lg2(n) : -INFINITY;
+					lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
+					lg_s[lane] = lgn;
+					lg1_s[lane] = lgn1;
+				}
+				__syncwarp();
+				st_moved++;
+				if (lane == je) znew = dst;
+				j0 = je + 1;
+				if (lane > je) {
+					const float lgd = dst == zold ? lg1_s[dst] : lg_s[dst]; // the gaining slot's key went up
+					if (w == dst) top = basew + lgd;
+					else {
+						const float b = tile[dst * 33 + lane] + g_noise(T, (uint32_t)lane, (uint32_t)dst);
+						const float key = lgd > -INFINITY ? b + lgd : -INFINITY;
+						if (key > top || (key == top && dst < w)) { ubmax = fmaxf(ubmax, top); w = dst; basew = b; top = key; }
+						else ubmax = fmaxf(ubmax, key);
+					}
+					if (w == src) { // the losing slot's went down
+						const float lgs = src == zold ? lg1_s[src] : lg_s[src];
+						top = lgs > -INFINITY ? basew + lgs : -INFINITY;
+					}
+				}
+			}
 		}
-		recent_moves = 0;
-
 		if (j0 < cnt) {
 			// ---- sequential pass from step j0: lane = slot ----
 			if (grp) {
@@ -401,7 +440,6 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 					lgn = n > 0.0f ? fast_lg2(n) : -INFINITY;
 					lgn1 = n > 1.0f ? fast_lg2(n - 1.0f) : -INFINITY;
 					st_moved++;
-					recent_moves++;
 					if (lane == j) znew = new_slot;
 				}
 			}
