@@ -259,6 +259,8 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 			for (int jj = 0; jj < 32; ++jj) nxt[PF ? jj : 0] = __ldcg(Lc + (size_t)(b0 + 32 + jj) * 32 + lane);
 		}
 		__syncwarp();
+		if (!PF && b0 + 32 + lane < p.nsteps) // the next tile's row of this lane on its way into L2 while this tile is decided
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(Lc + (size_t)(b0 + 32 + lane) * 32));
 		unsigned cand_tile = 0u;
 
 		int j0 = 0;
@@ -280,13 +282,15 @@ __device__ __forceinline__ void g_consume_chain(const PreArgs &p, const int chai
 			float top = lg_own > -INFINITY ? basew + lg_own : -INFINITY;
 			float ubmax = -INFINITY;
 			unsigned need = 0u;
+			const float thr = top - (G_NOISE_CAP + 1.0f); // (the own slot itself never falls below it: its noise is at most the cap)
 #pragma unroll 8
 			for (int k = 0; k < 32; ++k) {
-				const float ub = (tile[k * 33 + lane] + lg_s[k]) + (G_NOISE_CAP + 1.0f);
-				const bool nd = ub >= top;
-				need |= nd ? (1u << k) : 0u;
-				ubmax = (nd || k == zold) ? ubmax : fmaxf(ubmax, ub);
+				const float v = tile[k * 33 + lane] + lg_s[k];
+				const bool nd = v >= thr;
+				if (nd) need |= 1u << k;
+				ubmax = fmaxf(ubmax, nd ? -INFINITY : v);
 			}
+			ubmax += G_NOISE_CAP + 1.0f;
 			need &= ~(1u << zold);
 			if (!valid) need = 0u;
 			while (need) {
@@ -1104,8 +1108,11 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) k_density_tc16(const GemmArgs
 // prefetched into registers.  (Round 1: 128 registers with the prefetch, four CTAs per SM.  In a chain that keeps moving items
 // the race is a sequential pass of ~52 dependent instructions per step and was issuing 49 % of the time at 4 warps per scheduler;
 // twice the warps: 165 -> 144 ms per sweep at 15 % moved, 97 -> 95 ms with the chains stationary; 10 or 12 CTAs per SM spill.)
+#ifndef NPB_RACE_CTAS
+#define NPB_RACE_CTAS 8
+#endif
 template <int CD, int M, int AM>
-__global__ void __launch_bounds__(128, 8) k_race(const PreArgs p) {
+__global__ void __launch_bounds__(128, NPB_RACE_CTAS) k_race(const PreArgs p) {
 	__shared__ float sm[4][G_CONS_FLOATS];
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int chain = blockIdx.x * 4 + w;
