@@ -20,7 +20,11 @@ for name, D, N, chains, K in [sh for sh in shapes if sh[0] in os.environ.get("A2
             continue
         ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K, seed=1234)
         ch.set_option("a2_tile", str(tile))
-        ch.init_from_params(*given(X, y))
+        if os.environ.get("A2_TRUTH"):
+            ch.set_state(0, y.astype(np.int32), np.arange(K, dtype=np.int32), *given(X, y))
+            ch.broadcast_state(0)
+        else:
+            ch.init_from_params(*given(X, y))
         out = []
         for i in range(4):
             st = ch.sweep(npb.ALG2_CONJUGATE, 1)

@@ -173,3 +173,32 @@ def test_step_at_a_time_kernel_still_follows_the_moves(npb, ctx, D, N):
         assert np.allclose(sx[k], M.sum(0), rtol=1e-10, atol=1e-9) and np.allclose(sxx[k], M.T @ M, rtol=1e-10, atol=1e-8)
     ch.close()
     ds.close()
+
+
+@pytest.mark.parametrize("D,N", [(16, 800), (64, 500)])
+def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N):
+    """k_a2_tile's quadratic forms (register-blocked products) against k_a2_sweep's row dots: the two
+    kernels draw the same race noise, so from the same state one sweep must make the same decisions except where two keys lie within
+    the FP32 rounding of the forms (~1e-6 relative); an error of 1e-4 in a form would flip a visible share of the steps"""
+    X, y = syn.gmm(N, D, 4, 800 + D, min_dist=3.0)
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**conj_prior(X)).bind(ctx)
+    base = npb.Chains(ctx, ds, 6, Kmax=32, K0=6, seed=31)
+    base.sweep(npb.ALG2_CONJUGATE, 4 if D == 16 else 1)  # past the first reshuffle, still moving
+    zs = base.assignments()
+    out = {}
+    for tile in (0, 64):
+        ch = npb.Chains(ctx, ds, 6, Kmax=32, K0=6, seed=31)
+        ch.set_option("a2_tile", str(tile))
+        for c in range(6):
+            slots = np.unique(zs[c]).astype(np.int32)
+            ch.set_state(c, zs[c], slots, np.zeros((len(slots), D)), np.tile(np.eye(D), (len(slots), 1, 1)))
+        st = ch.sweep(npb.ALG2_CONJUGATE, 1)
+        out[tile] = (ch.assignments().copy(), st.moved)
+        ch.close()
+    same = (out[0][0] == out[64][0]).mean()
+    print("D = %d: %.5f of the assignments equal after one sweep; moves %d (step at a time) / %d (tile)" % (D, same, out[0][1], out[64][1]))
+    assert out[0][1] > 0
+    assert same > 0.99
+    base.close()
+    ds.close()
