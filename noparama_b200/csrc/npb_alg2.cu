@@ -28,6 +28,7 @@
 #include "npb_alg2.cuh"
 
 npb_status npb_launch_a2_tile(npb_chains *ch, const A2Args &a); // npb_alg2_tile.cu
+npb_status npb_launch_a2_tc(npb_chains *ch, const A2Args &a);   // npb_alg2_tc.cu
 
 template <int D, int LPS, bool PREG>
 __global__ void __launch_bounds__(32 * LPS) k_a2_sweep(const A2Args a) {
@@ -534,7 +535,7 @@ npb_status npb_launch_alg2_conjugate(npb_chains *ch, int n_sweeps) {
 			else k_a2_sweep<16, 2, true><<<C, 64, 0, ctx->stream>>>(a);
 			break;
 		case 64:
-			if (ch->sw.a2_tile > 0) { s = npb_launch_a2_tile(ch, a); if (s != NPB_OK) return s; }
+			if (ch->sw.a2_tile > 0) { s = ch->sw.a2_tc ? npb_launch_a2_tc(ch, a) : npb_launch_a2_tile(ch, a); if (s != NPB_OK) return s; }
 			else k_a2_sweep<64, 32, false><<<C, 1024, 0, ctx->stream>>>(a);
 			break;
 		default: return npb_fail(ctx, NPB_E_UNSUPPORTED, "D");

@@ -1,0 +1,438 @@
+// npb_alg2_tc.cu -- CONJUGATE Algorithm 2 at D = 64 (BASELINE configs[3]: "tensor-core whitened quadratic forms"): the tile
+// schedule of npb_alg2_tile.cu -- up to 128 steps evaluated ahead of the chain, the two changed columns corrected after every
+// move -- with the quadratic forms on tcgen05.
+//
+// For a tile of 128 steps and one cluster k:  Y = X' P_k  (128 x 64 x 64) is ONE accumulator of 64 TMEM columns, X' the items
+// centred on the data mean.  FP32 accuracy from FP16 operands as in npb_alg8_gemm.cu: both operands are scaled by a power of two to
+// just below 2^14 and split into two FP16 terms, three products (hi hi + hi lo + lo hi) = 12 `tcgen05.mma kind::f16` of
+// M = 128, N = 64, K = 16 per (tile, cluster).  P is symmetric, so with mu' the centred posterior mean
+//     t = (x' - mu')^T P (x' - mu') = sum_c Y_c (x'_c - 2 mu'_c) + mu'^T P mu'
+// and the epilogue is 64 FMAs per (step, cluster) -- thread = step = TMEM lane, the accumulator's 64 columns split over two warps --
+// instead of the 4096 of the FP32 product; the race key follows in the same thread.  A images are built once per tile (the items
+// gathered in scan order, centred, scaled, split, stored K-major with the 128-byte swizzle), the B image of a cluster from its FP32
+// P in global memory every time it is used -- so there is no second copy of the state to keep consistent: after a move the two
+// changed clusters are simply evaluated again.  Same schedule-independence as the FP32 tile kernel: a row of the product depends
+// only on its own item and the cluster's state, so a.tile = 1 ... 128 give the same chain bit for bit.
+//
+// One CTA of 8 warps per chain, two CTAs per SM (112 KB of shared memory, 64 TMEM columns, <= 128 registers).  Per cluster: all
+// threads build the B image; one thread issues the 12 MMAs and commits to an mbarrier; all wait; all read TMEM.
+#include "npb_alg2.cuh"
+#include "npb_tc_common.cuh"
+
+npb_status npb_launch_a2_tc(npb_chains *ch, const A2Args &a);
+
+namespace {
+
+constexpr int TD = 64;    // dimension
+constexpr int TM = 128;   // steps per tile = UMMA M
+constexpr int XSS = 65;   // row stride of the FP32 item tile (a thread walks its own row: conflict-free)
+constexpr uint32_t S_AHI = 0, S_ALO = 16384, S_BHI = 32768, S_BLO = 40960, S_XS = 49152;
+constexpr uint32_t S_KT = S_XS + TM * XSS * 4;   // [TM][33] race keys
+constexpr uint32_t S_MU = S_KT + TM * 33 * 4;    // [32][64] centred means
+constexpr uint32_t S_MISC = S_MU + 32 * TD * 4;
+
+struct TcMisc {
+	double xd[TD];       // the moving item in FP64
+	unsigned long long bar;
+	float ldv[32];
+	int cnt[32];
+	int zold[TM], items[TM], win[TM];
+	int slist[36];
+	float red[16];
+	float dm[2 * TD], pu[2 * TD];
+	float tpart[TM];
+	float xbar[TD];
+	uint32_t tmem;
+};
+constexpr uint32_t TC_SMEM = S_MISC + sizeof(TcMisc) + 1024; // + alignment slack
+
+struct TcArgs {
+	A2Args a;
+	const double *xbar; // [2 D + 1] column means of the dataset, exponent of the A scale, column maxima (npb_dataset::Xbar)
+};
+
+__device__ __forceinline__ float tc_key(const A2Args &a, const TcMisc *m, float t, int j, int k, uint32_t step, uint32_t ka, uint32_t kb) {
+	const int n = m->cnt[k];
+	const bool own = k == m->zold[j];
+	const int n_eff = n - (own ? 1 : 0);
+	if (n_eff <= 0) return -INFINITY;
+	float q_eff = t, ld_eff = m->ldv[k];
+	if (own) { // the item's own cluster with the item removed, in closed form (Sherman-Morrison)
+		const float kp = a.kappa0 + (float)n, cdown = kp / (kp - 1.0f);
+		const float one_m = fmaxf(1.0f - cdown * t, 1e-12f);
+		q_eff = cdown * cdown * t / one_m;
+		ld_eff += __logf(one_m);
+	}
+	const float kap = a.kappa0 + (float)n_eff;
+	const float lp = __ldg(a.G + n_eff) - 0.5f * ld_eff - 0.5f * (a.nu0 + (float)n_eff + 1.0f) * log1pf(kap / (kap + 1.0f) * q_eff);
+	return fast_lg2((float)n_eff) + lp * NPB_LOG2E + a2_noise(ka ^ step, kb, (uint32_t)k);
+}
+
+// keys of cluster k for the tile's steps [j_lo, T): B image, 12 MMAs, epilogue
+__device__ __forceinline__ void tc_slot(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, int k, int j_lo, int T, uint32_t s0, uint32_t ka,
+		uint32_t kb, float sx_inv, uint32_t &phase) {
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t base = g_smem_u32(gen);
+	const float *xs = reinterpret_cast<const float *>(gen + S_XS);
+	const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD;
+	float *ktab = reinterpret_cast<float *>(gen + S_KT);
+	const float *Pk = Pc + (size_t)k * TD * TD;
+	// scale of the B operand: P is positive definite, its largest magnitude sits on the diagonal (every warp finds it for itself)
+	const float dmax = redux_max_f32(fmaxf(Pk[lane * (TD + 1)], Pk[(lane + 32) * (TD + 1)]));
+	const int ep = g_scale_exp(dmax);
+	const float sp = ldexpf(1.0f, ep);
+	{
+		const int r = tid >> 2, q = tid & 3; // row of P, 16 of its columns
+		const float4 *src = reinterpret_cast<const float4 *>(Pk + r * TD + 16 * q);
+		float v[16];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const float4 p = src[i];
+			v[4 * i] = p.x; v[4 * i + 1] = p.y; v[4 * i + 2] = p.z; v[4 * i + 3] = p.w;
+		}
+		float mp = 0.0f; // mu'^T P mu', this thread's share
+		__align__(16) __half hi[16], lo[16];
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			mp = fmaf(v[i], mus[16 * q + i], mp);
+			g_split(v[i] * sp, hi[i], lo[i]);
+		}
+		mp *= mus[r];
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			*reinterpret_cast<uint4 *>(gen + S_BHI + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(hi + 8 * h);
+			*reinterpret_cast<uint4 *>(gen + S_BLO + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(lo + 8 * h);
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);
+		if (lane == 0) m->red[warp] = mp;
+	}
+	asm volatile("fence.proxy.async;" ::: "memory"); // the image was written through the generic proxy, the MMA reads through the async one
+	g_tc_fence_before();
+	__syncthreads();
+	if (tid == 0) {
+		g_tc_fence_after();
+		constexpr uint32_t ID = g_idesc(TM, TD);
+#pragma unroll
+		for (int prod = 0; prod < 3; ++prod) {
+			const uint32_t A = base + (prod == 2 ? S_ALO : S_AHI), B = base + (prod == 1 ? S_BLO : S_BHI);
+#pragma unroll
+			for (int ks = 0; ks < 4; ++ks) g_mma_f16(m->tmem, g_desc(A + ks * 32), g_desc(B + ks * 32), ID, (prod | ks) != 0);
+		}
+		g_tc_commit(g_smem_u32(&m->bar));
+	}
+	float mk = 0.0f;
+#pragma unroll
+	for (int w = 0; w < 8; ++w) mk += m->red[w];
+	const float descale = ldexpf(sx_inv, -ep);
+	g_mbar_wait(g_smem_u32(&m->bar), phase);
+	phase ^= 1u;
+	g_tc_fence_after();
+	// epilogue: thread = step (TMEM lane), half of the accumulator's columns per warp group
+	const int wq = warp & 3, half = warp >> 2, j = wq * 32 + lane;
+	float v[32];
+	g_tmem_ld32(m->tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(32 * half), v);
+	float part = 0.0f;
+	const float *xr = xs + j * XSS + 32 * half;
+#pragma unroll
+	for (int i = 0; i < 32; ++i) part = fmaf(v[i], fmaf(-2.0f, mus[32 * half + i], xr[i]), part);
+	if (half) m->tpart[j] = part;
+	g_tc_fence_before();
+	__syncthreads();
+	if (!half && j >= j_lo && j < T) {
+		const float t = fmaxf(fmaf(descale, part + m->tpart[j], mk), 0.0f);
+		ktab[j * 33 + k] = tc_key(a, m, t, j, k, s0 + (uint32_t)j, ka, kb);
+	}
+}
+
+__global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
+	extern __shared__ uint8_t tc_raw[];
+	uint8_t *gen = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
+	const A2Args &a = g.a;
+	TcMisc *m = reinterpret_cast<TcMisc *>(gen + S_MISC);
+	float *xs = reinterpret_cast<float *>(gen + S_XS), *ktab = reinterpret_cast<float *>(gen + S_KT), *mus = reinterpret_cast<float *>(gen + S_MU);
+	const int chain = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int C = a.C, N = a.N;
+	float *Pc = a.P + (size_t)chain * 32 * TD * TD;
+	double *sxc = a.sx + (size_t)chain * 32 * TD, *sxxc = a.sxx + (size_t)chain * 32 * TD * TD;
+
+	if (tid < TD) m->xbar[tid] = (float)g.xbar[tid];
+	if (tid < 32) { m->cnt[tid] = a.counts[(size_t)chain * 32 + tid]; m->ldv[tid] = a.ld[(size_t)chain * 32 + tid]; }
+	if (tid == 0) {
+		g_mbar_init(g_smem_u32(&m->bar), 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async;" ::: "memory");
+	}
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(g_smem_u32(&m->tmem)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	g_tc_fence_after();
+	for (int e = tid; e < 32 * TD; e += 256) mus[e] = a.mu[(size_t)chain * 32 * TD + e] - m->xbar[e & (TD - 1)];
+	const int ex = (int)g.xbar[TD];
+	const float sx = ldexpf(1.0f, ex), sx_inv = ldexpf(1.0f, -ex);
+	int kocc = a.kocc[chain];
+	unsigned long long st_cand = 0ull, st_moved = 0ull, st_births = 0ull; // thread 0's are the ones written back
+	const uint32_t ka = (uint32_t)a.seed ^ 0xA2A2A2A2u, k1 = (uint32_t)(a.seed >> 32) + (uint32_t)chain;
+	const int tile_max = a.tile < 1 ? 1 : (a.tile > TM ? TM : a.tile);
+	int tile = tile_max;
+	uint32_t phase = 0u;
+	__syncthreads();
+
+	for (int sw = 0; sw < a.n_sweeps; ++sw) {
+		const int32_t *order = a.order + (size_t)sw * N;
+		const uint32_t kb = k1 ^ ((a.sweep0 + (uint32_t)sw) * 0x9E3779B9u);
+		for (int s = 0; s < N;) {
+			const int T = min(tile, N - s);
+			if (tid < T) {
+				const int it = order[s + tid];
+				m->items[tid] = it;
+				m->zold[tid] = (int)a.z[(size_t)it * C + chain];
+			}
+			__syncthreads();
+			// ---- A image (FP16 hi / lo, K-major, swizzled) and the FP32 tile of the centred items: thread = (step, 8 coordinates) ----
+			for (int e = tid; e < TM * 8; e += 256) {
+				const int j = e >> 3, q = e & 7;
+				__align__(16) __half hi[8], lo[8];
+				if (j < T) {
+					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)m->items[j] * TD + 8 * q);
+					const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
+					float x[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+					for (int i = 0; i < 8; ++i) {
+						x[i] -= m->xbar[8 * q + i];
+						xs[j * XSS + 8 * q + i] = x[i];
+						g_split(x[i] * sx, hi[i], lo[i]);
+					}
+				} else {
+#pragma unroll
+					for (int i = 0; i < 8; ++i) {
+						hi[i] = lo[i] = __float2half_rn(0.0f);
+						xs[j * XSS + 8 * q + i] = 0.0f;
+					}
+				}
+				*reinterpret_cast<uint4 *>(gen + S_AHI + g_sw128(j, 8 * q)) = *reinterpret_cast<const uint4 *>(hi);
+				*reinterpret_cast<uint4 *>(gen + S_ALO + g_sw128(j, 8 * q)) = *reinterpret_cast<const uint4 *>(lo);
+			}
+			unsigned occ = 0u;
+#pragma unroll
+			for (int k = 0; k < 32; ++k) occ |= m->cnt[k] > 0 ? 1u << k : 0u;
+			// the candidate "a new cluster" (prior predictive, tabulated per item)
+			if (tid < T) ktab[tid * 33 + 32] = a.log2_alpha + __ldg(a.lp0 + m->items[tid]) * NPB_LOG2E + a2_noise(ka ^ (uint32_t)(s + tid), kb, 32u);
+			__syncthreads();
+			for (unsigned rest = occ; rest; rest &= rest - 1) tc_slot(a, gen, m, Pc, __ffs(rest) - 1, 0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+			__syncthreads();
+			int j0 = 0, tile_moves = 0;
+			while (j0 < T) {
+				// ---- winners of the steps not yet final ----
+				for (int j = j0 + warp; j < T; j += 8) {
+					const float key = m->cnt[lane] - (lane == m->zold[j] ? 1 : 0) > 0 ? ktab[j * 33 + lane] : -INFINITY;
+					const float top = fmaxf(redux_max_f32(key), ktab[j * 33 + 32]);
+					const unsigned bal = __ballot_sync(0xffffffffu, key == top && key > -INFINITY);
+					int w = bal ? __ffs(bal) - 1 : 32;
+					if (w == 32) { // a new cluster needs a slot without members once the item is retracted; none: the item stays (code 33)
+						const unsigned fb = __ballot_sync(0xffffffffu, m->cnt[lane] - (lane == m->zold[j] ? 1 : 0) <= 0);
+						if (!fb) w = 33;
+					}
+					if (lane == 0) m->win[j] = w;
+				}
+				__syncthreads();
+				// ---- the first step that does not simply stay ----
+				int jm = T;
+#pragma unroll
+				for (int q = 3; q >= 0; --q) {
+					const int jq = j0 + lane + 32 * q;
+					const unsigned ev = __ballot_sync(0xffffffffu, jq < T && m->win[jq] != m->zold[jq]);
+					if (ev) jm = j0 + 32 * q + __ffs(ev) - 1;
+				}
+				if (warp == 0) { // candidates weighed by the steps now final (the event step included)
+					int cs = 0;
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
+						const int jq = j0 + lane + 32 * q;
+						if (jq <= jm && jq < T) cs += kocc - (m->cnt[m->zold[jq]] == 1 ? 1 : 0) + 1;
+					}
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+					st_cand += (unsigned long long)cs;
+				}
+				if (jm >= T) break;
+				const int w = m->win[jm], src = m->zold[jm], item = m->items[jm];
+				j0 = jm + 1;
+				if (w == 33) { // no room for a new cluster: the item stays, the chain is reported
+					if (tid == 0) a.overflow[chain] = 1;
+					__syncthreads();
+					continue;
+				}
+				// ================= the move (FP32, as in npb_alg2_tile.cu): src loses the item, dst gains it =================
+				const bool born = w == 32;
+				int dst = w;
+				if (born) {
+					dst = 0;
+					while (m->cnt[dst] - (dst == src ? 1 : 0) > 0) ++dst;
+				}
+				const int n_src = m->cnt[src], n_eff = n_src - 1;
+				const bool died = n_eff == 0;
+				const int n_dst = born ? 0 : m->cnt[dst];
+				if (tid < TD) m->dm[tid] = xs[jm * XSS + tid] - mus[src * TD + tid];
+				else if (tid < 2 * TD) m->dm[tid] = xs[jm * XSS + tid - TD] - (born ? a.mu0[tid - TD] - m->xbar[tid - TD] : mus[dst * TD + tid - TD]);
+				else if (tid < 3 * TD) m->xd[tid - 2 * TD] = a.X64[(size_t)item * TD + tid - 2 * TD];
+				if (born) { // the new cluster starts from the prior
+					for (int e = tid; e < TD * TD; e += 256) { Pc[(size_t)dst * TD * TD + e] = __ldg(a.P0 + e); sxxc[(size_t)dst * TD * TD + e] = 0.0; }
+					if (tid < TD) sxc[dst * TD + tid] = 0.0;
+				}
+				__syncthreads();
+				float prod = 0.0f;
+				if (tid < 2 * TD) {
+					const int which = tid / TD, r = tid % TD;
+					if (which == 1 || !died) {
+						const float *Pk = Pc + (size_t)(which ? dst : src) * TD * TD + r;
+						const float *dv = m->dm + which * TD;
+						float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 4
+						for (int c = 0; c < TD; c += 4) {
+							a0 = fmaf(Pk[(c) * TD], dv[c], a0); a1 = fmaf(Pk[(c + 1) * TD], dv[c + 1], a1);
+							a2 = fmaf(Pk[(c + 2) * TD], dv[c + 2], a2); a3 = fmaf(Pk[(c + 3) * TD], dv[c + 3], a3);
+						}
+						const float v = (a0 + a1) + (a2 + a3);
+						m->pu[tid] = v;
+						prod = v * dv[r];
+					}
+				}
+				if (warp < 4) {
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) prod += __shfl_xor_sync(0xffffffffu, prod, o);
+					if (lane == 0) m->red[8 + warp] = prod;
+				}
+				__syncthreads();
+				const float t_s = m->red[8] + m->red[9], t_d = m->red[10] + m->red[11];
+				const float kp = a.kappa0 + (float)n_src, km = kp - 1.0f;
+				const float cdown = kp / km, one_m = fmaxf(1.0f - cdown * t_s, 1e-12f), f_s = cdown / one_m;
+				const float kap = a.kappa0 + (float)n_dst, kap1 = kap + 1.0f;
+				const float cc = kap / kap1, den = 1.0f + cc * t_d, f_d = cc / den;
+				for (int e = tid; e < TD * TD; e += 256) {
+					const int r = e / TD, c = e % TD;
+					if (!died) {
+						float *p = Pc + (size_t)src * TD * TD + e;
+						*p = fmaf(f_s, m->pu[r] * m->pu[c], *p);
+					}
+					float *p2 = Pc + (size_t)dst * TD * TD + e;
+					*p2 = fmaf(-f_d, m->pu[TD + r] * m->pu[TD + c], *p2);
+					const double xx = m->xd[r] * m->xd[c];
+					if (!(died && born && dst == src)) sxxc[(size_t)src * TD * TD + e] -= xx;
+					sxxc[(size_t)dst * TD * TD + e] += xx;
+				}
+				if (tid < TD) {
+					const float x = xs[jm * XSS + tid];
+					if (!died) mus[src * TD + tid] = (kp * mus[src * TD + tid] - x) / km;
+					if (!(died && born && dst == src)) sxc[src * TD + tid] -= m->xd[tid];
+				}
+				__syncthreads();
+				if (tid < TD) {
+					const float x = xs[jm * XSS + tid];
+					const float m0 = born ? a.mu0[tid] - m->xbar[tid] : mus[dst * TD + tid];
+					mus[dst * TD + tid] = (kap * m0 + x) / kap1;
+					sxc[dst * TD + tid] += m->xd[tid];
+				}
+				if (tid == 0) {
+					if (!died) m->ldv[src] += __logf(one_m);
+					m->cnt[src] = n_eff;
+					m->ldv[dst] = (born ? a.ld0 : m->ldv[dst]) + __logf(den);
+					m->cnt[dst] = n_dst + 1;
+					a.z[(size_t)item * C + chain] = (npb_z_t)dst;
+					st_moved++;
+					if (born) st_births++;
+				}
+				kocc += (born ? 1 : 0) - (died ? 1 : 0);
+				++tile_moves;
+				__syncthreads();
+				if (j0 < T) { // the two changed clusters again, for the steps behind the move
+					if (!died) tc_slot(a, gen, m, Pc, src, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+					tc_slot(a, gen, m, Pc, dst, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+					__syncthreads();
+				}
+			}
+			__syncthreads();
+			s += T;
+			// a move costs two more cluster evaluations of the tile: shorter tiles only where that would no longer pay
+			if (tile_moves * 4 > T) tile = max(tile / 2, min(tile_max, 16));
+			else if (tile_moves * 16 <= T) tile = min(tile * 2, tile_max);
+		}
+	}
+	__syncthreads();
+	for (int e = tid; e < 32 * TD; e += 256) a.mu[(size_t)chain * 32 * TD + e] = mus[e] + m->xbar[e & (TD - 1)];
+	if (tid < 32) {
+		a.counts[(size_t)chain * 32 + tid] = m->cnt[tid];
+		a.ld[(size_t)chain * 32 + tid] = m->ldv[tid];
+		const int o = __popc(__ballot_sync(0xffffffffu, m->cnt[tid] > 0));
+		if (tid == 0) {
+			a.kocc[chain] = o;
+			a.st[(size_t)chain * 4 + 0] += st_cand;
+			a.st[(size_t)chain * 4 + 1] += st_moved;
+			a.st[(size_t)chain * 4 + 2] += st_births;
+		}
+	}
+	g_tc_fence_before();
+	__syncthreads();
+	if (warp == 0) {
+		g_tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(m->tmem) : "memory");
+	}
+}
+
+__global__ void k_a2_colmean(const double *X, int64_t N, int D, double *out) { // as k_colmean of npb_alg8_gemm.cu: mean and largest centred magnitude of column blockIdx.x
+	__shared__ double red[256];
+	const int c = blockIdx.x;
+	double s = 0.0;
+	for (int64_t i = threadIdx.x; i < N; i += 256) s += X[i * D + c];
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	const double mean = red[0] / (double)N;
+	__syncthreads();
+	double mx = 0.0;
+	for (int64_t i = threadIdx.x; i < N; i += 256) mx = fmax(mx, fabs(X[i * D + c] - mean));
+	red[threadIdx.x] = mx;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { out[c] = mean; out[D + 1 + c] = red[0]; }
+}
+__global__ void k_a2_xscale(double *out, int D) {
+	double mx = 0.0;
+	for (int c = 0; c < D; ++c) mx = fmax(mx, out[D + 1 + c]);
+	out[D] = (double)g_scale_exp((float)mx);
+}
+
+} // namespace
+
+npb_status npb_launch_a2_tc(npb_chains *ch, const A2Args &a) {
+	npb_ctx *ctx = ch->ctx;
+	npb_dataset *ds = ch->ds;
+	if (ch->D != TD) return npb_fail(ctx, NPB_E_UNSUPPORTED, "the tensor-core conjugate Algorithm 2 kernel covers D = 64");
+	if (!ds->Xbar) NPB_CUDA_OK(cudaMalloc((void **)&ds->Xbar, sizeof(double) * (2 * TD + 1)));
+	if (!ds->xbar_valid) { // the same contents the D = 64 Algorithm 8 path keeps there
+		ds->xbar_valid = true;
+		k_a2_colmean<<<TD, 256, 0, ctx->stream>>>(ds->X64, ds->N, TD, ds->Xbar);
+		NPB_CUDA_OK(cudaGetLastError());
+		k_a2_xscale<<<1, 1, 0, ctx->stream>>>(ds->Xbar, TD);
+		NPB_CUDA_OK(cudaGetLastError());
+	}
+	if (!ctx->a2_tc_attr_set) {
+		NPB_CUDA_OK(cudaFuncSetAttribute(k_a2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+		ctx->a2_tc_attr_set = true;
+	}
+	TcArgs g;
+	g.a = a;
+	g.xbar = ds->Xbar;
+	k_a2_tc<<<(unsigned)ch->C, 256, TC_SMEM, ctx->stream>>>(g);
+	NPB_CUDA_OK(cudaGetLastError());
+	return NPB_OK;
+}

@@ -122,8 +122,8 @@ def test_distribution_against_oracle(npb, ctx, oracle, which, T, seeds):
     ds.close()
 
 
-@pytest.mark.parametrize("D,N,K0", [(16, 900, 10), (64, 500, 8)])
-def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0):
+@pytest.mark.parametrize("D,N,K0,tc", [(16, 900, 10, 1), (64, 500, 8, 1), (64, 500, 8, 0)])
+def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0, tc):
     """k_a2_tile (npb_alg2_tile.cu) evaluates up to 64 steps ahead of the chain and corrects the two changed columns after every
     move: the assignments, counts and FP64 statistics must equal those of the strictly sequential schedule (a2_tile = 1) bit for
     bit, from a start where most items move (K0 random clusters) to the settled chain"""
@@ -131,9 +131,10 @@ def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0):
     ds = npb.Dataset(ctx, X)
     npb.NormalInverseWishart(**conj_prior(X)).bind(ctx)
     res = {}
-    for tile in (1, 8, 64):
+    for tile in (1, 8, 64, 128):
         ch = npb.Chains(ctx, ds, 7, Kmax=32, K0=K0, seed=21)
         ch.set_option("a2_tile", str(tile))
+        ch.set_option("a2_tc", str(tc))  # D = 64: the tcgen05 kernel k_a2_tc (tiles of up to 128 steps) or the FP32 tile kernel (up to 64)
         moved = births = 0
         zs = []
         for _ in range(3):
@@ -145,13 +146,13 @@ def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0):
         res[tile] = (zs, moved, births, st.candidates, [ch.alg2_suffstats(c) for c in (0, 6)])
         ch.close()
     assert res[1][1] > 2 * N  # items moved: the correction path ran
-    for tile in (8, 64):
+    for tile in (8, 64, 128):
         for a, b in zip(res[1][0], res[tile][0]):
             assert np.array_equal(a, b), tile
         assert res[1][1:4] == res[tile][1:4], tile
         for (n0, sx0, sxx0), (n1, sx1, sxx1) in zip(res[1][4], res[tile][4]):
             assert np.array_equal(n0, n1) and np.array_equal(sx0[n0 > 0], sx1[n1 > 0]) and np.array_equal(sxx0[n0 > 0], sxx1[n1 > 0])
-    print("D = %d: tiles of 1, 8, 64 steps give the same chain (%d moves, %d births over 6 sweeps of 7 chains)" % (D, res[1][1], res[1][2]))
+    print("D = %d: tiles of 1, 8, 64, 128 steps give the same chain (%d moves, %d births over 6 sweeps of 7 chains)" % (D, res[1][1], res[1][2]))
     ds.close()
 
 
@@ -175,8 +176,8 @@ def test_step_at_a_time_kernel_still_follows_the_moves(npb, ctx, D, N):
     ds.close()
 
 
-@pytest.mark.parametrize("D,N", [(16, 800), (64, 500)])
-def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N):
+@pytest.mark.parametrize("D,N,tc", [(16, 800, 1), (64, 500, 1), (64, 500, 0)])
+def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N, tc):
     """k_a2_tile's quadratic forms (register-blocked products) against k_a2_sweep's row dots: the two
     kernels draw the same race noise, so from the same state one sweep must make the same decisions except where two keys lie within
     the FP32 rounding of the forms (~1e-6 relative); an error of 1e-4 in a form would flip a visible share of the steps"""
@@ -190,6 +191,7 @@ def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N):
     for tile in (0, 64):
         ch = npb.Chains(ctx, ds, 6, Kmax=32, K0=6, seed=31)
         ch.set_option("a2_tile", str(tile))
+        ch.set_option("a2_tc", str(tc))
         for c in range(6):
             slots = np.unique(zs[c]).astype(np.int32)
             ch.set_state(c, zs[c], slots, np.zeros((len(slots), D)), np.tile(np.eye(D), (len(slots), 1, 1)))
