@@ -42,6 +42,7 @@ struct TcMisc {
 	float dm[2 * TD], pu[2 * TD];
 	float tpart[TM];
 	float xbar[TD];
+	float pmax[32];      // largest diagonal element of every cluster's P (the scale of its B operand)
 	uint32_t tmem;
 };
 constexpr uint32_t TC_SMEM = S_MISC + sizeof(TcMisc) + 1024; // + alignment slack
@@ -69,25 +70,29 @@ __device__ __forceinline__ float tc_key(const A2Args &a, const TcMisc *m, float 
 }
 
 // keys of cluster k for the tile's steps [j_lo, T): B image, 12 MMAs, epilogue
-__device__ __forceinline__ void tc_slot(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, int k, int j_lo, int T, uint32_t s0, uint32_t ka,
-		uint32_t kb, float sx_inv, uint32_t &phase) {
+// pf: this thread's 16 values of P_k (row tid / 4, columns 16 (tid % 4) ...), loaded by the previous call (or by tc_load); knext: the cluster
+// the NEXT call will evaluate (-1: none) -- its values are fetched while this call's MMAs run
+__device__ __forceinline__ void tc_load(const float *Pc, int k, float4 (&pf)[4]) {
+	const float4 *src = reinterpret_cast<const float4 *>(Pc + (size_t)k * TD * TD + (threadIdx.x >> 2) * TD + 16 * (threadIdx.x & 3));
+#pragma unroll
+	for (int i = 0; i < 4; ++i) pf[i] = src[i];
+}
+__device__ __forceinline__ void tc_slot(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, int k, int knext, float4 (&pf)[4], int j_lo, int T,
+		uint32_t s0, uint32_t ka, uint32_t kb, float sx_inv, uint32_t &phase) {
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t base = g_smem_u32(gen);
 	const float *xs = reinterpret_cast<const float *>(gen + S_XS);
 	const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD;
 	float *ktab = reinterpret_cast<float *>(gen + S_KT);
-	const float *Pk = Pc + (size_t)k * TD * TD;
-	// scale of the B operand: P is positive definite, its largest magnitude sits on the diagonal (every warp finds it for itself)
-	const float dmax = redux_max_f32(fmaxf(Pk[lane * (TD + 1)], Pk[(lane + 32) * (TD + 1)]));
-	const int ep = g_scale_exp(dmax);
+	// scale of the B operand: P is positive definite, its largest magnitude sits on the diagonal (kept per cluster in pmax)
+	const int ep = g_scale_exp(m->pmax[k]);
 	const float sp = ldexpf(1.0f, ep);
 	{
 		const int r = tid >> 2, q = tid & 3; // row of P, 16 of its columns
-		const float4 *src = reinterpret_cast<const float4 *>(Pk + r * TD + 16 * q);
 		float v[16];
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			const float4 p = src[i];
+			const float4 p = pf[i];
 			v[4 * i] = p.x; v[4 * i + 1] = p.y; v[4 * i + 2] = p.z; v[4 * i + 3] = p.w;
 		}
 		float mp = 0.0f; // mu'^T P mu', this thread's share
@@ -121,6 +126,7 @@ __device__ __forceinline__ void tc_slot(const A2Args &a, uint8_t *gen, TcMisc *m
 		}
 		g_tc_commit(g_smem_u32(&m->bar));
 	}
+	if (knext >= 0) tc_load(Pc, knext, pf);
 	float mk = 0.0f;
 #pragma unroll
 	for (int w = 0; w < 8; ++w) mk += m->red[w];
@@ -171,6 +177,11 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	__syncthreads();
 	g_tc_fence_after();
 	for (int e = tid; e < 32 * TD; e += 256) mus[e] = a.mu[(size_t)chain * 32 * TD + e] - m->xbar[e & (TD - 1)];
+	for (int k = warp; k < 32; k += 8) {
+		const float *Pk = Pc + (size_t)k * TD * TD;
+		const float d = redux_max_f32(fmaxf(Pk[lane * (TD + 1)], Pk[(lane + 32) * (TD + 1)]));
+		if (lane == 0) m->pmax[k] = d;
+	}
 	const int ex = (int)g.xbar[TD];
 	const float sx = ldexpf(1.0f, ex), sx_inv = ldexpf(1.0f, -ex);
 	int kocc = a.kocc[chain];
@@ -222,7 +233,14 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 			// the candidate "a new cluster" (prior predictive, tabulated per item)
 			if (tid < T) ktab[tid * 33 + 32] = a.log2_alpha + __ldg(a.lp0 + m->items[tid]) * NPB_LOG2E + a2_noise(ka ^ (uint32_t)(s + tid), kb, 32u);
 			__syncthreads();
-			for (unsigned rest = occ; rest; rest &= rest - 1) tc_slot(a, gen, m, Pc, __ffs(rest) - 1, 0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+			{
+				float4 pf[4];
+				if (occ) tc_load(Pc, __ffs(occ) - 1, pf);
+				for (unsigned rest = occ; rest; rest &= rest - 1) {
+					const unsigned nx = rest & (rest - 1);
+					tc_slot(a, gen, m, Pc, __ffs(rest) - 1, nx ? __ffs(nx) - 1 : -1, pf, 0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+				}
+			}
 			__syncthreads();
 			int j0 = 0, tile_moves = 0;
 			while (j0 < T) {
@@ -348,9 +366,17 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 				kocc += (born ? 1 : 0) - (died ? 1 : 0);
 				++tile_moves;
 				__syncthreads();
+				if (warp < 2) { // the two changed diagonals
+					const float *Pk = Pc + (size_t)(warp ? dst : src) * TD * TD;
+					const float d = redux_max_f32(fmaxf(Pk[lane * (TD + 1)], Pk[(lane + 32) * (TD + 1)]));
+					if (lane == 0) m->pmax[warp ? dst : src] = d;
+				}
+				__syncthreads();
 				if (j0 < T) { // the two changed clusters again, for the steps behind the move
-					if (!died) tc_slot(a, gen, m, Pc, src, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
-					tc_slot(a, gen, m, Pc, dst, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+					float4 pf[4];
+					tc_load(Pc, died ? dst : src, pf);
+					if (!died) tc_slot(a, gen, m, Pc, src, dst, pf, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+					tc_slot(a, gen, m, Pc, dst, -1, pf, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
 					__syncthreads();
 				}
 			}
