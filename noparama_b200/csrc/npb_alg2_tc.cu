@@ -14,8 +14,9 @@
 // changed clusters are simply evaluated again.  Same schedule-independence as the FP32 tile kernel: a row of the product depends
 // only on its own item and the cluster's state, so a.tile = 1 ... 128 give the same chain bit for bit.
 //
-// One CTA of 8 warps per chain, two CTAs per SM (112 KB of shared memory, 64 TMEM columns, <= 128 registers).  Per cluster: all
-// threads build the B image; one thread issues the 12 MMAs and commits to an mbarrier; all wait; all read TMEM.
+// One CTA of 8 warps per chain, two CTAs per SM (96 KB of shared memory, 128 TMEM columns = two accumulators, <= 128 registers).
+// Per cluster: all threads build the B image (two buffers: cluster k + 1 is built and issued while k's MMAs run); one thread issues
+// the 12 MMAs and commits to an mbarrier; all wait; all read TMEM and their own row of the A image.
 #include "npb_alg2.cuh"
 #include "npb_tc_common.cuh"
 
@@ -25,20 +26,22 @@ namespace {
 
 constexpr int TD = 64;    // dimension
 constexpr int TM = 128;   // steps per tile = UMMA M
-constexpr int XSS = 65;   // row stride of the FP32 item tile (a thread walks its own row: conflict-free)
-constexpr uint32_t S_AHI = 0, S_ALO = 16384, S_BHI = 32768, S_BLO = 40960, S_XS = 49152;
-constexpr uint32_t S_KT = S_XS + TM * XSS * 4;   // [TM][33] race keys
-constexpr uint32_t S_MU = S_KT + TM * 33 * 4;    // [32][64] centred means
+constexpr uint32_t S_AHI = 0, S_ALO = 16384;            // A image of the tile: 128 rows x 128 bytes, hi then lo
+constexpr uint32_t S_B = 32768, S_BSZ = 16384;          // two B images (hi 8 KB, lo 8 KB each): cluster k + 1 is built while k's MMAs run
+constexpr uint32_t S_KT = S_B + 2 * S_BSZ;              // [TM][33] race keys
+constexpr uint32_t S_MU = S_KT + TM * 33 * 4;           // [32][64] centred means
 constexpr uint32_t S_MISC = S_MU + 32 * TD * 4;
 
 struct TcMisc {
 	double xd[TD];       // the moving item in FP64
-	unsigned long long bar;
+	unsigned long long bar[2];
 	float ldv[32];
 	int cnt[32];
 	int zold[TM], items[TM], win[TM];
 	int slist[36];
-	float red[16];
+	float red[2][8];     // shares of mu'^T P mu' per warp, per B buffer
+	float red2[4];
+	float xm[TD];        // the moving item, centred
 	float dm[2 * TD], pu[2 * TD];
 	float tpart[TM];
 	float xbar[TD];
@@ -69,94 +72,123 @@ __device__ __forceinline__ float tc_key(const A2Args &a, const TcMisc *m, float 
 	return fast_lg2((float)n_eff) + lp * NPB_LOG2E + a2_noise(ka ^ step, kb, (uint32_t)k);
 }
 
-// keys of cluster k for the tile's steps [j_lo, T): B image, 12 MMAs, epilogue
-// pf: this thread's 16 values of P_k (row tid / 4, columns 16 (tid % 4) ...), loaded by the previous call (or by tc_load); knext: the cluster
-// the NEXT call will evaluate (-1: none) -- its values are fetched while this call's MMAs run
+// this thread's 16 values of P_k: row tid / 4, columns 16 (tid % 4) ...
 __device__ __forceinline__ void tc_load(const float *Pc, int k, float4 (&pf)[4]) {
 	const float4 *src = reinterpret_cast<const float4 *>(Pc + (size_t)k * TD * TD + (threadIdx.x >> 2) * TD + 16 * (threadIdx.x & 3));
 #pragma unroll
 	for (int i = 0; i < 4; ++i) pf[i] = src[i];
 }
-__device__ __forceinline__ void tc_slot(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, int k, int knext, float4 (&pf)[4], int j_lo, int T,
-		uint32_t s0, uint32_t ka, uint32_t kb, float sx_inv, uint32_t &phase) {
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t base = g_smem_u32(gen);
-	const float *xs = reinterpret_cast<const float *>(gen + S_XS);
+// B image of cluster k (from pf) into buffer b, and this warp's share of mu'^T P mu'
+__device__ __forceinline__ void tc_build(uint8_t *gen, TcMisc *m, int k, int b, const float4 (&pf)[4]) {
+	const int tid = threadIdx.x, r = tid >> 2, q = tid & 3;
 	const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD;
-	float *ktab = reinterpret_cast<float *>(gen + S_KT);
-	// scale of the B operand: P is positive definite, its largest magnitude sits on the diagonal (kept per cluster in pmax)
-	const int ep = g_scale_exp(m->pmax[k]);
-	const float sp = ldexpf(1.0f, ep);
-	{
-		const int r = tid >> 2, q = tid & 3; // row of P, 16 of its columns
-		float v[16];
+	const float sp = ldexpf(1.0f, g_scale_exp(m->pmax[k])); // P is positive definite: its largest magnitude sits on the diagonal
+	float v[16];
 #pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			const float4 p = pf[i];
-			v[4 * i] = p.x; v[4 * i + 1] = p.y; v[4 * i + 2] = p.z; v[4 * i + 3] = p.w;
-		}
-		float mp = 0.0f; // mu'^T P mu', this thread's share
-		__align__(16) __half hi[16], lo[16];
+	for (int i = 0; i < 4; ++i) { v[4 * i] = pf[i].x; v[4 * i + 1] = pf[i].y; v[4 * i + 2] = pf[i].z; v[4 * i + 3] = pf[i].w; }
+	float mp = 0.0f;
+	__align__(16) __half hi[16], lo[16];
 #pragma unroll
-		for (int i = 0; i < 16; ++i) {
-			mp = fmaf(v[i], mus[16 * q + i], mp);
-			g_split(v[i] * sp, hi[i], lo[i]);
-		}
-		mp *= mus[r];
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			*reinterpret_cast<uint4 *>(gen + S_BHI + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(hi + 8 * h);
-			*reinterpret_cast<uint4 *>(gen + S_BLO + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(lo + 8 * h);
-		}
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);
-		if (lane == 0) m->red[warp] = mp;
+	for (int i = 0; i < 16; ++i) {
+		mp = fmaf(v[i], mus[16 * q + i], mp);
+		g_split(v[i] * sp, hi[i], lo[i]);
 	}
-	asm volatile("fence.proxy.async;" ::: "memory"); // the image was written through the generic proxy, the MMA reads through the async one
-	g_tc_fence_before();
-	__syncthreads();
-	if (tid == 0) {
-		g_tc_fence_after();
-		constexpr uint32_t ID = g_idesc(TM, TD);
+	mp *= mus[r];
+	uint8_t *B = gen + S_B + b * S_BSZ;
 #pragma unroll
-		for (int prod = 0; prod < 3; ++prod) {
-			const uint32_t A = base + (prod == 2 ? S_ALO : S_AHI), B = base + (prod == 1 ? S_BLO : S_BHI);
-#pragma unroll
-			for (int ks = 0; ks < 4; ++ks) g_mma_f16(m->tmem, g_desc(A + ks * 32), g_desc(B + ks * 32), ID, (prod | ks) != 0);
-		}
-		g_tc_commit(g_smem_u32(&m->bar));
+	for (int h = 0; h < 2; ++h) {
+		*reinterpret_cast<uint4 *>(B + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(hi + 8 * h);
+		*reinterpret_cast<uint4 *>(B + 8192 + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(lo + 8 * h);
 	}
-	if (knext >= 0) tc_load(Pc, knext, pf);
-	float mk = 0.0f;
 #pragma unroll
-	for (int w = 0; w < 8; ++w) mk += m->red[w];
-	const float descale = ldexpf(sx_inv, -ep);
-	g_mbar_wait(g_smem_u32(&m->bar), phase);
-	phase ^= 1u;
+	for (int o = 16; o > 0; o >>= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);
+	if ((tid & 31) == 0) m->red[b][tid >> 5] = mp;
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // written through the generic proxy, read by the MMA through the async one
+}
+// the 12 MMAs of one cluster: accumulator b (64 TMEM columns), B buffer b; completion arrives on bar[b]
+__device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, int b) {
 	g_tc_fence_after();
-	// epilogue: thread = step (TMEM lane), half of the accumulator's columns per warp group
-	const int wq = warp & 3, half = warp >> 2, j = wq * 32 + lane;
-	float v[32];
-	g_tmem_ld32(m->tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(32 * half), v);
-	float part = 0.0f;
-	const float *xr = xs + j * XSS + 32 * half;
+	const uint32_t base = g_smem_u32(gen), Bb = base + S_B + b * S_BSZ;
+	constexpr uint32_t ID = g_idesc(TM, TD);
 #pragma unroll
-	for (int i = 0; i < 32; ++i) part = fmaf(v[i], fmaf(-2.0f, mus[32 * half + i], xr[i]), part);
-	if (half) m->tpart[j] = part;
+	for (int prod = 0; prod < 3; ++prod) {
+		const uint32_t A = base + (prod == 2 ? S_ALO : S_AHI), B = Bb + (prod == 1 ? 8192u : 0u);
+#pragma unroll
+		for (int ks = 0; ks < 4; ++ks) g_mma_f16(m->tmem + 64u * b, g_desc(A + ks * 32), g_desc(B + ks * 32), ID, (prod | ks) != 0);
+	}
+	g_tc_commit(g_smem_u32(&m->bar[b]));
+}
+// The race keys of the clusters in `mask` for the tile's steps [j_lo, T).  Software pipeline over the clusters: while the MMAs of
+// cluster k run, the B image of the next one is built into the other buffer and its MMAs are issued into the other accumulator;
+// then k's accumulator is read -- thread = step = TMEM lane, half of its 64 columns per warp group -- against the step's own row
+// of the A image (x' = (hi + lo) / scale: the very operand the MMA saw) and the cluster's mean.
+__device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, unsigned mask, int j_lo, int T, uint32_t s0,
+		uint32_t ka, uint32_t kb, float sx_inv, uint32_t (&phase)[2]) {
+	if (!mask) return;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int wq = warp & 3, half = warp >> 2, j = wq * 32 + lane;
+	float *ktab = reinterpret_cast<float *>(gen + S_KT);
+	float4 pf[4];
+	int k = __ffs(mask) - 1;
+	mask &= mask - 1;
+	tc_load(Pc, k, pf);
+	tc_build(gen, m, k, 0, pf);
+	if (mask) tc_load(Pc, __ffs(mask) - 1, pf);
 	g_tc_fence_before();
 	__syncthreads();
-	if (!half && j >= j_lo && j < T) {
-		const float t = fmaxf(fmaf(descale, part + m->tpart[j], mk), 0.0f);
-		ktab[j * 33 + k] = tc_key(a, m, t, j, k, s0 + (uint32_t)j, ka, kb);
+	if (tid == 0) tc_issue(gen, m, 0);
+	for (int b = 0;; b ^= 1) {
+		const int knext = mask ? __ffs(mask) - 1 : -1;
+		mask &= mask - 1;
+		if (knext >= 0) {
+			tc_build(gen, m, knext, b ^ 1, pf);
+			if (mask) tc_load(Pc, __ffs(mask) - 1, pf);
+		}
+		g_tc_fence_before();
+		__syncthreads(); // the other B image is complete; the other accumulator has been read (previous round)
+		if (knext >= 0 && tid == 0) tc_issue(gen, m, b ^ 1);
+		float mk = 0.0f;
+#pragma unroll
+		for (int w = 0; w < 8; ++w) mk += m->red[b][w];
+		const float descale = ldexpf(sx_inv, -g_scale_exp(m->pmax[k]));
+		const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD + 32 * half;
+		g_mbar_wait(g_smem_u32(&m->bar[b]), phase[b]);
+		phase[b] ^= 1u;
+		g_tc_fence_after();
+		float v[32];
+		g_tmem_ld32(m->tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * b + 32 * half), v);
+		float part = 0.0f;
+#pragma unroll
+		for (int c8 = 0; c8 < 4; ++c8) { // 8 coordinates per 16-byte chunk of the row, chunks swizzled by the row
+			const uint32_t off = (uint32_t)j * 128u + ((((uint32_t)(4 * half + c8)) ^ ((uint32_t)j & 7u)) << 4);
+			const uint4 h4 = *reinterpret_cast<const uint4 *>(gen + S_AHI + off), l4 = *reinterpret_cast<const uint4 *>(gen + S_ALO + off);
+			const __half2 *hh = reinterpret_cast<const __half2 *>(&h4), *ll = reinterpret_cast<const __half2 *>(&l4);
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+				const int c = 8 * c8 + 2 * e;
+				part = fmaf(v[c], fmaf(fh.x + fl.x, sx_inv, -2.0f * mus[c]), part);
+				part = fmaf(v[c + 1], fmaf(fh.y + fl.y, sx_inv, -2.0f * mus[c + 1]), part);
+			}
+		}
+		if (half) m->tpart[j] = part;
+		g_tc_fence_before();
+		__syncthreads();
+		if (!half && j >= j_lo && j < T) {
+			const float t = fmaxf(fmaf(descale, part + m->tpart[j], mk), 0.0f);
+			ktab[j * 33 + k] = tc_key(a, m, t, j, k, s0 + (uint32_t)j, ka, kb);
+		}
+		if (knext < 0) break;
+		k = knext;
 	}
 }
 
 __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	extern __shared__ uint8_t tc_raw[];
-	uint8_t *gen = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
+	uint8_t *gen = tc_raw + ((1024u - (g_smem_u32(tc_raw) & 1023u)) & 1023u); // 1024-aligned, and still known to be shared memory
 	const A2Args &a = g.a;
 	TcMisc *m = reinterpret_cast<TcMisc *>(gen + S_MISC);
-	float *xs = reinterpret_cast<float *>(gen + S_XS), *ktab = reinterpret_cast<float *>(gen + S_KT), *mus = reinterpret_cast<float *>(gen + S_MU);
+	float *ktab = reinterpret_cast<float *>(gen + S_KT), *mus = reinterpret_cast<float *>(gen + S_MU);
 	const int chain = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int C = a.C, N = a.N;
 	float *Pc = a.P + (size_t)chain * 32 * TD * TD;
@@ -165,12 +197,13 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	if (tid < TD) m->xbar[tid] = (float)g.xbar[tid];
 	if (tid < 32) { m->cnt[tid] = a.counts[(size_t)chain * 32 + tid]; m->ldv[tid] = a.ld[(size_t)chain * 32 + tid]; }
 	if (tid == 0) {
-		g_mbar_init(g_smem_u32(&m->bar), 1);
+		g_mbar_init(g_smem_u32(&m->bar[0]), 1);
+		g_mbar_init(g_smem_u32(&m->bar[1]), 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async;" ::: "memory");
 	}
 	if (warp == 0) {
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(g_smem_u32(&m->tmem)) : "memory");
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(g_smem_u32(&m->tmem)) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
 	g_tc_fence_before();
@@ -189,7 +222,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	const uint32_t ka = (uint32_t)a.seed ^ 0xA2A2A2A2u, k1 = (uint32_t)(a.seed >> 32) + (uint32_t)chain;
 	const int tile_max = a.tile < 1 ? 1 : (a.tile > TM ? TM : a.tile);
 	int tile = tile_max;
-	uint32_t phase = 0u;
+	uint32_t phase[2] = {0u, 0u};
 	__syncthreads();
 
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
@@ -203,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 				m->zold[tid] = (int)a.z[(size_t)it * C + chain];
 			}
 			__syncthreads();
-			// ---- A image (FP16 hi / lo, K-major, swizzled) and the FP32 tile of the centred items: thread = (step, 8 coordinates) ----
+			// ---- A image (FP16 hi / lo, K-major, swizzled) of the centred items: thread = (step, 8 coordinates) ----
 			for (int e = tid; e < TM * 8; e += 256) {
 				const int j = e >> 3, q = e & 7;
 				__align__(16) __half hi[8], lo[8];
@@ -212,17 +245,10 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 					const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
 					float x[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-					for (int i = 0; i < 8; ++i) {
-						x[i] -= m->xbar[8 * q + i];
-						xs[j * XSS + 8 * q + i] = x[i];
-						g_split(x[i] * sx, hi[i], lo[i]);
-					}
+					for (int i = 0; i < 8; ++i) g_split((x[i] - m->xbar[8 * q + i]) * sx, hi[i], lo[i]);
 				} else {
 #pragma unroll
-					for (int i = 0; i < 8; ++i) {
-						hi[i] = lo[i] = __float2half_rn(0.0f);
-						xs[j * XSS + 8 * q + i] = 0.0f;
-					}
+					for (int i = 0; i < 8; ++i) hi[i] = lo[i] = __float2half_rn(0.0f);
 				}
 				*reinterpret_cast<uint4 *>(gen + S_AHI + g_sw128(j, 8 * q)) = *reinterpret_cast<const uint4 *>(hi);
 				*reinterpret_cast<uint4 *>(gen + S_ALO + g_sw128(j, 8 * q)) = *reinterpret_cast<const uint4 *>(lo);
@@ -233,14 +259,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 			// the candidate "a new cluster" (prior predictive, tabulated per item)
 			if (tid < T) ktab[tid * 33 + 32] = a.log2_alpha + __ldg(a.lp0 + m->items[tid]) * NPB_LOG2E + a2_noise(ka ^ (uint32_t)(s + tid), kb, 32u);
 			__syncthreads();
-			{
-				float4 pf[4];
-				if (occ) tc_load(Pc, __ffs(occ) - 1, pf);
-				for (unsigned rest = occ; rest; rest &= rest - 1) {
-					const unsigned nx = rest & (rest - 1);
-					tc_slot(a, gen, m, Pc, __ffs(rest) - 1, nx ? __ffs(nx) - 1 : -1, pf, 0, T, (uint32_t)s, ka, kb, sx_inv, phase);
-				}
-			}
+			tc_pass(a, gen, m, Pc, occ, 0, T, (uint32_t)s, ka, kb, sx_inv, phase);
 			__syncthreads();
 			int j0 = 0, tile_moves = 0;
 			while (j0 < T) {
@@ -294,8 +313,11 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 				const int n_src = m->cnt[src], n_eff = n_src - 1;
 				const bool died = n_eff == 0;
 				const int n_dst = born ? 0 : m->cnt[dst];
-				if (tid < TD) m->dm[tid] = xs[jm * XSS + tid] - mus[src * TD + tid];
-				else if (tid < 2 * TD) m->dm[tid] = xs[jm * XSS + tid - TD] - (born ? a.mu0[tid - TD] - m->xbar[tid - TD] : mus[dst * TD + tid - TD]);
+				if (tid < TD) {
+					const float x = __ldg(a.X + (size_t)item * TD + tid) - m->xbar[tid];
+					m->xm[tid] = x;
+					m->dm[tid] = x - mus[src * TD + tid];
+				} else if (tid < 2 * TD) m->dm[tid] = (__ldg(a.X + (size_t)item * TD + tid - TD) - m->xbar[tid - TD]) - (born ? a.mu0[tid - TD] - m->xbar[tid - TD] : mus[dst * TD + tid - TD]);
 				else if (tid < 3 * TD) m->xd[tid - 2 * TD] = a.X64[(size_t)item * TD + tid - 2 * TD];
 				if (born) { // the new cluster starts from the prior
 					for (int e = tid; e < TD * TD; e += 256) { Pc[(size_t)dst * TD * TD + e] = __ldg(a.P0 + e); sxxc[(size_t)dst * TD * TD + e] = 0.0; }
@@ -322,10 +344,10 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 				if (warp < 4) {
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1) prod += __shfl_xor_sync(0xffffffffu, prod, o);
-					if (lane == 0) m->red[8 + warp] = prod;
+					if (lane == 0) m->red2[warp] = prod;
 				}
 				__syncthreads();
-				const float t_s = m->red[8] + m->red[9], t_d = m->red[10] + m->red[11];
+				const float t_s = m->red2[0] + m->red2[1], t_d = m->red2[2] + m->red2[3];
 				const float kp = a.kappa0 + (float)n_src, km = kp - 1.0f;
 				const float cdown = kp / km, one_m = fmaxf(1.0f - cdown * t_s, 1e-12f), f_s = cdown / one_m;
 				const float kap = a.kappa0 + (float)n_dst, kap1 = kap + 1.0f;
@@ -343,13 +365,13 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 					sxxc[(size_t)dst * TD * TD + e] += xx;
 				}
 				if (tid < TD) {
-					const float x = xs[jm * XSS + tid];
+					const float x = m->xm[tid];
 					if (!died) mus[src * TD + tid] = (kp * mus[src * TD + tid] - x) / km;
 					if (!(died && born && dst == src)) sxc[src * TD + tid] -= m->xd[tid];
 				}
 				__syncthreads();
 				if (tid < TD) {
-					const float x = xs[jm * XSS + tid];
+					const float x = m->xm[tid];
 					const float m0 = born ? a.mu0[tid] - m->xbar[tid] : mus[dst * TD + tid];
 					mus[dst * TD + tid] = (kap * m0 + x) / kap1;
 					sxc[dst * TD + tid] += m->xd[tid];
@@ -373,10 +395,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 				}
 				__syncthreads();
 				if (j0 < T) { // the two changed clusters again, for the steps behind the move
-					float4 pf[4];
-					tc_load(Pc, died ? dst : src, pf);
-					if (!died) tc_slot(a, gen, m, Pc, src, dst, pf, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
-					tc_slot(a, gen, m, Pc, dst, -1, pf, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
+					tc_pass(a, gen, m, Pc, (died ? 0u : 1u << src) | 1u << dst, j0, T, (uint32_t)s, ka, kb, sx_inv, phase);
 					__syncthreads();
 				}
 			}
@@ -404,7 +423,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	__syncthreads();
 	if (warp == 0) {
 		g_tc_fence_after();
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(m->tmem) : "memory");
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(m->tmem) : "memory");
 	}
 }
 
