@@ -30,7 +30,8 @@ constexpr uint32_t S_AHI = 0, S_ALO = 16384;            // A image of the tile: 
 constexpr uint32_t S_B = 32768, S_BSZ = 16384;          // two B images (hi 8 KB, lo 8 KB each): cluster k + 1 is built while k's MMAs run
 constexpr uint32_t S_KT = S_B + 2 * S_BSZ;              // [TM][33] race keys
 constexpr uint32_t S_MU = S_KT + TM * 33 * 4;           // [32][64] centred means
-constexpr uint32_t S_MISC = S_MU + 32 * TD * 4;
+constexpr uint32_t S_M2 = S_MU + 32 * TD * 4;           // [32][64] -2 2^ex mu': what the epilogue adds to the scaled item
+constexpr uint32_t S_MISC = S_M2 + 32 * TD * 4;
 
 struct TcMisc {
 	double xd[TD];       // the moving item in FP64
@@ -72,33 +73,30 @@ __device__ __forceinline__ float tc_key(const A2Args &a, const TcMisc *m, float 
 	return fast_lg2((float)n_eff) + lp * NPB_LOG2E + a2_noise(ka ^ step, kb, (uint32_t)k);
 }
 
-// this thread's 16 values of P_k: row tid / 4, columns 16 (tid % 4) ...
+// this thread's 16 values of P_k, coalesced: float4 number i 256 + tid of the matrix, i = 0..3 = row 16 i + tid / 16, columns 4 (tid % 16) ...
 __device__ __forceinline__ void tc_load(const float *Pc, int k, float4 (&pf)[4]) {
-	const float4 *src = reinterpret_cast<const float4 *>(Pc + (size_t)k * TD * TD + (threadIdx.x >> 2) * TD + 16 * (threadIdx.x & 3));
+	const float4 *src = reinterpret_cast<const float4 *>(Pc + (size_t)k * TD * TD) + threadIdx.x;
 #pragma unroll
-	for (int i = 0; i < 4; ++i) pf[i] = src[i];
+	for (int i = 0; i < 4; ++i) pf[i] = src[i * 256];
 }
 // B image of cluster k (from pf) into buffer b, and this warp's share of mu'^T P mu'
 __device__ __forceinline__ void tc_build(uint8_t *gen, TcMisc *m, int k, int b, const float4 (&pf)[4]) {
-	const int tid = threadIdx.x, r = tid >> 2, q = tid & 3;
+	const int tid = threadIdx.x, r0 = tid >> 4, c0 = 4 * (tid & 15);
 	const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD;
 	const float sp = ldexpf(1.0f, g_scale_exp(m->pmax[k])); // P is positive definite: its largest magnitude sits on the diagonal
-	float v[16];
-#pragma unroll
-	for (int i = 0; i < 4; ++i) { v[4 * i] = pf[i].x; v[4 * i + 1] = pf[i].y; v[4 * i + 2] = pf[i].z; v[4 * i + 3] = pf[i].w; }
-	float mp = 0.0f;
-	__align__(16) __half hi[16], lo[16];
-#pragma unroll
-	for (int i = 0; i < 16; ++i) {
-		mp = fmaf(v[i], mus[16 * q + i], mp);
-		g_split(v[i] * sp, hi[i], lo[i]);
-	}
-	mp *= mus[r];
+	const float4 mc = *reinterpret_cast<const float4 *>(mus + c0);
 	uint8_t *B = gen + S_B + b * S_BSZ;
+	float mp = 0.0f;
 #pragma unroll
-	for (int h = 0; h < 2; ++h) {
-		*reinterpret_cast<uint4 *>(B + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(hi + 8 * h);
-		*reinterpret_cast<uint4 *>(B + 8192 + g_sw128(r, 16 * q + 8 * h)) = *reinterpret_cast<const uint4 *>(lo + 8 * h);
+	for (int i = 0; i < 4; ++i) {
+		const int r = 16 * i + r0;
+		const float v[4] = {pf[i].x, pf[i].y, pf[i].z, pf[i].w};
+		mp = fmaf(mus[r], fmaf(v[0], mc.x, fmaf(v[1], mc.y, fmaf(v[2], mc.z, v[3] * mc.w))), mp);
+		__align__(8) __half hi[4], lo[4];
+#pragma unroll
+		for (int e = 0; e < 4; ++e) g_split(v[e] * sp, hi[e], lo[e]);
+		*reinterpret_cast<uint2 *>(B + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(hi);
+		*reinterpret_cast<uint2 *>(B + 8192 + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(lo);
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);
@@ -150,8 +148,8 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 		float mk = 0.0f;
 #pragma unroll
 		for (int w = 0; w < 8; ++w) mk += m->red[b][w];
-		const float descale = ldexpf(sx_inv, -g_scale_exp(m->pmax[k]));
-		const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD + 32 * half;
+		const float descale = ldexpf(sx_inv * sx_inv, -g_scale_exp(m->pmax[k])); // Y carries 2^(ex + ep), the item and -2 mu' another 2^ex
+		const float *m2 = reinterpret_cast<const float *>(gen + S_M2) + k * TD + 32 * half;
 		g_mbar_wait(g_smem_u32(&m->bar[b]), phase[b]);
 		phase[b] ^= 1u;
 		g_tc_fence_after();
@@ -162,13 +160,16 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 		for (int c8 = 0; c8 < 4; ++c8) { // 8 coordinates per 16-byte chunk of the row, chunks swizzled by the row
 			const uint32_t off = (uint32_t)j * 128u + ((((uint32_t)(4 * half + c8)) ^ ((uint32_t)j & 7u)) << 4);
 			const uint4 h4 = *reinterpret_cast<const uint4 *>(gen + S_AHI + off), l4 = *reinterpret_cast<const uint4 *>(gen + S_ALO + off);
-			const __half2 *hh = reinterpret_cast<const __half2 *>(&h4), *ll = reinterpret_cast<const __half2 *>(&l4);
+			const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+			const float4 ma = *reinterpret_cast<const float4 *>(m2 + 8 * c8), mb = *reinterpret_cast<const float4 *>(m2 + 8 * c8 + 4);
+			const float mq[2][4] = {{ma.x, ma.y, ma.z, ma.w}, {mb.x, mb.y, mb.z, mb.w}};
 #pragma unroll
 			for (int e = 0; e < 4; ++e) {
-				const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+				const float x0 = __half2float(__ushort_as_half((unsigned short)(hw[e] & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(lw[e] & 0xffffu)));
+				const float x1 = __half2float(__ushort_as_half((unsigned short)(hw[e] >> 16))) + __half2float(__ushort_as_half((unsigned short)(lw[e] >> 16)));
 				const int c = 8 * c8 + 2 * e;
-				part = fmaf(v[c], fmaf(fh.x + fl.x, sx_inv, -2.0f * mus[c]), part);
-				part = fmaf(v[c + 1], fmaf(fh.y + fl.y, sx_inv, -2.0f * mus[c + 1]), part);
+				part = fmaf(v[c], x0 + mq[e >> 1][2 * (e & 1)], part);
+				part = fmaf(v[c + 1], x1 + mq[e >> 1][2 * (e & 1) + 1], part);
 			}
 		}
 		if (half) m->tpart[j] = part;
@@ -209,7 +210,13 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	g_tc_fence_before();
 	__syncthreads();
 	g_tc_fence_after();
-	for (int e = tid; e < 32 * TD; e += 256) mus[e] = a.mu[(size_t)chain * 32 * TD + e] - m->xbar[e & (TD - 1)];
+	const float sx2 = -2.0f * ldexpf(1.0f, (int)g.xbar[TD]);
+	float *mus2 = reinterpret_cast<float *>(gen + S_M2);
+	for (int e = tid; e < 32 * TD; e += 256) {
+		const float v = a.mu[(size_t)chain * 32 * TD + e] - m->xbar[e & (TD - 1)];
+		mus[e] = v;
+		mus2[e] = sx2 * v;
+	}
 	for (int k = warp; k < 32; k += 8) {
 		const float *Pk = Pc + (size_t)k * TD * TD;
 		const float d = redux_max_f32(fmaxf(Pk[lane * (TD + 1)], Pk[(lane + 32) * (TD + 1)]));
@@ -366,14 +373,20 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 				}
 				if (tid < TD) {
 					const float x = m->xm[tid];
-					if (!died) mus[src * TD + tid] = (kp * mus[src * TD + tid] - x) / km;
+					if (!died) {
+						const float v = (kp * mus[src * TD + tid] - x) / km;
+						mus[src * TD + tid] = v;
+						mus2[src * TD + tid] = sx2 * v;
+					}
 					if (!(died && born && dst == src)) sxc[src * TD + tid] -= m->xd[tid];
 				}
 				__syncthreads();
 				if (tid < TD) {
 					const float x = m->xm[tid];
 					const float m0 = born ? a.mu0[tid] - m->xbar[tid] : mus[dst * TD + tid];
-					mus[dst * TD + tid] = (kap * m0 + x) / kap1;
+					const float v = (kap * m0 + x) / kap1;
+					mus[dst * TD + tid] = v;
+					mus2[dst * TD + tid] = sx2 * v;
 					sxc[dst * TD + tid] += m->xd[tid];
 				}
 				if (tid == 0) {
