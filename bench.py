@@ -421,19 +421,21 @@ def split_merge_cpu(X, D, n_items=1000, sweeps=1):
 
 def conjugate_measure(npb, syn, ctx, rank):
     """BASELINE configs[3]: CONJUGATE Algorithm 2 (collapsed Gibbs, NIW posterior predictive, statistics up- and down-dated per
-    move).  `cfg4_64d` is configs[3]'s own shape, 256 chains x N = 1 000 000 x 64-D, on k_a2_tile (npb_alg2_tile.cu: a tile of 64
-    steps evaluated ahead of the chain, the two changed columns corrected after every move; same chain as the sequential
-    schedule bit for bit); the chains start from the true partition (one state broadcast to all chains, their random streams
+    move).  `cfg4_64d` is configs[3]'s own shape, 256 chains x N = 1 000 000 x 64-D, on k_a2_tc (npb_alg2_tc.cu: a tile of 128
+    steps evaluated ahead of the chain with the quadratic forms on tcgen05, the two changed clusters evaluated again after every
+    move; same chain as the sequential schedule bit for bit); `fp32_tile_kernel_64d` is the FP32 tile kernel k_a2_tile on a prefix
+    of the same data; the chains start from the true partition (one state broadcast to all chains, their random streams
     their own) so that the warm-up does not have to move a million items per chain.  `step_at_a_time_kernel` is round 2's
     first path (k_a2_sweep) on a short prefix of the same data, for the ratio."""
     out = {}
-    for name, D, N, chains, K, tile, truth in (("cfg4_64d", 64, 1_000_000, 256, 16, 64, True), ("headline_shape_16d", 16, 100_000, 1024, 20, 64, False),
-                                                 ("step_at_a_time_kernel_64d", 64, 20_000, 256, 16, 0, True)):
+    for name, D, N, chains, K, tile, truth, tc in (("cfg4_64d", 64, 1_000_000, 256, 16, 128, True, 1), ("headline_shape_16d", 16, 100_000, 1024, 20, 64, False, 1),
+                                                     ("fp32_tile_kernel_64d", 64, 100_000, 256, 16, 64, True, 0), ("step_at_a_time_kernel_64d", 64, 20_000, 256, 16, 0, True, 0)):
         X, y = syn.gmm(N, D, K, 20261004)
         ds = npb.Dataset(ctx, X)
         npb.NormalInverseWishart(mu0=X.mean(0), kappa=0.01, nu=D + 2.0, Lambda=np.eye(D), alpha=1.0).bind(ctx)
         ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K, m_aux=M_AUX, seed=SEED + 59 * rank)
         ch.set_option("a2_tile", str(tile))
+        ch.set_option("a2_tc", str(tc))
         mu, Sig = given_clusters(X, y)
         if truth:
             ch.set_state(0, y.astype(np.int32), np.arange(K, dtype=np.int32), mu, Sig)
@@ -454,12 +456,19 @@ def conjugate_measure(npb, syn, ctx, rank):
         fl = (cand / 2) * (f_eval(D) + 12) + (moved / 2) * 2 * (2 * D * D + 6 * D)
         out[name] = {"workload": "%d chains x N=%d x %d-D, %d components, conjugate NIW (mu0 = data mean, kappa0 = 0.01, nu0 = D + 2, Lambda0 = I), "
                                  "Kmax=32; start: %s" % (chains, N, D, K, "the true partition" if truth else "the true clusters' parameters, random assignment"),
-                     "kernel": "k_a2_tile<%d> (tile of %d steps)" % (D, tile) if tile else "k_a2_sweep<%d> (one step at a time)" % D,
+                     "kernel": ("k_a2_tc (tcgen05 kind::f16, FP16x3 split; tile of %d steps)" % tile if (tc and D == 64) else
+                                "k_a2_tile<%d> (FP32, tile of %d steps)" % (D, tile)) if tile else "k_a2_sweep<%d> (one step at a time)" % D,
                      "value": chains * N / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "steps": 2,
                      "warmup": warm, "moved_fraction": moved / (2 * chains * N), "candidates_per_reassignment": cand / (2 * chains * N),
                      "mean_K": float(m["K"].mean()), "mean_purity": float(m["purity"].mean()), "algorithmic_tflops": fl / (k_ms * 1e-3) / 1e12}
         out[name]["roofline"] = {"bound": "fp32", "achieved": out[name]["algorithmic_tflops"], "unit": "TFLOP/s", "kernel": out[name]["kernel"],
                                  "note": "SURVEY 8(d) algorithmic flops of the sweep / the sweep time; FP32 FMA peak: roofline_fp32_equivalent.peak"}
+        if tc and D == 64 and tile:
+            # issued kind::f16 flops: 12 MMAs of 128 x 64 x 16 per (tile of 128 steps, cluster with members), clusters = candidates - 1 per step
+            issued = (cand / 2 - chains * N) / 128.0 * 12 * 2 * 128 * 64 * 16
+            out[name]["roofline"].update({"bound": "tensor", "issued_tflops": issued / (k_ms * 1e-3) / 1e12,
+                                          "note": "achieved = SURVEY 8(d) algorithmic flops / sweep time; issued_tflops = kind::f16 MMA flops "
+                                                  "(three FP16 products per FP32 product) / sweep time; peak: roofline.peak (measured bf16)"})
         ch.close()
         ds.close()
     return out

@@ -116,72 +116,80 @@ __device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, int b) {
 	}
 	g_tc_commit(g_smem_u32(&m->bar[b]));
 }
-// The race keys of the clusters in `mask` for the tile's steps [j_lo, T).  Software pipeline over the clusters: while the MMAs of
-// cluster k run, the B image of the next one is built into the other buffer and its MMAs are issued into the other accumulator;
-// then k's accumulator is read -- thread = step = TMEM lane, half of its 64 columns per warp group -- against the step's own row
-// of the A image (x' = (hi + lo) / scale: the very operand the MMA saw) and the cluster's mean.
+// The race keys of the clusters in `mask` for the tile's steps [j_lo, T), two clusters per round: all threads build both B images,
+// one thread issues both sets of MMAs (accumulator / buffer / mbarrier 0 and 1), then warps 0-3 take the first cluster and warps
+// 4-7 the second -- thread = step = TMEM lane, all 64 columns of its accumulator against the step's own row of the A image
+// (x' 2^ex = hi + lo: the very operand the MMA saw) and the cluster's -2 2^ex mu' -- and the race key follows in the same thread.
+// One CTA barrier per round; the first cluster of the next round is fetched while this round's accumulators are read.
 __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, unsigned mask, int j_lo, int T, uint32_t s0,
 		uint32_t ka, uint32_t kb, float sx_inv, uint32_t (&phase)[2]) {
 	if (!mask) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int wq = warp & 3, half = warp >> 2, j = wq * 32 + lane;
+	const int wq = warp & 3, grp = warp >> 2, j = wq * 32 + lane;
 	float *ktab = reinterpret_cast<float *>(gen + S_KT);
 	float4 pf[4];
-	int k = __ffs(mask) - 1;
-	mask &= mask - 1;
-	tc_load(Pc, k, pf);
-	tc_build(gen, m, k, 0, pf);
-	if (mask) tc_load(Pc, __ffs(mask) - 1, pf);
-	g_tc_fence_before();
-	__syncthreads();
-	if (tid == 0) tc_issue(gen, m, 0);
-	for (int b = 0;; b ^= 1) {
-		const int knext = mask ? __ffs(mask) - 1 : -1;
+	tc_load(Pc, __ffs(mask) - 1, pf);
+	while (mask) {
+		const int kA = __ffs(mask) - 1;
 		mask &= mask - 1;
-		if (knext >= 0) {
-			tc_build(gen, m, knext, b ^ 1, pf);
-			if (mask) tc_load(Pc, __ffs(mask) - 1, pf);
+		const int kB = mask ? __ffs(mask) - 1 : -1;
+		mask &= mask - 1;
+		{
+			float4 pg[4];
+			if (kB >= 0) tc_load(Pc, kB, pg); // in flight while the first image is built
+			tc_build(gen, m, kA, 0, pf);
+			if (kB >= 0) tc_build(gen, m, kB, 1, pg);
 		}
+		if (mask) tc_load(Pc, __ffs(mask) - 1, pf);
 		g_tc_fence_before();
-		__syncthreads(); // the other B image is complete; the other accumulator has been read (previous round)
-		if (knext >= 0 && tid == 0) tc_issue(gen, m, b ^ 1);
-		float mk = 0.0f;
+		__syncthreads(); // both images are complete; both accumulators have been read (previous round)
+		if (tid == 0) {
+			tc_issue(gen, m, 0);
+			if (kB >= 0) tc_issue(gen, m, 1);
+		}
+		const int k = grp ? kB : kA;
+		if (k >= 0) {
+			float mk = 0.0f;
 #pragma unroll
-		for (int w = 0; w < 8; ++w) mk += m->red[b][w];
-		const float descale = ldexpf(sx_inv * sx_inv, -g_scale_exp(m->pmax[k])); // Y carries 2^(ex + ep), the item and -2 mu' another 2^ex
-		const float *m2 = reinterpret_cast<const float *>(gen + S_M2) + k * TD + 32 * half;
-		g_mbar_wait(g_smem_u32(&m->bar[b]), phase[b]);
-		phase[b] ^= 1u;
-		g_tc_fence_after();
-		float v[32];
-		g_tmem_ld32(m->tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * b + 32 * half), v);
-		float part = 0.0f;
+			for (int w = 0; w < 8; ++w) mk += m->red[grp][w];
+			const float descale = ldexpf(sx_inv * sx_inv, -g_scale_exp(m->pmax[k])); // Y carries 2^(ex + ep), the item and -2 mu' another 2^ex
+			const float *m2 = reinterpret_cast<const float *>(gen + S_M2) + k * TD;
+			g_mbar_wait(g_smem_u32(&m->bar[grp]), phase[grp]); // (the second cluster's completion implies the first's: MMAs complete in order)
+			g_tc_fence_after();
+			float part = 0.0f;
 #pragma unroll
-		for (int c8 = 0; c8 < 4; ++c8) { // 8 coordinates per 16-byte chunk of the row, chunks swizzled by the row
-			const uint32_t off = (uint32_t)j * 128u + ((((uint32_t)(4 * half + c8)) ^ ((uint32_t)j & 7u)) << 4);
-			const uint4 h4 = *reinterpret_cast<const uint4 *>(gen + S_AHI + off), l4 = *reinterpret_cast<const uint4 *>(gen + S_ALO + off);
-			const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-			const float4 ma = *reinterpret_cast<const float4 *>(m2 + 8 * c8), mb = *reinterpret_cast<const float4 *>(m2 + 8 * c8 + 4);
-			const float mq[2][4] = {{ma.x, ma.y, ma.z, ma.w}, {mb.x, mb.y, mb.z, mb.w}};
+			for (int half = 0; half < 2; ++half) {
+				float v[32];
+				g_tmem_ld32(m->tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(64 * grp + 32 * half), v);
 #pragma unroll
-			for (int e = 0; e < 4; ++e) {
-				const float x0 = __half2float(__ushort_as_half((unsigned short)(hw[e] & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(lw[e] & 0xffffu)));
-				const float x1 = __half2float(__ushort_as_half((unsigned short)(hw[e] >> 16))) + __half2float(__ushort_as_half((unsigned short)(lw[e] >> 16)));
-				const int c = 8 * c8 + 2 * e;
-				part = fmaf(v[c], x0 + mq[e >> 1][2 * (e & 1)], part);
-				part = fmaf(v[c + 1], x1 + mq[e >> 1][2 * (e & 1) + 1], part);
+				for (int c8 = 0; c8 < 4; ++c8) { // 8 coordinates per 16-byte chunk of the row, chunks swizzled by the row
+					const uint32_t off = (uint32_t)j * 128u + ((((uint32_t)(4 * half + c8)) ^ ((uint32_t)j & 7u)) << 4);
+					const uint4 h4 = *reinterpret_cast<const uint4 *>(gen + S_AHI + off), l4 = *reinterpret_cast<const uint4 *>(gen + S_ALO + off);
+					const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+					const float4 ma = *reinterpret_cast<const float4 *>(m2 + 32 * half + 8 * c8), mb = *reinterpret_cast<const float4 *>(m2 + 32 * half + 8 * c8 + 4);
+					const float mq[2][4] = {{ma.x, ma.y, ma.z, ma.w}, {mb.x, mb.y, mb.z, mb.w}};
+#pragma unroll
+					for (int e = 0; e < 4; ++e) {
+						const float x0 = __half2float(__ushort_as_half((unsigned short)(hw[e] & 0xffffu))) + __half2float(__ushort_as_half((unsigned short)(lw[e] & 0xffffu)));
+						const float x1 = __half2float(__ushort_as_half((unsigned short)(hw[e] >> 16))) + __half2float(__ushort_as_half((unsigned short)(lw[e] >> 16)));
+						const int c = 8 * c8 + 2 * e;
+						part = fmaf(v[c], x0 + mq[e >> 1][2 * (e & 1)], part);
+						part = fmaf(v[c + 1], x1 + mq[e >> 1][2 * (e & 1) + 1], part);
+					}
+				}
+			}
+			if (j >= j_lo && j < T) {
+				const float t = fmaxf(fmaf(descale, part, mk), 0.0f);
+				ktab[j * 33 + k] = tc_key(a, m, t, j, k, s0 + (uint32_t)j, ka, kb);
 			}
 		}
-		if (half) m->tpart[j] = part;
+		// nobody builds into a buffer (next round) whose MMAs may still read it: everybody sees the last issued set complete
+		if (!(k >= 0 && grp == (kB >= 0 ? 1 : 0))) g_mbar_wait(g_smem_u32(&m->bar[kB >= 0 ? 1 : 0]), phase[kB >= 0 ? 1 : 0]);
+		phase[0] ^= 1u;
+		if (kB >= 0) phase[1] ^= 1u;
 		g_tc_fence_before();
-		__syncthreads();
-		if (!half && j >= j_lo && j < T) {
-			const float t = fmaxf(fmaf(descale, part + m->tpart[j], mk), 0.0f);
-			ktab[j * 33 + k] = tc_key(a, m, t, j, k, s0 + (uint32_t)j, ka, kb);
-		}
-		if (knext < 0) break;
-		k = knext;
 	}
+	__syncthreads(); // the keys are complete; the accumulators are free
 }
 
 __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
