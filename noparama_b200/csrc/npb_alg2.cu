@@ -316,6 +316,7 @@ __global__ void k_a2_refresh(const int *counts, const double *sx, const double *
 	const int cs = blockIdx.x * blockDim.x + threadIdx.x;
 	if (cs >= n_slots) return;
 	const int n = counts[cs];
+	if (n <= 0 && n_slots > 1) return; // a slot without members is never read: a birth starts it from the prior (the one-slot call IS the prior)
 	double *L = work + (size_t)cs * D * D;
 	const double *s1 = sx + (size_t)cs * D, *s2 = sxx + (size_t)cs * D * D;
 	const double kn = kappa0 + n;
