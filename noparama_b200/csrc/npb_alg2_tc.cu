@@ -129,6 +129,8 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 	float *ktab = reinterpret_cast<float *>(gen + S_KT);
 	float4 pf[4];
 	tc_load(Pc, __ffs(mask) - 1, pf);
+	float pend_t = 0.0f; // a round's race keys are computed while the next round's MMAs run
+	int pend_k = -1;
 	while (mask) {
 		const int kA = __ffs(mask) - 1;
 		mask &= mask - 1;
@@ -147,6 +149,8 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 			tc_issue(gen, m, 0);
 			if (kB >= 0) tc_issue(gen, m, 1);
 		}
+		if (pend_k >= 0 && j >= j_lo && j < T) ktab[j * 33 + pend_k] = tc_key(a, m, pend_t, j, pend_k, s0 + (uint32_t)j, ka, kb);
+		pend_k = -1;
 		const int k = grp ? kB : kA;
 		if (k >= 0) {
 			float mk = 0.0f;
@@ -178,10 +182,8 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 					}
 				}
 			}
-			if (j >= j_lo && j < T) {
-				const float t = fmaxf(fmaf(descale, part, mk), 0.0f);
-				ktab[j * 33 + k] = tc_key(a, m, t, j, k, s0 + (uint32_t)j, ka, kb);
-			}
+			pend_t = fmaxf(fmaf(descale, part, mk), 0.0f);
+			pend_k = k;
 		}
 		// nobody builds into a buffer (next round) whose MMAs may still read it: everybody sees the last issued set complete
 		if (!(k >= 0 && grp == (kB >= 0 ? 1 : 0))) g_mbar_wait(g_smem_u32(&m->bar[kB >= 0 ? 1 : 0]), phase[kB >= 0 ? 1 : 0]);
@@ -189,6 +191,7 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 		if (kB >= 0) phase[1] ^= 1u;
 		g_tc_fence_before();
 	}
+	if (pend_k >= 0 && j >= j_lo && j < T) ktab[j * 33 + pend_k] = tc_key(a, m, pend_t, j, pend_k, s0 + (uint32_t)j, ka, kb);
 	__syncthreads(); // the keys are complete; the accumulators are free
 }
 
