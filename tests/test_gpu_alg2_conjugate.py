@@ -10,6 +10,7 @@ import pytest
 from scipy import stats as sps
 
 from noparama_b200 import synthetic as syn
+from noparama_b200.api import NpbError
 
 pytestmark = pytest.mark.gpu
 
@@ -203,4 +204,35 @@ def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N, tc):
     assert out[0][1] > 0
     assert same > 0.99
     base.close()
+    ds.close()
+
+
+@pytest.mark.parametrize("D,N", [(16, 400), (64, 400)])
+def test_full_slot_table_is_handled_alike_by_every_tile_length(npb, ctx, D, N):
+    """all 32 slots occupied at the start (K0 = 32): a step that draws a new cluster while no slot is free keeps its item and reports the
+    chain (np_error_t's overflow), slots that empty are taken again by later births -- same chain for tiles of 1 and 128 steps, counts
+    consistent with the assignments"""
+    X, y = syn.gmm(N, D, 4, 900 + D, min_dist=2.0)
+    ds = npb.Dataset(ctx, X)
+    pr = conj_prior(X)
+    pr["alpha"] = 50.0  # births are frequent
+    npb.NormalInverseWishart(**pr).bind(ctx)
+    res = {}
+    for tile in (1, 128):
+        ch = npb.Chains(ctx, ds, 5, Kmax=32, K0=32, seed=3)
+        ch.set_option("a2_tile", str(tile))
+        full = 0
+        for _ in range(2):
+            try:
+                ch.sweep(npb.ALG2_CONJUGATE, 1)
+            except NpbError as e:  # NPB_E_KMAX_OVERFLOW: reported, the chains stay valid
+                assert "Kmax" in str(e)
+                full += 1
+        z = ch.assignments().copy()
+        n, _, _ = ch.alg2_suffstats(2)
+        assert np.array_equal(n, np.bincount(z[2], minlength=32))
+        res[tile] = (z, full, ch.metrics(y)["K"].copy())
+        ch.close()
+    assert np.array_equal(res[1][0], res[128][0]) and res[1][1] == res[128][1] and np.array_equal(res[1][2], res[128][2])
+    print("D = %d: %d of 2 sweeps met a full slot table; K after: %s" % (D, res[1][1], res[1][2]))
     ds.close()
