@@ -27,7 +27,7 @@ namespace {
 constexpr int TD = 64;    // dimension
 constexpr int TM = 128;   // steps per tile = UMMA M
 constexpr uint32_t S_AHI = 0, S_ALO = 16384;            // A image of the tile: 128 rows x 128 bytes, hi then lo
-constexpr uint32_t S_B = 32768, S_BSZ = 16384;          // two B images (hi 8 KB, lo 8 KB each): cluster k + 1 is built while k's MMAs run
+constexpr uint32_t S_B = 32768, S_BSZ = 16384;          // two B images: hi of cluster 0, hi of cluster 1 (8 KB each: 128 contiguous rows = ONE N = 128 operand), then the two lo
 constexpr uint32_t S_KT = S_B + 2 * S_BSZ;              // [TM][33] race keys
 constexpr uint32_t S_MU = S_KT + TM * 33 * 4;           // [32][64] centred means
 constexpr uint32_t S_M2 = S_MU + 32 * TD * 4;           // [32][64] -2 2^ex mu': what the epilogue adds to the scaled item
@@ -85,7 +85,7 @@ __device__ __forceinline__ void tc_build(uint8_t *gen, TcMisc *m, int k, int b, 
 	const float *mus = reinterpret_cast<const float *>(gen + S_MU) + k * TD;
 	const float sp = ldexpf(1.0f, g_scale_exp(m->pmax[k])); // P is positive definite: its largest magnitude sits on the diagonal
 	const float4 mc = *reinterpret_cast<const float4 *>(mus + c0);
-	uint8_t *B = gen + S_B + b * S_BSZ;
+	uint8_t *B = gen + S_B + b * 8192; // hi; lo 16 KB further
 	float mp = 0.0f;
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {
@@ -96,28 +96,29 @@ __device__ __forceinline__ void tc_build(uint8_t *gen, TcMisc *m, int k, int b, 
 #pragma unroll
 		for (int e = 0; e < 4; ++e) g_split(v[e] * sp, hi[e], lo[e]);
 		*reinterpret_cast<uint2 *>(B + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(hi);
-		*reinterpret_cast<uint2 *>(B + 8192 + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(lo);
+		*reinterpret_cast<uint2 *>(B + 16384 + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(lo);
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);
 	if ((tid & 31) == 0) m->red[b][tid >> 5] = mp;
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // written through the generic proxy, read by the MMA through the async one
 }
-// the 12 MMAs of one cluster: accumulator b (64 TMEM columns), B buffer b; completion arrives on bar[b]
-__device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, int b) {
+// the 12 MMAs of a round: both clusters at once as N = 128 (accumulator columns 0-63 and 64-127), or the first alone as N = 64;
+// completion arrives on bar[0]
+__device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, bool two) {
 	g_tc_fence_after();
-	const uint32_t base = g_smem_u32(gen), Bb = base + S_B + b * S_BSZ;
-	constexpr uint32_t ID = g_idesc(TM, TD);
+	const uint32_t base = g_smem_u32(gen);
+	const uint32_t ID = two ? g_idesc(TM, 2 * TD) : g_idesc(TM, TD);
 #pragma unroll
 	for (int prod = 0; prod < 3; ++prod) {
-		const uint32_t A = base + (prod == 2 ? S_ALO : S_AHI), B = Bb + (prod == 1 ? 8192u : 0u);
+		const uint32_t A = base + (prod == 2 ? S_ALO : S_AHI), B = base + S_B + (prod == 1 ? 16384u : 0u);
 #pragma unroll
-		for (int ks = 0; ks < 4; ++ks) g_mma_f16(m->tmem + 64u * b, g_desc(A + ks * 32), g_desc(B + ks * 32), ID, (prod | ks) != 0);
+		for (int ks = 0; ks < 4; ++ks) g_mma_f16(m->tmem, g_desc(A + ks * 32), g_desc(B + ks * 32), ID, (prod | ks) != 0);
 	}
-	g_tc_commit(g_smem_u32(&m->bar[b]));
+	g_tc_commit(g_smem_u32(&m->bar[0]));
 }
 // The race keys of the clusters in `mask` for the tile's steps [j_lo, T), two clusters per round: all threads build both B images,
-// one thread issues both sets of MMAs (accumulator / buffer / mbarrier 0 and 1), then warps 0-3 take the first cluster and warps
+// one thread issues the round's 12 MMAs (N = 128: both clusters at once), then warps 0-3 take the first cluster and warps
 // 4-7 the second -- thread = step = TMEM lane, all 64 columns of its accumulator against the step's own row of the A image
 // (x' 2^ex = hi + lo: the very operand the MMA saw) and the cluster's -2 2^ex mu' -- and the race key follows in the same thread.
 // One CTA barrier per round; the first cluster of the next round is fetched while this round's accumulators are read.
@@ -145,10 +146,7 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 		if (mask) tc_load(Pc, __ffs(mask) - 1, pf);
 		g_tc_fence_before();
 		__syncthreads(); // both images are complete; both accumulators have been read (previous round)
-		if (tid == 0) {
-			tc_issue(gen, m, 0);
-			if (kB >= 0) tc_issue(gen, m, 1);
-		}
+		if (tid == 0) tc_issue(gen, m, kB >= 0);
 		if (pend_k >= 0 && j >= j_lo && j < T) ktab[j * 33 + pend_k] = tc_key(a, m, pend_t, j, pend_k, s0 + (uint32_t)j, ka, kb);
 		pend_k = -1;
 		const int k = grp ? kB : kA;
@@ -158,7 +156,7 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 			for (int w = 0; w < 8; ++w) mk += m->red[grp][w];
 			const float descale = ldexpf(sx_inv * sx_inv, -g_scale_exp(m->pmax[k])); // Y carries 2^(ex + ep), the item and -2 mu' another 2^ex
 			const float *m2 = reinterpret_cast<const float *>(gen + S_M2) + k * TD;
-			g_mbar_wait(g_smem_u32(&m->bar[grp]), phase[grp]); // (the second cluster's completion implies the first's: MMAs complete in order)
+			g_mbar_wait(g_smem_u32(&m->bar[0]), phase[0]);
 			g_tc_fence_after();
 			float part = 0.0f;
 #pragma unroll
@@ -185,10 +183,9 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 			pend_t = fmaxf(fmaf(descale, part, mk), 0.0f);
 			pend_k = k;
 		}
-		// nobody builds into a buffer (next round) whose MMAs may still read it: everybody sees the last issued set complete
-		if (!(k >= 0 && grp == (kB >= 0 ? 1 : 0))) g_mbar_wait(g_smem_u32(&m->bar[kB >= 0 ? 1 : 0]), phase[kB >= 0 ? 1 : 0]);
+		// nobody builds into a buffer (next round) whose MMAs may still read it: everybody sees the round's MMAs complete
+		if (k < 0) g_mbar_wait(g_smem_u32(&m->bar[0]), phase[0]);
 		phase[0] ^= 1u;
-		if (kB >= 0) phase[1] ^= 1u;
 		g_tc_fence_before();
 	}
 	if (pend_k >= 0 && j >= j_lo && j < T) ktab[j * 33 + pend_k] = tc_key(a, m, pend_t, j, pend_k, s0 + (uint32_t)j, ka, kb);
