@@ -309,61 +309,73 @@ __global__ void __launch_bounds__(256) k_a2_recount(const double *X64, const npb
 
 // ---------------------------------------------------------------------------------------------------------
 // derived state of every (chain, slot) from its statistics: posterior mean, Lambda_n -> Cholesky -> log det and inverse
-// (fp64, one thread per cluster; work [C, 32, D, D] doubles is its scratch)
+// (fp64; one WARP per cluster, the matrix in shared memory [D][D + 1]; a slot without members is skipped: it is never read, a
+// birth starts it from the prior -- except in the one-slot call that computes the prior's own Lambda_0^-1)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_a2_refresh(const int *counts, const double *sx, const double *sxx, const double *mu0, double kappa0, const double *Lambda0, int D,
-		int n_slots, double *work, float *mu_out, float *P_out, float *ld_out) {
-	const int cs = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) k_a2_refresh(const int *counts, const double *sx, const double *sxx, const double *mu0, double kappa0,
+		const double *Lambda0, int D, int n_slots, float *mu_out, float *P_out, float *ld_out) {
+	extern __shared__ double a2S[]; // [D][D + 1]
+	const int cs = blockIdx.x, lane = threadIdx.x;
 	if (cs >= n_slots) return;
 	const int n = counts[cs];
-	if (n <= 0 && n_slots > 1) return; // a slot without members is never read: a birth starts it from the prior (the one-slot call IS the prior)
-	double *L = work + (size_t)cs * D * D;
+	if (n <= 0 && n_slots > 1) return;
+	const int LD = D + 1;
 	const double *s1 = sx + (size_t)cs * D, *s2 = sxx + (size_t)cs * D * D;
-	const double kn = kappa0 + n;
+	const double kn = kappa0 + n, inv_n = n > 0 ? 1.0 / n : 0.0;
 	// Lambda_n = Lambda_0 + sum x x^T - n xbar xbar^T + kappa_0 n / kappa_n (xbar - mu0)(xbar - mu0)^T
-	for (int a = 0; a < D; ++a) {
-		const double xa = n > 0 ? s1[a] / n : 0.0;
-		mu_out[(size_t)cs * D + a] = (float)((kappa0 * mu0[a] + (n > 0 ? s1[a] : 0.0)) / kn);
-		for (int b = 0; b <= a; ++b) {
-			const double xb = n > 0 ? s1[b] / n : 0.0;
-			double v = Lambda0[a * D + b];
-			if (n > 0) v += s2[(size_t)a * D + b] - n * xa * xb + kappa0 * n / kn * (xa - mu0[a]) * (xb - mu0[b]);
-			L[(size_t)a * D + b] = v;
+	for (int e = lane; e < D * D; e += 32) {
+		const int a = e / D, b = e % D;
+		double v = Lambda0[e];
+		if (n > 0) {
+			const double xa = s1[a] * inv_n, xb = s1[b] * inv_n;
+			v += s2[e] - n * xa * xb + kappa0 * n / kn * (xa - mu0[a]) * (xb - mu0[b]);
 		}
+		a2S[a * LD + b] = v;
 	}
-	// Cholesky in place (lower), log det
+	for (int a = lane; a < D; a += 32) mu_out[(size_t)cs * D + a] = (float)((kappa0 * mu0[a] + (n > 0 ? s1[a] : 0.0)) / kn);
+	__syncwarp();
+	// Cholesky in place (lower, right-looking): column j is scaled, then the rows below subtract their share of it
 	double ld = 0.0;
-	for (int i = 0; i < D; ++i) {
-		for (int j = 0; j <= i; ++j) {
-			double s = L[(size_t)i * D + j];
-			for (int k = 0; k < j; ++k) s -= L[(size_t)i * D + k] * L[(size_t)j * D + k];
-			if (i == j) { s = s > 1e-300 ? s : 1e-300; L[(size_t)i * D + i] = sqrt(s); ld += log(s); }
-			else L[(size_t)i * D + j] = s / L[(size_t)j * D + j];
-		}
-	}
-	// W = L^-1 (lower): W[j][j] = 1 / L[j][j], W[i][j] = -(sum_{j <= k < i} L[i][k] W[k][j]) / L[i][i]; the strict lower part of W is
-	// stored transposed in the (unused) strict upper triangle of the scratch: W[i][j], i > j, lives at L[j * D + i]
 	for (int j = 0; j < D; ++j) {
-		const double wjj = 1.0 / L[(size_t)j * D + j];
+		double d = a2S[j * LD + j];
+		d = d > 1e-300 ? d : 1e-300;
+		const double ljj = sqrt(d);
+		ld += log(d);
+		__syncwarp();
+		for (int i = j + 1 + lane; i < D; i += 32) a2S[i * LD + j] /= ljj;
+		if (lane == 0) a2S[j * LD + j] = ljj;
+		__syncwarp();
+		for (int i = j + 1 + lane; i < D; i += 32) {
+			const double lij = a2S[i * LD + j];
+			for (int k = j + 1; k <= i; ++k) a2S[i * LD + k] -= lij * a2S[k * LD + j];
+		}
+		__syncwarp();
+	}
+	// W = L^-1 (lower), a lane per column j: W[j][j] = 1 / L[j][j], W[i][j] = -(sum_{j <= k < i} L[i][k] W[k][j]) / L[i][i]; the strict
+	// lower part of W is stored transposed in the (now unused) strict upper triangle: W[i][j], i > j, lives at S[j][i] -- row j is the lane's own
+	for (int j = lane; j < D; j += 32) {
+		const double wjj = 1.0 / a2S[j * LD + j];
 		for (int i = j + 1; i < D; ++i) {
-			double s = L[(size_t)i * D + j] * wjj;
-			for (int k = j + 1; k < i; ++k) s += L[(size_t)i * D + k] * L[(size_t)j * D + k];
-			L[(size_t)j * D + i] = -s / L[(size_t)i * D + i];
+			double s = a2S[i * LD + j] * wjj;
+			for (int k = j + 1; k < i; ++k) s += a2S[i * LD + k] * a2S[j * LD + k];
+			a2S[j * LD + i] = -s / a2S[i * LD + i];
 		}
 	}
-	// P = W^T W: P[a][b] = sum_{i >= max(a, b)} W[i][a] W[i][b]
-	for (int a = 0; a < D; ++a)
-		for (int b = 0; b <= a; ++b) {
-			double s = 0.0;
-			for (int i = a; i < D; ++i) {
-				const double wa = i == a ? 1.0 / L[(size_t)a * D + a] : L[(size_t)a * D + i];
-				const double wb = i == b ? 1.0 / L[(size_t)b * D + b] : L[(size_t)b * D + i];
-				s += wa * wb;
-			}
-			P_out[(size_t)cs * D * D + a * D + b] = (float)s;
-			P_out[(size_t)cs * D * D + b * D + a] = (float)s;
+	__syncwarp();
+	// P = W^T W: P[a][b] = sum_{i >= a} W[i][a] W[i][b], b <= a, the pairs dealt over the lanes
+	for (int e = lane; e < D * D; e += 32) {
+		const int a = e / D, b = e % D;
+		if (b > a) continue;
+		double s = 0.0;
+		for (int i = a; i < D; ++i) {
+			const double wa = i == a ? 1.0 / a2S[a * LD + a] : a2S[a * LD + i];
+			const double wb = i == b ? 1.0 / a2S[b * LD + b] : a2S[b * LD + i];
+			s += wa * wb;
 		}
-	ld_out[cs] = (float)ld;
+		P_out[(size_t)cs * D * D + a * D + b] = (float)s;
+		P_out[(size_t)cs * D * D + b * D + a] = (float)s;
+	}
+	if (lane == 0) ld_out[cs] = (float)ld;
 }
 
 // G[n] and the prior predictive of every item
@@ -419,7 +431,6 @@ static npb_status a2_ensure(npb_chains *ch) {
 	if (!ch->a2_sx) {
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->a2_sx, CS * D * sizeof(double)));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->a2_sxx, CS * D * D * sizeof(double)));
-		NPB_CUDA_OK(cudaMalloc((void **)&ch->a2_work, CS * D * D * sizeof(double)));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->a2_mu, CS * D * sizeof(float)));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->a2_P, CS * D * D * sizeof(float)));
 		NPB_CUDA_OK(cudaMalloc((void **)&ch->a2_ld, CS * sizeof(float)));
@@ -483,7 +494,7 @@ static npb_status a2_sync(npb_chains *ch, bool force_recount) {
 		int *d_zero = reinterpret_cast<int *>(ch->a2_ld); // scratch: overwritten by the real refresh below
 		NPB_CUDA_OK(cudaMemcpyAsync(d_zero, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 		float *d_tmp = ch->a2_mu; // scratch for the posterior mean of the empty cluster
-		k_a2_refresh<<<1, 32, 0, ctx->stream>>>(d_zero, ch->a2_sx, ch->a2_sxx, d_mu0, p.kappa, d_L0, D, 1, ch->a2_work, d_tmp, d_P0, ch->a2_ld + 1);
+		k_a2_refresh<<<1, 32, sizeof(double) * D * (D + 1), ctx->stream>>>(d_zero, ch->a2_sx, ch->a2_sxx, d_mu0, p.kappa, d_L0, D, 1, d_tmp, d_P0, ch->a2_ld + 1);
 		NPB_CUDA_OK(cudaGetLastError());
 		NPB_CUDA_OK(cudaMemcpyAsync(&ch->a2_ld0, ch->a2_ld + 1, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 		NPB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -503,7 +514,7 @@ static npb_status a2_sync(npb_chains *ch, bool force_recount) {
 		NPB_CUDA_OK(cudaGetLastError());
 		ch->a2_gen = ch->z_gen;
 	}
-	k_a2_refresh<<<(CS + 63) / 64, 64, 0, ctx->stream>>>(ch->counts, ch->a2_sx, ch->a2_sxx, d_mu0, p.kappa, d_L0, D, CS, ch->a2_work, ch->a2_mu, ch->a2_P, ch->a2_ld);
+	k_a2_refresh<<<CS, 32, sizeof(double) * D * (D + 1), ctx->stream>>>(ch->counts, ch->a2_sx, ch->a2_sxx, d_mu0, p.kappa, d_L0, D, CS, ch->a2_mu, ch->a2_P, ch->a2_ld);
 	NPB_CUDA_OK(cudaGetLastError());
 	return NPB_OK;
 }
