@@ -50,6 +50,7 @@ struct SMArgs {
 	uint64_t seed;
 	double alpha;            // Dirichlet-process concentration (np_main.cpp:164)
 	int jn_bugcompat;        // Q8 rule on (reference behaviour) / off (linear-domain SAMS like the triadic sampler)
+	int seq_scan;            // 1: the restricted scan one member at a time (option spec = 0); 0: 32 members at a time, to a fixed point (same result)
 	PriorDev prior;
 };
 
@@ -368,6 +369,42 @@ __global__ void __launch_bounds__(SM_THREADS, 16) k_split_merge(SMArgs a) {
 						if (id == p.picks[q]) skipq = q;
 					int mydec = 0;
 					const int lim = min(32, cnt - j0);
+					if (!a.seq_scan) {
+						// 32 members at a time.  A member's part depends on the earlier members only through the part sizes, so every
+						// lane decides with the sizes implied by the earlier lanes' CURRENT decisions (ballot + popc), and the warp
+						// repeats until no decision changes: at that fixed point every lane's decision is the one the sequential scan
+						// makes (induction over the lanes; lane j is final after at most j + 1 rounds, in practice two or three:
+						// one more member rarely tips a draw).  Same arithmetic per decision as the loop below.
+						const bool live = my < cnt && skipq < 0;
+						const unsigned lt = (1u << lane) - 1u;
+						int d = skipq >= 0 ? skipq : 0;
+						for (int round = 0; round < 34; ++round) {
+							const unsigned m0 = __ballot_sync(0xffffffffu, live && d == 0), m1 = __ballot_sync(0xffffffffu, live && d == 1);
+							const unsigned m2 = __ballot_sync(0xffffffffu, live && d == 2);
+							const float n0 = npart[0] + (float)__popc(m0 & lt), n1 = npart[1] + (float)__popc(m1 & lt), n2 = npart[2] + (float)__popc(m2 & lt);
+							int dn;
+							if (p.type == SM_JN_SPLIT && a.jn_bugcompat) {
+								const float c0 = e0 + n0, c1 = c0 + (e1 + n1);
+								const float thr = u * c1;
+								dn = (c1 < thr) ? 1 : ((c0 < thr) ? 1 : 0);
+							} else {
+								const float w0 = e0 * n0, w1 = e1 * n1, w2 = e2 * n2;
+								const float c0 = w0, c1 = w0 + w1, c2 = c1 + w2;
+								const float thr = u * (p.Q > 2 ? c2 : c1);
+								dn = (c0 >= thr) ? 0 : ((c1 >= thr || p.Q == 2) ? 1 : 2);
+							}
+							const bool changed = live && dn != d;
+							if (live) d = dn;
+							if (!__any_sync(0xffffffffu, changed)) break;
+						}
+						{
+							const unsigned m0 = __ballot_sync(0xffffffffu, live && d == 0), m1 = __ballot_sync(0xffffffffu, live && d == 1);
+							const unsigned m2 = __ballot_sync(0xffffffffu, live && d == 2);
+							npart[0] += (float)__popc(m0); npart[1] += (float)__popc(m1); npart[2] += (float)__popc(m2);
+							sams += (unsigned long long)__popc(m0 | m1 | m2);
+						}
+						mydec = d;
+					} else
 					for (int j = 0; j < lim; ++j) {
 						const int bskip = __shfl_sync(0xffffffffu, skipq, j);
 						const float b0 = __shfl_sync(0xffffffffu, e0, j), b1 = __shfl_sync(0xffffffffu, e1, j);
@@ -545,6 +582,7 @@ npb_status npb_launch_split_merge(npb_chains *ch, int sampler, int64_t n_proposa
 	a.N = N; a.C = C; a.Kmax = ch->Kmax; a.sampler = sampler; a.zstride = zstride;
 	a.seed = ch->seed;
 	a.jn_bugcompat = 1;
+	a.seq_scan = ch->sw.spec == 0;
 	a.alpha = ctx->prior.alpha;
 	a.prior = npb_prior_dev(ctx, 1);
 	dim3 tb(32, 8);

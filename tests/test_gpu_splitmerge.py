@@ -323,3 +323,32 @@ def test_mixed_schedule_keeps_the_state_consistent(npb, ctx, D, kmax):
     assert ch.best_assignments().shape == z.shape
     ch.close()
     ds.close()
+
+
+@pytest.mark.parametrize("sampler_name,which", [("jain_neal", 1), ("triadic", 1), ("triadic", 3)])
+def test_scan_32_members_at_a_time_equals_the_sequential_scan(npb, ctx, sampler_name, which):
+    """the restricted (SAMS) scan of k_split_merge decides 32 pool members per round and repeats the round until no decision changes
+    (every lane uses the part sizes implied by the earlier lanes' decisions): that fixed point IS the sequential scan's result --
+    option spec = 0 runs the member-at-a-time loop; assignments, attempts and accepts must be identical"""
+    sampler = {"jain_neal": npb.JAIN_NEAL, "triadic": npb.TRIADIC}[sampler_name]
+    X, y = syn.config(which)
+    if which == 3:
+        X, y = X[:6000], y[:6000]
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**syn.reference_prior(X.shape[1])).bind(ctx)
+    res = {}
+    for spec in ("1", "0"):
+        ch = npb.Chains(ctx, ds, 48, Kmax=64, seed=11)
+        ch.set_option("spec", spec)
+        att, acc = np.zeros(4, np.int64), np.zeros(4, np.int64)
+        for _ in range(3):
+            st = ch.sweep(sampler, 2)
+            att += np.array(list(st.sm_attempts))
+            acc += np.array(list(st.sm_accepts))
+        res[spec] = (ch.assignments().copy(), att, acc)
+        ch.close()
+    assert np.array_equal(res["1"][0], res["0"][0])
+    assert np.array_equal(res["1"][1], res["0"][1]) and np.array_equal(res["1"][2], res["0"][2])
+    assert res["1"][1].sum() > 0
+    print("%s on config %d: identical; attempts %s accepts %s" % (sampler_name, which, res["1"][1], res["1"][2]))
+    ds.close()
