@@ -236,3 +236,31 @@ def test_full_slot_table_is_handled_alike_by_every_tile_length(npb, ctx, D, N):
     assert np.array_equal(res[1][0], res[128][0]) and res[1][1] == res[128][1] and np.array_equal(res[1][2], res[128][2])
     print("D = %d: %d of 2 sweeps met a full slot table; K after: %s" % (D, res[1][1], res[1][2]))
     ds.close()
+
+
+def test_tensor_core_forms_hold_on_shifted_wide_data(npb, ctx):
+    """k_a2_tc centres the items on the data mean and splits FP16 x 3: data far from the origin (+500) with widely separated components
+    (x 3) must still make the step-at-a-time FP32 kernel's decisions from the same state"""
+    D, N = 64, 500
+    X, y = syn.gmm(N, D, 4, 864, min_dist=3.0)
+    X = 3.0 * X + 500.0
+    ds = npb.Dataset(ctx, X)
+    npb.NormalInverseWishart(**conj_prior(X)).bind(ctx)
+    base = npb.Chains(ctx, ds, 6, Kmax=32, K0=6, seed=31)
+    base.sweep(npb.ALG2_CONJUGATE, 1)
+    zs = base.assignments()
+    out = {}
+    for tile in (0, 128):
+        ch = npb.Chains(ctx, ds, 6, Kmax=32, K0=6, seed=31)
+        ch.set_option("a2_tile", str(tile))
+        for c in range(6):
+            slots = np.unique(zs[c]).astype(np.int32)
+            ch.set_state(c, zs[c], slots, np.zeros((len(slots), D)), np.tile(np.eye(D), (len(slots), 1, 1)))
+        st = ch.sweep(npb.ALG2_CONJUGATE, 1)
+        out[tile] = (ch.assignments().copy(), st.moved)
+        ch.close()
+    same = (out[0][0] == out[128][0]).mean()
+    print("shifted, wide 64-D data: %.5f of the assignments equal after one sweep; moves %d / %d" % (same, out[0][1], out[128][1]))
+    assert out[0][1] > 0 and same > 0.99
+    base.close()
+    ds.close()
