@@ -1215,10 +1215,12 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	// memory).  Measured equal (101 against 102 ms per sweep): the bound leaves out the chi-square term, which is what makes
 	// an auxiliary draw hopeless at D = 16, so a third of the steps still need the exact key and every tile pays for it.
 	const bool prepass = ch->sw.d16_aux_pre;
+	// (same keys, same results in every mode; which one is a matter of time only)
+	const bool grp = ch->sw.d16_aux_grp && !(ch->sw.d16_aux_auto && ch->moved_frac_last > 0.01);
 	if (prepass) {
 		s = npb_launch_aux_keys<16>(ch, a);
 		if (s != NPB_OK) return s;
-	} else if (ch->sw.d16_aux_grp) { // group maxima of a bound (k_aux_bound), exact keys on demand: the default
+	} else if (grp) { // group maxima of a bound (k_aux_bound), exact keys on demand: the default while few items move
 		s = npb_launch_aux_bound<16>(ch, a);
 		if (s != NPB_OK) return s;
 	}
@@ -1228,7 +1230,7 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 	PreArgs p;
 	p.a = a;
 	if (!prepass) p.a.aux_keys = nullptr;
-	if (prepass || !ch->sw.d16_aux_grp) p.a.aux_max = nullptr;
+	if (prepass || !grp) p.a.aux_max = nullptr;
 	p.BS = BS + 32;
 	p.L = ch->g_L;
 	p.spec = ch->sw.spec != 0;
@@ -1244,7 +1246,7 @@ npb_status npb_launch_alg8_tc16(npb_chains *ch, const SweepArgs &a) {
 			p.s0 = s0;
 			p.nsteps = nsteps;
 			const unsigned blocks = (unsigned)((ch->C + 3) / 4);
-			const int am = prepass ? 0 : (ch->sw.d16_aux_grp ? 2 : 1);
+			const int am = prepass ? 0 : (grp ? 2 : 1);
 			if (ch->m_aux == 3 && am == 0) k_race<HD, 3, 0><<<blocks, 128, 0, ctx->stream>>>(p);
 			else if (ch->m_aux == 3 && am == 1) k_race<HD, 3, 1><<<blocks, 128, 0, ctx->stream>>>(p);
 			else if (ch->m_aux == 3) k_race<HD, 3, 2><<<blocks, 128, 0, ctx->stream>>>(p);

@@ -435,7 +435,7 @@ static npb_status set_switch(npb_chains *ch, const char *name, const char *value
 	else if (!strcmp(name, "d64_block")) { if (v < 1) return NPB_E_BAD_ARG; w.d64_block = v; }
 	else if (!strcmp(name, "d16_epi")) { if (v != 8 && v != 16) return NPB_E_BAD_ARG; w.d16_epi = v; }
 	else if (!strcmp(name, "d16_nh")) { if (v != 1 && v != 2 && v != 4) return NPB_E_BAD_ARG; w.d16_nh = v; }
-	else if (!strcmp(name, "d16_aux")) { w.d16_aux_pre = value[0] == 'p'; w.d16_aux_grp = value[0] != 'l' && value[0] != 'p'; } // pre | lazy | bound
+	else if (!strcmp(name, "d16_aux")) { w.d16_aux_pre = value[0] == 'p'; w.d16_aux_grp = value[0] != 'l' && value[0] != 'p'; w.d16_aux_auto = false; } // pre | lazy | bound
 	else if (!strcmp(name, "d64_overlap")) w.d64_overlap = value[0] != '0';
 	else if (!strcmp(name, "d64_density")) w.d64_fp32 = value[0] == 'f';
 	else if (!strcmp(name, "tile_kernel")) w.two_warp = value[0] == '2';

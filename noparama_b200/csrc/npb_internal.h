@@ -77,6 +77,8 @@ struct npb_chains {
 		int d16_nh = 4;           // NPB_D16_NH: chain halves per unit of k_density_tc16 (1 | 2 | 4)
 		bool d16_aux_pre = false; // NPB_D16_AUX=pre: the kernel pair reads exact auxiliary keys from the k_aux_keys pre-pass (round 1)
 		bool d16_aux_grp = true;  // NPB_D16_AUX=lazy -> false: no pre-pass at all, bounds per step inside the race; default: k_aux_bound group maxima
+		bool d16_aux_auto = true; // no explicit d16_aux: the kernel pair takes the bounds per step inside the race (lazy) in a chain that keeps moving items
+		                          // (there the race waits on its table reads and has issue slots to spare: 101 against 106 ms per sweep), group maxima otherwise
 		bool d64_overlap = true;  // NPB_D64_OVERLAP=0 -> false
 		bool d64_fp32 = false;    // NPB_D64_DENSITY=fp32
 		bool two_warp = false;    // NPB_TILE_KERNEL=2warp: round-1 one-chain-per-CTA kernel
