@@ -35,16 +35,14 @@ constexpr uint32_t S_MISC = S_M2 + 32 * TD * 4;
 
 struct TcMisc {
 	double xd[TD];       // the moving item in FP64
-	unsigned long long bar[2];
+	unsigned long long bar;
 	float ldv[32];
 	int cnt[32];
 	int zold[TM], items[TM], win[TM];
-	int slist[36];
 	float red[2][8];     // shares of mu'^T P mu' per warp, per B buffer
 	float red2[4];
 	float xm[TD];        // the moving item, centred
 	float dm[2 * TD], pu[2 * TD];
-	float tpart[TM];
 	float xbar[TD];
 	float pmax[32];      // largest diagonal element of every cluster's P (the scale of its B operand)
 	uint32_t tmem;
@@ -104,7 +102,7 @@ __device__ __forceinline__ void tc_build(uint8_t *gen, TcMisc *m, int k, int b, 
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // written through the generic proxy, read by the MMA through the async one
 }
 // the 12 MMAs of a round: both clusters at once as N = 128 (accumulator columns 0-63 and 64-127), or the first alone as N = 64;
-// completion arrives on bar[0]
+// completion arrives on the mbarrier
 __device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, bool two) {
 	g_tc_fence_after();
 	const uint32_t base = g_smem_u32(gen);
@@ -115,7 +113,7 @@ __device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, bool two) {
 #pragma unroll
 		for (int ks = 0; ks < 4; ++ks) g_mma_f16(m->tmem, g_desc(A + ks * 32), g_desc(B + ks * 32), ID, (prod | ks) != 0);
 	}
-	g_tc_commit(g_smem_u32(&m->bar[0]));
+	g_tc_commit(g_smem_u32(&m->bar));
 }
 // The race keys of the clusters in `mask` for the tile's steps [j_lo, T), two clusters per round: all threads build both B images,
 // one thread issues the round's 12 MMAs (N = 128: both clusters at once), then warps 0-3 take the first cluster and warps
@@ -123,7 +121,7 @@ __device__ __forceinline__ void tc_issue(uint8_t *gen, TcMisc *m, bool two) {
 // (x' 2^ex = hi + lo: the very operand the MMA saw) and the cluster's -2 2^ex mu' -- and the race key follows in the same thread.
 // One CTA barrier per round; the first cluster of the next round is fetched while this round's accumulators are read.
 __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m, const float *Pc, unsigned mask, int j_lo, int T, uint32_t s0,
-		uint32_t ka, uint32_t kb, float sx_inv, uint32_t (&phase)[2]) {
+		uint32_t ka, uint32_t kb, float sx_inv, uint32_t &phase) {
 	if (!mask) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int wq = warp & 3, grp = warp >> 2, j = wq * 32 + lane;
@@ -156,7 +154,7 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 			for (int w = 0; w < 8; ++w) mk += m->red[grp][w];
 			const float descale = ldexpf(sx_inv * sx_inv, -g_scale_exp(m->pmax[k])); // Y carries 2^(ex + ep), the item and -2 mu' another 2^ex
 			const float *m2 = reinterpret_cast<const float *>(gen + S_M2) + k * TD;
-			g_mbar_wait(g_smem_u32(&m->bar[0]), phase[0]);
+			g_mbar_wait(g_smem_u32(&m->bar), phase);
 			g_tc_fence_after();
 			float part = 0.0f;
 #pragma unroll
@@ -184,8 +182,8 @@ __device__ __forceinline__ void tc_pass(const A2Args &a, uint8_t *gen, TcMisc *m
 			pend_k = k;
 		}
 		// nobody builds into a buffer (next round) whose MMAs may still read it: everybody sees the round's MMAs complete
-		if (k < 0) g_mbar_wait(g_smem_u32(&m->bar[0]), phase[0]);
-		phase[0] ^= 1u;
+		if (k < 0) g_mbar_wait(g_smem_u32(&m->bar), phase);
+		phase ^= 1u;
 		g_tc_fence_before();
 	}
 	if (pend_k >= 0 && j >= j_lo && j < T) ktab[j * 33 + pend_k] = tc_key(a, m, pend_t, j, pend_k, s0 + (uint32_t)j, ka, kb);
@@ -206,8 +204,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	if (tid < TD) m->xbar[tid] = (float)g.xbar[tid];
 	if (tid < 32) { m->cnt[tid] = a.counts[(size_t)chain * 32 + tid]; m->ldv[tid] = a.ld[(size_t)chain * 32 + tid]; }
 	if (tid == 0) {
-		g_mbar_init(g_smem_u32(&m->bar[0]), 1);
-		g_mbar_init(g_smem_u32(&m->bar[1]), 1);
+		g_mbar_init(g_smem_u32(&m->bar), 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async;" ::: "memory");
 	}
@@ -237,7 +234,7 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 	const uint32_t ka = (uint32_t)a.seed ^ 0xA2A2A2A2u, k1 = (uint32_t)(a.seed >> 32) + (uint32_t)chain;
 	const int tile_max = a.tile < 1 ? 1 : (a.tile > TM ? TM : a.tile);
 	int tile = tile_max;
-	uint32_t phase[2] = {0u, 0u};
+	uint32_t phase = 0u;
 	__syncthreads();
 
 	for (int sw = 0; sw < a.n_sweeps; ++sw) {
