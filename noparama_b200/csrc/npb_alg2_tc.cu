@@ -71,6 +71,14 @@ __device__ __forceinline__ float tc_key(const A2Args &a, const TcMisc *m, float 
 	return fast_lg2((float)n_eff) + lp * NPB_LOG2E + a2_noise(ka ^ step, kb, (uint32_t)k);
 }
 
+// v0, v1 -> packed FP16 pairs (hi, lo) with v = hi + lo: the same roundings as g_split, two values per conversion instruction
+__device__ __forceinline__ void tc_split2(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+	const __half2 h = __floats2half2_rn(v0, v1);
+	const float2 f = __half22float2(h);
+	const __half2 l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+	hi = *reinterpret_cast<const uint32_t *>(&h);
+	lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 // this thread's 16 values of P_k, coalesced: float4 number i 256 + tid of the matrix, i = 0..3 = row 16 i + tid / 16, columns 4 (tid % 16) ...
 __device__ __forceinline__ void tc_load(const float *Pc, int k, float4 (&pf)[4]) {
 	const float4 *src = reinterpret_cast<const float4 *>(Pc + (size_t)k * TD * TD) + threadIdx.x;
@@ -90,11 +98,11 @@ __device__ __forceinline__ void tc_build(uint8_t *gen, TcMisc *m, int k, int b, 
 		const int r = 16 * i + r0;
 		const float v[4] = {pf[i].x, pf[i].y, pf[i].z, pf[i].w};
 		mp = fmaf(mus[r], fmaf(v[0], mc.x, fmaf(v[1], mc.y, fmaf(v[2], mc.z, v[3] * mc.w))), mp);
-		__align__(8) __half hi[4], lo[4];
-#pragma unroll
-		for (int e = 0; e < 4; ++e) g_split(v[e] * sp, hi[e], lo[e]);
-		*reinterpret_cast<uint2 *>(B + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(hi);
-		*reinterpret_cast<uint2 *>(B + 16384 + g_sw128(r, c0)) = *reinterpret_cast<const uint2 *>(lo);
+		uint2 hi, lo;
+		tc_split2(v[0] * sp, v[1] * sp, hi.x, lo.x);
+		tc_split2(v[2] * sp, v[3] * sp, hi.y, lo.y);
+		*reinterpret_cast<uint2 *>(B + g_sw128(r, c0)) = hi;
+		*reinterpret_cast<uint2 *>(B + 16384 + g_sw128(r, c0)) = lo;
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);
@@ -251,19 +259,18 @@ __global__ void __launch_bounds__(256, 2) k_a2_tc(const TcArgs g) {
 			// ---- A image (FP16 hi / lo, K-major, swizzled) of the centred items: thread = (step, 8 coordinates) ----
 			for (int e = tid; e < TM * 8; e += 256) {
 				const int j = e >> 3, q = e & 7;
-				__align__(16) __half hi[8], lo[8];
+				uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
 				if (j < T) {
 					const float4 *src = reinterpret_cast<const float4 *>(a.X + (size_t)m->items[j] * TD + 8 * q);
 					const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
-					float x[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-					for (int i = 0; i < 8; ++i) g_split((x[i] - m->xbar[8 * q + i]) * sx, hi[i], lo[i]);
-				} else {
-#pragma unroll
-					for (int i = 0; i < 8; ++i) hi[i] = lo[i] = __float2half_rn(0.0f);
+					const float *xb = m->xbar + 8 * q;
+					tc_split2((p0.x - xb[0]) * sx, (p0.y - xb[1]) * sx, hi.x, lo.x);
+					tc_split2((p0.z - xb[2]) * sx, (p0.w - xb[3]) * sx, hi.y, lo.y);
+					tc_split2((p1.x - xb[4]) * sx, (p1.y - xb[5]) * sx, hi.z, lo.z);
+					tc_split2((p1.z - xb[6]) * sx, (p1.w - xb[7]) * sx, hi.w, lo.w);
 				}
-				*reinterpret_cast<uint4 *>(gen + S_AHI + g_sw128(j, 8 * q)) = *reinterpret_cast<const uint4 *>(hi);
-				*reinterpret_cast<uint4 *>(gen + S_ALO + g_sw128(j, 8 * q)) = *reinterpret_cast<const uint4 *>(lo);
+				*reinterpret_cast<uint4 *>(gen + S_AHI + g_sw128(j, 8 * q)) = hi;
+				*reinterpret_cast<uint4 *>(gen + S_ALO + g_sw128(j, 8 * q)) = lo;
 			}
 			unsigned occ = 0u;
 #pragma unroll
