@@ -29,6 +29,7 @@
 
 npb_status npb_launch_a2_tile(npb_chains *ch, const A2Args &a); // npb_alg2_tile.cu
 npb_status npb_launch_a2_tc(npb_chains *ch, const A2Args &a);   // npb_alg2_tc.cu
+npb_status npb_launch_a2_tc16(npb_chains *ch, const A2Args &a); // npb_alg2_tc16.cu
 
 template <int D, int LPS, bool PREG>
 __global__ void __launch_bounds__(32 * LPS) k_a2_sweep(const A2Args a) {
@@ -543,7 +544,7 @@ npb_status npb_launch_alg2_conjugate(npb_chains *ch, int n_sweeps) {
 		case 4: k_a2_sweep<4, 1, true><<<C, 32, 0, ctx->stream>>>(a); break;
 		case 8: k_a2_sweep<8, 1, true><<<C, 32, 0, ctx->stream>>>(a); break;
 		case 16:
-			if (ch->sw.a2_tile > 0) { s = npb_launch_a2_tile(ch, a); if (s != NPB_OK) return s; }
+			if (ch->sw.a2_tile > 0) { s = ch->sw.a2_tc16 ? npb_launch_a2_tc16(ch, a) : npb_launch_a2_tile(ch, a); if (s != NPB_OK) return s; }
 			else k_a2_sweep<16, 2, true><<<C, 64, 0, ctx->stream>>>(a);
 			break;
 		case 64:

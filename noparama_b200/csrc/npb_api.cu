@@ -393,10 +393,10 @@ npb_status npb_chains_create(npb_ctx *ctx, npb_dataset *ds, int64_t n_chains, in
 		const char *e = getenv("NPB_D16_PATH");
 		strncpy(ch->opt_d16_path, e && e[0] ? e : "auto", sizeof(ch->opt_d16_path) - 1);
 		static const char *const names[] = {"NPB_D64_SPEC", "NPB_F16_FLAGS", "NPB_D16_BLOCK", "NPB_D64_BLOCK", "NPB_D16_EPI", "NPB_D16_NH",
-				"NPB_D16_AUX", "NPB_D64_OVERLAP", "NPB_D64_DENSITY", "NPB_TILE_KERNEL", "NPB_A2_TILE", "NPB_A2_TC"};
+				"NPB_D16_AUX", "NPB_D64_OVERLAP", "NPB_D64_DENSITY", "NPB_TILE_KERNEL", "NPB_A2_TILE", "NPB_A2_TC", "NPB_A2_TC16"};
 		static const char *const opts[] = {"spec", "f16_flags", "d16_block", "d64_block", "d16_epi", "d16_nh", "d16_aux", "d64_overlap",
-				"d64_density", "tile_kernel", "a2_tile", "a2_tc"};
-		for (int i = 0; i < 12; ++i)
+				"d64_density", "tile_kernel", "a2_tile", "a2_tc", "a2_tc16"};
+		for (int i = 0; i < 13; ++i)
 			if ((e = getenv(names[i])) && e[0] && set_switch(ch, opts[i], e) != NPB_OK) {
 				npb_chains_destroy(ch);
 				return npb_fail(ctx, NPB_E_BAD_ARG, "bad value in an NPB_* environment switch");
@@ -441,6 +441,7 @@ static npb_status set_switch(npb_chains *ch, const char *name, const char *value
 	else if (!strcmp(name, "tile_kernel")) w.two_warp = value[0] == '2';
 	else if (!strcmp(name, "a2_tile")) { if (v < 0 || v > 128) return NPB_E_BAD_ARG; w.a2_tile = v; }
 	else if (!strcmp(name, "a2_tc")) w.a2_tc = value[0] != '0';
+	else if (!strcmp(name, "a2_tc16")) w.a2_tc16 = value[0] != '0';
 	else return NPB_E_BAD_ARG;
 	return NPB_OK;
 }

@@ -37,6 +37,7 @@ struct npb_ctx {
 	int n_sm = 0;               // multiprocessors of this context's device (grid size of the persistent kernels)
 	bool a2_tile_attr_set = false; // the same for k_a2_tile (npb_alg2_tile.cu)
 	bool a2_tc_attr_set = false;   // and for k_a2_tc (npb_alg2_tc.cu)
+	bool a2_tc16_attr_set = false; // and for k_a2_tc16 (npb_alg2_tc16.cu)
 	bool fused_attr_set = false; // per device: the shared-memory opt-in of k_sweep_tc16 has been made on this context's device
 	PriorHost prior;
 	float *d_CT2 = nullptr, *d_S = nullptr; // device copies of the packed prior factors
@@ -84,6 +85,7 @@ struct npb_chains {
 		bool two_warp = false;    // NPB_TILE_KERNEL=2warp: round-1 one-chain-per-CTA kernel
 		int a2_tile = 128;        // NPB_A2_TILE: conjugate Algorithm 2 at D = 16, 64: steps evaluated ahead of the chain (1 .. 128, same results; k_a2_tile takes at most 64); 0 = the step-at-a-time kernel k_a2_sweep
 		bool a2_tc = true;        // NPB_A2_TC=0 -> false: D = 64 on the FP32 tile kernel k_a2_tile instead of the tcgen05 kernel k_a2_tc
+		bool a2_tc16 = false;     // NPB_A2_TC16=1 -> true: D = 16 on the tcgen05 kernel k_a2_tc16 instead of the FP32 tile kernel k_a2_tile
 	} sw;
 	double moved_frac_last = -1.0; // moved / reassignments of the last Algorithm 8 launch whose statistics were read; -1 unknown
 	bool time_kernels = false;  // option "time_kernels": CUDA events around every launch of the dominant sweep kernel

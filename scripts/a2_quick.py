@@ -21,6 +21,7 @@ for name, D, N, chains, K in [sh for sh in shapes if sh[0] in os.environ.get("A2
         ch = npb.Chains(ctx, ds, chains, Kmax=32, K0=K, seed=1234)
         ch.set_option("a2_tile", str(tile))
         ch.set_option("a2_tc", os.environ.get("A2_TC", "1"))
+        ch.set_option("a2_tc16", os.environ.get("A2_TC16", "0"))
         if os.environ.get("A2_TRUTH"):
             ch.set_state(0, y.astype(np.int32), np.arange(K, dtype=np.int32), *given(X, y))
             ch.broadcast_state(0)

@@ -123,7 +123,7 @@ def test_distribution_against_oracle(npb, ctx, oracle, which, T, seeds):
     ds.close()
 
 
-@pytest.mark.parametrize("D,N,K0,tc", [(16, 900, 10, 1), (64, 500, 8, 1), (64, 500, 8, 0)])
+@pytest.mark.parametrize("D,N,K0,tc", [(16, 900, 10, 0), (16, 900, 10, 1), (64, 500, 8, 1), (64, 500, 8, 0)])
 def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0, tc):
     """k_a2_tile (npb_alg2_tile.cu) evaluates up to 64 steps ahead of the chain and corrects the two changed columns after every
     move: the assignments, counts and FP64 statistics must equal those of the strictly sequential schedule (a2_tile = 1) bit for
@@ -136,6 +136,7 @@ def test_tile_length_does_not_change_the_chain(npb, ctx, D, N, K0, tc):
         ch = npb.Chains(ctx, ds, 7, Kmax=32, K0=K0, seed=21)
         ch.set_option("a2_tile", str(tile))
         ch.set_option("a2_tc", str(tc))  # D = 64: the tcgen05 kernel k_a2_tc (tiles of up to 128 steps) or the FP32 tile kernel (up to 64)
+        ch.set_option("a2_tc16", str(tc))  # D = 16: k_a2_tc16 or the FP32 tile kernel
         moved = births = 0
         zs = []
         for _ in range(3):
@@ -177,7 +178,7 @@ def test_step_at_a_time_kernel_still_follows_the_moves(npb, ctx, D, N):
     ds.close()
 
 
-@pytest.mark.parametrize("D,N,tc", [(16, 800, 1), (64, 500, 1), (64, 500, 0)])
+@pytest.mark.parametrize("D,N,tc", [(16, 800, 0), (16, 800, 1), (64, 500, 1), (64, 500, 0)])
 def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N, tc):
     """k_a2_tile's quadratic forms (register-blocked products) against k_a2_sweep's row dots: the two
     kernels draw the same race noise, so from the same state one sweep must make the same decisions except where two keys lie within
@@ -193,6 +194,7 @@ def test_tile_kernel_decides_like_the_step_at_a_time_kernel(npb, ctx, D, N, tc):
         ch = npb.Chains(ctx, ds, 6, Kmax=32, K0=6, seed=31)
         ch.set_option("a2_tile", str(tile))
         ch.set_option("a2_tc", str(tc))
+        ch.set_option("a2_tc16", str(tc))
         for c in range(6):
             slots = np.unique(zs[c]).astype(np.int32)
             ch.set_state(c, zs[c], slots, np.zeros((len(slots), D)), np.tile(np.eye(D), (len(slots), 1, 1)))
