@@ -152,6 +152,12 @@ void NealAlgorithm2::sweep(membertrix &cluster_matrix, int n_sweeps) {
 	record(st);
 	cluster_matrix.invalidate();
 }
+void NealAlgorithm2Conjugate::sweep(membertrix &cluster_matrix, int n_sweeps) {
+	npb_sweep_stats st{};
+	dev().check(npb_chains_sweep(cluster_matrix.chains, NPB_ALG2_CONJUGATE, n_sweeps, &st));
+	record(st);
+	cluster_matrix.invalidate();
+}
 void NealAlgorithm8::update(membertrix &cluster_matrix, const data_ids_t &data_ids) {
 	assert(data_ids.size() == 1); // np_neal_algorithm8.cpp:54
 	if (calls_++ % cluster_matrix.size() == 0) sweep(cluster_matrix, 1);

@@ -187,6 +187,15 @@ public:
 	void sweep(membertrix &cluster_matrix, int n_sweeps) override;
 };
 
+// The CONJUGATE Algorithm 2 the reference meant (np_neal_algorithm2.cpp:32-120 with updateSuffies; never completed there): collapsed
+// Gibbs with the NIW posterior predictive, sufficient statistics up- and down-dated per move (NPB_ALG2_CONJUGATE; Kmax = 32).
+class NealAlgorithm2Conjugate : public NealAlgorithm8 {
+public:
+	NealAlgorithm2Conjugate(device &dev, dirichlet_process &nonparametrics) : NealAlgorithm8(dev, nonparametrics) {}
+	int sampler() const override { return NPB_ALG2_CONJUGATE; }
+	void sweep(membertrix &cluster_matrix, int n_sweeps) override;
+};
+
 // The split-merge samplers (include/np_jain_neal_algorithm.h:75-79, include/np_triadic_algorithm.h:73-77).  update()
 // keeps MCMC::run's per-subset calling convention (np_mcmc.cpp:146-163): subsets of 2 / 3 items, asserted like the
 // reference (np_jain_neal_algorithm.cpp:429, np_triadic_algorithm.cpp:647); the first call of a sweep runs the whole

@@ -26,7 +26,7 @@
 using namespace npb;
 
 static void usage() {
-	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|algorithm2|jain_neal_split|triadic -T sweeps -c clustering|regression|angular [--chains C] [--gpus G] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR] [--selftest-membertrix]\n";
+	std::cout << "usage: noparama_b200 -d datafile -a algorithm8|algorithm2|algorithm2_conjugate|jain_neal_split|triadic -T sweeps -c clustering|regression|angular [--chains C] [--gpus G] [--seed S] [--kmax K] [--seam] [--fix-q1] [--output DIR] [--selftest-membertrix]\n";
 }
 
 // test/test_membertrix.cpp (the reference's unit test of the state class) through the host mutators over the DEVICE state:
@@ -117,11 +117,16 @@ int main(int argc, char **argv) {
 	if (datafile.empty()) { usage(); return 1; }
 	if (config != "clustering" && config != "regression" && config != "angular") { std::cerr << "Unknown likelihood" << std::endl; return 107; } // np_main.cpp:196-205, exit code :349
 	const representation_mode_t mode = config == "regression" ? regression_mode : (config == "angular" ? angular_mode : clustering_mode);
+	if (algorithm == "algorithm2_conjugate" && kmax != 32) {
+		std::cout << "algorithm2_conjugate keeps 32 cluster slots per chain: --kmax 32" << std::endl;
+		kmax = 32;
+	}
 	if (mode != clustering_mode && algorithm != "algorithm8") {
 		std::cerr << "-c " << config << " runs Algorithm 8 on the device (the split-merge samplers are multivariate-normal only)" << std::endl;
 		return 1;
 	}
-	if (algorithm != "algorithm8" && algorithm != "algorithm2" && algorithm != "jain_neal_split" && algorithm != "triadic") { // np_main.cpp:222-238
+	if (algorithm != "algorithm8" && algorithm != "algorithm2" && algorithm != "algorithm2_conjugate" && algorithm != "jain_neal_split" &&
+			algorithm != "triadic") { // np_main.cpp:222-238
 		std::cerr << "Unknown algorithm: " << algorithm << std::endl;
 		return 1;
 	}
@@ -167,7 +172,9 @@ int main(int argc, char **argv) {
 			JainNealAlgorithm jain_neal(dev, hyper);
 			TriadicAlgorithm triadic(dev, hyper);
 			NealAlgorithm2 alg2(dev, hyper); // np_main.cpp:222-227,425-431 (commented out in the reference)
+			NealAlgorithm2Conjugate alg2c(dev, hyper); // the collapsed form np_neal_algorithm2.cpp:32-120 describes
 			UpdateClusterPopulation &sampler = algorithm == "algorithm8" ? (UpdateClusterPopulation &)alg8
+					: algorithm == "algorithm2_conjugate" ? (UpdateClusterPopulation &)alg2c
 					: (algorithm == "algorithm2" ? (UpdateClusterPopulation &)alg2
 					: (algorithm == "jain_neal_split" ? (UpdateClusterPopulation &)jain_neal : (UpdateClusterPopulation &)triadic));
 			MCMC mcmc(dev, hyper, sampler, chains, kmax, 20, algorithm == "algorithm2" ? 1 : 3, seed);

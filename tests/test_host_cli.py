@@ -83,6 +83,19 @@ def test_cli_runs_algorithm2(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_runs_conjugate_algorithm2(tmp_path):
+    """-a algorithm2_conjugate: the collapsed sampler np_neal_algorithm2.cpp:32-120 describes, through the C++ host classes"""
+    ensure_built()
+    data = tmp_path / "twogaussians.data"
+    write_data(str(data))
+    r = subprocess.run([CLI, "-d", str(data), "-a", "algorithm2_conjugate", "-T", "100", "-c", "clustering", "--chains", "32", "--kmax", "64",
+                        "--seed", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "--kmax 32" in r.stdout
+    assert float(re.search(r"chains: purity ([0-9.]+)", r.stdout).group(1)) > 0.9
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("algorithm", ["jain_neal_split", "triadic"])
 def test_cli_runs_split_merge(tmp_path, algorithm):
     ensure_built()
