@@ -610,6 +610,13 @@ class NealAlgorithm2:
     subset_count = 1
 
 
+class NealAlgorithm2Conjugate:
+    """The CONJUGATE form of the same file's intent (updateSuffies, np_neal_algorithm2.cpp:54): collapsed Gibbs with the NIW posterior
+    predictive (npb_alg2*.cu).  Kmax = 32; the prior needs nu > D - 1."""
+    sampler = ALG2_CONJUGATE
+    subset_count = 1
+
+
 class JainNealAlgorithm:
     """UpdateClusterPopulation implementation selected by `-a jain_neal_split` (np_main.cpp:440-446)."""
     sampler = JAIN_NEAL
