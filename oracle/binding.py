@@ -35,6 +35,8 @@ class Stats(C.Structure):
 
 
 def build(force=False):
+    if os.environ.get("NP_ORACLE_LIB"):  # e.g. the sanitizer build (make -C oracle sanitize; scripts/oracle_sanitize.sh)
+        return os.environ["NP_ORACLE_LIB"]
     so = os.path.join(_HERE, "libnp_oracle.so")
     src = [os.path.join(_HERE, f) for f in ("np_oracle.cpp", "np_oracle.h", "np_oracle_sm.inc", "np_oracle_alg2.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src if os.path.exists(s)):

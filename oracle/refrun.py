@@ -71,6 +71,8 @@ def run(X, prior, algorithm=8, T=1000, seed_main=1, seed_shuffle=2, record=False
     with tempfile.TemporaryDirectory() as d:
         req, res = os.path.join(d, "req.bin"), os.path.join(d, "res.bin")
         write_request(req, X, prior)
+        # (the reference's binary is not instrumented: a sanitizer runtime preloaded for the oracle, scripts/oracle_sanitize.sh, stays out of it)
+        env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
         subprocess.run(command(algorithm, T, seed_main, seed_shuffle, req, res, record, family), check=True,
-                       stdout=subprocess.DEVNULL, timeout=timeout)
+                       stdout=subprocess.DEVNULL, timeout=timeout, env=env)
         return read_result(res)
